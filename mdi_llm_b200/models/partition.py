@@ -1,0 +1,215 @@
+"""Layer partitioning of a litGPT model over pipeline stages and chunk files.
+
+Parity: reference partition table ``N_LAYERS_NODES`` (``src/sub/config.py:56-98``),
+``split_parameters`` (``src/sub/utils/utils.py:241-385``) and ``split_and_store``
+(``utils.py:388-438``): the starter owns ``wte`` + the first blocks + ``ln_f`` + ``lm_head``;
+secondary ``i`` owns the next contiguous blocks, re-indexed from 0; files are written to
+``<ckpt>/chunks/<N>nodes/model_starter.pth`` and ``model_secondary{i}.pth``.
+
+New: the reference raises ``KeyError`` for any topology missing from its table (e.g. 8 nodes).
+Here :func:`plan_layers` falls back to a *balanced planner* that accounts for the bytes the
+starter additionally streams per token for ``ln_f`` + ``lm_head`` (≈2.4 Llama-3 blocks) and
+may give secondaries different layer counts — per-stage layer lists that the reference
+cannot express.  For topologies the reference supports the table wins, so chunk files are
+interchangeable.
+"""
+from __future__ import annotations
+
+import gc
+import os
+import warnings
+from pathlib import Path
+from typing import Any, Dict, List, Optional, Sequence, Tuple, Union
+
+import torch
+
+from .config import Config
+
+__all__ = [
+    "N_LAYERS_NODES", "plan_layers", "balanced_plan", "layer_ranges", "split_parameters",
+    "split_and_store", "merge_chunks", "count_transformer_blocks", "chunk_dir", "chunk_file",
+]
+
+# n_nodes -> n_layer -> (starter layers, layers per secondary).  Data of config.py:56-98.
+_TABLE = {
+    1: {n: (n, 0) for n in (5, 7, 9, 12, 22, 24, 32, 36, 48)},
+    2: {5: (2, 3), 7: (3, 4), 9: (4, 5), 12: (5, 7), 22: (10, 12), 24: (10, 14), 32: (14, 18),
+        36: (16, 20), 48: (22, 26)},
+    3: {5: (1, 2), 7: (1, 3), 9: (1, 4), 12: (2, 5), 22: (6, 8), 24: (4, 10), 32: (8, 12),
+        36: (10, 13), 48: (14, 17)},
+    4: {22: (4, 6), 32: (5, 9)},
+    5: {22: (2, 5), 32: (4, 7)},
+}
+N_LAYERS_NODES: Dict[int, Dict[int, Dict[str, int]]] = {
+    n: {
+        L: ({"N_LAYERS_START": s} if n == 1 else {"N_LAYERS_START": s, "N_LAYERS_SECONDARY": r})
+        for L, (s, r) in per.items()
+    }
+    for n, per in _TABLE.items()
+}
+
+
+def balanced_plan(n_nodes: int, n_layer: int, head_cost_blocks: float = 0.0) -> List[int]:
+    """Layers per stage ``[starter, sec0, ...]`` minimising the slowest stage when the starter
+    carries an extra ``head_cost_blocks`` blocks-worth of work (``ln_f``+``lm_head``+sampling).
+
+    Every stage gets at least one block.  Ties are broken towards the *later* stages being
+    lighter, so the wrap-around hop finds the starter ready.
+    """
+    if n_nodes < 1:
+        raise ValueError("n_nodes must be >= 1")
+    if n_nodes == 1:
+        return [n_layer]
+    if n_layer < n_nodes:
+        raise ValueError(f"cannot split {n_layer} layers over {n_nodes} nodes")
+    best: Optional[List[int]] = None
+    best_cost = float("inf")
+    for s in range(1, n_layer - (n_nodes - 1) + 1):
+        rest = n_layer - s
+        q, r = divmod(rest, n_nodes - 1)
+        if q == 0:
+            continue
+        secs = [q + 1] * r + [q] * (n_nodes - 1 - r)
+        cost = max(s + head_cost_blocks, max(secs))
+        # prefer lower bottleneck, then a heavier starter (fewer hops of imbalance downstream)
+        if cost < best_cost - 1e-9 or (abs(cost - best_cost) <= 1e-9 and best is not None and s > best[0]):
+            best, best_cost = [s] + secs, cost
+    assert best is not None
+    return best
+
+
+def plan_layers(
+    n_nodes: int,
+    n_layer: int,
+    config: Optional[Config] = None,
+    policy: str = "auto",
+) -> List[int]:
+    """Layers per stage.  ``policy``: ``"table"`` (reference table only, ``KeyError`` when
+    missing), ``"balanced"`` (planner only) or ``"auto"`` (table if present else planner)."""
+    if policy not in ("auto", "table", "balanced"):
+        raise ValueError(f"unknown partition policy {policy!r}")
+    if policy in ("auto", "table"):
+        entry = N_LAYERS_NODES.get(n_nodes, {}).get(n_layer)
+        if entry is not None:
+            s = entry["N_LAYERS_START"]
+            return [s] + [entry.get("N_LAYERS_SECONDARY", 0)] * (n_nodes - 1)
+        if policy == "table":
+            raise KeyError(f"no reference partition for {n_nodes} nodes x {n_layer} layers")
+    head = 0.0
+    if config is not None:
+        head = config.head_param_count() / max(1, config.block_param_count())
+    return balanced_plan(n_nodes, n_layer, head)
+
+
+def layer_ranges(plan: Sequence[int]) -> List[Tuple[int, int]]:
+    out, start = [], 0
+    for n in plan:
+        out.append((start, start + n))
+        start += n
+    return out
+
+
+def count_transformer_blocks(state_dict: Dict[str, Any], base_name_transformer: str = "transformer") -> int:
+    """Number of distinct ``transformer.h.<i>`` blocks in a state dict (utils.py:470-492)."""
+    prefix = f"{base_name_transformer}.h."
+    return len({k[len(prefix):].split(".", 1)[0] for k in state_dict if k.startswith(prefix)})
+
+
+def split_parameters(
+    model_params: Dict[str, Any],
+    n_nodes: int,
+    plan: Optional[Sequence[int]] = None,
+    config: Optional[Config] = None,
+) -> Tuple[Dict[str, Any], Dict[str, Any]]:
+    """Pop the entries of a full litGPT state dict into per-node chunks.
+
+    Returns ``({"starter": sd, "secondary": [sd, ...]}, layers_info)`` where ``layers_info`` has
+    the reference's ``N_LAYERS_START`` / ``N_LAYERS_SECONDARY`` keys (the latter is the first
+    secondary's count) plus ``"plan"`` with the full per-stage list.  ``model_params`` is
+    consumed: whatever is left afterwards was not assigned (the caller warns, utils.py:411-412).
+    """
+    if n_nodes < 2:
+        raise ValueError("There must be at least 2 nodes in the network")
+    n_layer = count_transformer_blocks(model_params)
+    plan = list(plan) if plan is not None else plan_layers(n_nodes, n_layer, config)
+    if len(plan) != n_nodes or sum(plan) != n_layer:
+        raise ValueError(f"plan {plan} does not cover {n_layer} layers over {n_nodes} nodes")
+
+    by_layer: Dict[int, List[str]] = {}
+    for k in model_params:
+        if k.startswith("transformer.h."):
+            by_layer.setdefault(int(k.split(".")[2]), []).append(k)
+
+    def take_layers(lo: int, hi: int) -> Dict[str, Any]:
+        out: Dict[str, Any] = {}
+        for li in range(lo, hi):
+            for k in by_layer.get(li, ()):
+                tail = k.split(".", 3)[3]
+                out[f"transformer.h.{li - lo}.{tail}"] = model_params.pop(k)
+        return out
+
+    ranges = layer_ranges(plan)
+    starter: Dict[str, Any] = {}
+    for k in ("transformer.wte.weight", "transformer.wte.bias", "transformer.wpe.weight"):
+        if k in model_params:
+            starter[k] = model_params.pop(k)
+    starter.update(take_layers(*ranges[0]))
+    for k in ("transformer.ln_f.weight", "transformer.ln_f.bias", "lm_head.weight", "lm_head.bias"):
+        if k in model_params:
+            starter[k] = model_params.pop(k)
+    secondary = [take_layers(lo, hi) for lo, hi in ranges[1:]]
+    info = {"N_LAYERS_START": plan[0], "N_LAYERS_SECONDARY": plan[1], "plan": list(plan)}
+    return {"starter": starter, "secondary": secondary}, info
+
+
+def chunk_dir(ckpt_dir: Union[str, Path], n_nodes: int) -> Path:
+    return Path(ckpt_dir) / "chunks" / f"{n_nodes}nodes"
+
+
+def chunk_file(ckpt_dir: Union[str, Path], n_nodes: int, role: str) -> Path:
+    """``role`` = "starter" or "secondary:<i>"."""
+    d = chunk_dir(ckpt_dir, n_nodes)
+    if role.startswith("starter"):
+        return d / "model_starter.pth"
+    return d / f"model_secondary{int(role.split(':')[1])}.pth"
+
+
+def split_and_store(
+    model_params: Dict[str, Any],
+    n_nodes: int,
+    ckpt_dir: Union[str, Path],
+    plan: Optional[Sequence[int]] = None,
+    config: Optional[Config] = None,
+    **kwargs: Any,
+) -> Path:
+    """Split a state dict and write the chunk files; returns the chunk directory."""
+    verb = bool(kwargs.get("verb", False))
+    chunks, info = split_parameters(model_params, n_nodes, plan=plan, config=config)
+    if len(model_params):
+        warnings.warn(f"{len(model_params)} elements have not been used")
+    del model_params
+    gc.collect()
+    if verb:
+        print(f"Using the following split: starter {info['plan'][0]} layers, secondaries {info['plan'][1:]}")
+    out = chunk_dir(ckpt_dir, n_nodes)
+    os.makedirs(out, exist_ok=True)
+    torch.save(chunks["starter"], out / "model_starter.pth")
+    for i, sd in enumerate(chunks["secondary"]):
+        torch.save(sd, out / f"model_secondary{i}.pth")
+    return out
+
+
+def merge_chunks(starter: Dict[str, Any], secondary: Sequence[Dict[str, Any]]) -> Dict[str, Any]:
+    """Inverse of :func:`split_parameters` (used by tests: split ∘ merge = identity)."""
+    full: Dict[str, Any] = {}
+    n0 = count_transformer_blocks(starter)
+    for k, v in starter.items():
+        full[k] = v
+    base = n0
+    for sd in secondary:
+        n = count_transformer_blocks(sd)
+        for k, v in sd.items():
+            parts = k.split(".", 3)
+            full[f"transformer.h.{int(parts[2]) + base}.{parts[3]}"] = v
+        base += n
+    return full

@@ -1,0 +1,157 @@
+"""Pipeline-stage modules: the local slice of the model that one node (GPU) owns.
+
+Parity: reference ``src/sub/submodels.py`` — ``StarterNode`` (:132-220: ``wte`` + first
+blocks **and** ``ln_f`` + ``lm_head``; ``forward(first_pass=True)`` runs embedding+blocks,
+``first_pass=False`` runs the output head) and ``SecondaryNode`` (:223-282: blocks only).
+State-dict keys match the chunk files ``model_starter.pth`` / ``model_secondary{i}.pth``
+(locally re-indexed ``transformer.h.{0..n-1}``).
+
+These eager modules are what runs on CPU, what the GPU tests use as oracle, and what holds
+the weights that the CUDA stage executor (``parallel/engine.py``) reads in place.
+Each stage owns a :class:`KVPool` with one slot per in-flight sample; the per-sample cache
+"rotation" of the reference (gptserver.py:975-978) becomes passing ``slot=``.
+"""
+from __future__ import annotations
+
+from typing import Any, Dict, Optional
+
+import torch
+import torch.nn as nn
+
+from .config import Config
+from .gpt import Block, KVPool, RopeMixin, build_norm, run_blocks
+
+__all__ = ["StageModule", "StarterNode", "SecondaryNode", "build_stage"]
+
+
+class StageModule(nn.Module, RopeMixin):
+    """Common behaviour of a pipeline stage (reference ``NodePrototype``, submodels.py:34-127)."""
+
+    role = "stage"
+
+    def __init__(self, config: Config, n_transf_layers: int, **kwargs: Any) -> None:
+        super().__init__()
+        self.config = config
+        self.n_local_layers = int(n_transf_layers)
+        self.verb = bool(kwargs.get("verb", False))
+        self.params_init = False
+        self.kv_pool: Optional[KVPool] = None
+        self.transformer = nn.ModuleDict()
+
+    # -- cache management --------------------------------------------------------------------
+    def set_kv_cache(
+        self,
+        n_slots: int,
+        device: Optional[torch.device] = None,
+        dtype: Optional[torch.dtype] = None,
+    ) -> KVPool:
+        p = next(self.parameters())
+        self.kv_pool = KVPool(
+            self.config, self.n_local_layers, n_slots, self.max_seq_length,
+            device=device or p.device, dtype=dtype or p.dtype,
+        )
+        return self.kv_pool
+
+    def ensure_slots(self, n_slots: int) -> KVPool:
+        """Grow the pool lazily — secondaries learn about samples as they arrive
+        (gptserver.py:1083-1088)."""
+        if self.kv_pool is None:
+            return self.set_kv_cache(n_slots)
+        if self.kv_pool.n_slots < n_slots:
+            old = self.kv_pool
+            new = self.set_kv_cache(n_slots, device=old.data.device, dtype=old.data.dtype)
+            new.data[:, : old.n_slots].copy_(old.data)
+        return self.kv_pool
+
+    def clear_kv_cache(self) -> None:
+        self.kv_pool = None
+
+    def load_weights(self, params: Dict[str, Any], **kwargs: Any) -> int:
+        """Fill this (possibly meta) module from a chunk state dict (submodels.py:161-168)."""
+        from ..utils.checkpoint import init_from_state_dict
+
+        init_from_state_dict(self, params)
+        self.params_init = True
+        return 1
+
+    def _blocks(self, x: torch.Tensor, input_pos: Optional[torch.Tensor], slot: int) -> torch.Tensor:
+        T = x.size(1)
+        if self.max_seq_length < T:
+            raise ValueError(f"Cannot forward sequence of length {T}, max seq length is only {self.max_seq_length}.")
+        if input_pos is not None and self.kv_pool is None:
+            raise TypeError("You need to call `set_kv_cache()`")
+        cos, sin = self.rope_for(T, input_pos)
+        return run_blocks(self.transformer.h, x, cos, sin, input_pos,
+                          self.kv_pool if input_pos is not None else None, slot)
+
+
+class StarterNode(StageModule):
+    role = "starter"
+
+    def __init__(self, config: Config, n_transf_layers: int, **kwargs: Any) -> None:
+        super().__init__(config, n_transf_layers, **kwargs)
+        parts = dict(
+            wte=nn.Embedding(config.padded_vocab_size, config.n_embd),
+            h=nn.ModuleList(Block(config) for _ in range(n_transf_layers)),
+            ln_f=build_norm(config),
+        )
+        if config.pos_embedding == "learned":
+            parts["wpe"] = nn.Embedding(config.block_size, config.n_embd)
+        self.transformer = nn.ModuleDict(parts)
+        self.lm_head = nn.Linear(config.n_embd, config.padded_vocab_size, bias=config.lm_head_bias)
+        if config.tie_embeddings:
+            self.lm_head.weight = self.transformer.wte.weight
+        self.max_seq_length = config.block_size
+
+    def embed(self, idx: torch.Tensor, input_pos: Optional[torch.Tensor]) -> torch.Tensor:
+        x = self.transformer.wte(idx)
+        if self.config.scale_embeddings:
+            x = x * (self.config.n_embd ** 0.5)
+        if "wpe" in self.transformer:
+            pos = input_pos if input_pos is not None else torch.arange(idx.size(1), device=idx.device)
+            x = x + self.transformer.wpe(pos)
+        return x
+
+    def head(self, x: torch.Tensor) -> torch.Tensor:
+        """``ln_f`` + ``lm_head``; only the last row is needed for sampling, so callers may pass
+        ``x[:, -1:]`` (the reference computes all T rows, submodels.py:219-220)."""
+        return self.lm_head(self.transformer.ln_f(x))
+
+    def forward(
+        self,
+        idx: torch.Tensor,
+        input_pos: Optional[torch.Tensor] = None,
+        *,
+        first_pass: bool = True,
+        slot: int = 0,
+    ) -> torch.Tensor:
+        if not first_pass:
+            return self.head(idx)
+        B, T = idx.shape
+        if T > self.config.block_size:
+            raise ValueError(f"Cannot forward sequence of length {T}, block size is {self.config.block_size}")
+        if B > 1 and input_pos is not None:
+            raise NotImplementedError("one sample per message (B=1) on the cached path")
+        return self._blocks(self.embed(idx, input_pos), input_pos, slot)
+
+
+class SecondaryNode(StageModule):
+    role = "secondary"
+
+    def __init__(self, config: Config, n_transf_layers: int, **kwargs: Any) -> None:
+        super().__init__(config, n_transf_layers, **kwargs)
+        self.transformer = nn.ModuleDict(dict(h=nn.ModuleList(Block(config) for _ in range(n_transf_layers))))
+        self.max_seq_length = config.block_size
+
+    def forward(self, x: torch.Tensor, input_pos: Optional[torch.Tensor] = None, *, slot: int = 0) -> torch.Tensor:
+        return self._blocks(x, input_pos, slot)
+
+
+def build_stage(config: Config, role: str, n_layers: int, *, meta: bool = False, **kw: Any) -> StageModule:
+    """Instantiate the stage for ``role`` ("starter" | "secondary[:i]"), optionally on the
+    meta device so that loading a chunk does not double the memory (gptserver.py:657-664)."""
+    cls = StarterNode if role.startswith("starter") else SecondaryNode
+    if meta:
+        with torch.device("meta"):
+            return cls(config, n_layers, **kw)
+    return cls(config, n_layers, **kw)
