@@ -162,10 +162,11 @@ class KVPool:
         return blk[0], blk[1]
 
     def reset(self, slot: Optional[int] = None) -> None:
-        if slot is None:
-            self.data.zero_()
-        else:
-            self.data[:, slot].zero_()
+        with torch.inference_mode():  # the pool may have been created inside inference mode
+            if slot is None:
+                self.data.zero_()
+            else:
+                self.data[:, slot].zero_()
 
     @property
     def nbytes(self) -> int:

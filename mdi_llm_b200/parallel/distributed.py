@@ -1,0 +1,225 @@
+"""Orchestration API: ``GPTDistributed`` — what ``starter.py`` / ``secondary.py`` instantiate.
+
+Parity: reference ``src/sub/model_dist.py`` ``GPTDistributed`` — constructor signature and
+path resolution (:136-339: checkpoint dir, ``chunks/<N>nodes/`` lookup, on-the-fly split when
+the chunks are absent, ``--chunk`` override, truncated ``model_seq_length``), ``start``
+(:341-397), ``configure_nodes`` (:402-484: one ``POST /init`` per secondary with role,
+prev/next node, model config, ``n_nodes``, ``n_local_layers``, ``n_samples``, ``max_seq_length``
+and optionally the chunk itself), ``stop_nodes`` (:486-497), ``_request_to_node`` (:499-573).
+
+Differences: ``n_local_layers`` is per secondary (non-uniform plans for topologies the reference
+table lacks, e.g. 8 stages); ``start`` does not crash when plotting is off (the reference
+indexes an empty ``time_gen``, model_dist.py:383, and then never stops its secondaries).
+"""
+from __future__ import annotations
+
+import json
+import warnings
+from pathlib import Path
+from typing import Any, Dict, List, Optional, Sequence, Tuple, Union
+
+import torch
+
+from ..models.config import Config
+from ..models.partition import chunk_dir, count_transformer_blocks, plan_layers, split_and_store
+from ..utils.checkpoint import lazy_load, load_from_pt
+from .control import request_to_node
+from .server import GPTServer
+
+FileType = Union[str, Path]
+__all__ = ["GPTDistributed"]
+
+
+class GPTDistributed:
+    init_msg: Dict[str, Any] = {
+        "role": "", "prev_node": {}, "next_node": {}, "model_config": {}, "n_nodes": 0,
+        "n_samples": 0, "max_seq_length": None,
+    }
+
+    def __init__(
+        self,
+        node_type: str,
+        config_file: Union[FileType, Dict[str, Any]],
+        *,
+        ckpt_dir: Optional[FileType] = None,
+        chunk_path: Optional[FileType] = None,
+        device: Optional[str] = None,
+        dtype: Optional[str] = None,
+        secondary_index: Optional[int] = None,
+        model_seq_length: Optional[int] = None,
+        **kwargs: Any,
+    ) -> None:
+        self.ckpt_dir = Path(ckpt_dir) if ckpt_dir is not None else None
+        self.chunk_path = Path(chunk_path) if chunk_path is not None else None
+        self.torch_device = device if device else None
+        self.verb = bool(kwargs.get("verb", False))
+        self.plots = bool(kwargs.get("plots", False))
+        self.dtype = dtype
+        self.partition_policy = kwargs.pop("partition", "auto")
+        self.push_chunks = bool(kwargs.pop("push_chunks", False))
+        self.full_model_name = self.ckpt_dir.name if self.ckpt_dir else None
+        self.node_type = node_type
+        if isinstance(config_file, dict):
+            self.node_config = config_file
+        else:
+            with open(config_file, "r") as f:
+                self.node_config = json.load(f)
+        self.model_config: Optional[Config] = None
+        self.model_seq_length: Optional[int] = None
+        self.plan: Optional[List[int]] = None
+
+        if self.node_type == "starter":
+            assert self.ckpt_dir, "No model was specified!"
+            self.n_secondary = len(self.node_config["nodes"].get("secondary", []))
+            self.n_nodes = 1 + self.n_secondary
+            self.own_config = self.node_config["nodes"]["starter"]
+            if self.chunk_path:
+                node_chunks_dir = self.chunk_path.resolve().parent
+                self.model_was_split = True
+            else:
+                node_chunks_dir = chunk_dir(self.ckpt_dir, self.n_nodes)
+                self.model_was_split = node_chunks_dir.is_dir() and (node_chunks_dir / "model_starter.pth").is_file()
+            if not self.model_was_split and self.n_nodes > 1:
+                if self.verb:
+                    print("Chunks not found! Splitting the model")
+                self.model_config, full_model = load_from_pt(self.ckpt_dir)
+                assert full_model is not None
+                self.plan = plan_layers(self.n_nodes, self.model_config.n_layer, self.model_config,
+                                        policy=self.partition_policy)
+                node_chunks_dir = split_and_store(full_model, self.n_nodes, self.ckpt_dir, plan=self.plan,
+                                                  config=self.model_config, verb=self.verb)
+                self.model_was_split = not self.push_chunks
+            else:
+                self.model_config, _ = load_from_pt(self.ckpt_dir, config_only=True)
+            if model_seq_length and model_seq_length > self.model_config.block_size:
+                raise ValueError(
+                    f"The truncated sequence length {model_seq_length} should be lower or equal than "
+                    f"the model's max sequence length {self.model_config.block_size}")
+            self.model_seq_length = model_seq_length
+            if not self.chunk_path:
+                self.chunk_path = (node_chunks_dir / "model_starter.pth") if self.n_nodes > 1 \
+                    else self.ckpt_dir / "lit_model.pth"
+            self.node_chunks_dir = node_chunks_dir
+            self.gpt_serv = GPTServer(
+                node_config=self.node_config, node_type=self.node_type, model_config=self.model_config,
+                chunk_path=self.chunk_path, tokenizer_dir=self.ckpt_dir, model_device=self.torch_device,
+                dtype=dtype, model_type=self.full_model_name, model_seq_length=self.model_seq_length, **kwargs)
+        elif "secondary" in self.node_type:
+            assert self.ckpt_dir or self.chunk_path, \
+                "Need to specify at least 1 between the chunk path and the checkpoint directory"
+            split_type = self.node_type.split(":")
+            self.secondary_index = secondary_index if len(split_type) < 2 else int(split_type[1])
+            assert self.secondary_index is not None
+            self.node_type = f"secondary:{self.secondary_index}"
+            self.n_nodes = None
+            if "nodes" in self.node_config:
+                self.own_config = self.node_config["nodes"]["secondary"][self.secondary_index]
+                self.n_nodes = 1 + len(self.node_config["nodes"]["secondary"])
+            else:
+                self.own_config = self.node_config
+            if self.ckpt_dir and self.n_nodes and self.chunk_path is None:
+                self.chunk_path = chunk_dir(self.ckpt_dir, self.n_nodes) / f"model_secondary{self.secondary_index}.pth"
+            elif not self.chunk_path and not self.n_nodes:
+                warnings.warn("Missing info about total n. of nodes, cannot select correct chunk")
+            if self.ckpt_dir and (self.ckpt_dir / "model_config.yaml").is_file():
+                self.model_config, _ = load_from_pt(self.ckpt_dir, config_only=True)
+            self.gpt_serv = GPTServer(
+                node_config=self.node_config, node_type=self.node_type, model_config=self.model_config,
+                chunk_path=self.chunk_path, model_device=self.torch_device, dtype=dtype, **kwargs)
+        else:
+            raise ValueError(f"unknown node type {node_type!r}")
+        self.torch_device = self.gpt_serv.model_device
+
+    # ---------------------------------------------------------------------------------------------
+    def start(self, *, n_samples: Optional[int] = None, tokens_per_sample: Optional[int] = None,
+              prompt: Optional[Union[str, Sequence[torch.Tensor]]] = None,
+              quiet: bool = False) -> Optional[List[Tuple[int, float]]]:
+        if self.node_type != "starter":
+            try:
+                self.gpt_serv.block()
+            except KeyboardInterrupt:
+                self.gpt_serv.shutdown()
+                print("Node was stopped!")
+            return None
+        assert n_samples and tokens_per_sample and self.model_config
+        if not self.configure_nodes(n_samples=n_samples):
+            raise RuntimeError("Unable to initialize network nodes!")
+        try:
+            out_text, time_gen = self.gpt_serv.launch_starter(n_samples, tokens_per_sample, prompt)
+            self.out_text = out_text
+            if not quiet:
+                print("-------------------------------------------------")
+                print("Produced output:\n")
+                for i, smpl in enumerate(out_text):
+                    print("-------------------------------------------------")
+                    print(f"Sample {i + 1}:")
+                    print(smpl, "\n")
+                print("-------------------------------------------------")
+                if time_gen:
+                    print(f"Total generation time: {time_gen[-1][1]}")
+            return time_gen
+        except KeyboardInterrupt:
+            self.gpt_serv.shutdown()
+            print("Node was stopped!")
+            return None
+        finally:
+            self.stop_nodes()
+
+    # ---------------------------------------------------------------------------------------------
+    def _secondary_layer_counts(self) -> List[int]:
+        """Layers of every secondary: from the chunk files if they are on this file system, else
+        from the plan."""
+        assert self.model_config is not None
+        counts: List[int] = []
+        for i in range(self.n_secondary):
+            f = self.node_chunks_dir / f"model_secondary{i}.pth"
+            if f.is_file():
+                counts.append(count_transformer_blocks(lazy_load(f)))
+            else:
+                counts = []
+                break
+        if len(counts) == self.n_secondary:
+            return counts
+        plan = self.plan or plan_layers(self.n_nodes, self.model_config.n_layer, self.model_config,
+                                        policy=self.partition_policy)
+        return list(plan[1:])
+
+    def configure_nodes(self, n_samples: int) -> int:
+        if self.node_type != "starter":
+            raise ValueError("This method can only be called on starter nodes!")
+        if not self.model_config:
+            raise ValueError("The model configuration was not loaded!")
+        nodes = self.node_config["nodes"]
+        secondaries = nodes.get("secondary", [])
+        if not secondaries:
+            if self.verb:
+                print("No secondary nodes found! Running standalone")
+            return 1
+        counts = self._secondary_layer_counts()
+        ring = [nodes["starter"]] + list(secondaries)  # ring order == order in the JSON
+        s = self.gpt_serv.sampling
+        for i, sec in enumerate(secondaries):
+            msg = dict(self.init_msg)
+            msg.update(
+                role=f"secondary:{i}", model_config=self.model_config.asdict(), n_nodes=self.n_nodes,
+                n_local_layers=counts[i], n_samples=n_samples, prev_node=ring[i],
+                next_node=ring[(i + 2) % len(ring)], max_seq_length=self.model_seq_length,
+                sampling=dict(temperature=s.temperature, top_k=s.top_k, top_p=s.top_p, seed=s.seed),
+            )
+            if not self.model_was_split:
+                msg["params"] = torch.load(self.node_chunks_dir / f"model_secondary{i}.pth",
+                                           map_location="cpu", weights_only=True)
+            addr = f"http://{sec['addr']}:{sec['communication']['port']}/init"
+            if not self._request_to_node("post", addr, msg):
+                return 0
+        return 1
+
+    def stop_nodes(self) -> int:
+        out = 1
+        for sec in self.node_config["nodes"].get("secondary", []):
+            addr = f"http://{sec['addr']}:{sec['communication']['port']}/stop"
+            out *= self._request_to_node("put", addr, "", max_n_requests=3)
+        return out
+
+    def _request_to_node(self, req_type: str, addr: str, content: Any, max_n_requests: int = 100) -> int:
+        return request_to_node(req_type, addr, content, max_n_requests=max_n_requests, verb=self.verb)

@@ -1,0 +1,57 @@
+import importlib.util
+import os
+
+import pytest
+
+from mdi_llm_b200.models.config import Config, find_multiple
+from mdi_llm_b200.models.registry import configs, lookup, name_to_config
+
+REF_CFG = "/root/reference/src/sub/config.py"
+
+
+def test_find_multiple():
+    assert find_multiple(50254, 512) == 50688
+    assert find_multiple(512, 512) == 512
+
+
+def test_llama3_8b_shape():
+    c = Config.from_name("Llama-3-8B")
+    assert (c.n_layer, c.n_embd, c.n_head, c.n_query_groups, c.head_size) == (32, 4096, 32, 8, 128)
+    assert c.qkv_size == 6144 and c.intermediate_size == 14336 and c.padded_vocab_size == 128256
+    assert c.rope_n_elem == 128 and c.rope_base == 500000
+    # lm_head costs ~2.4 blocks of bytes
+    assert 2.3 < c.head_param_count() / c.block_param_count() < 2.5
+
+
+def test_lookup_by_hf_name_and_yaml_roundtrip(tmp_path):
+    c = Config.from_name("Meta-Llama-3-8B-Instruct")
+    assert c.name == "Llama-3-8B-Instruct"
+    c.save(tmp_path)
+    c2 = Config.from_checkpoint(tmp_path)
+    assert c2.asdict() == c.asdict()
+    assert "pos_embedding" not in c.asdict()  # schema stays the reference's for litGPT models
+
+
+def test_gpt2_family_extension(tmp_path):
+    c = Config.from_name("gpt2")
+    assert c.pos_embedding == "learned" and c.tie_embeddings and c.rope_n_elem == 0
+    c.save(tmp_path)
+    assert Config.from_file(tmp_path / "model_config.yaml").pos_embedding == "learned"
+
+
+def test_unknown_name():
+    with pytest.raises(ValueError):
+        lookup("no-such-model")
+
+
+@pytest.mark.skipif(not os.path.isfile(REF_CFG), reason="reference tree not mounted")
+def test_registry_matches_reference(tmp_path, monkeypatch):
+    monkeypatch.chdir(tmp_path)  # the reference has a `typing.py` that shadows stdlib when cwd=sub/
+    spec = importlib.util.spec_from_file_location("_refcfg", REF_CFG)
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    assert len(ref.configs) <= len(configs)
+    for rc in ref.configs:
+        mine = Config(**name_to_config[rc["name"]])
+        theirs = Config(**rc)
+        assert mine.asdict() == theirs.asdict(), rc["name"]

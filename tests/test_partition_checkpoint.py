@@ -1,0 +1,81 @@
+import torch
+import pytest
+
+from mdi_llm_b200.models.config import Config
+from mdi_llm_b200.models.partition import (N_LAYERS_NODES, balanced_plan, count_transformer_blocks,
+                                            merge_chunks, plan_layers, split_and_store, split_parameters)
+from mdi_llm_b200.utils.checkpoint import (incremental_save, init_from_state_dict, lazy_load, load_from_pt,
+                                           random_state_dict, write_random_checkpoint)
+
+
+def test_reference_table_values():
+    assert N_LAYERS_NODES[2][32] == {"N_LAYERS_START": 14, "N_LAYERS_SECONDARY": 18}
+    assert N_LAYERS_NODES[3][22] == {"N_LAYERS_START": 6, "N_LAYERS_SECONDARY": 8}
+    assert N_LAYERS_NODES[1][12] == {"N_LAYERS_START": 12}
+    assert plan_layers(4, 32) == [5, 9, 9, 9] and plan_layers(5, 22) == [2, 5, 5, 5, 5]
+
+
+def test_planner_for_missing_topologies():
+    cfg = Config.from_name("Llama-3-8B")
+    plan = plan_layers(8, 32, cfg)
+    assert sum(plan) == 32 and len(plan) == 8 and min(plan) >= 1
+    head = cfg.head_param_count() / cfg.block_param_count()
+    assert max(plan[0] + head, max(plan[1:])) <= 5.0 + 1e-6  # uniform 4/4 would cost 6.4
+    with pytest.raises(KeyError):
+        plan_layers(8, 32, cfg, policy="table")
+    assert balanced_plan(1, 7) == [7]
+    with pytest.raises(ValueError):
+        balanced_plan(4, 3)
+
+
+@pytest.mark.parametrize("n_nodes", [2, 3])
+def test_split_reindex_and_merge_identity(tiny_llama_cfg, n_nodes):
+    sd = random_state_dict(tiny_llama_cfg, dtype=torch.float32)
+    ref = {k: v.clone() for k, v in sd.items()}
+    chunks, info = split_parameters(sd, n_nodes)
+    assert len(sd) == 0  # everything consumed
+    plan = info["plan"]
+    assert count_transformer_blocks(chunks["starter"]) == plan[0]
+    assert "lm_head.weight" in chunks["starter"] and "transformer.ln_f.weight" in chunks["starter"]
+    for i, c in enumerate(chunks["secondary"]):
+        assert count_transformer_blocks(c) == plan[i + 1]
+        assert all(k.startswith("transformer.h.") for k in c)
+        assert "transformer.h.0.norm_1.weight" in c  # locally re-indexed from 0
+    merged = merge_chunks(chunks["starter"], chunks["secondary"])
+    assert merged.keys() == ref.keys()
+    assert all(torch.equal(merged[k], ref[k]) for k in ref)
+
+
+def test_split_and_store_layout(tmp_path, tiny_llama_cfg):
+    ck = write_random_checkpoint(tmp_path / "org" / "model", tiny_llama_cfg, dtype=torch.float32)
+    cfg, sd = load_from_pt(ck)
+    assert cfg.asdict() == tiny_llama_cfg.asdict()
+    out = split_and_store(sd, 3, ck)
+    assert out == ck / "chunks" / "3nodes"
+    assert sorted(p.name for p in out.iterdir()) == ["model_secondary0.pth", "model_secondary1.pth", "model_starter.pth"]
+    lazy = lazy_load(out / "model_secondary1.pth")
+    assert count_transformer_blocks(lazy) == 2
+
+
+def test_init_from_state_dict_on_meta_and_ties(tiny_gpt2_cfg):
+    from mdi_llm_b200.models.gpt import GPT
+
+    sd = random_state_dict(tiny_gpt2_cfg, dtype=torch.float32)
+    with torch.device("meta"):
+        m = GPT(tiny_gpt2_cfg)
+    init_from_state_dict(m, sd)
+    assert all(p.device.type == "cpu" for p in m.parameters())
+    assert m.lm_head.weight.data_ptr() == m.transformer.wte.weight.data_ptr()
+    with pytest.raises(KeyError):
+        with torch.device("meta"):
+            m2 = GPT(tiny_gpt2_cfg)
+        init_from_state_dict(m2, {k: v for k, v in sd.items() if "ln_f" not in k})
+
+
+def test_incremental_save_roundtrip(tmp_path):
+    a, b = torch.randn(17, 5), torch.arange(12, dtype=torch.int32).reshape(3, 4)
+    with incremental_save(tmp_path / "out.pth") as saver:
+        sd = {"a": saver.store_early(a), "b": saver.store_early(b)}
+        saver.save(sd)
+    back = torch.load(tmp_path / "out.pth", weights_only=True)
+    assert torch.equal(back["a"], a) and torch.equal(back["b"], b)

@@ -1,0 +1,97 @@
+import pickle
+import socket
+import threading
+import time
+
+import pytest
+import torch
+
+from mdi_llm_b200.config import HEADERLENGTH
+from mdi_llm_b200.parallel.control import ControlServer, HTTPError, http_get_json, request_to_node
+from mdi_llm_b200.parallel.transport import (InputNodeConnection, LoopbackTransport, MessageQueue,
+                                              OutputNodeConnection, build_msg)
+from mdi_llm_b200.parallel.transport.socket_transport import encode_frame
+from conftest import free_ports
+
+
+def test_frame_is_reference_wire_format():
+    """16-char left-aligned ASCII decimal length + pickle (connections.py:338-342)."""
+    msg = build_msg(torch.arange(6).view(1, 2, 3), 4)
+    frame = encode_frame(msg)
+    payload = pickle.dumps(msg)
+    assert frame[:HEADERLENGTH] == f"{len(payload):<16}".encode()
+    assert int(frame[:HEADERLENGTH]) == len(frame) - HEADERLENGTH
+    back = pickle.loads(frame[HEADERLENGTH:])
+    assert back["sample_index"] == 4 and back["stop"] is False and torch.equal(back["data"], msg["data"])
+
+
+def test_socket_pair_roundtrip_and_raw_reference_sender():
+    p_in, p_out, p_raw = free_ports(3)
+    rx_cfg = {"addr": "127.0.0.1", "inference": {"port_in": p_in, "port_out": 0}}
+    tx_cfg = {"addr": "127.0.0.1", "inference": {"port_in": 0, "port_out": p_out}}
+    q_in, q_out = MessageQueue(), MessageQueue()
+    holder = {}
+    t = threading.Thread(target=lambda: holder.setdefault("rx", InputNodeConnection(rx_cfg, {"addr": "127.0.0.1"}, q_in)))
+    t.start()
+    tx = OutputNodeConnection(tx_cfg, rx_cfg, q_out)
+    t.join(timeout=5)
+    rx = holder["rx"]
+    rx.launch()
+    tx.launch()
+    for i in range(5):
+        q_out.put(build_msg(torch.full((1, 1, 8), float(i)), i))
+    q_out.put(build_msg("", 9, stop=True))
+    got = [q_in.get(timeout=2) for _ in range(6)]
+    assert [g["sample_index"] for g in got] == [0, 1, 2, 3, 4, 9]
+    assert got[-1]["stop"] and got[-1]["data"] == ""
+    assert float(got[3]["data"].sum()) == 24.0
+    tx.shutdown()
+    rx.shutdown()
+    assert tx.n_sent == 6 and rx.n_received == 6 and tx.bytes_sent == rx.bytes_received
+
+
+def test_loopback_transport_is_fifo():
+    t = LoopbackTransport()
+    for i in range(3):
+        t.send(build_msg(i, i))
+    assert [t.recv(0.1)["data"] for _ in range(3)] == [0, 1, 2]
+    assert t.recv(0.01) is None
+
+
+class _App:
+    def __init__(self):
+        self.got = []
+
+    def GET(self, path, body):
+        if not path:
+            return '{"hello": "node"}'
+        raise HTTPError(404, "Not found")
+
+    def POST(self, path, body):
+        if path == ("init",):
+            self.got.append(pickle.loads(body))
+            return None
+        raise HTTPError(404, "Not found")
+
+    def PUT(self, path, body):
+        raise HTTPError(501, "PUT not implemented!")
+
+
+def test_control_server_verbs_and_retrying_client():
+    (port,) = free_ports(1)
+    app = _App()
+    srv = ControlServer(app, "127.0.0.1", port)
+    srv.start()
+    try:
+        assert http_get_json(f"http://127.0.0.1:{port}/") == {"hello": "node"}
+        big = {"role": "secondary:0", "params": {"w": torch.randn(256, 256)}}
+        assert request_to_node("post", f"http://127.0.0.1:{port}/init", big, max_n_requests=2, retry_wait=0.01) == 1
+        assert torch.equal(app.got[0]["params"]["w"], big["params"]["w"])
+        assert request_to_node("put", f"http://127.0.0.1:{port}/stop", "", max_n_requests=2, retry_wait=0.01) == 0
+        assert request_to_node("post", f"http://127.0.0.1:{port}/nope", {}, max_n_requests=1, retry_wait=0.01) == 0
+        with pytest.raises(ValueError):
+            request_to_node("delete", "http://x", {})
+    finally:
+        srv.stop()
+    (dead,) = free_ports(1)
+    assert request_to_node("post", f"http://127.0.0.1:{dead}/init", {}, max_n_requests=2, retry_wait=0.01) == 0
