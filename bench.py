@@ -1,0 +1,240 @@
+#!/usr/bin/env python3
+"""Headline benchmark: generated tokens/sec of Llama-3-8B recurrent-pipeline decode on N B200s.
+
+Contract (driver): ``python bench.py --gpus N --steps K --warmup W`` (N > 1: launched under
+``torch.distributed.run`` with one rank per GPU).  Prints ONE JSON line on rank 0.
+
+* One *step* = one decode round of the recurrent pipeline: every one of the ``n_samples = N``
+  concurrent samples advances by one token (BASELINE.json configs: N GPUs ↔ N samples), so a step
+  generates N tokens and ``value = K * N / t`` is the whole-box aggregate.  Weak scaling: the
+  number of in-flight samples grows with N while each GPU holds 1/N of the layers.
+* Timed region = exactly K rounds after W warm-up rounds (prefill excluded: the metric is
+  *decode*), bracketed by barrier + ``torch.cuda.synchronize()``; device time from CUDA events,
+  MAX over ranks.  Inputs larger than L2: each round streams the stage's weights
+  (16 GB / N ≫ 126 MB L2) so no L2 flush is needed between iterations.
+* ``e2e``: the same rounds through the public host-fed API (``DevicePipeline`` mode="host"):
+  every step copies its descriptor H2D from pinned memory and reads the sampled token back D2H.
+* ``--impl reference`` runs the unmodified reference (baseline/_ref) — see baseline/run_reference.py.
+
+Synthetic prompts, random-init weights of the Llama-3-8B architecture (no network on the box).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from typing import Any, Dict, List, Optional
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "generated tokens/sec (whole box, device-timed, max over ranks) Llama-3-8B recurrent-pipeline decode"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons during the timed region (recipe's clocks line)."""
+
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, n_gpus: int) -> None:
+        self.n = n_gpus
+        self.proc: Optional[subprocess.Popen] = None
+        self.lines: List[str] = []
+
+    def start(self) -> None:
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self) -> None:
+        assert self.proc is not None and self.proc.stdout is not None
+        for line in self.proc.stdout:
+            self.lines.append(line)
+
+    def stop(self) -> Dict[str, Any]:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                if int(f[0]) >= self.n:
+                    continue
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def parse_args() -> argparse.Namespace:
+    ap = argparse.ArgumentParser(description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=128)
+    ap.add_argument("--warmup", type=int, default=8)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--model", default="Llama-3-8B")
+    ap.add_argument("--prompt-len", type=int, default=64)
+    ap.add_argument("--seq-len", type=int, default=0, help="KV/context budget (0 = prompt + all rounds)")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="rounds of the host-fed e2e measurement (0 = min(steps, 64))")
+    ap.add_argument("--n-samples", type=int, default=0, help="concurrent samples (0 = number of GPUs)")
+    ap.add_argument("--partition", default="balanced", choices=["auto", "table", "balanced"])
+    ap.add_argument("--no-pdl", action="store_true")
+    ap.add_argument("--ctas-per-sm", type=int, default=4)
+    ap.add_argument("--temperature", type=float, default=0.8)
+    ap.add_argument("--top-k", type=int, default=200)
+    ap.add_argument("--tiny", action="store_true", help="tiny model (CI smoke of the harness; NOT a valid bench number)")
+    return ap.parse_args()
+
+
+def run_ours(args: argparse.Namespace) -> Dict[str, Any]:
+    import torch
+    import torch.distributed as dist
+
+    from mdi_llm_b200.models.config import Config
+    from mdi_llm_b200.models.partition import plan_layers
+    from mdi_llm_b200.models.stage import build_stage
+    from mdi_llm_b200.parallel.pipeline import DevicePipeline
+    from mdi_llm_b200.parallel.scheduler import SamplingParams
+    from mdi_llm_b200.utils.checkpoint import random_init_stage_
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit(f"--gpus {args.gpus} needs torch.distributed.run --nproc-per-node {args.gpus}")
+        args.gpus = world
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+
+    def barrier() -> None:
+        torch.cuda.synchronize(device)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(device)
+
+    if args.tiny:
+        cfg = Config.from_name("tiny-llama-1.1b", n_layer=8, n_embd=512, n_head=8, n_query_groups=2,
+                               intermediate_size=1024, vocab_size=2000, padded_vocab_size=2048, block_size=2048)
+    else:
+        cfg = Config.from_name(args.model)
+    n_samples = args.n_samples or world
+    e2e_rounds = args.e2e_steps or min(args.steps, 64)
+    rounds_total = args.warmup + args.steps + 1
+    seq_len = args.seq_len or min(cfg.block_size, ((args.prompt_len + max(rounds_total, e2e_rounds + 4) + 64) // 64) * 64)
+    plan = plan_layers(world, cfg.n_layer, cfg, policy=args.partition) if world > 1 else [cfg.n_layer]
+    role = "starter" if rank == 0 else f"secondary:{rank - 1}"
+    stage = build_stage(cfg, role, plan[rank], meta=True)
+    random_init_stage_(stage, device, torch.bfloat16, seed=1234 + rank)
+    sampling = SamplingParams(temperature=args.temperature, top_k=args.top_k, seed=2024)
+    pipe = DevicePipeline(stage, rank, world, n_samples=n_samples, max_seq_length=seq_len, sampling=sampling,
+                          max_prompt_len=args.prompt_len, use_pdl=not args.no_pdl, ctas_per_sm=args.ctas_per_sm)
+    pipe.connect_distributed()
+    g = torch.Generator().manual_seed(7)
+    prompts = [torch.randint(0, cfg.vocab_size, (args.prompt_len,), generator=g, dtype=torch.int32) for _ in range(n_samples)]
+
+    # ---------------- device-driven, device-timed ----------------
+    pipe.prepare(prompts, rounds_total)
+    barrier()
+    pipe.prefill()
+    pipe.decode_rounds(args.warmup)
+    barrier()
+    sampler = ClockSampler(world)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = pipe.n_graph_launches
+    ev0.record()
+    pipe.decode_rounds(args.steps)
+    ev1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else {}
+    ms = torch.tensor([ev0.elapsed_time(ev1)], device=device, dtype=torch.float64)
+    graph_nodes = next(iter(pipe.stage._graphs.values())).n_nodes if pipe.stage._graphs else 0
+    launches = torch.tensor([(pipe.n_graph_launches - launches0) * graph_nodes], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(launches, op=dist.ReduceOp.SUM)
+    ms_total = float(ms.item())
+    tokens = args.steps * n_samples
+    value = tokens / (ms_total / 1e3)
+    status = int(pipe.stage.status.item())
+
+    # ---------------- end to end through the host-fed public API ----------------
+    pinned = [p.pin_memory() for p in prompts]  # inputs start in pinned host memory
+    pipe.prepare(pinned, e2e_rounds + 2)
+    barrier()
+    pipe.prefill()
+    pipe.decode_rounds_host(1)  # one untimed round (graph capture of the host-fed variant)
+    barrier()
+    t0 = time.perf_counter()
+    _, h2d, d2h = pipe.decode_rounds_host(e2e_rounds)
+    barrier()
+    e2e_s = torch.tensor([time.perf_counter() - t0], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = e2e_rounds * n_samples / float(e2e_s.item())
+    steps_e2e = e2e_rounds * n_samples
+
+    out = {
+        "metric": METRIC, "value": round(value, 3), "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(ms_total / args.steps, 5), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic prompts, random-init weights",
+        "impl": "ours",
+        "config": {"model": cfg.name, "n_layer": cfg.n_layer, "global_batch": n_samples, "seq_len": seq_len,
+                   "prompt_len": args.prompt_len, "parallelism": f"pp{world} recurrent pipeline, plan {plan}",
+                   "tokens_per_step": n_samples, "l2_policy": "inputs (stage weights) larger than L2, no flush",
+                   "sampling": {"temperature": args.temperature, "top_k": args.top_k}, "pdl": not args.no_pdl,
+                   "hop": "fused P2P store + flag (NVLink)" if world > 1 else "local (standalone ring)",
+                   "timing": "CUDA events, max over ranks"},
+        "clocks": clocks,
+        "e2e": {"value": round(e2e_value, 3), "unit": "tokens/s", "h2d_bytes_per_step": h2d // max(1, steps_e2e),
+                "d2h_bytes_per_step": d2h // max(1, steps_e2e), "rounds": e2e_rounds,
+                "how": "host-fed steps: pinned ctx H2D + sampled-token D2H every step, wall clock, max over ranks"},
+        "gpu_launches": int(launches.item()),
+        "hop_watchdog_status": status,
+    }
+    if args.tiny:
+        out["config"]["WARNING"] = "tiny smoke model — not the BASELINE config"
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return out if rank == 0 else {}
+
+
+def main() -> None:
+    args = parse_args()
+    if args.impl == "reference":
+        from baseline.run_reference import run_reference
+
+        out = run_reference(args)
+    else:
+        out = run_ours(args)
+    if out:
+        print(json.dumps(out), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,237 @@
+"""Python bindings of the sm_100a kernel library (``_mdi_ops.so``, C ABI via ctypes).
+
+The wrappers take torch tensors, pass raw device pointers and launch on the *current torch
+stream*, so they compose with torch ops and can be captured into CUDA graphs.  There is no
+silent fallback: on a CUDA machine a missing/unbuildable library raises, on a CPU-only machine
+``available()`` is False and callers use the eager path explicitly.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int, c_longlong, c_size_t, c_ulonglong, c_void_p, POINTER, byref
+from pathlib import Path
+from typing import Any, Optional, Tuple
+
+import torch
+
+from . import build as _build
+
+__all__ = ["lib", "available", "require", "OpsError", "ptr", "stream_ptr", "check", "ACT", "CTX_INTS",
+           "linear_decode", "qkv_decode", "attn_decode", "embed", "rmsnorm_rows", "sample", "advance_step",
+           "CudaGraph"]
+
+CTX_SLOT, CTX_POS, CTX_WAIT, CTX_SIGNAL, CTX_TOKEN, CTX_STEP = 0, 1, 2, 3, 4, 5
+CTX_INTS = 8
+ACT = {"none": 0, "silu_gate": 1, "gelu_tanh_gate": 2, "gelu_erf_gate": 3, "gelu_tanh": 4, "gelu_erf": 5}
+
+_lib: Optional[ctypes.CDLL] = None
+_load_error: Optional[BaseException] = None
+
+
+class OpsError(RuntimeError):
+    pass
+
+
+def _declare(lib: ctypes.CDLL) -> None:
+    vp, i32, i64, f32 = c_void_p, c_int, c_longlong, c_float
+    lib.mdi_error_string.restype = c_char_p
+    lib.mdi_error_string.argtypes = [i32]
+    lib.mdi_linear_decode.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, i32, i32, f32, i32, i32, i32,
+                                      vp, vp, i64, vp, vp, i32, i32, vp]
+    lib.mdi_qkv_decode.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, i32, i32, i32, f32, i32,
+                                   vp, vp, i64, i32, i32, vp]
+    lib.mdi_attn_decode.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]
+    lib.mdi_embed.argtypes = [vp, vp, vp, i64, vp, vp, i64, i32, f32, i32, vp]
+    lib.mdi_rmsnorm_rows.argtypes = [vp, vp, vp, i32, i32, f32, i32, vp]
+    lib.mdi_sample.argtypes = [vp, i64, vp, i64, vp, vp, i32, i32, f32, i32, c_ulonglong, i32, vp]
+    lib.mdi_advance_step.argtypes = [vp, vp, vp, i32, i32, i32, vp]
+    lib.mdi_wait_flag.argtypes = [vp, vp, vp, i64, vp]
+    lib.mdi_set_flag.argtypes = [vp, vp, vp]
+    lib.mdi_copy_bytes.argtypes = [vp, vp, c_size_t, vp]
+    lib.mdi_device_info.argtypes = [POINTER(i32), POINTER(i32), POINTER(i32), POINTER(c_size_t)]
+    lib.mdi_p2p_alloc.argtypes = [c_size_t, POINTER(vp), c_char_p]
+    lib.mdi_p2p_open.argtypes = [c_char_p, POINTER(vp)]
+    lib.mdi_p2p_close.argtypes = [vp]
+    lib.mdi_p2p_free.argtypes = [vp]
+    lib.mdi_enable_peer.argtypes = [i32, i32]
+    lib.mdi_graph_begin.argtypes = [vp]
+    lib.mdi_graph_end.argtypes = [vp, POINTER(vp), POINTER(i32)]
+    lib.mdi_graph_launch.argtypes = [vp, vp, i32]
+    lib.mdi_graph_launch_pattern.argtypes = [vp, i32, vp, i32, i32, vp]
+    lib.mdi_graph_destroy.argtypes = [vp]
+    lib.mdi_host_alloc.argtypes = [c_size_t, POINTER(vp)]
+    lib.mdi_host_free.argtypes = [vp]
+    lib.mdi_memcpy_async.argtypes = [vp, vp, c_size_t, i32, vp]
+    lib.mdi_stream_sync.argtypes = [vp]
+    for name in dir(lib):
+        pass
+
+
+def lib() -> ctypes.CDLL:
+    """Load (building if stale and nvcc is present) the kernel library."""
+    global _lib, _load_error
+    if _lib is not None:
+        return _lib
+    if _load_error is not None:
+        raise OpsError(f"kernel library unavailable: {_load_error}") from _load_error
+    try:
+        if not _build.LIB.exists() or (not _build.is_fresh() and _build.nvcc_path()):
+            _build.build()
+        handle = ctypes.CDLL(str(_build.LIB))
+        _declare(handle)
+        _lib = handle
+        return handle
+    except BaseException as e:  # noqa: BLE001
+        _load_error = e
+        raise OpsError(f"cannot load {_build.LIB}: {e}") from e
+
+
+def available() -> bool:
+    """True when CUDA is present *and* the library loads.  Raises on a CUDA box whose library is
+    broken (no silent eager fallback on the GPU)."""
+    if not torch.cuda.is_available():
+        return False
+    lib()
+    return True
+
+
+def require() -> ctypes.CDLL:
+    if not torch.cuda.is_available():
+        raise OpsError("the sm_100a kernels need a CUDA device")
+    return lib()
+
+
+def check(code: int, what: str = "") -> None:
+    if code != 0:
+        msg = {-2: "invalid shape/alignment", -3: "unsupported configuration", -4: "no peer access"}.get(code)
+        if msg is None:
+            msg = lib().mdi_error_string(code).decode()
+        raise OpsError(f"{what or 'kernel launch'} failed: {msg} ({code})")
+
+
+def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _bf16(t: Optional[torch.Tensor], name: str) -> None:
+    if t is not None and (t.dtype != torch.bfloat16 or not t.is_cuda or not t.is_contiguous()):
+        raise OpsError(f"{name}: expected a contiguous CUDA bf16 tensor, got {t.dtype} {t.device}")
+
+
+# ---------------------------------------------------------------------------------------------------
+def linear_decode(
+    W: torch.Tensor, x: torch.Tensor, y: torch.Tensor, ctx: torch.Tensor, *,
+    W2: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None, bias2: Optional[torch.Tensor] = None,
+    norm_w: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None, eps: float = 1e-5,
+    unit_offset: bool = False, act: str = "none", x_slot_stride: int = 0, res_slot_stride: int = 0,
+    y_slot_stride: int = 0, wait_flag: Optional[int] = None, status: Optional[int] = None, wait_max_cycles: int = 0,
+    signal_flag: Optional[int] = None, done_ctr: Optional[int] = None, ctas_per_sm: int = 4, use_pdl: bool = False,
+    y_ptr: Optional[int] = None, residual_ptr: Optional[int] = None, x_ptr: Optional[int] = None,
+) -> None:
+    """``y = epilogue(W @ norm?(x))`` for one token.  ``*_ptr`` overrides let the output /
+    residual / input live in peer-mapped (other GPU) memory that has no torch tensor."""
+    _bf16(W, "W"); _bf16(W2, "W2")
+    N, K = W.shape
+    out_fp32 = int(y is not None and y.dtype == torch.float32)
+    check(lib().mdi_linear_decode(
+        ptr(W), ptr(W2), ptr(bias), ptr(bias2), x_ptr if x_ptr is not None else ptr(x), ptr(norm_w),
+        residual_ptr if residual_ptr is not None else ptr(residual), y_ptr if y_ptr is not None else ptr(y),
+        ptr(ctx), x_slot_stride, res_slot_stride, y_slot_stride, N, K, eps, int(unit_offset), ACT[act], out_fp32,
+        wait_flag, status, wait_max_cycles, signal_flag, done_ctr, ctas_per_sm, int(use_pdl), stream_ptr()),
+        "linear_decode")
+
+
+def qkv_decode(
+    W: torch.Tensor, x: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor, q_out: torch.Tensor, kv_layer: torch.Tensor,
+    ctx: torch.Tensor, *, n_head: int, n_groups: int, head_size: int, rope_n_elem: int, max_seq: int,
+    bias: Optional[torch.Tensor] = None, norm_w: Optional[torch.Tensor] = None, eps: float = 1e-5,
+    unit_offset: bool = False, x_slot_stride: int = 0, wait_flag: Optional[int] = None, status: Optional[int] = None,
+    wait_max_cycles: int = 0, ctas_per_sm: int = 4, use_pdl: bool = False, x_ptr: Optional[int] = None,
+) -> None:
+    _bf16(W, "W")
+    if cos.dtype != torch.float32 or sin.dtype != torch.float32:
+        raise OpsError("rope tables must be fp32")
+    check(lib().mdi_qkv_decode(
+        ptr(W), ptr(bias), x_ptr if x_ptr is not None else ptr(x), ptr(norm_w), ptr(cos), ptr(sin), ptr(q_out),
+        ptr(kv_layer), ptr(ctx), x_slot_stride, W.shape[1], n_head, n_groups, head_size, rope_n_elem, max_seq, eps,
+        int(unit_offset), wait_flag, status, wait_max_cycles, ctas_per_sm, int(use_pdl), stream_ptr()), "qkv_decode")
+
+
+def attn_decode(q: torch.Tensor, kv_layer: torch.Tensor, y: torch.Tensor, part: torch.Tensor, ctx: torch.Tensor, *,
+                n_head: int, n_groups: int, head_size: int, max_seq: int, n_split: int, use_pdl: bool = False) -> None:
+    check(lib().mdi_attn_decode(ptr(q), ptr(kv_layer), ptr(y), ptr(part), ptr(ctx), n_head, n_groups, head_size,
+                                max_seq, n_split, int(use_pdl), stream_ptr()), "attn_decode")
+
+
+def embed(wte: torch.Tensor, x: torch.Tensor, ctx: torch.Tensor, *, tokens: Optional[torch.Tensor] = None,
+          tok_slot_stride: int = 0, wpe: Optional[torch.Tensor] = None, x_slot_stride: int = 0, scale: float = 1.0,
+          use_pdl: bool = False) -> None:
+    _bf16(wte, "wte")
+    check(lib().mdi_embed(ptr(wte), ptr(wpe), ptr(tokens), tok_slot_stride, ptr(ctx), ptr(x), x_slot_stride,
+                          wte.shape[1], scale, int(use_pdl), stream_ptr()), "embed")
+
+
+def rmsnorm_rows(x: torch.Tensor, w: torch.Tensor, eps: float, unit_offset: bool = False) -> torch.Tensor:
+    _bf16(x, "x"); _bf16(w, "w")
+    y = torch.empty_like(x)
+    C = x.shape[-1]
+    check(lib().mdi_rmsnorm_rows(ptr(x), ptr(w), ptr(y), x.numel() // C, C, eps, int(unit_offset), stream_ptr()),
+          "rmsnorm_rows")
+    return y
+
+
+def sample(logits: torch.Tensor, tokens: torch.Tensor, ctx: torch.Tensor, *, vocab: int, top_k: Optional[int],
+           temperature: float, greedy: bool, seed: int, tok_slot_stride: int, logits_slot_stride: int = 0,
+           last_token: Optional[torch.Tensor] = None, use_pdl: bool = False) -> None:
+    if logits.dtype != torch.float32 or tokens.dtype != torch.int32:
+        raise OpsError("sample: logits fp32 and tokens int32 expected")
+    check(lib().mdi_sample(ptr(logits), logits_slot_stride, ptr(tokens), tok_slot_stride, ptr(last_token), ptr(ctx),
+                           vocab, int(top_k or 0), float(temperature), int(greedy), seed & (2 ** 64 - 1), int(use_pdl),
+                           stream_ptr()), "sample")
+
+
+def advance_step(ctx: torch.Tensor, state: torch.Tensor, pos: torch.Tensor, n_slots: int, is_starter: bool,
+                 use_pdl: bool = False) -> None:
+    check(lib().mdi_advance_step(ptr(ctx), ptr(state), ptr(pos), n_slots, int(is_starter), int(use_pdl), stream_ptr()),
+          "advance_step")
+
+
+class CudaGraph:
+    """A captured sequence of launches on the current stream, replayed from C."""
+
+    def __init__(self) -> None:
+        self.exec = c_void_p()
+        self.n_nodes = 0
+        self._stream: Optional[torch.cuda.Stream] = None
+
+    def __enter__(self) -> "CudaGraph":
+        self._stream = torch.cuda.Stream()
+        self._stream.wait_stream(torch.cuda.current_stream())
+        self._ctx = torch.cuda.stream(self._stream)
+        self._ctx.__enter__()
+        check(lib().mdi_graph_begin(self._stream.cuda_stream), "graph capture begin")
+        return self
+
+    def __exit__(self, exc_type: Any, exc: Any, tb: Any) -> None:
+        n = c_int(0)
+        code = lib().mdi_graph_end(self._stream.cuda_stream, byref(self.exec), byref(n))
+        self._ctx.__exit__(exc_type, exc, tb)
+        torch.cuda.current_stream().wait_stream(self._stream)
+        if exc_type is None:
+            check(code, "graph capture end")
+            self.n_nodes = n.value
+
+    def launch(self, times: int = 1) -> None:
+        check(lib().mdi_graph_launch(self.exec, stream_ptr(), times), "graph launch")
+
+    def __del__(self) -> None:
+        try:
+            if self.exec and _lib is not None:
+                _lib.mdi_graph_destroy(self.exec)
+        except Exception:  # noqa: BLE001
+            pass

@@ -1,0 +1,129 @@
+// Shared device helpers for the sm_100a decode/prefill kernels of the B200 MDI engine.
+//
+// Conventions: activations and weights are bf16, all reductions/accumulators are fp32.
+// "ctx" is the per-step device descriptor {slot, pos, wait, signal, token, step} written either by the host
+// (host-driven scheduler, one tiny H2D per step) or by `mdi_advance_step` (device-driven
+// pipeline, no host involvement) so that CUDA-graph replays never need new kernel arguments.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define MDI_CTX_SLOT 0
+#define MDI_CTX_POS 1
+#define MDI_CTX_WAIT 2    // value the incoming-hop flag of `slot` must reach before reading input
+#define MDI_CTX_SIGNAL 3  // value published to the next stage's flag of `slot` after the output
+#define MDI_CTX_TOKEN 4   // input token id of this step (starter)
+#define MDI_CTX_STEP 5    // global step counter (device-driven mode)
+#define MDI_CTX_INTS 8
+
+#define MDI_CHECK(call)                                            \
+  do {                                                             \
+    cudaError_t _e = (call);                                       \
+    if (_e != cudaSuccess) return (int)_e;                         \
+  } while (0)
+
+namespace mdi {
+
+typedef __nv_bfloat16 bf16;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// two packed bf16 -> two fp32 (exact: bf16 is the top half of an fp32)
+__device__ __forceinline__ float bf16lo(uint32_t u) { return __uint_as_float(u << 16); }
+__device__ __forceinline__ float bf16hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
+__device__ __forceinline__ float round_bf16(float f) { return __bfloat162float(__float2bfloat16_rn(f)); }
+
+// streaming 16-byte weight load: read-only path, do not allocate in L1
+__device__ __forceinline__ uint4 ldg_stream(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
+// ---- cross-GPU flag protocol (system scope: producer and consumer are different devices) ----
+__device__ __forceinline__ int ld_acquire_sys(const int* p) {
+  int v;
+  asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(int* p, int v) {
+  asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ int ld_volatile(const int* p) {
+  int v;
+  asm volatile("ld.volatile.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// Bounded spin on a hop flag.  Returns false on watchdog expiry (the caller records an error
+// code in the status word instead of hanging the GPU — SURVEY §5.3).
+__device__ __forceinline__ bool wait_flag_ge(const int* flag, int want, long long max_cycles) {
+  long long t0 = clock64();
+  while (ld_acquire_sys(flag) < want) {
+    __nanosleep(64);
+    if (max_cycles > 0 && clock64() - t0 > max_cycles) return false;
+  }
+  return true;
+}
+
+struct HopWait {   // consumer side; flag == nullptr disables
+  const int* flag;       // base of this GPU's flag array (one int per sample slot)
+  int* status;           // error word (set to 1 on watchdog expiry), may be null
+  long long max_cycles;  // 0 = wait forever
+};
+struct HopSignal {  // producer side; flag == nullptr disables
+  int* flag;               // base of the NEXT stage's flag array (peer-mapped or local)
+  unsigned int* done_ctr;  // local counter of finished CTAs (self-resetting)
+};
+
+// All threads call; thread 0 spins, everybody leaves after the flag for ctx's slot >= ctx's seq.
+__device__ __forceinline__ void hop_wait(const HopWait& w, const int* ctx) {
+  if (w.flag == nullptr) return;
+  if (threadIdx.x == 0) {
+    int slot = ctx[MDI_CTX_SLOT], want = ctx[MDI_CTX_WAIT];
+    if (!wait_flag_ge(w.flag + slot, want, w.max_cycles) && w.status) atomicExch(w.status, 1);
+  }
+  __syncthreads();
+}
+
+// Called by every CTA after its output stores.  The last CTA to arrive publishes the flag.
+__device__ __forceinline__ void hop_signal(const HopSignal& s, const int* ctx) {
+  if (s.flag == nullptr) return;
+  __threadfence_system();  // every thread: its (possibly remote) stores are visible system-wide
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned int total = gridDim.x * gridDim.y * gridDim.z;
+    unsigned int prev = atomicAdd(s.done_ctr, 1u);
+    if (prev == total - 1) {
+      *s.done_ctr = 0;  // ready for the next launch (stream-ordered)
+      __threadfence_system();
+      st_release_sys(s.flag + ctx[MDI_CTX_SLOT], ctx[MDI_CTX_SIGNAL]);
+    }
+  }
+}
+
+// Programmatic dependent launch: let the next kernel's prologue overlap our tail, and wait for
+// the previous kernel's memory before touching activations.
+__device__ __forceinline__ void pdl_wait_prior() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+__device__ __forceinline__ void pdl_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
+}  // namespace mdi

@@ -1,0 +1,344 @@
+// Small decode-path kernels: embedding gather, stand-alone RMSNorm, sampling, step bookkeeping.
+//
+//  * embed        — SURVEY K1 (submodels.py:210-212): wte row gather (+ sqrt(C) scale for Gemma,
+//                   + learned position row for the GPT-2 family); the token id is read on device
+//                   (written by the sampler of the previous round) — no host round trip.
+//  * rmsnorm_rows — K2 for multi-row inputs (prefill); decode fuses the norm into its consumer.
+//  * sample       — K13 (model.py:67-90): greedy arg-max, or top-k -> temperature -> softmax ->
+//                   one multinomial draw, entirely on device with a counter-based RNG; replaces
+//                   topk + scatter + softmax + multinomial (≈6 launches + a D2H sync per token,
+//                   gptserver.py:933-949).  Exact k-th-largest via 4-pass radix select.
+//  * advance_step — device-driven pipeline: derive {slot, pos, wait, signal} for the next graph
+//                   replay from a device-resident counter (round-robin over the samples).
+#include "common.cuh"
+
+namespace mdi {
+
+__global__ void embed_kernel(const bf16* __restrict__ wte, const bf16* __restrict__ wpe, const int* __restrict__ tokens,
+                             long long tok_slot_stride, const int* __restrict__ ctx, bf16* __restrict__ x,
+                             long long x_slot_stride, int C, float scale) {
+  pdl_wait_prior();
+  pdl_launch_dependents();
+  const int slot = ctx[MDI_CTX_SLOT], pos = ctx[MDI_CTX_POS];
+  const int tok = tokens ? tokens[(size_t)slot * tok_slot_stride + pos] : ctx[MDI_CTX_TOKEN];
+  const bf16* row = wte + (size_t)tok * C;
+  bf16* dst = x + (size_t)slot * x_slot_stride;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < C; i += gridDim.x * blockDim.x) {
+    float v = __bfloat162float(row[i]);
+    if (scale != 1.f) v = round_bf16(v * scale);
+    if (wpe) v = v + __bfloat162float(wpe[(size_t)pos * C + i]);
+    dst[i] = __float2bfloat16_rn(v);
+  }
+}
+
+// y[r] = bf16(x[r] * rstd) * w   — one CTA per row
+__global__ void __launch_bounds__(256) rmsnorm_rows_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w,
+                                                           bf16* __restrict__ y, int C, float eps, int unit_offset) {
+  __shared__ float red[8];
+  const bf16* xr = x + (size_t)blockIdx.x * C;
+  bf16* yr = y + (size_t)blockIdx.x * C;
+  float ss = 0.f;
+  for (int i = threadIdx.x; i < C; i += 256) { float f = __bfloat162float(xr[i]); ss = fmaf(f, f, ss); }
+  ss = warp_sum(ss);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) tot += red[i];
+  const float rstd = rsqrtf(tot / (float)C + eps);
+  for (int i = threadIdx.x; i < C; i += 256) {
+    float xn = round_bf16(__bfloat162float(xr[i]) * rstd);
+    float ww = __bfloat162float(w[i]);
+    if (unit_offset) ww = round_bf16(1.f + ww);
+    yr[i] = __float2bfloat16_rn(xn * ww);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// sampling
+constexpr int SMP_THREADS = 1024;
+constexpr int SMP_KMAX = 1024;
+
+__device__ __forceinline__ uint32_t float_key(float f) {  // monotone: larger float -> larger key
+  uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+
+struct SampleArgs {
+  const float* logits;  // [V] (+ slot * logits_slot_stride)
+  long long logits_slot_stride;
+  int* tokens;          // sampled id stored at tokens[slot * tok_slot_stride + pos]
+  long long tok_slot_stride;
+  int* last_token;      // optional: [n_slots] latest token per slot (host-visible mirror)
+  const int* ctx;
+  int V;                // sample among the first V logits (true vocab may be < padded)
+  int top_k;            // <= 0: no top-k crop
+  float temperature;    // <= 0 with greedy != 0: arg-max
+  int greedy;
+  unsigned long long seed;
+};
+
+__global__ void __launch_bounds__(SMP_THREADS) sample_kernel(const SampleArgs a) {
+  __shared__ unsigned int hist[256];
+  __shared__ float cand_val[SMP_KMAX];
+  __shared__ int cand_idx[SMP_KMAX];
+  __shared__ float sorted_val[SMP_KMAX];
+  __shared__ int sorted_idx[SMP_KMAX];
+  __shared__ float red_f[32];
+  __shared__ int red_i[32];
+  __shared__ unsigned int sh_prefix, sh_kleft, sh_count, sh_ngreater;
+  __shared__ float sh_max, sh_sum;
+  __shared__ int sh_pick;
+
+  pdl_wait_prior();
+  pdl_launch_dependents();
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int slot = a.ctx[MDI_CTX_SLOT], pos = a.ctx[MDI_CTX_POS];
+  const float* lg = a.logits + (size_t)slot * a.logits_slot_stride;
+  const int V = a.V;
+
+  if (a.greedy) {
+    float best = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int i = tid; i < V; i += SMP_THREADS) {
+      float v = lg[i];
+      if (v > best || (v == best && i < bi)) { best = v; bi = i; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      float ov = __shfl_xor_sync(0xffffffffu, best, o);
+      int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    if (lane == 0) { red_f[warp] = best; red_i[warp] = bi; }
+    __syncthreads();
+    if (warp == 0) {
+      best = red_f[lane]; bi = red_i[lane];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        float ov = __shfl_xor_sync(0xffffffffu, best, o);
+        int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+      }
+      if (lane == 0) {
+        a.tokens[(size_t)slot * a.tok_slot_stride + pos] = bi;
+        if (a.last_token) a.last_token[slot] = bi;
+      }
+    }
+    return;
+  }
+
+  int k = (a.top_k > 0 && a.top_k < V) ? a.top_k : V;
+  if (k > SMP_KMAX) k = SMP_KMAX;  // documented cap of the device sampler
+  // ---- radix select: key of the k-th largest logit ---------------------------------------------
+  if (tid == 0) { sh_prefix = 0; sh_kleft = (unsigned)k; sh_ngreater = 0; }
+  __syncthreads();
+  for (int pass = 0; pass < 4; ++pass) {
+    const int shift = 24 - 8 * pass;
+    if (tid < 256) hist[tid] = 0;
+    __syncthreads();
+    const unsigned int prefix = sh_prefix;
+    const unsigned int mask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
+    for (int i = tid; i < V; i += SMP_THREADS) {
+      const uint32_t key = float_key(lg[i]);
+      if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 0xffu], 1u);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      unsigned int left = sh_kleft, cum = 0;
+      int b = 255;
+      for (; b > 0; --b) {
+        if (cum + hist[b] >= left) break;
+        cum += hist[b];
+      }
+      sh_ngreater += cum;
+      sh_kleft = left - cum;
+      sh_prefix = prefix | ((unsigned)b << shift);
+    }
+    __syncthreads();
+  }
+  const uint32_t thr = sh_prefix;        // exact key of the k-th largest
+  const unsigned int n_ties = sh_kleft;  // how many elements equal to thr belong to the top-k
+  if (tid == 0) sh_count = 0;
+  __syncthreads();
+  // ---- collect the top-k: first everything strictly greater, then the needed ties -------------
+  for (int i = tid; i < V; i += SMP_THREADS) {
+    const float v = lg[i];
+    if (float_key(v) > thr) {
+      unsigned int s = atomicAdd(&sh_count, 1u);
+      if (s < SMP_KMAX) { cand_val[s] = v; cand_idx[s] = i; }
+    }
+  }
+  __syncthreads();
+  const unsigned int n_greater = min(sh_count, (unsigned)SMP_KMAX);
+  __syncthreads();
+  if (tid == 0) sh_count = 0;
+  __syncthreads();
+  for (int i = tid; i < V; i += SMP_THREADS) {
+    const float v = lg[i];
+    if (float_key(v) == thr) {
+      unsigned int s = atomicAdd(&sh_count, 1u);
+      if (s < n_ties && n_greater + s < SMP_KMAX) { cand_val[n_greater + s] = v; cand_idx[n_greater + s] = i; }
+    }
+  }
+  __syncthreads();
+  const int n = (int)min(n_greater + n_ties, (unsigned)SMP_KMAX);
+  // ---- order candidates by vocabulary index so a fixed seed gives a fixed token ---------------
+  if (tid < n) {
+    const int my = cand_idx[tid];
+    int rank = 0;
+    for (int j = 0; j < n; ++j) rank += (cand_idx[j] < my);
+    sorted_idx[rank] = my;
+    sorted_val[rank] = cand_val[tid];
+  }
+  __syncthreads();
+  // ---- softmax(logit / T) over the candidates ------------------------------------------------------
+  const float inv_t = a.temperature > 0.f ? 1.f / a.temperature : 1.f;
+  float v = tid < n ? sorted_val[tid] * inv_t : -INFINITY;
+  float mx = warp_max(v);
+  if (lane == 0) red_f[warp] = mx;
+  __syncthreads();
+  if (warp == 0) { float t = warp_max(red_f[lane]); if (lane == 0) sh_max = t; }
+  __syncthreads();
+  float e = tid < n ? __expf(v - sh_max) : 0.f;
+  // inclusive scan of e over the block (warp scans + scan of warp totals)
+  float sc = e;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { float t = __shfl_up_sync(0xffffffffu, sc, o); if (lane >= o) sc += t; }
+  __syncthreads();
+  if (lane == 31) red_f[warp] = sc;
+  __syncthreads();
+  if (warp == 0) {
+    float w = red_f[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { float t = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += t; }
+    red_f[lane] = w;
+    if (lane == 31) sh_sum = w;
+  }
+  __syncthreads();
+  const float incl = sc + (warp > 0 ? red_f[warp - 1] : 0.f);
+  const float excl = incl - e;
+  // one uniform draw from a counter-based generator keyed by (seed, slot, pos)
+  const uint64_t r = splitmix64(a.seed ^ splitmix64(((uint64_t)(uint32_t)slot << 32) | (uint32_t)pos));
+  const float u = (float)((r >> 40) * (1.0 / 16777216.0)) * sh_sum;
+  if (tid == 0) sh_pick = sorted_idx[n - 1];  // guard against round-off at the upper end
+  __syncthreads();
+  if (tid < n && e > 0.f && u >= excl && u < incl) sh_pick = sorted_idx[tid];
+  __syncthreads();
+  if (tid == 0) {
+    a.tokens[(size_t)slot * a.tok_slot_stride + pos] = sh_pick;
+    if (a.last_token) a.last_token[slot] = sh_pick;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Device-driven schedule.  state[0] = global step counter; per slot: pos[slot].
+// Step t serves slot = t % n_slots at round = t / n_slots.
+//   secondary : wait = round + 1 (message `round` has arrived), signal = round + 1
+//   starter   : head waits `round` (the hidden state that came back), forward signals round + 1
+// (round 0 is the prefill, handled outside the graph; decode rounds start at first_round.)
+__global__ void advance_step_kernel(int* __restrict__ ctx, int* __restrict__ state, int* __restrict__ pos_arr,
+                                    int n_slots, int is_starter) {
+  pdl_wait_prior();
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    const int t = state[0];
+    const int slot = t % n_slots;
+    const int round = state[1] + t / n_slots;  // state[1] = first decode round (normally 1)
+    ctx[MDI_CTX_SLOT] = slot;
+    ctx[MDI_CTX_POS] = pos_arr[slot];
+    ctx[MDI_CTX_WAIT] = is_starter ? round : round + 1;
+    ctx[MDI_CTX_SIGNAL] = round + 1;
+    ctx[MDI_CTX_STEP] = t;
+    pos_arr[slot] += 1;
+    state[0] = t + 1;
+  }
+  pdl_launch_dependents();
+}
+
+__global__ void wait_flag_kernel(const int* flag, const int* ctx, int* status, long long max_cycles) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    if (!wait_flag_ge(flag + ctx[MDI_CTX_SLOT], ctx[MDI_CTX_WAIT], max_cycles) && status) atomicExch(status, 1);
+  }
+}
+__global__ void set_flag_kernel(int* flag, const int* ctx) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    __threadfence_system();
+    st_release_sys(flag + ctx[MDI_CTX_SLOT], ctx[MDI_CTX_SIGNAL]);
+  }
+}
+// copy n 16-byte vectors (prefill hop payload: T x C hidden states) to a (peer) destination
+__global__ void copy_vec_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, size_t nvec) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (size_t)gridDim.x * blockDim.x)
+    dst[i] = src[i];
+}
+
+}  // namespace mdi
+
+using namespace mdi;
+
+static int launch_small(const void* kern, dim3 grid, dim3 block, void** args, int use_pdl, cudaStream_t stream) {
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.stream = stream;
+  cfg.attrs = attr;
+  cfg.numAttrs = use_pdl ? 1 : 0;
+  return (int)cudaLaunchKernelExC(&cfg, kern, args);
+}
+
+extern "C" {
+
+int mdi_embed(const void* wte, const void* wpe, const int* tokens, long long tok_slot_stride, const int* ctx, void* x,
+              long long x_slot_stride, int C, float scale, int use_pdl, cudaStream_t stream) {
+  void* args[] = {&wte, &wpe, &tokens, &tok_slot_stride, &ctx, &x, &x_slot_stride, &C, &scale};
+  int threads = 256, blocks = (C + threads - 1) / threads;
+  return launch_small((const void*)embed_kernel, dim3(blocks), dim3(threads), args, use_pdl, stream);
+}
+
+int mdi_rmsnorm_rows(const void* x, const void* w, void* y, int rows, int C, float eps, int unit_offset,
+                     cudaStream_t stream) {
+  rmsnorm_rows_kernel<<<rows, 256, 0, stream>>>((const bf16*)x, (const bf16*)w, (bf16*)y, C, eps, unit_offset);
+  return (int)cudaGetLastError();
+}
+
+int mdi_sample(const float* logits, long long logits_slot_stride, int* tokens, long long tok_slot_stride,
+               int* last_token, const int* ctx, int V, int top_k, float temperature, int greedy,
+               unsigned long long seed, int use_pdl, cudaStream_t stream) {
+  SampleArgs a{logits, logits_slot_stride, tokens, tok_slot_stride, last_token, ctx, V, top_k, temperature, greedy, seed};
+  void* args[] = {&a};
+  return launch_small((const void*)sample_kernel, dim3(1), dim3(SMP_THREADS), args, use_pdl, stream);
+}
+
+int mdi_advance_step(int* ctx, int* state, int* pos_arr, int n_slots, int is_starter, int use_pdl, cudaStream_t stream) {
+  void* args[] = {&ctx, &state, &pos_arr, &n_slots, &is_starter};
+  return launch_small((const void*)advance_step_kernel, dim3(1), dim3(32), args, use_pdl, stream);
+}
+
+int mdi_wait_flag(const int* flag, const int* ctx, int* status, long long max_cycles, cudaStream_t stream) {
+  wait_flag_kernel<<<1, 32, 0, stream>>>(flag, ctx, status, max_cycles);
+  return (int)cudaGetLastError();
+}
+int mdi_set_flag(int* flag, const int* ctx, cudaStream_t stream) {
+  set_flag_kernel<<<1, 32, 0, stream>>>(flag, ctx);
+  return (int)cudaGetLastError();
+}
+int mdi_copy_bytes(const void* src, void* dst, size_t bytes, cudaStream_t stream) {
+  if (bytes % 16) return -2;
+  size_t nvec = bytes / 16;
+  int blocks = (int)((nvec + 255) / 256);
+  if (blocks > 1184) blocks = 1184;
+  if (blocks < 1) blocks = 1;
+  copy_vec_kernel<<<blocks, 256, 0, stream>>>((const uint4*)src, (uint4*)dst, nvec);
+  return (int)cudaGetLastError();
+}
+
+}  // extern "C"

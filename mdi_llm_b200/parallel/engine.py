@@ -1,0 +1,332 @@
+"""CUDA stage executor: one pipeline stage's decode step as a short chain of fused sm_100a kernels.
+
+Per transformer block the reference launches ≈35-40 ATen kernels from Python; here a
+block is 6 launches (5 weight-streaming kernels + attention combine) and a whole stage step is
+replayed as one CUDA graph::
+
+    [hop wait]→ QKV(+RMSNorm+RoPE+KV append) → attention(split-KV, GQA packed) → out-proj(+residual)
+              → gate/up(+RMSNorm+SiLU·mul) → down(+residual [+P2P store to next stage + flag])
+
+The starter additionally runs ``lm_head(+final RMSNorm)`` → on-device sampling → embedding gather
+at the start of its step.  Weights are used in place (the ``StageModule`` parameters), the KV
+pool is shared with the eager module, which still serves prefill (T > 1) in this round.
+
+Two ways to drive it:
+
+* :class:`FusedStageRunner` — the :class:`~.scheduler.StageRunner` interface (host-driven; any
+  transport).  Each call is: tiny H2D of the step descriptor → graph replay → result tensor.
+* :class:`DevicePipeline` (``parallel/pipeline.py``) — device-driven ring over NVLink with fused
+  hops; the host only enqueues graph replays.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Any, Dict, List, Optional, Tuple
+
+import torch
+
+from .. import ops
+from ..models.config import Config
+from ..models.stage import StageModule, StarterNode
+from .scheduler import SamplingParams, StageRunner
+
+__all__ = ["engine_supports", "FusedStage", "FusedStageRunner", "HopTarget"]
+
+
+def engine_supports(config: Config, dtype: torch.dtype) -> bool:
+    """Architectures the fused decode kernels cover (the rest runs on the eager runner)."""
+    return (
+        dtype == torch.bfloat16
+        and config.norm_class_name == "RMSNorm"
+        and not config.parallel_residual
+        and config.mlp_class_name in ("LLaMAMLP", "GemmaMLP")
+        and config.pos_embedding == "rope"
+        and config.head_size in (64, 128)
+        and config.q_per_kv in (1, 2, 4, 8)
+        and config.n_embd % 8 == 0 and config.intermediate_size % 8 == 0
+        and config.rope_n_elem % 2 == 0 and config.rope_n_elem > 0
+    )
+
+
+@dataclass
+class HopTarget:
+    """Where the last block's epilogue stores the stage output: raw device pointers of the NEXT
+    stage's ``hidden_in [n_slots, C]`` and ``flags [n_slots]`` (peer-mapped or local)."""
+
+    hidden_ptr: int
+    flag_ptr: int
+
+
+class RawBuffer:
+    """cudaMalloc'ed (IPC-exportable) memory with torch views on top."""
+
+    def __init__(self, nbytes: int, device: torch.device) -> None:
+        import ctypes
+
+        self.nbytes = nbytes
+        self.device = device
+        p = ctypes.c_void_p()
+        self._handle = ctypes.create_string_buffer(64)
+        with torch.cuda.device(device):
+            ops.check(ops.lib().mdi_p2p_alloc(nbytes, ctypes.byref(p), self._handle), "p2p_alloc")
+        self.ptr = int(p.value)
+
+    @property
+    def handle(self) -> bytes:
+        return bytes(self._handle.raw)
+
+    def view(self, offset: int, shape: Tuple[int, ...], dtype: torch.dtype) -> torch.Tensor:
+        n = int(torch.tensor(shape).prod().item()) if shape else 1
+        typestr = {torch.bfloat16: "<u2", torch.int32: "<i4", torch.float32: "<f4", torch.uint8: "|u1"}[dtype]
+
+        class _Iface:
+            pass
+
+        holder = _Iface()
+        holder.__cuda_array_interface__ = {  # type: ignore[attr-defined]
+            "shape": (n,), "typestr": typestr, "data": (self.ptr + offset, False), "version": 3,
+        }
+        t = torch.as_tensor(holder, device=self.device)
+        if dtype == torch.bfloat16:
+            t = t.view(torch.bfloat16)
+        return t.view(*shape)
+
+    def free(self) -> None:
+        if self.ptr:
+            ops.lib().mdi_p2p_free(self.ptr)
+            self.ptr = 0
+
+
+class FusedStage:
+    """Buffers + kernel sequence of one stage.  All methods enqueue on the current stream."""
+
+    def __init__(self, model: StageModule, n_slots: int, max_seq_length: Optional[int] = None,
+                 sampling: Optional[SamplingParams] = None, use_pdl: bool = True, ctas_per_sm: int = 4,
+                 wait_max_cycles: int = 0, exportable: bool = False) -> None:
+        ops.require()
+        cfg = model.config
+        p = next(model.parameters())
+        if not engine_supports(cfg, p.dtype):
+            raise ValueError(f"config {cfg.name!r} / dtype {p.dtype} is not supported by the fused engine")
+        self.model, self.cfg = model, cfg
+        self.device = p.device
+        self.is_starter = isinstance(model, StarterNode)
+        self.n_layers = model.n_local_layers
+        self.n_slots = n_slots
+        self.S = int(max_seq_length or model.max_seq_length)
+        if self.S != model.max_seq_length:
+            model.max_seq_length = self.S
+        self.sampling = sampling or SamplingParams()
+        self.use_pdl, self.ctas_per_sm, self.wait_max_cycles = use_pdl, ctas_per_sm, wait_max_cycles
+        C, dev = cfg.n_embd, self.device
+        with torch.cuda.device(dev):
+            model.cos, model.sin = model.cos.to(dev, torch.float32).contiguous(), model.sin.to(dev, torch.float32).contiguous()
+            if model.kv_pool is None or model.kv_pool.n_slots < n_slots or model.kv_pool.max_seq_length != self.S:
+                model.kv_pool = None
+                model.set_kv_cache(n_slots, device=dev, dtype=torch.bfloat16)
+            self.kv = model.kv_pool.data  # [L, n_slots, 2, G, S, hs]
+            i32 = dict(dtype=torch.int32, device=dev)
+            bf = dict(dtype=torch.bfloat16, device=dev)
+            # hop-visible region: hidden_in [n_slots, C] bf16 | flags [n_slots] i32 (64B aligned)
+            hid_bytes = n_slots * C * 2
+            self._flag_off = (hid_bytes + 255) // 256 * 256
+            self.raw = RawBuffer(self._flag_off + max(256, n_slots * 4), dev) if exportable else None
+            if self.raw is not None:
+                self.hidden_in = self.raw.view(0, (n_slots, C), torch.bfloat16)
+                self.flags = self.raw.view(self._flag_off, (n_slots,), torch.int32)
+            else:
+                self.hidden_in = torch.zeros(n_slots, C, **bf)
+                self.flags = torch.zeros(n_slots, **i32)
+            self.out_local = torch.zeros(n_slots, C, **bf)  # host-driven mode: stage output lands here
+            self.ctx = torch.zeros(ops.CTX_INTS, **i32)
+            self.ctx_ring = torch.zeros(4096, ops.CTX_INTS, dtype=torch.int32).pin_memory()
+            self._ring_i = 0
+            self.state = torch.zeros(4, **i32)
+            self.pos_arr = torch.zeros(n_slots, **i32)
+            self.status = torch.zeros(1, **i32)
+            self.done_ctr = torch.zeros(1, **i32)
+            self.xa = torch.zeros(C, **bf)
+            self.xb = torch.zeros(C, **bf)
+            self.q = torch.zeros(cfg.n_head * cfg.head_size, **bf)
+            self.y_attn = torch.zeros(cfg.n_head * cfg.head_size, **bf)
+            self.h_mlp = torch.zeros(cfg.intermediate_size, **bf)
+            sms = torch.cuda.get_device_properties(dev).multi_processor_count
+            self.n_split = max(1, min(64, (2 * sms) // max(1, cfg.n_query_groups)))
+            self.part = torch.zeros(cfg.n_head * self.n_split * (cfg.head_size + 2), dtype=torch.float32, device=dev)
+            if self.is_starter:
+                self.logits = torch.zeros(cfg.padded_vocab_size, dtype=torch.float32, device=dev)
+                self.tokens = torch.zeros(n_slots, self.S + 1, **i32)
+                self.last_token = torch.zeros(n_slots, **i32)
+        self.hop_self = HopTarget(self.hidden_in.data_ptr(), self.flags.data_ptr())
+        self._graphs: Dict[Any, ops.CudaGraph] = {}
+        self._check_weights()
+
+    # ---- weights ---------------------------------------------------------------------------------
+    def _check_weights(self) -> None:
+        for n, p in self.model.named_parameters():
+            if p.dtype != torch.bfloat16 or not p.is_contiguous() or p.device != self.device:
+                raise ValueError(f"parameter {n}: need contiguous bf16 on {self.device}")
+
+    def _gate_act(self) -> str:
+        if self.cfg.mlp_class_name == "LLaMAMLP":
+            return "silu_gate"
+        return "gelu_tanh_gate" if self.cfg.gelu_approximate == "tanh" else "gelu_erf_gate"
+
+    # ---- kernel sequences ------------------------------------------------------------------------
+    def enqueue_head(self, wait: bool) -> None:
+        """starter: final RMSNorm + lm_head on ``hidden_in[slot]`` → fp32 logits."""
+        m, cfg = self.model, self.cfg
+        ops.linear_decode(
+            m.lm_head.weight, self.hidden_in, self.logits, self.ctx, bias=m.lm_head.bias,
+            norm_w=m.transformer.ln_f.weight, eps=cfg.norm_eps, unit_offset=cfg.unit_offset_norm,
+            x_slot_stride=cfg.n_embd, wait_flag=self.flags.data_ptr() if wait else None,
+            status=self.status.data_ptr(), wait_max_cycles=self.wait_max_cycles, ctas_per_sm=self.ctas_per_sm,
+            use_pdl=self.use_pdl)
+
+    def enqueue_sample(self) -> None:
+        s = self.sampling
+        greedy = not (s.temperature > 0.0 or s.top_p > 0.0)
+        ops.sample(self.logits, self.tokens, self.ctx, vocab=self.cfg.padded_vocab_size, top_k=s.top_k,
+                   temperature=s.temperature, greedy=greedy, seed=s.seed if s.seed is not None else 0x5EED,
+                   tok_slot_stride=self.tokens.shape[1], last_token=self.last_token, use_pdl=self.use_pdl)
+
+    def enqueue_embed(self, from_tokens: bool) -> None:
+        m, cfg = self.model, self.cfg
+        ops.embed(m.transformer.wte.weight, self.xa, self.ctx, tokens=self.tokens if from_tokens else None,
+                  tok_slot_stride=self.tokens.shape[1], scale=float(cfg.n_embd ** 0.5) if cfg.scale_embeddings else 1.0,
+                  use_pdl=self.use_pdl)
+
+    def enqueue_blocks(self, hop: Optional[HopTarget], wait_input: bool) -> None:
+        """All local blocks for one token.  Input residual: ``xa`` on the starter (embedding),
+        ``hidden_in[slot]`` on a secondary.  Output: ``hop`` target (+flag) or ``out_local[slot]``."""
+        cfg, C = self.cfg, self.cfg.n_embd
+        x_in, x_in_stride = (self.xa, 0) if self.is_starter else (self.hidden_in, C)
+        common = dict(ctas_per_sm=self.ctas_per_sm, use_pdl=self.use_pdl)
+        for li, blk in enumerate(self.model.transformer.h):
+            first, last = li == 0, li == self.n_layers - 1
+            kv_layer = self.kv[li]
+            ops.qkv_decode(
+                blk.attn.attn.weight, x_in, self.model.cos, self.model.sin, self.q, kv_layer, self.ctx,
+                n_head=cfg.n_head, n_groups=cfg.n_query_groups, head_size=cfg.head_size,
+                rope_n_elem=cfg.rope_n_elem, max_seq=self.S, bias=blk.attn.attn.bias, norm_w=blk.norm_1.weight,
+                eps=cfg.norm_eps, unit_offset=cfg.unit_offset_norm, x_slot_stride=x_in_stride,
+                wait_flag=self.flags.data_ptr() if (first and wait_input and not self.is_starter) else None,
+                status=self.status.data_ptr(), wait_max_cycles=self.wait_max_cycles, **common)
+            ops.attn_decode(self.q, kv_layer, self.y_attn, self.part, self.ctx, n_head=cfg.n_head,
+                            n_groups=cfg.n_query_groups, head_size=cfg.head_size, max_seq=self.S,
+                            n_split=self.n_split, use_pdl=self.use_pdl)
+            ops.linear_decode(blk.attn.proj.weight, self.y_attn, self.xb, self.ctx, bias=blk.attn.proj.bias,
+                              residual=x_in, res_slot_stride=x_in_stride, **common)
+            ops.linear_decode(blk.mlp.fc_1.weight, self.xb, self.h_mlp, self.ctx, W2=blk.mlp.fc_2.weight,
+                              bias=blk.mlp.fc_1.bias, bias2=blk.mlp.fc_2.bias, norm_w=blk.norm_2.weight,
+                              eps=cfg.norm_eps, unit_offset=cfg.unit_offset_norm, act=self._gate_act(), **common)
+            if not last:
+                ops.linear_decode(blk.mlp.proj.weight, self.h_mlp, self.xa, self.ctx, bias=blk.mlp.proj.bias,
+                                  residual=self.xb, **common)
+                x_in, x_in_stride = self.xa, 0
+            elif hop is not None:
+                ops.linear_decode(blk.mlp.proj.weight, self.h_mlp, None, self.ctx, bias=blk.mlp.proj.bias,
+                                  residual=self.xb, y_ptr=hop.hidden_ptr, y_slot_stride=C,
+                                  signal_flag=hop.flag_ptr, done_ctr=self.done_ctr.data_ptr(), **common)
+            else:
+                ops.linear_decode(blk.mlp.proj.weight, self.h_mlp, self.out_local, self.ctx, bias=blk.mlp.proj.bias,
+                                  residual=self.xb, y_slot_stride=C, **common)
+
+    # ---- graphs ------------------------------------------------------------------------------------
+    def graph(self, key: Any, builder: Any, warm: bool = True) -> ops.CudaGraph:
+        """Capture ``builder()`` once per ``key``.  ``warm`` runs it eagerly first (loads the
+        kernels, sets smem attributes); graphs with hop waits/signals must pass ``warm=False``
+        (their side effects are not idempotent) after :meth:`warmup`."""
+        g = self._graphs.get(key)
+        if g is None:
+            with torch.cuda.device(self.device):
+                if warm:
+                    builder()
+                torch.cuda.current_stream().synchronize()
+                g = ops.CudaGraph()
+                with g:
+                    builder()
+            self._graphs[key] = g
+        return g
+
+    def warmup(self) -> None:
+        """Launch every kernel of the step once with hops disabled (slot 0, position 0)."""
+        with torch.cuda.device(self.device):
+            self.set_ctx(0, 0)
+            if self.is_starter:
+                self.enqueue_head(wait=False)
+                self.enqueue_sample()
+                self.enqueue_embed(from_tokens=True)
+            self.enqueue_blocks(None, False)
+            if self.is_starter:
+                self.tokens.zero_()
+                self.last_token.zero_()
+            self.kv[:, 0, :, :, 0].zero_()
+            torch.cuda.current_stream().synchronize()
+
+    def set_ctx(self, slot: int, pos: int, wait: int = 0, signal: int = 0, token: int = 0) -> None:
+        """Host-driven step descriptor: 32 bytes, pinned host ring entry → device (async).  The
+        ring keeps an entry untouched until 4096 later steps were issued, far beyond what can be
+        in flight, so the async copy never races with the host."""
+        h = self.ctx_ring[self._ring_i]
+        self._ring_i = (self._ring_i + 1) % self.ctx_ring.shape[0]
+        h[ops.CTX_SLOT], h[ops.CTX_POS], h[ops.CTX_WAIT], h[ops.CTX_SIGNAL], h[ops.CTX_TOKEN] = slot, pos, wait, signal, token
+        self.ctx.copy_(h, non_blocking=True)
+
+
+class FusedStageRunner(StageRunner):
+    """Host-driven adapter: prefill on the eager module, decode through the fused kernels."""
+
+    def __init__(self, model: StageModule, max_seq_length: Optional[int] = None, n_slots: int = 8,
+                 sampling: Optional[SamplingParams] = None, use_graphs: bool = True) -> None:
+        self.stage = FusedStage(model, n_slots=n_slots, max_seq_length=max_seq_length, sampling=sampling)
+        self.model = model.eval()
+        self.role = model.role
+        self.device = self.stage.device
+        self.dtype = torch.bfloat16
+        self.slots: Dict[int, int] = {}
+        self.use_graphs = use_graphs
+        self.n_launches = 0
+
+    def begin_sample(self, sample_id: int) -> None:
+        if sample_id in self.slots:
+            return
+        if len(self.slots) >= self.stage.n_slots:
+            raise RuntimeError(f"stage was sized for {self.stage.n_slots} concurrent samples")
+        self.slots[sample_id] = len(self.slots)
+
+    def _run(self, key: str, builder: Any) -> None:
+        if self.use_graphs:
+            self.stage.graph(key, builder).launch()
+            self.n_launches += self.stage._graphs[key].n_nodes
+        else:
+            builder()
+
+    @torch.inference_mode()
+    def forward(self, sample_id: int, data: torch.Tensor, input_pos: torch.Tensor) -> torch.Tensor:
+        st, slot = self.stage, self.slots[sample_id]
+        T = data.size(1)
+        with torch.cuda.device(self.device):
+            if T > 1:  # prefill: eager module on the shared KV pool
+                if self.role == "starter":
+                    return self.model(data.long(), input_pos, slot=slot)
+                return self.model(data.to(self.dtype), input_pos, slot=slot)
+            pos = int(input_pos[-1])
+            if self.role == "starter":
+                st.set_ctx(slot, pos, token=int(data.reshape(-1)[-1]))
+                self._run("fwd", lambda: (st.enqueue_embed(from_tokens=False), st.enqueue_blocks(None, False)))
+            else:
+                st.hidden_in[slot].copy_(data.reshape(-1).to(self.dtype))
+                st.set_ctx(slot, pos)
+                self._run("fwd", lambda: st.enqueue_blocks(None, False))
+            return st.out_local[slot].view(1, 1, -1).clone()
+
+    @torch.inference_mode()
+    def head(self, hidden: torch.Tensor) -> torch.Tensor:
+        st = self.stage
+        with torch.cuda.device(self.device):
+            st.hidden_in[0].copy_(hidden[0, -1].to(self.dtype))
+            st.set_ctx(0, 0)
+            self._run("head", lambda: st.enqueue_head(wait=False))
+            return st.logits.view(1, 1, -1).clone()

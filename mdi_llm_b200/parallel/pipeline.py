@@ -1,0 +1,287 @@
+"""Device-driven recurrent pipeline over NVLink: the product path.
+
+One process per GPU (``torch.distributed``/NCCL for control-plane collectives only).  Every rank
+owns one pipeline stage as a :class:`~.engine.FusedStage`; the ring
+``starter → sec0 → … → starter`` is closed with *peer-mapped* buffers (CUDA IPC):
+
+* the last down-projection kernel of stage *i* stores its output row straight into stage
+  *i+1*'s ``hidden_in[slot]`` through NVLink and then publishes ``flags[slot]`` with a
+  system-scope release (``hop_signal`` in ``csrc/common.cuh``);
+* the first kernel of stage *i+1*'s step (QKV projection; ``lm_head`` on the starter for the
+  wrap-around hop) prefetches its weights, then acquires that flag and reads the row
+  (``hop_wait``) — no socket, no pickle, no NCCL call, no host on the path
+  (reference: ``connections.py:325-353`` TX, ``:186-214`` RX, ``gptserver.py:924,1082`` H2D).
+
+The schedule is the reference's recurrent pipeline made static: with FIFO queues and a ring the
+order in which samples reach a stage is always ``0,1,…,n-1,0,1,…`` (gptserver.py:864-868,
+912-1001), so each stage simply replays "serve slot ``t mod n``" — slot/position/flag sequence
+numbers are derived on the device by ``advance_step``.  A sample owns one slot per stage buffer
+and is in exactly one place at a time, hence no back-pressure protocol is needed.
+
+``mode="host"`` keeps the same kernels and hops but the host feeds each step descriptor from
+pinned memory and reads every sampled token back (the end-to-end/streaming mode).
+"""
+from __future__ import annotations
+
+import ctypes
+import time
+from typing import Any, Callable, Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from .. import ops
+from ..models.stage import StageModule
+from .engine import FusedStage, HopTarget, RawBuffer
+from .scheduler import SamplingParams
+
+__all__ = ["DevicePipeline", "connect_ring_local"]
+
+
+class DevicePipeline:
+    def __init__(self, model: StageModule, rank: int, world: int, n_samples: int, max_seq_length: int,
+                 sampling: Optional[SamplingParams] = None, max_prompt_len: int = 0, use_pdl: bool = True,
+                 ctas_per_sm: int = 4, wait_max_cycles: int = 20_000_000_000, exportable: Optional[bool] = None) -> None:
+        self.rank, self.world, self.n = rank, world, n_samples
+        self.is_starter, self.is_last = rank == 0, rank == world - 1
+        exportable = (world > 1) if exportable is None else exportable
+        self.stage = FusedStage(model, n_slots=n_samples, max_seq_length=max_seq_length, sampling=sampling,
+                                use_pdl=use_pdl, ctas_per_sm=ctas_per_sm, wait_max_cycles=wait_max_cycles,
+                                exportable=exportable)
+        self.model = model.eval()
+        self.device = self.stage.device
+        self.C = model.config.n_embd
+        self.max_prompt_len = int(max_prompt_len or max_seq_length)
+        # prefill hop payload (T x C per sample) lands here on secondaries
+        self.prefill_raw: Optional[RawBuffer] = None
+        self.prefill_in: Optional[torch.Tensor] = None
+        if world > 1 and not self.is_starter:
+            nbytes = n_samples * self.max_prompt_len * self.C * 2
+            if exportable:
+                self.prefill_raw = RawBuffer(nbytes, self.device)
+                self.prefill_in = self.prefill_raw.view(0, (n_samples, self.max_prompt_len, self.C), torch.bfloat16)
+            else:
+                self.prefill_in = torch.zeros(n_samples, self.max_prompt_len, self.C, dtype=torch.bfloat16, device=self.device)
+        self.next_hop: HopTarget = self.stage.hop_self  # world == 1: the ring closes on myself
+        self.next_prefill_ptr: int = 0
+        self._opened: List[int] = []
+        self.prompt_lens: List[int] = []
+        self.round = 1
+        self.max_new = 0
+        self.n_graph_launches = 0
+
+    # ---- ring wiring ------------------------------------------------------------------------------
+    def export_handles(self) -> Dict[str, Any]:
+        st = self.stage
+        return {"rank": self.rank, "hidden": st.raw.handle if st.raw else None, "flag_off": st._flag_off,
+                "prefill": self.prefill_raw.handle if self.prefill_raw else None,
+                "hidden_ptr": st.hidden_in.data_ptr(), "flag_ptr": st.flags.data_ptr(),
+                "prefill_ptr": self.prefill_in.data_ptr() if self.prefill_in is not None else 0,
+                "device": self.device.index}
+
+    def connect_ipc(self, nxt: Dict[str, Any]) -> None:
+        """Open the next stage's exported buffers (other process)."""
+        lib = ops.lib()
+        with torch.cuda.device(self.device):
+            p = ctypes.c_void_p()
+            ops.check(lib.mdi_p2p_open(nxt["hidden"], ctypes.byref(p)), "open next hidden_in")
+            self._opened.append(int(p.value))
+            self.next_hop = HopTarget(int(p.value), int(p.value) + nxt["flag_off"])
+            if nxt.get("prefill"):
+                q = ctypes.c_void_p()
+                ops.check(lib.mdi_p2p_open(nxt["prefill"], ctypes.byref(q)), "open next prefill_in")
+                self._opened.append(int(q.value))
+                self.next_prefill_ptr = int(q.value)
+
+    def connect_distributed(self, group: Any = None) -> None:
+        """All-gather the IPC handles over the control plane and open the next rank's."""
+        import torch.distributed as dist
+
+        if self.world == 1:
+            return
+        infos: List[Any] = [None] * self.world
+        dist.all_gather_object(infos, self.export_handles(), group=group)
+        self.connect_ipc(infos[(self.rank + 1) % self.world])
+        dist.barrier(group=group)
+
+    def close(self) -> None:
+        for p in self._opened:
+            ops.lib().mdi_p2p_close(p)
+        self._opened.clear()
+
+    # ---- generation phases ------------------------------------------------------------------------
+    def prepare(self, prompts: Sequence[torch.Tensor], max_new_tokens: int) -> None:
+        """Reset per-generation state.  ``prompts`` (token ids) must be known on every rank
+        (at least their lengths); call on all ranks, then synchronise + barrier before
+        :meth:`prefill`."""
+        st = self.stage
+        if len(prompts) != self.n:
+            raise ValueError(f"pipeline was built for {self.n} samples, got {len(prompts)}")
+        self.prompt_lens = [int(p.numel()) for p in prompts]
+        if any(t + max_new_tokens > st.S for t in self.prompt_lens):
+            raise ValueError(f"Cannot generate {max_new_tokens} tokens - would exceed block size!")
+        if max(self.prompt_lens) > self.max_prompt_len and self.world > 1:
+            raise ValueError("prompt longer than the prefill hop buffer")
+        self.max_new = max_new_tokens
+        self.round = 1
+        with torch.cuda.device(self.device):
+            if not st._graphs:
+                st.warmup()
+            st.flags.zero_()
+            st.status.zero_()
+            st.done_ctr.zero_()
+            st.state.copy_(torch.tensor([0, 1, 0, 0], dtype=torch.int32))
+            st.pos_arr.copy_(torch.tensor(self.prompt_lens, dtype=torch.int32))
+            if self.is_starter:
+                st.tokens.zero_()
+                for i, p in enumerate(prompts):
+                    st.tokens[i, : p.numel()].copy_(p.to(torch.int32))
+            self.prompts = [p.to(self.device) for p in prompts] if self.is_starter else None
+            torch.cuda.current_stream().synchronize()
+
+    def _copy_to(self, src: torch.Tensor, dst_ptr: int) -> None:
+        ops.check(ops.lib().mdi_copy_bytes(src.data_ptr(), dst_ptr, src.numel() * src.element_size(), ops.stream_ptr()),
+                  "hop copy")
+
+    @torch.inference_mode()
+    def prefill(self) -> None:
+        """Round 0: every sample's prompt through all stages (eager blocks; hop = peer copy +
+        flag).  The last stage returns only the final row to the starter."""
+        st, lib = self.stage, ops.lib()
+        with torch.cuda.device(self.device):
+            for slot in range(self.n):
+                T = self.prompt_lens[slot]
+                pos = torch.arange(T, device=self.device)
+                st.set_ctx(slot, T - 1, wait=1, signal=1)
+                if self.is_starter:
+                    hidden = self.model(self.prompts[slot].view(1, -1).long(), pos, slot=slot)
+                else:
+                    ops.check(lib.mdi_wait_flag(st.flags.data_ptr(), st.ctx.data_ptr(), st.status.data_ptr(),
+                                                st.wait_max_cycles, ops.stream_ptr()), "wait prefill")
+                    hidden = self.model(self.prefill_in[slot, :T].unsqueeze(0), pos, slot=slot)
+                hidden = hidden.to(torch.bfloat16).contiguous()
+                if self.is_last:  # wrap-around: only the last position feeds lm_head
+                    self._copy_to(hidden[0, -1], self.next_hop.hidden_ptr + slot * self.C * 2)
+                else:
+                    self._copy_to(hidden[0], self.next_prefill_ptr + slot * self.max_prompt_len * self.C * 2)
+                ops.check(lib.mdi_set_flag(self.next_hop.flag_ptr, st.ctx.data_ptr(), ops.stream_ptr()), "signal prefill")
+
+    # graph builders ---------------------------------------------------------------------------------
+    def _g_full(self, dev_ctx: bool) -> ops.CudaGraph:
+        st = self.stage
+
+        def build() -> None:
+            if dev_ctx:
+                ops.advance_step(st.ctx, st.state, st.pos_arr, self.n, self.is_starter, use_pdl=False)
+            if self.is_starter:
+                st.enqueue_head(wait=True)
+                st.enqueue_sample()
+                st.enqueue_embed(from_tokens=True)
+            st.enqueue_blocks(self.next_hop, wait_input=True)
+
+        return st.graph(("full", dev_ctx, self.next_hop.hidden_ptr), build, warm=False)
+
+    def _g_head(self, dev_ctx: bool) -> ops.CudaGraph:
+        st = self.stage
+
+        def build() -> None:
+            if dev_ctx:
+                ops.advance_step(st.ctx, st.state, st.pos_arr, self.n, True, use_pdl=False)
+            st.enqueue_head(wait=True)
+            st.enqueue_sample()
+
+        return st.graph(("head", dev_ctx), build, warm=False)
+
+    def decode_rounds(self, n_rounds: int) -> int:
+        """Enqueue ``n_rounds`` decode rounds (every sample advances one token per round) in
+        device-driven mode.  Returns the number of graph launches issued."""
+        st = self.stage
+        launched = 0
+        with torch.cuda.device(self.device):
+            for _ in range(n_rounds):
+                r = self.round
+                if r > self.max_new:
+                    break
+                final = r == self.max_new
+                if final:
+                    if self.is_starter:
+                        self._g_head(True).launch(self.n)
+                        launched += self.n
+                else:
+                    self._g_full(True).launch(self.n)
+                    launched += self.n
+                self.round += 1
+        self.n_graph_launches += launched
+        return launched
+
+    def decode_rounds_host(self, n_rounds: int, on_token: Optional[Callable[[int, int, int], None]] = None) -> Tuple[int, int, int]:
+        """Host-fed variant (end-to-end mode): per step the descriptor goes H2D from pinned memory
+        and, on the starter, the sampled token comes back D2H before the next step is issued.
+        Returns (launches, h2d_bytes, d2h_bytes)."""
+        st = self.stage
+        launched = h2d = d2h = 0
+        with torch.cuda.device(self.device):
+            for _ in range(n_rounds):
+                r = self.round
+                if r > self.max_new:
+                    break
+                final = r == self.max_new
+                for slot in range(self.n):
+                    pos = self.prompt_lens[slot] + r - 1
+                    st.set_ctx(slot, pos, wait=r if self.is_starter else r + 1, signal=r + 1)
+                    h2d += ops.CTX_INTS * 4
+                    if final and not self.is_starter:
+                        continue
+                    (self._g_head(False) if final else self._g_full(False)).launch()
+                    launched += 1
+                    if not self.is_starter and launched % 2048 == 0:
+                        torch.cuda.current_stream().synchronize()  # keep the pinned ctx ring ahead of the GPU
+                    if self.is_starter:
+                        tok = int(st.last_token[slot].item())  # D2H + sync: the token the user sees
+                        d2h += 4
+                        if on_token is not None:
+                            on_token(slot, pos, tok)
+                self.round += 1
+        self.n_graph_launches += launched
+        return launched, h2d, d2h
+
+    def result_tokens(self) -> Dict[int, torch.Tensor]:
+        """starter: prompt + generated ids per sample (syncs)."""
+        st = self.stage
+        assert self.is_starter
+        torch.cuda.synchronize(self.device)
+        if int(st.status.item()) != 0:
+            raise RuntimeError("hop watchdog expired: a pipeline stage stopped responding")
+        done = min(self.round - 1, self.max_new)
+        out = {}
+        for i, T in enumerate(self.prompt_lens):
+            out[i] = st.tokens[i, : T + done].to("cpu", torch.int64).view(1, -1)
+        return out
+
+    def generate(self, prompts: Sequence[torch.Tensor], max_new_tokens: int, sync: Optional[Callable[[], None]] = None,
+                 mode: str = "device") -> Optional[Dict[int, torch.Tensor]]:
+        """Whole generation on this rank.  ``sync`` = cross-rank barrier (None when world == 1)."""
+        self.prepare(prompts, max_new_tokens)
+        if sync is not None:
+            sync()
+        self.prefill()
+        if mode == "device":
+            self.decode_rounds(max_new_tokens)
+        else:
+            self.decode_rounds_host(max_new_tokens)
+        torch.cuda.synchronize(self.device)
+        out = self.result_tokens() if self.is_starter else None
+        if sync is not None:
+            sync()
+        return out
+
+
+def connect_ring_local(pipes: Sequence[DevicePipeline]) -> None:
+    """Wire pipelines that live in ONE process (one per GPU) with direct peer access."""
+    n = len(pipes)
+    lib = ops.lib()
+    for i, p in enumerate(pipes):
+        nxt = pipes[(i + 1) % n]
+        if p.device != nxt.device:
+            ops.check(lib.mdi_enable_peer(p.device.index, nxt.device.index), "enable peer access")
+        p.next_hop = HopTarget(nxt.stage.hidden_in.data_ptr(), nxt.stage.flags.data_ptr())
+        p.next_prefill_ptr = nxt.prefill_in.data_ptr() if nxt.prefill_in is not None else 0

@@ -241,3 +241,31 @@ def write_random_checkpoint(
     torch.save(random_state_dict(config, dtype=dtype, seed=seed), out / "lit_model.pth")
     config.save(out)
     return out
+
+
+def random_init_stage_(model: nn.Module, device: Union[str, torch.device], dtype: torch.dtype = torch.bfloat16,
+                       seed: int = 1234, std: float = 0.02) -> nn.Module:
+    """Materialise a meta-built stage directly on ``device`` with random weights (no checkpoint
+    I/O — benchmarks on the network-less GPU box).  Norm weights ~ 1 ± 0.1, the rest N(0, std)."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    for key, (mod, attr) in get_keys_to_submodule(model).items():
+        old = getattr(mod, attr)
+        if old.device.type != "meta":
+            continue
+        if "norm" in key or "ln_f" in key:
+            t = (1.0 + 0.1 * torch.randn(old.shape, generator=g, device=device, dtype=torch.float32))
+            if key.endswith(".bias"):
+                t = t - 1.0
+        else:
+            t = torch.randn(old.shape, generator=g, device=device, dtype=torch.float32) * std
+        setattr(mod, attr, nn.Parameter(t.to(dtype), requires_grad=False))
+    if getattr(getattr(model, "config", None), "tie_embeddings", False) and hasattr(model, "lm_head"):
+        model.lm_head.weight = model.transformer.wte.weight
+    for name, buf in list(model.named_buffers()):
+        owner = model
+        *path, leaf = name.split(".")
+        for p_ in path:
+            owner = getattr(owner, p_)
+        if buf.device.type != "meta":
+            setattr(owner, leaf, buf.to(device))
+    return model

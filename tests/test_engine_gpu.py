@@ -1,0 +1,159 @@
+"""Fused CUDA stage executor vs the eager modules on the same bf16 weights (single GPU)."""
+import threading
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _cfg(**kw):
+    from mdi_llm_b200.models.config import Config
+
+    base = dict(n_layer=4, n_embd=512, n_head=8, n_query_groups=2, intermediate_size=1024, vocab_size=2000,
+                padded_vocab_size=2048, block_size=256)
+    base.update(kw)
+    return Config.from_name("tiny-llama-1.1b", **base)
+
+
+def _stages(cfg, n_nodes, device="cuda", seed=7):
+    from mdi_llm_b200.models.partition import plan_layers, split_parameters
+    from mdi_llm_b200.models.stage import build_stage
+    from mdi_llm_b200.utils.checkpoint import materialize_stage, random_state_dict
+
+    sd = random_state_dict(cfg, dtype=torch.bfloat16, seed=seed, std=0.05)
+    full = {k: v.clone() for k, v in sd.items()}
+    if n_nodes == 1:
+        st = build_stage(cfg, "starter", cfg.n_layer, meta=True)
+        materialize_stage(st, dict(sd), device, torch.bfloat16)
+        return full, [st]
+    chunks, info = split_parameters(sd, n_nodes, plan=plan_layers(n_nodes, cfg.n_layer, cfg))
+    out = []
+    for i in range(n_nodes):
+        role = "starter" if i == 0 else f"secondary:{i - 1}"
+        st = build_stage(cfg, role, info["plan"][i], meta=True)
+        dev = device if isinstance(device, str) else device[i]
+        materialize_stage(st, chunks["starter"] if i == 0 else chunks["secondary"][i - 1], dev, torch.bfloat16)
+        out.append(st)
+    return full, out
+
+
+def _near_argmax_check(cfg, full_sd, tokens, prompt_len, tol=0.15):
+    """Every generated token must be (near-)arg-max of the eager model's teacher-forced logits."""
+    from mdi_llm_b200.models.gpt import GPT
+
+    m = GPT(cfg)
+    m.load_state_dict(full_sd)
+    m = m.cuda().eval()
+    with torch.no_grad():
+        logits = m(tokens[:, :-1].cuda()).float()[0]
+    gen = tokens[0, prompt_len:].cuda()
+    rows = logits[prompt_len - 1:]
+    chosen = rows.gather(1, gen.view(-1, 1)).squeeze(1)
+    gap = rows.max(dim=1).values - chosen
+    assert gap.max().item() <= tol, f"token not near arg-max: gaps {gap.tolist()}"
+    return (gap == 0).float().mean().item()
+
+
+@pytest.mark.parametrize("variant", ["gqa_hs64", "mha_hs128", "qpk8_bias", "gemma_like"])
+def test_fused_runner_matches_eager_hidden_and_logits(variant):
+    from mdi_llm_b200.parallel.engine import FusedStageRunner
+    from mdi_llm_b200.parallel.scheduler import EagerStageRunner
+
+    kw = {"gqa_hs64": dict(), "mha_hs128": dict(n_head=4, n_query_groups=4), "qpk8_bias": dict(n_head=8, n_query_groups=1, bias=True),
+          "gemma_like": dict(mlp_class_name="GemmaMLP", gelu_approximate="tanh", rotary_percentage=0.5)}[variant]
+    cfg = _cfg(**kw)
+    _, (st_a,) = _stages(cfg, 1)
+    _, (st_b,) = _stages(cfg, 1)
+    eager, fused = EagerStageRunner(st_a), FusedStageRunner(st_b, max_seq_length=128, n_slots=2)
+    st_a.max_seq_length = 128
+    prompt = torch.tensor([[5, 17, 900, 33, 2, 1999]], device="cuda")
+    pos = torch.arange(6, device="cuda")
+    for r in (eager, fused):
+        r.begin_sample(0)
+        r.begin_sample(1)
+    h_e, h_f = eager.forward(1, prompt, pos), fused.forward(1, prompt, pos)  # prefill (both eager ops)
+    torch.testing.assert_close(h_e.float(), h_f.float(), rtol=2e-2, atol=2e-2)
+    tok = torch.tensor([[42]], device="cuda")
+    for step in range(5):
+        p = torch.tensor([6 + step], device="cuda")
+        h_e, h_f = eager.forward(1, tok, p), fused.forward(1, tok, p)
+        assert h_f.shape == h_e.shape == (1, 1, cfg.n_embd)
+        err = (h_e.float() - h_f.float()).abs().max().item()
+        scale = h_e.float().abs().max().item()
+        assert err <= 0.03 * scale + 0.03, f"step {step}: max err {err} (scale {scale})"
+        lg_e, lg_f = eager.head(h_e).float(), fused.head(h_e).float()
+        torch.testing.assert_close(lg_f.view(-1), lg_e.view(-1), rtol=3e-2, atol=3e-2)
+        tok = lg_e.view(-1).argmax().view(1, 1)
+    assert fused.n_launches > 0
+
+
+def test_device_pipeline_single_gpu_device_and_host_modes_agree():
+    from mdi_llm_b200.parallel.pipeline import DevicePipeline
+    from mdi_llm_b200.parallel.scheduler import SamplingParams
+
+    cfg = _cfg()
+    full, (st,) = _stages(cfg, 1)
+    pipe = DevicePipeline(st, 0, 1, n_samples=3, max_seq_length=128, sampling=SamplingParams.greedy())
+    prompts = [torch.tensor([1, 50, 60, 70]), torch.tensor([1, 9]), torch.tensor([1, 1500, 3, 4, 5, 6, 7])]
+    out_dev = pipe.generate(prompts, 12, mode="device")
+    out_host = pipe.generate(prompts, 12, mode="host")
+    for i, p in enumerate(prompts):
+        assert out_dev[i].shape == (1, len(p) + 12)
+        assert out_dev[i][0, : len(p)].tolist() == p.tolist()
+        assert torch.equal(out_dev[i], out_host[i]), f"sample {i}: device- and host-driven schedules disagree"
+        _near_argmax_check(cfg, full, out_dev[i], len(p))
+    assert pipe.n_graph_launches > 0
+
+
+def test_device_pipeline_stochastic_sampling_is_seeded():
+    from mdi_llm_b200.parallel.pipeline import DevicePipeline
+    from mdi_llm_b200.parallel.scheduler import SamplingParams
+
+    cfg = _cfg()
+    _, (st,) = _stages(cfg, 1)
+    pipe = DevicePipeline(st, 0, 1, n_samples=2, max_seq_length=64, sampling=SamplingParams(temperature=0.8, top_k=50, seed=11))
+    prompts = [torch.tensor([1, 2, 3]), torch.tensor([1, 2, 3])]
+    a = pipe.generate(prompts, 10)
+    b = pipe.generate(prompts, 10)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])  # same seed -> same text
+    assert not torch.equal(a[0], a[1])  # different slots draw differently
+
+
+@pytest.mark.multigpu
+@pytest.mark.parametrize("n_stages", [2, 4])
+def test_device_pipeline_multi_gpu_one_process(n_stages):
+    """Stages on different GPUs of one process (direct peer access): fused hop over NVLink."""
+    from mdi_llm_b200.parallel.pipeline import DevicePipeline, connect_ring_local
+    from mdi_llm_b200.parallel.scheduler import SamplingParams
+
+    if torch.cuda.device_count() < n_stages:
+        pytest.skip("not enough GPUs")
+    cfg = _cfg(n_layer=6)
+    devs = [f"cuda:{i}" for i in range(n_stages)]
+    full, stages = _stages(cfg, n_stages, device=devs)
+    prompts = [torch.tensor([1, 10 + i, 20, 30 + i]) for i in range(n_stages)]
+    pipes = [DevicePipeline(st, i, n_stages, n_samples=len(prompts), max_seq_length=64, sampling=SamplingParams.greedy(),
+                            exportable=False, wait_max_cycles=4 * 10 ** 9) for i, st in enumerate(stages)]
+    connect_ring_local(pipes)
+    barrier = threading.Barrier(n_stages)
+    results, errors = {}, []
+
+    def run(p):
+        try:
+            results[p.rank] = p.generate(prompts, 8, sync=lambda: barrier.wait(timeout=60))
+        except BaseException as e:  # noqa: BLE001
+            errors.append(e)
+            barrier.abort()
+
+    threads = [threading.Thread(target=run, args=(p,)) for p in pipes]
+    [t.start() for t in threads]
+    [t.join(timeout=120) for t in threads]
+    assert not errors, errors
+    # oracle: the same model on one GPU through the same kernels
+    _, (st1,) = _stages(cfg, 1)
+    single = DevicePipeline(st1, 0, 1, n_samples=len(prompts), max_seq_length=64, sampling=SamplingParams.greedy())
+    ref = single.generate(prompts, 8)
+    for i in range(len(prompts)):
+        assert torch.equal(results[0][i], ref[i]), f"sample {i}: {results[0][i].tolist()} vs {ref[i].tolist()}"
+        _near_argmax_check(cfg, full, results[0][i], len(prompts[i]))

@@ -1,0 +1,252 @@
+"""Numerics of every sm_100a decode kernel against a plain PyTorch fp32 reference of the same op."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _ops():
+    from mdi_llm_b200 import ops
+
+    ops.require()
+    return ops
+
+
+def _ctx(ops, slot=0, pos=0, wait=0, signal=0, token=0):
+    c = torch.zeros(ops.CTX_INTS, dtype=torch.int32)
+    c[0], c[1], c[2], c[3], c[4] = slot, pos, wait, signal, token
+    return c.cuda()
+
+
+def _rmsnorm_ref(x, w, eps, unit_offset=False):
+    xf = x.float()
+    xn = (xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + eps)).to(x.dtype)
+    return xn * ((1 + w) if unit_offset else w)
+
+
+def test_library_loaded_and_device_is_blackwell():
+    ops = _ops()
+    import ctypes
+
+    sm, maj, mino, mem = ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_size_t()
+    assert ops.lib().mdi_device_info(ctypes.byref(sm), ctypes.byref(maj), ctypes.byref(mino), ctypes.byref(mem)) == 0
+    assert sm.value > 0 and maj.value >= 10, f"expected an sm_100 device, got sm_{maj.value}{mino.value}"
+
+
+@pytest.mark.parametrize("N,K", [(4096, 4096), (6144, 4096), (4096, 14336), (2048, 5632), (1000, 256), (37, 64)])
+@pytest.mark.parametrize("fused_norm", [False, True])
+def test_linear_decode_plain_and_residual(N, K, fused_norm):
+    ops = _ops()
+    torch.manual_seed(N + K)
+    W = (torch.randn(N, K, device="cuda") * 0.02).bfloat16()
+    x = torch.randn(K, device="cuda").bfloat16()
+    res = torch.randn(N, device="cuda").bfloat16()
+    bias = (torch.randn(N, device="cuda") * 0.1).bfloat16()
+    nw = (1 + 0.1 * torch.randn(K, device="cuda")).bfloat16()
+    y = torch.empty(N, device="cuda", dtype=torch.bfloat16)
+    ops.linear_decode(W, x, y, _ctx(ops), bias=bias, residual=res, norm_w=nw if fused_norm else None, eps=1e-5)
+    xin = _rmsnorm_ref(x, nw, 1e-5) if fused_norm else x
+    ref = (xin.float() @ W.float().T + bias.float()).bfloat16().float() + res.float()
+    torch.testing.assert_close(y.float(), ref, rtol=2e-2, atol=2e-2)
+    # fp32 output path (logits): rounded like a bf16 linear would be, stored as fp32
+    y32 = torch.empty(N, device="cuda", dtype=torch.float32)
+    ops.linear_decode(W, x, y32, _ctx(ops))
+    torch.testing.assert_close(y32, x.float() @ W.float().T, rtol=2e-2, atol=2e-2)
+
+
+@pytest.mark.parametrize("act,fn", [("silu_gate", torch.nn.functional.silu),
+                                    ("gelu_tanh_gate", lambda t: torch.nn.functional.gelu(t, approximate="tanh")),
+                                    ("gelu_erf_gate", torch.nn.functional.gelu)])
+def test_linear_decode_gated_mlp(act, fn):
+    ops = _ops()
+    torch.manual_seed(0)
+    N, K = 14336, 4096
+    W1 = (torch.randn(N, K, device="cuda") * 0.02).bfloat16()
+    W2 = (torch.randn(N, K, device="cuda") * 0.02).bfloat16()
+    x = torch.randn(K, device="cuda").bfloat16()
+    nw = (1 + 0.1 * torch.randn(K, device="cuda")).bfloat16()
+    y = torch.empty(N, device="cuda", dtype=torch.bfloat16)
+    ops.linear_decode(W1, x, y, _ctx(ops), W2=W2, norm_w=nw, eps=1e-5, act=act)
+    xin = _rmsnorm_ref(x, nw, 1e-5).float()
+    a, b = (xin @ W1.float().T).bfloat16(), (xin @ W2.float().T).bfloat16()
+    ref = (fn(a.float()).bfloat16() * b).float()
+    torch.testing.assert_close(y.float(), ref, rtol=3e-2, atol=3e-2)
+
+
+def test_linear_decode_slotted_pointers():
+    """x / residual / y addressed as base + slot * stride with the slot read on device."""
+    ops = _ops()
+    torch.manual_seed(1)
+    N = K = 512
+    W = (torch.randn(N, K, device="cuda") * 0.05).bfloat16()
+    xs = torch.randn(4, K, device="cuda").bfloat16()
+    ys = torch.zeros(4, N, device="cuda", dtype=torch.bfloat16)
+    ops.linear_decode(W, xs, ys, _ctx(ops, slot=2), residual=xs, x_slot_stride=K, res_slot_stride=K, y_slot_stride=N)
+    ref = (xs[2].float() @ W.float().T).bfloat16().float() + xs[2].float()
+    torch.testing.assert_close(ys[2].float(), ref, rtol=2e-2, atol=2e-2)
+    assert ys[[0, 1, 3]].abs().sum() == 0
+
+
+def _interleaved_qkv_ref(W, bias, x, cfg, cos, sin, pos):
+    """litGPT split + RoPE in fp32 on bf16-rounded projections (model.py:686-724)."""
+    H, G, hs, ne = cfg
+    qpk = H // G
+    qkv = (x.float() @ W.float().T + (bias.float() if bias is not None else 0)).bfloat16().float()
+    qkv = qkv.view(G, qpk + 2, hs)
+    q, k, v = qkv[:, :qpk].reshape(H, hs), qkv[:, qpk], qkv[:, qpk + 1]
+
+    def rope(t):
+        r = t[..., :ne]
+        half = ne // 2
+        rot = torch.cat((-r[..., half:], r[..., :half]), -1)
+        return torch.cat((r * cos[pos] + rot * sin[pos], t[..., ne:]), -1)
+
+    return rope(q).bfloat16(), rope(k).bfloat16(), v.bfloat16()
+
+
+@pytest.mark.parametrize("H,G,hs,ne,C", [(32, 8, 128, 128, 4096), (32, 4, 64, 64, 2048), (8, 8, 64, 32, 512), (4, 1, 128, 128, 512)])
+def test_qkv_decode_rope_and_kv_append(H, G, hs, ne, C):
+    ops = _ops()
+    from mdi_llm_b200.models.gpt import build_rope_cache
+
+    torch.manual_seed(H * G)
+    S, n_slots, slot, pos = 64, 3, 1, 17
+    W = (torch.randn((H + 2 * G) * hs, C, device="cuda") * 0.02).bfloat16()
+    bias = (torch.randn((H + 2 * G) * hs, device="cuda") * 0.05).bfloat16()
+    x = torch.randn(C, device="cuda").bfloat16()
+    nw = (1 + 0.1 * torch.randn(C, device="cuda")).bfloat16()
+    cos, sin = build_rope_cache(S, ne, device=torch.device("cuda"), base=500000)
+    q = torch.zeros(H * hs, device="cuda", dtype=torch.bfloat16)
+    kv = torch.zeros(n_slots, 2, G, S, hs, device="cuda", dtype=torch.bfloat16)
+    ops.qkv_decode(W, x, cos, sin, q, kv, _ctx(ops, slot=slot, pos=pos), n_head=H, n_groups=G, head_size=hs,
+                   rope_n_elem=ne, max_seq=S, bias=bias, norm_w=nw, eps=1e-5)
+    qr, kr, vr = _interleaved_qkv_ref(W, bias, _rmsnorm_ref(x, nw, 1e-5), (H, G, hs, ne), cos, sin, pos)
+    torch.testing.assert_close(q.view(H, hs).float(), qr.float(), rtol=3e-2, atol=3e-2)
+    torch.testing.assert_close(kv[slot, 0, :, pos].float(), kr.float(), rtol=3e-2, atol=3e-2)
+    torch.testing.assert_close(kv[slot, 1, :, pos].float(), vr.float(), rtol=3e-2, atol=3e-2)
+    untouched = kv.clone()
+    untouched[slot, :, :, pos] = 0
+    assert untouched.abs().sum() == 0  # nothing else in the pool was written
+
+
+@pytest.mark.parametrize("H,G,hs", [(32, 8, 128), (32, 4, 64), (8, 8, 64), (16, 1, 128), (4, 2, 128)])
+@pytest.mark.parametrize("L", [1, 31, 32, 33, 500, 2048])
+def test_attn_decode_matches_sdpa(H, G, hs, L):
+    ops = _ops()
+    torch.manual_seed(L)
+    S, n_slots, slot = 2048, 2, 1
+    q = torch.randn(H * hs, device="cuda").bfloat16()
+    kv = torch.randn(n_slots, 2, G, S, hs, device="cuda").bfloat16()
+    y = torch.zeros(H * hs, device="cuda", dtype=torch.bfloat16)
+    for n_split in (1, 5, 37):
+        part = torch.zeros(H * n_split * (hs + 2), device="cuda", dtype=torch.float32)
+        ops.attn_decode(q, kv, y, part, _ctx(ops, slot=slot, pos=L - 1), n_head=H, n_groups=G, head_size=hs,
+                        max_seq=S, n_split=n_split)
+        k = kv[slot, 0, :, :L].float().repeat_interleave(H // G, 0)
+        v = kv[slot, 1, :, :L].float().repeat_interleave(H // G, 0)
+        ref = torch.softmax((q.view(H, 1, hs).float() @ k.transpose(1, 2)) / math.sqrt(hs), -1) @ v
+        torch.testing.assert_close(y.view(H, hs).float(), ref.view(H, hs), rtol=2e-2, atol=2e-2)
+
+
+def test_embed_and_rmsnorm_rows():
+    ops = _ops()
+    torch.manual_seed(3)
+    V, C = 1000, 512
+    wte = torch.randn(V, C, device="cuda").bfloat16()
+    x = torch.zeros(2, C, device="cuda", dtype=torch.bfloat16)
+    tokens = torch.zeros(2, 16, dtype=torch.int32, device="cuda")
+    tokens[1, 5] = 777
+    ops.embed(wte, x, _ctx(ops, slot=1, pos=5), tokens=tokens, tok_slot_stride=16, x_slot_stride=C, scale=math.sqrt(C))
+    torch.testing.assert_close(x[1].float(), (wte[777].float() * math.sqrt(C)).bfloat16().float())
+    ops.embed(wte, x, _ctx(ops, slot=0, pos=0, token=42), x_slot_stride=C)
+    assert torch.equal(x[0], wte[42])
+    rows = torch.randn(7, C, device="cuda").bfloat16()
+    w = (1 + 0.1 * torch.randn(C, device="cuda")).bfloat16()
+    for unit in (False, True):
+        torch.testing.assert_close(ops.rmsnorm_rows(rows, w, 1e-5, unit).float(), _rmsnorm_ref(rows, w, 1e-5, unit).float(),
+                                   rtol=2e-2, atol=2e-2)
+
+
+def test_sample_greedy_and_topk_distribution():
+    ops = _ops()
+    torch.manual_seed(4)
+    V = 128256
+    logits = torch.randn(V, device="cuda")
+    logits[[5, 77, 4000, 100000]] = torch.tensor([9.0, 9.5, 9.25, 9.5], device="cuda")
+    tokens = torch.zeros(2, 64, dtype=torch.int32, device="cuda")
+    last = torch.zeros(2, dtype=torch.int32, device="cuda")
+    ops.sample(logits, tokens, _ctx(ops, slot=1, pos=3), vocab=V, top_k=None, temperature=0.0, greedy=True, seed=0,
+               tok_slot_stride=64, last_token=last)
+    assert tokens[1, 3].item() == 77 and last[1].item() == 77  # first arg-max on ties, like torch.argmax
+    # top-k = 3 at T = 0.5: only {77, 100000, 4000} can appear, with softmax probabilities
+    counts = {}
+    n_draws = 3000
+    for i in range(n_draws):
+        ops.sample(logits, tokens, _ctx(ops, slot=0, pos=i % 64), vocab=V, top_k=3, temperature=0.5, greedy=False,
+                   seed=1234 + i * 7919, tok_slot_stride=64)
+        t = tokens[0, i % 64].item()
+        counts[t] = counts.get(t, 0) + 1
+    assert set(counts) <= {77, 100000, 4000}
+    p = torch.softmax(torch.tensor([9.5, 9.5, 9.25]) / 0.5, 0)
+    for tok, pi in zip((77, 100000, 4000), p.tolist()):
+        assert abs(counts.get(tok, 0) / n_draws - pi) < 0.04
+    # same (seed, slot, pos) -> same token
+    ops.sample(logits, tokens, _ctx(ops, slot=0, pos=1), vocab=V, top_k=200, temperature=0.8, greedy=False, seed=99,
+               tok_slot_stride=64)
+    a = tokens[0, 1].item()
+    ops.sample(logits, tokens, _ctx(ops, slot=0, pos=1), vocab=V, top_k=200, temperature=0.8, greedy=False, seed=99,
+               tok_slot_stride=64)
+    assert tokens[0, 1].item() == a
+    top200 = set(torch.topk(logits, 200).indices.tolist())
+    assert a in top200
+
+
+def test_hop_flag_wait_and_signal_same_device():
+    """Producer kernel publishes flag[slot] = ctx.signal after its stores; consumer waits for it."""
+    ops = _ops()
+    N = K = 256
+    W = torch.eye(N, device="cuda").bfloat16()
+    x = torch.randn(K, device="cuda").bfloat16()
+    inbox = torch.zeros(4, N, device="cuda", dtype=torch.bfloat16)
+    flags = torch.zeros(4, dtype=torch.int32, device="cuda")
+    done = torch.zeros(1, dtype=torch.int32, device="cuda")
+    status = torch.zeros(1, dtype=torch.int32, device="cuda")
+    ctx = _ctx(ops, slot=3, wait=7, signal=7)
+    ops.linear_decode(W, x, None, ctx, y_ptr=inbox.data_ptr(), y_slot_stride=N, signal_flag=flags.data_ptr(),
+                      done_ctr=done.data_ptr())
+    y = torch.zeros(N, device="cuda", dtype=torch.bfloat16)
+    ops.linear_decode(W, inbox, y, ctx, x_slot_stride=N, wait_flag=flags.data_ptr(), status=status.data_ptr(),
+                      wait_max_cycles=10 ** 9)
+    torch.cuda.synchronize()
+    assert flags.tolist() == [0, 0, 0, 7] and done.item() == 0 and status.item() == 0
+    assert torch.equal(y, x)
+    # watchdog: waiting for a value that never comes sets the status word instead of hanging
+    ctx2 = _ctx(ops, slot=0, wait=1)
+    ops.linear_decode(W, inbox, y, ctx2, x_slot_stride=N, wait_flag=flags.data_ptr(), status=status.data_ptr(),
+                      wait_max_cycles=2_000_000)
+    torch.cuda.synchronize()
+    assert status.item() == 1
+
+
+def test_cuda_graph_capture_and_replay():
+    ops = _ops()
+    N = K = 1024
+    W = (torch.randn(N, K, device="cuda") * 0.03).bfloat16()
+    x = torch.randn(K, device="cuda").bfloat16()
+    y = torch.zeros(N, device="cuda", dtype=torch.bfloat16)
+    ctx = _ctx(ops)
+    ops.linear_decode(W, x, y, ctx, use_pdl=True)
+    torch.cuda.synchronize()
+    g = ops.CudaGraph()
+    with g:
+        ops.linear_decode(W, x, y, ctx, use_pdl=True)
+        ops.linear_decode(W, y, x, ctx, use_pdl=True)
+    assert g.n_nodes == 2
+    x0 = x.clone()
+    g.launch(1)
+    torch.cuda.synchronize()
+    y_ref = (x0.float() @ W.float().T).bfloat16()
+    torch.testing.assert_close(y.float(), y_ref.float(), rtol=2e-2, atol=2e-2)
+    torch.testing.assert_close(x.float(), (y_ref.float() @ W.float().T).bfloat16().float(), rtol=3e-2, atol=3e-2)
