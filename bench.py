@@ -99,6 +99,7 @@ def parse_args() -> argparse.Namespace:
     ap.add_argument("--partition", default="balanced", choices=["auto", "table", "balanced"])
     ap.add_argument("--no-pdl", action="store_true")
     ap.add_argument("--ctas-per-sm", type=int, default=4)
+    ap.add_argument("--variant", type=int, default=-1, help="decode linear path: 0 LDG, 1 bulk-copy x4 stages, 2 bulk-copy x2")
     ap.add_argument("--temperature", type=float, default=0.8)
     ap.add_argument("--top-k", type=int, default=200)
     ap.add_argument("--tiny", action="store_true", help="tiny model (CI smoke of the harness; NOT a valid bench number)")
@@ -135,6 +136,10 @@ def run_ours(args: argparse.Namespace) -> Dict[str, Any]:
             dist.barrier()
             torch.cuda.synchronize(device)
 
+    if args.variant >= 0:
+        from mdi_llm_b200 import ops as _ops
+
+        _ops.set_linear_variant(args.variant)
     if args.tiny:
         cfg = Config.from_name("tiny-llama-1.1b", n_layer=8, n_embd=512, n_head=8, n_query_groups=2,
                                intermediate_size=1024, vocab_size=2000, padded_vocab_size=2048, block_size=2048)
@@ -207,6 +212,7 @@ def run_ours(args: argparse.Namespace) -> Dict[str, Any]:
                    "prompt_len": args.prompt_len, "parallelism": f"pp{world} recurrent pipeline, plan {plan}",
                    "tokens_per_step": n_samples, "l2_policy": "inputs (stage weights) larger than L2, no flush",
                    "sampling": {"temperature": args.temperature, "top_k": args.top_k}, "pdl": not args.no_pdl,
+                   "linear_variant": args.variant, "ctas_per_sm": args.ctas_per_sm,
                    "hop": "fused P2P store + flag (NVLink)" if world > 1 else "local (standalone ring)",
                    "timing": "CUDA events, max over ranks"},
         "clocks": clocks,

@@ -38,9 +38,11 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.mdi_error_string.restype = c_char_p
     lib.mdi_error_string.argtypes = [i32]
     lib.mdi_linear_decode.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, i32, i32, f32, i32, i32, i32,
-                                      vp, vp, i64, vp, vp, i32, i32, vp]
+                                      vp, vp, i64, vp, vp, i32, i32, i32, vp]
     lib.mdi_qkv_decode.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, i32, i32, i32, f32, i32,
-                                   vp, vp, i64, i32, i32, vp]
+                                   vp, vp, i64, i32, i32, i32, vp]
+    lib.mdi_set_linear_variant.argtypes = [i32]
+    lib.mdi_get_linear_variant.restype = i32
     lib.mdi_attn_decode.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]
     lib.mdi_embed.argtypes = [vp, vp, vp, i64, vp, vp, i64, i32, f32, i32, vp]
     lib.mdi_rmsnorm_rows.argtypes = [vp, vp, vp, i32, i32, f32, i32, vp]
@@ -87,6 +89,12 @@ def lib() -> ctypes.CDLL:
         raise OpsError(f"cannot load {_build.LIB}: {e}") from e
 
 
+def set_linear_variant(v: int) -> None:
+    """Default weight-streaming path of the decode linears: 0 = LDG register streaming,
+    1 = bulk-copy (TMA engine) ring with 4 stages / 1 CTA per SM, 2 = bulk-copy ring with 2 stages."""
+    lib().mdi_set_linear_variant(int(v))
+
+
 def available() -> bool:
     """True when CUDA is present *and* the library loads.  Raises on a CUDA box whose library is
     broken (no silent eager fallback on the GPU)."""
@@ -131,7 +139,7 @@ def linear_decode(
     unit_offset: bool = False, act: str = "none", x_slot_stride: int = 0, res_slot_stride: int = 0,
     y_slot_stride: int = 0, wait_flag: Optional[int] = None, status: Optional[int] = None, wait_max_cycles: int = 0,
     signal_flag: Optional[int] = None, done_ctr: Optional[int] = None, ctas_per_sm: int = 4, use_pdl: bool = False,
-    y_ptr: Optional[int] = None, residual_ptr: Optional[int] = None, x_ptr: Optional[int] = None,
+    y_ptr: Optional[int] = None, residual_ptr: Optional[int] = None, x_ptr: Optional[int] = None, variant: int = -1,
 ) -> None:
     """``y = epilogue(W @ norm?(x))`` for one token.  ``*_ptr`` overrides let the output /
     residual / input live in peer-mapped (other GPU) memory that has no torch tensor."""
@@ -142,7 +150,7 @@ def linear_decode(
         ptr(W), ptr(W2), ptr(bias), ptr(bias2), x_ptr if x_ptr is not None else ptr(x), ptr(norm_w),
         residual_ptr if residual_ptr is not None else ptr(residual), y_ptr if y_ptr is not None else ptr(y),
         ptr(ctx), x_slot_stride, res_slot_stride, y_slot_stride, N, K, eps, int(unit_offset), ACT[act], out_fp32,
-        wait_flag, status, wait_max_cycles, signal_flag, done_ctr, ctas_per_sm, int(use_pdl), stream_ptr()),
+        wait_flag, status, wait_max_cycles, signal_flag, done_ctr, ctas_per_sm, int(use_pdl), variant, stream_ptr()),
         "linear_decode")
 
 
@@ -152,6 +160,7 @@ def qkv_decode(
     bias: Optional[torch.Tensor] = None, norm_w: Optional[torch.Tensor] = None, eps: float = 1e-5,
     unit_offset: bool = False, x_slot_stride: int = 0, wait_flag: Optional[int] = None, status: Optional[int] = None,
     wait_max_cycles: int = 0, ctas_per_sm: int = 4, use_pdl: bool = False, x_ptr: Optional[int] = None,
+    variant: int = -1,
 ) -> None:
     _bf16(W, "W")
     if cos.dtype != torch.float32 or sin.dtype != torch.float32:
@@ -159,7 +168,8 @@ def qkv_decode(
     check(lib().mdi_qkv_decode(
         ptr(W), ptr(bias), x_ptr if x_ptr is not None else ptr(x), ptr(norm_w), ptr(cos), ptr(sin), ptr(q_out),
         ptr(kv_layer), ptr(ctx), x_slot_stride, W.shape[1], n_head, n_groups, head_size, rope_n_elem, max_seq, eps,
-        int(unit_offset), wait_flag, status, wait_max_cycles, ctas_per_sm, int(use_pdl), stream_ptr()), "qkv_decode")
+        int(unit_offset), wait_flag, status, wait_max_cycles, ctas_per_sm, int(use_pdl), variant, stream_ptr()),
+        "qkv_decode")
 
 
 def attn_decode(q: torch.Tensor, kv_layer: torch.Tensor, y: torch.Tensor, part: torch.Tensor, ctx: torch.Tensor, *,

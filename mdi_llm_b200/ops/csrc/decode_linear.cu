@@ -120,12 +120,13 @@ __device__ __forceinline__ float silu(float x) { return x / (1.f + __expf(-x)); 
 
 enum Act { ACT_NONE = 0, ACT_SILU_GATE = 1, ACT_GELU_TANH_GATE = 2, ACT_GELU_ERF_GATE = 3, ACT_GELU_TANH = 4, ACT_GELU_ERF = 5 };
 
-struct LinearArgs {
-  const bf16* W;         // [N, K]
+// One argument block for every weight-streaming decode linear (plain / gated / QKV).
+struct StreamArgs {
+  const bf16* W;         // [N, K]   (QKV: [(H + 2G) * hs, K], litGPT group-interleaved rows)
   const bf16* W2;        // gated: second projection [N, K]; else null
   const bf16* bias;      // [N] or null
   const bf16* bias2;     // [N] or null
-  const bf16* x;         // input activation row(s): x + slot * x_slot_stride
+  const bf16* x;         // input activation row: x + slot * x_slot_stride
   const bf16* norm_w;    // fused RMSNorm weight [K] or null
   const bf16* residual;  // residual + slot * res_slot_stride, [N], or null
   void* y;               // output (bf16, or fp32 when out_fp32): y + slot * y_slot_stride
@@ -136,167 +137,215 @@ struct LinearArgs {
   int unit_offset;
   int act;
   int out_fp32;
-  int items_per_cta;
+  int n_items;
   HopWait wait;
   HopSignal signal;
+  // QKV-only
+  const float* cos;  // [S, n_elem]
+  const float* sin;
+  bf16* q_out;       // [H * hs]
+  bf16* kv;          // this layer's pool: [n_slots, 2, G, S, hs]
+  int n_head, n_groups, head_size, rope_n_elem, max_seq;
 };
 
-__global__ void __launch_bounds__(LIN_THREADS) linear_decode_kernel(const LinearArgs a) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+enum Mode { MODE_PLAIN = 0, MODE_GATED = 1, MODE_QKV = 2 };
+
+// item -> the two weight rows a warp streams together
+template <int MODE>
+__device__ __forceinline__ void item_rows(const StreamArgs& a, int it, const bf16*& wa, const bf16*& wb) {
+  if (MODE == MODE_GATED) {
+    wa = a.W + (size_t)it * a.K;
+    wb = a.W2 + (size_t)it * a.K;
+  } else if (MODE == MODE_PLAIN) {
+    wa = a.W + (size_t)(2 * it) * a.K;
+    wb = a.W + (size_t)min(2 * it + 1, a.N - 1) * a.K;
+  } else {
+    const int hs = a.head_size, half_hs = hs / 2, ne = a.rope_n_elem, half_ne = ne / 2;
+    const int j = it / half_hs, i = it % half_hs;
+    int ra, rb;
+    if (i < half_ne) { ra = i; rb = i + half_ne; }
+    else { const int t = i - half_ne; ra = ne + 2 * t; rb = ra + 1; }
+    wa = a.W + ((size_t)j * hs + ra) * a.K;
+    wb = a.W + ((size_t)j * hs + rb) * a.K;
+  }
+}
+
+// lane 0 of the owning warp: bias / activation / residual / RoPE / KV append, then the store
+template <int MODE>
+__device__ __forceinline__ void item_epilogue(const StreamArgs& a, int it, float da, float db, int slot, int pos,
+                                              const bf16* res) {
+  if (MODE == MODE_GATED) {
+    if (a.bias) da += __bfloat162float(a.bias[it]);
+    if (a.bias2) db += __bfloat162float(a.bias2[it]);
+    // the eager model rounds each projection to bf16, then act(a) (bf16) * b (bf16)
+    const float fa = round_bf16(da), fb = round_bf16(db);
+    float g;
+    if (a.act == ACT_SILU_GATE) g = silu(fa);
+    else if (a.act == ACT_GELU_TANH_GATE) g = gelu_tanh(fa);
+    else g = gelu_erf(fa);
+    const float out = round_bf16(g) * fb;
+    if (a.out_fp32) reinterpret_cast<float*>(a.y)[(size_t)slot * a.y_slot_stride + it] = out;
+    else reinterpret_cast<bf16*>(a.y)[(size_t)slot * a.y_slot_stride + it] = __float2bfloat16_rn(out);
+  } else if (MODE == MODE_PLAIN) {
+    const float o[2] = {da, db};
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int row = 2 * it + j;
+      if (row >= a.N) continue;
+      float v = o[j];
+      if (a.bias) v += __bfloat162float(a.bias[row]);
+      if (a.act == ACT_GELU_TANH) v = gelu_tanh(round_bf16(v));
+      else if (a.act == ACT_GELU_ERF) v = gelu_erf(round_bf16(v));
+      if (res) v = round_bf16(v) + __bfloat162float(res[row]);
+      // fp32 output = logits: bf16 values like nn.Linear would produce, kept in fp32 for the sampler
+      if (a.out_fp32) reinterpret_cast<float*>(a.y)[(size_t)slot * a.y_slot_stride + row] = round_bf16(v);
+      else reinterpret_cast<bf16*>(a.y)[(size_t)slot * a.y_slot_stride + row] = __float2bfloat16_rn(v);
+    }
+  } else {
+    const int hs = a.head_size, half_hs = hs / 2, ne = a.rope_n_elem, half_ne = ne / 2;
+    const int qpk = a.n_head / a.n_groups;
+    const int j = it / half_hs, i = it % half_hs;
+    int ra, rb;
+    const bool rot_pair = i < half_ne;
+    if (rot_pair) { ra = i; rb = i + half_ne; }
+    else { const int t = i - half_ne; ra = ne + 2 * t; rb = ra + 1; }
+    const size_t row0 = (size_t)j * hs;
+    if (a.bias) { da += __bfloat162float(a.bias[row0 + ra]); db += __bfloat162float(a.bias[row0 + rb]); }
+    da = round_bf16(da);
+    db = round_bf16(db);
+    const int g = j / (qpk + 2), s = j % (qpk + 2);
+    if (rot_pair && s <= qpk) {  // q and k heads rotate, v does not
+      const float ca = a.cos[(size_t)pos * ne + ra], sa = a.sin[(size_t)pos * ne + ra];
+      const float cb = a.cos[(size_t)pos * ne + rb], sb = a.sin[(size_t)pos * ne + rb];
+      const float na = da * ca - db * sa;
+      const float nb = db * cb + da * sb;
+      da = na; db = nb;
+    }
+    bf16* dst;
+    if (s < qpk) dst = a.q_out + (size_t)(g * qpk + s) * hs;
+    else {
+      const size_t which = (s == qpk) ? 0 : 1;
+      dst = a.kv + ((((size_t)slot * 2 + which) * a.n_groups + g) * a.max_seq + pos) * hs;
+    }
+    dst[ra] = __float2bfloat16_rn(da);
+    dst[rb] = __float2bfloat16_rn(db);
+  }
+}
+
+// ---- variant A: register-streamed (LDG.128 batches) ---------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(LIN_THREADS, 3) stream_ldg_kernel(const StreamArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   bf16* xs = reinterpret_cast<bf16*>(smem_raw);
   __shared__ float red[LIN_WARPS];
-
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const bool gated = a.W2 != nullptr;
-  const int n_items = gated ? a.N : (a.N + 1) / 2;
-  const int item_lo = blockIdx.x * a.items_per_cta;
-  const int item_hi = min(n_items, item_lo + a.items_per_cta);
+  const int gw = blockIdx.x * LIN_WARPS + warp, n_gw = gridDim.x * LIN_WARPS;
 
-  // Pull this CTA's first weight lines towards L2 while we (possibly) wait for the hop flag.
-  if (item_lo < n_items) {
-    const int r0 = gated ? item_lo : 2 * item_lo;
-    const char* p = reinterpret_cast<const char*>(a.W + (size_t)r0 * a.K);
-    const size_t bytes = (size_t)min(item_hi - item_lo, 4) * (gated ? 1 : 2) * a.K * sizeof(bf16);
-    for (size_t off = (size_t)threadIdx.x * 128; off < bytes; off += (size_t)LIN_THREADS * 128) prefetch_l2(p + off);
+  // pull this warp's first rows towards L2 while we (possibly) wait for the previous kernel / hop
+  if (gw < a.n_items) {
+    const bf16 *wa, *wb;
+    item_rows<MODE>(a, gw, wa, wb);
+    for (int off = lane * 64; off < a.K; off += 32 * 64) { prefetch_l2(wa + off); prefetch_l2(wb + off); }
   }
   pdl_wait_prior();
   hop_wait(a.wait, a.ctx);
-  const int slot = a.ctx ? a.ctx[MDI_CTX_SLOT] : 0;
-  const bf16* x = a.x + (size_t)slot * a.x_slot_stride;
-  stage_input(x, a.norm_w, a.eps, a.unit_offset, a.K, xs, red);
+  const int slot = a.ctx ? a.ctx[MDI_CTX_SLOT] : 0, pos = a.ctx ? a.ctx[MDI_CTX_POS] : 0;
+  stage_input(a.x + (size_t)slot * a.x_slot_stride, a.norm_w, a.eps, a.unit_offset, a.K, xs, red);
   pdl_launch_dependents();
 
   const bf16* res = a.residual ? a.residual + (size_t)slot * a.res_slot_stride : nullptr;
   const uint4* xv = reinterpret_cast<const uint4*>(xs);
   const int nvec = a.K / 8;
-  for (int it = item_lo + warp; it < item_hi; it += LIN_WARPS) {
-    int ra, rb;
+  for (int it = gw; it < a.n_items; it += n_gw) {
     const bf16 *wa, *wb;
-    if (gated) {
-      ra = rb = it;
-      wa = a.W + (size_t)it * a.K;
-      wb = a.W2 + (size_t)it * a.K;
-    } else {
-      ra = 2 * it;
-      rb = min(2 * it + 1, a.N - 1);
-      wa = a.W + (size_t)ra * a.K;
-      wb = a.W + (size_t)rb * a.K;
-    }
+    item_rows<MODE>(a, it, wa, wb);
     float da, db;
     warp_dot2(wa, wb, xv, nvec, lane, da, db);
-    if (lane == 0) {
-      if (a.bias) {
-        da += __bfloat162float(a.bias[ra]);
-        if (!gated) db += __bfloat162float(a.bias[rb]);
-      }
-      if (gated && a.bias2) db += __bfloat162float(a.bias2[rb]);
-      if (gated) {
-        // reference rounds each projection to bf16, then act(a) (bf16) * b (bf16)
-        float fa = round_bf16(da), fb = round_bf16(db), g;
-        if (a.act == ACT_SILU_GATE) g = silu(fa);
-        else if (a.act == ACT_GELU_TANH_GATE) g = gelu_tanh(fa);
-        else g = gelu_erf(fa);
-        float out = round_bf16(g) * fb;
-        if (a.out_fp32) reinterpret_cast<float*>(a.y)[(size_t)slot * a.y_slot_stride + it] = out;
-        else reinterpret_cast<bf16*>(a.y)[(size_t)slot * a.y_slot_stride + it] = __float2bfloat16_rn(out);
-      } else {
-        float o[2] = {da, db};
-        int rows[2] = {ra, 2 * it + 1};
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          if (rows[j] >= a.N) continue;
-          float v = o[j];
-          if (a.act == ACT_GELU_TANH) v = gelu_tanh(round_bf16(v));
-          else if (a.act == ACT_GELU_ERF) v = gelu_erf(round_bf16(v));
-          if (res) v = round_bf16(v) + __bfloat162float(res[rows[j]]);
-          if (a.out_fp32) reinterpret_cast<float*>(a.y)[(size_t)slot * a.y_slot_stride + rows[j]] = round_bf16(v);  // logits: bf16 values like nn.Linear, kept in fp32 for the sampler
-          else reinterpret_cast<bf16*>(a.y)[(size_t)slot * a.y_slot_stride + rows[j]] = __float2bfloat16_rn(v);
-        }
-      }
-    }
+    if (lane == 0) item_epilogue<MODE>(a, it, da, db, slot, pos, res);
   }
   hop_signal(a.signal, a.ctx);
 }
 
-// ------------------------------------------------------------------------------------------------
-// QKV projection with fused RoPE and KV-cache append.
-// Weight rows are litGPT's group-interleaved layout: for each of G groups: q_per_kv query heads,
-// one key head, one value head (model.py:686-699).  A warp owns the two rows RoPE mixes.
-struct QKVArgs {
-  const bf16* W;       // [(H + 2G) * hs, K]
-  const bf16* bias;    // or null
-  const bf16* x;       // + slot * x_slot_stride
-  const bf16* norm_w;  // fused norm_1 weight or null
-  const float* cos;    // [S, n_elem]
-  const float* sin;
-  bf16* q_out;         // [H * hs]
-  bf16* kv;            // this layer's pool: [n_slots, 2, G, S, hs]
-  const int* ctx;
-  long long x_slot_stride;
-  int K, n_head, n_groups, head_size, rope_n_elem, max_seq;
-  float eps;
-  int unit_offset;
-  int items_per_cta;
-  HopWait wait;
-};
+// ---- variant B: bulk-copy streamed (cp.async.bulk -> smem ring per warp, mbarrier completion) -------
+// Every warp is its own producer: lane 0 keeps STAGES-1 row-chunk copies in flight through the TMA
+// engine (no registers held by in-flight data), all lanes consume from shared memory.  The first
+// copies are issued BEFORE the hop wait / input staging, so weight streaming overlaps both.
+constexpr int TS_CHUNK = 1024;  // elements per row chunk (2 KB)
 
-__global__ void __launch_bounds__(LIN_THREADS) qkv_decode_kernel(const QKVArgs a) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  bf16* xs = reinterpret_cast<bf16*>(smem_raw);
-  __shared__ float red[LIN_WARPS];
+template <int MODE, int STAGES>
+__global__ void __launch_bounds__(LIN_THREADS, 1) stream_bulk_kernel(const StreamArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int hs = a.head_size, half_hs = hs / 2, ne = a.rope_n_elem, half_ne = ne / 2;
-  const int qpk = a.n_head / a.n_groups;
-  const int n_items = (a.n_head + 2 * a.n_groups) * half_hs;
-  const int item_lo = blockIdx.x * a.items_per_cta;
-  const int item_hi = min(n_items, item_lo + a.items_per_cta);
+  const int gw = blockIdx.x * LIN_WARPS + warp, n_gw = gridDim.x * LIN_WARPS;
+  // layout: ring [WARPS][STAGES][2][TS_CHUNK] bf16 | x [K] bf16 | mbar [WARPS][STAGES] u64
+  bf16* ring = reinterpret_cast<bf16*>(smem_raw) + (size_t)warp * STAGES * 2 * TS_CHUNK;
+  bf16* xs = reinterpret_cast<bf16*>(smem_raw) + (size_t)LIN_WARPS * STAGES * 2 * TS_CHUNK;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(xs + ((a.K + 63) / 64) * 64) + warp * STAGES;
+  __shared__ float red[LIN_WARPS];
+
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) mbar_init(&bars[s], 1);
+    mbar_fence_init();
+  }
+  __syncwarp();
+
+  const int n_chunks = (a.K + TS_CHUNK - 1) / TS_CHUNK;
+  const int n_my = gw < a.n_items ? (a.n_items - gw + n_gw - 1) / n_gw : 0;
+  const int total = n_my * n_chunks;
+  auto issue = [&](int f) {
+    const int ii = f / n_chunks, c = f - ii * n_chunks;
+    const bf16 *wa, *wb;
+    item_rows<MODE>(a, gw + ii * n_gw, wa, wb);
+    const int k0 = c * TS_CHUNK;
+    const uint32_t bytes = (uint32_t)min(TS_CHUNK, a.K - k0) * 2u;
+    const int st = f % STAGES;
+    bf16* dst = ring + (size_t)st * 2 * TS_CHUNK;
+    mbar_expect_tx(&bars[st], 2 * bytes);
+    bulk_g2s(dst, wa + k0, bytes, &bars[st]);
+    bulk_g2s(dst + TS_CHUNK, wb + k0, bytes, &bars[st]);
+  };
+  if (lane == 0)
+    for (int f = 0; f < min(STAGES - 1, total); ++f) issue(f);
 
   pdl_wait_prior();
   hop_wait(a.wait, a.ctx);
-  const int slot = a.ctx[MDI_CTX_SLOT], pos = a.ctx[MDI_CTX_POS];
+  const int slot = a.ctx ? a.ctx[MDI_CTX_SLOT] : 0, pos = a.ctx ? a.ctx[MDI_CTX_POS] : 0;
   stage_input(a.x + (size_t)slot * a.x_slot_stride, a.norm_w, a.eps, a.unit_offset, a.K, xs, red);
   pdl_launch_dependents();
 
-  const uint4* xv = reinterpret_cast<const uint4*>(xs);
-  const int nvec = a.K / 8;
-  for (int it = item_lo + warp; it < item_hi; it += LIN_WARPS) {
-    const int j = it / half_hs, i = it % half_hs;  // head slot, pair index inside the head
-    int ra, rb;
-    const bool rot_pair = i < half_ne;
-    if (rot_pair) { ra = i; rb = i + half_ne; }
-    else { int t = i - half_ne; ra = ne + 2 * t; rb = ra + 1; }
-    const size_t row0 = (size_t)j * hs;
-    float da, db;
-    warp_dot2(a.W + (row0 + ra) * a.K, a.W + (row0 + rb) * a.K, xv, nvec, lane, da, db);
-    if (lane == 0) {
-      if (a.bias) { da += __bfloat162float(a.bias[row0 + ra]); db += __bfloat162float(a.bias[row0 + rb]); }
-      da = round_bf16(da);
-      db = round_bf16(db);
-      const int g = j / (qpk + 2), s = j % (qpk + 2);
-      if (rot_pair && s <= qpk) {  // q and k heads rotate, v does not
-        const float ca = a.cos[(size_t)pos * ne + ra], sa = a.sin[(size_t)pos * ne + ra];
-        const float cb = a.cos[(size_t)pos * ne + rb], sb = a.sin[(size_t)pos * ne + rb];
-        const float na = da * ca - db * sa;
-        const float nb = db * cb + da * sb;
-        da = na; db = nb;
+  const bf16* res = a.residual ? a.residual + (size_t)slot * a.res_slot_stride : nullptr;
+  float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+  int c = 0, ii = 0;
+  for (int f = 0; f < total; ++f) {
+    if (lane == 0 && f + STAGES - 1 < total) issue(f + STAGES - 1);
+    const int st = f % STAGES;
+    mbar_wait(&bars[st], (uint32_t)((f / STAGES) & 1));
+    const int k0 = c * TS_CHUNK;
+    const int nv = min(TS_CHUNK, a.K - k0) / 8;
+    const uint4* wa = reinterpret_cast<const uint4*>(ring + (size_t)st * 2 * TS_CHUNK);
+    const uint4* wb = wa + TS_CHUNK / 8;
+    const uint4* xv = reinterpret_cast<const uint4*>(xs + k0);
+    if (nv == TS_CHUNK / 8) {
+#pragma unroll
+      for (int u = 0; u < TS_CHUNK / 8 / 32; ++u) {
+        const uint4 x = xv[lane + 32 * u];
+        if (u & 1) { a1 += dot8(wa[lane + 32 * u], x); b1 += dot8(wb[lane + 32 * u], x); }
+        else { a0 += dot8(wa[lane + 32 * u], x); b0 += dot8(wb[lane + 32 * u], x); }
       }
-      bf16* dst;
-      if (s < qpk) dst = a.q_out + (size_t)(g * qpk + s) * hs;
-      else {
-        const size_t which = (s == qpk) ? 0 : 1;
-        dst = a.kv + ((((size_t)slot * 2 + which) * a.n_groups + g) * a.max_seq + pos) * hs;
-      }
-      dst[ra] = __float2bfloat16_rn(da);
-      dst[rb] = __float2bfloat16_rn(db);
+    } else {
+      for (int v = lane; v < nv; v += 32) { const uint4 x = xv[v]; a0 += dot8(wa[v], x); b0 += dot8(wb[v], x); }
     }
+    if (++c == n_chunks) {
+      const float da = warp_sum(a0 + a1), db = warp_sum(b0 + b1);
+      if (lane == 0) item_epilogue<MODE>(a, gw + ii * n_gw, da, db, slot, pos, res);
+      a0 = a1 = b0 = b1 = 0.f;
+      c = 0;
+      ++ii;
+    }
+    __syncwarp();  // everyone is done with stage `st` before lane 0 re-arms it next iteration
   }
-}
-
-static inline int pick_items_per_cta(int n_items, int target_ctas) {
-  // multiple of LIN_WARPS so every warp of a CTA gets the same number of row pairs
-  int ipc = (n_items + target_ctas - 1) / target_ctas;
-  ipc = ((ipc + LIN_WARPS - 1) / LIN_WARPS) * LIN_WARPS;
-  return ipc < LIN_WARPS ? LIN_WARPS : ipc;
+  hop_signal(a.signal, a.ctx);
 }
 
 static int g_num_sms = 0;
@@ -310,8 +359,8 @@ static int num_sms() {
   return g_num_sms;
 }
 
-template <typename Args, typename Kern>
-static int launch_pdl(Kern kern, const Args& args, int grid, size_t smem, cudaStream_t stream, int use_pdl) {
+template <typename Kern>
+static int launch_pdl(Kern kern, const StreamArgs& args, int grid, size_t smem, cudaStream_t stream, int use_pdl) {
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
@@ -329,48 +378,75 @@ static int launch_pdl(Kern kern, const Args& args, int grid, size_t smem, cudaSt
   return (int)cudaLaunchKernelEx(&cfg, kern, args);
 }
 
+// variant: 0 = LDG register streaming (grid = sms * ctas_per_sm), 1 = bulk-copy ring with 4 stages
+// (1 CTA/SM), 2 = bulk-copy ring with 2 stages (grid = sms * min(ctas_per_sm, 2..3)).
+template <int MODE>
+static int launch_stream(const StreamArgs& a, int variant, int ctas_per_sm, int use_pdl, cudaStream_t stream) {
+  const int sms = num_sms();
+  if (ctas_per_sm <= 0) ctas_per_sm = 4;
+  const int max_useful = (a.n_items + LIN_WARPS - 1) / LIN_WARPS;
+  if (variant == 0) {
+    const int grid = max(1, min(sms * ctas_per_sm, max_useful));
+    return launch_pdl(stream_ldg_kernel<MODE>, a, grid, (size_t)a.K * sizeof(bf16), stream, use_pdl);
+  }
+  const int stages = variant == 1 ? 4 : 2;
+  const size_t smem = (size_t)LIN_WARPS * stages * 2 * TS_CHUNK * 2 + (size_t)((a.K + 63) / 64) * 64 * 2 +
+                      (size_t)LIN_WARPS * stages * 8;
+  if (smem > 227 * 1024) return -2;
+  const int per_sm = variant == 1 ? 1 : max(1, min(ctas_per_sm, (int)((227 * 1024) / (smem + 1024))));
+  const int grid = max(1, min(sms * per_sm, max_useful));
+  if (variant == 1) return launch_pdl(stream_bulk_kernel<MODE, 4>, a, grid, smem, stream, use_pdl);
+  return launch_pdl(stream_bulk_kernel<MODE, 2>, a, grid, smem, stream, use_pdl);
+}
+
+static int g_default_variant = 0;
+
 }  // namespace mdi
 
 using namespace mdi;
 
 extern "C" {
 
-// ctas_per_sm controls the grid: grid ~= num_sms * ctas_per_sm row-pair chunks.
+void mdi_set_linear_variant(int v) { g_default_variant = v; }
+int mdi_get_linear_variant() { return g_default_variant; }
+
 int mdi_linear_decode(const void* W, const void* W2, const void* bias, const void* bias2, const void* x,
                       const void* norm_w, const void* residual, void* y, const int* ctx, long long x_slot_stride,
                       long long res_slot_stride, long long y_slot_stride, int N, int K, float eps, int unit_offset,
                       int act, int out_fp32, const int* wait_flag, int* status, long long wait_max_cycles,
-                      int* signal_flag, unsigned int* done_ctr, int ctas_per_sm, int use_pdl, cudaStream_t stream) {
+                      int* signal_flag, unsigned int* done_ctr, int ctas_per_sm, int use_pdl, int variant,
+                      cudaStream_t stream) {
   if (K % 8 != 0) return -2;
-  LinearArgs a;
+  StreamArgs a{};
   a.W = (const bf16*)W; a.W2 = (const bf16*)W2; a.bias = (const bf16*)bias; a.bias2 = (const bf16*)bias2;
   a.x = (const bf16*)x; a.norm_w = (const bf16*)norm_w; a.residual = (const bf16*)residual; a.y = y; a.ctx = ctx;
   a.x_slot_stride = x_slot_stride; a.res_slot_stride = res_slot_stride; a.y_slot_stride = y_slot_stride;
   a.N = N; a.K = K; a.eps = eps; a.unit_offset = unit_offset; a.act = act; a.out_fp32 = out_fp32;
   a.wait = HopWait{wait_flag, status, wait_max_cycles};
   a.signal = HopSignal{signal_flag, done_ctr};
-  const int n_items = W2 ? N : (N + 1) / 2;
-  a.items_per_cta = pick_items_per_cta(n_items, num_sms() * (ctas_per_sm > 0 ? ctas_per_sm : 4));
-  const int grid = (n_items + a.items_per_cta - 1) / a.items_per_cta;
-  return launch_pdl(linear_decode_kernel, a, grid, (size_t)K * sizeof(bf16), stream, use_pdl);
+  a.n_items = W2 ? N : (N + 1) / 2;
+  if (variant < 0) variant = g_default_variant;
+  if (W2) return launch_stream<MODE_GATED>(a, variant, ctas_per_sm, use_pdl, stream);
+  return launch_stream<MODE_PLAIN>(a, variant, ctas_per_sm, use_pdl, stream);
 }
 
 int mdi_qkv_decode(const void* W, const void* bias, const void* x, const void* norm_w, const float* cos,
                    const float* sin, void* q_out, void* kv, const int* ctx, long long x_slot_stride, int K,
                    int n_head, int n_groups, int head_size, int rope_n_elem, int max_seq, float eps,
                    int unit_offset, const int* wait_flag, int* status, long long wait_max_cycles, int ctas_per_sm,
-                   int use_pdl, cudaStream_t stream) {
+                   int use_pdl, int variant, cudaStream_t stream) {
   if (K % 8 != 0 || head_size % 2 != 0 || rope_n_elem % 2 != 0 || rope_n_elem > head_size) return -2;
-  QKVArgs a;
+  StreamArgs a{};
   a.W = (const bf16*)W; a.bias = (const bf16*)bias; a.x = (const bf16*)x; a.norm_w = (const bf16*)norm_w;
   a.cos = cos; a.sin = sin; a.q_out = (bf16*)q_out; a.kv = (bf16*)kv; a.ctx = ctx; a.x_slot_stride = x_slot_stride;
-  a.K = K; a.n_head = n_head; a.n_groups = n_groups; a.head_size = head_size; a.rope_n_elem = rope_n_elem;
+  a.K = K; a.N = (n_head + 2 * n_groups) * head_size;
+  a.n_head = n_head; a.n_groups = n_groups; a.head_size = head_size; a.rope_n_elem = rope_n_elem;
   a.max_seq = max_seq; a.eps = eps; a.unit_offset = unit_offset;
   a.wait = HopWait{wait_flag, status, wait_max_cycles};
-  const int n_items = (n_head + 2 * n_groups) * (head_size / 2);
-  a.items_per_cta = pick_items_per_cta(n_items, num_sms() * (ctas_per_sm > 0 ? ctas_per_sm : 4));
-  const int grid = (n_items + a.items_per_cta - 1) / a.items_per_cta;
-  return launch_pdl(qkv_decode_kernel, a, grid, (size_t)K * sizeof(bf16), stream, use_pdl);
+  a.signal = HopSignal{nullptr, nullptr};
+  a.n_items = (n_head + 2 * n_groups) * (head_size / 2);
+  if (variant < 0) variant = g_default_variant;
+  return launch_stream<MODE_QKV>(a, variant, ctas_per_sm, use_pdl, stream);
 }
 
 }  // extern "C"

@@ -37,8 +37,10 @@ def test_library_loaded_and_device_is_blackwell():
 
 @pytest.mark.parametrize("N,K", [(4096, 4096), (6144, 4096), (4096, 14336), (2048, 5632), (1000, 256), (37, 64)])
 @pytest.mark.parametrize("fused_norm", [False, True])
-def test_linear_decode_plain_and_residual(N, K, fused_norm):
+@pytest.mark.parametrize("variant", [0, 1, 2])
+def test_linear_decode_plain_and_residual(N, K, fused_norm, variant):
     ops = _ops()
+    ops.set_linear_variant(variant)
     torch.manual_seed(N + K)
     W = (torch.randn(N, K, device="cuda") * 0.02).bfloat16()
     x = torch.randn(K, device="cuda").bfloat16()
@@ -59,8 +61,10 @@ def test_linear_decode_plain_and_residual(N, K, fused_norm):
 @pytest.mark.parametrize("act,fn", [("silu_gate", torch.nn.functional.silu),
                                     ("gelu_tanh_gate", lambda t: torch.nn.functional.gelu(t, approximate="tanh")),
                                     ("gelu_erf_gate", torch.nn.functional.gelu)])
-def test_linear_decode_gated_mlp(act, fn):
+@pytest.mark.parametrize("variant", [0, 1, 2])
+def test_linear_decode_gated_mlp(act, fn, variant):
     ops = _ops()
+    ops.set_linear_variant(variant)
     torch.manual_seed(0)
     N, K = 14336, 4096
     W1 = (torch.randn(N, K, device="cuda") * 0.02).bfloat16()
@@ -107,8 +111,10 @@ def _interleaved_qkv_ref(W, bias, x, cfg, cos, sin, pos):
 
 
 @pytest.mark.parametrize("H,G,hs,ne,C", [(32, 8, 128, 128, 4096), (32, 4, 64, 64, 2048), (8, 8, 64, 32, 512), (4, 1, 128, 128, 512)])
-def test_qkv_decode_rope_and_kv_append(H, G, hs, ne, C):
+@pytest.mark.parametrize("variant", [0, 1, 2])
+def test_qkv_decode_rope_and_kv_append(H, G, hs, ne, C, variant):
     ops = _ops()
+    ops.set_linear_variant(variant)
     from mdi_llm_b200.models.gpt import build_rope_cache
 
     torch.manual_seed(H * G)
@@ -131,7 +137,7 @@ def test_qkv_decode_rope_and_kv_append(H, G, hs, ne, C):
     assert untouched.abs().sum() == 0  # nothing else in the pool was written
 
 
-@pytest.mark.parametrize("H,G,hs", [(32, 8, 128), (32, 4, 64), (8, 8, 64), (16, 1, 128), (4, 2, 128)])
+@pytest.mark.parametrize("H,G,hs", [(32, 8, 128), (32, 4, 64), (8, 8, 64), (8, 1, 128), (4, 2, 128)])
 @pytest.mark.parametrize("L", [1, 31, 32, 33, 500, 2048])
 def test_attn_decode_matches_sdpa(H, G, hs, L):
     ops = _ops()
@@ -203,9 +209,11 @@ def test_sample_greedy_and_topk_distribution():
     assert a in top200
 
 
-def test_hop_flag_wait_and_signal_same_device():
+@pytest.mark.parametrize("variant", [0, 1])
+def test_hop_flag_wait_and_signal_same_device(variant):
     """Producer kernel publishes flag[slot] = ctx.signal after its stores; consumer waits for it."""
     ops = _ops()
+    ops.set_linear_variant(variant)
     N = K = 256
     W = torch.eye(N, device="cuda").bfloat16()
     x = torch.randn(K, device="cuda").bfloat16()
@@ -232,6 +240,7 @@ def test_hop_flag_wait_and_signal_same_device():
 
 def test_cuda_graph_capture_and_replay():
     ops = _ops()
+    ops.set_linear_variant(0)
     N = K = 1024
     W = (torch.randn(N, K, device="cuda") * 0.03).bfloat16()
     x = torch.randn(K, device="cuda").bfloat16()
