@@ -51,6 +51,7 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.mdi_wait_flag.argtypes = [vp, vp, vp, i64, vp]
     lib.mdi_set_flag.argtypes = [vp, vp, vp]
     lib.mdi_copy_bytes.argtypes = [vp, vp, c_size_t, vp]
+    lib.mdi_copy_signal.argtypes = [vp, vp, c_size_t, vp, vp, vp, vp]
     lib.mdi_device_info.argtypes = [POINTER(i32), POINTER(i32), POINTER(i32), POINTER(c_size_t)]
     lib.mdi_p2p_alloc.argtypes = [c_size_t, POINTER(vp), c_char_p]
     lib.mdi_p2p_open.argtypes = [c_char_p, POINTER(vp)]

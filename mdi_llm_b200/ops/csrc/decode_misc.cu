@@ -278,6 +278,16 @@ __global__ void copy_vec_kernel(const uint4* __restrict__ src, uint4* __restrict
     dst[i] = src[i];
 }
 
+// Prefill hop: copy + publish in ONE kernel.  Every writer fences at system scope before the
+// last CTA releases the flag — a separate "set flag" kernel after a copy kernel is NOT enough:
+// nothing orders another kernel's peer stores (spread over many NVLink lanes) before the flag store.
+__global__ void copy_signal_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, size_t nvec,
+                                   HopSignal sig, const int* __restrict__ ctx) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (size_t)gridDim.x * blockDim.x)
+    dst[i] = src[i];
+  hop_signal(sig, ctx);
+}
+
 }  // namespace mdi
 
 using namespace mdi;
@@ -329,6 +339,16 @@ int mdi_wait_flag(const int* flag, const int* ctx, int* status, long long max_cy
 }
 int mdi_set_flag(int* flag, const int* ctx, cudaStream_t stream) {
   set_flag_kernel<<<1, 32, 0, stream>>>(flag, ctx);
+  return (int)cudaGetLastError();
+}
+int mdi_copy_signal(const void* src, void* dst, size_t bytes, int* flag, unsigned int* done_ctr, const int* ctx,
+                    cudaStream_t stream) {
+  if (bytes % 16) return -2;
+  size_t nvec = bytes / 16;
+  int blocks = (int)((nvec + 255) / 256);
+  if (blocks > 296) blocks = 296;
+  if (blocks < 1) blocks = 1;
+  copy_signal_kernel<<<blocks, 256, 0, stream>>>((const uint4*)src, (uint4*)dst, nvec, HopSignal{flag, done_ctr}, ctx);
   return (int)cudaGetLastError();
 }
 int mdi_copy_bytes(const void* src, void* dst, size_t bytes, cudaStream_t stream) {

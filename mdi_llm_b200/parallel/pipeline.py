@@ -138,9 +138,13 @@ class DevicePipeline:
             self.prompts = [p.to(self.device) for p in prompts] if self.is_starter else None
             torch.cuda.current_stream().synchronize()
 
-    def _copy_to(self, src: torch.Tensor, dst_ptr: int) -> None:
-        ops.check(ops.lib().mdi_copy_bytes(src.data_ptr(), dst_ptr, src.numel() * src.element_size(), ops.stream_ptr()),
-                  "hop copy")
+    def _hop_copy(self, src: torch.Tensor, dst_ptr: int) -> None:
+        """Prefill hop: peer copy and flag publication fused in one kernel (writers fence at system
+        scope before the flag is released — see ``copy_signal_kernel``)."""
+        st = self.stage
+        ops.check(ops.lib().mdi_copy_signal(src.data_ptr(), dst_ptr, src.numel() * src.element_size(),
+                                            self.next_hop.flag_ptr, st.done_ctr.data_ptr(), st.ctx.data_ptr(),
+                                            ops.stream_ptr()), "prefill hop")
 
     @torch.inference_mode()
     def prefill(self) -> None:
@@ -160,10 +164,9 @@ class DevicePipeline:
                     hidden = self.model(self.prefill_in[slot, :T].unsqueeze(0), pos, slot=slot)
                 hidden = hidden.to(torch.bfloat16).contiguous()
                 if self.is_last:  # wrap-around: only the last position feeds lm_head
-                    self._copy_to(hidden[0, -1], self.next_hop.hidden_ptr + slot * self.C * 2)
+                    self._hop_copy(hidden[0, -1], self.next_hop.hidden_ptr + slot * self.C * 2)
                 else:
-                    self._copy_to(hidden[0], self.next_prefill_ptr + slot * self.max_prompt_len * self.C * 2)
-                ops.check(lib.mdi_set_flag(self.next_hop.flag_ptr, st.ctx.data_ptr(), ops.stream_ptr()), "signal prefill")
+                    self._hop_copy(hidden[0], self.next_prefill_ptr + slot * self.max_prompt_len * self.C * 2)
 
     # graph builders ---------------------------------------------------------------------------------
     def _g_full(self, dev_ctx: bool) -> ops.CudaGraph:

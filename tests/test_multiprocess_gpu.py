@@ -1,0 +1,33 @@
+"""Multi-process (one rank per GPU, CUDA-IPC peer buffers) device pipeline, launched with torchrun."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = [pytest.mark.gpu, pytest.mark.multigpu]
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run(world, mode, port):
+    if torch.cuda.device_count() < world:
+        pytest.skip("not enough GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "_mp_pipeline_worker.py"), mode]
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT)
+    lines = [ln for ln in p.stdout.splitlines() if ln.startswith("MP_RESULT ")]
+    assert lines, f"worker produced no result\nstdout:\n{p.stdout[-2000:]}\nstderr:\n{p.stderr[-3000:]}"
+    res = json.loads(lines[-1][len("MP_RESULT "):])
+    assert res["ok"], res
+    assert p.returncode == 0
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_ipc_ring_device_mode_matches_single_gpu(world):
+    _run(world, "device", 29600 + world)
+
+
+def test_ipc_ring_host_fed_mode_matches_single_gpu():
+    _run(2, "host", 29650)
