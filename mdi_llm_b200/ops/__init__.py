@@ -38,15 +38,17 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.mdi_error_string.restype = c_char_p
     lib.mdi_error_string.argtypes = [i32]
     lib.mdi_linear_decode.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, i32, i32, f32, i32, i32, i32,
-                                      vp, vp, i64, vp, vp, i32, i32, i32, vp]
+                                      vp, vp, i64, vp, vp, i32, i32, i32, vp, vp, vp]
     lib.mdi_qkv_decode.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, i32, i32, i32, f32, i32,
                                    vp, vp, i64, i32, i32, i32, vp]
     lib.mdi_set_linear_variant.argtypes = [i32]
     lib.mdi_get_linear_variant.restype = i32
-    lib.mdi_attn_decode.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]
+    lib.mdi_attn_decode.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]
     lib.mdi_embed.argtypes = [vp, vp, vp, i64, vp, vp, i64, i32, f32, i32, vp]
     lib.mdi_rmsnorm_rows.argtypes = [vp, vp, vp, i32, i32, f32, i32, vp]
     lib.mdi_sample.argtypes = [vp, i64, vp, i64, vp, vp, i32, i32, f32, i32, c_ulonglong, i32, vp]
+    lib.mdi_sample_fast.argtypes = [vp, vp, vp, i64, vp, vp, i32, i32, f32, i32, c_ulonglong, i32, vp]
+    lib.mdi_sample_scratch_bytes.restype = c_size_t
     lib.mdi_advance_step.argtypes = [vp, vp, vp, i32, i32, i32, vp]
     lib.mdi_wait_flag.argtypes = [vp, vp, vp, i64, vp]
     lib.mdi_set_flag.argtypes = [vp, vp, vp]
@@ -141,18 +143,22 @@ def linear_decode(
     y_slot_stride: int = 0, wait_flag: Optional[int] = None, status: Optional[int] = None, wait_max_cycles: int = 0,
     signal_flag: Optional[int] = None, done_ctr: Optional[int] = None, ctas_per_sm: int = 4, use_pdl: bool = False,
     y_ptr: Optional[int] = None, residual_ptr: Optional[int] = None, x_ptr: Optional[int] = None, variant: int = -1,
+    stats: Optional[torch.Tensor] = None,
 ) -> None:
     """``y = epilogue(W @ norm?(x))`` for one token.  ``*_ptr`` overrides let the output /
     residual / input live in peer-mapped (other GPU) memory that has no torch tensor."""
     _bf16(W, "W"); _bf16(W2, "W2")
     N, K = W.shape
     out_fp32 = int(y is not None and y.dtype == torch.float32)
+    hist = amax = None
+    if stats is not None:  # sampler scratch: histogram at offset 0, packed arg-max right after it
+        hist, amax = stats.data_ptr(), stats.data_ptr() + 4096 * 4
     check(lib().mdi_linear_decode(
         ptr(W), ptr(W2), ptr(bias), ptr(bias2), x_ptr if x_ptr is not None else ptr(x), ptr(norm_w),
         residual_ptr if residual_ptr is not None else ptr(residual), y_ptr if y_ptr is not None else ptr(y),
         ptr(ctx), x_slot_stride, res_slot_stride, y_slot_stride, N, K, eps, int(unit_offset), ACT[act], out_fp32,
-        wait_flag, status, wait_max_cycles, signal_flag, done_ctr, ctas_per_sm, int(use_pdl), variant, stream_ptr()),
-        "linear_decode")
+        wait_flag, status, wait_max_cycles, signal_flag, done_ctr, ctas_per_sm, int(use_pdl), variant, hist, amax,
+        stream_ptr()), "linear_decode")
 
 
 def qkv_decode(
@@ -173,10 +179,13 @@ def qkv_decode(
         "qkv_decode")
 
 
-def attn_decode(q: torch.Tensor, kv_layer: torch.Tensor, y: torch.Tensor, part: torch.Tensor, ctx: torch.Tensor, *,
-                n_head: int, n_groups: int, head_size: int, max_seq: int, n_split: int, use_pdl: bool = False) -> None:
-    check(lib().mdi_attn_decode(ptr(q), ptr(kv_layer), ptr(y), ptr(part), ptr(ctx), n_head, n_groups, head_size,
-                                max_seq, n_split, int(use_pdl), stream_ptr()), "attn_decode")
+def attn_decode(q: torch.Tensor, kv_layer: torch.Tensor, y: torch.Tensor, part: torch.Tensor, tickets: torch.Tensor,
+                ctx: torch.Tensor, *, n_head: int, n_groups: int, head_size: int, max_seq: int, n_split: int,
+                use_pdl: bool = False) -> None:
+    """Split-KV decode attention.  ``part``: fp32 ``[H, n_split, hs+2]`` scratch; ``tickets``: zeroed
+    int32 ``[G]`` (self-resetting) used by the last CTA of a group to merge the spans."""
+    check(lib().mdi_attn_decode(ptr(q), ptr(kv_layer), ptr(y), ptr(part), ptr(tickets), ptr(ctx), n_head, n_groups,
+                                head_size, max_seq, n_split, int(use_pdl), stream_ptr()), "attn_decode")
 
 
 def embed(wte: torch.Tensor, x: torch.Tensor, ctx: torch.Tensor, *, tokens: Optional[torch.Tensor] = None,
@@ -204,6 +213,22 @@ def sample(logits: torch.Tensor, tokens: torch.Tensor, ctx: torch.Tensor, *, voc
     check(lib().mdi_sample(ptr(logits), logits_slot_stride, ptr(tokens), tok_slot_stride, ptr(last_token), ptr(ctx),
                            vocab, int(top_k or 0), float(temperature), int(greedy), seed & (2 ** 64 - 1), int(use_pdl),
                            stream_ptr()), "sample")
+
+
+def sample_scratch(device: Any) -> torch.Tensor:
+    """Zeroed scratch of the fast sampler: logit-key histogram, packed arg-max, candidate list."""
+    return torch.zeros(int(lib().mdi_sample_scratch_bytes()) // 4 + 4, dtype=torch.int32, device=device)
+
+
+def sample_fast(logits: torch.Tensor, scratch: torch.Tensor, tokens: torch.Tensor, ctx: torch.Tensor, *, vocab: int,
+                top_k: Optional[int], temperature: float, greedy: bool, seed: int, tok_slot_stride: int,
+                last_token: Optional[torch.Tensor] = None, use_pdl: bool = False) -> None:
+    """Sampling from statistics the lm_head epilogue left in ``scratch`` (``linear_decode(stats=scratch)``)."""
+    if logits.dtype != torch.float32 or tokens.dtype != torch.int32:
+        raise OpsError("sample_fast: logits fp32 and tokens int32 expected")
+    check(lib().mdi_sample_fast(ptr(logits), ptr(scratch), ptr(tokens), tok_slot_stride, ptr(last_token), ptr(ctx),
+                                vocab, int(top_k or 0), float(temperature), int(greedy), seed & (2 ** 64 - 1),
+                                int(use_pdl), stream_ptr()), "sample_fast")
 
 
 def advance_step(ctx: torch.Tensor, state: torch.Tensor, pos: torch.Tensor, n_slots: int, is_starter: bool,

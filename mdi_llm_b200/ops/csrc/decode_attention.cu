@@ -4,13 +4,15 @@
 // cache slots through a [1,1,1,S] boolean mask row, with K/V already expanded to n_head heads
 // (model.py:704-751).  Here the cache holds the G group heads only, a CTA serves all q_per_kv
 // query heads of one group from a single pass over that group's K/V (GQA packing: 4x fewer
-// bytes for Llama-3), only the live prefix [0, pos] is scanned, and the sequence is split over
-// `n_split` CTAs per group so the grid fills the GPU for any context length.
+// bytes for Llama-3) and only the live prefix [0, pos] is scanned.
 //
-//   partial kernel : grid (G, n_split), 4 warps; each warp walks 32-position tiles with an
-//                    online softmax per query head; CTA merges its warps and writes
-//                    (m, l, acc[hs]) per (head, split).
-//   combine kernel : grid (H), merges the splits -> bf16 y[H*hs] (input of the output proj).
+// One kernel, grid (G, n_split), 4 warps per CTA, a warp owns 32-position tiles:
+//   * the context is cut into spans of >= 128 positions, so short contexts use few CTAs and
+//     the others exit at once (the grid is fixed at graph-capture time, the length is not);
+//   * all K loads of a tile (16 x 16 B per lane) and the V loads (batches of 16 rows) are issued
+//     before they are consumed — decode attention is latency-, not bandwidth-bound;
+//   * the last CTA of a group to finish merges the spans (atomic ticket) and writes bf16
+//     y[H*hs] directly: no separate combine launch.
 #include "common.cuh"
 
 namespace mdi {
@@ -22,20 +24,26 @@ constexpr int ATT_TILE = 32;
 struct AttnArgs {
   const bf16* q;   // [H * hs] (already roped)
   const bf16* kv;  // this layer's pool [n_slots, 2, G, S, hs]
+  bf16* y;         // [H * hs]
   float* part;     // [H, n_split, hs + 2]
+  unsigned int* tickets;  // [G] zero-initialised, self-resetting
   const int* ctx;
   int n_head, n_groups, max_seq, n_split;
   float scale_log2;  // (1/sqrt(hs)) * log2(e)
 };
 
 template <int HS, int QPK>
-__global__ void __launch_bounds__(ATT_THREADS) attn_decode_partial_kernel(const AttnArgs a) {
-  constexpr int DPL = HS / 32;  // output dims per lane in the PV phase
-  constexpr int QDIM = HS / 4;  // dims per lane in the QK phase (4 lanes per position)
+__global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const AttnArgs a) {
+  constexpr int DPL = HS / 32;   // output dims per lane in the PV phase
+  constexpr int QDIM = HS / 4;   // dims per lane in the QK phase (4 lanes per position)
+  constexpr int KV4 = QDIM / 8;  // uint4 loads per lane per position
+  constexpr int VB = (QPK >= 8 && HS >= 128) ? 8 : 16;  // V rows per load batch (register budget)
+  constexpr int KPASS = (QPK >= 8 && HS >= 128) ? 2 : 4;  // K passes whose loads are batched
   __shared__ __align__(16) float q_s[QPK][HS];
   __shared__ float s_s[ATT_WARPS][QPK][ATT_TILE];
   __shared__ float mrg_m[ATT_WARPS][QPK], mrg_l[ATT_WARPS][QPK];
   __shared__ float mrg_acc[ATT_WARPS][QPK][HS];
+  __shared__ int sh_last;
 
   const int g = blockIdx.x, split = blockIdx.y;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -43,13 +51,16 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_decode_partial_kernel(const 
   const int slot = a.ctx[MDI_CTX_SLOT], L = a.ctx[MDI_CTX_POS] + 1;
   pdl_launch_dependents();
 
-  // this split's position range, tile aligned
+  // spans of whole tiles, at least ATT_WARPS tiles (128 positions) each
   const int tiles = (L + ATT_TILE - 1) / ATT_TILE;
-  const int tiles_per_split = (tiles + a.n_split - 1) / a.n_split;
+  int tiles_per_split = (tiles + a.n_split - 1) / a.n_split;
+  if (tiles_per_split < ATT_WARPS) tiles_per_split = ATT_WARPS;
+  const int n_active = (tiles + tiles_per_split - 1) / tiles_per_split;
+  if (split >= n_active) return;
   const int t_lo = split * tiles_per_split, t_hi = min(tiles, t_lo + tiles_per_split);
 
   for (int i = threadIdx.x; i < QPK * HS; i += ATT_THREADS) {
-    int h = i / HS, d = i % HS;
+    const int h = i / HS, d = i % HS;
     q_s[h][d] = __bfloat162float(a.q[(size_t)(g * QPK + h) * HS + d]) * a.scale_log2;
   }
   __syncthreads();
@@ -67,34 +78,45 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_decode_partial_kernel(const 
 
   for (int t = t_lo + warp; t < t_hi; t += ATT_WARPS) {
     const int p0 = t * ATT_TILE;
-    // ---- QK^T: 4 lanes per position, 8 positions per pass, 4 passes -------------------------
+    // ---- issue the K loads of KPASS passes (8 positions each) up-front, then consume --------------
 #pragma unroll
-    for (int pass = 0; pass < 4; ++pass) {
-      const int pj = pass * 8 + (lane >> 2), pos = p0 + pj, qd = (lane & 3) * QDIM;
-      float sc[QPK];
+    for (int pg = 0; pg < 4 / KPASS; ++pg) {
+      uint4 kk[KPASS][KV4];
 #pragma unroll
-      for (int h = 0; h < QPK; ++h) sc[h] = 0.f;
-      if (pos < L) {
-        const uint4* kr = reinterpret_cast<const uint4*>(kbase + (size_t)pos * HS + qd);
+      for (int pp = 0; pp < KPASS; ++pp) {
+        const int pos = min(p0 + (pg * KPASS + pp) * 8 + (lane >> 2), L - 1);  // clamp: masked below
+        const uint4* kr = reinterpret_cast<const uint4*>(kbase + (size_t)pos * HS + (lane & 3) * QDIM);
 #pragma unroll
-        for (int v = 0; v < QDIM / 8; ++v) {
-          uint4 kk = __ldg(kr + v);
-          float kf[8] = {bf16lo(kk.x), bf16hi(kk.x), bf16lo(kk.y), bf16hi(kk.y),
-                         bf16lo(kk.z), bf16hi(kk.z), bf16lo(kk.w), bf16hi(kk.w)};
-#pragma unroll
-          for (int h = 0; h < QPK; ++h) {
-            const float* qq = &q_s[h][qd + v * 8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) sc[h] = fmaf(kf[e], qq[e], sc[h]);
-          }
-        }
+        for (int v = 0; v < KV4; ++v) kk[pp][v] = __ldg(kr + v);
       }
 #pragma unroll
-      for (int h = 0; h < QPK; ++h) {
-        float s = sc[h];
-        s += __shfl_xor_sync(0xffffffffu, s, 1);
-        s += __shfl_xor_sync(0xffffffffu, s, 2);
-        if ((lane & 3) == 0) s_s[warp][h][pj] = (pos < L) ? s : -INFINITY;
+      for (int pp = 0; pp < KPASS; ++pp) {
+        const int pj = (pg * KPASS + pp) * 8 + (lane >> 2), pos = p0 + pj, qd = (lane & 3) * QDIM;
+        float sc[QPK];
+#pragma unroll
+        for (int h = 0; h < QPK; ++h) sc[h] = 0.f;
+#pragma unroll
+        for (int v = 0; v < KV4; ++v) {
+          const uint4 k4 = kk[pp][v];
+          const float kf[8] = {bf16lo(k4.x), bf16hi(k4.x), bf16lo(k4.y), bf16hi(k4.y),
+                               bf16lo(k4.z), bf16hi(k4.z), bf16lo(k4.w), bf16hi(k4.w)};
+#pragma unroll
+          for (int h = 0; h < QPK; ++h) {
+            const float4 qa = *reinterpret_cast<const float4*>(&q_s[h][qd + v * 8]);
+            const float4 qb = *reinterpret_cast<const float4*>(&q_s[h][qd + v * 8 + 4]);
+            sc[h] = fmaf(kf[0], qa.x, sc[h]); sc[h] = fmaf(kf[1], qa.y, sc[h]);
+            sc[h] = fmaf(kf[2], qa.z, sc[h]); sc[h] = fmaf(kf[3], qa.w, sc[h]);
+            sc[h] = fmaf(kf[4], qb.x, sc[h]); sc[h] = fmaf(kf[5], qb.y, sc[h]);
+            sc[h] = fmaf(kf[6], qb.z, sc[h]); sc[h] = fmaf(kf[7], qb.w, sc[h]);
+          }
+        }
+#pragma unroll
+        for (int h = 0; h < QPK; ++h) {
+          float s = sc[h];
+          s += __shfl_xor_sync(0xffffffffu, s, 1);
+          s += __shfl_xor_sync(0xffffffffu, s, 2);
+          if ((lane & 3) == 0) s_s[warp][h][pj] = (pos < L) ? s : -INFINITY;
+        }
       }
     }
     __syncwarp();
@@ -112,26 +134,28 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_decode_partial_kernel(const 
       s_s[warp][h][lane] = p;
     }
     __syncwarp();
-    // ---- PV: lane owns DPL consecutive output dims --------------------------------------------
-    const int n_pos = min(ATT_TILE, L - p0);
-    for (int pj = 0; pj < n_pos; ++pj) {
-      const bf16* vr = vbase + (size_t)(p0 + pj) * HS + lane * DPL;
-      float vf[DPL];
-      if (DPL == 4) {
-        uint2 vv = __ldg(reinterpret_cast<const uint2*>(vr));
-        vf[0] = bf16lo(vv.x); vf[1] = bf16hi(vv.x); vf[2 % DPL] = bf16lo(vv.y); vf[3 % DPL] = bf16hi(vv.y);
-      } else {
+    // ---- PV: lane owns DPL consecutive output dims; rows loaded 16 at a time -------------------
 #pragma unroll
-        for (int d = 0; d < DPL; d += 2) {
-          uint32_t vv = __ldg(reinterpret_cast<const uint32_t*>(vr + d));
-          vf[d] = bf16lo(vv); vf[d + 1] = bf16hi(vv);
-        }
+    for (int half = 0; half < ATT_TILE / VB; ++half) {
+      uint32_t vv[VB][DPL / 2];
+#pragma unroll
+      for (int r = 0; r < VB; ++r) {
+        const int pos = min(p0 + half * VB + r, L - 1);  // masked rows have p == 0
+        const uint32_t* vr = reinterpret_cast<const uint32_t*>(vbase + (size_t)pos * HS + lane * DPL);
+#pragma unroll
+        for (int w = 0; w < DPL / 2; ++w) vv[r][w] = __ldg(vr + w);
       }
 #pragma unroll
-      for (int h = 0; h < QPK; ++h) {
-        const float p = s_s[warp][h][pj];
+      for (int r = 0; r < VB; ++r) {
 #pragma unroll
-        for (int d = 0; d < DPL; ++d) acc[h][d] = fmaf(p, vf[d], acc[h][d]);
+        for (int h = 0; h < QPK; ++h) {
+          const float p = s_s[warp][h][half * VB + r];
+#pragma unroll
+          for (int w = 0; w < DPL / 2; ++w) {
+            acc[h][2 * w] = fmaf(p, bf16lo(vv[r][w]), acc[h][2 * w]);
+            acc[h][2 * w + 1] = fmaf(p, bf16hi(vv[r][w]), acc[h][2 * w + 1]);
+          }
+        }
       }
     }
     __syncwarp();
@@ -157,33 +181,47 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_decode_partial_kernel(const 
       o = fmaf(sc, mrg_acc[w][h][d], o);
       ll = fmaf(sc, mrg_l[w][h], ll);
     }
-    float* dst = a.part + ((size_t)(g * QPK + h) * a.n_split + split) * (HS + 2);
-    dst[2 + d] = o;
-    if (d == 0) { dst[0] = mm; dst[1] = ll; }
+    if (n_active == 1) {  // single span: final answer, no round trip through the partial buffer
+      a.y[(size_t)(g * QPK + h) * HS + d] = __float2bfloat16_rn(ll > 0.f ? o / ll : 0.f);
+    } else {
+      float* dst = a.part + ((size_t)(g * QPK + h) * a.n_split + split) * (HS + 2);
+      dst[2 + d] = o;
+      if (d == 0) { dst[0] = mm; dst[1] = ll; }
+    }
   }
-}
+  if (n_active == 1) return;
 
-template <int HS>
-__global__ void __launch_bounds__(HS) attn_decode_combine_kernel(const float* __restrict__ part, bf16* __restrict__ y,
-                                                                 int n_split) {
-  pdl_wait_prior();
-  pdl_launch_dependents();
-  const int h = blockIdx.x, d = threadIdx.x;
-  const float* base = part + (size_t)h * n_split * (HS + 2);
-  float mm = -INFINITY;
-  for (int s = 0; s < n_split; ++s) mm = fmaxf(mm, base[(size_t)s * (HS + 2)]);
-  float o = 0.f, ll = 0.f;
-  for (int s = 0; s < n_split; ++s) {
-    const float* p = base + (size_t)s * (HS + 2);
-    const float sc = (p[0] == -INFINITY) ? 0.f : exp2f(p[0] - mm);
-    o = fmaf(sc, p[2 + d], o);
-    ll = fmaf(sc, p[1], ll);
+  // ---- the group's last CTA merges the spans ------------------------------------------------------
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int prev = atomicAdd(a.tickets + g, 1u);
+    sh_last = (prev == (unsigned)n_active - 1);
+    if (sh_last) a.tickets[g] = 0;
   }
-  y[(size_t)h * HS + d] = __float2bfloat16_rn(ll > 0.f ? o / ll : 0.f);
+  __syncthreads();
+  if (!sh_last) return;
+  __threadfence();
+  for (int i = threadIdx.x; i < QPK * HS; i += ATT_THREADS) {
+    const int h = i / HS, d = i % HS;
+    const float* base = a.part + (size_t)(g * QPK + h) * a.n_split * (HS + 2);
+    float mm = -INFINITY;
+    for (int s = 0; s < n_active; ++s) mm = fmaxf(mm, __ldcg(base + (size_t)s * (HS + 2)));
+    float o = 0.f, ll = 0.f;
+#pragma unroll 4
+    for (int s = 0; s < n_active; ++s) {
+      const float* p = base + (size_t)s * (HS + 2);
+      const float pm = __ldcg(p), pl = __ldcg(p + 1), po = __ldcg(p + 2 + d);
+      const float sc = (pm == -INFINITY) ? 0.f : exp2f(pm - mm);
+      o = fmaf(sc, po, o);
+      ll = fmaf(sc, pl, ll);
+    }
+    a.y[(size_t)(g * QPK + h) * HS + d] = __float2bfloat16_rn(ll > 0.f ? o / ll : 0.f);
+  }
 }
 
 template <int HS, int QPK>
-static int launch_attn(const AttnArgs& a, bf16* y, int use_pdl, cudaStream_t stream) {
+static int launch_attn(const AttnArgs& a, int use_pdl, cudaStream_t stream) {
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
@@ -193,27 +231,24 @@ static int launch_attn(const AttnArgs& a, bf16* y, int use_pdl, cudaStream_t str
   cfg.stream = stream;
   cfg.attrs = attr;
   cfg.numAttrs = use_pdl ? 1 : 0;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, attn_decode_partial_kernel<HS, QPK>, a);
-  if (e != cudaSuccess) return (int)e;
-  cfg.gridDim = dim3(a.n_head);
-  cfg.blockDim = dim3(HS);
-  return (int)cudaLaunchKernelEx(&cfg, attn_decode_combine_kernel<HS>, (const float*)a.part, y, a.n_split);
+  return (int)cudaLaunchKernelEx(&cfg, attn_decode_kernel<HS, QPK>, a);
 }
 
 }  // namespace mdi
 
 using namespace mdi;
 
-extern "C" int mdi_attn_decode(const void* q, const void* kv, void* y, float* part, const int* ctx, int n_head,
-                               int n_groups, int head_size, int max_seq, int n_split, int use_pdl,
-                               cudaStream_t stream) {
+// part: fp32 [H, n_split, hs + 2]; tickets: uint32 [G], zeroed once at allocation.
+extern "C" int mdi_attn_decode(const void* q, const void* kv, void* y, float* part, unsigned int* tickets,
+                               const int* ctx, int n_head, int n_groups, int head_size, int max_seq, int n_split,
+                               int use_pdl, cudaStream_t stream) {
   AttnArgs a;
-  a.q = (const bf16*)q; a.kv = (const bf16*)kv; a.part = part; a.ctx = ctx;
+  a.q = (const bf16*)q; a.kv = (const bf16*)kv; a.y = (bf16*)y; a.part = part; a.tickets = tickets; a.ctx = ctx;
   a.n_head = n_head; a.n_groups = n_groups; a.max_seq = max_seq; a.n_split = n_split;
   a.scale_log2 = 1.4426950408889634f / sqrtf((float)head_size);
   const int qpk = n_head / n_groups;
 #define MDI_ATT_CASE(HS_, QPK_) \
-  if (head_size == HS_ && qpk == QPK_) return launch_attn<HS_, QPK_>(a, (bf16*)y, use_pdl, stream);
+  if (head_size == HS_ && qpk == QPK_) return launch_attn<HS_, QPK_>(a, use_pdl, stream);
   MDI_ATT_CASE(128, 1) MDI_ATT_CASE(128, 2) MDI_ATT_CASE(128, 4) MDI_ATT_CASE(128, 8)
   MDI_ATT_CASE(64, 1) MDI_ATT_CASE(64, 2) MDI_ATT_CASE(64, 4) MDI_ATT_CASE(64, 8)
 #undef MDI_ATT_CASE

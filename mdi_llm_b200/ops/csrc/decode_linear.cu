@@ -146,7 +146,15 @@ struct StreamArgs {
   bf16* q_out;       // [H * hs]
   bf16* kv;          // this layer's pool: [n_slots, 2, G, S, hs]
   int n_head, n_groups, head_size, rope_n_elem, max_seq;
+  // logits-only (lm_head): sampling statistics gathered while the logits are produced
+  unsigned int* hist;        // [4096] histogram of the top 12 bits of the orderable logit key, or null
+  unsigned long long* amax;  // packed (key << 32 | ~row) running arg-max, or null
 };
+
+__device__ __forceinline__ uint32_t float_key(float f) {  // monotone: larger float -> larger key
+  const uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
 
 enum Mode { MODE_PLAIN = 0, MODE_GATED = 1, MODE_QKV = 2 };
 
@@ -198,8 +206,15 @@ __device__ __forceinline__ void item_epilogue(const StreamArgs& a, int it, float
       else if (a.act == ACT_GELU_ERF) v = gelu_erf(round_bf16(v));
       if (res) v = round_bf16(v) + __bfloat162float(res[row]);
       // fp32 output = logits: bf16 values like nn.Linear would produce, kept in fp32 for the sampler
-      if (a.out_fp32) reinterpret_cast<float*>(a.y)[(size_t)slot * a.y_slot_stride + row] = round_bf16(v);
-      else reinterpret_cast<bf16*>(a.y)[(size_t)slot * a.y_slot_stride + row] = __float2bfloat16_rn(v);
+      if (a.out_fp32) {
+        v = round_bf16(v);
+        reinterpret_cast<float*>(a.y)[(size_t)slot * a.y_slot_stride + row] = v;
+        const uint32_t key = float_key(v);
+        if (a.hist) atomicAdd(a.hist + (key >> 20), 1u);
+        if (a.amax) atomicMax(a.amax, ((unsigned long long)key << 32) | (unsigned long long)(0xffffffffu - (uint32_t)row));
+      } else {
+        reinterpret_cast<bf16*>(a.y)[(size_t)slot * a.y_slot_stride + row] = __float2bfloat16_rn(v);
+      }
     }
   } else {
     const int hs = a.head_size, half_hs = hs / 2, ne = a.rope_n_elem, half_ne = ne / 2;
@@ -415,7 +430,7 @@ int mdi_linear_decode(const void* W, const void* W2, const void* bias, const voi
                       long long res_slot_stride, long long y_slot_stride, int N, int K, float eps, int unit_offset,
                       int act, int out_fp32, const int* wait_flag, int* status, long long wait_max_cycles,
                       int* signal_flag, unsigned int* done_ctr, int ctas_per_sm, int use_pdl, int variant,
-                      cudaStream_t stream) {
+                      unsigned int* hist, unsigned long long* amax, cudaStream_t stream) {
   if (K % 8 != 0) return -2;
   StreamArgs a{};
   a.W = (const bf16*)W; a.W2 = (const bf16*)W2; a.bias = (const bf16*)bias; a.bias2 = (const bf16*)bias2;
@@ -425,6 +440,7 @@ int mdi_linear_decode(const void* W, const void* W2, const void* bias, const voi
   a.wait = HopWait{wait_flag, status, wait_max_cycles};
   a.signal = HopSignal{signal_flag, done_ctr};
   a.n_items = W2 ? N : (N + 1) / 2;
+  a.hist = hist; a.amax = amax;
   if (variant < 0) variant = g_default_variant;
   if (W2) return launch_stream<MODE_GATED>(a, variant, ctas_per_sm, use_pdl, stream);
   return launch_stream<MODE_PLAIN>(a, variant, ctas_per_sm, use_pdl, stream);

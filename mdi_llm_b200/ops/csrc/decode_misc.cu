@@ -238,6 +238,187 @@ __global__ void __launch_bounds__(SMP_THREADS) sample_kernel(const SampleArgs a)
 }
 
 // ------------------------------------------------------------------------------------------------
+// Fast sampler (the decode path): the lm_head epilogue has already histogrammed the top 12 key
+// bits of every logit (and tracked the arg-max), so sampling is two short kernels:
+//   filter (many CTAs): find the histogram bin holding the k-th largest logit, append every
+//                       logit at or above that bin to a candidate list (a few hundred entries);
+//   final  (one CTA)  : exact top-k among the candidates (radix select in shared memory),
+//                       temperature softmax, one draw; resets the statistics for the next step.
+constexpr int SF_BINS = 4096;
+constexpr int SF_CAND_MAX = 8192;
+
+struct SampleFastArgs {
+  const float* logits;
+  unsigned int* hist;           // [4096]
+  unsigned long long* amax;     // [1]
+  unsigned int* cand_count;     // [1]
+  float* cand_val;              // [SF_CAND_MAX]
+  int* cand_idx;                // [SF_CAND_MAX]
+  int* tokens; long long tok_slot_stride; int* last_token;
+  const int* ctx;
+  int V, top_k; float temperature; int greedy; unsigned long long seed;
+};
+
+__global__ void __launch_bounds__(256) sample_filter_kernel(const SampleFastArgs a) {
+  __shared__ unsigned int tsum[256];
+  __shared__ int sh_bin;
+  pdl_wait_prior();
+  pdl_launch_dependents();
+  if (a.greedy) return;
+  const int tid = threadIdx.x;
+  const int k = (a.top_k > 0 && a.top_k < a.V) ? min(a.top_k, 1024) : min(a.V, 1024);
+  // threshold bin: highest b with sum_{j >= b} hist[j] >= k   (thread t owns bins [16t, 16t+16))
+  unsigned int loc[16], s = 0;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) { loc[j] = __ldcg(a.hist + tid * 16 + j); s += loc[j]; }
+  tsum[tid] = s;
+  if (tid == 0) sh_bin = 0;
+  __syncthreads();
+  unsigned int above = 0;  // population of all bins owned by higher threads
+  for (int t = tid + 1; t < 256; ++t) above += tsum[t];
+  if (above < (unsigned)k && above + s >= (unsigned)k) {
+    unsigned int cum = above;
+    int j = 15;
+    for (; j > 0; --j) {
+      if (cum + loc[j] >= (unsigned)k) break;
+      cum += loc[j];
+    }
+    sh_bin = tid * 16 + j;
+  }
+  __syncthreads();
+  const uint32_t bin = (uint32_t)sh_bin;
+  for (int i = blockIdx.x * blockDim.x + tid; i < a.V; i += gridDim.x * blockDim.x) {
+    const float v = __ldcg(a.logits + i);
+    if ((float_key(v) >> 20) >= bin) {
+      const unsigned int slot = atomicAdd(a.cand_count, 1u);
+      if (slot < SF_CAND_MAX) { a.cand_val[slot] = v; a.cand_idx[slot] = i; }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(SMP_THREADS) sample_final_kernel(const SampleFastArgs a) {
+  extern __shared__ __align__(16) unsigned char sf_smem[];
+  float* cv = reinterpret_cast<float*>(sf_smem);             // [SF_CAND_MAX]
+  int* ci = reinterpret_cast<int*>(sf_smem) + SF_CAND_MAX;  // [SF_CAND_MAX]
+  __shared__ unsigned int hist[256];
+  __shared__ float top_val[SMP_KMAX], sorted_val[SMP_KMAX];
+  __shared__ int top_idx[SMP_KMAX], sorted_idx[SMP_KMAX];
+  __shared__ float red_f[32];
+  __shared__ unsigned int sh_prefix, sh_kleft, sh_count;
+  __shared__ float sh_max, sh_sum;
+  __shared__ int sh_pick;
+  pdl_wait_prior();
+  pdl_launch_dependents();
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int slot = a.ctx[MDI_CTX_SLOT], pos = a.ctx[MDI_CTX_POS];
+
+  if (a.greedy) {
+    if (tid == 0) {
+      const unsigned long long best = *a.amax;
+      const int tok = (int)(0xffffffffu - (uint32_t)(best & 0xffffffffull));
+      a.tokens[(size_t)slot * a.tok_slot_stride + pos] = tok;
+      if (a.last_token) a.last_token[slot] = tok;
+      *a.amax = 0ull;
+    }
+    return;
+  }
+  const int n_cand = (int)min(__ldcg(a.cand_count), (unsigned)SF_CAND_MAX);
+  for (int i = tid; i < n_cand; i += SMP_THREADS) { cv[i] = __ldcg(a.cand_val + i); ci[i] = __ldcg(a.cand_idx + i); }
+  int k = (a.top_k > 0 && a.top_k < a.V) ? a.top_k : a.V;
+  k = min(min(k, SMP_KMAX), n_cand);
+  if (tid == 0) { sh_prefix = 0; sh_kleft = (unsigned)k; }
+  __syncthreads();
+  for (int pass = 0; pass < 4; ++pass) {  // exact k-th largest among the candidates
+    const int shift = 24 - 8 * pass;
+    if (tid < 256) hist[tid] = 0;
+    __syncthreads();
+    const unsigned int prefix = sh_prefix;
+    const unsigned int mask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
+    for (int i = tid; i < n_cand; i += SMP_THREADS) {
+      const uint32_t key = float_key(cv[i]);
+      if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 0xffu], 1u);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      unsigned int left = sh_kleft, cum = 0;
+      int b = 255;
+      for (; b > 0; --b) {
+        if (cum + hist[b] >= left) break;
+        cum += hist[b];
+      }
+      sh_kleft = left - cum;
+      sh_prefix = prefix | ((unsigned)b << shift);
+    }
+    __syncthreads();
+  }
+  const uint32_t thr = sh_prefix;
+  const unsigned int n_ties = sh_kleft;
+  if (tid == 0) sh_count = 0;
+  __syncthreads();
+  for (int i = tid; i < n_cand; i += SMP_THREADS)
+    if (float_key(cv[i]) > thr) {
+      const unsigned int s = atomicAdd(&sh_count, 1u);
+      if (s < SMP_KMAX) { top_val[s] = cv[i]; top_idx[s] = ci[i]; }
+    }
+  __syncthreads();
+  const unsigned int n_greater = min(sh_count, (unsigned)SMP_KMAX);
+  __syncthreads();
+  if (tid == 0) sh_count = 0;
+  __syncthreads();
+  for (int i = tid; i < n_cand; i += SMP_THREADS)
+    if (float_key(cv[i]) == thr) {
+      const unsigned int s = atomicAdd(&sh_count, 1u);
+      if (s < n_ties && n_greater + s < SMP_KMAX) { top_val[n_greater + s] = cv[i]; top_idx[n_greater + s] = ci[i]; }
+    }
+  __syncthreads();
+  const int n = (int)min(n_greater + n_ties, (unsigned)SMP_KMAX);
+  if (tid < n) {  // order by vocabulary index: a fixed seed gives a fixed token
+    const int my = top_idx[tid];
+    int rank = 0;
+    for (int j = 0; j < n; ++j) rank += (top_idx[j] < my);
+    sorted_idx[rank] = my;
+    sorted_val[rank] = top_val[tid];
+  }
+  __syncthreads();
+  const float inv_t = a.temperature > 0.f ? 1.f / a.temperature : 1.f;
+  const float v = tid < n ? sorted_val[tid] * inv_t : -INFINITY;
+  const float mx = warp_max(v);
+  if (lane == 0) red_f[warp] = mx;
+  __syncthreads();
+  if (warp == 0) { const float t = warp_max(red_f[lane]); if (lane == 0) sh_max = t; }
+  __syncthreads();
+  const float e = tid < n ? __expf(v - sh_max) : 0.f;
+  float sc = e;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const float t = __shfl_up_sync(0xffffffffu, sc, o); if (lane >= o) sc += t; }
+  __syncthreads();
+  if (lane == 31) red_f[warp] = sc;
+  __syncthreads();
+  if (warp == 0) {
+    float w = red_f[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const float t = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += t; }
+    red_f[lane] = w;
+    if (lane == 31) sh_sum = w;
+  }
+  __syncthreads();
+  const float incl = sc + (warp > 0 ? red_f[warp - 1] : 0.f);
+  const float excl = incl - e;
+  const uint64_t r = splitmix64(a.seed ^ splitmix64(((uint64_t)(uint32_t)slot << 32) | (uint32_t)pos));
+  const float u = (float)((r >> 40) * (1.0 / 16777216.0)) * sh_sum;
+  if (tid == 0) sh_pick = n > 0 ? sorted_idx[n - 1] : 0;
+  __syncthreads();
+  if (tid < n && e > 0.f && u >= excl && u < incl) sh_pick = sorted_idx[tid];
+  __syncthreads();
+  if (tid == 0) {
+    a.tokens[(size_t)slot * a.tok_slot_stride + pos] = sh_pick;
+    if (a.last_token) a.last_token[slot] = sh_pick;
+    *a.cand_count = 0;
+  }
+  for (int i = tid; i < SF_BINS; i += SMP_THREADS) a.hist[i] = 0;  // statistics ready for the next token
+}
+
+// ------------------------------------------------------------------------------------------------
 // Device-driven schedule.  state[0] = global step counter; per slot: pos[slot].
 // Step t serves slot = t % n_slots at round = t / n_slots.
 //   secondary : wait = round + 1 (message `round` has arrived), signal = round + 1
@@ -326,6 +507,48 @@ int mdi_sample(const float* logits, long long logits_slot_stride, int* tokens, l
   SampleArgs a{logits, logits_slot_stride, tokens, tok_slot_stride, last_token, ctx, V, top_k, temperature, greedy, seed};
   void* args[] = {&a};
   return launch_small((const void*)sample_kernel, dim3(1), dim3(SMP_THREADS), args, use_pdl, stream);
+}
+
+// scratch: u32 hist[4096] | u64 amax | u32 cand_count | pad | f32 cand_val[8192] | i32 cand_idx[8192]
+size_t mdi_sample_scratch_bytes() { return 4096 * 4 + 8 + 8 + 8192 * 4 + 8192 * 4; }
+
+int mdi_sample_fast(const float* logits, void* scratch, int* tokens, long long tok_slot_stride, int* last_token,
+                    const int* ctx, int V, int top_k, float temperature, int greedy, unsigned long long seed,
+                    int use_pdl, cudaStream_t stream) {
+  char* base = (char*)scratch;
+  SampleFastArgs a;
+  a.logits = logits;
+  a.hist = (unsigned int*)base;
+  a.amax = (unsigned long long*)(base + 4096 * 4);
+  a.cand_count = (unsigned int*)(base + 4096 * 4 + 8);
+  a.cand_val = (float*)(base + 4096 * 4 + 16);
+  a.cand_idx = (int*)(base + 4096 * 4 + 16 + 8192 * 4);
+  a.tokens = tokens; a.tok_slot_stride = tok_slot_stride; a.last_token = last_token; a.ctx = ctx;
+  a.V = V; a.top_k = top_k; a.temperature = temperature; a.greedy = greedy; a.seed = seed;
+  void* args[] = {&a};
+  int rc = 0;
+  if (!greedy) {
+    rc = launch_small((const void*)sample_filter_kernel, dim3(64), dim3(256), args, use_pdl, stream);
+    if (rc) return rc;
+  }
+  const size_t smem = (size_t)SF_CAND_MAX * 8;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(sample_final_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(1);
+  cfg.blockDim = dim3(SMP_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cfg.attrs = attr;
+  cfg.numAttrs = use_pdl ? 1 : 0;
+  return (int)cudaLaunchKernelExC(&cfg, (const void*)sample_final_kernel, args);
 }
 
 int mdi_advance_step(int* ctx, int* state, int* pos_arr, int n_slots, int is_starter, int use_pdl, cudaStream_t stream) {

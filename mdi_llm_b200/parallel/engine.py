@@ -154,10 +154,12 @@ class FusedStage:
             sms = torch.cuda.get_device_properties(dev).multi_processor_count
             self.n_split = max(1, min(64, (2 * sms) // max(1, cfg.n_query_groups)))
             self.part = torch.zeros(cfg.n_head * self.n_split * (cfg.head_size + 2), dtype=torch.float32, device=dev)
+            self.tickets = torch.zeros(cfg.n_query_groups, **i32)
             if self.is_starter:
                 self.logits = torch.zeros(cfg.padded_vocab_size, dtype=torch.float32, device=dev)
                 self.tokens = torch.zeros(n_slots, self.S + 1, **i32)
                 self.last_token = torch.zeros(n_slots, **i32)
+                self.sample_scratch = ops.sample_scratch(dev)
         self.hop_self = HopTarget(self.hidden_in.data_ptr(), self.flags.data_ptr())
         self._graphs: Dict[Any, ops.CudaGraph] = {}
         self._check_weights()
@@ -174,22 +176,25 @@ class FusedStage:
         return "gelu_tanh_gate" if self.cfg.gelu_approximate == "tanh" else "gelu_erf_gate"
 
     # ---- kernel sequences ------------------------------------------------------------------------
-    def enqueue_head(self, wait: bool) -> None:
-        """starter: final RMSNorm + lm_head on ``hidden_in[slot]`` → fp32 logits."""
+    def enqueue_head(self, wait: bool, stats: bool = True) -> None:
+        """starter: final RMSNorm + lm_head on ``hidden_in[slot]`` → fp32 logits (+ the sampler's
+        logit histogram / arg-max, gathered in the same pass when ``stats``)."""
         m, cfg = self.model, self.cfg
         ops.linear_decode(
             m.lm_head.weight, self.hidden_in, self.logits, self.ctx, bias=m.lm_head.bias,
             norm_w=m.transformer.ln_f.weight, eps=cfg.norm_eps, unit_offset=cfg.unit_offset_norm,
             x_slot_stride=cfg.n_embd, wait_flag=self.flags.data_ptr() if wait else None,
             status=self.status.data_ptr(), wait_max_cycles=self.wait_max_cycles, ctas_per_sm=self.ctas_per_sm,
-            use_pdl=self.use_pdl)
+            use_pdl=self.use_pdl, stats=self.sample_scratch if stats else None)
 
     def enqueue_sample(self) -> None:
+        """Must follow ``enqueue_head(stats=True)``: consumes (and clears) the logit statistics."""
         s = self.sampling
         greedy = not (s.temperature > 0.0 or s.top_p > 0.0)
-        ops.sample(self.logits, self.tokens, self.ctx, vocab=self.cfg.padded_vocab_size, top_k=s.top_k,
-                   temperature=s.temperature, greedy=greedy, seed=s.seed if s.seed is not None else 0x5EED,
-                   tok_slot_stride=self.tokens.shape[1], last_token=self.last_token, use_pdl=self.use_pdl)
+        ops.sample_fast(self.logits, self.sample_scratch, self.tokens, self.ctx, vocab=self.cfg.padded_vocab_size,
+                        top_k=s.top_k, temperature=s.temperature, greedy=greedy,
+                        seed=s.seed if s.seed is not None else 0x5EED, tok_slot_stride=self.tokens.shape[1],
+                        last_token=self.last_token, use_pdl=self.use_pdl)
 
     def enqueue_embed(self, from_tokens: bool) -> None:
         m, cfg = self.model, self.cfg
@@ -213,7 +218,7 @@ class FusedStage:
                 eps=cfg.norm_eps, unit_offset=cfg.unit_offset_norm, x_slot_stride=x_in_stride,
                 wait_flag=self.flags.data_ptr() if (first and wait_input and not self.is_starter) else None,
                 status=self.status.data_ptr(), wait_max_cycles=self.wait_max_cycles, **common)
-            ops.attn_decode(self.q, kv_layer, self.y_attn, self.part, self.ctx, n_head=cfg.n_head,
+            ops.attn_decode(self.q, kv_layer, self.y_attn, self.part, self.tickets, self.ctx, n_head=cfg.n_head,
                             n_groups=cfg.n_query_groups, head_size=cfg.head_size, max_seq=self.S,
                             n_split=self.n_split, use_pdl=self.use_pdl)
             ops.linear_decode(blk.attn.proj.weight, self.y_attn, self.xb, self.ctx, bias=blk.attn.proj.bias,
@@ -328,5 +333,5 @@ class FusedStageRunner(StageRunner):
         with torch.cuda.device(self.device):
             st.hidden_in[0].copy_(hidden[0, -1].to(self.dtype))
             st.set_ctx(0, 0)
-            self._run("head", lambda: st.enqueue_head(wait=False))
+            self._run("head", lambda: st.enqueue_head(wait=False, stats=False))
             return st.logits.view(1, 1, -1).clone()

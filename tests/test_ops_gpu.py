@@ -146,14 +146,17 @@ def test_attn_decode_matches_sdpa(H, G, hs, L):
     q = torch.randn(H * hs, device="cuda").bfloat16()
     kv = torch.randn(n_slots, 2, G, S, hs, device="cuda").bfloat16()
     y = torch.zeros(H * hs, device="cuda", dtype=torch.bfloat16)
+    tickets = torch.zeros(G, device="cuda", dtype=torch.int32)
     for n_split in (1, 5, 37):
         part = torch.zeros(H * n_split * (hs + 2), device="cuda", dtype=torch.float32)
-        ops.attn_decode(q, kv, y, part, _ctx(ops, slot=slot, pos=L - 1), n_head=H, n_groups=G, head_size=hs,
+        y.zero_()
+        ops.attn_decode(q, kv, y, part, tickets, _ctx(ops, slot=slot, pos=L - 1), n_head=H, n_groups=G, head_size=hs,
                         max_seq=S, n_split=n_split)
         k = kv[slot, 0, :, :L].float().repeat_interleave(H // G, 0)
         v = kv[slot, 1, :, :L].float().repeat_interleave(H // G, 0)
         ref = torch.softmax((q.view(H, 1, hs).float() @ k.transpose(1, 2)) / math.sqrt(hs), -1) @ v
         torch.testing.assert_close(y.view(H, hs).float(), ref.view(H, hs), rtol=2e-2, atol=2e-2)
+        assert tickets.abs().sum() == 0  # self-resetting
 
 
 def test_embed_and_rmsnorm_rows():
@@ -207,6 +210,34 @@ def test_sample_greedy_and_topk_distribution():
     assert tokens[0, 1].item() == a
     top200 = set(torch.topk(logits, 200).indices.tolist())
     assert a in top200
+
+
+@pytest.mark.parametrize("greedy,top_k,temp", [(True, None, 0.0), (False, 200, 0.8), (False, 3, 0.5), (False, 1000, 1.3)])
+def test_fast_sampler_equals_reference_sampler(greedy, top_k, temp):
+    """lm_head-fused statistics + filter/final kernels pick exactly the token the single-CTA
+    full-vocabulary reference sampler picks (same key order, same RNG stream)."""
+    ops = _ops()
+    ops.set_linear_variant(0)
+    torch.manual_seed(5)
+    V, K = 128256, 512
+    W = torch.randn(V, K, device="cuda").bfloat16()
+    nw = torch.ones(K, device="cuda", dtype=torch.bfloat16)
+    scratch = ops.sample_scratch("cuda")
+    logits = torch.zeros(V, device="cuda", dtype=torch.float32)
+    tok_a = torch.zeros(1, 32, dtype=torch.int32, device="cuda")
+    tok_b = torch.zeros(1, 32, dtype=torch.int32, device="cuda")
+    for step in range(12):
+        x = torch.randn(K, device="cuda").bfloat16()
+        ctx = _ctx(ops, slot=0, pos=step)
+        ops.linear_decode(W, x, logits, ctx, norm_w=nw, stats=scratch)
+        ops.sample_fast(logits, scratch, tok_a, ctx, vocab=V, top_k=top_k, temperature=temp, greedy=greedy, seed=77,
+                        tok_slot_stride=32)
+        ops.sample(logits, tok_b, ctx, vocab=V, top_k=top_k, temperature=temp, greedy=greedy, seed=77, tok_slot_stride=32)
+        torch.cuda.synchronize()
+        assert tok_a[0, step].item() == tok_b[0, step].item(), f"step {step}"
+        if greedy:
+            assert tok_a[0, step].item() == int(torch.argmax(logits))
+    assert scratch[: 4096 + 4].abs().sum() == 0  # histogram, arg-max and candidate counter were reset
 
 
 @pytest.mark.parametrize("variant", [0, 1])
