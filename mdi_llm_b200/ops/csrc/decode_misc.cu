@@ -320,6 +320,7 @@ __global__ void __launch_bounds__(SMP_THREADS) sample_final_kernel(const SampleF
       if (a.last_token) a.last_token[slot] = tok;
       *a.amax = 0ull;
     }
+    for (int i = tid; i < SF_BINS; i += SMP_THREADS) a.hist[i] = 0;
     return;
   }
   const int n_cand = (int)min(__ldcg(a.cand_count), (unsigned)SF_CAND_MAX);
@@ -414,6 +415,7 @@ __global__ void __launch_bounds__(SMP_THREADS) sample_final_kernel(const SampleF
     a.tokens[(size_t)slot * a.tok_slot_stride + pos] = sh_pick;
     if (a.last_token) a.last_token[slot] = sh_pick;
     *a.cand_count = 0;
+    *a.amax = 0ull;
   }
   for (int i = tid; i < SF_BINS; i += SMP_THREADS) a.hist[i] = 0;  // statistics ready for the next token
 }
