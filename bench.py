@@ -171,6 +171,7 @@ def run_ours(args: argparse.Namespace) -> Dict[str, Any]:
         sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = pipe.n_graph_launches
+    wait0 = pipe.stage.wait_cycles()
     ev0.record()
     pipe.decode_rounds(args.steps)
     ev1.record()
@@ -185,7 +186,14 @@ def run_ours(args: argparse.Namespace) -> Dict[str, Any]:
     ms_total = float(ms.item())
     tokens = args.steps * n_samples
     value = tokens / (ms_total / 1e3)
-    status = int(pipe.stage.status.item())
+    status = int(pipe.stage.status[0].item())
+    # exposed wait per stage step (cycles CTA 0 spun on the incoming hop flag), gathered from all ranks
+    sm_clock_khz = torch.cuda.get_device_properties(device).clock_rate if hasattr(torch.cuda.get_device_properties(device), "clock_rate") else 1_965_000
+    wait_us = (pipe.stage.wait_cycles() - wait0) / (sm_clock_khz / 1e3) / max(1, args.steps * n_samples)
+    waits = torch.zeros(world, device=device, dtype=torch.float64)
+    waits[rank] = wait_us
+    if world > 1:
+        dist.all_reduce(waits, op=dist.ReduceOp.SUM)
 
     # ---------------- end to end through the host-fed public API ----------------
     pinned = [p.pin_memory() for p in prompts]  # inputs start in pinned host memory
@@ -221,6 +229,8 @@ def run_ours(args: argparse.Namespace) -> Dict[str, Any]:
                 "how": "host-fed steps: pinned ctx H2D + sampled-token D2H every step, wall clock, max over ranks"},
         "gpu_launches": int(launches.item()),
         "hop_watchdog_status": status,
+        "stage_wait_us_per_step": [round(x, 2) for x in waits.tolist()],
+        "stage_busy_us_per_step": [round(ms_total * 1e3 / (args.steps * n_samples) - x, 2) for x in waits.tolist()],
     }
     if args.tiny:
         out["config"]["WARNING"] = "tiny smoke model — not the BASELINE config"

@@ -86,24 +86,31 @@ struct HopSignal {  // producer side; flag == nullptr disables
   unsigned int* done_ctr;  // local counter of finished CTAs (self-resetting)
 };
 
-// All threads call; thread 0 spins, everybody leaves after the flag for ctx's slot >= ctx's seq.
+// All threads call; thread 0 spins, everybody leaves after the flag for ctx's slot >= ctx's wait value.
+// status[0] = watchdog error; status[2..3] (as one 64-bit word) accumulates the cycles CTA 0 spent
+// waiting — the *exposed* hop/idle time the benchmark reports per token.
 __device__ __forceinline__ void hop_wait(const HopWait& w, const int* ctx) {
   if (w.flag == nullptr) return;
   if (threadIdx.x == 0) {
-    int slot = ctx[MDI_CTX_SLOT], want = ctx[MDI_CTX_WAIT];
+    const int slot = ctx[MDI_CTX_SLOT], want = ctx[MDI_CTX_WAIT];
+    const long long t0 = clock64();
     if (!wait_flag_ge(w.flag + slot, want, w.max_cycles) && w.status) atomicExch(w.status, 1);
+    if (w.status && blockIdx.x == 0 && blockIdx.y == 0)
+      atomicAdd(reinterpret_cast<unsigned long long*>(w.status + 2), (unsigned long long)(clock64() - t0));
   }
   __syncthreads();
 }
 
 // Called by every CTA after its output stores.  The last CTA to arrive publishes the flag.
+// Ordering: the CTA's stores -> bar.sync -> thread 0's system-scope fence (cumulative) -> ticket;
+// the last ticket holder fences again and releases the flag (same pattern as a grid barrier).
 __device__ __forceinline__ void hop_signal(const HopSignal& s, const int* ctx) {
   if (s.flag == nullptr) return;
-  __threadfence_system();  // every thread: its (possibly remote) stores are visible system-wide
   __syncthreads();
   if (threadIdx.x == 0) {
-    unsigned int total = gridDim.x * gridDim.y * gridDim.z;
-    unsigned int prev = atomicAdd(s.done_ctr, 1u);
+    __threadfence_system();
+    const unsigned int total = gridDim.x * gridDim.y * gridDim.z;
+    const unsigned int prev = atomicAdd(s.done_ctr, 1u);
     if (prev == total - 1) {
       *s.done_ctr = 0;  // ready for the next launch (stream-ordered)
       __threadfence_system();

@@ -144,7 +144,7 @@ class FusedStage:
             self._ring_i = 0
             self.state = torch.zeros(4, **i32)
             self.pos_arr = torch.zeros(n_slots, **i32)
-            self.status = torch.zeros(1, **i32)
+            self.status = torch.zeros(4, **i32)  # [0] watchdog flag, [2:4] 64-bit exposed-wait cycle counter
             self.done_ctr = torch.zeros(1, **i32)
             self.xa = torch.zeros(C, **bf)
             self.xb = torch.zeros(C, **bf)
@@ -254,6 +254,11 @@ class FusedStage:
                     builder()
             self._graphs[key] = g
         return g
+
+    def wait_cycles(self) -> int:
+        """Cycles CTA 0 of the hop-consuming kernels spent spinning on the incoming flag so far."""
+        lo, hi = self.status[2].item(), self.status[3].item()
+        return (lo & 0xFFFFFFFF) | ((hi & 0xFFFFFFFF) << 32)
 
     def warmup(self) -> None:
         """Launch every kernel of the step once with hops disabled (slot 0, position 0)."""

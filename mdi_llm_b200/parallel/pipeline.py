@@ -252,7 +252,7 @@ class DevicePipeline:
         st = self.stage
         assert self.is_starter
         torch.cuda.synchronize(self.device)
-        if int(st.status.item()) != 0:
+        if int(st.status[0].item()) != 0:
             raise RuntimeError("hop watchdog expired: a pipeline stage stopped responding")
         done = min(self.round - 1, self.max_new)
         out = {}
