@@ -181,7 +181,7 @@ __device__ __forceinline__ void item_rows(const StreamArgs& a, int it, const bf1
 // lane 0 of the owning warp: bias / activation / residual / RoPE / KV append, then the store
 template <int MODE>
 __device__ __forceinline__ void item_epilogue(const StreamArgs& a, int it, float da, float db, int slot, int pos,
-                                              const bf16* res) {
+                                              const bf16* res, unsigned int* hist_s, unsigned long long& best) {
   if (MODE == MODE_GATED) {
     if (a.bias) da += __bfloat162float(a.bias[it]);
     if (a.bias2) db += __bfloat162float(a.bias2[it]);
@@ -209,9 +209,12 @@ __device__ __forceinline__ void item_epilogue(const StreamArgs& a, int it, float
       if (a.out_fp32) {
         v = round_bf16(v);
         reinterpret_cast<float*>(a.y)[(size_t)slot * a.y_slot_stride + row] = v;
-        const uint32_t key = float_key(v);
-        if (a.hist) atomicAdd(a.hist + (key >> 20), 1u);
-        if (a.amax) atomicMax(a.amax, ((unsigned long long)key << 32) | (unsigned long long)(0xffffffffu - (uint32_t)row));
+        if (hist_s) {  // sampling statistics: CTA-local histogram + per-warp arg-max, flushed once at the end
+          const uint32_t key = float_key(v);
+          atomicAdd(hist_s + (key >> 20), 1u);
+          const unsigned long long packed = ((unsigned long long)key << 32) | (unsigned long long)(0xffffffffu - (uint32_t)row);
+          best = packed > best ? packed : best;
+        }
       } else {
         reinterpret_cast<bf16*>(a.y)[(size_t)slot * a.y_slot_stride + row] = __float2bfloat16_rn(v);
       }
@@ -247,6 +250,26 @@ __device__ __forceinline__ void item_epilogue(const StreamArgs& a, int it, float
   }
 }
 
+constexpr int STAT_BINS = 4096;
+
+// zero the CTA-local histogram (placed after everything else in dynamic smem)
+__device__ __forceinline__ unsigned int* stats_begin(const StreamArgs& a, unsigned char* smem_after) {
+  if (a.hist == nullptr) return nullptr;
+  unsigned int* h = reinterpret_cast<unsigned int*>(smem_after);
+  for (int i = threadIdx.x; i < STAT_BINS; i += LIN_THREADS) h[i] = 0;
+  return h;  // visibility: the callers __syncthreads() in stage_input before any epilogue runs
+}
+// one global atomic per populated bin per CTA, one atomicMax per warp
+__device__ __forceinline__ void stats_flush(const StreamArgs& a, unsigned int* hist_s, unsigned long long best) {
+  if (hist_s == nullptr) return;
+  __syncthreads();
+  for (int i = threadIdx.x; i < STAT_BINS; i += LIN_THREADS) {
+    const unsigned int c = hist_s[i];
+    if (c) atomicAdd(a.hist + i, c);
+  }
+  if ((threadIdx.x & 31) == 0 && best != 0ull && a.amax) atomicMax(a.amax, best);
+}
+
 // ---- variant A: register-streamed (LDG.128 batches) ---------------------------------------------
 template <int MODE>
 __global__ void __launch_bounds__(LIN_THREADS, 3) stream_ldg_kernel(const StreamArgs a) {
@@ -262,6 +285,8 @@ __global__ void __launch_bounds__(LIN_THREADS, 3) stream_ldg_kernel(const Stream
     item_rows<MODE>(a, gw, wa, wb);
     for (int off = lane * 64; off < a.K; off += 32 * 64) { prefetch_l2(wa + off); prefetch_l2(wb + off); }
   }
+  unsigned int* hist_s = stats_begin(a, smem_raw + (size_t)((a.K + 63) / 64) * 64 * sizeof(bf16));
+  unsigned long long best = 0ull;
   pdl_wait_prior();
   hop_wait(a.wait, a.ctx);
   const int slot = a.ctx ? a.ctx[MDI_CTX_SLOT] : 0, pos = a.ctx ? a.ctx[MDI_CTX_POS] : 0;
@@ -276,8 +301,9 @@ __global__ void __launch_bounds__(LIN_THREADS, 3) stream_ldg_kernel(const Stream
     item_rows<MODE>(a, it, wa, wb);
     float da, db;
     warp_dot2(wa, wb, xv, nvec, lane, da, db);
-    if (lane == 0) item_epilogue<MODE>(a, it, da, db, slot, pos, res);
+    if (lane == 0) item_epilogue<MODE>(a, it, da, db, slot, pos, res, hist_s, best);
   }
+  stats_flush(a, hist_s, best);
   hop_signal(a.signal, a.ctx);
 }
 
@@ -322,6 +348,8 @@ __global__ void __launch_bounds__(LIN_THREADS, 1) stream_bulk_kernel(const Strea
   };
   if (lane == 0)
     for (int f = 0; f < min(STAGES - 1, total); ++f) issue(f);
+  unsigned int* hist_s = stats_begin(a, reinterpret_cast<unsigned char*>(bars - warp * STAGES + LIN_WARPS * STAGES));
+  unsigned long long best = 0ull;
 
   pdl_wait_prior();
   hop_wait(a.wait, a.ctx);
@@ -353,13 +381,14 @@ __global__ void __launch_bounds__(LIN_THREADS, 1) stream_bulk_kernel(const Strea
     }
     if (++c == n_chunks) {
       const float da = warp_sum(a0 + a1), db = warp_sum(b0 + b1);
-      if (lane == 0) item_epilogue<MODE>(a, gw + ii * n_gw, da, db, slot, pos, res);
+      if (lane == 0) item_epilogue<MODE>(a, gw + ii * n_gw, da, db, slot, pos, res, hist_s, best);
       a0 = a1 = b0 = b1 = 0.f;
       c = 0;
       ++ii;
     }
     __syncwarp();  // everyone is done with stage `st` before lane 0 re-arms it next iteration
   }
+  stats_flush(a, hist_s, best);
   hop_signal(a.signal, a.ctx);
 }
 
@@ -402,11 +431,12 @@ static int launch_stream(const StreamArgs& a, int variant, int ctas_per_sm, int 
   const int max_useful = (a.n_items + LIN_WARPS - 1) / LIN_WARPS;
   if (variant == 0) {
     const int grid = max(1, min(sms * ctas_per_sm, max_useful));
-    return launch_pdl(stream_ldg_kernel<MODE>, a, grid, (size_t)a.K * sizeof(bf16), stream, use_pdl);
+    const size_t smem0 = (size_t)((a.K + 63) / 64) * 64 * sizeof(bf16) + (a.hist ? STAT_BINS * 4 : 0);
+    return launch_pdl(stream_ldg_kernel<MODE>, a, grid, smem0, stream, use_pdl);
   }
   const int stages = variant == 1 ? 4 : 2;
   const size_t smem = (size_t)LIN_WARPS * stages * 2 * TS_CHUNK * 2 + (size_t)((a.K + 63) / 64) * 64 * 2 +
-                      (size_t)LIN_WARPS * stages * 8;
+                      (size_t)LIN_WARPS * stages * 8 + (a.hist ? STAT_BINS * 4 : 0);
   if (smem > 227 * 1024) return -2;
   const int per_sm = variant == 1 ? 1 : max(1, min(ctas_per_sm, (int)((227 * 1024) / (smem + 1024))));
   const int grid = max(1, min(sms * per_sm, max_useful));
