@@ -140,7 +140,8 @@ def run_reference(args: Any) -> Dict[str, Any]:
             del full_sd
         if world > 1:
             dist.barrier()
-        topo = _topology(world, 18000 + (os.getpid() % 500) * 0 + 0)
+        # ports derived from the rendezvous port so that concurrent / stale runs never collide
+        topo = _topology(world, 20000 + (int(os.environ.get("MASTER_PORT", "29500")) % 2000) * 10)
         topo_file = ckpt.parent / f"nodes_{world}.json"
         if rank == 0:
             topo_file.write_text(json.dumps(topo))

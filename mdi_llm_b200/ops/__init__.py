@@ -18,7 +18,7 @@ import torch
 from . import build as _build
 
 __all__ = ["lib", "available", "require", "OpsError", "ptr", "stream_ptr", "check", "ACT", "CTX_INTS",
-           "linear_decode", "qkv_decode", "attn_decode", "embed", "rmsnorm_rows", "sample", "advance_step",
+           "linear_decode", "qkv_decode", "attn_decode", "gemm", "sample_fast", "sample_scratch", "embed", "rmsnorm_rows", "sample", "advance_step",
            "CudaGraph"]
 
 CTX_SLOT, CTX_POS, CTX_WAIT, CTX_SIGNAL, CTX_TOKEN, CTX_STEP = 0, 1, 2, 3, 4, 5
@@ -49,6 +49,7 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.mdi_sample.argtypes = [vp, i64, vp, i64, vp, vp, i32, i32, f32, i32, c_ulonglong, i32, vp]
     lib.mdi_sample_fast.argtypes = [vp, vp, vp, i64, vp, vp, i32, i32, f32, i32, c_ulonglong, i32, vp]
     lib.mdi_sample_scratch_bytes.restype = c_size_t
+    lib.mdi_gemm_bf16.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp]
     lib.mdi_advance_step.argtypes = [vp, vp, vp, i32, i32, i32, vp]
     lib.mdi_wait_flag.argtypes = [vp, vp, vp, i64, vp]
     lib.mdi_set_flag.argtypes = [vp, vp, vp]
@@ -213,6 +214,22 @@ def sample(logits: torch.Tensor, tokens: torch.Tensor, ctx: torch.Tensor, *, voc
     check(lib().mdi_sample(ptr(logits), logits_slot_stride, ptr(tokens), tok_slot_stride, ptr(last_token), ptr(ctx),
                            vocab, int(top_k or 0), float(temperature), int(greedy), seed & (2 ** 64 - 1), int(use_pdl),
                            stream_ptr()), "sample")
+
+
+def gemm(a: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
+         out: Optional[torch.Tensor] = None, block_n: int = 128, _knobs: Tuple[int, int, int, int] = (0, 0, 0, 0)) -> torch.Tensor:
+    """``a [M, K] @ w [N, K]^T (+bias) (+residual)`` on the tcgen05 tensor cores (TMA-fed, TMEM
+    accumulator) — the prefill GEMM.  bf16 in/out, fp32 accumulate."""
+    _bf16(a, "a"); _bf16(w, "w"); _bf16(bias, "bias"); _bf16(residual, "residual")
+    M, K = a.shape
+    N = w.shape[0]
+    if w.shape[1] != K:
+        raise OpsError(f"gemm: inner dimensions differ ({K} vs {w.shape[1]})")
+    if out is None:
+        out = torch.empty(M, N, device=a.device, dtype=torch.bfloat16)
+    check(lib().mdi_gemm_bf16(ptr(a), ptr(w), ptr(out), ptr(bias), ptr(residual), M, N, K, block_n, *_knobs, stream_ptr()),
+          "gemm_bf16 (tcgen05)")
+    return out
 
 
 def sample_scratch(device: Any) -> torch.Tensor:

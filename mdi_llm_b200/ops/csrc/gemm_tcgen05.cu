@@ -1,0 +1,265 @@
+// bf16 GEMM on the 5th-generation tensor cores (tcgen05 + TMEM + TMA), hand-written for sm_100a.
+//
+//   C[M, N] = A[M, K] · W[N, K]^T  (+ bias[N]) (+ residual[M, N])        bf16 in, fp32 accumulate
+//
+// This is the prefill path (T = prompt length rows through every linear of a stage — SURVEY K3/K8/
+// K10/K11/K12 at T > 1), where the work is GEMM-shaped; decode (T = 1) is bandwidth-bound and uses
+// the weight-streaming kernels in decode_linear.cu instead.
+//
+// Structure (one 128 x BLOCK_N output tile per CTA, warp-specialised, 4-stage TMA pipeline):
+//   warp 0      : TMA producer — cp.async.bulk.tensor loads of the A and W tiles (64-element = 128 B
+//                 K slabs, SWIZZLE_128B) into shared memory, completion on "full" mbarriers;
+//   warp 1      : MMA issuer — one elected thread issues tcgen05.mma (M=128, N=BLOCK_N, K=16) from
+//                 shared-memory descriptors into a TMEM accumulator; tcgen05.commit releases the
+//                 stage ("empty" mbarrier) and finally signals the epilogue;
+//   warp 2      : TMEM allocator / deallocator;
+//   warps 4..7  : epilogue — tcgen05.ld (32 lanes x 32 columns per warp), bias/residual, bf16 store.
+//
+// Both operands are K-major (row-major with K contiguous), i.e. activations [T, C] and nn.Linear
+// weights [out, in] are consumed as stored; out-of-range rows of the last M/N tile are zero-filled
+// by TMA on load and masked on store.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace mdi {
+
+constexpr int GEMM_BLOCK_M = 128;
+constexpr int GEMM_BLOCK_K = 64;  // 64 bf16 = 128 bytes = one swizzle atom row
+constexpr int GEMM_STAGES = 4;
+constexpr int GEMM_THREADS = 256;
+constexpr int UMMA_K = 16;
+
+struct GemmParams {
+  CUtensorMap tma_a;
+  CUtensorMap tma_b;
+  bf16* C;
+  const bf16* bias;
+  const bf16* residual;
+  int M, N, K;
+  // descriptor knobs (kept as parameters so a bring-up test can sweep them; defaults are the
+  // canonical K-major SWIZZLE_128B encoding)
+  unsigned int desc_sbo;      // stride-byte-offset >> 4 (8 rows x 128 B = 1024 B -> 64)
+  unsigned int desc_lbo;      // leading-byte-offset >> 4 (ignored for swizzled K-major; 1)
+  unsigned int desc_hi_bits;  // bits [46..63] >> 32 shifted: version (bit 46) | layout type (bits 61-63)
+  unsigned int k_step_bytes;  // start-address advance per UMMA_K (16 bf16 = 32 B)
+};
+
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int x, int y) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tcgen05_mma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 32 lanes x 32 columns of fp32: thread t of the warp gets lane (warp_lane_base + t), columns c0..c0+31
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// shared-memory matrix descriptor: K-major, SWIZZLE_128B (cute::UMMA::SmemDescriptor bit layout)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, const GemmParams& p) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);            // start address, bits [0,14)
+  d |= (uint64_t)(p.desc_lbo & 0x3FFF) << 16;             // leading byte offset, bits [16,30)
+  d |= (uint64_t)(p.desc_sbo & 0x3FFF) << 32;             // stride byte offset, bits [32,46)
+  d |= (uint64_t)p.desc_hi_bits << 46;                    // version (bit 46) ... layout type (bits 61-63)
+  return d;
+}
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(const __grid_constant__ GemmParams p) {
+  extern __shared__ __align__(1024) unsigned char gemm_smem[];
+  constexpr int A_BYTES = GEMM_BLOCK_M * GEMM_BLOCK_K * 2;
+  constexpr int B_BYTES = BLOCK_N * GEMM_BLOCK_K * 2;
+  // carve: [A stages][B stages][barriers][tmem ptr]
+  unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(gemm_smem) + 1023) & ~uintptr_t(1023));
+  unsigned char* smem_a = base;
+  unsigned char* smem_b = base + GEMM_STAGES * A_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_b + GEMM_STAGES * B_BYTES);
+  uint64_t* empty_bar = full_bar + GEMM_STAGES;
+  uint64_t* tmem_full_bar = empty_bar + GEMM_STAGES;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * GEMM_BLOCK_M, n0 = blockIdx.y * BLOCK_N;
+  const int num_k_blocks = (p.K + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tma_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tma_b) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < GEMM_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(tmem_full_bar, 1);
+    mbar_fence_init();
+  }
+  if (warp == 2) {  // whole warp: allocate BLOCK_N TMEM columns (power of two >= 32)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "n"(BLOCK_N) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      for (int kb = 0; kb < num_k_blocks; ++kb) {
+        const int s = kb % GEMM_STAGES;
+        const uint32_t phase = (kb / GEMM_STAGES) & 1;
+        mbar_wait(&empty_bar[s], phase ^ 1);
+        mbar_expect_tx(&full_bar[s], A_BYTES + B_BYTES);
+        tma_load_2d(smem_a + s * A_BYTES, &p.tma_a, &full_bar[s], kb * GEMM_BLOCK_K, m0);
+        tma_load_2d(smem_b + s * B_BYTES, &p.tma_b, &full_bar[s], kb * GEMM_BLOCK_K, n0);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    // instruction descriptor (cute::UMMA::InstrDescriptor): fp32 accumulate, bf16 x bf16, both K-major
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(GEMM_BLOCK_M >> 4) << 24);
+    for (int kb = 0; kb < num_k_blocks; ++kb) {
+      const int s = kb % GEMM_STAGES;
+      const uint32_t phase = (kb / GEMM_STAGES) & 1;
+      mbar_wait(&full_bar[s], phase);
+      tcgen05_fence_after();
+      if (lane == 0) {
+        const uint32_t a_addr = smem_u32(smem_a + s * A_BYTES), b_addr = smem_u32(smem_b + s * B_BYTES);
+#pragma unroll
+        for (int k = 0; k < GEMM_BLOCK_K / UMMA_K; ++k) {
+          const uint64_t da = make_smem_desc(a_addr + k * p.k_step_bytes, p);
+          const uint64_t db = make_smem_desc(b_addr + k * p.k_step_bytes, p);
+          tcgen05_mma_f16(tmem_base, da, db, idesc, (kb | k) ? 1u : 0u);
+        }
+        tcgen05_commit(&empty_bar[s]);                       // stage reusable once these MMAs retire
+        if (kb == num_k_blocks - 1) tcgen05_commit(tmem_full_bar);  // accumulator complete
+      }
+      __syncwarp();
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue: TMEM -> registers -> bf16 global =====
+    const int ew = warp - 4;  // TMEM lanes [32*ew, 32*ew + 32) belong to this warp
+    mbar_wait(tmem_full_bar, 0);
+    tcgen05_fence_after();
+    const int row = m0 + ew * 32 + lane;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+      uint32_t acc[32];
+      tmem_ld_32x32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)c0, acc);
+      if (row < p.M) {
+        const int col0 = n0 + c0;
+        bf16* crow = p.C + (size_t)row * p.N + col0;
+        const bf16* rrow = p.residual ? p.residual + (size_t)row * p.N + col0 : nullptr;
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          if (col0 + j >= p.N) break;
+          float v0 = __uint_as_float(acc[j]), v1 = __uint_as_float(acc[j + 1]);
+          if (p.bias) { v0 += __bfloat162float(p.bias[col0 + j]); if (col0 + j + 1 < p.N) v1 += __bfloat162float(p.bias[col0 + j + 1]); }
+          if (rrow) {  // eager semantics: linear output rounded to bf16, then added to the bf16 residual
+            v0 = round_bf16(v0) + __bfloat162float(rrow[j]);
+            if (col0 + j + 1 < p.N) v1 = round_bf16(v1) + __bfloat162float(rrow[j + 1]);
+          }
+          if (col0 + j + 1 < p.N) {
+            __nv_bfloat162 o = __floats2bfloat162_rn(v0, v1);
+            *reinterpret_cast<__nv_bfloat162*>(crow + j) = o;
+          } else {
+            crow[j] = __float2bfloat16_rn(v0);
+          }
+        }
+      }
+    }
+    tcgen05_fence_before();
+  }
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(BLOCK_N) : "memory");
+  }
+}
+
+// ---- host side ------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (PFN_encodeTiled)p;
+  }
+  return fn;
+}
+
+// 2-D bf16 row-major [rows, cols] tensor, box = [box_rows, 64 cols], 128-byte swizzle
+static int make_map(CUtensorMap* map, const void* ptr, int rows, int cols, int box_rows) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) return -5;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+  cuuint32_t box[2] = {(cuuint32_t)GEMM_BLOCK_K, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -6;
+}
+
+}  // namespace mdi
+
+using namespace mdi;
+
+// C[M,N] = A[M,K] W[N,K]^T (+bias) (+residual).  K must be a multiple of 8 (16-byte rows for TMA).
+// knobs: sbo/lbo/hi_bits/k_step <= 0 select the canonical encoding.
+extern "C" int mdi_gemm_bf16(const void* A, const void* W, void* C, const void* bias, const void* residual, int M,
+                             int N, int K, int block_n, int sbo, int lbo, int hi_bits, int k_step,
+                             cudaStream_t stream) {
+  if (K % 8 != 0 || M <= 0 || N <= 0) return -2;
+  GemmParams p;
+  p.C = (bf16*)C; p.bias = (const bf16*)bias; p.residual = (const bf16*)residual; p.M = M; p.N = N; p.K = K;
+  p.desc_sbo = sbo > 0 ? (unsigned)sbo : 64u;
+  p.desc_lbo = lbo > 0 ? (unsigned)lbo : 1u;
+  p.desc_hi_bits = hi_bits > 0 ? (unsigned)hi_bits : (1u | (2u << 15));  // version = 1 (bit 46), SWIZZLE_128B = 2 (bits 61-63)
+  p.k_step_bytes = k_step > 0 ? (unsigned)k_step : 32u;
+  if (block_n != 64 && block_n != 128 && block_n != 256) block_n = 128;
+  int rc = make_map(&p.tma_a, A, M, K, GEMM_BLOCK_M);
+  if (rc) return rc;
+  rc = make_map(&p.tma_b, W, N, K, block_n);
+  if (rc) return rc;
+  const size_t smem = 1024 + (size_t)GEMM_STAGES * (GEMM_BLOCK_M + block_n) * GEMM_BLOCK_K * 2 + 128;
+  dim3 grid((M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M, (N + block_n - 1) / block_n);
+  cudaError_t e;
+#define MDI_GEMM_LAUNCH(BN)                                                                                          \
+  e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
+  if (e != cudaSuccess) return (int)e;                                                                               \
+  gemm_bf16_tcgen05_kernel<BN><<<grid, GEMM_THREADS, smem, stream>>>(p);
+  if (block_n == 64) { MDI_GEMM_LAUNCH(64) } else if (block_n == 256) { MDI_GEMM_LAUNCH(256) } else { MDI_GEMM_LAUNCH(128) }
+#undef MDI_GEMM_LAUNCH
+  return (int)cudaGetLastError();
+}
