@@ -197,17 +197,20 @@ class CausalSelfAttention(nn.Module):
         v = qkv[:, :, :, qpk + 1].transpose(1, 2)
         return q, k, v
 
-    def forward(
+    def attend_qkv(
         self,
-        x: torch.Tensor,
+        qkv: torch.Tensor,
         cos: torch.Tensor,
         sin: torch.Tensor,
         input_pos: Optional[torch.Tensor] = None,
         kv: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
     ) -> torch.Tensor:
+        """Everything between the two projections: split, RoPE, KV-slot update, attention.
+        ``qkv [B,T,(H+2G)hs]`` -> ``y [B,T,H*hs]`` (also used by the tcgen05 prefill path, which
+        computes the projections itself)."""
         cfg = self.config
-        B, T, _ = x.shape
-        q, k, v = self.split_qkv(self.attn(x))
+        B, T, _ = qkv.shape
+        q, k, v = self.split_qkv(qkv)
         n = cfg.rope_n_elem
         if n > 0:
             q = torch.cat((apply_rope(q[..., :n], cos, sin), q[..., n:]), dim=-1)
@@ -225,7 +228,7 @@ class CausalSelfAttention(nn.Module):
             k = k_cache[:, :live].unsqueeze(0).to(q.dtype)
             v = v_cache[:, :live].unsqueeze(0).to(q.dtype)
             # rows attend to cache positions <= their own position
-            mask = torch.arange(live, device=x.device)[None, :] <= input_pos[:, None]
+            mask = torch.arange(live, device=qkv.device)[None, :] <= input_pos[:, None]
             mask = mask[None, None]
             causal = False
         else:
@@ -235,8 +238,17 @@ class CausalSelfAttention(nn.Module):
             k = k.repeat_interleave(cfg.q_per_kv, dim=1)
             v = v.repeat_interleave(cfg.q_per_kv, dim=1)
         y = F.scaled_dot_product_attention(q, k, v, attn_mask=mask, dropout_p=0.0, is_causal=causal)
-        y = y.transpose(1, 2).reshape(B, T, cfg.attn_out_dim)
-        return self.proj(y)
+        return y.transpose(1, 2).reshape(B, T, cfg.attn_out_dim)
+
+    def forward(
+        self,
+        x: torch.Tensor,
+        cos: torch.Tensor,
+        sin: torch.Tensor,
+        input_pos: Optional[torch.Tensor] = None,
+        kv: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
+    ) -> torch.Tensor:
+        return self.proj(self.attend_qkv(self.attn(x), cos, sin, input_pos, kv))
 
 
 class GptNeoxMLP(nn.Module):

@@ -238,6 +238,33 @@ class FusedStage:
                 ops.linear_decode(blk.mlp.proj.weight, self.h_mlp, self.out_local, self.ctx, bias=blk.mlp.proj.bias,
                                   residual=self.xb, y_slot_stride=C, **common)
 
+    # ---- prefill (T > 1): linears on the tcgen05 GEMM ------------------------------------------------
+    @torch.inference_mode()
+    def prefill(self, data: torch.Tensor, input_pos: torch.Tensor, slot: int) -> torch.Tensor:
+        """All local blocks for a whole prompt.  Every projection (SURVEY K3/K8/K10/K11 at T > 1) runs
+        on the hand-written tcgen05/TMEM/TMA GEMM with its bias/residual epilogue; RMSNorm is the
+        row kernel; RoPE, the KV-slot write and causal attention reuse the eager helper.
+        ``data``: token ids ``[1,T]`` on the starter, hidden state ``[1,T,C]`` on a secondary."""
+        m, cfg = self.model, self.cfg
+        T = data.size(1)
+        if self.is_starter:
+            x = m.embed(data.long(), input_pos)[0].to(torch.bfloat16).contiguous()
+        else:
+            x = data[0].to(torch.bfloat16).contiguous()
+        cos, sin = m.rope_for(T, input_pos)
+        eps, uo = cfg.norm_eps, cfg.unit_offset_norm
+        for li, blk in enumerate(m.transformer.h):
+            h = ops.rmsnorm_rows(x, blk.norm_1.weight, eps, uo)
+            qkv = ops.gemm(h, blk.attn.attn.weight, bias=blk.attn.attn.bias)
+            y = blk.attn.attend_qkv(qkv.unsqueeze(0), cos, sin, input_pos, m.kv_pool.layer(li, slot))[0].contiguous()
+            x = ops.gemm(y, blk.attn.proj.weight, bias=blk.attn.proj.bias, residual=x)
+            h = ops.rmsnorm_rows(x, blk.norm_2.weight, eps, uo)
+            a = ops.gemm(h, blk.mlp.fc_1.weight, bias=blk.mlp.fc_1.bias, block_n=256)
+            b = ops.gemm(h, blk.mlp.fc_2.weight, bias=blk.mlp.fc_2.bias, block_n=256)
+            g = (blk.mlp.gate(a) * b).contiguous()
+            x = ops.gemm(g, blk.mlp.proj.weight, bias=blk.mlp.proj.bias, residual=x)
+        return x.unsqueeze(0)
+
     # ---- graphs ------------------------------------------------------------------------------------
     def graph(self, key: Any, builder: Any, warm: bool = True) -> ops.CudaGraph:
         """Capture ``builder()`` once per ``key``.  ``warm`` runs it eagerly first (loads the
@@ -318,10 +345,8 @@ class FusedStageRunner(StageRunner):
         st, slot = self.stage, self.slots[sample_id]
         T = data.size(1)
         with torch.cuda.device(self.device):
-            if T > 1:  # prefill: eager module on the shared KV pool
-                if self.role == "starter":
-                    return self.model(data.long(), input_pos, slot=slot)
-                return self.model(data.to(self.dtype), input_pos, slot=slot)
+            if T > 1:  # prefill: tcgen05 GEMMs + eager attention on the shared KV pool
+                return st.prefill(data, input_pos, slot)
             pos = int(input_pos[-1])
             if self.role == "starter":
                 st.set_ctx(slot, pos, token=int(data.reshape(-1)[-1]))

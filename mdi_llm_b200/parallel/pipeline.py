@@ -157,11 +157,11 @@ class DevicePipeline:
                 pos = torch.arange(T, device=self.device)
                 st.set_ctx(slot, T - 1, wait=1, signal=1)
                 if self.is_starter:
-                    hidden = self.model(self.prompts[slot].view(1, -1).long(), pos, slot=slot)
+                    hidden = st.prefill(self.prompts[slot].view(1, -1), pos, slot)
                 else:
                     ops.check(lib.mdi_wait_flag(st.flags.data_ptr(), st.ctx.data_ptr(), st.status.data_ptr(),
                                                 st.wait_max_cycles, ops.stream_ptr()), "wait prefill")
-                    hidden = self.model(self.prefill_in[slot, :T].unsqueeze(0), pos, slot=slot)
+                    hidden = st.prefill(self.prefill_in[slot, :T].unsqueeze(0), pos, slot)
                 hidden = hidden.to(torch.bfloat16).contiguous()
                 if self.is_last:  # wrap-around: only the last position feeds lm_head
                     self._hop_copy(hidden[0, -1], self.next_hop.hidden_ptr + slot * self.C * 2)
