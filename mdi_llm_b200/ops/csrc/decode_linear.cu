@@ -423,7 +423,8 @@ static int launch_pdl(Kern kern, const StreamArgs& args, int grid, size_t smem, 
 }
 
 // variant: 0 = LDG register streaming (grid = sms * ctas_per_sm), 1 = bulk-copy ring with 4 stages
-// (1 CTA/SM), 2 = bulk-copy ring with 2 stages (grid = sms * min(ctas_per_sm, 2..3)).
+// (1 CTA/SM), 2 / 3 = bulk-copy ring with 2 / 3 stages (grid = sms * as many CTAs as shared memory allows,
+// capped by ctas_per_sm).
 template <int MODE>
 static int launch_stream(const StreamArgs& a, int variant, int ctas_per_sm, int use_pdl, cudaStream_t stream) {
   const int sms = num_sms();
@@ -434,13 +435,14 @@ static int launch_stream(const StreamArgs& a, int variant, int ctas_per_sm, int 
     const size_t smem0 = (size_t)((a.K + 63) / 64) * 64 * sizeof(bf16) + (a.hist ? STAT_BINS * 4 : 0);
     return launch_pdl(stream_ldg_kernel<MODE>, a, grid, smem0, stream, use_pdl);
   }
-  const int stages = variant == 1 ? 4 : 2;
+  const int stages = variant == 1 ? 4 : (variant == 3 ? 3 : 2);
   const size_t smem = (size_t)LIN_WARPS * stages * 2 * TS_CHUNK * 2 + (size_t)((a.K + 63) / 64) * 64 * 2 +
                       (size_t)LIN_WARPS * stages * 8 + (a.hist ? STAT_BINS * 4 : 0);
   if (smem > 227 * 1024) return -2;
   const int per_sm = variant == 1 ? 1 : max(1, min(ctas_per_sm, (int)((227 * 1024) / (smem + 1024))));
   const int grid = max(1, min(sms * per_sm, max_useful));
   if (variant == 1) return launch_pdl(stream_bulk_kernel<MODE, 4>, a, grid, smem, stream, use_pdl);
+  if (variant == 3) return launch_pdl(stream_bulk_kernel<MODE, 3>, a, grid, smem, stream, use_pdl);
   return launch_pdl(stream_bulk_kernel<MODE, 2>, a, grid, smem, stream, use_pdl);
 }
 

@@ -33,7 +33,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default="")
     ap.add_argument("--iters", type=int, default=40)
-    ap.add_argument("--ctas", default="2,3,4")
+    ap.add_argument("--ctas", default="3")
     ap.add_argument("--peak", type=float, default=6577.0, help="measured copy bandwidth GB/s (MEASURED_PEAKS.json)")
     args = ap.parse_args()
     ops.require()
@@ -51,7 +51,7 @@ def main():
         res = torch.randn(N, device=dev, dtype=torch.bfloat16) if residual else None
         y = torch.empty(N, device=dev, dtype=torch.float32 if out_fp32 else torch.bfloat16)
         nbytes = n_w * N * K * 2
-        combos = [(0, int(c)) for c in args.ctas.split(",")] + [(1, 1), (2, 2), (2, 3)]
+        combos = [(0, int(c)) for c in args.ctas.split(",")] + [(1, 1), (2, 2), (2, 3), (3, 2)]
         for variant, cps in combos:
             def fn(i):
                 j = i % ring
@@ -59,7 +59,7 @@ def main():
                                   act="silu_gate" if gated else "none", ctas_per_sm=cps, use_pdl=pdl, variant=variant)
             us = time_launches(fn, args.iters)
             gbs = nbytes / us / 1e3
-            r = {"kernel": name, "N": N, "K": K, "variant": ["ldg", "bulk4", "bulk2"][variant], "ctas_per_sm": cps,
+            r = {"kernel": name, "N": N, "K": K, "variant": ["ldg", "bulk4", "bulk2", "bulk3"][variant], "ctas_per_sm": cps,
                  "us": round(us, 2), "GBps": round(gbs, 1),
                  "frac_of_measured_copy_bw": round(gbs / args.peak, 3), "MB": round(nbytes / 1e6, 1), "pdl": pdl}
             results.append(r)

@@ -72,8 +72,9 @@ def test_fused_runner_matches_eager_hidden_and_logits(variant):
     for r in (eager, fused):
         r.begin_sample(0)
         r.begin_sample(1)
-    h_e, h_f = eager.forward(1, prompt, pos), fused.forward(1, prompt, pos)  # prefill (both eager ops)
-    torch.testing.assert_close(h_e.float(), h_f.float(), rtol=2e-2, atol=2e-2)
+    h_e, h_f = eager.forward(1, prompt, pos), fused.forward(1, prompt, pos)  # prefill: cuBLAS vs tcgen05 GEMMs
+    err, scale = (h_e.float() - h_f.float()).abs().max().item(), h_e.float().abs().max().item()
+    assert err <= 0.03 * scale + 0.03, f"prefill: max err {err} (scale {scale})"
     tok = torch.tensor([[42]], device="cuda")
     for step in range(5):
         p = torch.tensor([6 + step], device="cuda")
