@@ -99,6 +99,8 @@ def parse_args() -> argparse.Namespace:
     ap.add_argument("--partition", default="balanced", choices=["auto", "table", "balanced"])
     ap.add_argument("--no-pdl", action="store_true")
     ap.add_argument("--ctas-per-sm", type=int, default=4)
+    ap.add_argument("--hop", default="p2p", choices=["p2p", "nccl"],
+                    help="inter-stage hop: fused peer stores + flags (product) or NCCL send/recv (baseline midpoint)")
     ap.add_argument("--variant", type=int, default=-1, help="decode linear path: 0 LDG, 1 bulk-copy x4 stages, 2 bulk-copy x2")
     ap.add_argument("--temperature", type=float, default=0.8)
     ap.add_argument("--top-k", type=int, default=200)
@@ -155,7 +157,7 @@ def run_ours(args: argparse.Namespace) -> Dict[str, Any]:
     random_init_stage_(stage, device, torch.bfloat16, seed=1234 + rank)
     sampling = SamplingParams(temperature=args.temperature, top_k=args.top_k, seed=2024)
     pipe = DevicePipeline(stage, rank, world, n_samples=n_samples, max_seq_length=seq_len, sampling=sampling,
-                          max_prompt_len=args.prompt_len, use_pdl=not args.no_pdl, ctas_per_sm=args.ctas_per_sm)
+                          max_prompt_len=args.prompt_len, use_pdl=not args.no_pdl, ctas_per_sm=args.ctas_per_sm, hop=args.hop)
     pipe.connect_distributed()
     g = torch.Generator().manual_seed(7)
     prompts = [torch.randint(0, cfg.vocab_size, (args.prompt_len,), generator=g, dtype=torch.int32) for _ in range(n_samples)]
@@ -196,20 +198,23 @@ def run_ours(args: argparse.Namespace) -> Dict[str, Any]:
         dist.all_reduce(waits, op=dist.ReduceOp.SUM)
 
     # ---------------- end to end through the host-fed public API ----------------
-    pinned = [p.pin_memory() for p in prompts]  # inputs start in pinned host memory
-    pipe.prepare(pinned, e2e_rounds + 2)
-    barrier()
-    pipe.prefill()
-    pipe.decode_rounds_host(1)  # one untimed round (graph capture of the host-fed variant)
-    barrier()
-    t0 = time.perf_counter()
-    _, h2d, d2h = pipe.decode_rounds_host(e2e_rounds)
-    barrier()
-    e2e_s = torch.tensor([time.perf_counter() - t0], device=device, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    e2e_value = e2e_rounds * n_samples / float(e2e_s.item())
-    steps_e2e = e2e_rounds * n_samples
+    if args.hop == "nccl":  # comparison midpoint only: no separate e2e measurement
+        e2e_value, h2d, d2h, steps_e2e = None, 0, 0, 1
+    else:
+        pinned = [p.pin_memory() for p in prompts]  # inputs start in pinned host memory
+        pipe.prepare(pinned, e2e_rounds + 2)
+        barrier()
+        pipe.prefill()
+        pipe.decode_rounds_host(1)  # one untimed round (graph capture of the host-fed variant)
+        barrier()
+        t0 = time.perf_counter()
+        _, h2d, d2h = pipe.decode_rounds_host(e2e_rounds)
+        barrier()
+        e2e_s = torch.tensor([time.perf_counter() - t0], device=device, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+        e2e_value = e2e_rounds * n_samples / float(e2e_s.item())
+        steps_e2e = e2e_rounds * n_samples
 
     out = {
         "metric": METRIC, "value": round(value, 3), "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
@@ -221,10 +226,10 @@ def run_ours(args: argparse.Namespace) -> Dict[str, Any]:
                    "tokens_per_step": n_samples, "l2_policy": "inputs (stage weights) larger than L2, no flush",
                    "sampling": {"temperature": args.temperature, "top_k": args.top_k}, "pdl": not args.no_pdl,
                    "linear_variant": args.variant, "ctas_per_sm": args.ctas_per_sm,
-                   "hop": "fused P2P store + flag (NVLink)" if world > 1 else "local (standalone ring)",
+                   "hop": ("NCCL send/recv (baseline midpoint)" if args.hop == "nccl" else "fused P2P store + flag (NVLink)") if world > 1 else "local (standalone ring)",
                    "timing": "CUDA events, max over ranks"},
         "clocks": clocks,
-        "e2e": {"value": round(e2e_value, 3), "unit": "tokens/s", "h2d_bytes_per_step": h2d // max(1, steps_e2e),
+        "e2e": {"value": round(e2e_value, 3) if e2e_value is not None else None, "unit": "tokens/s", "h2d_bytes_per_step": h2d // max(1, steps_e2e),
                 "d2h_bytes_per_step": d2h // max(1, steps_e2e), "rounds": e2e_rounds,
                 "how": "host-fed steps: pinned ctx H2D + sampled-token D2H every step, wall clock, max over ranks"},
         "gpu_launches": int(launches.item()),

@@ -40,7 +40,12 @@ __all__ = ["DevicePipeline", "connect_ring_local"]
 class DevicePipeline:
     def __init__(self, model: StageModule, rank: int, world: int, n_samples: int, max_seq_length: int,
                  sampling: Optional[SamplingParams] = None, max_prompt_len: int = 0, use_pdl: bool = True,
-                 ctas_per_sm: int = 4, wait_max_cycles: int = 20_000_000_000, exportable: Optional[bool] = None) -> None:
+                 ctas_per_sm: int = 4, wait_max_cycles: int = 20_000_000_000, exportable: Optional[bool] = None,
+                 hop: str = "p2p") -> None:
+        if hop not in ("p2p", "nccl"):
+            raise ValueError("hop must be 'p2p' (fused peer stores + flags) or 'nccl' (send/recv baseline)")
+        self.hop = hop if world > 1 else "p2p"
+        self.edge_groups: Optional[List[Any]] = None
         self.rank, self.world, self.n = rank, world, n_samples
         self.is_starter, self.is_last = rank == 0, rank == world - 1
         exportable = (world > 1) if exportable is None else exportable
@@ -98,6 +103,12 @@ class DevicePipeline:
 
         if self.world == 1:
             return
+        if self.hop == "nccl":  # baseline hop: one communicator per ring edge, no peer mapping
+            from .transport.nccl_p2p import make_edge_groups
+
+            self.edge_groups = make_edge_groups(self.world)
+            dist.barrier(group=group)
+            return
         infos: List[Any] = [None] * self.world
         dist.all_gather_object(infos, self.export_handles(), group=group)
         self.connect_ipc(infos[(self.rank + 1) % self.world])
@@ -151,6 +162,8 @@ class DevicePipeline:
         """Round 0: every sample's prompt through all stages (eager blocks; hop = peer copy +
         flag).  The last stage returns only the final row to the starter."""
         st, lib = self.stage, ops.lib()
+        if self.hop == "nccl":
+            return self._prefill_nccl()
         with torch.cuda.device(self.device):
             for slot in range(self.n):
                 T = self.prompt_lens[slot]
@@ -167,6 +180,67 @@ class DevicePipeline:
                     self._hop_copy(hidden[0, -1], self.next_hop.hidden_ptr + slot * self.C * 2)
                 else:
                     self._hop_copy(hidden[0], self.next_prefill_ptr + slot * self.max_prompt_len * self.C * 2)
+
+    # ---- NCCL-hop baseline ("ours with NCCL send/recv instead of the fused hop") --------------------
+    def _edges(self):
+        import torch.distributed as dist
+
+        prev, nxt = (self.rank - 1) % self.world, (self.rank + 1) % self.world
+        return dist, prev, nxt, self.edge_groups[prev], self.edge_groups[self.rank]
+
+    @torch.inference_mode()
+    def _prefill_nccl(self) -> None:
+        dist, prev, nxt, g_in, g_out = self._edges()
+        st = self.stage
+        with torch.cuda.device(self.device):
+            for slot in range(self.n):
+                T = self.prompt_lens[slot]
+                pos = torch.arange(T, device=self.device)
+                if self.is_starter:
+                    hidden = st.prefill(self.prompts[slot].view(1, -1), pos, slot)
+                else:
+                    buf = torch.empty(1, T, self.C, dtype=torch.bfloat16, device=self.device)
+                    dist.recv(buf, src=prev, group=g_in)
+                    hidden = st.prefill(buf, pos, slot)
+                hidden = hidden.to(torch.bfloat16).contiguous()
+                dist.send(hidden[0, -1].contiguous() if self.is_last else hidden, dst=nxt, group=g_out)
+
+    def _g_nccl(self, head_only: bool) -> ops.CudaGraph:
+        st = self.stage
+
+        def build() -> None:
+            ops.advance_step(st.ctx, st.state, st.pos_arr, self.n, self.is_starter, use_pdl=False)
+            if self.is_starter:
+                st.enqueue_head(wait=False)
+                st.enqueue_sample()
+                if not head_only:
+                    st.enqueue_embed(from_tokens=True)
+            if not head_only:
+                st.enqueue_blocks(None, wait_input=False)
+
+        return st.graph(("nccl", head_only), build, warm=False)
+
+    def _decode_rounds_nccl(self, n_rounds: int) -> int:
+        dist, prev, nxt, g_in, g_out = self._edges()
+        st = self.stage
+        launched = 0
+        with torch.cuda.device(self.device):
+            for _ in range(n_rounds):
+                r = self.round
+                if r > self.max_new:
+                    break
+                final = r == self.max_new
+                for slot in range(self.n):
+                    if final and not self.is_starter:
+                        continue
+                    dist.recv(st.hidden_in[slot], src=prev, group=g_in)  # stream-ordered, host does not block
+                    self._g_nccl(final).launch()
+                    launched += 1
+                    if not final:
+                        dist.send(st.out_local[slot], dst=nxt, group=g_out)
+                self.round += 1
+        self.n_graph_launches += launched
+        return launched
 
     # graph builders ---------------------------------------------------------------------------------
     def _g_full(self, dev_ctx: bool) -> ops.CudaGraph:
@@ -198,6 +272,8 @@ class DevicePipeline:
         """Enqueue ``n_rounds`` decode rounds (every sample advances one token per round) in
         device-driven mode.  Returns the number of graph launches issued."""
         st = self.stage
+        if self.hop == "nccl":
+            return self._decode_rounds_nccl(n_rounds)
         launched = 0
         with torch.cuda.device(self.device):
             for _ in range(n_rounds):

@@ -95,3 +95,22 @@ def test_control_server_verbs_and_retrying_client():
         srv.stop()
     (dead,) = free_ports(1)
     assert request_to_node("post", f"http://127.0.0.1:{dead}/init", {}, max_n_requests=2, retry_wait=0.01) == 0
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_torch_distributed_transport_ring_gloo(world):
+    """The NCCL/gloo p2p transport under the host-driven scheduler: token-exact vs single device."""
+    import json
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    (port,) = free_ports(1)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(root, "tests", "_mp_transport_worker.py")]
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=240, cwd=root)
+    lines = [ln for ln in p.stdout.splitlines() if ln.startswith("TR_RESULT ")]
+    assert lines, p.stderr[-2000:]
+    res = json.loads(lines[-1][len("TR_RESULT "):])
+    assert res["ok"] and res["bytes_sent"] > 0 and p.returncode == 0
