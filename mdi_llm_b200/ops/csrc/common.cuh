@@ -143,6 +143,22 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint3
                ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+// ---- device-side tracer ---------------------------------------------------------------------------
+// Each traced kernel owns one record of 6 x u64 (ns, %globaltimer):
+//   [0] min entry  [1] min "input ready" (after PDL/hop wait)  [2] max "staged"  [3] min exit  [4] max exit  [5] #CTAs
+// Recording is per CTA (thread 0), costs a handful of atomics and is off when `rec == nullptr`.
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void trace_mark(unsigned long long* rec, int field, bool is_min) {
+  if (rec == nullptr || threadIdx.x != 0) return;
+  const unsigned long long t = globaltimer_ns();
+  if (is_min) atomicMin(rec + field, t); else atomicMax(rec + field, t);
+  if (field == 4) atomicAdd(rec + 5, 1ull);
+}
+
 // Programmatic dependent launch: let the next kernel's prologue overlap our tail, and wait for
 // the previous kernel's memory before touching activations.
 __device__ __forceinline__ void pdl_wait_prior() {

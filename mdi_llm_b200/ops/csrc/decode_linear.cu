@@ -149,6 +149,7 @@ struct StreamArgs {
   // logits-only (lm_head): sampling statistics gathered while the logits are produced
   unsigned int* hist;        // [4096] histogram of the top 12 bits of the orderable logit key, or null
   unsigned long long* amax;  // packed (key << 32 | ~row) running arg-max, or null
+  unsigned long long* trace; // tracer record of this launch (6 x u64) or null
 };
 
 __device__ __forceinline__ uint32_t float_key(float f) {  // monotone: larger float -> larger key
@@ -278,6 +279,7 @@ __global__ void __launch_bounds__(LIN_THREADS, 3) stream_ldg_kernel(const Stream
   __shared__ float red[LIN_WARPS];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int gw = blockIdx.x * LIN_WARPS + warp, n_gw = gridDim.x * LIN_WARPS;
+  trace_mark(a.trace, 0, true);
 
   // pull this warp's first rows towards L2 while we (possibly) wait for the previous kernel / hop
   if (gw < a.n_items) {
@@ -289,8 +291,10 @@ __global__ void __launch_bounds__(LIN_THREADS, 3) stream_ldg_kernel(const Stream
   unsigned long long best = 0ull;
   pdl_wait_prior();
   hop_wait(a.wait, a.ctx);
+  trace_mark(a.trace, 1, true);
   const int slot = a.ctx ? a.ctx[MDI_CTX_SLOT] : 0, pos = a.ctx ? a.ctx[MDI_CTX_POS] : 0;
   stage_input(a.x + (size_t)slot * a.x_slot_stride, a.norm_w, a.eps, a.unit_offset, a.K, xs, red);
+  trace_mark(a.trace, 2, false);
   pdl_launch_dependents();
 
   const bf16* res = a.residual ? a.residual + (size_t)slot * a.res_slot_stride : nullptr;
@@ -305,6 +309,8 @@ __global__ void __launch_bounds__(LIN_THREADS, 3) stream_ldg_kernel(const Stream
   }
   stats_flush(a, hist_s, best);
   hop_signal(a.signal, a.ctx);
+  trace_mark(a.trace, 3, true);
+  trace_mark(a.trace, 4, false);
 }
 
 // ---- variant B: bulk-copy streamed (cp.async.bulk -> smem ring per warp, mbarrier completion) -------
@@ -318,6 +324,7 @@ __global__ void __launch_bounds__(LIN_THREADS, 1) stream_bulk_kernel(const Strea
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int gw = blockIdx.x * LIN_WARPS + warp, n_gw = gridDim.x * LIN_WARPS;
+  trace_mark(a.trace, 0, true);
   // layout: ring [WARPS][STAGES][2][TS_CHUNK] bf16 | x [K] bf16 | mbar [WARPS][STAGES] u64
   bf16* ring = reinterpret_cast<bf16*>(smem_raw) + (size_t)warp * STAGES * 2 * TS_CHUNK;
   bf16* xs = reinterpret_cast<bf16*>(smem_raw) + (size_t)LIN_WARPS * STAGES * 2 * TS_CHUNK;
@@ -353,8 +360,10 @@ __global__ void __launch_bounds__(LIN_THREADS, 1) stream_bulk_kernel(const Strea
 
   pdl_wait_prior();
   hop_wait(a.wait, a.ctx);
+  trace_mark(a.trace, 1, true);
   const int slot = a.ctx ? a.ctx[MDI_CTX_SLOT] : 0, pos = a.ctx ? a.ctx[MDI_CTX_POS] : 0;
   stage_input(a.x + (size_t)slot * a.x_slot_stride, a.norm_w, a.eps, a.unit_offset, a.K, xs, red);
+  trace_mark(a.trace, 2, false);
   pdl_launch_dependents();
 
   const bf16* res = a.residual ? a.residual + (size_t)slot * a.res_slot_stride : nullptr;
@@ -390,6 +399,8 @@ __global__ void __launch_bounds__(LIN_THREADS, 1) stream_bulk_kernel(const Strea
   }
   stats_flush(a, hist_s, best);
   hop_signal(a.signal, a.ctx);
+  trace_mark(a.trace, 3, true);
+  trace_mark(a.trace, 4, false);
 }
 
 static int g_num_sms = 0;
@@ -462,7 +473,7 @@ int mdi_linear_decode(const void* W, const void* W2, const void* bias, const voi
                       long long res_slot_stride, long long y_slot_stride, int N, int K, float eps, int unit_offset,
                       int act, int out_fp32, const int* wait_flag, int* status, long long wait_max_cycles,
                       int* signal_flag, unsigned int* done_ctr, int ctas_per_sm, int use_pdl, int variant,
-                      unsigned int* hist, unsigned long long* amax, cudaStream_t stream) {
+                      unsigned int* hist, unsigned long long* amax, unsigned long long* trace, cudaStream_t stream) {
   if (K % 8 != 0) return -2;
   StreamArgs a{};
   a.W = (const bf16*)W; a.W2 = (const bf16*)W2; a.bias = (const bf16*)bias; a.bias2 = (const bf16*)bias2;
@@ -472,7 +483,7 @@ int mdi_linear_decode(const void* W, const void* W2, const void* bias, const voi
   a.wait = HopWait{wait_flag, status, wait_max_cycles};
   a.signal = HopSignal{signal_flag, done_ctr};
   a.n_items = W2 ? N : (N + 1) / 2;
-  a.hist = hist; a.amax = amax;
+  a.hist = hist; a.amax = amax; a.trace = trace;
   if (variant < 0) variant = g_default_variant;
   if (W2) return launch_stream<MODE_GATED>(a, variant, ctas_per_sm, use_pdl, stream);
   return launch_stream<MODE_PLAIN>(a, variant, ctas_per_sm, use_pdl, stream);
@@ -482,7 +493,7 @@ int mdi_qkv_decode(const void* W, const void* bias, const void* x, const void* n
                    const float* sin, void* q_out, void* kv, const int* ctx, long long x_slot_stride, int K,
                    int n_head, int n_groups, int head_size, int rope_n_elem, int max_seq, float eps,
                    int unit_offset, const int* wait_flag, int* status, long long wait_max_cycles, int ctas_per_sm,
-                   int use_pdl, int variant, cudaStream_t stream) {
+                   int use_pdl, int variant, unsigned long long* trace, cudaStream_t stream) {
   if (K % 8 != 0 || head_size % 2 != 0 || rope_n_elem % 2 != 0 || rope_n_elem > head_size) return -2;
   StreamArgs a{};
   a.W = (const bf16*)W; a.bias = (const bf16*)bias; a.x = (const bf16*)x; a.norm_w = (const bf16*)norm_w;
@@ -492,6 +503,7 @@ int mdi_qkv_decode(const void* W, const void* bias, const void* x, const void* n
   a.max_seq = max_seq; a.eps = eps; a.unit_offset = unit_offset;
   a.wait = HopWait{wait_flag, status, wait_max_cycles};
   a.signal = HopSignal{nullptr, nullptr};
+  a.trace = trace;
   a.n_items = (n_head + 2 * n_groups) * (head_size / 2);
   if (variant < 0) variant = g_default_variant;
   return launch_stream<MODE_QKV>(a, variant, ctas_per_sm, use_pdl, stream);

@@ -162,6 +162,8 @@ class FusedStage:
                 self.sample_scratch = ops.sample_scratch(dev)
         self.hop_self = HopTarget(self.hidden_in.data_ptr(), self.flags.data_ptr())
         self._graphs: Dict[Any, ops.CudaGraph] = {}
+        self._trace: Optional[torch.Tensor] = None  # device tracer records [n, 6] int64 (see common.cuh)
+        self._trace_names: List[str] = []
         self._check_weights()
 
     # ---- weights ---------------------------------------------------------------------------------
@@ -175,6 +177,39 @@ class FusedStage:
             return "silu_gate"
         return "gelu_tanh_gate" if self.cfg.gelu_approximate == "tanh" else "gelu_erf_gate"
 
+    # ---- device-side tracing (per-kernel timeline of a stage step) ---------------------
+    def _tr(self, name: str) -> Optional[int]:
+        if self._trace is None:
+            return None
+        i = len(self._trace_names)
+        if i >= self._trace.shape[0]:
+            return None
+        self._trace_names.append(name)
+        return self._trace[i].data_ptr()
+
+    def trace_step(self, builder: Any, max_records: int = 512) -> List[Dict[str, Any]]:
+        """Run ``builder()`` (a sequence of ``enqueue_*`` calls) once with the kernel tracer on and
+        return one row per launch: times in µs relative to the first kernel's entry —
+        ``entry`` (first CTA starts), ``ready`` (first CTA past the PDL/hop wait), ``staged`` (last CTA
+        has its input in shared memory), ``first_exit`` / ``last_exit`` and the CTA count."""
+        with torch.cuda.device(self.device):
+            self._trace = torch.zeros(max_records, 6, dtype=torch.int64, device=self.device)
+            self._trace[:, [0, 1, 3]] = torch.iinfo(torch.int64).max
+            self._trace_names = []
+            try:
+                builder()
+                torch.cuda.synchronize(self.device)
+                rec = self._trace[: len(self._trace_names)].cpu()
+            finally:
+                names, self._trace, self._trace_names = self._trace_names, None, []
+        t0 = int(rec[:, 0].min()) if len(names) else 0
+        rows = []
+        for i, n in enumerate(names):
+            e, r, st_, fx, lx, c = (int(x) for x in rec[i])
+            rows.append({"kernel": n, "entry": (e - t0) / 1e3, "ready": (r - t0) / 1e3, "staged": (st_ - t0) / 1e3 if st_ else None,
+                         "first_exit": (fx - t0) / 1e3, "last_exit": (lx - t0) / 1e3, "ctas": c})
+        return rows
+
     # ---- kernel sequences ------------------------------------------------------------------------
     def enqueue_head(self, wait: bool, stats: bool = True) -> None:
         """starter: final RMSNorm + lm_head on ``hidden_in[slot]`` → fp32 logits (+ the sampler's
@@ -185,7 +220,7 @@ class FusedStage:
             norm_w=m.transformer.ln_f.weight, eps=cfg.norm_eps, unit_offset=cfg.unit_offset_norm,
             x_slot_stride=cfg.n_embd, wait_flag=self.flags.data_ptr() if wait else None,
             status=self.status.data_ptr(), wait_max_cycles=self.wait_max_cycles, ctas_per_sm=self.ctas_per_sm,
-            use_pdl=self.use_pdl, stats=self.sample_scratch if stats else None)
+            use_pdl=self.use_pdl, stats=self.sample_scratch if stats else None, trace=self._tr("lm_head"))
 
     def enqueue_sample(self) -> None:
         """Must follow ``enqueue_head(stats=True)``: consumes (and clears) the logit statistics."""
@@ -217,26 +252,28 @@ class FusedStage:
                 rope_n_elem=cfg.rope_n_elem, max_seq=self.S, bias=blk.attn.attn.bias, norm_w=blk.norm_1.weight,
                 eps=cfg.norm_eps, unit_offset=cfg.unit_offset_norm, x_slot_stride=x_in_stride,
                 wait_flag=self.flags.data_ptr() if (first and wait_input and not self.is_starter) else None,
-                status=self.status.data_ptr(), wait_max_cycles=self.wait_max_cycles, **common)
+                status=self.status.data_ptr(), wait_max_cycles=self.wait_max_cycles, trace=self._tr(f"L{li}.qkv"), **common)
             ops.attn_decode(self.q, kv_layer, self.y_attn, self.part, self.tickets, self.ctx, n_head=cfg.n_head,
                             n_groups=cfg.n_query_groups, head_size=cfg.head_size, max_seq=self.S,
-                            n_split=self.n_split, use_pdl=self.use_pdl)
+                            n_split=self.n_split, use_pdl=self.use_pdl, trace=self._tr(f"L{li}.attn"))
             ops.linear_decode(blk.attn.proj.weight, self.y_attn, self.xb, self.ctx, bias=blk.attn.proj.bias,
-                              residual=x_in, res_slot_stride=x_in_stride, **common)
+                              residual=x_in, res_slot_stride=x_in_stride, trace=self._tr(f"L{li}.o_proj"), **common)
             ops.linear_decode(blk.mlp.fc_1.weight, self.xb, self.h_mlp, self.ctx, W2=blk.mlp.fc_2.weight,
                               bias=blk.mlp.fc_1.bias, bias2=blk.mlp.fc_2.bias, norm_w=blk.norm_2.weight,
-                              eps=cfg.norm_eps, unit_offset=cfg.unit_offset_norm, act=self._gate_act(), **common)
+                              eps=cfg.norm_eps, unit_offset=cfg.unit_offset_norm, act=self._gate_act(),
+                              trace=self._tr(f"L{li}.gate_up"), **common)
             if not last:
                 ops.linear_decode(blk.mlp.proj.weight, self.h_mlp, self.xa, self.ctx, bias=blk.mlp.proj.bias,
-                                  residual=self.xb, **common)
+                                  residual=self.xb, trace=self._tr(f"L{li}.down"), **common)
                 x_in, x_in_stride = self.xa, 0
             elif hop is not None:
                 ops.linear_decode(blk.mlp.proj.weight, self.h_mlp, None, self.ctx, bias=blk.mlp.proj.bias,
                                   residual=self.xb, y_ptr=hop.hidden_ptr, y_slot_stride=C,
-                                  signal_flag=hop.flag_ptr, done_ctr=self.done_ctr.data_ptr(), **common)
+                                  signal_flag=hop.flag_ptr, done_ctr=self.done_ctr.data_ptr(),
+                                  trace=self._tr(f"L{li}.down+hop"), **common)
             else:
                 ops.linear_decode(blk.mlp.proj.weight, self.h_mlp, self.out_local, self.ctx, bias=blk.mlp.proj.bias,
-                                  residual=self.xb, y_slot_stride=C, **common)
+                                  residual=self.xb, y_slot_stride=C, trace=self._tr(f"L{li}.down"), **common)
 
     # ---- prefill (T > 1): linears on the tcgen05 GEMM ------------------------------------------------
     @torch.inference_mode()

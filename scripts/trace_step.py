@@ -1,0 +1,56 @@
+#!/usr/bin/env python3
+"""Per-kernel timeline of one decode step of a Llama-3-8B stage, from the device-side tracer
+(%globaltimer marks inside the kernels; no profiler attached).  Shows, per launch: when its first
+CTA started, when its input was staged, first/last CTA exit — i.e. ramp, steady state, tail and the
+gap to the next kernel."""
+import argparse
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from mdi_llm_b200 import ops  # noqa: E402
+from mdi_llm_b200.models.config import Config  # noqa: E402
+from mdi_llm_b200.models.stage import build_stage  # noqa: E402
+from mdi_llm_b200.parallel.engine import FusedStage  # noqa: E402
+from mdi_llm_b200.utils.checkpoint import random_init_stage_  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--layers", type=int, default=4)
+ap.add_argument("--variant", type=int, default=2)
+ap.add_argument("--no-pdl", action="store_true")
+ap.add_argument("--pos", type=int, default=100)
+ap.add_argument("--out", default="")
+a = ap.parse_args()
+ops.require()
+ops.set_linear_variant(a.variant)
+cfg = Config.from_name("Llama-3-8B", n_layer=a.layers, block_size=1024)
+st_mod = build_stage(cfg, "starter", a.layers, meta=True)
+random_init_stage_(st_mod, "cuda", torch.bfloat16)
+st = FusedStage(st_mod, n_slots=1, max_seq_length=512, use_pdl=not a.no_pdl)
+st.warmup()
+st.set_ctx(0, a.pos)
+
+
+def step():
+    st.enqueue_head(wait=False)
+    st.enqueue_sample()
+    st.enqueue_embed(from_tokens=True)
+    st.enqueue_blocks(None, False)
+
+
+for _ in range(3):
+    step()
+torch.cuda.synchronize()
+rows = st.trace_step(step)
+prev_end = None
+print(f"{'kernel':14s} {'entry':>8s} {'ready':>8s} {'staged':>8s} {'1st exit':>9s} {'last exit':>9s} {'dur':>7s} {'gap':>6s} ctas")
+for r in rows:
+    gap = r["entry"] - prev_end if prev_end is not None else 0.0
+    print(f"{r['kernel']:14s} {r['entry']:8.2f} {r['ready']:8.2f} {(r['staged'] or 0):8.2f} {r['first_exit']:9.2f} {r['last_exit']:9.2f} "
+          f"{r['last_exit'] - r['entry']:7.2f} {gap:6.2f} {r['ctas']}")
+    prev_end = r["last_exit"]
+if a.out:
+    json.dump(rows, open(a.out, "w"), indent=1)
