@@ -99,6 +99,8 @@ def parse_args() -> argparse.Namespace:
     ap.add_argument("--partition", default="balanced", choices=["auto", "table", "balanced"])
     ap.add_argument("--no-pdl", action="store_true")
     ap.add_argument("--ctas-per-sm", type=int, default=4)
+    ap.add_argument("--weights", default="bf16", choices=["bf16", "fp8"],
+                    help="bf16 (headline) or fp8-e4m3 block-scaled weights (BASELINE config #5; NOT the headline dtype)")
     ap.add_argument("--hop", default="p2p", choices=["p2p", "nccl"],
                     help="inter-stage hop: fused peer stores + flags (product) or NCCL send/recv (baseline midpoint)")
     ap.add_argument("--variant", type=int, default=-1, help="decode linear path: 0 LDG, 1 bulk-copy x4 stages, 2 bulk-copy x2")
@@ -157,7 +159,8 @@ def run_ours(args: argparse.Namespace) -> Dict[str, Any]:
     random_init_stage_(stage, device, torch.bfloat16, seed=1234 + rank)
     sampling = SamplingParams(temperature=args.temperature, top_k=args.top_k, seed=2024)
     pipe = DevicePipeline(stage, rank, world, n_samples=n_samples, max_seq_length=seq_len, sampling=sampling,
-                          max_prompt_len=args.prompt_len, use_pdl=not args.no_pdl, ctas_per_sm=args.ctas_per_sm, hop=args.hop)
+                          max_prompt_len=args.prompt_len, use_pdl=not args.no_pdl, ctas_per_sm=args.ctas_per_sm, hop=args.hop,
+                          weight_dtype=args.weights, free_bf16=args.weights == "fp8")
     pipe.connect_distributed()
     g = torch.Generator().manual_seed(7)
     prompts = [torch.randint(0, cfg.vocab_size, (args.prompt_len,), generator=g, dtype=torch.int32) for _ in range(n_samples)]
@@ -219,8 +222,9 @@ def run_ours(args: argparse.Namespace) -> Dict[str, Any]:
     out = {
         "metric": METRIC, "value": round(value, 3), "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(ms_total / args.steps, 5), "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic prompts, random-init weights",
-        "impl": "ours",
+        "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16" if args.weights == "bf16" else "fp8-e4m3 block-scaled weights (128), bf16 activations, fp32 accumulate",
+        "data": "synthetic prompts, random-init weights", "impl": "ours",
         "config": {"model": cfg.name, "n_layer": cfg.n_layer, "global_batch": n_samples, "seq_len": seq_len,
                    "prompt_len": args.prompt_len, "parallelism": f"pp{world} recurrent pipeline, plan {plan}",
                    "tokens_per_step": n_samples, "l2_policy": "inputs (stage weights) larger than L2, no flush",

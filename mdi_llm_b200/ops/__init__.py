@@ -38,9 +38,9 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.mdi_error_string.restype = c_char_p
     lib.mdi_error_string.argtypes = [i32]
     lib.mdi_linear_decode.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, i32, i32, f32, i32, i32, i32,
-                                      vp, vp, i64, vp, vp, i32, i32, i32, vp, vp, vp, vp]
+                                      vp, vp, i64, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp]
     lib.mdi_qkv_decode.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, i32, i32, i32, f32, i32,
-                                   vp, vp, i64, i32, i32, i32, vp, vp]
+                                   vp, vp, i64, i32, i32, i32, vp, vp, vp]
     lib.mdi_set_linear_variant.argtypes = [i32]
     lib.mdi_get_linear_variant.restype = i32
     lib.mdi_attn_decode.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp]
@@ -135,6 +135,15 @@ def _bf16(t: Optional[torch.Tensor], name: str) -> None:
         raise OpsError(f"{name}: expected a contiguous CUDA bf16 tensor, got {t.dtype} {t.device}")
 
 
+def _fp8(t: Optional[torch.Tensor], scale: Optional[torch.Tensor], name: str) -> None:
+    if t is None:
+        return
+    if t.element_size() != 1 or not t.is_cuda or not t.is_contiguous():
+        raise OpsError(f"{name}: expected a contiguous CUDA fp8 (1-byte) tensor, got {t.dtype} {t.device}")
+    if scale is None or scale.dtype != torch.float32 or scale.shape != (t.shape[0], t.shape[1] // 128) or t.shape[1] % 128:
+        raise OpsError(f"{name}: block scales must be fp32 [N, K/128] with K a multiple of 128")
+
+
 # ---------------------------------------------------------------------------------------------------
 def linear_decode(
     W: torch.Tensor, x: torch.Tensor, y: torch.Tensor, ctx: torch.Tensor, *,
@@ -145,10 +154,15 @@ def linear_decode(
     signal_flag: Optional[int] = None, done_ctr: Optional[int] = None, ctas_per_sm: int = 4, use_pdl: bool = False,
     y_ptr: Optional[int] = None, residual_ptr: Optional[int] = None, x_ptr: Optional[int] = None, variant: int = -1,
     stats: Optional[torch.Tensor] = None, trace: Optional[int] = None,
+    wscale: Optional[torch.Tensor] = None, wscale2: Optional[torch.Tensor] = None,
 ) -> None:
     """``y = epilogue(W @ norm?(x))`` for one token.  ``*_ptr`` overrides let the output /
-    residual / input live in peer-mapped (other GPU) memory that has no torch tensor."""
-    _bf16(W, "W"); _bf16(W2, "W2")
+    residual / input live in peer-mapped (other GPU) memory that has no torch tensor.
+    With ``wscale`` (fp32 ``[N, K/128]``) ``W`` (and ``W2``/``wscale2``) are fp8-e4m3 block-scaled."""
+    if wscale is None:
+        _bf16(W, "W"); _bf16(W2, "W2")
+    else:
+        _fp8(W, wscale, "W"); _fp8(W2, wscale2, "W2")
     N, K = W.shape
     out_fp32 = int(y is not None and y.dtype == torch.float32)
     hist = amax = None
@@ -159,7 +173,7 @@ def linear_decode(
         residual_ptr if residual_ptr is not None else ptr(residual), y_ptr if y_ptr is not None else ptr(y),
         ptr(ctx), x_slot_stride, res_slot_stride, y_slot_stride, N, K, eps, int(unit_offset), ACT[act], out_fp32,
         wait_flag, status, wait_max_cycles, signal_flag, done_ctr, ctas_per_sm, int(use_pdl), variant, hist, amax,
-        trace, stream_ptr()), "linear_decode")
+        trace, ptr(wscale), ptr(wscale2), stream_ptr()), "linear_decode")
 
 
 def qkv_decode(
@@ -168,15 +182,18 @@ def qkv_decode(
     bias: Optional[torch.Tensor] = None, norm_w: Optional[torch.Tensor] = None, eps: float = 1e-5,
     unit_offset: bool = False, x_slot_stride: int = 0, wait_flag: Optional[int] = None, status: Optional[int] = None,
     wait_max_cycles: int = 0, ctas_per_sm: int = 4, use_pdl: bool = False, x_ptr: Optional[int] = None,
-    variant: int = -1, trace: Optional[int] = None,
+    variant: int = -1, trace: Optional[int] = None, wscale: Optional[torch.Tensor] = None,
 ) -> None:
-    _bf16(W, "W")
+    if wscale is None:
+        _bf16(W, "W")
+    else:
+        _fp8(W, wscale, "W")
     if cos.dtype != torch.float32 or sin.dtype != torch.float32:
         raise OpsError("rope tables must be fp32")
     check(lib().mdi_qkv_decode(
         ptr(W), ptr(bias), x_ptr if x_ptr is not None else ptr(x), ptr(norm_w), ptr(cos), ptr(sin), ptr(q_out),
         ptr(kv_layer), ptr(ctx), x_slot_stride, W.shape[1], n_head, n_groups, head_size, rope_n_elem, max_seq, eps,
-        int(unit_offset), wait_flag, status, wait_max_cycles, ctas_per_sm, int(use_pdl), variant, trace, stream_ptr()),
+        int(unit_offset), wait_flag, status, wait_max_cycles, ctas_per_sm, int(use_pdl), variant, trace, ptr(wscale), stream_ptr()),
         "qkv_decode")
 
 

@@ -15,6 +15,9 @@
 // A warp computes two output rows at a time ("row pair"): for gated MLPs the pair is
 // (fc_1[n], fc_2[n]); for QKV it is the two rows that RoPE rotates together; otherwise two
 // adjacent rows.  The activation vector lives in shared memory as bf16.
+#include <cuda_fp16.h>
+#include <cuda_fp8.h>
+
 #include "common.cuh"
 
 namespace mdi {
@@ -150,6 +153,10 @@ struct StreamArgs {
   unsigned int* hist;        // [4096] histogram of the top 12 bits of the orderable logit key, or null
   unsigned long long* amax;  // packed (key << 32 | ~row) running arg-max, or null
   unsigned long long* trace; // tracer record of this launch (6 x u64) or null
+  // fp8 (e4m3) block-scaled weights: W/W2 then point at 1-byte elements and these hold one fp32
+  // scale per 128 consecutive K elements of every row ([N, K/128]); null = bf16 weights
+  const float* wscale;
+  const float* wscale2;
 };
 
 __device__ __forceinline__ uint32_t float_key(float f) {  // monotone: larger float -> larger key
@@ -403,6 +410,133 @@ __global__ void __launch_bounds__(LIN_THREADS, 1) stream_bulk_kernel(const Strea
   trace_mark(a.trace, 4, false);
 }
 
+// ---- fp8 (e4m3) block-scaled weights, bf16/fp16 activations ("W8A16") ------------------------------
+// Decode is bandwidth-bound, so serving in fp8 halves the bytes per token.  Weights are dequantised
+// in registers: cvt.e4m3x2 -> f16x2, HFMA2 against the fp16 activation vector over one 16-element
+// vector, then one fp32 FMA with the block scale (block = 128 elements of K, so a lane's 16-byte
+// vector never straddles two scales).
+template <int MODE>
+__device__ __forceinline__ void item_rows_fp8(const StreamArgs& a, int it, const unsigned char*& wa, const unsigned char*& wb,
+                                              const float*& sa, const float*& sb) {
+  const unsigned char* W = reinterpret_cast<const unsigned char*>(a.W);
+  const int nblk = a.K / 128;
+  size_t ra, rb;
+  const unsigned char* W2 = W;
+  const float* S2 = a.wscale;
+  if (MODE == MODE_GATED) {
+    ra = rb = (size_t)it;
+    W2 = reinterpret_cast<const unsigned char*>(a.W2);
+    S2 = a.wscale2;
+  } else if (MODE == MODE_PLAIN) {
+    ra = (size_t)2 * it;
+    rb = (size_t)min(2 * it + 1, a.N - 1);
+  } else {
+    const int hs = a.head_size, half_hs = hs / 2, ne = a.rope_n_elem, half_ne = ne / 2;
+    const int j = it / half_hs, i = it % half_hs;
+    int r0, r1;
+    if (i < half_ne) { r0 = i; r1 = i + half_ne; }
+    else { const int t = i - half_ne; r0 = ne + 2 * t; r1 = r0 + 1; }
+    ra = (size_t)j * hs + r0;
+    rb = (size_t)j * hs + r1;
+  }
+  wa = W + ra * a.K;
+  wb = W2 + rb * a.K;
+  sa = a.wscale + ra * nblk;
+  sb = S2 + rb * nblk;
+}
+
+__device__ __forceinline__ float dot16_fp8(const uint4& w, const uint4& x0, const uint4& x1) {
+  const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+  const uint32_t xx[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+  __half2 acc = __float2half2_rn(0.f);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __half2_raw lo = __nv_cvt_fp8x2_to_halfraw2((__nv_fp8x2_storage_t)(ww[i] & 0xffffu), __NV_E4M3);
+    const __half2_raw hi = __nv_cvt_fp8x2_to_halfraw2((__nv_fp8x2_storage_t)(ww[i] >> 16), __NV_E4M3);
+    acc = __hfma2(*reinterpret_cast<const __half2*>(&lo), *reinterpret_cast<const __half2*>(&xx[2 * i]), acc);
+    acc = __hfma2(*reinterpret_cast<const __half2*>(&hi), *reinterpret_cast<const __half2*>(&xx[2 * i + 1]), acc);
+  }
+  const float2 f = __half22float2(acc);
+  return f.x + f.y;
+}
+
+__device__ __forceinline__ void warp_dot2_fp8(const unsigned char* wa, const unsigned char* wb, const float* sa, const float* sb,
+                                              const uint4* __restrict__ xh, int nvec, int lane, float& out_a, float& out_b) {
+  const uint4* pa = reinterpret_cast<const uint4*>(wa);
+  const uint4* pb = reinterpret_cast<const uint4*>(wb);
+  float a0 = 0.f, b0 = 0.f;
+  int v = lane;  // 16 fp8 weights per vector
+  for (; v + 32 * (LIN_UNROLL - 1) < nvec; v += 32 * LIN_UNROLL) {
+    uint4 ra[LIN_UNROLL], rb[LIN_UNROLL];
+    float fa[LIN_UNROLL], fb[LIN_UNROLL];
+#pragma unroll
+    for (int u = 0; u < LIN_UNROLL; ++u) {
+      ra[u] = ldg_stream(pa + v + 32 * u);
+      rb[u] = ldg_stream(pb + v + 32 * u);
+      fa[u] = __ldg(sa + ((v + 32 * u) >> 3));
+      fb[u] = __ldg(sb + ((v + 32 * u) >> 3));
+    }
+#pragma unroll
+    for (int u = 0; u < LIN_UNROLL; ++u) {
+      const uint4 x0 = xh[2 * (v + 32 * u)], x1 = xh[2 * (v + 32 * u) + 1];
+      a0 = fmaf(fa[u], dot16_fp8(ra[u], x0, x1), a0);
+      b0 = fmaf(fb[u], dot16_fp8(rb[u], x0, x1), b0);
+    }
+  }
+  for (; v < nvec; v += 32) {
+    const uint4 x0 = xh[2 * v], x1 = xh[2 * v + 1];
+    a0 = fmaf(__ldg(sa + (v >> 3)), dot16_fp8(ldg_stream(pa + v), x0, x1), a0);
+    b0 = fmaf(__ldg(sb + (v >> 3)), dot16_fp8(ldg_stream(pb + v), x0, x1), b0);
+  }
+  out_a = warp_sum(a0);
+  out_b = warp_sum(b0);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(LIN_THREADS, 3) stream_ldg_fp8_kernel(const StreamArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  bf16* xs = reinterpret_cast<bf16*>(smem_raw);
+  __shared__ float red[LIN_WARPS];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int gw = blockIdx.x * LIN_WARPS + warp, n_gw = gridDim.x * LIN_WARPS;
+  trace_mark(a.trace, 0, true);
+  if (gw < a.n_items) {
+    const unsigned char *wa, *wb;
+    const float *sa, *sb;
+    item_rows_fp8<MODE>(a, gw, wa, wb, sa, sb);
+    for (int off = lane * 128; off < a.K; off += 32 * 128) { prefetch_l2(wa + off); prefetch_l2(wb + off); }
+  }
+  unsigned int* hist_s = stats_begin(a, smem_raw + (size_t)((a.K + 63) / 64) * 64 * sizeof(bf16));
+  unsigned long long best = 0ull;
+  pdl_wait_prior();
+  hop_wait(a.wait, a.ctx);
+  trace_mark(a.trace, 1, true);
+  const int slot = a.ctx ? a.ctx[MDI_CTX_SLOT] : 0, pos = a.ctx ? a.ctx[MDI_CTX_POS] : 0;
+  stage_input(a.x + (size_t)slot * a.x_slot_stride, a.norm_w, a.eps, a.unit_offset, a.K, xs, red);
+  // activations to fp16 in place (same 2 bytes) for the HFMA2 inner product
+  __half* xh16 = reinterpret_cast<__half*>(smem_raw);
+  for (int i = threadIdx.x; i < a.K; i += LIN_THREADS) xh16[i] = __float2half_rn(__bfloat162float(xs[i]));
+  __syncthreads();
+  trace_mark(a.trace, 2, false);
+  pdl_launch_dependents();
+
+  const bf16* res = a.residual ? a.residual + (size_t)slot * a.res_slot_stride : nullptr;
+  const uint4* xv = reinterpret_cast<const uint4*>(smem_raw);
+  const int nvec = a.K / 16;
+  for (int it = gw; it < a.n_items; it += n_gw) {
+    const unsigned char *wa, *wb;
+    const float *sa, *sb;
+    item_rows_fp8<MODE>(a, it, wa, wb, sa, sb);
+    float da, db;
+    warp_dot2_fp8(wa, wb, sa, sb, xv, nvec, lane, da, db);
+    if (lane == 0) item_epilogue<MODE>(a, it, da, db, slot, pos, res, hist_s, best);
+  }
+  stats_flush(a, hist_s, best);
+  hop_signal(a.signal, a.ctx);
+  trace_mark(a.trace, 3, true);
+  trace_mark(a.trace, 4, false);
+}
+
 static int g_num_sms = 0;
 static int num_sms() {
   if (!g_num_sms) {
@@ -441,6 +575,12 @@ static int launch_stream(const StreamArgs& a, int variant, int ctas_per_sm, int 
   const int sms = num_sms();
   if (ctas_per_sm <= 0) ctas_per_sm = 4;
   const int max_useful = (a.n_items + LIN_WARPS - 1) / LIN_WARPS;
+  if (a.wscale != nullptr) {  // fp8 block-scaled weights: register-streamed kernel
+    if (a.K % 128 != 0) return -2;
+    const int grid = max(1, min(sms * min(ctas_per_sm, 3), max_useful));
+    const size_t smem8 = (size_t)((a.K + 63) / 64) * 64 * sizeof(bf16) + (a.hist ? STAT_BINS * 4 : 0);
+    return launch_pdl(stream_ldg_fp8_kernel<MODE>, a, grid, smem8, stream, use_pdl);
+  }
   if (variant == 0) {
     const int grid = max(1, min(sms * ctas_per_sm, max_useful));
     const size_t smem0 = (size_t)((a.K + 63) / 64) * 64 * sizeof(bf16) + (a.hist ? STAT_BINS * 4 : 0);
@@ -473,7 +613,8 @@ int mdi_linear_decode(const void* W, const void* W2, const void* bias, const voi
                       long long res_slot_stride, long long y_slot_stride, int N, int K, float eps, int unit_offset,
                       int act, int out_fp32, const int* wait_flag, int* status, long long wait_max_cycles,
                       int* signal_flag, unsigned int* done_ctr, int ctas_per_sm, int use_pdl, int variant,
-                      unsigned int* hist, unsigned long long* amax, unsigned long long* trace, cudaStream_t stream) {
+                      unsigned int* hist, unsigned long long* amax, unsigned long long* trace, const float* wscale,
+                      const float* wscale2, cudaStream_t stream) {
   if (K % 8 != 0) return -2;
   StreamArgs a{};
   a.W = (const bf16*)W; a.W2 = (const bf16*)W2; a.bias = (const bf16*)bias; a.bias2 = (const bf16*)bias2;
@@ -483,7 +624,7 @@ int mdi_linear_decode(const void* W, const void* W2, const void* bias, const voi
   a.wait = HopWait{wait_flag, status, wait_max_cycles};
   a.signal = HopSignal{signal_flag, done_ctr};
   a.n_items = W2 ? N : (N + 1) / 2;
-  a.hist = hist; a.amax = amax; a.trace = trace;
+  a.hist = hist; a.amax = amax; a.trace = trace; a.wscale = wscale; a.wscale2 = wscale2;
   if (variant < 0) variant = g_default_variant;
   if (W2) return launch_stream<MODE_GATED>(a, variant, ctas_per_sm, use_pdl, stream);
   return launch_stream<MODE_PLAIN>(a, variant, ctas_per_sm, use_pdl, stream);
@@ -493,7 +634,7 @@ int mdi_qkv_decode(const void* W, const void* bias, const void* x, const void* n
                    const float* sin, void* q_out, void* kv, const int* ctx, long long x_slot_stride, int K,
                    int n_head, int n_groups, int head_size, int rope_n_elem, int max_seq, float eps,
                    int unit_offset, const int* wait_flag, int* status, long long wait_max_cycles, int ctas_per_sm,
-                   int use_pdl, int variant, unsigned long long* trace, cudaStream_t stream) {
+                   int use_pdl, int variant, unsigned long long* trace, const float* wscale, cudaStream_t stream) {
   if (K % 8 != 0 || head_size % 2 != 0 || rope_n_elem % 2 != 0 || rope_n_elem > head_size) return -2;
   StreamArgs a{};
   a.W = (const bf16*)W; a.bias = (const bf16*)bias; a.x = (const bf16*)x; a.norm_w = (const bf16*)norm_w;
@@ -503,7 +644,7 @@ int mdi_qkv_decode(const void* W, const void* bias, const void* x, const void* n
   a.max_seq = max_seq; a.eps = eps; a.unit_offset = unit_offset;
   a.wait = HopWait{wait_flag, status, wait_max_cycles};
   a.signal = HopSignal{nullptr, nullptr};
-  a.trace = trace;
+  a.trace = trace; a.wscale = wscale;
   a.n_items = (n_head + 2 * n_groups) * (head_size / 2);
   if (variant < 0) variant = g_default_variant;
   return launch_stream<MODE_QKV>(a, variant, ctas_per_sm, use_pdl, stream);

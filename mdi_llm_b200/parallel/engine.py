@@ -103,7 +103,8 @@ class FusedStage:
 
     def __init__(self, model: StageModule, n_slots: int, max_seq_length: Optional[int] = None,
                  sampling: Optional[SamplingParams] = None, use_pdl: bool = True, ctas_per_sm: int = 4,
-                 wait_max_cycles: int = 0, exportable: bool = False) -> None:
+                 wait_max_cycles: int = 0, exportable: bool = False, weight_dtype: str = "bf16",
+                 free_bf16: bool = False) -> None:
         ops.require()
         cfg = model.config
         p = next(model.parameters())
@@ -165,12 +166,49 @@ class FusedStage:
         self._trace: Optional[torch.Tensor] = None  # device tracer records [n, 6] int64 (see common.cuh)
         self._trace_names: List[str] = []
         self._check_weights()
+        self.weight_dtype = weight_dtype
+        self._q: Dict[int, Tuple[torch.Tensor, torch.Tensor]] = {}  # id(linear) -> (fp8 weight, block scales)
+        if weight_dtype == "fp8":
+            self._quantize(free_bf16)
+        elif weight_dtype != "bf16":
+            raise ValueError("weight_dtype must be 'bf16' or 'fp8'")
 
     # ---- weights ---------------------------------------------------------------------------------
     def _check_weights(self) -> None:
         for n, p in self.model.named_parameters():
             if p.dtype != torch.bfloat16 or not p.is_contiguous() or p.device != self.device:
                 raise ValueError(f"parameter {n}: need contiguous bf16 on {self.device}")
+
+    def _quantize(self, free_bf16: bool) -> None:
+        """fp8-e4m3 block-scaled copies of every projection (BASELINE config #5); embeddings/norms stay bf16."""
+        from ..utils.quantize import quantize_fp8_block
+
+        lins = []
+        for blk in self.model.transformer.h:
+            lins += [blk.attn.attn, blk.attn.proj, blk.mlp.fc_1, blk.mlp.fc_2, blk.mlp.proj]
+        if self.is_starter and not self.cfg.tie_embeddings:
+            lins.append(self.model.lm_head)
+        with torch.cuda.device(self.device):
+            for lin in lins:
+                self._q[id(lin)] = quantize_fp8_block(lin.weight.data)
+                if free_bf16:
+                    lin.weight.data = torch.empty(0, dtype=torch.bfloat16, device=self.device)
+
+    def _w(self, lin: Any, second: bool = False) -> Dict[str, Any]:
+        """kwargs selecting a projection's weights for ``ops.linear_decode`` / ``qkv_decode``."""
+        q = self._q.get(id(lin))
+        if second:
+            return dict(W2=lin.weight, bias2=lin.bias) if q is None else dict(W2=q[0], wscale2=q[1], bias2=lin.bias)
+        return dict(W=lin.weight, bias=lin.bias) if q is None else dict(W=q[0], wscale=q[1], bias=lin.bias)
+
+    def _dense(self, lin: Any) -> torch.Tensor:
+        """bf16 weight matrix for the prefill GEMM (dequantised scratch in fp8 mode)."""
+        q = self._q.get(id(lin))
+        if q is None:
+            return lin.weight
+        from ..utils.quantize import dequantize_fp8_block
+
+        return dequantize_fp8_block(q[0], q[1], torch.bfloat16)
 
     def _gate_act(self) -> str:
         if self.cfg.mlp_class_name == "LLaMAMLP":
@@ -215,8 +253,9 @@ class FusedStage:
         """starter: final RMSNorm + lm_head on ``hidden_in[slot]`` → fp32 logits (+ the sampler's
         logit histogram / arg-max, gathered in the same pass when ``stats``)."""
         m, cfg = self.model, self.cfg
+        lw = self._w(m.lm_head)
         ops.linear_decode(
-            m.lm_head.weight, self.hidden_in, self.logits, self.ctx, bias=m.lm_head.bias,
+            lw.pop("W"), self.hidden_in, self.logits, self.ctx, **lw,
             norm_w=m.transformer.ln_f.weight, eps=cfg.norm_eps, unit_offset=cfg.unit_offset_norm,
             x_slot_stride=cfg.n_embd, wait_flag=self.flags.data_ptr() if wait else None,
             status=self.status.data_ptr(), wait_max_cycles=self.wait_max_cycles, ctas_per_sm=self.ctas_per_sm,
@@ -246,33 +285,37 @@ class FusedStage:
         for li, blk in enumerate(self.model.transformer.h):
             first, last = li == 0, li == self.n_layers - 1
             kv_layer = self.kv[li]
+            qw = self._w(blk.attn.attn)
             ops.qkv_decode(
-                blk.attn.attn.weight, x_in, self.model.cos, self.model.sin, self.q, kv_layer, self.ctx,
+                qw.pop("W"), x_in, self.model.cos, self.model.sin, self.q, kv_layer, self.ctx,
                 n_head=cfg.n_head, n_groups=cfg.n_query_groups, head_size=cfg.head_size,
-                rope_n_elem=cfg.rope_n_elem, max_seq=self.S, bias=blk.attn.attn.bias, norm_w=blk.norm_1.weight,
+                rope_n_elem=cfg.rope_n_elem, max_seq=self.S, norm_w=blk.norm_1.weight, **qw,
                 eps=cfg.norm_eps, unit_offset=cfg.unit_offset_norm, x_slot_stride=x_in_stride,
                 wait_flag=self.flags.data_ptr() if (first and wait_input and not self.is_starter) else None,
                 status=self.status.data_ptr(), wait_max_cycles=self.wait_max_cycles, trace=self._tr(f"L{li}.qkv"), **common)
             ops.attn_decode(self.q, kv_layer, self.y_attn, self.part, self.tickets, self.ctx, n_head=cfg.n_head,
                             n_groups=cfg.n_query_groups, head_size=cfg.head_size, max_seq=self.S,
                             n_split=self.n_split, use_pdl=self.use_pdl, trace=self._tr(f"L{li}.attn"))
-            ops.linear_decode(blk.attn.proj.weight, self.y_attn, self.xb, self.ctx, bias=blk.attn.proj.bias,
+            ow = self._w(blk.attn.proj)
+            ops.linear_decode(ow.pop("W"), self.y_attn, self.xb, self.ctx, **ow,
                               residual=x_in, res_slot_stride=x_in_stride, trace=self._tr(f"L{li}.o_proj"), **common)
-            ops.linear_decode(blk.mlp.fc_1.weight, self.xb, self.h_mlp, self.ctx, W2=blk.mlp.fc_2.weight,
-                              bias=blk.mlp.fc_1.bias, bias2=blk.mlp.fc_2.bias, norm_w=blk.norm_2.weight,
+            gw = {**self._w(blk.mlp.fc_1), **self._w(blk.mlp.fc_2, second=True)}
+            ops.linear_decode(gw.pop("W"), self.xb, self.h_mlp, self.ctx, **gw, norm_w=blk.norm_2.weight,
                               eps=cfg.norm_eps, unit_offset=cfg.unit_offset_norm, act=self._gate_act(),
                               trace=self._tr(f"L{li}.gate_up"), **common)
+            dw = self._w(blk.mlp.proj)
+            d_w = dw.pop("W")
             if not last:
-                ops.linear_decode(blk.mlp.proj.weight, self.h_mlp, self.xa, self.ctx, bias=blk.mlp.proj.bias,
+                ops.linear_decode(d_w, self.h_mlp, self.xa, self.ctx, **dw,
                                   residual=self.xb, trace=self._tr(f"L{li}.down"), **common)
                 x_in, x_in_stride = self.xa, 0
             elif hop is not None:
-                ops.linear_decode(blk.mlp.proj.weight, self.h_mlp, None, self.ctx, bias=blk.mlp.proj.bias,
+                ops.linear_decode(d_w, self.h_mlp, None, self.ctx, **dw,
                                   residual=self.xb, y_ptr=hop.hidden_ptr, y_slot_stride=C,
                                   signal_flag=hop.flag_ptr, done_ctr=self.done_ctr.data_ptr(),
                                   trace=self._tr(f"L{li}.down+hop"), **common)
             else:
-                ops.linear_decode(blk.mlp.proj.weight, self.h_mlp, self.out_local, self.ctx, bias=blk.mlp.proj.bias,
+                ops.linear_decode(d_w, self.h_mlp, self.out_local, self.ctx, **dw,
                                   residual=self.xb, y_slot_stride=C, trace=self._tr(f"L{li}.down"), **common)
 
     # ---- prefill (T > 1): linears on the tcgen05 GEMM ------------------------------------------------
@@ -292,14 +335,14 @@ class FusedStage:
         eps, uo = cfg.norm_eps, cfg.unit_offset_norm
         for li, blk in enumerate(m.transformer.h):
             h = ops.rmsnorm_rows(x, blk.norm_1.weight, eps, uo)
-            qkv = ops.gemm(h, blk.attn.attn.weight, bias=blk.attn.attn.bias)
+            qkv = ops.gemm(h, self._dense(blk.attn.attn), bias=blk.attn.attn.bias)
             y = blk.attn.attend_qkv(qkv.unsqueeze(0), cos, sin, input_pos, m.kv_pool.layer(li, slot))[0].contiguous()
-            x = ops.gemm(y, blk.attn.proj.weight, bias=blk.attn.proj.bias, residual=x)
+            x = ops.gemm(y, self._dense(blk.attn.proj), bias=blk.attn.proj.bias, residual=x)
             h = ops.rmsnorm_rows(x, blk.norm_2.weight, eps, uo)
-            a = ops.gemm(h, blk.mlp.fc_1.weight, bias=blk.mlp.fc_1.bias, block_n=256)
-            b = ops.gemm(h, blk.mlp.fc_2.weight, bias=blk.mlp.fc_2.bias, block_n=256)
+            a = ops.gemm(h, self._dense(blk.mlp.fc_1), bias=blk.mlp.fc_1.bias, block_n=256)
+            b = ops.gemm(h, self._dense(blk.mlp.fc_2), bias=blk.mlp.fc_2.bias, block_n=256)
             g = (blk.mlp.gate(a) * b).contiguous()
-            x = ops.gemm(g, blk.mlp.proj.weight, bias=blk.mlp.proj.bias, residual=x)
+            x = ops.gemm(g, self._dense(blk.mlp.proj), bias=blk.mlp.proj.bias, residual=x)
         return x.unsqueeze(0)
 
     # ---- graphs ------------------------------------------------------------------------------------

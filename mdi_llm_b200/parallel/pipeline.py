@@ -41,7 +41,7 @@ class DevicePipeline:
     def __init__(self, model: StageModule, rank: int, world: int, n_samples: int, max_seq_length: int,
                  sampling: Optional[SamplingParams] = None, max_prompt_len: int = 0, use_pdl: bool = True,
                  ctas_per_sm: int = 4, wait_max_cycles: int = 20_000_000_000, exportable: Optional[bool] = None,
-                 hop: str = "p2p") -> None:
+                 hop: str = "p2p", weight_dtype: str = "bf16", free_bf16: bool = False) -> None:
         if hop not in ("p2p", "nccl"):
             raise ValueError("hop must be 'p2p' (fused peer stores + flags) or 'nccl' (send/recv baseline)")
         self.hop = hop if world > 1 else "p2p"
@@ -51,7 +51,7 @@ class DevicePipeline:
         exportable = (world > 1) if exportable is None else exportable
         self.stage = FusedStage(model, n_slots=n_samples, max_seq_length=max_seq_length, sampling=sampling,
                                 use_pdl=use_pdl, ctas_per_sm=ctas_per_sm, wait_max_cycles=wait_max_cycles,
-                                exportable=exportable)
+                                exportable=exportable, weight_dtype=weight_dtype, free_bf16=free_bf16)
         self.model = model.eval()
         self.device = self.stage.device
         self.C = model.config.n_embd

@@ -158,3 +158,29 @@ def test_device_pipeline_multi_gpu_one_process(n_stages):
     for i in range(len(prompts)):
         assert torch.equal(results[0][i], ref[i]), f"sample {i}: {results[0][i].tolist()} vs {ref[i].tolist()}"
         _near_argmax_check(cfg, full, results[0][i], len(prompts[i]))
+
+
+def test_fp8_weights_pipeline_follows_the_dequantised_model():
+    """BASELINE config #5 path: fp8 block-scaled weights end to end (prefill dequantised + tcgen05,
+    decode on the fp8 streaming kernels) tracks the eager model run on the dequantised weights."""
+    from mdi_llm_b200.parallel.pipeline import DevicePipeline
+    from mdi_llm_b200.parallel.scheduler import SamplingParams
+    from mdi_llm_b200.utils.quantize import dequantize_fp8_block, fp8_error, quantize_fp8_block
+
+    cfg = _cfg()
+    full, (st,) = _stages(cfg, 1)
+    deq = {}
+    for k, v in full.items():
+        if v.dim() == 2 and "wte" not in k and v.shape[1] % 128 == 0:
+            assert fp8_error(v) < 0.05
+            q, s = quantize_fp8_block(v.cuda())
+            deq[k] = dequantize_fp8_block(q, s, torch.bfloat16).cpu()
+        else:
+            deq[k] = v
+    pipe = DevicePipeline(st, 0, 1, n_samples=2, max_seq_length=128, sampling=SamplingParams.greedy(), weight_dtype="fp8",
+                          free_bf16=True)
+    assert st.transformer.h[0].mlp.proj.weight.numel() == 0  # bf16 copies released
+    prompts = [torch.tensor([1, 50, 60, 70]), torch.tensor([1, 9, 8])]
+    out = pipe.generate(prompts, 10)
+    for i, p in enumerate(prompts):
+        _near_argmax_check(cfg, deq, out[i], len(p), tol=0.3)

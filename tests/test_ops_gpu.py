@@ -290,3 +290,51 @@ def test_cuda_graph_capture_and_replay():
     y_ref = (x0.float() @ W.float().T).bfloat16()
     torch.testing.assert_close(y.float(), y_ref.float(), rtol=2e-2, atol=2e-2)
     torch.testing.assert_close(x.float(), (y_ref.float() @ W.float().T).bfloat16().float(), rtol=3e-2, atol=3e-2)
+
+
+@pytest.mark.parametrize("N,K", [(4096, 4096), (6144, 4096), (4096, 14336), (1000, 256)])
+def test_linear_decode_fp8_block_scaled(N, K):
+    """W8A16: fp8-e4m3 weights with per-128 block scales vs the dequantised fp32 reference."""
+    ops = _ops()
+    from mdi_llm_b200.utils.quantize import dequantize_fp8_block, quantize_fp8_block
+
+    torch.manual_seed(N * 3 + K)
+    W = (torch.randn(N, K, device="cuda") * 0.02).bfloat16()
+    W2 = (torch.randn(N, K, device="cuda") * 0.02).bfloat16()
+    x = torch.randn(K, device="cuda").bfloat16()
+    nw = (1 + 0.1 * torch.randn(K, device="cuda")).bfloat16()
+    res = torch.randn(N, device="cuda").bfloat16()
+    (q, s), (q2, s2) = quantize_fp8_block(W), quantize_fp8_block(W2)
+    Wd, W2d = dequantize_fp8_block(q, s, torch.float32), dequantize_fp8_block(q2, s2, torch.float32)
+    xin = _rmsnorm_ref(x, nw, 1e-5).float()
+    y = torch.empty(N, device="cuda", dtype=torch.bfloat16)
+    ops.linear_decode(q, x, y, _ctx(ops), wscale=s, norm_w=nw, residual=res, eps=1e-5)
+    ref = (xin @ Wd.T).bfloat16().float() + res.float()
+    torch.testing.assert_close(y.float(), ref, rtol=3e-2, atol=3e-2)
+    ops.linear_decode(q, x, y, _ctx(ops), wscale=s, W2=q2, wscale2=s2, norm_w=nw, act="silu_gate", eps=1e-5)
+    a, b = (xin @ Wd.T).bfloat16(), (xin @ W2d.T).bfloat16()
+    ref = (torch.nn.functional.silu(a.float()).bfloat16() * b).float()
+    torch.testing.assert_close(y.float(), ref, rtol=4e-2, atol=4e-2)
+
+
+def test_qkv_decode_fp8_block_scaled():
+    ops = _ops()
+    from mdi_llm_b200.models.gpt import build_rope_cache
+    from mdi_llm_b200.utils.quantize import dequantize_fp8_block, quantize_fp8_block
+
+    torch.manual_seed(11)
+    H, G, hs, ne, C, S, pos = 32, 8, 128, 128, 4096, 64, 9
+    W = (torch.randn((H + 2 * G) * hs, C, device="cuda") * 0.02).bfloat16()
+    x = torch.randn(C, device="cuda").bfloat16()
+    nw = (1 + 0.1 * torch.randn(C, device="cuda")).bfloat16()
+    q8, s8 = quantize_fp8_block(W)
+    cos, sin = build_rope_cache(S, ne, device=torch.device("cuda"), base=500000)
+    q = torch.zeros(H * hs, device="cuda", dtype=torch.bfloat16)
+    kv = torch.zeros(1, 2, G, S, hs, device="cuda", dtype=torch.bfloat16)
+    ops.qkv_decode(q8, x, cos, sin, q, kv, _ctx(ops, pos=pos), n_head=H, n_groups=G, head_size=hs, rope_n_elem=ne,
+                   max_seq=S, norm_w=nw, eps=1e-5, wscale=s8)
+    Wd = dequantize_fp8_block(q8, s8, torch.bfloat16)
+    qr, kr, vr = _interleaved_qkv_ref(Wd, None, _rmsnorm_ref(x, nw, 1e-5), (H, G, hs, ne), cos, sin, pos)
+    torch.testing.assert_close(q.view(H, hs).float(), qr.float(), rtol=4e-2, atol=4e-2)
+    torch.testing.assert_close(kv[0, 0, :, pos].float(), kr.float(), rtol=4e-2, atol=4e-2)
+    torch.testing.assert_close(kv[0, 1, :, pos].float(), vr.float(), rtol=4e-2, atol=4e-2)

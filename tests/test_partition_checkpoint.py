@@ -79,3 +79,24 @@ def test_incremental_save_roundtrip(tmp_path):
         saver.save(sd)
     back = torch.load(tmp_path / "out.pth", weights_only=True)
     assert torch.equal(back["a"], a) and torch.equal(back["b"], b)
+
+
+def test_fp8_block_quantisation_roundtrip_error():
+    from mdi_llm_b200.utils.quantize import dequantize_fp8_block, fp8_error, quantize_fp8_block, quantize_linear_weights
+
+    torch.manual_seed(0)
+    w = torch.randn(96, 512) * 0.02
+    w[3, 100] = 1.5  # an outlier only hurts its own 128-block
+    q, s = quantize_fp8_block(w)
+    assert q.dtype == torch.float8_e4m3fn and s.shape == (96, 4) and s.dtype == torch.float32
+    d = dequantize_fp8_block(q, s, torch.float32)
+    assert fp8_error(w) < 0.04
+    clean = torch.ones(96, 512, dtype=torch.bool)
+    clean[3, :128] = False
+    assert ((d - w).abs()[clean] <= 0.0625 * w.abs()[clean] + 1e-6).all()  # e4m3: 3 mantissa bits
+    sd = quantize_linear_weights({"transformer.wte.weight": torch.randn(10, 128), "transformer.h.0.attn.proj.weight": w,
+                                  "transformer.h.0.norm_1.weight": torch.ones(512)})
+    assert sd["transformer.h.0.attn.proj.weight"].dtype == torch.float8_e4m3fn
+    assert "transformer.h.0.attn.proj.weight_scale" in sd and sd["transformer.wte.weight"].dtype == torch.float32
+    with pytest.raises(ValueError):
+        quantize_fp8_block(torch.randn(4, 100))
