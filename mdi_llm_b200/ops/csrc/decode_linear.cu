@@ -76,27 +76,78 @@ __device__ __forceinline__ void warp_dot2(const bf16* __restrict__ wa, const bf1
 
 // Stage the activation row into shared memory, optionally RMS-normalised:
 //   xn = bf16(x * rsqrt(mean(x^2) + eps)) * (w | 1 + w)      (same rounding points as the eager model)
+// Fully vectorised: every thread owns up to STAGE_VPT 16-byte vectors of x (and of the norm weight),
+// all loads are issued before the first use, the row stays in registers across the reduction.
+// (The first version re-read x from shared memory and fetched the norm weight with 2-byte global
+//  loads inside the loop: 16 dependent L2 round trips = 11 us on the QKV kernel — see
+//  profiles/trace_step_*.json.)
+constexpr int STAGE_VPT = 4;  // covers K <= 4 * 256 * 8 = 8192 (n_embd of 70B models); longer rows use the loop
+
+__device__ __forceinline__ uint32_t norm_pair(uint32_t xp, uint32_t wp, float rstd, int unit_offset) {
+  float x0 = round_bf16(bf16lo(xp) * rstd), x1 = round_bf16(bf16hi(xp) * rstd);
+  float w0 = bf16lo(wp), w1 = bf16hi(wp);
+  if (unit_offset) { w0 = round_bf16(1.f + w0); w1 = round_bf16(1.f + w1); }
+  const __nv_bfloat162 o = __floats2bfloat162_rn(x0 * w0, x1 * w1);
+  return *reinterpret_cast<const uint32_t*>(&o);
+}
+
 __device__ __forceinline__ void stage_input(const bf16* __restrict__ x, const bf16* __restrict__ norm_w,
                                             float eps, int unit_offset, int K, bf16* xs, float* red) {
   const int tid = threadIdx.x;
+  const int nvec = K / 8;
+  const uint4* src = reinterpret_cast<const uint4*>(x);
+  uint4* dst = reinterpret_cast<uint4*>(xs);
   if (norm_w == nullptr) {
-    const uint4* src = reinterpret_cast<const uint4*>(x);
-    uint4* dst = reinterpret_cast<uint4*>(xs);
-    for (int v = tid; v < K / 8; v += LIN_THREADS) dst[v] = __ldcg(src + v);
+    for (int v = tid; v < nvec; v += LIN_THREADS) dst[v] = __ldcg(src + v);
     __syncthreads();
     return;
   }
+  const uint4* wsrc = reinterpret_cast<const uint4*>(norm_w);
+  if (nvec <= STAGE_VPT * LIN_THREADS) {
+    uint4 xr[STAGE_VPT], wr[STAGE_VPT];
+#pragma unroll
+    for (int j = 0; j < STAGE_VPT; ++j) {
+      const int v = tid + j * LIN_THREADS;
+      if (v < nvec) { xr[j] = __ldcg(src + v); wr[j] = __ldg(wsrc + v); }
+      else { xr[j] = make_uint4(0, 0, 0, 0); wr[j] = xr[j]; }
+    }
+    float ss = 0.f;
+#pragma unroll
+    for (int j = 0; j < STAGE_VPT; ++j) {
+      const uint32_t p[4] = {xr[j].x, xr[j].y, xr[j].z, xr[j].w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { const float a = bf16lo(p[q]), b = bf16hi(p[q]); ss = fmaf(a, a, ss); ss = fmaf(b, b, ss); }
+    }
+    ss = warp_sum(ss);
+    if ((tid & 31) == 0) red[tid >> 5] = ss;
+    __syncthreads();
+    float tot = 0.f;
+#pragma unroll
+    for (int w = 0; w < LIN_WARPS; ++w) tot += red[w];
+    const float rstd = rsqrtf(tot / (float)K + eps);
+#pragma unroll
+    for (int j = 0; j < STAGE_VPT; ++j) {
+      const int v = tid + j * LIN_THREADS;
+      if (v < nvec) {
+        uint4 o;
+        o.x = norm_pair(xr[j].x, wr[j].x, rstd, unit_offset);
+        o.y = norm_pair(xr[j].y, wr[j].y, rstd, unit_offset);
+        o.z = norm_pair(xr[j].z, wr[j].z, rstd, unit_offset);
+        o.w = norm_pair(xr[j].w, wr[j].w, rstd, unit_offset);
+        dst[v] = o;
+      }
+    }
+    __syncthreads();
+    return;
+  }
+  // very long rows: two vectorised passes through shared memory
   float ss = 0.f;
-  const uint4* src = reinterpret_cast<const uint4*>(x);
-  uint4* dst = reinterpret_cast<uint4*>(xs);
-  for (int v = tid; v < K / 8; v += LIN_THREADS) {
-    uint4 r = __ldcg(src + v);
+  for (int v = tid; v < nvec; v += LIN_THREADS) {
+    const uint4 r = __ldcg(src + v);
     dst[v] = r;
-    float f;
-    f = bf16lo(r.x); ss = fmaf(f, f, ss); f = bf16hi(r.x); ss = fmaf(f, f, ss);
-    f = bf16lo(r.y); ss = fmaf(f, f, ss); f = bf16hi(r.y); ss = fmaf(f, f, ss);
-    f = bf16lo(r.z); ss = fmaf(f, f, ss); f = bf16hi(r.z); ss = fmaf(f, f, ss);
-    f = bf16lo(r.w); ss = fmaf(f, f, ss); f = bf16hi(r.w); ss = fmaf(f, f, ss);
+    const uint32_t p[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { const float a = bf16lo(p[q]), b = bf16hi(p[q]); ss = fmaf(a, a, ss); ss = fmaf(b, b, ss); }
   }
   ss = warp_sum(ss);
   if ((tid & 31) == 0) red[tid >> 5] = ss;
@@ -105,11 +156,12 @@ __device__ __forceinline__ void stage_input(const bf16* __restrict__ x, const bf
 #pragma unroll
   for (int w = 0; w < LIN_WARPS; ++w) tot += red[w];
   const float rstd = rsqrtf(tot / (float)K + eps);
-  for (int i = tid; i < K; i += LIN_THREADS) {
-    float xn = round_bf16(__bfloat162float(xs[i]) * rstd);
-    float w = __bfloat162float(norm_w[i]);
-    if (unit_offset) w = round_bf16(1.f + w);
-    xs[i] = __float2bfloat16_rn(xn * w);
+  for (int v = tid; v < nvec; v += LIN_THREADS) {
+    const uint4 r = dst[v], wv = __ldg(wsrc + v);
+    uint4 o;
+    o.x = norm_pair(r.x, wv.x, rstd, unit_offset); o.y = norm_pair(r.y, wv.y, rstd, unit_offset);
+    o.z = norm_pair(r.z, wv.z, rstd, unit_offset); o.w = norm_pair(r.w, wv.w, rstd, unit_offset);
+    dst[v] = o;
   }
   __syncthreads();
 }
