@@ -97,8 +97,20 @@ __device__ __forceinline__ void stage_input(const bf16* __restrict__ x, const bf
   const int nvec = K / 8;
   const uint4* src = reinterpret_cast<const uint4*>(x);
   uint4* dst = reinterpret_cast<uint4*>(xs);
-  if (norm_w == nullptr) {
-    for (int v = tid; v < nvec; v += LIN_THREADS) dst[v] = __ldcg(src + v);
+  if (norm_w == nullptr) {  // plain copy: all loads in flight before the first store
+    for (int v0 = 0; v0 < nvec; v0 += 8 * LIN_THREADS) {
+      uint4 r[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int v = v0 + tid + j * LIN_THREADS;
+        if (v < nvec) r[j] = __ldcg(src + v);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int v = v0 + tid + j * LIN_THREADS;
+        if (v < nvec) dst[v] = r[j];
+      }
+    }
     __syncthreads();
     return;
   }
@@ -641,7 +653,7 @@ static int launch_stream(const StreamArgs& a, int variant, int ctas_per_sm, int 
   const int stages = variant == 1 ? 4 : (variant == 3 ? 3 : 2);
   const size_t smem = (size_t)LIN_WARPS * stages * 2 * TS_CHUNK * 2 + (size_t)((a.K + 63) / 64) * 64 * 2 +
                       (size_t)LIN_WARPS * stages * 8 + (a.hist ? STAT_BINS * 4 : 0);
-  if (smem > 227 * 1024) return -2;
+  if (smem > 227 * 1024) return launch_stream<MODE>(a, 0, ctas_per_sm, use_pdl, stream);  // huge K: LDG path
   const int per_sm = variant == 1 ? 1 : max(1, min(ctas_per_sm, (int)((227 * 1024) / (smem + 1024))));
   const int grid = max(1, min(sms * per_sm, max_useful));
   if (variant == 1) return launch_pdl(stream_bulk_kernel<MODE, 4>, a, grid, smem, stream, use_pdl);
@@ -649,7 +661,7 @@ static int launch_stream(const StreamArgs& a, int variant, int ctas_per_sm, int 
   return launch_pdl(stream_bulk_kernel<MODE, 2>, a, grid, smem, stream, use_pdl);
 }
 
-static int g_default_variant = 0;
+static int g_default_variant = 2;  // bulk-copy ring x2 stages: fastest in-pipeline (profiles/README.md)
 
 }  // namespace mdi
 
