@@ -82,9 +82,13 @@ def lib() -> ctypes.CDLL:
     if _load_error is not None:
         raise OpsError(f"kernel library unavailable: {_load_error}") from _load_error
     try:
-        if not _build.LIB.exists() or (not _build.is_fresh() and _build.nvcc_path()):
-            _build.build()
-        handle = ctypes.CDLL(str(_build.LIB))
+        alt = os.environ.get("MDI_OPS_LIB")  # kernel A/B experiments: load another build of the same ABI
+        if alt:
+            handle = ctypes.CDLL(alt)
+        else:
+            if not _build.LIB.exists() or (not _build.is_fresh() and _build.nvcc_path()):
+                _build.build()
+            handle = ctypes.CDLL(str(_build.LIB))
         _declare(handle)
         _lib = handle
         return handle

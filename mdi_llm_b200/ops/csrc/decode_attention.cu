@@ -38,8 +38,8 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const AttnArgs
   constexpr int DPL = HS / 32;   // output dims per lane in the PV phase
   constexpr int QDIM = HS / 4;   // dims per lane in the QK phase (4 lanes per position)
   constexpr int KV4 = QDIM / 8;  // uint4 loads per lane per position
-  constexpr int VB = (QPK >= 8) ? (HS >= 128 ? 8 : 16) : ATT_TILE;  // V rows per load batch (register budget)
-  constexpr int KPASS = (QPK * HS >= 1024) ? 1 : (QPK * HS >= 512) ? 2 : 4;  // K passes whose loads are batched
+  constexpr int VB = (QPK >= 8 && HS >= 128) ? 8 : 16;  // V rows per load batch (register budget)
+  constexpr int KPASS = (QPK >= 8 && HS >= 128) ? 1 : 4;  // K passes whose loads are batched
   __shared__ __align__(16) float q_s[QPK][HS];
   __shared__ float s_s[ATT_WARPS][QPK][ATT_TILE];
   __shared__ float mrg_m[ATT_WARPS][QPK], mrg_l[ATT_WARPS][QPK];
@@ -63,6 +63,12 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const AttnArgs
   trace_mark(a.trace, 2, false);
   const int t_lo = split * tiles_per_split, t_hi = min(tiles, t_lo + tiles_per_split);
 
+  for (int i = threadIdx.x; i < QPK * HS; i += ATT_THREADS) {
+    const int h = i / HS, d = i % HS;
+    q_s[h][d] = __bfloat162float(a.q[(size_t)(g * QPK + h) * HS + d]) * a.scale_log2;
+  }
+  __syncthreads();
+
   const bf16* kbase = a.kv + (((size_t)slot * 2 + 0) * a.n_groups + g) * (size_t)a.max_seq * HS;
   const bf16* vbase = a.kv + (((size_t)slot * 2 + 1) * a.n_groups + g) * (size_t)a.max_seq * HS;
 
@@ -74,47 +80,19 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const AttnArgs
     for (int d = 0; d < DPL; ++d) acc[h][d] = 0.f;
   }
 
-  // Latency chain: ctx -> {K tile, V tile, q} all in flight together -> math.  The K (and, when the
-  // register budget allows, V) loads of a warp's tile are issued BEFORE q is fetched and before the
-  // block-wide barrier, so a short context costs two memory round trips, not five.
-  uint4 kk[KPASS][KV4];
-  uint32_t vv[VB][DPL / 2];
-  auto issue_k = [&](int p0, int pg) {
-#pragma unroll
-    for (int pp = 0; pp < KPASS; ++pp) {
-      const int pos = min(p0 + (pg * KPASS + pp) * 8 + (lane >> 2), L - 1);  // clamp: masked later
-      const uint4* kr = reinterpret_cast<const uint4*>(kbase + (size_t)pos * HS + (lane & 3) * QDIM);
-#pragma unroll
-      for (int v = 0; v < KV4; ++v) kk[pp][v] = __ldg(kr + v);
-    }
-  };
-  auto issue_v = [&](int p0, int half) {
-#pragma unroll
-    for (int r = 0; r < VB; ++r) {
-      const int pos = min(p0 + half * VB + r, L - 1);  // masked rows have p == 0
-      const uint32_t* vr = reinterpret_cast<const uint32_t*>(vbase + (size_t)pos * HS + lane * DPL);
-#pragma unroll
-      for (int w = 0; w < DPL / 2; ++w) vv[r][w] = __ldg(vr + w);
-    }
-  };
-  constexpr bool V_EARLY = (VB == ATT_TILE);  // whole V tile fits the register budget
-  const int t_first = t_lo + warp;
-  if (t_first < t_hi) {
-    issue_k(t_first * ATT_TILE, 0);
-    if (V_EARLY) issue_v(t_first * ATT_TILE, 0);
-  }
-  for (int i = threadIdx.x; i < QPK * HS; i += ATT_THREADS) {
-    const int h = i / HS, d = i % HS;
-    q_s[h][d] = __bfloat162float(a.q[(size_t)(g * QPK + h) * HS + d]) * a.scale_log2;
-  }
-  __syncthreads();
-
-  for (int t = t_first; t < t_hi; t += ATT_WARPS) {
+  for (int t = t_lo + warp; t < t_hi; t += ATT_WARPS) {
     const int p0 = t * ATT_TILE;
+    // ---- issue the K loads of KPASS passes (8 positions each) up-front, then consume --------------
 #pragma unroll
     for (int pg = 0; pg < 4 / KPASS; ++pg) {
-      if (pg > 0 || t != t_first) issue_k(p0, pg);
-      if (V_EARLY && pg == 0 && t != t_first) issue_v(p0, 0);
+      uint4 kk[KPASS][KV4];
+#pragma unroll
+      for (int pp = 0; pp < KPASS; ++pp) {
+        const int pos = min(p0 + (pg * KPASS + pp) * 8 + (lane >> 2), L - 1);  // clamp: masked below
+        const uint4* kr = reinterpret_cast<const uint4*>(kbase + (size_t)pos * HS + (lane & 3) * QDIM);
+#pragma unroll
+        for (int v = 0; v < KV4; ++v) kk[pp][v] = __ldg(kr + v);
+      }
 #pragma unroll
       for (int pp = 0; pp < KPASS; ++pp) {
         const int pj = (pg * KPASS + pp) * 8 + (lane >> 2), pos = p0 + pj, qd = (lane & 3) * QDIM;
@@ -138,10 +116,10 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const AttnArgs
         }
 #pragma unroll
         for (int h = 0; h < QPK; ++h) {
-          float sv = sc[h];
-          sv += __shfl_xor_sync(0xffffffffu, sv, 1);
-          sv += __shfl_xor_sync(0xffffffffu, sv, 2);
-          if ((lane & 3) == 0) s_s[warp][h][pj] = (pos < L) ? sv : -INFINITY;
+          float s = sc[h];
+          s += __shfl_xor_sync(0xffffffffu, s, 1);
+          s += __shfl_xor_sync(0xffffffffu, s, 2);
+          if ((lane & 3) == 0) s_s[warp][h][pj] = (pos < L) ? s : -INFINITY;
         }
       }
     }
@@ -149,9 +127,9 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const AttnArgs
     // ---- online softmax update: lane == position inside the tile --------------------------
 #pragma unroll
     for (int h = 0; h < QPK; ++h) {
-      const float sv = s_s[warp][h][lane];
-      const float m_new = fmaxf(m[h], warp_max(sv));
-      const float p = (sv == -INFINITY) ? 0.f : exp2f(sv - m_new);
+      const float s = s_s[warp][h][lane];
+      const float m_new = fmaxf(m[h], warp_max(s));
+      const float p = (s == -INFINITY) ? 0.f : exp2f(s - m_new);
       const float corr = (m[h] == -INFINITY) ? 0.f : exp2f(m[h] - m_new);
       l[h] = l[h] * corr + warp_sum(p);
       m[h] = m_new;
@@ -160,10 +138,17 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const AttnArgs
       s_s[warp][h][lane] = p;
     }
     __syncwarp();
-    // ---- PV: lane owns DPL consecutive output dims ---------------------------------------------------
+    // ---- PV: lane owns DPL consecutive output dims; rows loaded 16 at a time -------------------
 #pragma unroll
     for (int half = 0; half < ATT_TILE / VB; ++half) {
-      if (!V_EARLY) issue_v(p0, half);
+      uint32_t vv[VB][DPL / 2];
+#pragma unroll
+      for (int r = 0; r < VB; ++r) {
+        const int pos = min(p0 + half * VB + r, L - 1);  // masked rows have p == 0
+        const uint32_t* vr = reinterpret_cast<const uint32_t*>(vbase + (size_t)pos * HS + lane * DPL);
+#pragma unroll
+        for (int w = 0; w < DPL / 2; ++w) vv[r][w] = __ldg(vr + w);
+      }
 #pragma unroll
       for (int r = 0; r < VB; ++r) {
 #pragma unroll

@@ -391,7 +391,7 @@ __global__ void __launch_bounds__(LIN_THREADS, 3) stream_ldg_kernel(const Stream
 constexpr int TS_CHUNK = 1024;  // elements per row chunk (2 KB)
 
 template <int MODE, int STAGES>
-__global__ void __launch_bounds__(LIN_THREADS, 1) stream_bulk_kernel(const StreamArgs a) {
+__global__ void __launch_bounds__(LIN_THREADS, STAGES == 2 ? 3 : (STAGES == 3 ? 2 : 1)) stream_bulk_kernel(const StreamArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int gw = blockIdx.x * LIN_WARPS + warp, n_gw = gridDim.x * LIN_WARPS;
