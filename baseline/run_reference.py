@@ -63,20 +63,19 @@ def _write_checkpoint(ckpt: Path, model_name: str, device: str) -> None:
     def ones(n: int) -> "torch.Tensor":
         return (1.0 + 0.1 * torch.randn(n, generator=g, device=device)).to(torch.bfloat16).cpu()
 
-    C, I, V = cfg.n_embd, cfg.intermediate_size, cfg.padded_vocab_size
-    qkv = (cfg.n_head + 2 * cfg.n_query_groups) * cfg.head_size
-    sd = {"transformer.wte.weight": rnd(V, C)}
-    for l in range(cfg.n_layer):
-        p = f"transformer.h.{l}"
-        sd[f"{p}.norm_1.weight"] = ones(C)
-        sd[f"{p}.attn.attn.weight"] = rnd(qkv, C)
-        sd[f"{p}.attn.proj.weight"] = rnd(C, cfg.n_head * cfg.head_size)
-        sd[f"{p}.norm_2.weight"] = ones(C)
-        sd[f"{p}.mlp.fc_1.weight"] = rnd(I, C)
-        sd[f"{p}.mlp.fc_2.weight"] = rnd(I, C)
-        sd[f"{p}.mlp.proj.weight"] = rnd(C, I)
-    sd["transformer.ln_f.weight"] = ones(C)
-    sd["lm_head.weight"] = rnd(V, C)
+    # parameter names and shapes come from the reference's own module tree (built on the meta device),
+    # so every architecture its Config can describe gets a loadable checkpoint
+    from sub.model import GPT
+
+    with torch.device("meta"):
+        skeleton = GPT(cfg)
+    sd = {}
+    for name, t in skeleton.state_dict().items():
+        if t.ndim == 1 and name.endswith(".weight"):
+            sd[name] = ones(t.shape[0])  # normalisation gains
+        else:
+            sd[name] = rnd(*t.shape)
+    V = cfg.padded_vocab_size
     torch.save(sd, ckpt / "lit_model.pth")
     with open(ckpt / "model_config.yaml", "w") as f:
         yaml.safe_dump(cfg.asdict(), f)
@@ -170,7 +169,7 @@ def run_reference(args: Any) -> Dict[str, Any]:
         dt = tok_time[hi][1] - tok_time[lo][1]
         value = (hi - lo) / dt
         return {
-            "metric": METRIC, "value": round(value, 3), "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
+            "metric": METRIC.replace("Llama-3-8B", cfg.name) if cfg.name != "Llama-3-8B" else METRIC, "value": round(value, 3), "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(dt * 1e3 / args.steps, 5), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if dtype == "bfloat16" else dtype,
             "data": "synthetic prompts, random-init weights", "impl": "reference",

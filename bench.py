@@ -220,7 +220,7 @@ def run_ours(args: argparse.Namespace) -> Dict[str, Any]:
         steps_e2e = e2e_rounds * n_samples
 
     out = {
-        "metric": METRIC, "value": round(value, 3), "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
+        "metric": METRIC.replace("Llama-3-8B", cfg.name) if cfg.name != "Llama-3-8B" else METRIC, "value": round(value, 3), "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(ms_total / args.steps, 5), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16" if args.weights == "bf16" else "fp8-e4m3 block-scaled weights (128), bf16 activations, fp32 accumulate",
@@ -254,7 +254,17 @@ def main() -> None:
     if args.impl == "reference":
         from baseline.run_reference import run_reference
 
-        out = run_reference(args)
+        # the reference prints its generated samples and progress spinners on stdout: keep stdout for
+        # the one JSON line by pointing fd 1 at stderr while it runs
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            out = run_reference(args)
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     else:
         out = run_ours(args)
     if out:
