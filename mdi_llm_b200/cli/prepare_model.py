@@ -25,6 +25,8 @@ def build_parser() -> argparse.ArgumentParser:
     p.add_argument("--device", type=str, default="cpu")
     p.add_argument("--random-init", action="store_true", help="create random weights instead of downloading")
     p.add_argument("--partition", default="auto", choices=["auto", "table", "balanced"])
+    p.add_argument("--head-on", default="starter", choices=["starter", "finisher"],
+                   help="which node owns ln_f + lm_head ('finisher' = first-generation chain layout)")
     p.add_argument("--seed", type=int, default=1234)
     return p
 
@@ -63,7 +65,7 @@ def main(argv=None) -> int:
     print(f"Model {cfg.name}: {cfg.n_layer} layers, checkpoint at {model_path}")
     if args.n_nodes and args.n_nodes > 1:
         plan = plan_layers(args.n_nodes, cfg.n_layer, cfg, policy=args.partition)
-        out = split_and_store(sd, args.n_nodes, model_path, plan=plan, config=cfg, verb=True)
+        out = split_and_store(sd, args.n_nodes, model_path, plan=plan, config=cfg, verb=True, head_on=args.head_on)
         print(f"Chunks written to {out} (layers per node: {plan})")
     return 0
 

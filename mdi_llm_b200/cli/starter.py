@@ -42,6 +42,10 @@ def build_parser() -> argparse.ArgumentParser:
     p.add_argument("--greedy", action="store_true", help="arg-max decoding")
     p.add_argument("--temperature", type=float, default=None)
     p.add_argument("--top-k", type=int, default=None)
+    p.add_argument("--no-kv-cache", action="store_true",
+                   help="GPT-2 generation protocol: no KV caches, the whole context travels the ring every step")
+    p.add_argument("--head-on", default="starter", choices=["starter", "finisher"],
+                   help="'finisher': first-generation chain, the last node owns ln_f + lm_head and returns logits")
     p.add_argument("--partition", default="auto", choices=["auto", "table", "balanced"], help="layer partition policy")
     return p
 
@@ -66,7 +70,8 @@ def main(argv=None) -> int:
     gpt_distr = GPTDistributed(
         node_type="starter", config_file=args.nodes_config, ckpt_dir=args.ckpt, chunk_path=args.chunk,
         device=args.device, dtype=args.dtype, model_seq_length=args.sequence_length, verb=args.verb, plots=args.plots,
-        compile=args.compile, engine=args.engine, sampling=sampling, partition=args.partition)
+        compile=args.compile, engine=args.engine, sampling=sampling, partition=args.partition,
+        use_kv_cache=not args.no_kv_cache, head_on=args.head_on)
     gen_times = gpt_distr.start(n_samples=args.n_samples, tokens_per_sample=args.n_tokens, prompt=args.prompt)
 
     if args.plots and gen_times:

@@ -120,8 +120,12 @@ def split_parameters(
     n_nodes: int,
     plan: Optional[Sequence[int]] = None,
     config: Optional[Config] = None,
+    head_on: str = "starter",
 ) -> Tuple[Dict[str, Any], Dict[str, Any]]:
     """Pop the entries of a full litGPT state dict into per-node chunks.
+
+    ``head_on="finisher"`` gives the first-generation layout (old/nanoGPT/sub/model_dist.py:90-221):
+    ``ln_f`` + ``lm_head`` go to the last chunk instead of the starter (a tied head is cloned).
 
     Returns ``({"starter": sd, "secondary": [sd, ...]}, layers_info)`` where ``layers_info`` has
     the reference's ``N_LAYERS_START`` / ``N_LAYERS_SECONDARY`` keys (the latter is the first
@@ -154,10 +158,19 @@ def split_parameters(
         if k in model_params:
             starter[k] = model_params.pop(k)
     starter.update(take_layers(*ranges[0]))
+    if head_on not in ("starter", "finisher"):
+        raise ValueError(f"head_on must be 'starter' or 'finisher', got {head_on!r}")
+    head: Dict[str, Any] = {}
     for k in ("transformer.ln_f.weight", "transformer.ln_f.bias", "lm_head.weight", "lm_head.bias"):
         if k in model_params:
-            starter[k] = model_params.pop(k)
+            head[k] = model_params.pop(k)
     secondary = [take_layers(lo, hi) for lo, hi in ranges[1:]]
+    if head_on == "starter":
+        starter.update(head)
+    else:
+        if "lm_head.weight" not in head and "transformer.wte.weight" in starter:  # tied embeddings
+            head["lm_head.weight"] = starter["transformer.wte.weight"].clone()
+        secondary[-1].update(head)
     info = {"N_LAYERS_START": plan[0], "N_LAYERS_SECONDARY": plan[1], "plan": list(plan)}
     return {"starter": starter, "secondary": secondary}, info
 
@@ -184,7 +197,8 @@ def split_and_store(
 ) -> Path:
     """Split a state dict and write the chunk files; returns the chunk directory."""
     verb = bool(kwargs.get("verb", False))
-    chunks, info = split_parameters(model_params, n_nodes, plan=plan, config=config)
+    chunks, info = split_parameters(model_params, n_nodes, plan=plan, config=config,
+                                    head_on=kwargs.get("head_on", "starter"))
     if len(model_params):
         warnings.warn(f"{len(model_params)} elements have not been used")
     del model_params

@@ -21,7 +21,7 @@ import torch.nn as nn
 from .config import Config
 from .gpt import Block, KVPool, RopeMixin, build_norm, run_blocks
 
-__all__ = ["StageModule", "StarterNode", "SecondaryNode", "build_stage"]
+__all__ = ["StageModule", "StarterNode", "SecondaryNode", "FinisherNode", "build_stage"]
 
 
 class StageModule(nn.Module, RopeMixin):
@@ -88,19 +88,24 @@ class StageModule(nn.Module, RopeMixin):
 class StarterNode(StageModule):
     role = "starter"
 
-    def __init__(self, config: Config, n_transf_layers: int, **kwargs: Any) -> None:
+    def __init__(self, config: Config, n_transf_layers: int, *, with_head: bool = True, **kwargs: Any) -> None:
+        """``with_head=False`` builds the first-generation starter (old/nanoGPT/sub/model_dist.py:90-144):
+        embeddings + blocks only, the output head lives on a :class:`FinisherNode`."""
         super().__init__(config, n_transf_layers, **kwargs)
+        self.with_head = bool(with_head)
         parts = dict(
             wte=nn.Embedding(config.padded_vocab_size, config.n_embd),
             h=nn.ModuleList(Block(config) for _ in range(n_transf_layers)),
-            ln_f=build_norm(config),
         )
+        if self.with_head:
+            parts["ln_f"] = build_norm(config)
         if config.pos_embedding == "learned":
             parts["wpe"] = nn.Embedding(config.block_size, config.n_embd)
         self.transformer = nn.ModuleDict(parts)
-        self.lm_head = nn.Linear(config.n_embd, config.padded_vocab_size, bias=config.lm_head_bias)
-        if config.tie_embeddings:
-            self.lm_head.weight = self.transformer.wte.weight
+        if self.with_head:
+            self.lm_head = nn.Linear(config.n_embd, config.padded_vocab_size, bias=config.lm_head_bias)
+            if config.tie_embeddings:
+                self.lm_head.weight = self.transformer.wte.weight
         self.max_seq_length = config.block_size
 
     def embed(self, idx: torch.Tensor, input_pos: Optional[torch.Tensor]) -> torch.Tensor:
@@ -115,6 +120,8 @@ class StarterNode(StageModule):
     def head(self, x: torch.Tensor) -> torch.Tensor:
         """``ln_f`` + ``lm_head``; only the last row is needed for sampling, so callers may pass
         ``x[:, -1:]`` (the reference computes all T rows, submodels.py:219-220)."""
+        if not self.with_head:
+            raise RuntimeError("this starter has no output head (finisher topology)")
         return self.lm_head(self.transformer.ln_f(x))
 
     def forward(
@@ -147,10 +154,30 @@ class SecondaryNode(StageModule):
         return self._blocks(x, input_pos, slot)
 
 
+class FinisherNode(StageModule):
+    """Last node of the first-generation open chain: its blocks, then ``ln_f`` + ``lm_head``; returns
+    the logits of the last position, which travel back to the starter for sampling
+    (old/nanoGPT/sub/model_dist.py:181-221; the ring generation moved the head to the starter)."""
+
+    role = "finisher"
+
+    def __init__(self, config: Config, n_transf_layers: int, **kwargs: Any) -> None:
+        super().__init__(config, n_transf_layers, **kwargs)
+        self.transformer = nn.ModuleDict(dict(
+            h=nn.ModuleList(Block(config) for _ in range(n_transf_layers)), ln_f=build_norm(config)))
+        self.lm_head = nn.Linear(config.n_embd, config.padded_vocab_size, bias=config.lm_head_bias)
+        self.max_seq_length = config.block_size
+
+    def forward(self, x: torch.Tensor, input_pos: Optional[torch.Tensor] = None, *, slot: int = 0) -> torch.Tensor:
+        x = self._blocks(x, input_pos, slot)
+        return self.lm_head(self.transformer.ln_f(x[:, -1:]))
+
+
 def build_stage(config: Config, role: str, n_layers: int, *, meta: bool = False, **kw: Any) -> StageModule:
-    """Instantiate the stage for ``role`` ("starter" | "secondary[:i]"), optionally on the
-    meta device so that loading a chunk does not double the memory (gptserver.py:657-664)."""
-    cls = StarterNode if role.startswith("starter") else SecondaryNode
+    """Instantiate the stage for ``role`` ("starter" | "secondary[:i]" | "intermediate[:i]" | "finisher"),
+    optionally on the meta device so that loading a chunk does not double the memory
+    (gptserver.py:657-664)."""
+    cls = StarterNode if role.startswith("starter") else FinisherNode if role.startswith("finisher") else SecondaryNode
     if meta:
         with torch.device("meta"):
             return cls(config, n_layers, **kw)

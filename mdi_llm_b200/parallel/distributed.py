@@ -57,6 +57,7 @@ class GPTDistributed:
         self.dtype = dtype
         self.partition_policy = kwargs.pop("partition", "auto")
         self.push_chunks = bool(kwargs.pop("push_chunks", False))
+        self.head_on: str = kwargs.get("head_on", "starter")
         self.full_model_name = self.ckpt_dir.name if self.ckpt_dir else None
         self.node_type = node_type
         if isinstance(config_file, dict):
@@ -87,7 +88,7 @@ class GPTDistributed:
                 self.plan = plan_layers(self.n_nodes, self.model_config.n_layer, self.model_config,
                                         policy=self.partition_policy)
                 node_chunks_dir = split_and_store(full_model, self.n_nodes, self.ckpt_dir, plan=self.plan,
-                                                  config=self.model_config, verb=self.verb)
+                                                  config=self.model_config, verb=self.verb, head_on=self.head_on)
                 self.model_was_split = not self.push_chunks
             else:
                 self.model_config, _ = load_from_pt(self.ckpt_dir, config_only=True)
@@ -205,6 +206,7 @@ class GPTDistributed:
                 n_local_layers=counts[i], n_samples=n_samples, prev_node=ring[i],
                 next_node=ring[(i + 2) % len(ring)], max_seq_length=self.model_seq_length,
                 sampling=dict(temperature=s.temperature, top_k=s.top_k, top_p=s.top_p, seed=s.seed),
+                use_kv_cache=self.gpt_serv.use_kv_cache, head_on=self.head_on,
             )
             if not self.model_was_split:
                 msg["params"] = torch.load(self.node_chunks_dir / f"model_secondary{i}.pth",

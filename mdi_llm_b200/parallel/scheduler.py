@@ -16,6 +16,14 @@ sample; a finished sample emits a ``stop`` marker that travels the ring and the 
 when the first marker returns (gptserver.py:919-921, 985-994); secondaries create per-sample
 state lazily on first sight (:1083-1088).
 
+Two earlier generations of the protocol are kept as options:
+
+* ``use_kv_cache=False`` — the GPT-2 generation: no KV caches, every message carries the whole
+  growing context ``(1,T,C)`` cropped to ``block_size`` (old/GPT2/sub/model_dist.py:959-972);
+* ``head_remote=True`` — the nanoGPT generation's starter / intermediate / finisher chain: the last
+  node owns ``ln_f`` + ``lm_head`` and returns logits to the starter, which only samples
+  (old/nanoGPT/sub/model_dist.py:90-221).
+
 The device-driven form of the same schedule (static round-robin order, no host in the loop,
 fused P2P hops) lives in ``engine.py``; both produce identical tokens under greedy sampling.
 """
@@ -58,8 +66,9 @@ class StageRunner:
     def begin_sample(self, sample_id: int) -> None:  # allocate per-sample state (KV slot)
         raise NotImplementedError
 
-    def forward(self, sample_id: int, data: torch.Tensor, input_pos: torch.Tensor) -> torch.Tensor:
-        """starter: ``data`` = token ids ``[1,T]``; secondary: hidden state ``[1,T,C]``."""
+    def forward(self, sample_id: int, data: torch.Tensor, input_pos: Optional[torch.Tensor]) -> torch.Tensor:
+        """starter: ``data`` = token ids ``[1,T]``; secondary: hidden state ``[1,T,C]``.
+        ``input_pos=None`` = cache-less causal forward over the whole of ``data``."""
         raise NotImplementedError
 
     def head(self, hidden: torch.Tensor) -> torch.Tensor:
@@ -88,8 +97,8 @@ class EagerStageRunner(StageRunner):
         self.model.ensure_slots(max(self._hint, len(self.slots)))
 
     @torch.inference_mode()
-    def forward(self, sample_id: int, data: torch.Tensor, input_pos: torch.Tensor) -> torch.Tensor:
-        slot = self.slots[sample_id]
+    def forward(self, sample_id: int, data: torch.Tensor, input_pos: Optional[torch.Tensor]) -> torch.Tensor:
+        slot = self.slots.get(sample_id, 0) if input_pos is None else self.slots[sample_id]
         if self.role == "starter":
             return self.model(data.long(), input_pos, slot=slot)
         return self.model(data.to(self.dtype), input_pos, slot=slot)
@@ -121,6 +130,9 @@ def starter_loop(
     on_token: Optional[Callable[[int, int], None]] = None,
     recv_timeout: float = 2.0,
     watchdog_s: Optional[float] = None,
+    use_kv_cache: bool = True,
+    head_remote: bool = False,
+    block_size: Optional[int] = None,
 ) -> GenerationResult:
     """Generation loop of node 0.  ``prompts[i]`` is a 1-D tensor of token ids."""
     n_samples = len(prompts)
@@ -159,7 +171,7 @@ def starter_loop(
         sid = msg["sample_index"]
         data = runner.to_device(msg["data"])
         if iter_ind[sid] >= 1:
-            logits = runner.head(data)
+            logits = data if head_remote else runner.head(data)
             nxt = sample_logits(logits.float().cpu() if gen is not None else logits.float(),
                                 temperature=sampling.temperature, top_k=sampling.top_k,
                                 top_p=sampling.top_p, generator=gen)
@@ -173,12 +185,17 @@ def starter_loop(
                 on_token(sid, int(nxt))
         else:
             samples[sid] = data.view(1, -1)
-            runner.begin_sample(sid)
+            if use_kv_cache:
+                runner.begin_sample(sid)
             input_pos[sid] = torch.arange(0, prompt_len[sid], device=runner.device)
 
         if iter_ind[sid] < max_new_tokens:
-            idx_cond = samples[sid] if iter_ind[sid] == 0 else samples[sid][:, -1:]
-            out = build_msg(runner.forward(sid, idx_cond, input_pos[sid]), sid)
+            if use_kv_cache:
+                idx_cond = samples[sid] if iter_ind[sid] == 0 else samples[sid][:, -1:]
+                out = build_msg(runner.forward(sid, idx_cond, input_pos[sid]), sid)
+            else:  # whole context again, cropped to the model's window
+                idx_cond = samples[sid] if block_size is None else samples[sid][:, -block_size:]
+                out = build_msg(runner.forward(sid, idx_cond, None), sid)
         else:
             out = build_msg("", sid, stop=True)
         iter_ind[sid] += 1
@@ -196,6 +213,7 @@ def secondary_loop(
     running: threading.Event,
     n_samples: Optional[int] = None,
     recv_timeout: float = 2.0,
+    use_kv_cache: bool = True,
 ) -> int:
     """Worker loop of nodes 1..N-1: forward every hidden state, relay stop markers.  Returns the
     number of forwards executed.  Ends when ``running`` is cleared (PUT /stop)."""
@@ -210,6 +228,10 @@ def secondary_loop(
             transport.send(msg)
             continue
         data = runner.to_device(msg["data"])
+        if not use_kv_cache:
+            transport.send(build_msg(runner.forward(sid, data, None), sid))
+            n_fwd += 1
+            continue
         if sid not in input_pos:
             if n_samples is not None and n_fwd >= n_samples:
                 raise AssertionError("Should have seen this sample already...")

@@ -80,6 +80,9 @@ class GPTServer:
         self.chaos = kwargs.get("chaos")
         self.watchdog_s: Optional[float] = kwargs.get("watchdog_s")
         self.start_http = bool(kwargs.get("start_http", True))
+        # earlier protocol generations: cache-less context re-send; head on the last node
+        self.use_kv_cache = bool(kwargs.get("use_kv_cache", True))
+        self.head_on: str = kwargs.get("head_on", "starter")
         self.requested_dtype = dtype
 
         # --- per-instance run-time state ----------------------------------------------------
@@ -193,7 +196,13 @@ class GPTServer:
         assert self.model is None, "The model was already initialized!"
         if not (model_path or model_parameters):
             raise ValueError("At least one between model_path and model_parameters must be nonempty")
-        model = build_stage(self.model_config, self.node_type, n_transf_layers, meta=True, verb=self.verb)
+        role, extra = self.node_type, {}
+        if self.head_on == "finisher" and (self.n_nodes or 1) > 1:
+            if "starter" in role:
+                extra["with_head"] = False
+            elif int(role.split(":")[1]) == self.n_nodes - 2:
+                role = "finisher"
+        model = build_stage(self.model_config, role, n_transf_layers, meta=True, verb=self.verb, **extra)
         sd = lazy_load(model_path) if model_path else model_parameters
         assert sd is not None
         wanted = {k for k, _ in model.named_parameters()}
@@ -213,7 +222,8 @@ class GPTServer:
 
     def _make_runner(self, model: StageModule) -> StageRunner:
         kind = self.engine_kind
-        if kind in ("auto", "cuda") and self.torch_model_device.type == "cuda":
+        legacy = not self.use_kv_cache or (self.head_on == "finisher" and (self.n_nodes or 1) > 1)
+        if kind in ("auto", "cuda") and self.torch_model_device.type == "cuda" and not legacy:
             try:
                 from .engine import FusedStageRunner, engine_supports
 
@@ -319,7 +329,7 @@ class GPTServer:
         S = self.model.max_seq_length
         if "max_new_tokens" in kwargs and kwargs["max_new_tokens"] is not None:
             max_new = int(kwargs["max_new_tokens"])
-            if any(max_new + p.numel() > S for p in idx):
+            if self.use_kv_cache and any(max_new + p.numel() > S for p in idx):  # cache-less mode crops
                 raise ValueError(f"Cannot generate {max_new} tokens - would exceed block size!")
         else:
             max_new = S - max(p.numel() for p in idx)
@@ -331,7 +341,9 @@ class GPTServer:
             spinner.start()
         with catch_loop_errors(running_event=self.running, event_to_be_set=[spinner_stop]):
             res = starter_loop(self.runner, self.transport, idx, max_new, self.sampling, self.running,
-                               n_nodes=self.n_nodes or 1, record_times=True, watchdog_s=self.watchdog_s)
+                               n_nodes=self.n_nodes or 1, record_times=True, watchdog_s=self.watchdog_s,
+                               use_kv_cache=self.use_kv_cache, block_size=self.model.max_seq_length,
+                               head_remote=self.head_on == "finisher" and (self.n_nodes or 1) > 1)
         self.running.clear()
         self.last_result = res
         self.tok_time = res.tok_time
@@ -343,7 +355,8 @@ class GPTServer:
     def _secondary_loop(self) -> None:
         assert self.runner is not None and self.transport is not None
         with catch_loop_errors(running_event=self.running):
-            secondary_loop(self.runner, self.transport, self.running, n_samples=self.n_samples)
+            secondary_loop(self.runner, self.transport, self.running, n_samples=self.n_samples,
+                           use_kv_cache=self.use_kv_cache)
 
     def stop_generation(self) -> int:
         try:
@@ -394,6 +407,8 @@ class GPTServer:
         self.n_samples = init_msg["n_samples"]
         if init_msg.get("sampling"):
             self.sampling = SamplingParams(**init_msg["sampling"])
+        self.use_kv_cache = bool(init_msg.get("use_kv_cache", True))
+        self.head_on = init_msg.get("head_on", "starter")
         params = init_msg.pop("params", None)
         if params is not None:
             self._init_model(self.n_layers_local, model_parameters=params)

@@ -150,3 +150,78 @@ def test_watchdog_fires_when_a_hop_is_dropped(tiny_llama_cfg):
                      n_nodes=2, recv_timeout=0.05, watchdog_s=0.3)
     assert not running.is_set()
     w.join(timeout=2)
+
+
+# ---- earlier protocol generations ----------------------------------------------------
+def _greedy_ref(cfg, sd, prompts, n_new):
+    m = GPT(cfg)
+    m.load_state_dict(sd, strict=not cfg.tie_embeddings)
+    m.eval()
+    out = []
+    for p in prompts:
+        m.clear_kv_cache()
+        out.append(m.generate(p, len(p) + n_new, temperature=0.0, top_p=0.0).tolist())
+    return out
+
+
+def test_cacheless_context_resend_mode_matches_cached_decode(tiny_gpt2_cfg):
+    """GPT-2 generation protocol: no KV caches, the whole (growing) context travels the ring each step
+    (old/GPT2/sub/model_dist.py:959-972).  Same tokens as cached decode while the context fits."""
+    sd, runners, ts = _inproc_ring(tiny_gpt2_cfg, 2)
+    running = threading.Event()
+    running.set()
+    w = threading.Thread(target=secondary_loop, args=(runners[1], ts[1], running),
+                         kwargs={"recv_timeout": 0.05, "use_kv_cache": False}, daemon=True)
+    w.start()
+    prompts = [torch.tensor([1, 2, 3]), torch.tensor([4, 5])]
+    res = starter_loop(runners[0], ts[0], prompts, 6, SamplingParams.greedy(), running, n_nodes=2,
+                       use_kv_cache=False, block_size=tiny_gpt2_cfg.block_size)
+    running.clear()
+    w.join(timeout=2)
+    assert runners[0].model.kv_pool is None and runners[1].model.kv_pool is None  # really cache-less
+    assert [res.samples[i].tolist() for i in range(2)] == _greedy_ref(tiny_gpt2_cfg, sd, prompts, 6)
+
+
+def test_cacheless_mode_crops_to_block_size(tiny_llama_cfg):
+    sd, runners, ts = _inproc_ring(tiny_llama_cfg, 2)
+    running = threading.Event()
+    running.set()
+    w = threading.Thread(target=secondary_loop, args=(runners[1], ts[1], running),
+                         kwargs={"recv_timeout": 0.05, "use_kv_cache": False}, daemon=True)
+    w.start()
+    res = starter_loop(runners[0], ts[0], [torch.tensor([1, 2, 3, 4, 5, 6])], 5, SamplingParams.greedy(), running,
+                       n_nodes=2, use_kv_cache=False, block_size=8)
+    running.clear()
+    w.join(timeout=2)
+    assert res.samples[0].size(1) == 11  # longer than the 8-token window: the context slid
+
+
+@pytest.mark.parametrize("n_nodes", [2, 3])
+def test_finisher_topology_token_exact(tmp_path, topology, tiny_llama_cfg, n_nodes):
+    """First-generation chain starter -> intermediate -> finisher: the last node owns ln_f + lm_head
+    and returns logits (old/nanoGPT/sub/model_dist.py:90-221)."""
+    ck = write_random_checkpoint(tmp_path / "custom" / "tiny-fin", tiny_llama_cfg, dtype=torch.float32)
+    topo = topology(n_nodes)
+    prompts = [torch.tensor([256, 10 + i, 20]) for i in range(n_nodes)]
+    secs = [GPTDistributed(f"secondary:{i}", topo, ckpt_dir=ck, dtype="float32") for i in range(n_nodes - 1)]
+    st = GPTDistributed("starter", topo, ckpt_dir=ck, dtype="float32", sampling=SamplingParams.greedy(),
+                        head_on="finisher")
+    st.start(n_samples=len(prompts), tokens_per_sample=6, prompt=prompts, quiet=True)
+    for s in secs:
+        s.gpt_serv.shutdown()
+    assert not hasattr(st.gpt_serv.model, "lm_head")
+    assert secs[-1].gpt_serv.model.role == "finisher"
+    assert [st.gpt_serv.last_result.samples[i].tolist() for i in range(len(prompts))] == _reference_tokens(ck, prompts, 6)
+
+
+def test_cacheless_mode_through_gptdistributed(tmp_path, topology, tiny_gpt2_cfg):
+    ck = write_random_checkpoint(tmp_path / "custom" / "tiny-gpt2-nc", tiny_gpt2_cfg, dtype=torch.float32)
+    topo = topology(2)
+    prompts = [torch.tensor([256, 3, 4]), torch.tensor([256, 9])]
+    sec = GPTDistributed("secondary:0", topo, ckpt_dir=ck, dtype="float32")
+    st = GPTDistributed("starter", topo, ckpt_dir=ck, dtype="float32", sampling=SamplingParams.greedy(),
+                        use_kv_cache=False)
+    st.start(n_samples=2, tokens_per_sample=5, prompt=prompts, quiet=True)
+    sec.gpt_serv.shutdown()
+    assert sec.gpt_serv.use_kv_cache is False
+    assert [st.gpt_serv.last_result.samples[i].tolist() for i in range(2)] == _reference_tokens(ck, prompts, 5)
