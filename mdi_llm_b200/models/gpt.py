@@ -27,7 +27,7 @@ import torch.nn.functional as F
 from .config import Config
 
 __all__ = [
-    "GPT", "Block", "CausalSelfAttention", "RMSNorm", "KVPool", "build_rope_cache",
+    "GPT", "Block", "CausalSelfAttention", "RMSNorm", "KVPool", "build_rope_cache", "build_mask_cache",
     "apply_rope", "sample", "sample_top_p", "build_norm", "build_mlp", "LLaMAMLP",
     "GptNeoxMLP", "GemmaMLP", "LLaMAMoE",
 ]
@@ -124,6 +124,14 @@ def build_rope_cache(
     ang = torch.outer(pos, inv_freq)
     ang = torch.cat((ang, ang), dim=-1)
     return torch.cos(ang), torch.sin(ang)
+
+
+def build_mask_cache(max_seq_length: int, device: Optional[torch.device] = None) -> torch.Tensor:
+    """Lower-triangular boolean mask ``[1,1,S,S]`` (reference model.py:940-947).  The reference
+    indexes rows of it by ``input_pos`` on every decode step and so always attends over all ``S``
+    cache slots; this framework masks by the live length instead and keeps the helper for parity."""
+    ones = torch.ones((max_seq_length, max_seq_length), device=device, dtype=torch.bool)
+    return torch.tril(ones).unsqueeze(0).unsqueeze(0)
 
 
 def apply_rope(x: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor) -> torch.Tensor:

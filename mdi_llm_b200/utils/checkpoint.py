@@ -26,7 +26,7 @@ import torch.nn as nn
 from ..models.config import Config
 
 __all__ = [
-    "load_sd", "load_from_pt", "save_config", "init_from_state_dict", "get_keys_to_submodule",
+    "load_sd", "load_from_pt", "load_from_hf", "save_config", "init_from_state_dict", "get_keys_to_submodule",
     "lazy_load", "incremental_save", "IncrementalSaver", "write_random_checkpoint",
     "random_state_dict", "materialize_stage",
 ]
@@ -65,6 +65,24 @@ def load_from_pt(
     if config_only:
         return config, None
     return config, load_sd(model_dir / "lit_model.pth", device)
+
+
+def load_from_hf(
+    repo_id: str,
+    access_token: Optional[str] = None,
+    dtype: Optional[str] = None,
+    checkpoint_dir: PathLike = Path("checkpoints"),
+    model_name: Optional[str] = None,
+    device: Optional[Union[torch.device, str]] = "cpu",
+    config_only: bool = False,
+) -> Tuple[Config, Optional[Dict[str, Any]]]:
+    """Download ``repo_id`` from the HF hub into ``checkpoint_dir/repo_id``, convert it to the
+    litGPT layout and load it (reference utils.py:565-605).  Needs network + ``huggingface_hub``."""
+    from .download import download_from_hub
+
+    download_from_hub(repo_id=repo_id, access_token=access_token, dtype=dtype,
+                      checkpoint_dir=Path(checkpoint_dir), model_name=model_name)
+    return load_from_pt(Path(checkpoint_dir) / repo_id, device, config_only=config_only)
 
 
 def save_config(config: Config, checkpoint_dir: PathLike) -> None:
