@@ -50,6 +50,8 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.mdi_sample_fast.argtypes = [vp, vp, vp, i64, vp, vp, i32, i32, f32, i32, c_ulonglong, i32, vp]
     lib.mdi_sample_scratch_bytes.restype = c_size_t
     lib.mdi_gemm_bf16.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp]
+    lib.mdi_gemm_bf16_ex.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp,
+                                     i32, i32, i32, i32, vp]
     lib.mdi_advance_step.argtypes = [vp, vp, vp, i32, i32, i32, vp]
     lib.mdi_wait_flag.argtypes = [vp, vp, vp, i64, vp]
     lib.mdi_set_flag.argtypes = [vp, vp, vp]
@@ -238,18 +240,32 @@ def sample(logits: torch.Tensor, tokens: torch.Tensor, ctx: torch.Tensor, *, voc
 
 
 def gemm(a: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
-         out: Optional[torch.Tensor] = None, block_n: int = 128, _knobs: Tuple[int, int, int, int] = (0, 0, 0, 0)) -> torch.Tensor:
+         out: Optional[torch.Tensor] = None, block_n: int = 128, w2: Optional[torch.Tensor] = None,
+         bias2: Optional[torch.Tensor] = None, act: str = "silu_gate", out_ptr: Optional[int] = None,
+         signal_flag: Optional[int] = None, done_ctr: Optional[torch.Tensor] = None, ctx: Optional[torch.Tensor] = None,
+         _knobs: Tuple[int, int, int, int] = (0, 0, 0, 0)) -> Optional[torch.Tensor]:
     """``a [M, K] @ w [N, K]^T (+bias) (+residual)`` on the tcgen05 tensor cores (TMA-fed, TMEM
-    accumulator) — the prefill GEMM.  bf16 in/out, fp32 accumulate."""
-    _bf16(a, "a"); _bf16(w, "w"); _bf16(bias, "bias"); _bf16(residual, "residual")
+    accumulator) — the prefill GEMM.  bf16 in/out, fp32 accumulate.
+
+    * ``w2``: gated MLP in one pass — ``act(a w^T + bias) * (a w2^T + bias2)``, two TMEM accumulators
+      sharing the A tile.
+    * ``out_ptr`` (raw device address, may be a peer mapping) + ``signal_flag``/``done_ctr``/``ctx``:
+      the fused prefill hop — the epilogue stores straight into the next stage's input buffer and the
+      last CTA releases ``flag[ctx.slot] = ctx.signal`` at system scope.  Returns None."""
+    _bf16(a, "a"); _bf16(w, "w"); _bf16(bias, "bias"); _bf16(residual, "residual"); _bf16(w2, "w2"); _bf16(bias2, "bias2")
     M, K = a.shape
     N = w.shape[0]
-    if w.shape[1] != K:
-        raise OpsError(f"gemm: inner dimensions differ ({K} vs {w.shape[1]})")
-    if out is None:
-        out = torch.empty(M, N, device=a.device, dtype=torch.bfloat16)
-    check(lib().mdi_gemm_bf16(ptr(a), ptr(w), ptr(out), ptr(bias), ptr(residual), M, N, K, block_n, *_knobs, stream_ptr()),
-          "gemm_bf16 (tcgen05)")
+    if w.shape[1] != K or (w2 is not None and tuple(w2.shape) != tuple(w.shape)):
+        raise OpsError(f"gemm: operand shapes differ ({tuple(a.shape)} x {tuple(w.shape)})")
+    if out_ptr is None:
+        if out is None:
+            out = torch.empty(M, N, device=a.device, dtype=torch.bfloat16)
+        c_ptr = ptr(out)
+    else:
+        c_ptr, out = out_ptr, None
+    check(lib().mdi_gemm_bf16_ex(ptr(a), ptr(w), ptr(w2), c_ptr, ptr(bias), ptr(bias2), ptr(residual), M, N, K,
+                                 ACT[act] if w2 is not None else 0, block_n, signal_flag, ptr(done_ctr), ptr(ctx),
+                                 *_knobs, stream_ptr()), "gemm_bf16 (tcgen05)")
     return out
 
 

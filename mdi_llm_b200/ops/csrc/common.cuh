@@ -143,9 +143,31 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint3
                ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+// ---- activations (shared by the decode linears and the tcgen05 GEMM epilogue) ---------------------------
+__device__ __forceinline__ float gelu_tanh(float x) {
+  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+  return 0.5f * x * (1.f + tanhf(k0 * (x + k1 * x * x * x)));
+}
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float silu(float x) { return x / (1.f + __expf(-x)); }
+
+enum Act { ACT_NONE = 0, ACT_SILU_GATE = 1, ACT_GELU_TANH_GATE = 2, ACT_GELU_ERF_GATE = 3, ACT_GELU_TANH = 4, ACT_GELU_ERF = 5 };
+
+// gate activation of a gated MLP (ACT_*_GATE)
+__device__ __forceinline__ float apply_act(float x, int act) {
+  if (act == ACT_SILU_GATE) return silu(x);
+  if (act == ACT_GELU_TANH_GATE) return gelu_tanh(x);
+  return gelu_erf(x);
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
 // ---- device-side tracer ---------------------------------------------------------------------------
-// Each traced kernel owns one record of 6 x u64 (ns, %globaltimer):
+// Each traced kernel owns one record of 8 x u64 (ns, %globaltimer):
 //   [0] min entry  [1] min "input ready" (after PDL/hop wait)  [2] max "staged"  [3] min exit  [4] max exit  [5] #CTAs
+//   [6] optional device pointer to a per-CTA table (8 x u64 per CTA: the five marks, [5] = SM id)  [7] its capacity (CTAs)
 // Recording is per CTA (thread 0), costs a handful of atomics and is off when `rec == nullptr`.
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
   unsigned long long t;
@@ -157,6 +179,16 @@ __device__ __forceinline__ void trace_mark(unsigned long long* rec, int field, b
   const unsigned long long t = globaltimer_ns();
   if (is_min) atomicMin(rec + field, t); else atomicMax(rec + field, t);
   if (field == 4) atomicAdd(rec + 5, 1ull);
+  unsigned long long* detail = reinterpret_cast<unsigned long long*>(rec[6]);
+  if (detail != nullptr && blockIdx.x + gridDim.x * blockIdx.y < rec[7]) {
+    unsigned long long* d = detail + (size_t)(blockIdx.x + gridDim.x * blockIdx.y) * 8;
+    d[field] = t;
+    if (field == 0) {
+      unsigned int smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      d[5] = smid;
+    }
+  }
 }
 
 // Programmatic dependent launch: let the next kernel's prologue overlap our tail, and wait for

@@ -178,15 +178,6 @@ __device__ __forceinline__ void stage_input(const bf16* __restrict__ x, const bf
   __syncthreads();
 }
 
-__device__ __forceinline__ float gelu_tanh(float x) {
-  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
-  return 0.5f * x * (1.f + tanhf(k0 * (x + k1 * x * x * x)));
-}
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
-__device__ __forceinline__ float silu(float x) { return x / (1.f + __expf(-x)); }
-
-enum Act { ACT_NONE = 0, ACT_SILU_GATE = 1, ACT_GELU_TANH_GATE = 2, ACT_GELU_ERF_GATE = 3, ACT_GELU_TANH = 4, ACT_GELU_ERF = 5 };
-
 // One argument block for every weight-streaming decode linear (plain / gated / QKV).
 struct StreamArgs {
   const bf16* W;         // [N, K]   (QKV: [(H + 2G) * hs, K], litGPT group-interleaved rows)

@@ -33,10 +33,17 @@ constexpr int UMMA_K = 16;
 struct GemmParams {
   CUtensorMap tma_a;
   CUtensorMap tma_b;
-  bf16* C;
+  CUtensorMap tma_b2;         // gated mode: second weight matrix (same shape as B)
+  bf16* C;                     // may be peer-mapped memory: the epilogue's stores ARE the prefill hop
   const bf16* bias;
+  const bf16* bias2;
   const bf16* residual;
   int M, N, K;
+  int act;                     // gated mode (ACT_*): C = act(A W^T + bias) * (A W2^T + bias2)
+  // fused hop: after its stores every CTA takes a ticket; the last one publishes flag[slot] = signal
+  // (values from ctx, like the decode kernels) with a system-scope release.
+  HopSignal signal;
+  const int* ctx;
   // descriptor knobs (kept as parameters so a bring-up test can sweep them; defaults are the
   // canonical K-major SWIZZLE_128B encoding)
   unsigned int desc_sbo;      // stride-byte-offset >> 4 (8 rows x 128 B = 1024 B -> 64)
@@ -89,11 +96,14 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, const Gem
   return d;
 }
 
-template <int BLOCK_N>
+// GATED: two B operands share the A tile; accumulators live side by side in TMEM (columns [0,BLOCK_N)
+// and [BLOCK_N, 2*BLOCK_N)) and the epilogue writes act(acc0) * acc1 — SwiGLU / GeGLU in one pass.
+template <int BLOCK_N, bool GATED>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(const __grid_constant__ GemmParams p) {
   extern __shared__ __align__(1024) unsigned char gemm_smem[];
   constexpr int A_BYTES = GEMM_BLOCK_M * GEMM_BLOCK_K * 2;
-  constexpr int B_BYTES = BLOCK_N * GEMM_BLOCK_K * 2;
+  constexpr int B_BYTES = (GATED ? 2 : 1) * BLOCK_N * GEMM_BLOCK_K * 2;
+  constexpr int TMEM_COLS = (GATED ? 2 : 1) * BLOCK_N;
   // carve: [A stages][B stages][barriers][tmem ptr]
   unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(gemm_smem) + 1023) & ~uintptr_t(1023));
   unsigned char* smem_a = base;
@@ -110,14 +120,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tma_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tma_b) : "memory");
+    if (GATED) asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tma_b2) : "memory");
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < GEMM_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     mbar_init(tmem_full_bar, 1);
     mbar_fence_init();
   }
-  if (warp == 2) {  // whole warp: allocate BLOCK_N TMEM columns (power of two >= 32)
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "n"(BLOCK_N) : "memory");
+  if (warp == 2) {  // whole warp: allocate the accumulator's TMEM columns (power of two >= 32)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "n"(TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tcgen05_fence_before();
@@ -135,6 +146,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
         mbar_expect_tx(&full_bar[s], A_BYTES + B_BYTES);
         tma_load_2d(smem_a + s * A_BYTES, &p.tma_a, &full_bar[s], kb * GEMM_BLOCK_K, m0);
         tma_load_2d(smem_b + s * B_BYTES, &p.tma_b, &full_bar[s], kb * GEMM_BLOCK_K, n0);
+        if (GATED) tma_load_2d(smem_b + s * B_BYTES + B_BYTES / 2, &p.tma_b2, &full_bar[s], kb * GEMM_BLOCK_K, n0);
       }
     }
   } else if (warp == 1) {
@@ -153,6 +165,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
           const uint64_t da = make_smem_desc(a_addr + k * p.k_step_bytes, p);
           const uint64_t db = make_smem_desc(b_addr + k * p.k_step_bytes, p);
           tcgen05_mma_f16(tmem_base, da, db, idesc, (kb | k) ? 1u : 0u);
+          if (GATED) {
+            const uint64_t db2 = make_smem_desc(b_addr + B_BYTES / 2 + k * p.k_step_bytes, p);
+            tcgen05_mma_f16(tmem_base + BLOCK_N, da, db2, idesc, (kb | k) ? 1u : 0u);
+          }
         }
         tcgen05_commit(&empty_bar[s]);                       // stage reusable once these MMAs retire
         if (kb == num_k_blocks - 1) tcgen05_commit(tmem_full_bar);  // accumulator complete
@@ -165,27 +181,61 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
     mbar_wait(tmem_full_bar, 0);
     tcgen05_fence_after();
     const int row = m0 + ew * 32 + lane;
+    const bool vec_ok = (p.N % 8 == 0);
 #pragma unroll 1
     for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
       uint32_t acc[32];
       tmem_ld_32x32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)c0, acc);
-      if (row < p.M) {
-        const int col0 = n0 + c0;
+      const int col0 = n0 + c0;
+      if (GATED) {
+        uint32_t acc2[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(BLOCK_N + c0), acc2);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float g = __uint_as_float(acc[j]), u = __uint_as_float(acc2[j]);
+          if (col0 + j < p.N) {
+            if (p.bias) g += __bfloat162float(p.bias[col0 + j]);
+            if (p.bias2) u += __bfloat162float(p.bias2[col0 + j]);
+          }
+          // eager semantics: both projections are rounded to bf16 before the activation and the product
+          g = round_bf16(g); u = round_bf16(u);
+          acc[j] = __float_as_uint(round_bf16(apply_act(g, p.act)) * u);
+        }
+      }
+      if (row < p.M && col0 < p.N) {
         bf16* crow = p.C + (size_t)row * p.N + col0;
         const bf16* rrow = p.residual ? p.residual + (size_t)row * p.N + col0 : nullptr;
+        if (vec_ok && col0 + 32 <= p.N) {
+          // 4 x 16-byte stores per thread (64 contiguous bytes of one output row): full sectors on the
+          // wire when C is peer memory
 #pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-          if (col0 + j >= p.N) break;
-          float v0 = __uint_as_float(acc[j]), v1 = __uint_as_float(acc[j + 1]);
-          if (p.bias) { v0 += __bfloat162float(p.bias[col0 + j]); if (col0 + j + 1 < p.N) v1 += __bfloat162float(p.bias[col0 + j + 1]); }
-          if (rrow) {  // eager semantics: linear output rounded to bf16, then added to the bf16 residual
-            v0 = round_bf16(v0) + __bfloat162float(rrow[j]);
-            if (col0 + j + 1 < p.N) v1 = round_bf16(v1) + __bfloat162float(rrow[j + 1]);
+          for (int v = 0; v < 4; ++v) {
+            float f[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              f[j] = __uint_as_float(acc[v * 8 + j]);
+              if (!GATED && p.bias) f[j] += __bfloat162float(p.bias[col0 + v * 8 + j]);
+            }
+            if (rrow) {  // eager semantics: linear output rounded to bf16, then added to the bf16 residual
+              const uint4 r4 = *reinterpret_cast<const uint4*>(rrow + v * 8);
+              const uint32_t rw[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                f[2 * j] = round_bf16(f[2 * j]) + bf16lo(rw[j]);
+                f[2 * j + 1] = round_bf16(f[2 * j + 1]) + bf16hi(rw[j]);
+              }
+            }
+            uint4 o;
+            o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]);
+            o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
+            *reinterpret_cast<uint4*>(crow + v * 8) = o;
           }
-          if (col0 + j + 1 < p.N) {
-            __nv_bfloat162 o = __floats2bfloat162_rn(v0, v1);
-            *reinterpret_cast<__nv_bfloat162*>(crow + j) = o;
-          } else {
+        } else {
+#pragma unroll 1
+          for (int j = 0; j < 32 && col0 + j < p.N; ++j) {
+            float v0 = __uint_as_float(acc[j]);
+            if (!GATED && p.bias) v0 += __bfloat162float(p.bias[col0 + j]);
+            if (rrow) v0 = round_bf16(v0) + __bfloat162float(rrow[j]);
             crow[j] = __float2bfloat16_rn(v0);
           }
         }
@@ -196,8 +246,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
   __syncthreads();
   if (warp == 2) {
     tcgen05_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(BLOCK_N) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
   }
+  hop_signal(p.signal, p.ctx);  // the __syncthreads above ordered every epilogue store before the ticket
 }
 
 // ---- host side ------------------------------------------------------------------------------------
@@ -235,31 +286,50 @@ static int make_map(CUtensorMap* map, const void* ptr, int rows, int cols, int b
 
 using namespace mdi;
 
-// C[M,N] = A[M,K] W[N,K]^T (+bias) (+residual).  K must be a multiple of 8 (16-byte rows for TMA).
+// C[M,N] = A[M,K] W[N,K]^T (+bias) (+residual); with W2: C = act(A W^T + bias) * (A W2^T + bias2).
+// K must be a multiple of 8 (16-byte rows for TMA).  signal_flag != null: fused hop (see GemmParams).
 // knobs: sbo/lbo/hi_bits/k_step <= 0 select the canonical encoding.
-extern "C" int mdi_gemm_bf16(const void* A, const void* W, void* C, const void* bias, const void* residual, int M,
-                             int N, int K, int block_n, int sbo, int lbo, int hi_bits, int k_step,
-                             cudaStream_t stream) {
+extern "C" int mdi_gemm_bf16_ex(const void* A, const void* W, const void* W2, void* C, const void* bias,
+                                const void* bias2, const void* residual, int M, int N, int K, int act, int block_n,
+                                int* signal_flag, unsigned int* done_ctr, const int* ctx, int sbo, int lbo,
+                                int hi_bits, int k_step, cudaStream_t stream) {
   if (K % 8 != 0 || M <= 0 || N <= 0) return -2;
+  if (W2 && residual) return -2;
+  if (signal_flag && (!done_ctr || !ctx)) return -2;
   GemmParams p;
-  p.C = (bf16*)C; p.bias = (const bf16*)bias; p.residual = (const bf16*)residual; p.M = M; p.N = N; p.K = K;
+  p.C = (bf16*)C; p.bias = (const bf16*)bias; p.bias2 = (const bf16*)bias2; p.residual = (const bf16*)residual;
+  p.M = M; p.N = N; p.K = K; p.act = act;
+  p.signal = HopSignal{signal_flag, done_ctr}; p.ctx = ctx;
   p.desc_sbo = sbo > 0 ? (unsigned)sbo : 64u;
   p.desc_lbo = lbo > 0 ? (unsigned)lbo : 1u;
   p.desc_hi_bits = hi_bits > 0 ? (unsigned)hi_bits : (1u | (2u << 15));  // version = 1 (bit 46), SWIZZLE_128B = 2 (bits 61-63)
   p.k_step_bytes = k_step > 0 ? (unsigned)k_step : 32u;
+  const bool gated = W2 != nullptr;
   if (block_n != 64 && block_n != 128 && block_n != 256) block_n = 128;
+  if (gated && block_n == 256) block_n = 128;  // two accumulators: 2 x BLOCK_N <= 512 TMEM columns, smem budget
   int rc = make_map(&p.tma_a, A, M, K, GEMM_BLOCK_M);
   if (rc) return rc;
   rc = make_map(&p.tma_b, W, N, K, block_n);
   if (rc) return rc;
-  const size_t smem = 1024 + (size_t)GEMM_STAGES * (GEMM_BLOCK_M + block_n) * GEMM_BLOCK_K * 2 + 128;
+  rc = make_map(&p.tma_b2, gated ? W2 : W, N, K, block_n);
+  if (rc) return rc;
+  const size_t smem = 1024 + (size_t)GEMM_STAGES * (GEMM_BLOCK_M + (gated ? 2 : 1) * block_n) * GEMM_BLOCK_K * 2 + 128;
   dim3 grid((M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M, (N + block_n - 1) / block_n);
   cudaError_t e;
-#define MDI_GEMM_LAUNCH(BN)                                                                                          \
-  e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
+#define MDI_GEMM_LAUNCH(BN, G)                                                                                        \
+  e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
   if (e != cudaSuccess) return (int)e;                                                                               \
-  gemm_bf16_tcgen05_kernel<BN><<<grid, GEMM_THREADS, smem, stream>>>(p);
-  if (block_n == 64) { MDI_GEMM_LAUNCH(64) } else if (block_n == 256) { MDI_GEMM_LAUNCH(256) } else { MDI_GEMM_LAUNCH(128) }
+  gemm_bf16_tcgen05_kernel<BN, G><<<grid, GEMM_THREADS, smem, stream>>>(p);
+  if (gated) { if (block_n == 64) { MDI_GEMM_LAUNCH(64, true) } else { MDI_GEMM_LAUNCH(128, true) } }
+  else if (block_n == 64) { MDI_GEMM_LAUNCH(64, false) } else if (block_n == 256) { MDI_GEMM_LAUNCH(256, false) }
+  else { MDI_GEMM_LAUNCH(128, false) }
 #undef MDI_GEMM_LAUNCH
   return (int)cudaGetLastError();
+}
+
+extern "C" int mdi_gemm_bf16(const void* A, const void* W, void* C, const void* bias, const void* residual, int M,
+                             int N, int K, int block_n, int sbo, int lbo, int hi_bits, int k_step,
+                             cudaStream_t stream) {
+  return mdi_gemm_bf16_ex(A, W, nullptr, C, bias, nullptr, residual, M, N, K, 0, block_n, nullptr, nullptr, nullptr,
+                          sbo, lbo, hi_bits, k_step, stream);
 }

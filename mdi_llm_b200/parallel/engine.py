@@ -22,7 +22,7 @@ from __future__ import annotations
 
 import math
 from dataclasses import dataclass
-from typing import Any, Dict, List, Optional, Tuple
+from typing import Sequence, Any, Dict, List, Optional, Tuple
 
 import torch
 
@@ -223,29 +223,43 @@ class FusedStage:
         if i >= self._trace.shape[0]:
             return None
         self._trace_names.append(name)
+        det = getattr(self, "_trace_detail", {}).get(name)
+        if det is not None:
+            self._trace[i, 6] = det.data_ptr()
+            self._trace[i, 7] = det.shape[0]
         return self._trace[i].data_ptr()
 
-    def trace_step(self, builder: Any, max_records: int = 512) -> List[Dict[str, Any]]:
+    def trace_step(self, builder: Any, max_records: int = 512, detail: Sequence[str] = (),
+                   detail_ctas: int = 1024) -> List[Dict[str, Any]]:
         """Run ``builder()`` (a sequence of ``enqueue_*`` calls) once with the kernel tracer on and
         return one row per launch: times in µs relative to the first kernel's entry —
         ``entry`` (first CTA starts), ``ready`` (first CTA past the PDL/hop wait), ``staged`` (last CTA
-        has its input in shared memory), ``first_exit`` / ``last_exit`` and the CTA count."""
+        has its input in shared memory), ``first_exit`` / ``last_exit`` and the CTA count.  Kernels named
+        in ``detail`` additionally get a per-CTA table (``row["per_cta"]``: entry, ready, staged, exit in µs
+        and the SM each CTA ran on)."""
         with torch.cuda.device(self.device):
-            self._trace = torch.zeros(max_records, 6, dtype=torch.int64, device=self.device)
+            self._trace = torch.zeros(max_records, 8, dtype=torch.int64, device=self.device)
             self._trace[:, [0, 1, 3]] = torch.iinfo(torch.int64).max
             self._trace_names = []
+            self._trace_detail = {n: torch.zeros(detail_ctas, 8, dtype=torch.int64, device=self.device) for n in detail}
+            self._trace_detail_ctas = detail_ctas
             try:
                 builder()
                 torch.cuda.synchronize(self.device)
                 rec = self._trace[: len(self._trace_names)].cpu()
+                details = {n: t.cpu() for n, t in self._trace_detail.items()}
             finally:
-                names, self._trace, self._trace_names = self._trace_names, None, []
+                names, self._trace, self._trace_names, self._trace_detail = self._trace_names, None, [], {}
         t0 = int(rec[:, 0].min()) if len(names) else 0
         rows = []
         for i, n in enumerate(names):
-            e, r, st_, fx, lx, c = (int(x) for x in rec[i])
+            e, r, st_, fx, lx, c = (int(x) for x in rec[i][:6])
             rows.append({"kernel": n, "entry": (e - t0) / 1e3, "ready": (r - t0) / 1e3, "staged": (st_ - t0) / 1e3 if st_ else None,
                          "first_exit": (fx - t0) / 1e3, "last_exit": (lx - t0) / 1e3, "ctas": c})
+            if n in details:
+                d = details[n][: min(c, details[n].shape[0])]
+                rows[-1]["per_cta"] = [{"cta": j, "sm": int(x[5]), "entry": (int(x[0]) - t0) / 1e3, "ready": (int(x[1]) - t0) / 1e3,
+                                        "staged": (int(x[2]) - t0) / 1e3, "exit": (int(x[4]) - t0) / 1e3} for j, x in enumerate(d)]
         return rows
 
     # ---- kernel sequences ------------------------------------------------------------------------
@@ -320,11 +334,16 @@ class FusedStage:
 
     # ---- prefill (T > 1): linears on the tcgen05 GEMM ------------------------------------------------
     @torch.inference_mode()
-    def prefill(self, data: torch.Tensor, input_pos: torch.Tensor, slot: int) -> torch.Tensor:
+    def prefill(self, data: torch.Tensor, input_pos: torch.Tensor, slot: int,
+                hop: Optional[Tuple[int, int]] = None) -> Optional[torch.Tensor]:
         """All local blocks for a whole prompt.  Every projection (SURVEY K3/K8/K10/K11 at T > 1) runs
-        on the hand-written tcgen05/TMEM/TMA GEMM with its bias/residual epilogue; RMSNorm is the
-        row kernel; RoPE, the KV-slot write and causal attention reuse the eager helper.
-        ``data``: token ids ``[1,T]`` on the starter, hidden state ``[1,T,C]`` on a secondary."""
+        on the hand-written tcgen05/TMEM/TMA GEMM with its bias/residual epilogue (gate and up
+        projections in one dual-accumulator GEMM with the SiLU/GELU·mul epilogue); RMSNorm is the row
+        kernel; RoPE, the KV-slot write and causal attention reuse the eager helper.
+        ``data``: token ids ``[1,T]`` on the starter, hidden state ``[1,T,C]`` on a secondary.
+        ``hop = (dst_ptr, flag_ptr)``: the last down-projection's epilogue stores its ``[T,C]`` output
+        (residual added) straight into the next stage's buffer at ``dst_ptr`` (peer memory) and releases
+        ``flag[ctx.slot] = ctx.signal`` from inside the GEMM — the fused prefill hop; returns None."""
         m, cfg = self.model, self.cfg
         T = data.size(1)
         if self.is_starter:
@@ -333,15 +352,19 @@ class FusedStage:
             x = data[0].to(torch.bfloat16).contiguous()
         cos, sin = m.rope_for(T, input_pos)
         eps, uo = cfg.norm_eps, cfg.unit_offset_norm
+        n_local = len(m.transformer.h)
         for li, blk in enumerate(m.transformer.h):
             h = ops.rmsnorm_rows(x, blk.norm_1.weight, eps, uo)
             qkv = ops.gemm(h, self._dense(blk.attn.attn), bias=blk.attn.attn.bias)
             y = blk.attn.attend_qkv(qkv.unsqueeze(0), cos, sin, input_pos, m.kv_pool.layer(li, slot))[0].contiguous()
             x = ops.gemm(y, self._dense(blk.attn.proj), bias=blk.attn.proj.bias, residual=x)
             h = ops.rmsnorm_rows(x, blk.norm_2.weight, eps, uo)
-            a = ops.gemm(h, self._dense(blk.mlp.fc_1), bias=blk.mlp.fc_1.bias, block_n=256)
-            b = ops.gemm(h, self._dense(blk.mlp.fc_2), bias=blk.mlp.fc_2.bias, block_n=256)
-            g = (blk.mlp.gate(a) * b).contiguous()
+            g = ops.gemm(h, self._dense(blk.mlp.fc_1), bias=blk.mlp.fc_1.bias, w2=self._dense(blk.mlp.fc_2),
+                         bias2=blk.mlp.fc_2.bias, act=self._gate_act())
+            if hop is not None and li == n_local - 1:
+                ops.gemm(g, self._dense(blk.mlp.proj), bias=blk.mlp.proj.bias, residual=x, out_ptr=hop[0],
+                         signal_flag=hop[1], done_ctr=self.done_ctr, ctx=self.ctx)
+                return None
             x = ops.gemm(g, self._dense(blk.mlp.proj), bias=blk.mlp.proj.bias, residual=x)
         return x.unsqueeze(0)
 

@@ -159,8 +159,10 @@ class DevicePipeline:
 
     @torch.inference_mode()
     def prefill(self) -> None:
-        """Round 0: every sample's prompt through all stages (eager blocks; hop = peer copy +
-        flag).  The last stage returns only the final row to the starter."""
+        """Round 0: every sample's prompt through all stages (tcgen05 GEMMs, see ``FusedStage.prefill``).
+        Inter-stage hop: the stage's last down-projection GEMM stores its output tiles straight into
+        the next stage's prefill buffer over NVLink and publishes the flag from its last CTA — no copy
+        kernel, no NCCL.  The last stage returns only the final row to the starter (8 KB copy+signal)."""
         st, lib = self.stage, ops.lib()
         if self.hop == "nccl":
             return self._prefill_nccl()
@@ -169,17 +171,16 @@ class DevicePipeline:
                 T = self.prompt_lens[slot]
                 pos = torch.arange(T, device=self.device)
                 st.set_ctx(slot, T - 1, wait=1, signal=1)
+                hop = None if self.is_last else (self.next_prefill_ptr + slot * self.max_prompt_len * self.C * 2,
+                                                 self.next_hop.flag_ptr)
                 if self.is_starter:
-                    hidden = st.prefill(self.prompts[slot].view(1, -1), pos, slot)
+                    hidden = st.prefill(self.prompts[slot].view(1, -1), pos, slot, hop=hop)
                 else:
                     ops.check(lib.mdi_wait_flag(st.flags.data_ptr(), st.ctx.data_ptr(), st.status.data_ptr(),
                                                 st.wait_max_cycles, ops.stream_ptr()), "wait prefill")
-                    hidden = st.prefill(self.prefill_in[slot, :T].unsqueeze(0), pos, slot)
-                hidden = hidden.to(torch.bfloat16).contiguous()
+                    hidden = st.prefill(self.prefill_in[slot, :T].unsqueeze(0), pos, slot, hop=hop)
                 if self.is_last:  # wrap-around: only the last position feeds lm_head
-                    self._hop_copy(hidden[0, -1], self.next_hop.hidden_ptr + slot * self.C * 2)
-                else:
-                    self._hop_copy(hidden[0], self.next_prefill_ptr + slot * self.max_prompt_len * self.C * 2)
+                    self._hop_copy(hidden[0, -1].to(torch.bfloat16).contiguous(), self.next_hop.hidden_ptr + slot * self.C * 2)
 
     # ---- NCCL-hop baseline ("ours with NCCL send/recv instead of the fused hop") --------------------
     def _edges(self):
