@@ -96,7 +96,8 @@ def parse_args() -> argparse.Namespace:
     ap.add_argument("--seq-len", type=int, default=0, help="KV/context budget (0 = prompt + all rounds)")
     ap.add_argument("--e2e-steps", type=int, default=0, help="rounds of the host-fed e2e measurement (0 = min(steps, 64))")
     ap.add_argument("--n-samples", type=int, default=0, help="concurrent samples (0 = number of GPUs)")
-    ap.add_argument("--partition", default="balanced", choices=["auto", "table", "balanced"])
+    ap.add_argument("--partition", default="balanced", choices=["auto", "table", "balanced", "half"],
+                    help="table: the reference's N_LAYERS_NODES; balanced: whole layers, head-aware; half: attention|MLP half-layer units")
     ap.add_argument("--no-pdl", action="store_true")
     ap.add_argument("--ctas-per-sm", type=int, default=4)
     ap.add_argument("--weights", default="bf16", choices=["bf16", "fp8"],
@@ -153,9 +154,20 @@ def run_ours(args: argparse.Namespace) -> Dict[str, Any]:
     e2e_rounds = args.e2e_steps or min(args.steps, 64)
     rounds_total = args.warmup + args.steps + 1
     seq_len = args.seq_len or min(cfg.block_size, ((args.prompt_len + max(rounds_total, e2e_rounds + 4) + 64) // 64) * 64)
-    plan = plan_layers(world, cfg.n_layer, cfg, policy=args.partition) if world > 1 else [cfg.n_layer]
     role = "starter" if rank == 0 else f"secondary:{rank - 1}"
-    stage = build_stage(cfg, role, plan[rank], meta=True)
+    if args.partition == "half" and world > 1 and not cfg.parallel_residual:
+        # half-layer units (attention | MLP): pipeline boundaries may fall inside a layer
+        from mdi_llm_b200.models.partition import half_stages, plan_half_units
+
+        units = plan_half_units(world, cfg)
+        hs = half_stages(units)[rank]
+        plan = [u / 2 for u in units]
+        stage = build_stage(cfg, role, hs.n_blocks, meta=True, first_mlp_only=hs.first_mlp_only,
+                            last_attn_only=hs.last_attn_only)
+    else:
+        policy = "balanced" if args.partition == "half" else args.partition
+        plan = plan_layers(world, cfg.n_layer, cfg, policy=policy) if world > 1 else [cfg.n_layer]
+        stage = build_stage(cfg, role, plan[rank], meta=True)
     random_init_stage_(stage, device, torch.bfloat16, seed=1234 + rank)
     sampling = SamplingParams(temperature=args.temperature, top_k=args.top_k, seed=2024)
     pipe = DevicePipeline(stage, rank, world, n_samples=n_samples, max_seq_length=seq_len, sampling=sampling,

@@ -332,15 +332,27 @@ def build_mlp(config: Config) -> nn.Module:
 class Block(nn.Module):
     """Transformer block, sequential or parallel residual (model.py:576-629)."""
 
-    def __init__(self, config: Config) -> None:
+    def __init__(self, config: Config, parts: str = "both") -> None:
+        """``parts``: "both" (a whole block), or one sub-layer of a sequential-residual block —
+        "attn" (``norm_1`` + attention + residual) / "mlp" (``norm_2`` + MLP + residual).  Half blocks
+        let a pipeline boundary fall *inside* a layer (finer stage balancing than the reference's
+        whole-layer chunks); the owner of the attention half owns the layer's KV cache."""
         super().__init__()
         if not config.parallel_residual and config.shared_attention_norm:
             raise NotImplementedError("sequential residual with a shared attention norm")
+        if parts not in ("both", "attn", "mlp"):
+            raise ValueError(f"parts must be 'both', 'attn' or 'mlp', got {parts!r}")
+        if parts != "both" and config.parallel_residual:
+            raise ValueError("a parallel-residual block cannot be split between stages")
         self.config = config
-        self.norm_1 = build_norm(config)
-        self.attn = CausalSelfAttention(config)
-        self.norm_2 = None if config.shared_attention_norm else build_norm(config)
-        self.mlp = build_mlp(config)
+        self.parts = parts
+        self.has_attn, self.has_mlp = parts in ("both", "attn"), parts in ("both", "mlp")
+        if self.has_attn:
+            self.norm_1 = build_norm(config)
+            self.attn = CausalSelfAttention(config)
+        if self.has_mlp:
+            self.norm_2 = None if config.shared_attention_norm else build_norm(config)
+            self.mlp = build_mlp(config)
 
     def forward(
         self,
@@ -350,8 +362,12 @@ class Block(nn.Module):
         input_pos: Optional[torch.Tensor] = None,
         kv: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
     ) -> torch.Tensor:
+        if self.parts == "mlp":
+            return x + self.mlp(self.norm_2(x))
         h = self.norm_1(x)
         a = self.attn(h, cos, sin, input_pos, kv)
+        if self.parts == "attn":
+            return x + a
         if self.config.parallel_residual:
             h2 = h if self.norm_2 is None else self.norm_2(x)
             return self.mlp(h2) + a + x

@@ -28,6 +28,7 @@ from .config import Config
 __all__ = [
     "N_LAYERS_NODES", "plan_layers", "balanced_plan", "layer_ranges", "split_parameters",
     "split_and_store", "merge_chunks", "count_transformer_blocks", "chunk_dir", "chunk_file",
+    "HalfStage", "plan_half_units", "half_stages", "split_parameters_half", "decode_unit_costs",
 ]
 
 # n_nodes -> n_layer -> (starter layers, layers per secondary).  Data of config.py:56-98.
@@ -99,6 +100,117 @@ def plan_layers(
     if config is not None:
         head = config.head_param_count() / max(1, config.block_param_count())
     return balanced_plan(n_nodes, n_layer, head)
+
+
+# ---- half-layer partitions ---------------------------------------------------------------------------
+# A sequential-residual block is two independent residual sub-layers: attention (norm_1 + attn) and MLP
+# (norm_2 + mlp).  Cutting the pipeline between them doubles the planner's granularity: 8 stages x
+# Llama-3-8B goes from a 5-layer bottleneck stage to ~4.4 layer-equivalents (the reference's chunks
+# are whole layers, utils.py:241-385).  Unit u = 2*layer + (0: attention | 1: MLP).
+from dataclasses import dataclass
+
+
+@dataclass(frozen=True)
+class HalfStage:
+    lo_unit: int            # first half-unit owned (inclusive)
+    hi_unit: int            # one past the last half-unit
+    first_mlp_only: bool    # first local block holds only its MLP half
+    last_attn_only: bool    # last local block holds only its attention half
+
+    @property
+    def lo_layer(self) -> int:
+        return self.lo_unit // 2
+
+    @property
+    def hi_layer(self) -> int:  # one past the last (possibly partial) global layer
+        return (self.hi_unit + 1) // 2
+
+    @property
+    def n_blocks(self) -> int:
+        return self.hi_layer - self.lo_layer
+
+
+def half_stages(units_per_stage: Sequence[int]) -> List[HalfStage]:
+    out, u = [], 0
+    for n in units_per_stage:
+        if n < 1:
+            raise ValueError("every stage needs at least one half-layer unit")
+        out.append(HalfStage(u, u + n, first_mlp_only=u % 2 == 1, last_attn_only=(u + n) % 2 == 1))
+        u += n
+    return out
+
+
+def decode_unit_costs(config: Config, bytes_per_param: float = 2.0, eff_tbps: float = 5.9, kernel_us: float = 2.0,
+                      attn_kernel_us: float = 8.0, sampler_us: float = 45.0) -> Tuple[float, float, float]:
+    """Per-token decode cost model in microseconds -> ``(attention unit, MLP unit, output head)``.
+    Decode is weight-streaming bound: bytes over the achieved HBM rate plus a per-launch term; defaults
+    are the measured B200 values (profiles/README.md)."""
+    C = config.n_embd
+    bw = eff_tbps * 1e6  # bytes per microsecond
+    attn_b = (config.qkv_size + config.attn_out_dim) * C * bytes_per_param
+    mlp_mats = 3 if config.mlp_class_name in ("LLaMAMLP", "GemmaMLP") else 2
+    mlp_b = mlp_mats * C * config.intermediate_size * bytes_per_param
+    head_b = config.padded_vocab_size * C * bytes_per_param
+    return (attn_b / bw + 2 * kernel_us + attn_kernel_us, mlp_b / bw + 2 * kernel_us,
+            head_b / bw + kernel_us + sampler_us)
+
+
+def plan_half_units(n_nodes: int, config: Config, costs: Optional[Tuple[float, float, float]] = None) -> List[int]:
+    """Half-units per stage (sum = 2 * n_layer) minimising the slowest stage of the decode ring; stage 0
+    additionally carries the output head.  Exact DP over contiguous partitions."""
+    if config.parallel_residual:
+        raise ValueError("half-layer partitions need sequential-residual blocks")
+    U = 2 * config.n_layer
+    if n_nodes < 1 or U < n_nodes:
+        raise ValueError(f"cannot split {U} half-layers over {n_nodes} nodes")
+    ca, cm, ch = costs if costs is not None else decode_unit_costs(config)
+    pre = [0.0]
+    for u in range(U):
+        pre.append(pre[-1] + (ca if u % 2 == 0 else cm))
+    seg = lambda a, b, first: pre[b] - pre[a] + (ch if first else 0.0)  # noqa: E731
+    INF = float("inf")
+    # best[k][u] = minimal bottleneck covering units [0,u) with k stages
+    best = [[INF] * (U + 1) for _ in range(n_nodes + 1)]
+    arg = [[0] * (U + 1) for _ in range(n_nodes + 1)]
+    for u in range(1, U + 1):
+        best[1][u] = seg(0, u, True)
+    for k in range(2, n_nodes + 1):
+        for u in range(k, U + 1):
+            for a in range(k - 1, u):
+                c = max(best[k - 1][a], seg(a, u, False))
+                if c < best[k][u] - 1e-9:
+                    best[k][u], arg[k][u] = c, a
+    cuts, u = [], U
+    for k in range(n_nodes, 1, -1):
+        a = arg[k][u]
+        cuts.append(u - a)
+        u = a
+    cuts.append(u)
+    return cuts[::-1]
+
+
+_ATTN_HALF = ("norm_1.", "attn.")
+
+
+def split_parameters_half(model_params: Dict[str, Any], units_per_stage: Sequence[int]) -> Dict[str, Any]:
+    """Like :func:`split_parameters` for a half-unit plan.  A layer cut in two appears in both
+    neighbouring chunks: its ``norm_1``/``attn`` tensors as the *last* local block of one stage, its
+    ``norm_2``/``mlp`` (and any other) tensors as local block 0 of the next."""
+    n_layer = count_transformer_blocks(model_params)
+    stages = half_stages(units_per_stage)
+    if stages[-1].hi_unit != 2 * n_layer:
+        raise ValueError(f"plan {list(units_per_stage)} does not cover {2 * n_layer} half-layers")
+    chunks: List[Dict[str, Any]] = [{} for _ in stages]
+    for k in [k for k in model_params if k.startswith("transformer.h.")]:
+        _, _, li, tail = k.split(".", 3)
+        unit = 2 * int(li) + (0 if tail.startswith(_ATTN_HALF) else 1)
+        si = next(i for i, st in enumerate(stages) if st.lo_unit <= unit < st.hi_unit)
+        chunks[si][f"transformer.h.{int(li) - stages[si].lo_layer}.{tail}"] = model_params.pop(k)
+    for k in ("transformer.wte.weight", "transformer.wte.bias", "transformer.wpe.weight", "transformer.ln_f.weight",
+              "transformer.ln_f.bias", "lm_head.weight", "lm_head.bias"):
+        if k in model_params:
+            chunks[0][k] = model_params.pop(k)
+    return {"starter": chunks[0], "secondary": chunks[1:]}
 
 
 def layer_ranges(plan: Sequence[int]) -> List[Tuple[int, int]]:

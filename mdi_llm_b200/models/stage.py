@@ -33,6 +33,10 @@ class StageModule(nn.Module, RopeMixin):
         super().__init__()
         self.config = config
         self.n_local_layers = int(n_transf_layers)
+        # half-layer boundaries (models/partition.py:plan_half_units): the first local block may hold
+        # only its MLP half, the last one only its attention half
+        self.first_mlp_only = bool(kwargs.get("first_mlp_only", False))
+        self.last_attn_only = bool(kwargs.get("last_attn_only", False))
         self.verb = bool(kwargs.get("verb", False))
         self.params_init = False
         self.kv_pool: Optional[KVPool] = None
@@ -74,6 +78,20 @@ class StageModule(nn.Module, RopeMixin):
         self.params_init = True
         return 1
 
+    def _make_blocks(self) -> nn.ModuleList:
+        n = self.n_local_layers
+        if n == 1 and self.first_mlp_only and self.last_attn_only:
+            raise ValueError("a stage cannot hold only 'mlp' and only 'attn' of the same single block")
+
+        def parts(i: int) -> str:
+            if i == 0 and self.first_mlp_only:
+                return "mlp"
+            if i == n - 1 and self.last_attn_only:
+                return "attn"
+            return "both"
+
+        return nn.ModuleList(Block(self.config, parts(i)) for i in range(n))
+
     def _blocks(self, x: torch.Tensor, input_pos: Optional[torch.Tensor], slot: int) -> torch.Tensor:
         T = x.size(1)
         if self.max_seq_length < T:
@@ -95,7 +113,7 @@ class StarterNode(StageModule):
         self.with_head = bool(with_head)
         parts = dict(
             wte=nn.Embedding(config.padded_vocab_size, config.n_embd),
-            h=nn.ModuleList(Block(config) for _ in range(n_transf_layers)),
+            h=self._make_blocks(),
         )
         if self.with_head:
             parts["ln_f"] = build_norm(config)
@@ -147,7 +165,7 @@ class SecondaryNode(StageModule):
 
     def __init__(self, config: Config, n_transf_layers: int, **kwargs: Any) -> None:
         super().__init__(config, n_transf_layers, **kwargs)
-        self.transformer = nn.ModuleDict(dict(h=nn.ModuleList(Block(config) for _ in range(n_transf_layers))))
+        self.transformer = nn.ModuleDict(dict(h=self._make_blocks()))
         self.max_seq_length = config.block_size
 
     def forward(self, x: torch.Tensor, input_pos: Optional[torch.Tensor] = None, *, slot: int = 0) -> torch.Tensor:
@@ -164,7 +182,7 @@ class FinisherNode(StageModule):
     def __init__(self, config: Config, n_transf_layers: int, **kwargs: Any) -> None:
         super().__init__(config, n_transf_layers, **kwargs)
         self.transformer = nn.ModuleDict(dict(
-            h=nn.ModuleList(Block(config) for _ in range(n_transf_layers)), ln_f=build_norm(config)))
+            h=self._make_blocks(), ln_f=build_norm(config)))
         self.lm_head = nn.Linear(config.n_embd, config.padded_vocab_size, bias=config.lm_head_bias)
         self.max_seq_length = config.block_size
 

@@ -185,7 +185,10 @@ class FusedStage:
 
         lins = []
         for blk in self.model.transformer.h:
-            lins += [blk.attn.attn, blk.attn.proj, blk.mlp.fc_1, blk.mlp.fc_2, blk.mlp.proj]
+            if getattr(blk, "has_attn", True):
+                lins += [blk.attn.attn, blk.attn.proj]
+            if getattr(blk, "has_mlp", True):
+                lins += [blk.mlp.fc_1, blk.mlp.fc_2, blk.mlp.proj]
         if self.is_starter and not self.cfg.tie_embeddings:
             lins.append(self.model.lm_head)
         with torch.cuda.device(self.device):
@@ -290,47 +293,65 @@ class FusedStage:
                   tok_slot_stride=self.tokens.shape[1], scale=float(cfg.n_embd ** 0.5) if cfg.scale_embeddings else 1.0,
                   use_pdl=self.use_pdl)
 
+    def _units(self) -> List[Tuple[int, str]]:
+        """The stage's work as residual sub-layers ``(local block, "attn" | "mlp")`` — whole blocks
+        contribute both; a half-layer pipeline boundary contributes one (models/partition.py)."""
+        out: List[Tuple[int, str]] = []
+        for li, blk in enumerate(self.model.transformer.h):
+            if getattr(blk, "has_attn", True):
+                out.append((li, "attn"))
+            if getattr(blk, "has_mlp", True):
+                out.append((li, "mlp"))
+        return out
+
     def enqueue_blocks(self, hop: Optional[HopTarget], wait_input: bool) -> None:
-        """All local blocks for one token.  Input residual: ``xa`` on the starter (embedding),
-        ``hidden_in[slot]`` on a secondary.  Output: ``hop`` target (+flag) or ``out_local[slot]``."""
+        """All local sub-layers for one token.  Input residual: ``xa`` on the starter (embedding),
+        ``hidden_in[slot]`` on a secondary.  The first kernel (QKV projection, or gate/up projection when
+        the stage starts inside a layer) acquires the incoming hop; the last one (down projection, or
+        attention output projection when the stage ends inside a layer) writes the ``hop`` target and
+        releases its flag, or writes ``out_local[slot]``."""
         cfg, C = self.cfg, self.cfg.n_embd
         x_in, x_in_stride = (self.xa, 0) if self.is_starter else (self.hidden_in, C)
         common = dict(ctas_per_sm=self.ctas_per_sm, use_pdl=self.use_pdl)
-        for li, blk in enumerate(self.model.transformer.h):
-            first, last = li == 0, li == self.n_layers - 1
-            kv_layer = self.kv[li]
-            qw = self._w(blk.attn.attn)
-            ops.qkv_decode(
-                qw.pop("W"), x_in, self.model.cos, self.model.sin, self.q, kv_layer, self.ctx,
-                n_head=cfg.n_head, n_groups=cfg.n_query_groups, head_size=cfg.head_size,
-                rope_n_elem=cfg.rope_n_elem, max_seq=self.S, norm_w=blk.norm_1.weight, **qw,
-                eps=cfg.norm_eps, unit_offset=cfg.unit_offset_norm, x_slot_stride=x_in_stride,
-                wait_flag=self.flags.data_ptr() if (first and wait_input and not self.is_starter) else None,
-                status=self.status.data_ptr(), wait_max_cycles=self.wait_max_cycles, trace=self._tr(f"L{li}.qkv"), **common)
-            ops.attn_decode(self.q, kv_layer, self.y_attn, self.part, self.tickets, self.ctx, n_head=cfg.n_head,
-                            n_groups=cfg.n_query_groups, head_size=cfg.head_size, max_seq=self.S,
-                            n_split=self.n_split, use_pdl=self.use_pdl, trace=self._tr(f"L{li}.attn"))
-            ow = self._w(blk.attn.proj)
-            ops.linear_decode(ow.pop("W"), self.y_attn, self.xb, self.ctx, **ow,
-                              residual=x_in, res_slot_stride=x_in_stride, trace=self._tr(f"L{li}.o_proj"), **common)
-            gw = {**self._w(blk.mlp.fc_1), **self._w(blk.mlp.fc_2, second=True)}
-            ops.linear_decode(gw.pop("W"), self.xb, self.h_mlp, self.ctx, **gw, norm_w=blk.norm_2.weight,
-                              eps=cfg.norm_eps, unit_offset=cfg.unit_offset_norm, act=self._gate_act(),
-                              trace=self._tr(f"L{li}.gate_up"), **common)
-            dw = self._w(blk.mlp.proj)
-            d_w = dw.pop("W")
-            if not last:
-                ops.linear_decode(d_w, self.h_mlp, self.xa, self.ctx, **dw,
-                                  residual=self.xb, trace=self._tr(f"L{li}.down"), **common)
-                x_in, x_in_stride = self.xa, 0
-            elif hop is not None:
-                ops.linear_decode(d_w, self.h_mlp, None, self.ctx, **dw,
-                                  residual=self.xb, y_ptr=hop.hidden_ptr, y_slot_stride=C,
-                                  signal_flag=hop.flag_ptr, done_ctr=self.done_ctr.data_ptr(),
-                                  trace=self._tr(f"L{li}.down+hop"), **common)
+        units = self._units()
+        for ui, (li, kind) in enumerate(units):
+            first, last = ui == 0, ui == len(units) - 1
+            blk = self.model.transformer.h[li]
+            wait = dict(wait_flag=self.flags.data_ptr() if (first and wait_input and not self.is_starter) else None,
+                        status=self.status.data_ptr(), wait_max_cycles=self.wait_max_cycles)
+            x_out = self.xb if x_in is not self.xb else self.xa
+            if kind == "attn":
+                kv_layer = self.kv[li]
+                qw = self._w(blk.attn.attn)
+                ops.qkv_decode(
+                    qw.pop("W"), x_in, self.model.cos, self.model.sin, self.q, kv_layer, self.ctx,
+                    n_head=cfg.n_head, n_groups=cfg.n_query_groups, head_size=cfg.head_size,
+                    rope_n_elem=cfg.rope_n_elem, max_seq=self.S, norm_w=blk.norm_1.weight, **qw,
+                    eps=cfg.norm_eps, unit_offset=cfg.unit_offset_norm, x_slot_stride=x_in_stride,
+                    trace=self._tr(f"L{li}.qkv"), **wait, **common)
+                ops.attn_decode(self.q, kv_layer, self.y_attn, self.part, self.tickets, self.ctx, n_head=cfg.n_head,
+                                n_groups=cfg.n_query_groups, head_size=cfg.head_size, max_seq=self.S,
+                                n_split=self.n_split, use_pdl=self.use_pdl, trace=self._tr(f"L{li}.attn"))
+                lw, src, name = self._w(blk.attn.proj), self.y_attn, f"L{li}.o_proj"
             else:
-                ops.linear_decode(d_w, self.h_mlp, self.out_local, self.ctx, **dw,
-                                  residual=self.xb, y_slot_stride=C, trace=self._tr(f"L{li}.down"), **common)
+                gw = {**self._w(blk.mlp.fc_1), **self._w(blk.mlp.fc_2, second=True)}
+                ops.linear_decode(gw.pop("W"), x_in, self.h_mlp, self.ctx, **gw, norm_w=blk.norm_2.weight,
+                                  eps=cfg.norm_eps, unit_offset=cfg.unit_offset_norm, act=self._gate_act(),
+                                  x_slot_stride=x_in_stride, trace=self._tr(f"L{li}.gate_up"),
+                                  **(wait if first else {}), **common)
+                lw, src, name = self._w(blk.mlp.proj), self.h_mlp, f"L{li}.down"
+            w_out = lw.pop("W")
+            res = dict(residual=x_in, res_slot_stride=x_in_stride)
+            if not last:
+                ops.linear_decode(w_out, src, x_out, self.ctx, **lw, **res, trace=self._tr(name), **common)
+                x_in, x_in_stride = x_out, 0
+            elif hop is not None:
+                ops.linear_decode(w_out, src, None, self.ctx, **lw, **res, y_ptr=hop.hidden_ptr, y_slot_stride=C,
+                                  signal_flag=hop.flag_ptr, done_ctr=self.done_ctr.data_ptr(),
+                                  trace=self._tr(name + "+hop"), **common)
+            else:
+                ops.linear_decode(w_out, src, self.out_local, self.ctx, **lw, **res, y_slot_stride=C,
+                                  trace=self._tr(name), **common)
 
     # ---- prefill (T > 1): linears on the tcgen05 GEMM ------------------------------------------------
     @torch.inference_mode()
@@ -352,20 +373,29 @@ class FusedStage:
             x = data[0].to(torch.bfloat16).contiguous()
         cos, sin = m.rope_for(T, input_pos)
         eps, uo = cfg.norm_eps, cfg.unit_offset_norm
-        n_local = len(m.transformer.h)
-        for li, blk in enumerate(m.transformer.h):
-            h = ops.rmsnorm_rows(x, blk.norm_1.weight, eps, uo)
-            qkv = ops.gemm(h, self._dense(blk.attn.attn), bias=blk.attn.attn.bias)
-            y = blk.attn.attend_qkv(qkv.unsqueeze(0), cos, sin, input_pos, m.kv_pool.layer(li, slot))[0].contiguous()
-            x = ops.gemm(y, self._dense(blk.attn.proj), bias=blk.attn.proj.bias, residual=x)
-            h = ops.rmsnorm_rows(x, blk.norm_2.weight, eps, uo)
-            g = ops.gemm(h, self._dense(blk.mlp.fc_1), bias=blk.mlp.fc_1.bias, w2=self._dense(blk.mlp.fc_2),
-                         bias2=blk.mlp.fc_2.bias, act=self._gate_act())
-            if hop is not None and li == n_local - 1:
-                ops.gemm(g, self._dense(blk.mlp.proj), bias=blk.mlp.proj.bias, residual=x, out_ptr=hop[0],
-                         signal_flag=hop[1], done_ctr=self.done_ctr, ctx=self.ctx)
+        units = self._units()
+
+        def out_gemm(a_in: torch.Tensor, lin: Any, last: bool) -> Optional[torch.Tensor]:
+            if hop is not None and last:
+                ops.gemm(a_in, self._dense(lin), bias=lin.bias, residual=x, out_ptr=hop[0], signal_flag=hop[1],
+                         done_ctr=self.done_ctr, ctx=self.ctx)
                 return None
-            x = ops.gemm(g, self._dense(blk.mlp.proj), bias=blk.mlp.proj.bias, residual=x)
+            return ops.gemm(a_in, self._dense(lin), bias=lin.bias, residual=x)
+
+        for ui, (li, kind) in enumerate(units):
+            blk, last = m.transformer.h[li], ui == len(units) - 1
+            if kind == "attn":
+                h = ops.rmsnorm_rows(x, blk.norm_1.weight, eps, uo)
+                qkv = ops.gemm(h, self._dense(blk.attn.attn), bias=blk.attn.attn.bias)
+                y = blk.attn.attend_qkv(qkv.unsqueeze(0), cos, sin, input_pos, m.kv_pool.layer(li, slot))[0].contiguous()
+                x = out_gemm(y, blk.attn.proj, last)
+            else:
+                h = ops.rmsnorm_rows(x, blk.norm_2.weight, eps, uo)
+                g = ops.gemm(h, self._dense(blk.mlp.fc_1), bias=blk.mlp.fc_1.bias, w2=self._dense(blk.mlp.fc_2),
+                             bias2=blk.mlp.fc_2.bias, act=self._gate_act())
+                x = out_gemm(g, blk.mlp.proj, last)
+            if x is None:
+                return None
         return x.unsqueeze(0)
 
     # ---- graphs ------------------------------------------------------------------------------------

@@ -160,6 +160,94 @@ def test_device_pipeline_multi_gpu_one_process(n_stages):
         _near_argmax_check(cfg, full, results[0][i], len(prompts[i]))
 
 
+def _half_stages(cfg, units, devs, seed=7):
+    from mdi_llm_b200.models.partition import half_stages, split_parameters_half
+    from mdi_llm_b200.models.stage import build_stage
+    from mdi_llm_b200.utils.checkpoint import materialize_stage, random_state_dict
+
+    sd = random_state_dict(cfg, dtype=torch.bfloat16, seed=seed, std=0.05)
+    chunks = split_parameters_half(dict(sd), units)
+    out = []
+    for i, hs in enumerate(half_stages(units)):
+        st = build_stage(cfg, "starter" if i == 0 else f"secondary:{i - 1}", hs.n_blocks, meta=True,
+                         first_mlp_only=hs.first_mlp_only, last_attn_only=hs.last_attn_only)
+        materialize_stage(st, chunks["starter"] if i == 0 else chunks["secondary"][i - 1], devs[i], torch.bfloat16)
+        out.append(st)
+    return out
+
+
+@pytest.mark.multigpu
+def test_device_pipeline_half_layer_boundaries():
+    """Pipeline boundaries inside layers (attention | MLP): o_proj carries the outgoing hop, gate/up
+    acquires the incoming one.  Tokens must equal the one-GPU pipeline's."""
+    from mdi_llm_b200.parallel.pipeline import DevicePipeline, connect_ring_local
+    from mdi_llm_b200.parallel.scheduler import SamplingParams
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    cfg = _cfg(n_layer=4)
+    units = [3, 5]  # stage 0: layer 0 + attention of layer 1; stage 1: MLP of layer 1 + layers 2, 3
+    stages = _half_stages(cfg, units, ["cuda:0", "cuda:1"])
+    assert stages[0].transformer.h[-1].parts == "attn" and stages[1].transformer.h[0].parts == "mlp"
+    prompts = [torch.tensor([1, 10 + i, 20, 30 + i]) for i in range(2)]
+    pipes = [DevicePipeline(st, i, 2, n_samples=2, max_seq_length=64, sampling=SamplingParams.greedy(),
+                            exportable=False, wait_max_cycles=4 * 10 ** 9) for i, st in enumerate(stages)]
+    connect_ring_local(pipes)
+    barrier = threading.Barrier(2)
+    results, errors = {}, []
+
+    def run(p):
+        try:
+            results[p.rank] = p.generate(prompts, 8, sync=lambda: barrier.wait(timeout=60))
+        except BaseException as e:  # noqa: BLE001
+            errors.append(e)
+            barrier.abort()
+
+    threads = [threading.Thread(target=run, args=(p,)) for p in pipes]
+    [t.start() for t in threads]
+    [t.join(timeout=120) for t in threads]
+    assert not errors, errors
+    _, (st1,) = _stages(cfg, 1)
+    ref = DevicePipeline(st1, 0, 1, n_samples=2, max_seq_length=64, sampling=SamplingParams.greedy()).generate(prompts, 8)
+    for i in range(2):
+        assert torch.equal(results[0][i], ref[i]), f"sample {i}: {results[0][i].tolist()} vs {ref[i].tolist()}"
+
+
+def test_fused_stage_half_blocks_single_gpu():
+    """A stage that starts with an MLP half and ends with an attention half, against the eager modules."""
+    from mdi_llm_b200.parallel.engine import FusedStage
+
+    cfg = _cfg(n_layer=4)
+    stages = _half_stages(cfg, [3, 4, 1], ["cuda", "cuda", "cuda"])
+    mid = stages[1]  # MLP of layer 1, layer 2, attention of layer 3
+    assert [b.parts for b in mid.transformer.h] == ["mlp", "both", "attn"]
+    fs = FusedStage(mid, n_slots=1, max_seq_length=32)
+    fs.warmup()
+    mid.set_kv_cache(1) if mid.kv_pool is None else None
+    x = (torch.randn(1, 5, cfg.n_embd, device="cuda") * 0.5).bfloat16()
+    pos = torch.arange(5, device="cuda")
+    fs.set_ctx(0, 4)
+    out_f = fs.prefill(x, pos, 0)
+    import copy
+    eager = copy.deepcopy(mid)
+    eager.kv_pool = None
+    eager.set_kv_cache(1)
+    with torch.inference_mode():
+        out_e = eager(x, pos)
+    scale = out_e.float().abs().max().item()
+    assert (out_f.float() - out_e.float()).abs().max().item() <= 0.03 * scale + 0.03
+    # one decode token through the fused kernels vs eager
+    xt = (torch.randn(cfg.n_embd, device="cuda") * 0.5).bfloat16()
+    fs.hidden_in[0].copy_(xt)
+    fs.set_ctx(0, 5)
+    fs.enqueue_blocks(None, wait_input=False)
+    torch.cuda.synchronize()
+    with torch.inference_mode():
+        ref = eager(xt.view(1, 1, -1), torch.tensor([5], device="cuda"))[0, 0]
+    got = fs.out_local[0]
+    assert (got.float() - ref.float()).abs().max().item() <= 0.03 * ref.float().abs().max().item() + 0.03
+
+
 def test_fp8_weights_pipeline_follows_the_dequantised_model():
     """BASELINE config #5 path: fp8 block-scaled weights end to end (prefill dequantised + tcgen05,
     decode on the fp8 streaming kernels) tracks the eager model run on the dequantised weights."""

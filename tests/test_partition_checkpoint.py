@@ -100,3 +100,66 @@ def test_fp8_block_quantisation_roundtrip_error():
     assert "transformer.h.0.attn.proj.weight_scale" in sd and sd["transformer.wte.weight"].dtype == torch.float32
     with pytest.raises(ValueError):
         quantize_fp8_block(torch.randn(4, 100))
+
+
+# ---- half-layer partitions ------------------------------------------------------------------------------
+def test_half_unit_plan_covers_and_balances():
+    from mdi_llm_b200.models.config import Config
+    from mdi_llm_b200.models.partition import decode_unit_costs, half_stages, plan_half_units, plan_layers
+
+    cfg = Config.from_name("Llama-3-8B")
+    ca, cm, ch = decode_unit_costs(cfg)
+    for n in (1, 2, 4, 8):
+        plan = plan_half_units(n, cfg)
+        assert len(plan) == n and sum(plan) == 2 * cfg.n_layer and min(plan) >= 1
+        st = half_stages(plan)
+        cost = [sum(ca if u % 2 == 0 else cm for u in range(s.lo_unit, s.hi_unit)) + (ch if i == 0 else 0) for i, s in enumerate(st)]
+        whole = plan_layers(n, cfg.n_layer, cfg, policy="balanced")
+        whole_cost = [l * (ca + cm) + (ch if i == 0 else 0) for i, l in enumerate(whole)]
+        assert max(cost) <= max(whole_cost) + 1e-6  # never worse than whole-layer stages
+    assert max(cost) < max(whole_cost)  # and strictly better for 8 x Llama-3-8B
+    with pytest.raises(ValueError):
+        plan_half_units(2, Config.from_name("pythia-14m"))  # parallel residual cannot be cut
+
+
+def test_half_stage_chain_equals_full_model(tiny_llama_cfg):
+    """Stages cut inside layers (attention | MLP) reproduce the full model exactly, with KV caches."""
+    import torch
+    from mdi_llm_b200.models.gpt import GPT
+    from mdi_llm_b200.models.partition import half_stages, split_parameters_half
+    from mdi_llm_b200.models.stage import build_stage
+    from mdi_llm_b200.utils.checkpoint import random_state_dict
+
+    cfg = tiny_llama_cfg
+    sd = random_state_dict(cfg, dtype=torch.float32)
+    full = GPT(cfg)
+    full.load_state_dict(sd)
+    full.eval()
+    plan = [3, 2, 2 * cfg.n_layer - 5]  # cuts after unit 3 (inside layer 1) and unit 5 (inside layer 2)
+    st = half_stages(plan)
+    assert st[0].last_attn_only and st[1].first_mlp_only and st[1].last_attn_only and st[2].first_mlp_only
+    chunks = split_parameters_half(dict(sd), plan)
+    mods = []
+    for i, s in enumerate(st):
+        m = build_stage(cfg, "starter" if i == 0 else f"secondary:{i - 1}", s.n_blocks, meta=True,
+                        first_mlp_only=s.first_mlp_only, last_attn_only=s.last_attn_only)
+        m.load_weights(chunks["starter"] if i == 0 else chunks["secondary"][i - 1])
+        m.set_kv_cache(1)
+        mods.append(m.eval())
+    idx = torch.tensor([[1, 5, 9, 2]])
+    full.set_kv_cache(1)
+    with torch.no_grad():
+        pos = torch.arange(4)
+        ref = full(idx, pos)
+        x = mods[0](idx, pos)
+        for m in mods[1:]:
+            x = m(x, pos)
+        out = mods[0].head(x)
+        torch.testing.assert_close(out, ref, rtol=1e-4, atol=1e-5)
+        nxt = torch.tensor([[7]])
+        pos = torch.tensor([4])
+        ref = full(nxt, pos)
+        x = mods[0](nxt, pos)
+        for m in mods[1:]:
+            x = m(x, pos)
+        torch.testing.assert_close(mods[0].head(x), ref, rtol=1e-4, atol=1e-5)
