@@ -191,6 +191,14 @@ __device__ __forceinline__ void trace_mark(unsigned long long* rec, int field, b
   }
 }
 
+// extra per-CTA phase marks (detail table fields 6 and 7), only recorded when a detail table is attached
+__device__ __forceinline__ void trace_phase(unsigned long long* rec, int field) {
+  if (rec == nullptr || threadIdx.x != 0) return;
+  unsigned long long* detail = reinterpret_cast<unsigned long long*>(rec[6]);
+  if (detail != nullptr && blockIdx.x + gridDim.x * blockIdx.y < rec[7])
+    detail[(size_t)(blockIdx.x + gridDim.x * blockIdx.y) * 8 + field] = globaltimer_ns();
+}
+
 // Programmatic dependent launch: let the next kernel's prologue overlap our tail, and wait for
 // the previous kernel's memory before touching activations.
 __device__ __forceinline__ void pdl_wait_prior() {

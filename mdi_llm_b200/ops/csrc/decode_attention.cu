@@ -165,6 +165,8 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const AttnArgs
     __syncwarp();
   }
 
+  __syncthreads();
+  trace_phase(a.trace, 6);  // all tiles done
   // ---- merge the CTA's warps ------------------------------------------------------------------
 #pragma unroll
   for (int h = 0; h < QPK; ++h) {

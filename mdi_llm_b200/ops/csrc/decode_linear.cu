@@ -415,8 +415,10 @@ __global__ void __launch_bounds__(LIN_THREADS, STAGES == 2 ? 3 : (STAGES == 3 ? 
     bulk_g2s(dst, wa + k0, bytes, &bars[st]);
     bulk_g2s(dst + TS_CHUNK, wb + k0, bytes, &bars[st]);
   };
+  // Fill the WHOLE ring before waiting for the input: the previous kernel's tail (and, for o_proj, the
+  // attention kernel's latency chain) then overlaps with up to STAGES x 4 KB per warp of weight traffic.
   if (lane == 0)
-    for (int f = 0; f < min(STAGES - 1, total); ++f) issue(f);
+    for (int f = 0; f < min(STAGES, total); ++f) issue(f);
   unsigned int* hist_s = stats_begin(a, reinterpret_cast<unsigned char*>(bars - warp * STAGES + LIN_WARPS * STAGES));
   unsigned long long best = 0ull;
 
@@ -432,7 +434,6 @@ __global__ void __launch_bounds__(LIN_THREADS, STAGES == 2 ? 3 : (STAGES == 3 ? 
   float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
   int c = 0, ii = 0;
   for (int f = 0; f < total; ++f) {
-    if (lane == 0 && f + STAGES - 1 < total) issue(f + STAGES - 1);
     const int st = f % STAGES;
     mbar_wait(&bars[st], (uint32_t)((f / STAGES) & 1));
     const int k0 = c * TS_CHUNK;
@@ -457,7 +458,8 @@ __global__ void __launch_bounds__(LIN_THREADS, STAGES == 2 ? 3 : (STAGES == 3 ? 
       c = 0;
       ++ii;
     }
-    __syncwarp();  // everyone is done with stage `st` before lane 0 re-arms it next iteration
+    __syncwarp();  // everyone is done with stage `st` ...
+    if (lane == 0 && f + STAGES < total) issue(f + STAGES);  // ... so it can be refilled right away
   }
   stats_flush(a, hist_s, best);
   hop_signal(a.signal, a.ctx);
@@ -628,6 +630,7 @@ static int launch_pdl(Kern kern, const StreamArgs& args, int grid, size_t smem, 
 template <int MODE>
 static int launch_stream(const StreamArgs& a, int variant, int ctas_per_sm, int use_pdl, cudaStream_t stream) {
   const int sms = num_sms();
+  const int grid_override = ctas_per_sm < 0 ? -ctas_per_sm : 0;  // experiments: ctas_per_sm = -G forces a grid of G CTAs
   if (ctas_per_sm <= 0) ctas_per_sm = 4;
   const int max_useful = (a.n_items + LIN_WARPS - 1) / LIN_WARPS;
   if (a.wscale != nullptr) {  // fp8 block-scaled weights: register-streamed kernel
@@ -646,7 +649,7 @@ static int launch_stream(const StreamArgs& a, int variant, int ctas_per_sm, int 
                       (size_t)LIN_WARPS * stages * 8 + (a.hist ? STAT_BINS * 4 : 0);
   if (smem > 227 * 1024) return launch_stream<MODE>(a, 0, ctas_per_sm, use_pdl, stream);  // huge K: LDG path
   const int per_sm = variant == 1 ? 1 : max(1, min(ctas_per_sm, (int)((227 * 1024) / (smem + 1024))));
-  const int grid = max(1, min(sms * per_sm, max_useful));
+  const int grid = grid_override > 0 ? min(grid_override, max_useful) : max(1, min(sms * per_sm, max_useful));
   if (variant == 1) return launch_pdl(stream_bulk_kernel<MODE, 4>, a, grid, smem, stream, use_pdl);
   if (variant == 3) return launch_pdl(stream_bulk_kernel<MODE, 3>, a, grid, smem, stream, use_pdl);
   return launch_pdl(stream_bulk_kernel<MODE, 2>, a, grid, smem, stream, use_pdl);

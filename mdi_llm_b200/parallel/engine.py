@@ -21,6 +21,7 @@ Two ways to drive it:
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass
 from typing import Sequence, Any, Dict, List, Optional, Tuple
 
@@ -213,6 +214,12 @@ class FusedStage:
 
         return dequantize_fp8_block(q[0], q[1], torch.bfloat16)
 
+    def _ctas(self, kernel: str) -> int:
+        """CTAs per SM for one of the decode linears; ``MDI_CTAS_<KERNEL>`` (e.g. ``MDI_CTAS_GATE_UP=-256``:
+        negative = absolute grid size) overrides the stage-wide setting for tuning experiments."""
+        v = os.environ.get(f"MDI_CTAS_{kernel.upper()}")
+        return int(v) if v else self.ctas_per_sm
+
     def _gate_act(self) -> str:
         if self.cfg.mlp_class_name == "LLaMAMLP":
             return "silu_gate"
@@ -226,10 +233,6 @@ class FusedStage:
         if i >= self._trace.shape[0]:
             return None
         self._trace_names.append(name)
-        det = getattr(self, "_trace_detail", {}).get(name)
-        if det is not None:
-            self._trace[i, 6] = det.data_ptr()
-            self._trace[i, 7] = det.shape[0]
         return self._trace[i].data_ptr()
 
     def trace_step(self, builder: Any, max_records: int = 512, detail: Sequence[str] = (),
@@ -240,19 +243,30 @@ class FusedStage:
         has its input in shared memory), ``first_exit`` / ``last_exit`` and the CTA count.  Kernels named
         in ``detail`` additionally get a per-CTA table (``row["per_cta"]``: entry, ready, staged, exit in µs
         and the SM each CTA ran on)."""
+        want = set(detail)
         with torch.cuda.device(self.device):
             self._trace = torch.zeros(max_records, 8, dtype=torch.int64, device=self.device)
             self._trace[:, [0, 1, 3]] = torch.iinfo(torch.int64).max
             self._trace_names = []
-            self._trace_detail = {n: torch.zeros(detail_ctas, 8, dtype=torch.int64, device=self.device) for n in detail}
-            self._trace_detail_ctas = detail_ctas
+            table = None
+            if want:
+                # one per-CTA table per record, wired up BEFORE the launches so that nothing is enqueued
+                # between the traced kernels (extra launches would break the PDL chain being measured)
+                table = torch.zeros(max_records, detail_ctas, 8, dtype=torch.int64, device=self.device)
+                self._trace[:, 6] = table.data_ptr() + torch.arange(max_records, device=self.device) * (detail_ctas * 64)
+                self._trace[:, 7] = detail_ctas
             try:
                 builder()
                 torch.cuda.synchronize(self.device)
                 rec = self._trace[: len(self._trace_names)].cpu()
-                details = {n: t.cpu() for n, t in self._trace_detail.items()}
+                names = list(self._trace_names)
+                details = {}
+                if table is not None:
+                    for i, n in enumerate(names):
+                        if n in want or "*" in want:
+                            details[n] = table[i].cpu()
             finally:
-                names, self._trace, self._trace_names, self._trace_detail = self._trace_names, None, [], {}
+                names, self._trace, self._trace_names = list(self._trace_names), None, []
         t0 = int(rec[:, 0].min()) if len(names) else 0
         rows = []
         for i, n in enumerate(names):
@@ -262,7 +276,8 @@ class FusedStage:
             if n in details:
                 d = details[n][: min(c, details[n].shape[0])]
                 rows[-1]["per_cta"] = [{"cta": j, "sm": int(x[5]), "entry": (int(x[0]) - t0) / 1e3, "ready": (int(x[1]) - t0) / 1e3,
-                                        "staged": (int(x[2]) - t0) / 1e3, "exit": (int(x[4]) - t0) / 1e3} for j, x in enumerate(d)]
+                                        "staged": (int(x[2]) - t0) / 1e3, "exit": (int(x[4]) - t0) / 1e3,
+                                        "p6": (int(x[6]) - t0) / 1e3 if int(x[6]) else None} for j, x in enumerate(d)]
         return rows
 
     # ---- kernel sequences ------------------------------------------------------------------------
@@ -275,7 +290,7 @@ class FusedStage:
             lw.pop("W"), self.hidden_in, self.logits, self.ctx, **lw,
             norm_w=m.transformer.ln_f.weight, eps=cfg.norm_eps, unit_offset=cfg.unit_offset_norm,
             x_slot_stride=cfg.n_embd, wait_flag=self.flags.data_ptr() if wait else None,
-            status=self.status.data_ptr(), wait_max_cycles=self.wait_max_cycles, ctas_per_sm=self.ctas_per_sm,
+            status=self.status.data_ptr(), wait_max_cycles=self.wait_max_cycles, ctas_per_sm=self._ctas("lm_head"),
             use_pdl=self.use_pdl, stats=self.sample_scratch if stats else None, trace=self._tr("lm_head"))
 
     def enqueue_sample(self) -> None:
@@ -312,7 +327,7 @@ class FusedStage:
         releases its flag, or writes ``out_local[slot]``."""
         cfg, C = self.cfg, self.cfg.n_embd
         x_in, x_in_stride = (self.xa, 0) if self.is_starter else (self.hidden_in, C)
-        common = dict(ctas_per_sm=self.ctas_per_sm, use_pdl=self.use_pdl)
+        common = dict(use_pdl=self.use_pdl)
         units = self._units()
         for ui, (li, kind) in enumerate(units):
             first, last = ui == 0, ui == len(units) - 1
@@ -328,7 +343,7 @@ class FusedStage:
                     n_head=cfg.n_head, n_groups=cfg.n_query_groups, head_size=cfg.head_size,
                     rope_n_elem=cfg.rope_n_elem, max_seq=self.S, norm_w=blk.norm_1.weight, **qw,
                     eps=cfg.norm_eps, unit_offset=cfg.unit_offset_norm, x_slot_stride=x_in_stride,
-                    trace=self._tr(f"L{li}.qkv"), **wait, **common)
+                    trace=self._tr(f"L{li}.qkv"), ctas_per_sm=self._ctas("qkv"), **wait, **common)
                 ops.attn_decode(self.q, kv_layer, self.y_attn, self.part, self.tickets, self.ctx, n_head=cfg.n_head,
                                 n_groups=cfg.n_query_groups, head_size=cfg.head_size, max_seq=self.S,
                                 n_split=self.n_split, use_pdl=self.use_pdl, trace=self._tr(f"L{li}.attn"))
@@ -338,9 +353,10 @@ class FusedStage:
                 ops.linear_decode(gw.pop("W"), x_in, self.h_mlp, self.ctx, **gw, norm_w=blk.norm_2.weight,
                                   eps=cfg.norm_eps, unit_offset=cfg.unit_offset_norm, act=self._gate_act(),
                                   x_slot_stride=x_in_stride, trace=self._tr(f"L{li}.gate_up"),
-                                  **(wait if first else {}), **common)
+                                  ctas_per_sm=self._ctas("gate_up"), **(wait if first else {}), **common)
                 lw, src, name = self._w(blk.mlp.proj), self.h_mlp, f"L{li}.down"
             w_out = lw.pop("W")
+            common["ctas_per_sm"] = self._ctas("o_proj" if kind == "attn" else "down")
             res = dict(residual=x_in, res_slot_stride=x_in_stride)
             if not last:
                 ops.linear_decode(w_out, src, x_out, self.ctx, **lw, **res, trace=self._tr(name), **common)

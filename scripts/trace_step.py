@@ -46,7 +46,7 @@ def step():
 for _ in range(3):
     step()
 torch.cuda.synchronize()
-rows = st.trace_step(step, detail=[d for d in a.detail.split(",") if d])
+rows = st.trace_step(step, detail=[d for d in a.detail.split(",") if d])  # "*" = every kernel
 prev_end = None
 print(f"{'kernel':14s} {'entry':>8s} {'ready':>8s} {'staged':>8s} {'1st exit':>9s} {'last exit':>9s} {'dur':>7s} {'gap':>6s} ctas")
 for r in rows:
@@ -75,6 +75,9 @@ for r in rows:
     st_dur = [c["staged"] - c["ready"] for c in pc]
     run = [c["exit"] - c["staged"] for c in pc]
     print(f"   staging (ready->staged) p50 {S.median(st_dur):.2f} max {max(st_dur):.2f};  stream+epilogue (staged->exit) p50 {S.median(run):.2f} max {max(run):.2f}")
+    p6 = [c["p6"] - r["ready"] for c in pc if c.get("p6") is not None]
+    if p6:
+        print(f"   phase mark (main loop done) p50 {S.median(p6):.2f} max {max(p6):.2f}")
     by_cnt = collections.defaultdict(list)
     for c in pc:
         by_cnt[per_sm[c["sm"]]].append(c["exit"] - r["ready"])
