@@ -356,8 +356,7 @@ class FusedStage:
                                   ctas_per_sm=self._ctas("gate_up"), **(wait if first else {}), **common)
                 lw, src, name = self._w(blk.mlp.proj), self.h_mlp, f"L{li}.down"
             w_out = lw.pop("W")
-            common["ctas_per_sm"] = self._ctas("o_proj" if kind == "attn" else "down")
-            res = dict(residual=x_in, res_slot_stride=x_in_stride)
+            res = dict(residual=x_in, res_slot_stride=x_in_stride, ctas_per_sm=self._ctas("o_proj" if kind == "attn" else "down"))
             if not last:
                 ops.linear_decode(w_out, src, x_out, self.ctx, **lw, **res, trace=self._tr(name), **common)
                 x_in, x_in_stride = x_out, 0

@@ -1,0 +1,114 @@
+"""CPU dry run of the fused engine's launch sequences: every ``ops.*`` kernel entry point is replaced
+by a recorder that binds the call against the real Python signature, so wrong/duplicate keyword
+arguments, missing buffers and mis-ordered hops are caught without a GPU."""
+import contextlib
+import inspect
+import types
+from unittest import mock
+
+import pytest
+import torch
+
+from mdi_llm_b200 import ops
+from mdi_llm_b200.models.config import Config
+from mdi_llm_b200.models.stage import build_stage
+from mdi_llm_b200.parallel import engine as eng
+from mdi_llm_b200.parallel.engine import FusedStage, HopTarget
+
+KERNELS = ["linear_decode", "qkv_decode", "attn_decode", "embed", "sample_fast", "advance_step", "rmsnorm_rows", "gemm"]
+
+
+def _cfg(n_layer=3):
+    return Config.from_name("tiny-llama-1.1b", n_layer=n_layer, n_embd=256, n_head=4, n_query_groups=2,
+                            intermediate_size=128, vocab_size=120, padded_vocab_size=128, block_size=64)
+
+
+@contextlib.contextmanager
+def dry_ops():
+    calls = []
+    patches = []
+    for name in KERNELS:
+        real = getattr(ops, name)
+        sig = inspect.signature(real)
+
+        def rec(*a, _n=name, _sig=sig, **kw):
+            bound = _sig.bind(*a, **kw)  # TypeError on bad / duplicate / unknown arguments
+            calls.append((_n, bound.arguments))
+            if _n == "gemm":
+                if kw.get("out_ptr") is not None:
+                    return None
+                return torch.zeros(a[0].shape[0], a[1].shape[0], dtype=torch.bfloat16)
+            if _n == "rmsnorm_rows":
+                return torch.zeros_like(a[0])
+            return None
+
+        patches.append(mock.patch.object(ops, name, rec))
+    props = types.SimpleNamespace(multi_processor_count=148)
+    patches += [
+        mock.patch.object(ops, "require", lambda: None),
+        mock.patch.object(ops, "sample_scratch", lambda dev: torch.zeros(16, dtype=torch.int32)),
+        mock.patch.object(torch.cuda, "device", lambda d: contextlib.nullcontext()),
+        mock.patch.object(torch.cuda, "get_device_properties", lambda d: props),
+        mock.patch.object(torch.Tensor, "pin_memory", lambda self: self),
+    ]
+    with contextlib.ExitStack() as es:
+        for p in patches:
+            es.enter_context(p)
+        yield calls
+
+
+def _stage(role, n_blocks, **kw):
+    st = build_stage(_cfg(), role, n_blocks, **kw).to(torch.bfloat16)
+    st.max_seq_length = 32
+    return st
+
+
+@pytest.mark.parametrize("role,kw,expect_first,expect_last", [
+    ("starter", {}, "qkv_decode", "linear_decode"),
+    ("secondary:0", {}, "qkv_decode", "linear_decode"),
+    ("secondary:0", {"first_mlp_only": True}, "linear_decode", "linear_decode"),
+    ("secondary:0", {"last_attn_only": True}, "qkv_decode", "linear_decode"),
+    ("secondary:0", {"first_mlp_only": True, "last_attn_only": True}, "linear_decode", "linear_decode"),
+])
+def test_decode_launch_sequence_binds(role, kw, expect_first, expect_last):
+    with dry_ops() as calls:
+        fs = FusedStage(_stage(role, 3, **kw), n_slots=2, max_seq_length=32)
+        hop = HopTarget(0x1000, 0x2000)
+        if fs.is_starter:
+            fs.enqueue_head(wait=True)
+            fs.enqueue_sample()
+            fs.enqueue_embed(from_tokens=True)
+        n0 = len(calls)
+        fs.enqueue_blocks(hop, wait_input=True)
+        seq = calls[n0:]
+    names = [c[0] for c in seq]
+    assert names[0] == expect_first and names[-1] == expect_last
+    units = fs._units()
+    assert len(names) == sum(3 if k == "attn" else 2 for _, k in units)
+    # hop protocol: only the first kernel may wait (secondaries), only the last one signals
+    waits = [c[1].get("wait_flag") for c in seq]
+    sigs = [c[1].get("signal_flag") for c in seq]
+    assert all(w is None for w in waits[1:]) and all(s is None for s in sigs[:-1]) and sigs[-1] == 0x2000
+    assert (waits[0] is None) == fs.is_starter
+    assert seq[-1][1]["y_ptr"] == 0x1000 and seq[-1][1]["done_ctr"] is not None
+    # residual stream ping-pong: a kernel never writes the buffer it reads its residual from
+    for n, args in seq:
+        if n == "linear_decode" and args.get("residual") is not None and args.get("y") is not None:
+            assert args["y"] is not args["residual"]
+
+
+def test_local_output_and_prefill_sequences_bind():
+    with dry_ops() as calls:
+        st = _stage("secondary:0", 3, first_mlp_only=True, last_attn_only=True)
+        st.set_kv_cache(2, dtype=torch.bfloat16)
+        fs = FusedStage(st, n_slots=2, max_seq_length=32)
+        fs.enqueue_blocks(None, wait_input=False)
+        assert calls[-1][1]["y"] is fs.out_local and calls[-1][1].get("signal_flag") is None
+        calls.clear()
+        x = torch.zeros(1, 5, 256, dtype=torch.bfloat16)
+        with mock.patch.object(type(st.transformer.h[1].attn), "attend_qkv", lambda self, qkv, *a, **k: torch.zeros(1, 5, 256, dtype=torch.bfloat16)):
+            assert fs.prefill(x, torch.arange(5), 0, hop=(0x3000, 0x4000)) is None
+    gemms = [c[1] for c in calls if c[0] == "gemm"]
+    assert gemms[-1]["out_ptr"] == 0x3000 and gemms[-1]["signal_flag"] == 0x4000 and gemms[-1]["residual"] is not None
+    assert all(g.get("out_ptr") is None for g in gemms[:-1])
+    assert sum(1 for g in gemms if g.get("w2") is not None) == 2  # two MLP halves -> two gated GEMMs
