@@ -42,6 +42,7 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.mdi_qkv_decode.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, i32, i32, i32, f32, i32,
                                    vp, vp, i64, i32, i32, i32, vp, vp, vp]
     lib.mdi_set_linear_variant.argtypes = [i32]
+    lib.mdi_set_l2_prefetch_mb.argtypes = [i32]
     lib.mdi_get_linear_variant.restype = i32
     lib.mdi_attn_decode.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp]
     lib.mdi_embed.argtypes = [vp, vp, vp, i64, vp, vp, i64, i32, f32, i32, vp]
@@ -93,10 +94,18 @@ def lib() -> ctypes.CDLL:
             handle = ctypes.CDLL(str(_build.LIB))
         _declare(handle)
         _lib = handle
+        if os.environ.get("MDI_L2_PF_MB"):
+            handle.mdi_set_l2_prefetch_mb(int(os.environ["MDI_L2_PF_MB"]))
         return handle
     except BaseException as e:  # noqa: BLE001
         _load_error = e
         raise OpsError(f"cannot load {_build.LIB}: {e}") from e
+
+
+def set_l2_prefetch_mb(mb: int) -> None:
+    """L2 look-ahead of the bulk-copy decode linears: each launch asks the TMA engine to pull up to ``mb`` MiB
+    of the weights it will stream next into L2 before it waits for its input (0 = off)."""
+    lib().mdi_set_l2_prefetch_mb(int(mb))
 
 
 def set_linear_variant(v: int) -> None:
@@ -161,7 +170,7 @@ def linear_decode(
     y_ptr: Optional[int] = None, residual_ptr: Optional[int] = None, x_ptr: Optional[int] = None, variant: int = -1,
     stats: Optional[torch.Tensor] = None, trace: Optional[int] = None,
     wscale: Optional[torch.Tensor] = None, wscale2: Optional[torch.Tensor] = None,
-) -> None:
+ ctx_early: bool = False) -> None:
     """``y = epilogue(W @ norm?(x))`` for one token.  ``*_ptr`` overrides let the output /
     residual / input live in peer-mapped (other GPU) memory that has no torch tensor.
     With ``wscale`` (fp32 ``[N, K/128]``) ``W`` (and ``W2``/``wscale2``) are fp8-e4m3 block-scaled."""
@@ -178,7 +187,7 @@ def linear_decode(
         ptr(W), ptr(W2), ptr(bias), ptr(bias2), x_ptr if x_ptr is not None else ptr(x), ptr(norm_w),
         residual_ptr if residual_ptr is not None else ptr(residual), y_ptr if y_ptr is not None else ptr(y),
         ptr(ctx), x_slot_stride, res_slot_stride, y_slot_stride, N, K, eps, int(unit_offset), ACT[act], out_fp32,
-        wait_flag, status, wait_max_cycles, signal_flag, done_ctr, ctas_per_sm, int(use_pdl), variant, hist, amax,
+        wait_flag, status, wait_max_cycles, signal_flag, done_ctr, ctas_per_sm, int(use_pdl) | (2 if ctx_early else 0), variant, hist, amax,
         trace, ptr(wscale), ptr(wscale2), stream_ptr()), "linear_decode")
 
 
@@ -188,8 +197,7 @@ def qkv_decode(
     bias: Optional[torch.Tensor] = None, norm_w: Optional[torch.Tensor] = None, eps: float = 1e-5,
     unit_offset: bool = False, x_slot_stride: int = 0, wait_flag: Optional[int] = None, status: Optional[int] = None,
     wait_max_cycles: int = 0, ctas_per_sm: int = 4, use_pdl: bool = False, x_ptr: Optional[int] = None,
-    variant: int = -1, trace: Optional[int] = None, wscale: Optional[torch.Tensor] = None,
-) -> None:
+    variant: int = -1, trace: Optional[int] = None, wscale: Optional[torch.Tensor] = None, ctx_early: bool = False) -> None:
     if wscale is None:
         _bf16(W, "W")
     else:
@@ -199,7 +207,7 @@ def qkv_decode(
     check(lib().mdi_qkv_decode(
         ptr(W), ptr(bias), x_ptr if x_ptr is not None else ptr(x), ptr(norm_w), ptr(cos), ptr(sin), ptr(q_out),
         ptr(kv_layer), ptr(ctx), x_slot_stride, W.shape[1], n_head, n_groups, head_size, rope_n_elem, max_seq, eps,
-        int(unit_offset), wait_flag, status, wait_max_cycles, ctas_per_sm, int(use_pdl), variant, trace, ptr(wscale), stream_ptr()),
+        int(unit_offset), wait_flag, status, wait_max_cycles, ctas_per_sm, int(use_pdl) | (2 if ctx_early else 0), variant, trace, ptr(wscale), stream_ptr()),
         "qkv_decode")
 
 

@@ -164,6 +164,12 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
+// L2 prefetch through the TMA engine (no shared-memory destination): extends the look-ahead of a
+// weight stream beyond what the shared-memory ring can hold
+__device__ __forceinline__ void bulk_prefetch_l2(const void* gsrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gsrc), "r"(bytes) : "memory");
+}
+
 // ---- device-side tracer ---------------------------------------------------------------------------
 // Each traced kernel owns one record of 8 x u64 (ns, %globaltimer):
 //   [0] min entry  [1] min "input ready" (after PDL/hop wait)  [2] max "staged"  [3] min exit  [4] max exit  [5] #CTAs

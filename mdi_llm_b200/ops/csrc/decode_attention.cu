@@ -6,20 +6,22 @@
 // query heads of one group from a single pass over that group's K/V (GQA packing: 4x fewer
 // bytes for Llama-3) and only the live prefix [0, pos] is scanned.
 //
-// One kernel, grid (G, n_split), 4 warps per CTA, a warp owns 32-position tiles:
+// One kernel, grid (G, n_split), 8 warps per CTA, a warp owns 16-position tiles:
 //   * the context is cut into spans of >= 128 positions, so short contexts use few CTAs and
 //     the others exit at once (the grid is fixed at graph-capture time, the length is not);
-//   * all K loads of a tile (16 x 16 B per lane) and the V loads (batches of 16 rows) are issued
-//     before they are consumed — decode attention is latency-, not bandwidth-bound;
+//   * ALL K and V loads of a tile are issued together before anything is consumed — decode attention
+//     is a latency chain (ctx -> q -> K -> softmax -> V -> merge), not a bandwidth problem; small
+//     tiles over many warps keep the serial instruction count per warp low;
 //   * the last CTA of a group to finish merges the spans (atomic ticket) and writes bf16
 //     y[H*hs] directly: no separate combine launch.
 #include "common.cuh"
 
 namespace mdi {
 
-constexpr int ATT_WARPS = 4;
+constexpr int ATT_WARPS = 8;
 constexpr int ATT_THREADS = ATT_WARPS * 32;
-constexpr int ATT_TILE = 32;
+constexpr int ATT_TILE = 16;
+constexpr int ATT_NPASS = ATT_TILE / 8;  // QK passes per tile (4 lanes per position, 8 positions per pass)
 
 struct AttnArgs {
   const bf16* q;   // [H * hs] (already roped)
@@ -38,8 +40,9 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const AttnArgs
   constexpr int DPL = HS / 32;   // output dims per lane in the PV phase
   constexpr int QDIM = HS / 4;   // dims per lane in the QK phase (4 lanes per position)
   constexpr int KV4 = QDIM / 8;  // uint4 loads per lane per position
-  constexpr int VB = (QPK >= 8 && HS >= 128) ? 8 : 16;  // V rows per load batch (register budget)
-  constexpr int KPASS = (QPK >= 8 && HS >= 128) ? 1 : 4;  // K passes whose loads are batched
+  constexpr int VB = (QPK >= 8 && HS >= 128) ? 8 : ATT_TILE;  // V rows per load batch (register budget)
+  constexpr int KPASS = (QPK >= 8 && HS >= 128) ? 1 : ATT_NPASS;  // K passes whose loads are batched
+  constexpr bool V_EARLY = (VB == ATT_TILE);  // the whole V tile is requested together with the K tile
   __shared__ __align__(16) float q_s[QPK][HS];
   __shared__ float s_s[ATT_WARPS][QPK][ATT_TILE];
   __shared__ float mrg_m[ATT_WARPS][QPK], mrg_l[ATT_WARPS][QPK];
@@ -82,9 +85,19 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const AttnArgs
 
   for (int t = t_lo + warp; t < t_hi; t += ATT_WARPS) {
     const int p0 = t * ATT_TILE;
-    // ---- issue the K loads of KPASS passes (8 positions each) up-front, then consume --------------
+    // ---- issue the K loads of KPASS passes (8 positions each) and the V rows up-front, then consume --
+    uint32_t vv[VB][DPL / 2];
+    auto load_v = [&](int half) {
 #pragma unroll
-    for (int pg = 0; pg < 4 / KPASS; ++pg) {
+      for (int r = 0; r < VB; ++r) {
+        const int pos = min(p0 + half * VB + r, L - 1);  // masked rows have p == 0
+        const uint32_t* vr = reinterpret_cast<const uint32_t*>(vbase + (size_t)pos * HS + lane * DPL);
+#pragma unroll
+        for (int w = 0; w < DPL / 2; ++w) vv[r][w] = __ldg(vr + w);
+      }
+    };
+#pragma unroll
+    for (int pg = 0; pg < ATT_NPASS / KPASS; ++pg) {
       uint4 kk[KPASS][KV4];
 #pragma unroll
       for (int pp = 0; pp < KPASS; ++pp) {
@@ -93,6 +106,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const AttnArgs
 #pragma unroll
         for (int v = 0; v < KV4; ++v) kk[pp][v] = __ldg(kr + v);
       }
+      if (V_EARLY && pg == 0) load_v(0);
 #pragma unroll
       for (int pp = 0; pp < KPASS; ++pp) {
         const int pj = (pg * KPASS + pp) * 8 + (lane >> 2), pos = p0 + pj, qd = (lane & 3) * QDIM;
@@ -127,7 +141,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const AttnArgs
     // ---- online softmax update: lane == position inside the tile --------------------------
 #pragma unroll
     for (int h = 0; h < QPK; ++h) {
-      const float s = s_s[warp][h][lane];
+      const float s = lane < ATT_TILE ? s_s[warp][h][lane] : -INFINITY;
       const float m_new = fmaxf(m[h], warp_max(s));
       const float p = (s == -INFINITY) ? 0.f : exp2f(s - m_new);
       const float corr = (m[h] == -INFINITY) ? 0.f : exp2f(m[h] - m_new);
@@ -135,20 +149,13 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const AttnArgs
       m[h] = m_new;
 #pragma unroll
       for (int d = 0; d < DPL; ++d) acc[h][d] *= corr;
-      s_s[warp][h][lane] = p;
+      if (lane < ATT_TILE) s_s[warp][h][lane] = p;
     }
     __syncwarp();
-    // ---- PV: lane owns DPL consecutive output dims; rows loaded 16 at a time -------------------
+    // ---- PV: lane owns DPL consecutive output dims ---------------------------------------------------
 #pragma unroll
     for (int half = 0; half < ATT_TILE / VB; ++half) {
-      uint32_t vv[VB][DPL / 2];
-#pragma unroll
-      for (int r = 0; r < VB; ++r) {
-        const int pos = min(p0 + half * VB + r, L - 1);  // masked rows have p == 0
-        const uint32_t* vr = reinterpret_cast<const uint32_t*>(vbase + (size_t)pos * HS + lane * DPL);
-#pragma unroll
-        for (int w = 0; w < DPL / 2; ++w) vv[r][w] = __ldg(vr + w);
-      }
+      if (!V_EARLY) load_v(half);
 #pragma unroll
       for (int r = 0; r < VB; ++r) {
 #pragma unroll

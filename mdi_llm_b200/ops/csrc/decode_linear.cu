@@ -212,6 +212,8 @@ struct StreamArgs {
   // scale per 128 consecutive K elements of every row ([N, K/128]); null = bf16 weights
   const float* wscale;
   const float* wscale2;
+  int l2_pf_chunks;  // bulk kernels: chunk pairs per warp prefetched into L2 beyond the smem ring (0 = off)
+  int ctx_early;     // ctx was written >= 2 launches ago: slot/pos may be read before the PDL wait
 };
 
 __device__ __forceinline__ uint32_t float_key(float f) {  // monotone: larger float -> larger key
@@ -220,6 +222,7 @@ __device__ __forceinline__ uint32_t float_key(float f) {  // monotone: larger fl
 }
 
 enum Mode { MODE_PLAIN = 0, MODE_GATED = 1, MODE_QKV = 2 };
+static int g_l2_prefetch_mb = 0;  // see mdi_set_l2_prefetch_mb
 
 // item -> the two weight rows a warp streams together
 template <int MODE>
@@ -417,15 +420,29 @@ __global__ void __launch_bounds__(LIN_THREADS, STAGES == 2 ? 3 : (STAGES == 3 ? 
   };
   // Fill the WHOLE ring before waiting for the input: the previous kernel's tail (and, for o_proj, the
   // attention kernel's latency chain) then overlaps with up to STAGES x 4 KB per warp of weight traffic.
-  if (lane == 0)
+  if (lane == 0) {
     for (int f = 0; f < min(STAGES, total); ++f) issue(f);
+    // ... and ask the TMA engine to pull the next chunks into L2, so that the ring refills issued after
+    // the wait hit L2 (lower latency, ~2x HBM bandwidth) instead of DRAM
+    for (int f = STAGES; f < min(total, STAGES + a.l2_pf_chunks); ++f) {
+      const int ii = f / n_chunks, c = f - ii * n_chunks;
+      const bf16 *wa, *wb;
+      item_rows<MODE>(a, gw + ii * n_gw, wa, wb);
+      const int k0 = c * TS_CHUNK;
+      const uint32_t bytes = (uint32_t)min(TS_CHUNK, a.K - k0) * 2u;
+      bulk_prefetch_l2(wa + k0, bytes);
+      bulk_prefetch_l2(wb + k0, bytes);
+    }
+  }
   unsigned int* hist_s = stats_begin(a, reinterpret_cast<unsigned char*>(bars - warp * STAGES + LIN_WARPS * STAGES));
   unsigned long long best = 0ull;
 
+  int slot = 0, pos = 0;
+  if (a.ctx_early && a.ctx) { slot = a.ctx[MDI_CTX_SLOT]; pos = a.ctx[MDI_CTX_POS]; }  // off the post-wait chain
   pdl_wait_prior();
   hop_wait(a.wait, a.ctx);
   trace_mark(a.trace, 1, true);
-  const int slot = a.ctx ? a.ctx[MDI_CTX_SLOT] : 0, pos = a.ctx ? a.ctx[MDI_CTX_POS] : 0;
+  if (!a.ctx_early && a.ctx) { slot = a.ctx[MDI_CTX_SLOT]; pos = a.ctx[MDI_CTX_POS]; }
   stage_input(a.x + (size_t)slot * a.x_slot_stride, a.norm_w, a.eps, a.unit_offset, a.K, xs, red);
   trace_mark(a.trace, 2, false);
   pdl_launch_dependents();
@@ -650,9 +667,14 @@ static int launch_stream(const StreamArgs& a, int variant, int ctas_per_sm, int 
   if (smem > 227 * 1024) return launch_stream<MODE>(a, 0, ctas_per_sm, use_pdl, stream);  // huge K: LDG path
   const int per_sm = variant == 1 ? 1 : max(1, min(ctas_per_sm, (int)((227 * 1024) / (smem + 1024))));
   const int grid = grid_override > 0 ? min(grid_override, max_useful) : max(1, min(sms * per_sm, max_useful));
-  if (variant == 1) return launch_pdl(stream_bulk_kernel<MODE, 4>, a, grid, smem, stream, use_pdl);
-  if (variant == 3) return launch_pdl(stream_bulk_kernel<MODE, 3>, a, grid, smem, stream, use_pdl);
-  return launch_pdl(stream_bulk_kernel<MODE, 2>, a, grid, smem, stream, use_pdl);
+  StreamArgs b = a;
+  if (g_l2_prefetch_mb > 0) {  // bytes of L2 look-ahead per launch, spread evenly over the warps
+    const size_t per_step = (size_t)grid * LIN_WARPS * 2 * TS_CHUNK * 2;
+    b.l2_pf_chunks = (int)min((size_t)16, ((size_t)g_l2_prefetch_mb << 20) / per_step);
+  }
+  if (variant == 1) return launch_pdl(stream_bulk_kernel<MODE, 4>, b, grid, smem, stream, use_pdl);
+  if (variant == 3) return launch_pdl(stream_bulk_kernel<MODE, 3>, b, grid, smem, stream, use_pdl);
+  return launch_pdl(stream_bulk_kernel<MODE, 2>, b, grid, smem, stream, use_pdl);
 }
 
 static int g_default_variant = 2;  // bulk-copy ring x2 stages: fastest in-pipeline (profiles/README.md)
@@ -664,6 +686,7 @@ using namespace mdi;
 extern "C" {
 
 void mdi_set_linear_variant(int v) { g_default_variant = v; }
+void mdi_set_l2_prefetch_mb(int mb) { g_l2_prefetch_mb = mb; }
 int mdi_get_linear_variant() { return g_default_variant; }
 
 int mdi_linear_decode(const void* W, const void* W2, const void* bias, const void* bias2, const void* x,
@@ -683,6 +706,7 @@ int mdi_linear_decode(const void* W, const void* W2, const void* bias, const voi
   a.signal = HopSignal{signal_flag, done_ctr};
   a.n_items = W2 ? N : (N + 1) / 2;
   a.hist = hist; a.amax = amax; a.trace = trace; a.wscale = wscale; a.wscale2 = wscale2;
+  a.ctx_early = (use_pdl >> 1) & 1; use_pdl &= 1;  // launch flags: bit 0 = PDL, bit 1 = ctx readable before the wait
   if (variant < 0) variant = g_default_variant;
   if (W2) return launch_stream<MODE_GATED>(a, variant, ctas_per_sm, use_pdl, stream);
   return launch_stream<MODE_PLAIN>(a, variant, ctas_per_sm, use_pdl, stream);
@@ -703,6 +727,7 @@ int mdi_qkv_decode(const void* W, const void* bias, const void* x, const void* n
   a.wait = HopWait{wait_flag, status, wait_max_cycles};
   a.signal = HopSignal{nullptr, nullptr};
   a.trace = trace; a.wscale = wscale;
+  a.ctx_early = (use_pdl >> 1) & 1; use_pdl &= 1;
   a.n_items = (n_head + 2 * n_groups) * (head_size / 2);
   if (variant < 0) variant = g_default_variant;
   return launch_stream<MODE_QKV>(a, variant, ctas_per_sm, use_pdl, stream);

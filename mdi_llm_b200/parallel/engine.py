@@ -343,7 +343,7 @@ class FusedStage:
                     n_head=cfg.n_head, n_groups=cfg.n_query_groups, head_size=cfg.head_size,
                     rope_n_elem=cfg.rope_n_elem, max_seq=self.S, norm_w=blk.norm_1.weight, **qw,
                     eps=cfg.norm_eps, unit_offset=cfg.unit_offset_norm, x_slot_stride=x_in_stride,
-                    trace=self._tr(f"L{li}.qkv"), ctas_per_sm=self._ctas("qkv"), **wait, **common)
+                    trace=self._tr(f"L{li}.qkv"), ctas_per_sm=self._ctas("qkv"), ctx_early=not first, **wait, **common)
                 ops.attn_decode(self.q, kv_layer, self.y_attn, self.part, self.tickets, self.ctx, n_head=cfg.n_head,
                                 n_groups=cfg.n_query_groups, head_size=cfg.head_size, max_seq=self.S,
                                 n_split=self.n_split, use_pdl=self.use_pdl, trace=self._tr(f"L{li}.attn"))
@@ -353,10 +353,12 @@ class FusedStage:
                 ops.linear_decode(gw.pop("W"), x_in, self.h_mlp, self.ctx, **gw, norm_w=blk.norm_2.weight,
                                   eps=cfg.norm_eps, unit_offset=cfg.unit_offset_norm, act=self._gate_act(),
                                   x_slot_stride=x_in_stride, trace=self._tr(f"L{li}.gate_up"),
-                                  ctas_per_sm=self._ctas("gate_up"), **(wait if first else {}), **common)
+                                  ctas_per_sm=self._ctas("gate_up"), ctx_early=not first,
+                                  **(wait if first else {}), **common)
                 lw, src, name = self._w(blk.mlp.proj), self.h_mlp, f"L{li}.down"
             w_out = lw.pop("W")
-            res = dict(residual=x_in, res_slot_stride=x_in_stride, ctas_per_sm=self._ctas("o_proj" if kind == "attn" else "down"))
+            res = dict(residual=x_in, res_slot_stride=x_in_stride, ctx_early=True,  # never the first launch after advance_step
+                       ctas_per_sm=self._ctas("o_proj" if kind == "attn" else "down"))
             if not last:
                 ops.linear_decode(w_out, src, x_out, self.ctx, **lw, **res, trace=self._tr(name), **common)
                 x_in, x_in_stride = x_out, 0
