@@ -10,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-from test_engine_gpu import _cfg, _stages  # noqa: E402
+from test_engine_gpu import _cfg, _half_stages, _stages  # noqa: E402
 from mdi_llm_b200.parallel.pipeline import DevicePipeline  # noqa: E402
 from mdi_llm_b200.parallel.scheduler import SamplingParams  # noqa: E402
 
@@ -24,7 +24,11 @@ def main():
     mode = sys.argv[1] if len(sys.argv) > 1 else "device"
     n_new = int(sys.argv[2]) if len(sys.argv) > 2 else 8
     cfg = _cfg(n_layer=max(6, world))
-    _, stages = _stages(cfg, world, device=[f"cuda:{local}"] * world)  # every rank materialises only its own use
+    if len(sys.argv) > 3 and sys.argv[3] == "half":  # boundaries inside layers (attention | MLP units)
+        units = [3] + [2] * (world - 2) + [2 * cfg.n_layer - 3 - 2 * (world - 2)]
+        stages = _half_stages(cfg, units, [f"cuda:{local}"] * world)
+    else:
+        _, stages = _stages(cfg, world, device=[f"cuda:{local}"] * world)  # every rank materialises only its own use
     stage = stages[rank]
     n_samples = world + 1
     prompts = [torch.tensor([1, 10 + i, 20, 30 + i, 7][: 4 + i % 2]) for i in range(n_samples)]

@@ -11,11 +11,11 @@ pytestmark = [pytest.mark.gpu, pytest.mark.multigpu]
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _run(world, mode, port):
+def _run(world, mode, port, *extra):
     if torch.cuda.device_count() < world:
         pytest.skip("not enough GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
-           "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "_mp_pipeline_worker.py"), mode]
+           "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "_mp_pipeline_worker.py"), mode, *extra]
     p = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT)
     lines = [ln for ln in p.stdout.splitlines() if ln.startswith("MP_RESULT ")]
     assert lines, f"worker produced no result\nstdout:\n{p.stdout[-2000:]}\nstderr:\n{p.stderr[-3000:]}"
@@ -31,3 +31,10 @@ def test_ipc_ring_device_mode_matches_single_gpu(world):
 
 def test_ipc_ring_host_fed_mode_matches_single_gpu():
     _run(2, "host", 29650)
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_ipc_ring_half_layer_boundaries(world):
+    """Stage boundaries inside layers: o_proj carries the hop out, gate/up acquires it (fused prefill hop
+    from the attention-output GEMM included)."""
+    _run(world, "device", 29660 + world, "8", "half")
