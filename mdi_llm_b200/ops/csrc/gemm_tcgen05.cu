@@ -98,23 +98,33 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, const Gem
 
 // GATED: two B operands share the A tile; accumulators live side by side in TMEM (columns [0,BLOCK_N)
 // and [BLOCK_N, 2*BLOCK_N)) and the epilogue writes act(acc0) * acc1 — SwiGLU / GeGLU in one pass.
+//
+// Persistent: one CTA per SM walks the tile list (m fastest, so the CTAs that run together share B tiles
+// through L2).  The accumulator is double-buffered in TMEM: while the epilogue warps drain tile i
+// (tcgen05.ld -> bias/act/residual -> 16-byte stores), the MMA warp is already accumulating tile i+1 in
+// the other buffer and the TMA warp keeps the shared-memory ring full across tile boundaries.
 template <int BLOCK_N, bool GATED>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(const __grid_constant__ GemmParams p) {
   extern __shared__ __align__(1024) unsigned char gemm_smem[];
   constexpr int A_BYTES = GEMM_BLOCK_M * GEMM_BLOCK_K * 2;
   constexpr int B_BYTES = (GATED ? 2 : 1) * BLOCK_N * GEMM_BLOCK_K * 2;
-  constexpr int TMEM_COLS = (GATED ? 2 : 1) * BLOCK_N;
+  constexpr int ACC_COLS = (GATED ? 2 : 1) * BLOCK_N;  // TMEM columns of one accumulator buffer
+  constexpr int TMEM_COLS = 2 * ACC_COLS;              // two buffers (power of two, <= 512)
+  static_assert(TMEM_COLS <= 512, "accumulators exceed TMEM");
   // carve: [A stages][B stages][barriers][tmem ptr]
   unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(gemm_smem) + 1023) & ~uintptr_t(1023));
   unsigned char* smem_a = base;
   unsigned char* smem_b = base + GEMM_STAGES * A_BYTES;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_b + GEMM_STAGES * B_BYTES);
   uint64_t* empty_bar = full_bar + GEMM_STAGES;
-  uint64_t* tmem_full_bar = empty_bar + GEMM_STAGES;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* tmem_full_bar = empty_bar + GEMM_STAGES;  // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;        // [2]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * GEMM_BLOCK_M, n0 = blockIdx.y * BLOCK_N;
+  const int tiles_m = (p.M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M;
+  const int tiles_n = (p.N + BLOCK_N - 1) / BLOCK_N;
+  const int n_tiles = tiles_m * tiles_n;
   const int num_k_blocks = (p.K + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K;
 
   if (warp == 0 && lane == 0) {
@@ -124,10 +134,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < GEMM_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    mbar_init(tmem_full_bar, 1);
+    for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full_bar[b], 1); mbar_init(&tmem_empty_bar[b], 4); }
     mbar_fence_init();
   }
-  if (warp == 2) {  // whole warp: allocate the accumulator's TMEM columns (power of two >= 32)
+  if (warp == 2) {  // whole warp: allocate both accumulator buffers
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "n"(TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -137,111 +147,131 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
   const uint32_t tmem_base = *tmem_ptr_smem;
 
   if (warp == 0) {
-    // ===== TMA producer =====
+    // ===== TMA producer: the ring runs straight through tile boundaries =====
     if (lane == 0) {
-      for (int kb = 0; kb < num_k_blocks; ++kb) {
-        const int s = kb % GEMM_STAGES;
-        const uint32_t phase = (kb / GEMM_STAGES) & 1;
-        mbar_wait(&empty_bar[s], phase ^ 1);
-        mbar_expect_tx(&full_bar[s], A_BYTES + B_BYTES);
-        tma_load_2d(smem_a + s * A_BYTES, &p.tma_a, &full_bar[s], kb * GEMM_BLOCK_K, m0);
-        tma_load_2d(smem_b + s * B_BYTES, &p.tma_b, &full_bar[s], kb * GEMM_BLOCK_K, n0);
-        if (GATED) tma_load_2d(smem_b + s * B_BYTES + B_BYTES / 2, &p.tma_b2, &full_bar[s], kb * GEMM_BLOCK_K, n0);
+      int it = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int m0 = (tile % tiles_m) * GEMM_BLOCK_M, n0 = (tile / tiles_m) * BLOCK_N;
+        for (int kb = 0; kb < num_k_blocks; ++kb, ++it) {
+          const int s = it % GEMM_STAGES;
+          const uint32_t phase = (it / GEMM_STAGES) & 1;
+          mbar_wait(&empty_bar[s], phase ^ 1);
+          mbar_expect_tx(&full_bar[s], A_BYTES + B_BYTES);
+          tma_load_2d(smem_a + s * A_BYTES, &p.tma_a, &full_bar[s], kb * GEMM_BLOCK_K, m0);
+          tma_load_2d(smem_b + s * B_BYTES, &p.tma_b, &full_bar[s], kb * GEMM_BLOCK_K, n0);
+          if (GATED) tma_load_2d(smem_b + s * B_BYTES + B_BYTES / 2, &p.tma_b2, &full_bar[s], kb * GEMM_BLOCK_K, n0);
+        }
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
     // instruction descriptor (cute::UMMA::InstrDescriptor): fp32 accumulate, bf16 x bf16, both K-major
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(GEMM_BLOCK_M >> 4) << 24);
-    for (int kb = 0; kb < num_k_blocks; ++kb) {
-      const int s = kb % GEMM_STAGES;
-      const uint32_t phase = (kb / GEMM_STAGES) & 1;
-      mbar_wait(&full_bar[s], phase);
+    int it = 0, lt = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
+      const int acc = lt & 1;
+      const uint32_t tmem_acc = tmem_base + (uint32_t)(acc * ACC_COLS);
+      mbar_wait(&tmem_empty_bar[acc], ((lt >> 1) & 1) ^ 1);  // the epilogue has drained this buffer
       tcgen05_fence_after();
-      if (lane == 0) {
-        const uint32_t a_addr = smem_u32(smem_a + s * A_BYTES), b_addr = smem_u32(smem_b + s * B_BYTES);
+      for (int kb = 0; kb < num_k_blocks; ++kb, ++it) {
+        const int s = it % GEMM_STAGES;
+        const uint32_t phase = (it / GEMM_STAGES) & 1;
+        mbar_wait(&full_bar[s], phase);
+        tcgen05_fence_after();
+        if (lane == 0) {
+          const uint32_t a_addr = smem_u32(smem_a + s * A_BYTES), b_addr = smem_u32(smem_b + s * B_BYTES);
 #pragma unroll
-        for (int k = 0; k < GEMM_BLOCK_K / UMMA_K; ++k) {
-          const uint64_t da = make_smem_desc(a_addr + k * p.k_step_bytes, p);
-          const uint64_t db = make_smem_desc(b_addr + k * p.k_step_bytes, p);
-          tcgen05_mma_f16(tmem_base, da, db, idesc, (kb | k) ? 1u : 0u);
-          if (GATED) {
-            const uint64_t db2 = make_smem_desc(b_addr + B_BYTES / 2 + k * p.k_step_bytes, p);
-            tcgen05_mma_f16(tmem_base + BLOCK_N, da, db2, idesc, (kb | k) ? 1u : 0u);
+          for (int k = 0; k < GEMM_BLOCK_K / UMMA_K; ++k) {
+            const uint64_t da = make_smem_desc(a_addr + k * p.k_step_bytes, p);
+            const uint64_t db = make_smem_desc(b_addr + k * p.k_step_bytes, p);
+            tcgen05_mma_f16(tmem_acc, da, db, idesc, (kb | k) ? 1u : 0u);
+            if (GATED) {
+              const uint64_t db2 = make_smem_desc(b_addr + B_BYTES / 2 + k * p.k_step_bytes, p);
+              tcgen05_mma_f16(tmem_acc + BLOCK_N, da, db2, idesc, (kb | k) ? 1u : 0u);
+            }
           }
+          tcgen05_commit(&empty_bar[s]);                            // stage reusable once these MMAs retire
+          if (kb == num_k_blocks - 1) tcgen05_commit(&tmem_full_bar[acc]);  // accumulator complete
         }
-        tcgen05_commit(&empty_bar[s]);                       // stage reusable once these MMAs retire
-        if (kb == num_k_blocks - 1) tcgen05_commit(tmem_full_bar);  // accumulator complete
+        __syncwarp();
       }
-      __syncwarp();
     }
   } else if (warp >= 4) {
     // ===== epilogue: TMEM -> registers -> bf16 global =====
     const int ew = warp - 4;  // TMEM lanes [32*ew, 32*ew + 32) belong to this warp
-    mbar_wait(tmem_full_bar, 0);
-    tcgen05_fence_after();
-    const int row = m0 + ew * 32 + lane;
     const bool vec_ok = (p.N % 8 == 0);
+    int lt = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
+      const int m0 = (tile % tiles_m) * GEMM_BLOCK_M, n0 = (tile / tiles_m) * BLOCK_N;
+      const int acc = lt & 1;
+      const uint32_t tmem_acc = tmem_base + (uint32_t)(acc * ACC_COLS) + ((uint32_t)(ew * 32) << 16);
+      mbar_wait(&tmem_full_bar[acc], (lt >> 1) & 1);
+      tcgen05_fence_after();
+      const int row = m0 + ew * 32 + lane;
 #pragma unroll 1
-    for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-      uint32_t acc[32];
-      tmem_ld_32x32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)c0, acc);
-      const int col0 = n0 + c0;
-      if (GATED) {
-        uint32_t acc2[32];
-        tmem_ld_32x32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(BLOCK_N + c0), acc2);
+      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+        uint32_t acc_r[32];
+        tmem_ld_32x32(tmem_acc + (uint32_t)c0, acc_r);
+        const int col0 = n0 + c0;
+        if (GATED) {
+          uint32_t acc2[32];
+          tmem_ld_32x32(tmem_acc + (uint32_t)(BLOCK_N + c0), acc2);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float g = __uint_as_float(acc[j]), u = __uint_as_float(acc2[j]);
-          if (col0 + j < p.N) {
-            if (p.bias) g += __bfloat162float(p.bias[col0 + j]);
-            if (p.bias2) u += __bfloat162float(p.bias2[col0 + j]);
-          }
-          // eager semantics: both projections are rounded to bf16 before the activation and the product
-          g = round_bf16(g); u = round_bf16(u);
-          acc[j] = __float_as_uint(round_bf16(apply_act(g, p.act)) * u);
-        }
-      }
-      if (row < p.M && col0 < p.N) {
-        bf16* crow = p.C + (size_t)row * p.N + col0;
-        const bf16* rrow = p.residual ? p.residual + (size_t)row * p.N + col0 : nullptr;
-        if (vec_ok && col0 + 32 <= p.N) {
-          // 4 x 16-byte stores per thread (64 contiguous bytes of one output row): full sectors on the
-          // wire when C is peer memory
-#pragma unroll
-          for (int v = 0; v < 4; ++v) {
-            float f[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              f[j] = __uint_as_float(acc[v * 8 + j]);
-              if (!GATED && p.bias) f[j] += __bfloat162float(p.bias[col0 + v * 8 + j]);
+          for (int j = 0; j < 32; ++j) {
+            float g = __uint_as_float(acc_r[j]), u = __uint_as_float(acc2[j]);
+            if (col0 + j < p.N) {
+              if (p.bias) g += __bfloat162float(p.bias[col0 + j]);
+              if (p.bias2) u += __bfloat162float(p.bias2[col0 + j]);
             }
-            if (rrow) {  // eager semantics: linear output rounded to bf16, then added to the bf16 residual
-              const uint4 r4 = *reinterpret_cast<const uint4*>(rrow + v * 8);
-              const uint32_t rw[4] = {r4.x, r4.y, r4.z, r4.w};
+            // eager semantics: both projections are rounded to bf16 before the activation and the product
+            g = round_bf16(g); u = round_bf16(u);
+            acc_r[j] = __float_as_uint(round_bf16(apply_act(g, p.act)) * u);
+          }
+        }
+        if (row < p.M && col0 < p.N) {
+          bf16* crow = p.C + (size_t)row * p.N + col0;
+          const bf16* rrow = p.residual ? p.residual + (size_t)row * p.N + col0 : nullptr;
+          if (vec_ok && col0 + 32 <= p.N) {
+            // 4 x 16-byte stores per thread (64 contiguous bytes of one output row): full sectors on the
+            // wire when C is peer memory
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                f[2 * j] = round_bf16(f[2 * j]) + bf16lo(rw[j]);
-                f[2 * j + 1] = round_bf16(f[2 * j + 1]) + bf16hi(rw[j]);
+            for (int v = 0; v < 4; ++v) {
+              float f[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                f[j] = __uint_as_float(acc_r[v * 8 + j]);
+                if (!GATED && p.bias) f[j] += __bfloat162float(p.bias[col0 + v * 8 + j]);
               }
+              if (rrow) {  // eager semantics: linear output rounded to bf16, then added to the bf16 residual
+                const uint4 r4 = *reinterpret_cast<const uint4*>(rrow + v * 8);
+                const uint32_t rw[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  f[2 * j] = round_bf16(f[2 * j]) + bf16lo(rw[j]);
+                  f[2 * j + 1] = round_bf16(f[2 * j + 1]) + bf16hi(rw[j]);
+                }
+              }
+              uint4 o;
+              o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]);
+              o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
+              *reinterpret_cast<uint4*>(crow + v * 8) = o;
             }
-            uint4 o;
-            o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]);
-            o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
-            *reinterpret_cast<uint4*>(crow + v * 8) = o;
-          }
-        } else {
+          } else {
 #pragma unroll 1
-          for (int j = 0; j < 32 && col0 + j < p.N; ++j) {
-            float v0 = __uint_as_float(acc[j]);
-            if (!GATED && p.bias) v0 += __bfloat162float(p.bias[col0 + j]);
-            if (rrow) v0 = round_bf16(v0) + __bfloat162float(rrow[j]);
-            crow[j] = __float2bfloat16_rn(v0);
+            for (int j = 0; j < 32 && col0 + j < p.N; ++j) {
+              float v0 = __uint_as_float(acc_r[j]);
+              if (!GATED && p.bias) v0 += __bfloat162float(p.bias[col0 + j]);
+              if (rrow) v0 = round_bf16(v0) + __bfloat162float(rrow[j]);
+              crow[j] = __float2bfloat16_rn(v0);
+            }
           }
         }
       }
+      // this warp is done reading the buffer: hand it back to the MMA warp (4 arrivals = 4 epilogue warps)
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
     }
-    tcgen05_fence_before();
   }
   __syncthreads();
   if (warp == 2) {
@@ -306,7 +336,7 @@ extern "C" int mdi_gemm_bf16_ex(const void* A, const void* W, const void* W2, vo
   p.k_step_bytes = k_step > 0 ? (unsigned)k_step : 32u;
   const bool gated = W2 != nullptr;
   if (block_n != 64 && block_n != 128 && block_n != 256) block_n = 128;
-  if (gated && block_n == 256) block_n = 128;  // two accumulators: 2 x BLOCK_N <= 512 TMEM columns, smem budget
+  if (gated && block_n == 256) block_n = 128;  // 2 buffers x 2 accumulators x BLOCK_N <= 512 TMEM columns
   int rc = make_map(&p.tma_a, A, M, K, GEMM_BLOCK_M);
   if (rc) return rc;
   rc = make_map(&p.tma_b, W, N, K, block_n);
@@ -314,7 +344,8 @@ extern "C" int mdi_gemm_bf16_ex(const void* A, const void* W, const void* W2, vo
   rc = make_map(&p.tma_b2, gated ? W2 : W, N, K, block_n);
   if (rc) return rc;
   const size_t smem = 1024 + (size_t)GEMM_STAGES * (GEMM_BLOCK_M + (gated ? 2 : 1) * block_n) * GEMM_BLOCK_K * 2 + 128;
-  dim3 grid((M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M, (N + block_n - 1) / block_n);
+  const int n_tiles = ((M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M) * ((N + block_n - 1) / block_n);
+  dim3 grid(min(n_tiles, device_sm_count()));  // persistent: one CTA per SM walks the tile list
   cudaError_t e;
 #define MDI_GEMM_LAUNCH(BN, G)                                                                                        \
   e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \

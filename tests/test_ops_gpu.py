@@ -138,7 +138,7 @@ def test_qkv_decode_rope_and_kv_append(H, G, hs, ne, C, variant):
 
 
 @pytest.mark.parametrize("H,G,hs", [(32, 8, 128), (32, 4, 64), (8, 8, 64), (8, 1, 128), (4, 2, 128)])
-@pytest.mark.parametrize("L", [1, 31, 32, 33, 500, 2048])
+@pytest.mark.parametrize("L", [1, 15, 16, 17, 31, 32, 33, 129, 500, 2048])
 def test_attn_decode_matches_sdpa(H, G, hs, L):
     ops = _ops()
     torch.manual_seed(L)
