@@ -53,6 +53,7 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.mdi_gemm_bf16.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp]
     lib.mdi_gemm_bf16_ex.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp,
                                      i32, i32, i32, i32, vp]
+    lib.mdi_attn_prefill.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp]
     lib.mdi_advance_step.argtypes = [vp, vp, vp, i32, i32, i32, vp]
     lib.mdi_wait_flag.argtypes = [vp, vp, vp, i64, vp]
     lib.mdi_set_flag.argtypes = [vp, vp, vp]
@@ -275,6 +276,35 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] = Non
                                  ACT[act] if w2 is not None else 0, block_n, signal_flag, ptr(done_ctr), ptr(ctx),
                                  *_knobs, stream_ptr()), "gemm_bf16 (tcgen05)")
     return out
+
+
+def attn_prefill(qkv: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor, kv_layer: torch.Tensor, slot: int, *,
+                 n_head: int, n_groups: int, head_size: int, rope_n_elem: int,
+                 scratch: Optional[Tuple[torch.Tensor, torch.Tensor]] = None) -> torch.Tensor:
+    """Causal attention over a whole prompt (positions ``0..T-1``) on tcgen05: RoPE + split of the fused
+    QKV GEMM output ``qkv [T, (H+2G)*hs]``, K/V appended to ``kv_layer[slot]`` (``[n_slots, 2, G, S, hs]``),
+    flash attention with S and the per-tile P.V product in TMEM.  Returns ``y [T, H*hs]`` (bf16)."""
+    _bf16(qkv, "qkv"); _bf16(kv_layer, "kv_layer")
+    if cos.dtype != torch.float32 or sin.dtype != torch.float32:
+        raise OpsError("rope tables must be fp32")
+    T = qkv.shape[0]
+    if qkv.shape[1] != (n_head + 2 * n_groups) * head_size or not qkv.is_contiguous():
+        raise OpsError("attn_prefill: qkv must be contiguous [T, (H + 2G) * hs]")
+    n_slots, _, G, S, hs = kv_layer.shape
+    if G != n_groups or hs != head_size:
+        raise OpsError("attn_prefill: KV pool shape does not match the head configuration")
+    T_pad = (T + 127) // 128 * 128
+    if scratch is None:
+        scratch = (torch.zeros(n_head, T_pad, head_size, device=qkv.device, dtype=torch.bfloat16),
+                   torch.zeros(n_groups, head_size, T_pad, device=qkv.device, dtype=torch.bfloat16))
+    q_s, vt_s = scratch
+    if tuple(q_s.shape) != (n_head, T_pad, head_size) or tuple(vt_s.shape) != (n_groups, head_size, T_pad):
+        raise OpsError("attn_prefill: scratch tensors have the wrong shape")
+    y = torch.empty(T, n_head * head_size, device=qkv.device, dtype=torch.bfloat16)
+    check(lib().mdi_attn_prefill(ptr(qkv), ptr(cos), ptr(sin), ptr(kv_layer), ptr(q_s), ptr(vt_s), ptr(y), T, T_pad,
+                                 int(slot), n_slots, n_head, n_groups, head_size, rope_n_elem, S, stream_ptr()),
+          "attn_prefill (tcgen05)")
+    return y
 
 
 def sample_scratch(device: Any) -> torch.Tensor:

@@ -1,0 +1,299 @@
+// Causal flash attention for the prefill (T > 1) on the 5th-generation tensor cores, sm_100a.
+//
+// Reference behaviour being replaced (SURVEY K4-K7 at prefill): view/permute/split of the fused QKV
+// output, RoPE as ~8 elementwise launches, index_copy_ into a cache expanded to n_head heads, then
+// F.scaled_dot_product_attention with an explicit mask (model.py:693-751).  Here:
+//
+//   rope_split_kernel     one pass over the QKV GEMM's output [T, (H+2G)*hs]: RoPE on q and k, q written
+//                         head-major for TMA, k/v appended to the slot KV pool (G group heads only) and v
+//                         additionally transposed to [G, hs, T] so that P.V sees a K-major B operand;
+//   attn_prefill_tcgen05  grid (T/128 query tiles, H heads).  Per 128-key tile:
+//                         S = Q K^T      tcgen05.mma, operands staged by TMA (SWIZZLE_128B), S in TMEM
+//                         softmax        4 warps, one query row per thread: tcgen05.ld, scale, causal
+//                                        mask, online max/sum in registers, P (bf16) written to shared
+//                                        memory in the same swizzled K-major layout TMA would produce
+//                         O_t = P V      tcgen05.mma into a second TMEM region, added to the register
+//                                        accumulator (already rescaled by exp2(m_old - m_new))
+//                         one elected thread issues every TMA and MMA; mbarriers carry all hand-offs.
+//
+// GQA: the q heads of a group read the same K / V^T tiles (L2 hits after the first head).
+#include "tcgen05.cuh"
+
+namespace mdi {
+
+constexpr int PA_BM = 128;       // query rows per CTA  (= TMEM lanes)
+constexpr int PA_BN = 128;       // keys per tile
+constexpr int PA_THREADS = 192;  // warps 0-3 softmax / epilogue, warp 4 TMA + MMA issue, warp 5 TMEM alloc
+
+struct PrefillAttnParams {
+  CUtensorMap map_q;   // [H * T_pad, hs]
+  CUtensorMap map_k;   // this layer's KV pool viewed as [n_slots * 2 * G * S, hs]
+  CUtensorMap map_vt;  // [G * hs, T_pad]
+  bf16* y;             // [T, H * hs]
+  int T, T_pad, n_head, q_per_kv, n_groups, max_seq, slot;
+  float scale_log2;    // (1 / sqrt(hs)) * log2(e)
+};
+
+// ---- RoPE + split ------------------------------------------------------------------------------------
+struct RopeSplitArgs {
+  const bf16* qkv;   // [T, (H + 2G) * hs], litGPT group-interleaved columns
+  const float* cos;  // [S, ne]
+  const float* sin;
+  bf16* q_out;       // [H, T_pad, hs]
+  bf16* kv;          // layer pool [n_slots, 2, G, S, hs]
+  bf16* vt;          // [G, hs, T_pad]
+  int T, T_pad, slot, n_head, n_groups, hs, ne, max_seq;
+};
+
+__global__ void __launch_bounds__(256) rope_split_kernel(const RopeSplitArgs a) {
+  const int t = blockIdx.x;
+  const int hs = a.hs, half_hs = hs / 2, ne = a.ne, half_ne = ne / 2;
+  const int qpk = a.n_head / a.n_groups;
+  const int n_slots_hd = a.n_head + 2 * a.n_groups;
+  const bf16* row = a.qkv + (size_t)t * n_slots_hd * hs;
+  for (int pr = threadIdx.x; pr < n_slots_hd * half_hs; pr += blockDim.x) {
+    const int j = pr / half_hs, i = pr % half_hs;
+    int ra, rb;
+    bool rot;
+    if (i < half_ne) { ra = i; rb = i + half_ne; rot = true; }
+    else { const int u = i - half_ne; ra = ne + 2 * u; rb = ra + 1; rot = false; }
+    float xa = __bfloat162float(row[j * hs + ra]), xb = __bfloat162float(row[j * hs + rb]);
+    const int g = j / (qpk + 2), s = j % (qpk + 2);
+    if (rot && s <= qpk) {  // q and k heads rotate (NeoX half rotation, model.py:881-891), v does not
+      const float ca = a.cos[(size_t)t * ne + ra], sa = a.sin[(size_t)t * ne + ra];
+      const float cb = a.cos[(size_t)t * ne + rb], sb = a.sin[(size_t)t * ne + rb];
+      const float na = xa * ca - xb * sa, nb = xb * cb + xa * sb;
+      xa = na; xb = nb;
+    }
+    const bf16 va = __float2bfloat16_rn(xa), vb = __float2bfloat16_rn(xb);
+    if (s < qpk) {
+      bf16* dst = a.q_out + ((size_t)(g * qpk + s) * a.T_pad + t) * hs;
+      dst[ra] = va; dst[rb] = vb;
+    } else {
+      const size_t which = (s == qpk) ? 0 : 1;
+      bf16* dst = a.kv + ((((size_t)a.slot * 2 + which) * a.n_groups + g) * a.max_seq + t) * hs;
+      dst[ra] = va; dst[rb] = vb;
+      if (which == 1) {
+        a.vt[((size_t)g * hs + ra) * a.T_pad + t] = va;
+        a.vt[((size_t)g * hs + rb) * a.T_pad + t] = vb;
+      }
+    }
+  }
+}
+
+// ---- attention -----------------------------------------------------------------------------------------
+template <int HS>
+__global__ void __launch_bounds__(PA_THREADS, 1) attn_prefill_tcgen05_kernel(const __grid_constant__ PrefillAttnParams p) {
+  extern __shared__ __align__(1024) unsigned char pa_smem[];
+  constexpr int KA = HS / 64;                  // 64-column swizzle atoms along the head dimension
+  constexpr int ROW_ATOM = 128 * 128;          // bytes of one [128 rows x 128 B] atom
+  constexpr int Q_BYTES = KA * ROW_ATOM;
+  constexpr int K_BYTES = KA * ROW_ATOM;
+  constexpr int VT_ATOM = HS * 128;            // [HS rows x 64 keys]
+  constexpr int VT_BYTES = 2 * VT_ATOM;
+  constexpr int P_BYTES = 2 * ROW_ATOM;
+  constexpr int TMEM_COLS = 256;               // S: columns [0,128), O_t: [128, 128 + HS)
+  unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(pa_smem) + 1023) & ~uintptr_t(1023));
+  unsigned char* q_s = base;
+  unsigned char* k_s = q_s + Q_BYTES;
+  unsigned char* vt_s = k_s + K_BYTES;
+  unsigned char* p_s = vt_s + VT_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(p_s + P_BYTES);
+  uint64_t *q_full = bars, *kv_full = bars + 1, *s_full = bars + 2, *p_ready = bars + 3, *o_full = bars + 4, *o_done = bars + 5;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 6);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m_tile = blockIdx.x, h = blockIdx.y, g = h / p.q_per_kv;
+  const int m0 = m_tile * PA_BM;
+  const int n_tiles = m_tile + 1;  // causal: keys [0, m0 + 128)
+
+  if (warp == 4 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&p.map_q) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&p.map_k) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&p.map_vt) : "memory");
+    mbar_init(q_full, 1); mbar_init(kv_full, 1); mbar_init(s_full, 1); mbar_init(o_full, 1);
+    mbar_init(p_ready, 128); mbar_init(o_done, 128);
+    mbar_fence_init();
+  }
+  if (warp == 5) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "n"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_s = *tmem_ptr_smem, tmem_o = tmem_s + 128;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      // ===== TMA + MMA issue =====
+      const uint32_t idesc_s = umma_idesc_bf16(PA_BM, PA_BN), idesc_o = umma_idesc_bf16(PA_BM, HS);
+      const int q_row0 = h * p.T_pad + m0;
+      const int k_row0 = ((p.slot * 2 + 0) * p.n_groups + g) * p.max_seq;
+      mbar_expect_tx(q_full, Q_BYTES);
+#pragma unroll
+      for (int a = 0; a < KA; ++a) tma_load_2d(q_s + a * ROW_ATOM, &p.map_q, q_full, a * 64, q_row0);
+      for (int t = 0; t < n_tiles; ++t) {
+        const int j0 = t * PA_BN;
+        if (t > 0) mbar_wait(o_full, (t - 1) & 1);  // previous P.V retired: K, V^T and P buffers are free
+        mbar_expect_tx(kv_full, K_BYTES + VT_BYTES);
+#pragma unroll
+        for (int a = 0; a < KA; ++a) tma_load_2d(k_s + a * ROW_ATOM, &p.map_k, kv_full, a * 64, k_row0 + j0);
+#pragma unroll
+        for (int a = 0; a < 2; ++a) tma_load_2d(vt_s + a * VT_ATOM, &p.map_vt, kv_full, j0 + a * 64, g * HS);
+        if (t == 0) mbar_wait(q_full, 0);
+        mbar_wait(kv_full, t & 1);
+        tcgen05_fence_after();
+        // S = Q K^T : K dimension = head size
+#pragma unroll
+        for (int k = 0; k < HS / 16; ++k) {
+          const uint32_t off = (uint32_t)(k / 4) * ROW_ATOM + (uint32_t)(k % 4) * 32;
+          tcgen05_mma_f16(tmem_s, umma_desc_sw128(smem_u32(q_s) + off), umma_desc_sw128(smem_u32(k_s) + off), idesc_s, k ? 1u : 0u);
+        }
+        tcgen05_commit(s_full);
+        mbar_wait(p_ready, t & 1);                  // P is in shared memory, S has been read
+        if (t > 0) mbar_wait(o_done, (t - 1) & 1);  // previous O_t has been read out of TMEM
+        tcgen05_fence_after();
+        // O_t = P V : K dimension = the 128 keys of this tile
+#pragma unroll
+        for (int k = 0; k < PA_BN / 16; ++k) {
+          const uint32_t offp = (uint32_t)(k / 4) * ROW_ATOM + (uint32_t)(k % 4) * 32;
+          const uint32_t offv = (uint32_t)(k / 4) * VT_ATOM + (uint32_t)(k % 4) * 32;
+          tcgen05_mma_f16(tmem_o, umma_desc_sw128(smem_u32(p_s) + offp), umma_desc_sw128(smem_u32(vt_s) + offv), idesc_o, k ? 1u : 0u);
+        }
+        tcgen05_commit(o_full);
+      }
+    }
+  } else if (warp < 4) {
+    // ===== softmax + output: thread <-> query row <-> TMEM lane =====
+    const int r = threadIdx.x;
+    const int q_idx = m0 + r;
+    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+    float O[HS];
+#pragma unroll
+    for (int d = 0; d < HS; ++d) O[d] = 0.f;
+    float m_run = -INFINITY, l_run = 0.f;
+    for (int t = 0; t < n_tiles; ++t) {
+      const int j0 = t * PA_BN;
+      mbar_wait(s_full, t & 1);
+      tcgen05_fence_after();
+      // pass 1: row maximum of the masked, scaled scores
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < PA_BN / 32; ++c) {
+        uint32_t sv[32];
+        tmem_ld_32x32(tmem_s + lane_off + (uint32_t)(c * 32), sv);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int j = j0 + c * 32 + i;
+          if (j <= q_idx && j < p.T) mx = fmaxf(mx, __uint_as_float(sv[i]) * p.scale_log2);
+        }
+      }
+      const float m_new = fmaxf(m_run, mx);
+      const float corr = (m_run == -INFINITY) ? 0.f : exp2f(m_run - m_new);
+      // pass 2: probabilities -> bf16 -> swizzled K-major tile in shared memory
+      float psum = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < PA_BN / 32; ++c) {
+        uint32_t sv[32];
+        tmem_ld_32x32(tmem_s + lane_off + (uint32_t)(c * 32), sv);
+        float pf[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int j = j0 + c * 32 + i;
+          const float pv = (j <= q_idx && j < p.T && m_new != -INFINITY) ? exp2f(__uint_as_float(sv[i]) * p.scale_log2 - m_new) : 0.f;
+          pf[i] = pv;
+          psum += pv;
+        }
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {  // 4 x 16 B = keys [c*32 + 8v, c*32 + 8v + 8)
+          const int key = c * 32 + v * 8;
+          const int atom = key >> 6, chunk = (key & 63) >> 3;
+          uint4 o;
+          o.x = pack_bf16x2(pf[v * 8 + 0], pf[v * 8 + 1]); o.y = pack_bf16x2(pf[v * 8 + 2], pf[v * 8 + 3]);
+          o.z = pack_bf16x2(pf[v * 8 + 4], pf[v * 8 + 5]); o.w = pack_bf16x2(pf[v * 8 + 6], pf[v * 8 + 7]);
+          *reinterpret_cast<uint4*>(p_s + atom * ROW_ATOM + r * 128 + ((chunk ^ (r & 7)) << 4)) = o;
+        }
+      }
+      l_run = l_run * corr + psum;
+      m_run = m_new;
+#pragma unroll
+      for (int d = 0; d < HS; ++d) O[d] *= corr;
+      fence_proxy_async_smem();  // P stores (generic proxy) -> visible to the MMA's operand reads (async proxy)
+      tcgen05_fence_before();
+      mbar_arrive(p_ready);
+      mbar_wait(o_full, t & 1);
+      tcgen05_fence_after();
+#pragma unroll
+      for (int c = 0; c < HS / 32; ++c) {
+        uint32_t ov[32];
+        tmem_ld_32x32(tmem_o + lane_off + (uint32_t)(c * 32), ov);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) O[c * 32 + i] += __uint_as_float(ov[i]);
+      }
+      tcgen05_fence_before();
+      mbar_arrive(o_done);
+    }
+    if (q_idx < p.T) {
+      const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
+      bf16* dst = p.y + (size_t)q_idx * p.n_head * HS + (size_t)h * HS;
+#pragma unroll
+      for (int v = 0; v < HS / 8; ++v) {
+        uint4 o;
+        o.x = pack_bf16x2(O[v * 8 + 0] * inv, O[v * 8 + 1] * inv); o.y = pack_bf16x2(O[v * 8 + 2] * inv, O[v * 8 + 3] * inv);
+        o.z = pack_bf16x2(O[v * 8 + 4] * inv, O[v * 8 + 5] * inv); o.w = pack_bf16x2(O[v * 8 + 6] * inv, O[v * 8 + 7] * inv);
+        *reinterpret_cast<uint4*>(dst + v * 8) = o;
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_s), "n"(TMEM_COLS) : "memory");
+  }
+}
+
+template <int HS>
+static int launch_prefill_attn(const PrefillAttnParams& p, cudaStream_t stream) {
+  const size_t smem = 1024 + (size_t)(2 * (HS / 64) * 128 * 128 + 2 * HS * 128 + 2 * 128 * 128) + 128;
+  cudaError_t e = cudaFuncSetAttribute(attn_prefill_tcgen05_kernel<HS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  dim3 grid((p.T + PA_BM - 1) / PA_BM, p.n_head);
+  attn_prefill_tcgen05_kernel<HS><<<grid, PA_THREADS, smem, stream>>>(p);
+  return (int)cudaGetLastError();
+}
+
+}  // namespace mdi
+
+using namespace mdi;
+
+// qkv: [T, (H + 2G) * hs] bf16 (output of the QKV GEMM), positions 0..T-1.  q_scratch: [H, T_pad, hs],
+// vt_scratch: [G, hs, T_pad] (T_pad = T rounded up to 128, both finite — zero-initialised once),
+// kv: the layer's pool [n_slots, 2, G, S, hs], y: [T, H * hs].
+extern "C" int mdi_attn_prefill(const void* qkv, const float* cos, const float* sin, void* kv, void* q_scratch,
+                                void* vt_scratch, void* y, int T, int T_pad, int slot, int n_slots, int n_head,
+                                int n_groups, int head_size, int rope_n_elem, int max_seq, cudaStream_t stream) {
+  if (T <= 0 || T > max_seq || T_pad % PA_BN != 0 || T_pad < T || n_head % n_groups != 0) return -2;
+  if (head_size != 64 && head_size != 128) return -3;
+  if (rope_n_elem % 2 != 0 || rope_n_elem > head_size) return -2;
+  RopeSplitArgs r;
+  r.qkv = (const bf16*)qkv; r.cos = cos; r.sin = sin; r.q_out = (bf16*)q_scratch; r.kv = (bf16*)kv; r.vt = (bf16*)vt_scratch;
+  r.T = T; r.T_pad = T_pad; r.slot = slot; r.n_head = n_head; r.n_groups = n_groups; r.hs = head_size; r.ne = rope_n_elem;
+  r.max_seq = max_seq;
+  rope_split_kernel<<<T, 256, 0, stream>>>(r);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return (int)e;
+
+  PrefillAttnParams p;
+  p.y = (bf16*)y; p.T = T; p.T_pad = T_pad; p.n_head = n_head; p.n_groups = n_groups; p.q_per_kv = n_head / n_groups;
+  p.max_seq = max_seq; p.slot = slot;
+  p.scale_log2 = 1.4426950408889634f / sqrtf((float)head_size);
+  int rc = make_map(&p.map_q, q_scratch, (long long)n_head * T_pad, head_size, PA_BM);
+  if (rc) return rc;
+  rc = make_map(&p.map_k, kv, (long long)n_slots * 2 * n_groups * max_seq, head_size, PA_BN);
+  if (rc) return rc;
+  rc = make_map(&p.map_vt, vt_scratch, (long long)n_groups * head_size, T_pad, head_size);
+  if (rc) return rc;
+  return head_size == 128 ? launch_prefill_attn<128>(p, stream) : launch_prefill_attn<64>(p, stream);
+}

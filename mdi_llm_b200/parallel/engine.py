@@ -168,6 +168,8 @@ class FusedStage:
         self._trace_names: List[str] = []
         self._check_weights()
         self.weight_dtype = weight_dtype
+        # prefill attention: "tcgen05" (hand-written flash attention, prompts start at position 0) or "sdpa"
+        self.prefill_attn = os.environ.get("MDI_PREFILL_ATTN", "tcgen05")
         self._q: Dict[int, Tuple[torch.Tensor, torch.Tensor]] = {}  # id(linear) -> (fp8 weight, block scales)
         if weight_dtype == "fp8":
             self._quantize(free_bf16)
@@ -405,7 +407,11 @@ class FusedStage:
             if kind == "attn":
                 h = ops.rmsnorm_rows(x, blk.norm_1.weight, eps, uo)
                 qkv = ops.gemm(h, self._dense(blk.attn.attn), bias=blk.attn.attn.bias, block_n=bn)
-                y = blk.attn.attend_qkv(qkv.unsqueeze(0), cos, sin, input_pos, m.kv_pool.layer(li, slot))[0].contiguous()
+                if self.prefill_attn == "tcgen05":  # RoPE + KV append + causal flash attention, S/P.V in TMEM
+                    y = ops.attn_prefill(qkv, m.cos, m.sin, self.kv[li], slot, n_head=cfg.n_head,
+                                         n_groups=cfg.n_query_groups, head_size=cfg.head_size, rope_n_elem=cfg.rope_n_elem)
+                else:  # eager helper (SDPA): the oracle path
+                    y = blk.attn.attend_qkv(qkv.unsqueeze(0), cos, sin, input_pos, m.kv_pool.layer(li, slot))[0].contiguous()
                 x = out_gemm(y, blk.attn.proj, last)
             else:
                 h = ops.rmsnorm_rows(x, blk.norm_2.weight, eps, uo)

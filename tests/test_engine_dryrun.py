@@ -15,7 +15,8 @@ from mdi_llm_b200.models.stage import build_stage
 from mdi_llm_b200.parallel import engine as eng
 from mdi_llm_b200.parallel.engine import FusedStage, HopTarget
 
-KERNELS = ["linear_decode", "qkv_decode", "attn_decode", "embed", "sample_fast", "advance_step", "rmsnorm_rows", "gemm"]
+KERNELS = ["linear_decode", "qkv_decode", "attn_decode", "embed", "sample_fast", "advance_step", "rmsnorm_rows", "gemm",
+           "attn_prefill"]
 
 
 def _cfg(n_layer=3):
@@ -40,6 +41,8 @@ def dry_ops():
                 return torch.zeros(a[0].shape[0], a[1].shape[0], dtype=torch.bfloat16)
             if _n == "rmsnorm_rows":
                 return torch.zeros_like(a[0])
+            if _n == "attn_prefill":
+                return torch.zeros(a[0].shape[0], kw["n_head"] * kw["head_size"], dtype=torch.bfloat16)
             return None
 
         patches.append(mock.patch.object(ops, name, rec))
@@ -106,8 +109,9 @@ def test_local_output_and_prefill_sequences_bind():
         assert calls[-1][1]["y"] is fs.out_local and calls[-1][1].get("signal_flag") is None
         calls.clear()
         x = torch.zeros(1, 5, 256, dtype=torch.bfloat16)
-        with mock.patch.object(type(st.transformer.h[1].attn), "attend_qkv", lambda self, qkv, *a, **k: torch.zeros(1, 5, 256, dtype=torch.bfloat16)):
-            assert fs.prefill(x, torch.arange(5), 0, hop=(0x3000, 0x4000)) is None
+        assert fs.prefill_attn == "tcgen05"
+        assert fs.prefill(x, torch.arange(5), 0, hop=(0x3000, 0x4000)) is None
+        assert sum(1 for c in calls if c[0] == "attn_prefill") == 2  # blocks 1 ("both") and 2 ("attn")
     gemms = [c[1] for c in calls if c[0] == "gemm"]
     assert gemms[-1]["out_ptr"] == 0x3000 and gemms[-1]["signal_flag"] == 0x4000 and gemms[-1]["residual"] is not None
     assert all(g.get("out_ptr") is None for g in gemms[:-1])

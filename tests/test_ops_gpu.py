@@ -338,3 +338,33 @@ def test_qkv_decode_fp8_block_scaled():
     torch.testing.assert_close(q.view(H, hs).float(), qr.float(), rtol=4e-2, atol=4e-2)
     torch.testing.assert_close(kv[0, 0, :, pos].float(), kr.float(), rtol=4e-2, atol=4e-2)
     torch.testing.assert_close(kv[0, 1, :, pos].float(), vr.float(), rtol=4e-2, atol=4e-2)
+
+
+@pytest.mark.parametrize("H,G,hs,ne", [(32, 8, 128, 128), (8, 2, 64, 64), (4, 4, 128, 64), (8, 1, 64, 32)])
+@pytest.mark.parametrize("T", [5, 64, 128, 129, 300])
+def test_attn_prefill_tcgen05_matches_eager(H, G, hs, ne, T):
+    """RoPE + KV append + causal flash attention (tcgen05, S / P.V in TMEM) vs the eager attend_qkv."""
+    from mdi_llm_b200.models.config import Config
+    from mdi_llm_b200.models.gpt import CausalSelfAttention, build_rope_cache
+
+    ops = _ops()
+    torch.manual_seed(T + H)
+    cfg = Config.from_name("tiny-llama-1.1b", n_layer=1, n_embd=H * hs, n_head=H, n_query_groups=G,
+                           rotary_percentage=ne / hs, block_size=512)
+    assert cfg.head_size == hs and cfg.rope_n_elem == ne
+    S, n_slots, slot = 512, 3, 1
+    qkv = (torch.randn(T, (H + 2 * G) * hs, device="cuda") * 0.7).bfloat16()
+    cos, sin = build_rope_cache(S, ne, device=torch.device("cuda"))
+    cos, sin = cos.float().contiguous(), sin.float().contiguous()
+    pool = (torch.randn(n_slots, 2, G, S, hs, device="cuda") * 0.3).bfloat16()
+    pool_ref = pool.clone()
+    y = ops.attn_prefill(qkv, cos, sin, pool, slot, n_head=H, n_groups=G, head_size=hs, rope_n_elem=ne)
+    attn = CausalSelfAttention(cfg).cuda().bfloat16()
+    pos = torch.arange(T, device="cuda")
+    with torch.no_grad():
+        ref = attn.attend_qkv(qkv.unsqueeze(0), cos[:T], sin[:T], pos, (pool_ref[slot, 0], pool_ref[slot, 1]))[0]
+    torch.testing.assert_close(y.float(), ref.float(), rtol=3e-2, atol=3e-2)
+    # K and V of the prompt landed in the slot; nothing else in the pool moved
+    torch.testing.assert_close(pool[slot, :, :, :T].float(), pool_ref[slot, :, :, :T].float(), rtol=2e-2, atol=2e-2)
+    other = [s for s in range(n_slots) if s != slot]
+    assert torch.equal(pool[other], pool_ref[other]) and torch.equal(pool[slot, :, :, T:], pool_ref[slot, :, :, T:])
