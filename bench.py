@@ -96,7 +96,7 @@ def parse_args() -> argparse.Namespace:
     ap.add_argument("--seq-len", type=int, default=0, help="KV/context budget (0 = prompt + all rounds)")
     ap.add_argument("--e2e-steps", type=int, default=0, help="rounds of the host-fed e2e measurement (0 = min(steps, 64))")
     ap.add_argument("--n-samples", type=int, default=0, help="concurrent samples (0 = number of GPUs)")
-    ap.add_argument("--partition", default="balanced", choices=["auto", "table", "balanced", "half"],
+    ap.add_argument("--partition", default="half", choices=["auto", "table", "balanced", "half"],
                     help="table: the reference's N_LAYERS_NODES; balanced: whole layers, head-aware; half: attention|MLP half-layer units")
     ap.add_argument("--no-pdl", action="store_true")
     ap.add_argument("--ctas-per-sm", type=int, default=4)

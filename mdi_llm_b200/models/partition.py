@@ -140,8 +140,8 @@ def half_stages(units_per_stage: Sequence[int]) -> List[HalfStage]:
     return out
 
 
-def decode_unit_costs(config: Config, bytes_per_param: float = 2.0, eff_tbps: float = 5.9, kernel_us: float = 2.0,
-                      attn_kernel_us: float = 8.0, sampler_us: float = 45.0) -> Tuple[float, float, float]:
+def decode_unit_costs(config: Config, bytes_per_param: float = 2.0, eff_tbps: float = 6.4, kernel_us: float = 1.5,
+                      attn_kernel_us: float = 6.0, sampler_us: float = 35.0) -> Tuple[float, float, float]:
     """Per-token decode cost model in microseconds -> ``(attention unit, MLP unit, output head)``.
     Decode is weight-streaming bound: bytes over the achieved HBM rate plus a per-launch term; defaults
     are the measured B200 values (profiles/README.md)."""
