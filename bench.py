@@ -38,7 +38,9 @@ METRIC = "generated tokens/sec (whole box, device-timed, max over ranks) Llama-3
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons during the timed region (recipe's clocks line)."""
+    """SM clocks / throttle reasons sampled DURING the timed region (the recipe's clocks line).
+    NVML in-process (a sample every 2 ms, so even a 100 ms region gets dozens); falls back to one
+    ``nvidia-smi`` poller when NVML is not importable."""
 
     QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -48,14 +50,50 @@ class ClockSampler:
         self.n = n_gpus
         self.proc: Optional[subprocess.Popen] = None
         self.lines: List[str] = []
+        self.sm: List[float] = []
+        self.mx: List[float] = []
+        self.reasons: set = set()
+        self._stop = threading.Event()
+        self._thread: Optional[threading.Thread] = None
+        self._nvml = None
 
     def start(self) -> None:
         try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self._nvml = pynvml
+            self._handles = [pynvml.nvmlDeviceGetHandleByIndex(i) for i in range(min(self.n, pynvml.nvmlDeviceGetCount()))]
+            self._thread = threading.Thread(target=self._poll_nvml, daemon=True)
+            self._thread.start()
+            return
+        except Exception:  # noqa: BLE001
+            self._nvml = None
+        try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except OSError:
             self.proc = None
+
+    def _poll_nvml(self) -> None:
+        nv = self._nvml
+        bits = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        while not self._stop.is_set():
+            for h in self._handles:
+                try:
+                    self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                    self.mx.append(float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)))
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                    for name, bit in bits.items():
+                        if r & bit:
+                            self.reasons.add(name)
+                except Exception:  # noqa: BLE001
+                    pass
+            time.sleep(0.002)
 
     def _pump(self) -> None:
         assert self.proc is not None and self.proc.stdout is not None
@@ -63,6 +101,12 @@ class ClockSampler:
             self.lines.append(line)
 
     def stop(self) -> Dict[str, Any]:
+        if self._nvml is not None:
+            self._stop.set()
+            if self._thread is not None:
+                self._thread.join(timeout=1.0)
+            return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": max(self.mx) if self.mx else None,
+                    "reasons": sorted(self.reasons), "samples": len(self.sm), "source": "nvml"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -82,7 +126,7 @@ class ClockSampler:
                 if val.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
 def parse_args() -> argparse.Namespace:
