@@ -8,5 +8,4 @@ $TR --master-port 29521 $B --partition half > gpurun_out/bench_n8_half.json 2> g
 $TR --master-port 29522 $B --partition balanced > gpurun_out/bench_n8.json 2>> gpurun_out/bench_n8.err; show gpurun_out/bench_n8.json
 $TR --master-port 29523 $B --partition half --weights fp8 --prompt-len 1024 --seq-len 2048 > gpurun_out/bench_n8_fp8_2048ctx.json 2>> gpurun_out/bench_n8.err; show gpurun_out/bench_n8_fp8_2048ctx.json
 $TR --master-port 29524 $B --partition half --hop nccl > gpurun_out/bench_n8_nccl.json 2>> gpurun_out/bench_n8.err; show gpurun_out/bench_n8_nccl.json
-python -m torch.distributed.run --nnodes=1 --master-addr 127.0.0.1 --nproc-per-node 8 --master-port 29525 bench.py --gpus 8 > gpurun_out/bench_n8_default.json 2>> gpurun_out/bench_n8.err; show gpurun_out/bench_n8_default.json
 tail -5 gpurun_out/bench_n8.err
