@@ -224,7 +224,14 @@ def run_ours(args: argparse.Namespace) -> Dict[str, Any]:
     # ---------------- device-driven, device-timed ----------------
     pipe.prepare(prompts, rounds_total)
     barrier()
-    pipe.prefill()
+    pf0, pf1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    pf0.record()
+    pipe.prefill()  # round 0: every prompt through every stage (tcgen05 GEMMs + attention, fused hop)
+    pf1.record()
+    barrier()
+    prefill_ms = torch.tensor([pf0.elapsed_time(pf1)], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(prefill_ms, op=dist.ReduceOp.MAX)
     pipe.decode_rounds(args.warmup)
     barrier()
     sampler = ClockSampler(world)
@@ -292,7 +299,7 @@ def run_ours(args: argparse.Namespace) -> Dict[str, Any]:
         "e2e": {"value": round(e2e_value, 3) if e2e_value is not None else None, "unit": "tokens/s", "h2d_bytes_per_step": h2d // max(1, steps_e2e),
                 "d2h_bytes_per_step": d2h // max(1, steps_e2e), "rounds": e2e_rounds,
                 "how": "host-fed steps: pinned ctx H2D + sampled-token D2H every step, wall clock, max over ranks"},
-        "gpu_launches": int(launches.item()),
+        "prefill_ms_all_samples": round(float(prefill_ms.item()), 3), "gpu_launches": int(launches.item()),
         "hop_watchdog_status": status,
         "stage_wait_us_per_step": [round(x, 2) for x in waits.tolist()],
         "stage_busy_us_per_step": [round(ms_total * 1e3 / (args.steps * n_samples) - x, 2) for x in waits.tolist()],
