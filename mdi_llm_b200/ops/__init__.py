@@ -38,13 +38,13 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.mdi_error_string.restype = c_char_p
     lib.mdi_error_string.argtypes = [i32]
     lib.mdi_linear_decode.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, i32, i32, f32, i32, i32, i32,
-                                      vp, vp, i64, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp]
+                                      vp, vp, i64, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.mdi_qkv_decode.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, i32, i32, i32, f32, i32,
-                                   vp, vp, i64, i32, i32, i32, vp, vp, vp]
+                                   vp, vp, i64, i32, i32, i32, vp, vp, vp, vp, vp, vp]
     lib.mdi_set_linear_variant.argtypes = [i32]
     lib.mdi_set_l2_prefetch_mb.argtypes = [i32]
     lib.mdi_get_linear_variant.restype = i32
-    lib.mdi_attn_decode.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp]
+    lib.mdi_attn_decode.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, i64, vp]
     lib.mdi_embed.argtypes = [vp, vp, vp, i64, vp, vp, i64, i32, f32, i32, vp]
     lib.mdi_rmsnorm_rows.argtypes = [vp, vp, vp, i32, i32, f32, i32, vp]
     lib.mdi_sample.argtypes = [vp, i64, vp, i64, vp, vp, i32, i32, f32, i32, c_ulonglong, i32, vp]
@@ -171,7 +171,8 @@ def linear_decode(
     y_ptr: Optional[int] = None, residual_ptr: Optional[int] = None, x_ptr: Optional[int] = None, variant: int = -1,
     stats: Optional[torch.Tensor] = None, trace: Optional[int] = None,
     wscale: Optional[torch.Tensor] = None, wscale2: Optional[torch.Tensor] = None,
- ctx_early: bool = False) -> None:
+ ctx_early: bool = False, dep_wait: Optional[int] = None,
+    dep_signal: Optional[int] = None, dep_ctr: Optional[int] = None) -> None:
     """``y = epilogue(W @ norm?(x))`` for one token.  ``*_ptr`` overrides let the output /
     residual / input live in peer-mapped (other GPU) memory that has no torch tensor.
     With ``wscale`` (fp32 ``[N, K/128]``) ``W`` (and ``W2``/``wscale2``) are fp8-e4m3 block-scaled."""
@@ -189,7 +190,7 @@ def linear_decode(
         residual_ptr if residual_ptr is not None else ptr(residual), y_ptr if y_ptr is not None else ptr(y),
         ptr(ctx), x_slot_stride, res_slot_stride, y_slot_stride, N, K, eps, int(unit_offset), ACT[act], out_fp32,
         wait_flag, status, wait_max_cycles, signal_flag, done_ctr, ctas_per_sm, int(use_pdl) | (2 if ctx_early else 0), variant, hist, amax,
-        trace, ptr(wscale), ptr(wscale2), stream_ptr()), "linear_decode")
+        trace, ptr(wscale), ptr(wscale2), dep_wait, dep_signal, dep_ctr, stream_ptr()), "linear_decode")
 
 
 def qkv_decode(
@@ -198,7 +199,8 @@ def qkv_decode(
     bias: Optional[torch.Tensor] = None, norm_w: Optional[torch.Tensor] = None, eps: float = 1e-5,
     unit_offset: bool = False, x_slot_stride: int = 0, wait_flag: Optional[int] = None, status: Optional[int] = None,
     wait_max_cycles: int = 0, ctas_per_sm: int = 4, use_pdl: bool = False, x_ptr: Optional[int] = None,
-    variant: int = -1, trace: Optional[int] = None, wscale: Optional[torch.Tensor] = None, ctx_early: bool = False) -> None:
+    variant: int = -1, trace: Optional[int] = None, wscale: Optional[torch.Tensor] = None, ctx_early: bool = False, dep_wait: Optional[int] = None,
+    dep_signal: Optional[int] = None, dep_ctr: Optional[int] = None) -> None:
     if wscale is None:
         _bf16(W, "W")
     else:
@@ -208,17 +210,20 @@ def qkv_decode(
     check(lib().mdi_qkv_decode(
         ptr(W), ptr(bias), x_ptr if x_ptr is not None else ptr(x), ptr(norm_w), ptr(cos), ptr(sin), ptr(q_out),
         ptr(kv_layer), ptr(ctx), x_slot_stride, W.shape[1], n_head, n_groups, head_size, rope_n_elem, max_seq, eps,
-        int(unit_offset), wait_flag, status, wait_max_cycles, ctas_per_sm, int(use_pdl) | (2 if ctx_early else 0), variant, trace, ptr(wscale), stream_ptr()),
+        int(unit_offset), wait_flag, status, wait_max_cycles, ctas_per_sm, int(use_pdl) | (2 if ctx_early else 0), variant, trace, ptr(wscale), dep_wait, dep_signal, dep_ctr, stream_ptr()),
         "qkv_decode")
 
 
 def attn_decode(q: torch.Tensor, kv_layer: torch.Tensor, y: torch.Tensor, part: torch.Tensor, tickets: torch.Tensor,
                 ctx: torch.Tensor, *, n_head: int, n_groups: int, head_size: int, max_seq: int, n_split: int,
-                use_pdl: bool = False, trace: Optional[int] = None) -> None:
+                use_pdl: bool = False, trace: Optional[int] = None, dep_wait: Optional[int] = None,
+                dep_signal: Optional[int] = None, dep_ctr: Optional[int] = None, status: Optional[int] = None,
+                wait_max_cycles: int = 0) -> None:
     """Split-KV decode attention.  ``part``: fp32 ``[H, n_split, hs+2]`` scratch; ``tickets``: zeroed
     int32 ``[G]`` (self-resetting) used by the last CTA of a group to merge the spans."""
     check(lib().mdi_attn_decode(ptr(q), ptr(kv_layer), ptr(y), ptr(part), ptr(tickets), ptr(ctx), n_head, n_groups,
-                                head_size, max_seq, n_split, int(use_pdl), trace, stream_ptr()), "attn_decode")
+                                head_size, max_seq, n_split, int(use_pdl), trace, dep_wait, dep_signal, dep_ctr, status, wait_max_cycles,
+                                stream_ptr()), "attn_decode")
 
 
 def embed(wte: torch.Tensor, x: torch.Tensor, ctx: torch.Tensor, *, tokens: Optional[torch.Tensor] = None,

@@ -119,6 +119,63 @@ __device__ __forceinline__ void hop_signal(const HopSignal& s, const int* ctx) {
   }
 }
 
+// ---- intra-stage dependencies by flag instead of grid completion -----------------------------------------
+// A PDL-launched consumer is already resident while its producer runs; `griddepcontrol.wait` releases it
+// only after the producer grid has completed AND flushed (~1.4 us after the last CTA's exit, measured).
+// With these flags the producer's last CTA (ticket) publishes `flag = step + 1` right after its stores
+// and the consumer's thread 0 acquires it (gpu scope; the acquire invalidates the SM's L1), which cuts
+// the boundary to the ticket + poll latency.  Legal because PDL starts a dependent grid only once every
+// producer CTA is resident (no deadlock) and every kernel of a stage depends on its predecessor (the
+// chain is linear, so WAR hazards on the ping-pong buffers are covered transitively).
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(int* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+struct DepWait {   // flag == nullptr: fall back to griddepcontrol.wait
+  const int* flag;
+  int* status;           // watchdog error word (set to 2 on expiry), may be null
+  long long max_cycles;  // 0 = wait forever
+};
+struct DepSignal {  // flag == nullptr disables
+  int* flag;
+  unsigned int* ctr;  // ticket counter (self-resetting)
+};
+// all threads call; returns after the producer's flag shows this step
+__device__ __forceinline__ void dep_wait(const DepWait& w, const int* ctx) {
+  if (threadIdx.x == 0) {
+    const int want = ctx[MDI_CTX_STEP] + 1;
+    const long long t0 = clock64();
+    // a producer is one kernel of this stage (< 1 ms); cap the watchdog at 2e8 cycles so that a protocol bug
+    // shows up as status 2 within a fraction of a second per launch instead of hanging the GPU
+    const long long cap = (w.max_cycles > 0 && w.max_cycles < 200000000ll) ? w.max_cycles : 200000000ll;
+    while (ld_acquire_gpu(w.flag) < want) {
+      if (clock64() - t0 > cap) {
+        if (w.status) atomicExch(w.status, 2);
+        break;
+      }
+    }
+  }
+  __syncthreads();
+}
+// every CTA calls after its last output store (idle CTAs too: the ticket count is the whole grid)
+__device__ __forceinline__ void dep_signal(const DepSignal& s, const int* ctx) {
+  if (s.flag == nullptr) return;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned int total = gridDim.x * gridDim.y * gridDim.z;
+    if (atomicAdd(s.ctr, 1u) == total - 1) {
+      *s.ctr = 0;
+      __threadfence();
+      st_release_gpu(s.flag, ctx[MDI_CTX_STEP] + 1);
+    }
+  }
+}
+
 // ---- mbarrier + 1-D bulk async copy (TMA engine, no tensor map needed) ------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {

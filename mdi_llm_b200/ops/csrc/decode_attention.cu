@@ -33,6 +33,8 @@ struct AttnArgs {
   int n_head, n_groups, max_seq, n_split;
   float scale_log2;  // (1/sqrt(hs)) * log2(e)
   unsigned long long* trace;
+  DepWait dep_wait;      // flag dependency on the QKV kernel (else griddepcontrol.wait)
+  DepSignal dep_signal;  // flag for the out-projection
 };
 
 template <int HS, int QPK>
@@ -52,7 +54,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const AttnArgs
   const int g = blockIdx.x, split = blockIdx.y;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   trace_mark(a.trace, 0, true);
-  pdl_wait_prior();
+  if (a.dep_wait.flag) dep_wait(a.dep_wait, a.ctx); else pdl_wait_prior();
   trace_mark(a.trace, 1, true);
   const int slot = a.ctx[MDI_CTX_SLOT], L = a.ctx[MDI_CTX_POS] + 1;
   pdl_launch_dependents();
@@ -62,7 +64,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const AttnArgs
   int tiles_per_split = (tiles + a.n_split - 1) / a.n_split;
   if (tiles_per_split < ATT_WARPS) tiles_per_split = ATT_WARPS;
   const int n_active = (tiles + tiles_per_split - 1) / tiles_per_split;
-  if (split >= n_active) return;
+  if (split >= n_active) { dep_signal(a.dep_signal, a.ctx); return; }  // idle span: only its ticket
   trace_mark(a.trace, 2, false);
   const int t_lo = split * tiles_per_split, t_hi = min(tiles, t_lo + tiles_per_split);
 
@@ -202,7 +204,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const AttnArgs
       if (d == 0) { dst[0] = mm; dst[1] = ll; }
     }
   }
-  if (n_active == 1) { trace_mark(a.trace, 3, true); trace_mark(a.trace, 4, false); return; }
+  if (n_active == 1) { dep_signal(a.dep_signal, a.ctx); trace_mark(a.trace, 3, true); trace_mark(a.trace, 4, false); return; }
 
   // ---- the group's last CTA merges the spans ------------------------------------------------------
   __threadfence();
@@ -213,7 +215,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const AttnArgs
     if (sh_last) a.tickets[g] = 0;
   }
   __syncthreads();
-  if (!sh_last) { trace_mark(a.trace, 3, true); trace_mark(a.trace, 4, false); return; }
+  if (!sh_last) { dep_signal(a.dep_signal, a.ctx); trace_mark(a.trace, 3, true); trace_mark(a.trace, 4, false); return; }
   __threadfence();
   for (int i = threadIdx.x; i < QPK * HS; i += ATT_THREADS) {
     const int h = i / HS, d = i % HS;
@@ -231,6 +233,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const AttnArgs
     }
     a.y[(size_t)(g * QPK + h) * HS + d] = __float2bfloat16_rn(ll > 0.f ? o / ll : 0.f);
   }
+  dep_signal(a.dep_signal, a.ctx);
   trace_mark(a.trace, 3, true);
   trace_mark(a.trace, 4, false);
 }
@@ -256,9 +259,11 @@ using namespace mdi;
 // part: fp32 [H, n_split, hs + 2]; tickets: uint32 [G], zeroed once at allocation.
 extern "C" int mdi_attn_decode(const void* q, const void* kv, void* y, float* part, unsigned int* tickets,
                                const int* ctx, int n_head, int n_groups, int head_size, int max_seq, int n_split,
-                               int use_pdl, unsigned long long* trace, cudaStream_t stream) {
+                               int use_pdl, unsigned long long* trace, const int* dep_wait_flag, int* dep_signal_flag,
+                               unsigned int* dep_ctr, int* status, long long wait_max_cycles, cudaStream_t stream) {
   AttnArgs a;
   a.trace = trace;
+  a.dep_wait = DepWait{dep_wait_flag, status, wait_max_cycles}; a.dep_signal = DepSignal{dep_signal_flag, dep_ctr};
   a.q = (const bf16*)q; a.kv = (const bf16*)kv; a.y = (bf16*)y; a.part = part; a.tickets = tickets; a.ctx = ctx;
   a.n_head = n_head; a.n_groups = n_groups; a.max_seq = max_seq; a.n_split = n_split;
   a.scale_log2 = 1.4426950408889634f / sqrtf((float)head_size);

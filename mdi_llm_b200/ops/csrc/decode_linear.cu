@@ -212,6 +212,8 @@ struct StreamArgs {
   // scale per 128 consecutive K elements of every row ([N, K/128]); null = bf16 weights
   const float* wscale;
   const float* wscale2;
+  DepWait dep_wait;      // intra-stage dependency on the previous kernel by flag (else griddepcontrol.wait)
+  DepSignal dep_signal;  // ... and the flag this kernel publishes for the next one
   int l2_pf_chunks;  // bulk kernels: chunk pairs per warp prefetched into L2 beyond the smem ring (0 = off)
   int ctx_early;     // ctx was written >= 2 launches ago: slot/pos may be read before the PDL wait
 };
@@ -354,7 +356,7 @@ __global__ void __launch_bounds__(LIN_THREADS, 3) stream_ldg_kernel(const Stream
   }
   unsigned int* hist_s = stats_begin(a, smem_raw + (size_t)((a.K + 63) / 64) * 64 * sizeof(bf16));
   unsigned long long best = 0ull;
-  pdl_wait_prior();
+  if (a.dep_wait.flag) dep_wait(a.dep_wait, a.ctx); else pdl_wait_prior();
   hop_wait(a.wait, a.ctx);
   trace_mark(a.trace, 1, true);
   const int slot = a.ctx ? a.ctx[MDI_CTX_SLOT] : 0, pos = a.ctx ? a.ctx[MDI_CTX_POS] : 0;
@@ -374,6 +376,7 @@ __global__ void __launch_bounds__(LIN_THREADS, 3) stream_ldg_kernel(const Stream
   }
   stats_flush(a, hist_s, best);
   hop_signal(a.signal, a.ctx);
+  dep_signal(a.dep_signal, a.ctx);
   trace_mark(a.trace, 3, true);
   trace_mark(a.trace, 4, false);
 }
@@ -439,7 +442,7 @@ __global__ void __launch_bounds__(LIN_THREADS, STAGES == 2 ? 3 : (STAGES == 3 ? 
 
   int slot = 0, pos = 0;
   if (a.ctx_early && a.ctx) { slot = a.ctx[MDI_CTX_SLOT]; pos = a.ctx[MDI_CTX_POS]; }  // off the post-wait chain
-  pdl_wait_prior();
+  if (a.dep_wait.flag) dep_wait(a.dep_wait, a.ctx); else pdl_wait_prior();
   hop_wait(a.wait, a.ctx);
   trace_mark(a.trace, 1, true);
   if (!a.ctx_early && a.ctx) { slot = a.ctx[MDI_CTX_SLOT]; pos = a.ctx[MDI_CTX_POS]; }
@@ -480,6 +483,7 @@ __global__ void __launch_bounds__(LIN_THREADS, STAGES == 2 ? 3 : (STAGES == 3 ? 
   }
   stats_flush(a, hist_s, best);
   hop_signal(a.signal, a.ctx);
+  dep_signal(a.dep_signal, a.ctx);
   trace_mark(a.trace, 3, true);
   trace_mark(a.trace, 4, false);
 }
@@ -582,7 +586,7 @@ __global__ void __launch_bounds__(LIN_THREADS, 3) stream_ldg_fp8_kernel(const St
   }
   unsigned int* hist_s = stats_begin(a, smem_raw + (size_t)((a.K + 63) / 64) * 64 * sizeof(bf16));
   unsigned long long best = 0ull;
-  pdl_wait_prior();
+  if (a.dep_wait.flag) dep_wait(a.dep_wait, a.ctx); else pdl_wait_prior();
   hop_wait(a.wait, a.ctx);
   trace_mark(a.trace, 1, true);
   const int slot = a.ctx ? a.ctx[MDI_CTX_SLOT] : 0, pos = a.ctx ? a.ctx[MDI_CTX_POS] : 0;
@@ -607,6 +611,7 @@ __global__ void __launch_bounds__(LIN_THREADS, 3) stream_ldg_fp8_kernel(const St
   }
   stats_flush(a, hist_s, best);
   hop_signal(a.signal, a.ctx);
+  dep_signal(a.dep_signal, a.ctx);
   trace_mark(a.trace, 3, true);
   trace_mark(a.trace, 4, false);
 }
@@ -695,7 +700,8 @@ int mdi_linear_decode(const void* W, const void* W2, const void* bias, const voi
                       int act, int out_fp32, const int* wait_flag, int* status, long long wait_max_cycles,
                       int* signal_flag, unsigned int* done_ctr, int ctas_per_sm, int use_pdl, int variant,
                       unsigned int* hist, unsigned long long* amax, unsigned long long* trace, const float* wscale,
-                      const float* wscale2, cudaStream_t stream) {
+                      const float* wscale2, const int* dep_wait_flag, int* dep_signal_flag, unsigned int* dep_ctr,
+                      cudaStream_t stream) {
   if (K % 8 != 0) return -2;
   StreamArgs a{};
   a.W = (const bf16*)W; a.W2 = (const bf16*)W2; a.bias = (const bf16*)bias; a.bias2 = (const bf16*)bias2;
@@ -706,6 +712,7 @@ int mdi_linear_decode(const void* W, const void* W2, const void* bias, const voi
   a.signal = HopSignal{signal_flag, done_ctr};
   a.n_items = W2 ? N : (N + 1) / 2;
   a.hist = hist; a.amax = amax; a.trace = trace; a.wscale = wscale; a.wscale2 = wscale2;
+  a.dep_wait = DepWait{dep_wait_flag, status, wait_max_cycles}; a.dep_signal = DepSignal{dep_signal_flag, dep_ctr};
   a.ctx_early = (use_pdl >> 1) & 1; use_pdl &= 1;  // launch flags: bit 0 = PDL, bit 1 = ctx readable before the wait
   if (variant < 0) variant = g_default_variant;
   if (W2) return launch_stream<MODE_GATED>(a, variant, ctas_per_sm, use_pdl, stream);
@@ -716,7 +723,8 @@ int mdi_qkv_decode(const void* W, const void* bias, const void* x, const void* n
                    const float* sin, void* q_out, void* kv, const int* ctx, long long x_slot_stride, int K,
                    int n_head, int n_groups, int head_size, int rope_n_elem, int max_seq, float eps,
                    int unit_offset, const int* wait_flag, int* status, long long wait_max_cycles, int ctas_per_sm,
-                   int use_pdl, int variant, unsigned long long* trace, const float* wscale, cudaStream_t stream) {
+                   int use_pdl, int variant, unsigned long long* trace, const float* wscale, const int* dep_wait_flag,
+                   int* dep_signal_flag, unsigned int* dep_ctr, cudaStream_t stream) {
   if (K % 8 != 0 || head_size % 2 != 0 || rope_n_elem % 2 != 0 || rope_n_elem > head_size) return -2;
   StreamArgs a{};
   a.W = (const bf16*)W; a.bias = (const bf16*)bias; a.x = (const bf16*)x; a.norm_w = (const bf16*)norm_w;
@@ -727,6 +735,7 @@ int mdi_qkv_decode(const void* W, const void* bias, const void* x, const void* n
   a.wait = HopWait{wait_flag, status, wait_max_cycles};
   a.signal = HopSignal{nullptr, nullptr};
   a.trace = trace; a.wscale = wscale;
+  a.dep_wait = DepWait{dep_wait_flag, status, wait_max_cycles}; a.dep_signal = DepSignal{dep_signal_flag, dep_ctr};
   a.ctx_early = (use_pdl >> 1) & 1; use_pdl &= 1;
   a.n_items = (n_head + 2 * n_groups) * (head_size / 2);
   if (variant < 0) variant = g_default_variant;

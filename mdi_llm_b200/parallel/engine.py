@@ -148,6 +148,10 @@ class FusedStage:
             self.pos_arr = torch.zeros(n_slots, **i32)
             self.status = torch.zeros(4, **i32)  # [0] watchdog flag, [2:4] 64-bit exposed-wait cycle counter
             self.done_ctr = torch.zeros(1, **i32)
+            # intra-stage flag dependencies (see common.cuh: dep_wait / dep_signal): one flag per kernel of a step
+            self.dep_flags = torch.zeros(1024, **i32)
+            self.dep_ctr = torch.zeros(1, **i32)
+            self._step_seq = 0  # host mirror of ctx[STEP] (device mode: advance_step counts the same steps)
             self.xa = torch.zeros(C, **bf)
             self.xb = torch.zeros(C, **bf)
             self.q = torch.zeros(cfg.n_head * cfg.head_size, **bf)
@@ -321,7 +325,7 @@ class FusedStage:
                 out.append((li, "mlp"))
         return out
 
-    def enqueue_blocks(self, hop: Optional[HopTarget], wait_input: bool) -> None:
+    def enqueue_blocks(self, hop: Optional[HopTarget], wait_input: bool, dep_flags: bool = False) -> None:
         """All local sub-layers for one token.  Input residual: ``xa`` on the starter (embedding),
         ``hidden_in[slot]`` on a secondary.  The first kernel (QKV projection, or gate/up projection when
         the stage starts inside a layer) acquires the incoming hop; the last one (down projection, or
@@ -331,6 +335,20 @@ class FusedStage:
         x_in, x_in_stride = (self.xa, 0) if self.is_starter else (self.hidden_in, C)
         common = dict(use_pdl=self.use_pdl)
         units = self._units()
+        n_kernels = sum(3 if k == "attn" else 2 for _, k in units)
+        kidx = [0]
+
+        def dep() -> Dict[str, Any]:
+            """Flag dependency wiring of the next launch: wait on the previous kernel's flag, publish ours
+            (the first kernel keeps the grid-level wait, the last one has no local consumer)."""
+            j = kidx[0]
+            kidx[0] += 1
+            if not dep_flags:
+                return {}
+            base = self.dep_flags.data_ptr()
+            return dict(dep_wait=base + 4 * (j - 1) if j > 0 else None,
+                        dep_signal=base + 4 * j if j < n_kernels - 1 else None, dep_ctr=self.dep_ctr.data_ptr())
+
         for ui, (li, kind) in enumerate(units):
             first, last = ui == 0, ui == len(units) - 1
             blk = self.model.transformer.h[li]
@@ -345,10 +363,11 @@ class FusedStage:
                     n_head=cfg.n_head, n_groups=cfg.n_query_groups, head_size=cfg.head_size,
                     rope_n_elem=cfg.rope_n_elem, max_seq=self.S, norm_w=blk.norm_1.weight, **qw,
                     eps=cfg.norm_eps, unit_offset=cfg.unit_offset_norm, x_slot_stride=x_in_stride,
-                    trace=self._tr(f"L{li}.qkv"), ctas_per_sm=self._ctas("qkv"), ctx_early=not first, **wait, **common)
+                    trace=self._tr(f"L{li}.qkv"), ctas_per_sm=self._ctas("qkv"), ctx_early=not first, **wait, **dep(), **common)
                 ops.attn_decode(self.q, kv_layer, self.y_attn, self.part, self.tickets, self.ctx, n_head=cfg.n_head,
                                 n_groups=cfg.n_query_groups, head_size=cfg.head_size, max_seq=self.S,
-                                n_split=self.n_split, use_pdl=self.use_pdl, trace=self._tr(f"L{li}.attn"))
+                                n_split=self.n_split, use_pdl=self.use_pdl, trace=self._tr(f"L{li}.attn"),
+                                status=self.status.data_ptr(), wait_max_cycles=self.wait_max_cycles, **dep())
                 lw, src, name = self._w(blk.attn.proj), self.y_attn, f"L{li}.o_proj"
             else:
                 gw = {**self._w(blk.mlp.fc_1), **self._w(blk.mlp.fc_2, second=True)}
@@ -356,11 +375,13 @@ class FusedStage:
                                   eps=cfg.norm_eps, unit_offset=cfg.unit_offset_norm, act=self._gate_act(),
                                   x_slot_stride=x_in_stride, trace=self._tr(f"L{li}.gate_up"),
                                   ctas_per_sm=self._ctas("gate_up"), ctx_early=not first,
-                                  **(wait if first else {}), **common)
+                                  **(wait if first else dict(status=self.status.data_ptr(), wait_max_cycles=self.wait_max_cycles)),
+                                  **dep(), **common)
                 lw, src, name = self._w(blk.mlp.proj), self.h_mlp, f"L{li}.down"
             w_out = lw.pop("W")
             res = dict(residual=x_in, res_slot_stride=x_in_stride, ctx_early=True,  # never the first launch after advance_step
-                       ctas_per_sm=self._ctas("o_proj" if kind == "attn" else "down"))
+                       ctas_per_sm=self._ctas("o_proj" if kind == "attn" else "down"), status=self.status.data_ptr(),
+                       wait_max_cycles=self.wait_max_cycles, **dep())
             if not last:
                 ops.linear_decode(w_out, src, x_out, self.ctx, **lw, **res, trace=self._tr(name), **common)
                 x_in, x_in_stride = x_out, 0
@@ -466,7 +487,15 @@ class FusedStage:
         h = self.ctx_ring[self._ring_i]
         self._ring_i = (self._ring_i + 1) % self.ctx_ring.shape[0]
         h[ops.CTX_SLOT], h[ops.CTX_POS], h[ops.CTX_WAIT], h[ops.CTX_SIGNAL], h[ops.CTX_TOKEN] = slot, pos, wait, signal, token
+        h[ops.CTX_STEP] = self._step_seq  # same numbering as advance_step's: the flag dependencies wait for step + 1
+        self._step_seq += 1
         self.ctx.copy_(h, non_blocking=True)
+
+    def reset_deps(self) -> None:
+        """New generation: the step numbering restarts at 0, so the dependency flags do too."""
+        self.dep_flags.zero_()
+        self.dep_ctr.zero_()
+        self._step_seq = 0
 
 
 class FusedStageRunner(StageRunner):

@@ -23,6 +23,8 @@ pinned memory and reads every sampled token back (the end-to-end/streaming mode)
 """
 from __future__ import annotations
 
+import os
+
 import ctypes
 import time
 from typing import Any, Callable, Dict, List, Optional, Sequence, Tuple
@@ -45,6 +47,9 @@ class DevicePipeline:
         if hop not in ("p2p", "nccl"):
             raise ValueError("hop must be 'p2p' (fused peer stores + flags) or 'nccl' (send/recv baseline)")
         self.hop = hop if world > 1 else "p2p"
+        # kernels of a stage step depend on each other through device flags instead of grid completion
+        # (MDI_DEP_FLAGS=1; needs PDL, see common.cuh); off: every kernel waits with griddepcontrol.wait
+        self.dep_flags = bool(int(os.environ.get("MDI_DEP_FLAGS", "0"))) and use_pdl
         self.edge_groups: Optional[List[Any]] = None
         self.rank, self.world, self.n = rank, world, n_samples
         self.is_starter, self.is_last = rank == 0, rank == world - 1
@@ -140,6 +145,7 @@ class DevicePipeline:
             st.flags.zero_()
             st.status.zero_()
             st.done_ctr.zero_()
+            st.reset_deps()
             st.state.copy_(torch.tensor([0, 1, 0, 0], dtype=torch.int32))
             st.pos_arr.copy_(torch.tensor(self.prompt_lens, dtype=torch.int32))
             if self.is_starter:
@@ -254,9 +260,9 @@ class DevicePipeline:
                 st.enqueue_head(wait=True)
                 st.enqueue_sample()
                 st.enqueue_embed(from_tokens=True)
-            st.enqueue_blocks(self.next_hop, wait_input=True)
+            st.enqueue_blocks(self.next_hop, wait_input=True, dep_flags=self.dep_flags)
 
-        return st.graph(("full", dev_ctx, self.next_hop.hidden_ptr), build, warm=False)
+        return st.graph(("full", dev_ctx, self.next_hop.hidden_ptr, self.dep_flags), build, warm=False)
 
     def _g_head(self, dev_ctx: bool) -> ops.CudaGraph:
         st = self.stage
@@ -290,6 +296,7 @@ class DevicePipeline:
                     self._g_full(True).launch(self.n)
                     launched += self.n
                 self.round += 1
+        st._step_seq += launched  # advance_step numbered these steps on the device
         self.n_graph_launches += launched
         return launched
 

@@ -116,3 +116,23 @@ def test_local_output_and_prefill_sequences_bind():
     assert gemms[-1]["out_ptr"] == 0x3000 and gemms[-1]["signal_flag"] == 0x4000 and gemms[-1]["residual"] is not None
     assert all(g.get("out_ptr") is None for g in gemms[:-1])
     assert sum(1 for g in gemms if g.get("w2") is not None) == 2  # two MLP halves -> two gated GEMMs
+
+
+def test_flag_dependency_wiring_is_a_linear_chain():
+    """dep_flags=True: kernel j waits on kernel j-1's flag and publishes its own; the first kernel keeps
+    the grid-level wait, the last one has no local consumer (it carries the hop)."""
+    with dry_ops() as calls:
+        fs = FusedStage(_stage("secondary:0", 3, first_mlp_only=True), n_slots=2, max_seq_length=32)
+        fs.enqueue_blocks(HopTarget(0x1000, 0x2000), wait_input=True, dep_flags=True)
+    seq = [c[1] for c in calls]
+    base = fs.dep_flags.data_ptr()
+    assert seq[0].get("dep_wait") is None and seq[-1].get("dep_signal") is None
+    for j in range(1, len(seq)):
+        assert seq[j]["dep_wait"] == base + 4 * (j - 1) == seq[j - 1]["dep_signal"]
+        assert seq[j]["dep_ctr"] == fs.dep_ctr.data_ptr()
+    assert seq[-1]["signal_flag"] == 0x2000  # the hop is still signalled by the last kernel
+    # host-fed step descriptors carry a monotonically increasing step number
+    fs.set_ctx(0, 3); fs.set_ctx(1, 3)
+    assert fs._step_seq == 2 and int(fs.ctx_ring[1][ops.CTX_STEP]) == 1
+    fs.reset_deps()
+    assert fs._step_seq == 0
