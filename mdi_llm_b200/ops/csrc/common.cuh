@@ -152,12 +152,16 @@ __device__ __forceinline__ void dep_wait(const DepWait& w, const int* ctx) {
     // a producer is one kernel of this stage (< 1 ms); cap the watchdog at 2e8 cycles so that a protocol bug
     // shows up as status 2 within a fraction of a second per launch instead of hanging the GPU
     const long long cap = (w.max_cycles > 0 && w.max_cycles < 200000000ll) ? w.max_cycles : 200000000ll;
-    while (ld_acquire_gpu(w.flag) < want) {
+    // poll with plain volatile loads (an acquire per poll would invalidate this SM's L1 every iteration and
+    // disturb the producer CTAs that share it); one acquire when the value is there orders the data reads
+    while (ld_volatile(w.flag) < want) {
+      __nanosleep(20);
       if (clock64() - t0 > cap) {
         if (w.status) atomicExch(w.status, 2);
         break;
       }
     }
+    (void)ld_acquire_gpu(w.flag);
   }
   __syncthreads();
 }
