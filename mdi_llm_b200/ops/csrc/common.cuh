@@ -165,17 +165,30 @@ __device__ __forceinline__ void dep_wait(const DepWait& w, const int* ctx) {
   }
   __syncthreads();
 }
-// every CTA calls after its last output store (idle CTAs too: the ticket count is the whole grid)
+// every CTA calls after its last output store (idle CTAs too: the ticket count is the whole grid).
+// Same-address atomics from hundreds of CTAs serialise in L2 (~14 ns each), so the tickets are two-level:
+// 16 sub-counters on separate 128-byte lines (CTA index mod 16), whose last arrivals meet on a top counter.
+constexpr int DEP_FAN = 16;
+constexpr int DEP_CTR_STRIDE = 32;  // uints: one L2 line per counter; ctr[0] = top, ctr[(1 + i) * 32] = sub i
 __device__ __forceinline__ void dep_signal(const DepSignal& s, const int* ctx) {
   if (s.flag == nullptr) return;
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
     const unsigned int total = gridDim.x * gridDim.y * gridDim.z;
-    if (atomicAdd(s.ctr, 1u) == total - 1) {
-      *s.ctr = 0;
+    const unsigned int me = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+    const unsigned int fan = total < (unsigned)DEP_FAN ? total : (unsigned)DEP_FAN;
+    const unsigned int sub = me % fan;
+    const unsigned int n_sub = (total - sub + fan - 1) / fan;  // CTAs that share this sub-counter
+    unsigned int* c_sub = s.ctr + (1 + sub) * DEP_CTR_STRIDE;
+    if (atomicAdd(c_sub, 1u) == n_sub - 1) {
+      *c_sub = 0;
       __threadfence();
-      st_release_gpu(s.flag, ctx[MDI_CTX_STEP] + 1);
+      if (atomicAdd(s.ctr, 1u) == fan - 1) {
+        *s.ctr = 0;
+        __threadfence();
+        st_release_gpu(s.flag, ctx[MDI_CTX_STEP] + 1);
+      }
     }
   }
 }

@@ -150,7 +150,7 @@ class FusedStage:
             self.done_ctr = torch.zeros(1, **i32)
             # intra-stage flag dependencies (see common.cuh: dep_wait / dep_signal): one flag per kernel of a step
             self.dep_flags = torch.zeros(1024, **i32)
-            self.dep_ctr = torch.zeros(1, **i32)
+            self.dep_ctr = torch.zeros(17 * 32, **i32)  # two-level ticket counters, one L2 line each
             self._step_seq = 0  # host mirror of ctx[STEP] (device mode: advance_step counts the same steps)
             self.xa = torch.zeros(C, **bf)
             self.xb = torch.zeros(C, **bf)
