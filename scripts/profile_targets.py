@@ -2,7 +2,8 @@
 """Small deterministic workloads for `ncu --set full` captures (see profiles/README.md):
    decode: the Llama-3-8B gate/up weight-streaming kernel (+RMSNorm, SiLU*mul epilogue), 235 MB of weights
    gemm  : the tcgen05 prefill GEMM 2048 x 14336 x 4096
-   attn  : decode attention at 2048 context, Llama-3-8B heads"""
+   attn  : decode attention at 2048 context, Llama-3-8B heads
+   attnp : tcgen05 prefill attention, 2048-token prompt, Llama-3-8B heads"""
 import os
 import sys
 
@@ -41,3 +42,15 @@ elif what == "attn":
         ops.attn_decode(q, kv, y, part, tickets, ctx, n_head=H, n_groups=G, head_size=hs, max_seq=S, n_split=37)
 torch.cuda.synchronize()
 print("done", what)
+
+if what == "attnp":
+    from mdi_llm_b200.models.gpt import build_rope_cache
+
+    H, G, hs, S, T = 32, 8, 128, 2048, 2048
+    qkv = (torch.randn(T, (H + 2 * G) * hs, device="cuda") * 0.5).bfloat16()
+    cos, sin = build_rope_cache(S, hs, device=torch.device("cuda"))
+    cos, sin = cos.float().contiguous(), sin.float().contiguous()
+    pool = torch.zeros(1, 2, G, S, hs, device="cuda", dtype=torch.bfloat16)
+    for _ in range(4):
+        ops.attn_prefill(qkv, cos, sin, pool, 0, n_head=H, n_groups=G, head_size=hs, rope_n_elem=hs)
+torch.cuda.synchronize()
