@@ -54,6 +54,8 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.mdi_gemm_bf16_ex.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp,
                                      i32, i32, i32, i32, vp]
     lib.mdi_attn_prefill.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp]
+    lib.mdi_set_prefill_attn_pipe.argtypes = [i32]
+    lib.mdi_get_prefill_attn_pipe.restype = i32
     lib.mdi_advance_step.argtypes = [vp, vp, vp, i32, i32, i32, vp]
     lib.mdi_wait_flag.argtypes = [vp, vp, vp, i64, vp]
     lib.mdi_set_flag.argtypes = [vp, vp, vp]
@@ -95,12 +97,20 @@ def lib() -> ctypes.CDLL:
             handle = ctypes.CDLL(str(_build.LIB))
         _declare(handle)
         _lib = handle
+        if os.environ.get("MDI_PREFILL_ATTN_PIPE"):
+            handle.mdi_set_prefill_attn_pipe(int(os.environ["MDI_PREFILL_ATTN_PIPE"]))
         if os.environ.get("MDI_L2_PF_MB"):
             handle.mdi_set_l2_prefetch_mb(int(os.environ["MDI_L2_PF_MB"]))
         return handle
     except BaseException as e:  # noqa: BLE001
         _load_error = e
         raise OpsError(f"cannot load {_build.LIB}: {e}") from e
+
+
+def set_prefill_attn_pipe(on: bool) -> None:
+    """Prefill attention kernel: True = pipelined (double-buffered K/V^T tiles and score matrix), False = the
+    simple sequential kernel.  ``MDI_PREFILL_ATTN_PIPE`` sets it at load."""
+    lib().mdi_set_prefill_attn_pipe(int(bool(on)))
 
 
 def set_l2_prefetch_mb(mb: int) -> None:

@@ -38,12 +38,17 @@ cos, sin = cos.float().contiguous(), sin.float().contiguous()
 pool = torch.zeros(1, 2, G, S, hs, device="cuda", dtype=torch.bfloat16)
 for T in (128, 512, 2048, 4096):
     qkv = (torch.randn(T, (H + 2 * G) * hs, device="cuda") * 0.5).bfloat16()
+    ops.set_prefill_attn_pipe(False)
     ms = timeit(lambda: ops.attn_prefill(qkv, cos, sin, pool, 0, n_head=H, n_groups=G, head_size=hs, rope_n_elem=hs))
+    ops.set_prefill_attn_pipe(True)
+    ms_pipe = timeit(lambda: ops.attn_prefill(qkv, cos, sin, pool, 0, n_head=H, n_groups=G, head_size=hs, rope_n_elem=hs))
+    ops.set_prefill_attn_pipe(bool(int(os.environ.get("MDI_PREFILL_ATTN_PIPE", "0"))))
     q = torch.randn(1, H, T, hs, device="cuda").bfloat16()
     k = torch.randn(1, H, T, hs, device="cuda").bfloat16()
     ms_ref = timeit(lambda: torch.nn.functional.scaled_dot_product_attention(q, k, k, is_causal=True))
     flops = 4.0 * H * hs * T * T / 2  # causal
     out["attention"].append({"T": T, "tcgen05_ms": round(ms, 4), "tcgen05_tflops": round(flops / ms / 1e9, 1),
+                             "tcgen05_pipelined_ms": round(ms_pipe, 4), "tcgen05_pipelined_tflops": round(flops / ms_pipe / 1e9, 1),
                              "sdpa_ms (attention only, no rope/split/cache)": round(ms_ref, 4)})
     print(out["attention"][-1], flush=True)
 

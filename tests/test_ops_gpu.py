@@ -341,13 +341,15 @@ def test_qkv_decode_fp8_block_scaled():
 
 
 @pytest.mark.parametrize("H,G,hs,ne", [(32, 8, 128, 128), (8, 2, 64, 64), (4, 4, 128, 64), (8, 1, 64, 32)])
-@pytest.mark.parametrize("T", [5, 64, 128, 129, 300])
-def test_attn_prefill_tcgen05_matches_eager(H, G, hs, ne, T):
+@pytest.mark.parametrize("T", [5, 64, 128, 129, 300, 512])
+@pytest.mark.parametrize("pipe", [False, True])
+def test_attn_prefill_tcgen05_matches_eager(H, G, hs, ne, T, pipe):
     """RoPE + KV append + causal flash attention (tcgen05, S / P.V in TMEM) vs the eager attend_qkv."""
     from mdi_llm_b200.models.config import Config
     from mdi_llm_b200.models.gpt import CausalSelfAttention, build_rope_cache
 
     ops = _ops()
+    ops.set_prefill_attn_pipe(pipe)
     torch.manual_seed(T + H)
     cfg = Config.from_name("tiny-llama-1.1b", n_layer=1, n_embd=H * hs, n_head=H, n_query_groups=G,
                            rotary_percentage=ne / hs, block_size=512)
@@ -358,7 +360,11 @@ def test_attn_prefill_tcgen05_matches_eager(H, G, hs, ne, T):
     cos, sin = cos.float().contiguous(), sin.float().contiguous()
     pool = (torch.randn(n_slots, 2, G, S, hs, device="cuda") * 0.3).bfloat16()
     pool_ref = pool.clone()
-    y = ops.attn_prefill(qkv, cos, sin, pool, slot, n_head=H, n_groups=G, head_size=hs, rope_n_elem=ne)
+    try:
+        y = ops.attn_prefill(qkv, cos, sin, pool, slot, n_head=H, n_groups=G, head_size=hs, rope_n_elem=ne)
+        torch.cuda.synchronize()
+    finally:
+        ops.set_prefill_attn_pipe(False)
     attn = CausalSelfAttention(cfg).cuda().bfloat16()
     pos = torch.arange(T, device="cuda")
     with torch.no_grad():
