@@ -372,31 +372,47 @@ __global__ void __launch_bounds__(PA_THREADS, 1) attn_prefill_tcgen05_pipe_kerne
       const uint32_t tmem_s = tmem_base + (uint32_t)((t & 1) * 128) + lane_off;
       mbar_wait(&s_full[t & 1], (t >> 1) & 1);
       tcgen05_fence_after();
-      float mx = -INFINITY;
+      // only the diagonal tile (and a ragged last one) needs the causal / length mask; four independent
+      // max / sum chains keep the single warp per scheduler from serialising on FP latency
+      const bool full = (j0 + PA_BN - 1 <= m0) && (j0 + PA_BN <= p.T);
+      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll 1
       for (int c = 0; c < PA_BN / 32; ++c) {
         uint32_t sv[32];
         tmem_ld_32x32(tmem_s + (uint32_t)(c * 32), sv);
+        if (full) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int j = j0 + c * 32 + i;
-          if (j <= q_idx && j < p.T) mx = fmaxf(mx, __uint_as_float(sv[i]) * p.scale_log2);
+          for (int i = 0; i < 32; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(sv[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int j = j0 + c * 32 + i;
+            if (j <= q_idx && j < p.T) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(sv[i]));
+          }
         }
       }
+      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])) * p.scale_log2;  // scale > 0: max commutes
       const float m_new = fmaxf(m_run, mx);
       const float corr = (m_run == -INFINITY) ? 0.f : exp2f(m_run - m_new);
-      float psum = 0.f;
+      float ps4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
       for (int c = 0; c < PA_BN / 32; ++c) {
         uint32_t sv[32];
         tmem_ld_32x32(tmem_s + (uint32_t)(c * 32), sv);
         float pf[32];
+        if (full) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int j = j0 + c * 32 + i;
-          const float pv = (j <= q_idx && j < p.T && m_new != -INFINITY) ? exp2f(__uint_as_float(sv[i]) * p.scale_log2 - m_new) : 0.f;
-          pf[i] = pv;
-          psum += pv;
+          for (int i = 0; i < 32; ++i) {
+            pf[i] = exp2f(fmaf(__uint_as_float(sv[i]), p.scale_log2, -m_new));
+            ps4[i & 3] += pf[i];
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int j = j0 + c * 32 + i;
+            pf[i] = (j <= q_idx && j < p.T && m_new != -INFINITY) ? exp2f(fmaf(__uint_as_float(sv[i]), p.scale_log2, -m_new)) : 0.f;
+            ps4[i & 3] += pf[i];
+          }
         }
 #pragma unroll
         for (int v = 0; v < 4; ++v) {
@@ -408,7 +424,7 @@ __global__ void __launch_bounds__(PA_THREADS, 1) attn_prefill_tcgen05_pipe_kerne
           *reinterpret_cast<uint4*>(p_s + atom * ROW_ATOM + r * 128 + ((chunk ^ (r & 7)) << 4)) = o;
         }
       }
-      l_run = l_run * corr + psum;
+      l_run = l_run * corr + ((ps4[0] + ps4[1]) + (ps4[2] + ps4[3]));
       m_run = m_new;
 #pragma unroll
       for (int d = 0; d < HS; ++d) O[d] *= corr;
@@ -447,7 +463,7 @@ __global__ void __launch_bounds__(PA_THREADS, 1) attn_prefill_tcgen05_pipe_kerne
   }
 }
 
-static int g_prefill_attn_pipe = 0;  // see mdi_set_prefill_attn_pipe
+static int g_prefill_attn_pipe = 1;  // see mdi_set_prefill_attn_pipe
 
 template <int HS>
 static int launch_prefill_attn_pipe(const PrefillAttnParams& p, cudaStream_t stream) {

@@ -42,7 +42,7 @@ for T in (128, 512, 2048, 4096):
     ms = timeit(lambda: ops.attn_prefill(qkv, cos, sin, pool, 0, n_head=H, n_groups=G, head_size=hs, rope_n_elem=hs))
     ops.set_prefill_attn_pipe(True)
     ms_pipe = timeit(lambda: ops.attn_prefill(qkv, cos, sin, pool, 0, n_head=H, n_groups=G, head_size=hs, rope_n_elem=hs))
-    ops.set_prefill_attn_pipe(bool(int(os.environ.get("MDI_PREFILL_ATTN_PIPE", "0"))))
+    ops.set_prefill_attn_pipe(bool(int(os.environ.get("MDI_PREFILL_ATTN_PIPE", "1"))))
     q = torch.randn(1, H, T, hs, device="cuda").bfloat16()
     k = torch.randn(1, H, T, hs, device="cuda").bfloat16()
     ms_ref = timeit(lambda: torch.nn.functional.scaled_dot_product_attention(q, k, k, is_causal=True))

@@ -349,6 +349,7 @@ def test_attn_prefill_tcgen05_matches_eager(H, G, hs, ne, T, pipe):
     from mdi_llm_b200.models.gpt import CausalSelfAttention, build_rope_cache
 
     ops = _ops()
+    default_pipe = bool(ops.lib().mdi_get_prefill_attn_pipe())
     ops.set_prefill_attn_pipe(pipe)
     torch.manual_seed(T + H)
     cfg = Config.from_name("tiny-llama-1.1b", n_layer=1, n_embd=H * hs, n_head=H, n_query_groups=G,
@@ -364,7 +365,7 @@ def test_attn_prefill_tcgen05_matches_eager(H, G, hs, ne, T, pipe):
         y = ops.attn_prefill(qkv, cos, sin, pool, slot, n_head=H, n_groups=G, head_size=hs, rope_n_elem=ne)
         torch.cuda.synchronize()
     finally:
-        ops.set_prefill_attn_pipe(False)
+        ops.set_prefill_attn_pipe(default_pipe)
     attn = CausalSelfAttention(cfg).cuda().bfloat16()
     pos = torch.arange(T, device="cuda")
     with torch.no_grad():
