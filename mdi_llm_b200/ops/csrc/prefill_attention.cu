@@ -45,40 +45,63 @@ struct RopeSplitArgs {
   int T, T_pad, slot, n_head, n_groups, hs, ne, max_seq;
 };
 
+// grid (ceil(T / 16), H + 2G): one head slot (a q head, the k head or the v head of a group) for 16 tokens.
+// A thread owns 8 consecutive dims of one token: 16-byte loads / stores everywhere; V is additionally
+// transposed through shared memory so that V^T rows are written 16 tokens (32 B) at a time.
+constexpr int RS_TOK = 16;
 __global__ void __launch_bounds__(256) rope_split_kernel(const RopeSplitArgs a) {
-  const int t = blockIdx.x;
-  const int hs = a.hs, half_hs = hs / 2, ne = a.ne, half_ne = ne / 2;
+  __shared__ __align__(16) bf16 vt_tile[128][RS_TOK];
+  const int hs = a.hs, ne = a.ne, half_ne = ne / 2;
+  const int chunks = hs / 8;                       // 8-dim chunks per head (8 or 16)
+  const int tt = threadIdx.x / chunks, ch = threadIdx.x % chunks;
+  const int t = blockIdx.x * RS_TOK + tt, j = blockIdx.y;
   const int qpk = a.n_head / a.n_groups;
-  const int n_slots_hd = a.n_head + 2 * a.n_groups;
-  const bf16* row = a.qkv + (size_t)t * n_slots_hd * hs;
-  for (int pr = threadIdx.x; pr < n_slots_hd * half_hs; pr += blockDim.x) {
-    const int j = pr / half_hs, i = pr % half_hs;
-    int ra, rb;
-    bool rot;
-    if (i < half_ne) { ra = i; rb = i + half_ne; rot = true; }
-    else { const int u = i - half_ne; ra = ne + 2 * u; rb = ra + 1; rot = false; }
-    float xa = __bfloat162float(row[j * hs + ra]), xb = __bfloat162float(row[j * hs + rb]);
-    const int g = j / (qpk + 2), s = j % (qpk + 2);
-    if (rot && s <= qpk) {  // q and k heads rotate (NeoX half rotation, model.py:881-891), v does not
-      const float ca = a.cos[(size_t)t * ne + ra], sa = a.sin[(size_t)t * ne + ra];
-      const float cb = a.cos[(size_t)t * ne + rb], sb = a.sin[(size_t)t * ne + rb];
-      const float na = xa * ca - xb * sa, nb = xb * cb + xa * sb;
-      xa = na; xb = nb;
-    }
-    const bf16 va = __float2bfloat16_rn(xa), vb = __float2bfloat16_rn(xb);
-    if (s < qpk) {
-      bf16* dst = a.q_out + ((size_t)(g * qpk + s) * a.T_pad + t) * hs;
-      dst[ra] = va; dst[rb] = vb;
-    } else {
-      const size_t which = (s == qpk) ? 0 : 1;
-      bf16* dst = a.kv + ((((size_t)a.slot * 2 + which) * a.n_groups + g) * a.max_seq + t) * hs;
-      dst[ra] = va; dst[rb] = vb;
-      if (which == 1) {
-        a.vt[((size_t)g * hs + ra) * a.T_pad + t] = va;
-        a.vt[((size_t)g * hs + rb) * a.T_pad + t] = vb;
+  const int g = j / (qpk + 2), sl = j % (qpk + 2);
+  const bool active = tt < RS_TOK && t < a.T;
+  const int d0 = ch * 8;
+  uint4 out = make_uint4(0, 0, 0, 0);
+  if (active) {
+    const bf16* row = a.qkv + ((size_t)t * (a.n_head + 2 * a.n_groups) + j) * hs;
+    const uint4 xv = *reinterpret_cast<const uint4*>(row + d0);
+    out = xv;
+    if (sl <= qpk && d0 < ne) {  // q and k heads: NeoX half rotation on the first `ne` dims (model.py:881-891)
+      const bool lo = d0 < half_ne;
+      const uint4 pv = *reinterpret_cast<const uint4*>(row + (lo ? d0 + half_ne : d0 - half_ne));
+      const float4 c0 = *reinterpret_cast<const float4*>(a.cos + (size_t)t * ne + d0), c1 = *reinterpret_cast<const float4*>(a.cos + (size_t)t * ne + d0 + 4);
+      const float4 s0 = *reinterpret_cast<const float4*>(a.sin + (size_t)t * ne + d0), s1 = *reinterpret_cast<const float4*>(a.sin + (size_t)t * ne + d0 + 4);
+      const float cs[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+      const float sn[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+      const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w}, pw[4] = {pv.x, pv.y, pv.z, pv.w};
+      uint32_t ow[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float x0 = bf16lo(xw[q]), x1 = bf16hi(xw[q]);
+        const float r0 = lo ? -bf16lo(pw[q]) : bf16lo(pw[q]), r1 = lo ? -bf16hi(pw[q]) : bf16hi(pw[q]);
+        ow[q] = pack_bf16x2(fmaf(x0, cs[2 * q], r0 * sn[2 * q]), fmaf(x1, cs[2 * q + 1], r1 * sn[2 * q + 1]));
       }
+      out = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+    }
+    if (sl < qpk) {
+      *reinterpret_cast<uint4*>(a.q_out + ((size_t)(g * qpk + sl) * a.T_pad + t) * hs + d0) = out;
+    } else {
+      const size_t which = (sl == qpk) ? 0 : 1;
+      *reinterpret_cast<uint4*>(a.kv + ((((size_t)a.slot * 2 + which) * a.n_groups + g) * a.max_seq + t) * hs + d0) = out;
     }
   }
+  if (sl != qpk + 1) return;  // uniform per block: only V blocks transpose
+  if (tt < RS_TOK) {
+    const uint32_t w[4] = {out.x, out.y, out.z, out.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      vt_tile[d0 + 2 * q][tt] = __ushort_as_bfloat16((unsigned short)(w[q] & 0xffffu));
+      vt_tile[d0 + 2 * q + 1][tt] = __ushort_as_bfloat16((unsigned short)(w[q] >> 16));
+    }
+  }
+  __syncthreads();
+  const int d = threadIdx.x / 2, part = threadIdx.x % 2;  // two threads per V^T row, 8 tokens (16 B) each
+  if (d < hs)
+    *reinterpret_cast<uint4*>(a.vt + ((size_t)g * hs + d) * a.T_pad + blockIdx.x * RS_TOK + part * 8) =
+        *reinterpret_cast<const uint4*>(&vt_tile[d][part * 8]);
 }
 
 // ---- attention -----------------------------------------------------------------------------------------
@@ -497,12 +520,12 @@ extern "C" int mdi_attn_prefill(const void* qkv, const float* cos, const float* 
                                 int n_groups, int head_size, int rope_n_elem, int max_seq, cudaStream_t stream) {
   if (T <= 0 || T > max_seq || T_pad % PA_BN != 0 || T_pad < T || n_head % n_groups != 0) return -2;
   if (head_size != 64 && head_size != 128) return -3;
-  if (rope_n_elem % 2 != 0 || rope_n_elem > head_size) return -2;
+  if (rope_n_elem % 16 != 0 || rope_n_elem > head_size) return -2;  // the vectorised pre-pass rotates 8-dim chunks
   RopeSplitArgs r;
   r.qkv = (const bf16*)qkv; r.cos = cos; r.sin = sin; r.q_out = (bf16*)q_scratch; r.kv = (bf16*)kv; r.vt = (bf16*)vt_scratch;
   r.T = T; r.T_pad = T_pad; r.slot = slot; r.n_head = n_head; r.n_groups = n_groups; r.hs = head_size; r.ne = rope_n_elem;
   r.max_seq = max_seq;
-  rope_split_kernel<<<T, 256, 0, stream>>>(r);
+  rope_split_kernel<<<dim3((T + RS_TOK - 1) / RS_TOK, n_head + 2 * n_groups), 256, 0, stream>>>(r);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return (int)e;
 

@@ -428,7 +428,7 @@ class FusedStage:
             if kind == "attn":
                 h = ops.rmsnorm_rows(x, blk.norm_1.weight, eps, uo)
                 qkv = ops.gemm(h, self._dense(blk.attn.attn), bias=blk.attn.attn.bias, block_n=bn)
-                if self.prefill_attn == "tcgen05":  # RoPE + KV append + causal flash attention, S/P.V in TMEM
+                if self.prefill_attn == "tcgen05" and cfg.rope_n_elem % 16 == 0:  # RoPE + KV append + flash attention, S / P.V in TMEM
                     y = ops.attn_prefill(qkv, m.cos, m.sin, self.kv[li], slot, n_head=cfg.n_head,
                                          n_groups=cfg.n_query_groups, head_size=cfg.head_size, rope_n_elem=cfg.rope_n_elem)
                 else:  # eager helper (SDPA): the oracle path
