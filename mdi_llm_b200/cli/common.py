@@ -5,7 +5,6 @@ import logging
 import os
 from datetime import datetime
 from pathlib import Path
-from typing import Any, List, Optional, Sequence, Tuple
 
 PKG_DIR = Path(__file__).resolve().parent.parent
 SETTINGS_DIR = PKG_DIR / "settings_distr"

@@ -15,7 +15,7 @@ from __future__ import annotations
 import argparse
 import pickle
 from pathlib import Path
-from typing import Any, Dict, Optional
+from typing import Any, Dict
 
 import torch
 

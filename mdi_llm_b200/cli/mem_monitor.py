@@ -11,7 +11,6 @@ import argparse
 import csv
 import shlex
 import subprocess
-import sys
 import time
 from pathlib import Path
 from typing import List

@@ -11,7 +11,6 @@ from __future__ import annotations
 
 import argparse
 import cProfile
-import os
 import pstats
 import time
 from pathlib import Path

@@ -11,7 +11,6 @@ B200 execution path: ``--engine`` (auto|eager|cuda), ``--greedy``, ``--temperatu
 from __future__ import annotations
 
 import argparse
-import os
 from pathlib import Path
 
 from .common import IMG_DIR, LOGS_DIR, SETTINGS_DIR, append_run_stats, seed_everything, setup_debug_log, tokens_time_csv_name

@@ -26,7 +26,7 @@ import pickle
 import time
 from contextlib import nullcontext
 from pathlib import Path
-from typing import Any, Dict, Optional
+from typing import Any, Dict
 
 
 def build_parser() -> argparse.ArgumentParser:

@@ -16,7 +16,6 @@ checkpoints load unchanged.  Design differences (B200-first):
 """
 from __future__ import annotations
 
-import math
 import time
 from typing import Any, Iterator, List, Optional, Sequence, Tuple
 

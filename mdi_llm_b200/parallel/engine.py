@@ -20,7 +20,6 @@ Two ways to drive it:
 """
 from __future__ import annotations
 
-import math
 import os
 from dataclasses import dataclass
 from typing import Sequence, Any, Dict, List, Optional, Tuple

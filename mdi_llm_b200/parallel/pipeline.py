@@ -26,7 +26,6 @@ from __future__ import annotations
 import os
 
 import ctypes
-import time
 from typing import Any, Callable, Dict, List, Optional, Sequence, Tuple
 
 import torch

@@ -17,7 +17,6 @@ import json
 import logging
 import pickle
 import threading
-import time
 import warnings
 from pathlib import Path
 from typing import Any, Dict, List, Optional, Sequence, Tuple, Union

@@ -20,7 +20,7 @@ import threading
 import time
 from collections import deque
 from dataclasses import dataclass, field
-from typing import Any, Callable, Deque, Dict, Optional
+from typing import Any, Deque, Dict, Optional
 
 __all__ = ["Message", "build_msg", "Transport", "MessageQueue", "ChaosPolicy", "TransportError"]
 

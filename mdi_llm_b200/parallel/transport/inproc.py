@@ -6,7 +6,7 @@ tests to chain several stage runners inside one process (``pair()``).
 """
 from __future__ import annotations
 
-from typing import List, Optional, Tuple
+from typing import List, Optional
 
 from .base import ChaosPolicy, Message, MessageQueue, Transport
 

@@ -13,7 +13,7 @@ communicator a 2-node ring deadlocks (each rank's ``recv`` is queued behind its 
 from __future__ import annotations
 
 import threading
-from typing import Any, Dict, List, Optional
+from typing import Any, List, Optional
 
 import torch
 import torch.distributed as dist

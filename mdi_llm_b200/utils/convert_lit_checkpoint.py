@@ -10,7 +10,7 @@ from __future__ import annotations
 import gc
 import re
 from pathlib import Path
-from typing import Dict, List, Optional, Tuple, Union
+from typing import Dict, Tuple, Union
 
 import torch
 

@@ -11,9 +11,8 @@ import gc
 import math
 import sys
 import threading
-import time
 from contextlib import nullcontext
-from typing import Any, Dict, List, Mapping, Optional, Sequence, Tuple, Union
+from typing import Any, Dict, List, Mapping, Sequence, Tuple, Union
 
 import torch
 from torch import nn
