@@ -616,6 +616,112 @@ __global__ void __launch_bounds__(LIN_THREADS, 3) stream_ldg_fp8_kernel(const St
   trace_mark(a.trace, 4, false);
 }
 
+// ---- fp8 weights through the bulk-copy (TMA engine) ring ------------------------------------------------
+// Same per-warp mbarrier ring as the bf16 kernel, but a chunk is 2048 one-byte weights per row (so a stage
+// holds the same 2 x 2 KB), the activations sit in shared memory as fp16 and the block scales of the
+// chunk are requested before the mbarrier wait so their L2 latency hides behind the copy.
+constexpr int TS8 = 2048;
+template <int MODE, int STAGES>
+__global__ void __launch_bounds__(LIN_THREADS, 3) stream_bulk_fp8_kernel(const StreamArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int gw = blockIdx.x * LIN_WARPS + warp, n_gw = gridDim.x * LIN_WARPS;
+  trace_mark(a.trace, 0, true);
+  // layout: ring [WARPS][STAGES][2][TS8] bytes | x [K] fp16 | mbar [WARPS][STAGES] u64
+  unsigned char* ring = smem_raw + (size_t)warp * STAGES * 2 * TS8;
+  bf16* xs = reinterpret_cast<bf16*>(smem_raw + (size_t)LIN_WARPS * STAGES * 2 * TS8);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(xs + ((a.K + 63) / 64) * 64) + warp * STAGES;
+  __shared__ float red[LIN_WARPS];
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) mbar_init(&bars[s], 1);
+    mbar_fence_init();
+  }
+  __syncwarp();
+  const int n_chunks = (a.K + TS8 - 1) / TS8;
+  const int n_my = gw < a.n_items ? (a.n_items - gw + n_gw - 1) / n_gw : 0;
+  const int total = n_my * n_chunks;
+  auto issue = [&](int f) {
+    const int ii = f / n_chunks, c = f - ii * n_chunks;
+    const unsigned char *wa, *wb;
+    const float *sa, *sb;
+    item_rows_fp8<MODE>(a, gw + ii * n_gw, wa, wb, sa, sb);
+    const int k0 = c * TS8;
+    const uint32_t bytes = (uint32_t)min(TS8, a.K - k0);
+    const int st = f % STAGES;
+    unsigned char* dst = ring + (size_t)st * 2 * TS8;
+    mbar_expect_tx(&bars[st], 2 * bytes);
+    bulk_g2s(dst, wa + k0, bytes, &bars[st]);
+    bulk_g2s(dst + TS8, wb + k0, bytes, &bars[st]);
+  };
+  if (lane == 0)
+    for (int f = 0; f < min(STAGES, total); ++f) issue(f);
+  unsigned int* hist_s = stats_begin(a, reinterpret_cast<unsigned char*>(bars - warp * STAGES + LIN_WARPS * STAGES));
+  unsigned long long best = 0ull;
+
+  int slot = 0, pos = 0;
+  if (a.ctx_early && a.ctx) { slot = a.ctx[MDI_CTX_SLOT]; pos = a.ctx[MDI_CTX_POS]; }
+  if (a.dep_wait.flag) dep_wait(a.dep_wait, a.ctx); else pdl_wait_prior();
+  hop_wait(a.wait, a.ctx);
+  trace_mark(a.trace, 1, true);
+  if (!a.ctx_early && a.ctx) { slot = a.ctx[MDI_CTX_SLOT]; pos = a.ctx[MDI_CTX_POS]; }
+  stage_input(a.x + (size_t)slot * a.x_slot_stride, a.norm_w, a.eps, a.unit_offset, a.K, xs, red);
+  __half* xh16 = reinterpret_cast<__half*>(xs);  // activations to fp16 in place for the HFMA2 inner product
+  for (int i = threadIdx.x; i < a.K; i += LIN_THREADS) xh16[i] = __float2half_rn(__bfloat162float(xs[i]));
+  __syncthreads();
+  trace_mark(a.trace, 2, false);
+  pdl_launch_dependents();
+
+  const bf16* res = a.residual ? a.residual + (size_t)slot * a.res_slot_stride : nullptr;
+  const uint4* xv = reinterpret_cast<const uint4*>(xs);
+  float acc_a = 0.f, acc_b = 0.f;
+  int c = 0, ii = 0;
+  const float *sa = nullptr, *sb = nullptr;
+  for (int f = 0; f < total; ++f) {
+    const int st = f % STAGES;
+    if (c == 0) {
+      const unsigned char *wa, *wb;
+      item_rows_fp8<MODE>(a, gw + ii * n_gw, wa, wb, sa, sb);
+    }
+    const int k0 = c * TS8;
+    const int nv = min(TS8, a.K - k0) / 16;  // 16-weight vectors in this chunk (<= 128: 4 per lane)
+    float fa[4], fb[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int v = lane + 32 * u;
+      const int blk = (k0 >> 7) + (v >> 3);
+      fa[u] = v < nv ? __ldg(sa + blk) : 0.f;
+      fb[u] = v < nv ? __ldg(sb + blk) : 0.f;
+    }
+    mbar_wait(&bars[st], (uint32_t)((f / STAGES) & 1));
+    const uint4* wa4 = reinterpret_cast<const uint4*>(ring + (size_t)st * 2 * TS8);
+    const uint4* wb4 = wa4 + TS8 / 16;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int v = lane + 32 * u;
+      if (v < nv) {
+        const uint4 x0 = xv[(k0 >> 3) + 2 * v], x1 = xv[(k0 >> 3) + 2 * v + 1];
+        acc_a = fmaf(fa[u], dot16_fp8(wa4[v], x0, x1), acc_a);
+        acc_b = fmaf(fb[u], dot16_fp8(wb4[v], x0, x1), acc_b);
+      }
+    }
+    if (++c == n_chunks) {
+      const float da = warp_sum(acc_a), db = warp_sum(acc_b);
+      if (lane == 0) item_epilogue<MODE>(a, gw + ii * n_gw, da, db, slot, pos, res, hist_s, best);
+      acc_a = acc_b = 0.f;
+      c = 0;
+      ++ii;
+    }
+    __syncwarp();
+    if (lane == 0 && f + STAGES < total) issue(f + STAGES);
+  }
+  stats_flush(a, hist_s, best);
+  hop_signal(a.signal, a.ctx);
+  dep_signal(a.dep_signal, a.ctx);
+  trace_mark(a.trace, 3, true);
+  trace_mark(a.trace, 4, false);
+}
+
 static int g_num_sms = 0;
 static int num_sms() {
   if (!g_num_sms) {
@@ -655,8 +761,17 @@ static int launch_stream(const StreamArgs& a, int variant, int ctas_per_sm, int 
   const int grid_override = ctas_per_sm < 0 ? -ctas_per_sm : 0;  // experiments: ctas_per_sm = -G forces a grid of G CTAs
   if (ctas_per_sm <= 0) ctas_per_sm = 4;
   const int max_useful = (a.n_items + LIN_WARPS - 1) / LIN_WARPS;
-  if (a.wscale != nullptr) {  // fp8 block-scaled weights: register-streamed kernel
+  if (a.wscale != nullptr) {  // fp8 block-scaled weights
     if (a.K % 128 != 0) return -2;
+    if (variant != 0) {  // bulk-copy ring (2 stages), like the bf16 default
+      const size_t smem8b = (size_t)LIN_WARPS * 2 * 2 * TS8 + (size_t)((a.K + 63) / 64) * 64 * 2 + (size_t)LIN_WARPS * 2 * 8 +
+                            (a.hist ? STAT_BINS * 4 : 0);
+      if (smem8b <= 227 * 1024) {
+        const int per_sm8 = max(1, min(ctas_per_sm, (int)((227 * 1024) / (smem8b + 1024))));
+        const int grid8 = grid_override > 0 ? min(grid_override, max_useful) : max(1, min(sms * per_sm8, max_useful));
+        return launch_pdl(stream_bulk_fp8_kernel<MODE, 2>, a, grid8, smem8b, stream, use_pdl);
+      }
+    }
     const int grid = max(1, min(sms * min(ctas_per_sm, 3), max_useful));
     const size_t smem8 = (size_t)((a.K + 63) / 64) * 64 * sizeof(bf16) + (a.hist ? STAT_BINS * 4 : 0);
     return launch_pdl(stream_ldg_fp8_kernel<MODE>, a, grid, smem8, stream, use_pdl);
