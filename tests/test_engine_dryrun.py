@@ -136,3 +136,104 @@ def test_flag_dependency_wiring_is_a_linear_chain():
     assert fs._step_seq == 2 and int(fs.ctx_ring[1][ops.CTX_STEP]) == 1
     fs.reset_deps()
     assert fs._step_seq == 0
+
+
+# ---- DevicePipeline orchestration (fake graphs, no GPU) ---------------------------------------------------
+class _FakeGraph:
+    instances = []
+
+    def __init__(self):
+        self.n_nodes, self.launched = 0, 0
+        _FakeGraph.instances.append(self)
+
+    def __enter__(self):
+        self._mark = len(_FakeGraph.calls)
+        return self
+
+    def __exit__(self, *exc):
+        self.kernels = [c[0] for c in _FakeGraph.calls[self._mark:]]
+        self.n_nodes = len(self.kernels)
+
+    def launch(self, times=1):
+        self.launched += times
+
+
+@contextlib.contextmanager
+def dry_pipeline():
+    with dry_ops() as calls:
+        _FakeGraph.calls, _FakeGraph.instances = calls, []
+        fake_lib = mock.MagicMock()
+        fake_lib.mdi_wait_flag.return_value = 0
+        fake_lib.mdi_copy_signal.return_value = 0
+        stream = types.SimpleNamespace(synchronize=lambda: None)
+        with mock.patch.object(ops, "CudaGraph", _FakeGraph), mock.patch.object(ops, "lib", lambda: fake_lib), \
+                mock.patch.object(ops, "stream_ptr", lambda: 0), mock.patch.object(ops, "check", lambda code, what="": None), \
+                mock.patch.object(torch.cuda, "current_stream", lambda *a: stream), \
+                mock.patch.object(torch.cuda, "synchronize", lambda *a: None):
+            yield calls, fake_lib
+
+
+@pytest.mark.parametrize("mode", ["device", "host"])
+def test_device_pipeline_orchestration_single_stage(mode):
+    """prepare -> prefill -> decode rounds: graph launches, step numbering and the wrap-around prefill hop."""
+    from mdi_llm_b200.parallel.pipeline import DevicePipeline
+    from mdi_llm_b200.parallel.scheduler import SamplingParams
+
+    with dry_pipeline() as (calls, lib):
+        st = _stage("starter", 3)
+        pipe = DevicePipeline(st, 0, 1, n_samples=2, max_seq_length=32, sampling=SamplingParams.greedy())
+        prompts = [torch.tensor([1, 2, 3]), torch.tensor([4, 5, 6, 7])]
+        out = pipe.generate(prompts, 5, mode=mode)
+    assert set(out) == {0, 1} and out[0].shape == (1, 3 + 5) and out[1].shape == (1, 4 + 5)
+    assert out[0][0, :3].tolist() == [1, 2, 3]
+    # prefill: one wrap-around copy+signal per sample (world == 1: the last stage is also the starter)
+    assert lib.mdi_copy_signal.call_count == 2
+    # rounds 1..4 run the full step for both samples, the final round only the head (ln_f + lm_head + sample)
+    full = [g for g in _FakeGraph.instances if "qkv_decode" in g.kernels]
+    head = [g for g in _FakeGraph.instances if "qkv_decode" not in g.kernels and "sample_fast" in g.kernels]
+    assert sum(g.launched for g in full) == 4 * 2 and sum(g.launched for g in head) == 2
+    assert pipe.n_graph_launches == 10
+    dev_ctx = mode == "device"
+    assert all(("advance_step" in g.kernels) == dev_ctx for g in full + head)
+    # the host's step counter stays ahead of the device's in both modes (2 prefill descriptors + 10 steps): the
+    # flag dependencies only need it to be strictly increasing from step to step
+    assert pipe.stage._step_seq == 12
+    with pytest.raises(ValueError, match="exceed block size"):
+        pipe.prepare(prompts, 40)
+
+
+def test_device_pipeline_orchestration_two_stages():
+    """rank 0 of 2: prefill hop fused into the last GEMM (no copy kernel); rank 1 (last): waits for its input
+    flag per sample and returns only the final row with the copy+signal kernel; secondaries skip the head."""
+    from mdi_llm_b200.parallel.pipeline import DevicePipeline
+    from mdi_llm_b200.parallel.scheduler import SamplingParams
+
+    prompts = [torch.tensor([1, 2, 3]), torch.tensor([4, 5, 6, 7])]
+    with dry_pipeline() as (calls, lib):
+        p0 = DevicePipeline(_stage("starter", 2), 0, 2, n_samples=2, max_seq_length=32, sampling=SamplingParams.greedy(),
+                            exportable=False)
+        p0.next_hop, p0.next_prefill_ptr = HopTarget(0x10000, 0x20000), 0x30000
+        p0.prepare(prompts, 4)
+        calls.clear()
+        p0.prefill()
+        gemms = [c[1] for c in calls if c[0] == "gemm"]
+        hops = [g for g in gemms if g.get("out_ptr") is not None]
+        assert len(hops) == 2 and lib.mdi_copy_signal.call_count == 0 and lib.mdi_wait_flag.call_count == 0
+        assert hops[0]["out_ptr"] == 0x30000 and hops[1]["out_ptr"] == 0x30000 + 32 * 256 * 2  # slot 1: + max_prompt_len * C * 2
+        assert all(h["signal_flag"] == 0x20000 for h in hops)
+        p0.decode_rounds(3)
+        assert p0.n_graph_launches == 6
+
+    with dry_pipeline() as (calls, lib):
+        p1 = DevicePipeline(_stage("secondary:0", 1), 1, 2, n_samples=2, max_seq_length=32, sampling=SamplingParams.greedy(),
+                            exportable=False)
+        p1.next_hop = HopTarget(0x40000, 0x50000)
+        p1.prepare(prompts, 4)
+        calls.clear()
+        p1.prefill()
+        assert lib.mdi_wait_flag.call_count == 2 and lib.mdi_copy_signal.call_count == 2
+        assert all(c[1].get("out_ptr") is None for c in calls if c[0] == "gemm")
+        p1.decode_rounds(4)  # rounds 1..3 forward; the final round has nothing to do on a secondary
+        g = [x for x in _FakeGraph.instances if "qkv_decode" in x.kernels]
+        assert sum(x.launched for x in g) == 6 and not any("sample_fast" in x.kernels for x in _FakeGraph.instances)
+        assert g[0].kernels[0] == "advance_step" and g[0].kernels[1] == "qkv_decode"
