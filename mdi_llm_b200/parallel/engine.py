@@ -414,6 +414,10 @@ class FusedStage:
         eps, uo = cfg.norm_eps, cfg.unit_offset_norm
         units = self._units()
         bn = 256 if T > 128 else 128  # 128x256 tiles reach 1.18 PFLOP/s; short prompts want more (smaller) tiles
+        # the tcgen05 attention kernel covers a prompt that starts at position 0 (every prefill of the pipeline);
+        # anything else (a continuation at an offset) takes the eager helper
+        use_fa = (self.prefill_attn == "tcgen05" and cfg.rope_n_elem % 16 == 0
+                  and int(input_pos[0]) == 0 and int(input_pos.numel()) == T)
 
         def out_gemm(a_in: torch.Tensor, lin: Any, last: bool) -> Optional[torch.Tensor]:
             if hop is not None and last:
@@ -427,7 +431,7 @@ class FusedStage:
             if kind == "attn":
                 h = ops.rmsnorm_rows(x, blk.norm_1.weight, eps, uo)
                 qkv = ops.gemm(h, self._dense(blk.attn.attn), bias=blk.attn.attn.bias, block_n=bn)
-                if self.prefill_attn == "tcgen05" and cfg.rope_n_elem % 16 == 0:  # RoPE + KV append + flash attention, S / P.V in TMEM
+                if use_fa:  # RoPE + KV append + causal flash attention with S / P.V in TMEM
                     y = ops.attn_prefill(qkv, m.cos, m.sin, self.kv[li], slot, n_head=cfg.n_head,
                                          n_groups=cfg.n_query_groups, head_size=cfg.head_size, rope_n_elem=cfg.rope_n_elem)
                 else:  # eager helper (SDPA): the oracle path
