@@ -79,6 +79,7 @@ BACKEND = "nccl"  # DDP backend for train.py (gloo on CPU-only hosts)
 
 VERB = False
 DEBUG = False
+PLOTS = False
 
 
 class TrainingConfig:
@@ -124,3 +125,38 @@ class TrainingConfig:
         if value not in DTYPE_TORCH_MAPPING:
             raise ValueError(f"Supported dtypes are: {list(DTYPE_TORCH_MAPPING)}")
         self._dtype_torch = DTYPE_TORCH_MAPPING[value]
+
+
+# ---- per-family config lists (the reference's module-level names, config.py:170-1669) --------------
+# The registry is table-driven (models/registry.py); these views group it the way the reference's source does
+# so that ``from sub.config import llama_3`` style code keeps working.
+def _family(*patterns: str):
+    import re as _re
+
+    rx = [_re.compile(p) for p in patterns]
+    return [c for c in configs if any(r.search(c["name"]) for r in rx)]
+
+
+stablecode = _family(r"^stablecode", r"^stable-code")
+pythia = _family(r"^pythia")
+dolly = _family(r"^dolly")
+redpajama_incite = _family(r"^RedPajama-INCITE")
+falcon = _family(r"^falcon-(7|40)b")
+falcon180b = _family(r"^falcon-180B")
+open_LLaMA = _family(r"^open_llama")
+vicuna = _family(r"^vicuna")
+long_chat = _family(r"^longchat")
+nous_research = _family(r"^Nous-Hermes")
+llama_2 = _family(r"^Llama-2-\d+b(-chat)?-hf$")
+llama_3 = _family(r"^Llama-3")
+gemma = _family(r"^Gemma")
+codegemma = _family(r"^CodeGemma")
+danube2 = _family(r"^Danube2")
+freewilly_2 = _family(r"^FreeWilly2")
+code_llama = _family(r"^CodeLlama")
+platypus = _family(r"Platypus")
+together_llama2_32k = _family(r"^LLaMA-2-7B-32K")
+phi = _family(r"^phi")
+mistral = _family(r"^Mistral|^Mixtral")
+tiny_llama = _family(r"^tiny-llama")
+llama_2_function_calling = _family(r"function-calling")

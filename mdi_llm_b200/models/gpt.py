@@ -27,7 +27,7 @@ from .config import Config
 
 __all__ = [
     "GPT", "Block", "CausalSelfAttention", "RMSNorm", "KVPool", "build_rope_cache", "build_mask_cache",
-    "apply_rope", "sample", "sample_top_p", "build_norm", "build_mlp", "LLaMAMLP",
+    "apply_rope", "sample", "sample_top_p", "multinomial_num_samples_1", "KVCache", "build_norm", "build_mlp", "LLaMAMLP",
     "GptNeoxMLP", "GemmaMLP", "LLaMAMoE",
 ]
 
@@ -35,6 +35,11 @@ __all__ = [
 # =============================================================================================
 # sampling
 # =============================================================================================
+def multinomial_num_samples_1(probs: torch.Tensor, generator: Optional[torch.Generator] = None) -> torch.Tensor:
+    """One draw per row (reference model.py:34-39)."""
+    return torch.multinomial(probs, num_samples=1, generator=generator)
+
+
 def sample_top_p(logits: torch.Tensor, top_p: float) -> torch.Tensor:
     """Nucleus filtering on a 1-D logits vector (reference model.py:42-64)."""
     order = torch.argsort(logits, descending=False)
@@ -138,6 +143,28 @@ def apply_rope(x: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor) -> torch.T
     half = x.size(-1) // 2
     rot = torch.cat((-x[..., half:], x[..., :half]), dim=-1)
     return (x * cos + rot * sin).to(x.dtype)
+
+
+class KVCache(nn.Module):
+    """Stand-alone per-layer KV cache with the reference's interface (model.py:894-937): ``forward(input_pos,
+    k, v)`` writes the rows at ``input_pos`` and returns the whole cache.  The models here use slots of a
+    :class:`KVPool` instead (G group heads, indexed by sample on the device); this class is kept for code written
+    against the reference's ``KVCache``."""
+
+    def __init__(self, k_shape: Tuple[int, int, int, int], v_shape: Tuple[int, int, int, int],
+                 device: Optional[torch.device] = None, dtype: Optional[torch.dtype] = None) -> None:
+        super().__init__()
+        self.register_buffer("k", torch.zeros(k_shape, device=device, dtype=dtype), persistent=False)
+        self.register_buffer("v", torch.zeros(v_shape, device=device, dtype=dtype), persistent=False)
+
+    def forward(self, input_pos: torch.Tensor, k: torch.Tensor, v: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        self.k = self.k.to(k.dtype)
+        self.v = self.v.to(v.dtype)
+        return self.k.index_copy_(2, input_pos, k), self.v.index_copy_(2, input_pos, v)
+
+    def reset_parameters(self) -> None:
+        torch.nn.init.zeros_(self.k)
+        torch.nn.init.zeros_(self.v)
 
 
 class KVPool:

@@ -21,7 +21,7 @@ import torch.nn as nn
 from .config import Config
 from .gpt import Block, KVPool, RopeMixin, build_norm, run_blocks
 
-__all__ = ["StageModule", "StarterNode", "SecondaryNode", "FinisherNode", "build_stage"]
+__all__ = ["StageModule", "NodePrototype", "StarterNode", "SecondaryNode", "FinisherNode", "build_stage"]
 
 
 class StageModule(nn.Module, RopeMixin):
@@ -101,6 +101,9 @@ class StageModule(nn.Module, RopeMixin):
         cos, sin = self.rope_for(T, input_pos)
         return run_blocks(self.transformer.h, x, cos, sin, input_pos,
                           self.kv_pool if input_pos is not None else None, slot)
+
+
+NodePrototype = StageModule  # the reference's name for the common base (submodels.py:34)
 
 
 class StarterNode(StageModule):

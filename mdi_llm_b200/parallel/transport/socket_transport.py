@@ -57,7 +57,21 @@ def _to_wire(msg: Message) -> Message:
     return msg
 
 
-class InputNodeConnection:
+class NodeConnection:
+    """Common interface of the two socket endpoints (reference connections.py:15-54): a ``running`` event, a
+    ``launch()`` that starts the worker thread and a ``shutdown()`` that stops it."""
+
+    msg_format = {"sample_index": 0, "data": None, "stop": False}
+    name = "connection"
+
+    def launch(self) -> None:  # pragma: no cover - overridden
+        raise NotImplementedError
+
+    def shutdown(self) -> None:  # pragma: no cover - overridden
+        raise NotImplementedError
+
+
+class InputNodeConnection(NodeConnection):
     """Server side: accept the previous node, then RX thread -> queue."""
 
     name = "input_queue"
@@ -144,7 +158,7 @@ class InputNodeConnection:
                 pass
 
 
-class OutputNodeConnection:
+class OutputNodeConnection(NodeConnection):
     """Client side: connect to the next node, then queue -> TX thread."""
 
     name = "output_queue"

@@ -21,6 +21,7 @@ from .. import config as C
 from .data_loader import get_batch
 
 __all__ = [
+    "format_output",
     "get_obj_size", "estimate_loss", "get_lr", "loading_bar", "waiting_animation", "remove_prefix",
     "find_eot", "detect_stop_tokens", "serialize_params", "deserialize_params", "as_id_list",
 ]
@@ -132,3 +133,24 @@ def serialize_params(params: Mapping[str, Any]) -> Dict[str, Any]:
 
 def deserialize_params(params: Dict[str, Any]) -> Dict[str, Any]:
     return {k: (torch.tensor(v) if isinstance(v, list) else v) for k, v in params.items()}
+
+
+def format_output(text: str, user_tag: str = "<|user|>", assistant_tag: str = "<|assistant|>", color: bool = False) -> str:
+    """Pretty-print a chat transcript: every ``<|user|>`` / ``<|assistant|>`` turn on its own paragraph with
+    a speaker label (optionally ANSI-coloured).  The reference leaves this as an empty stub
+    (``utils.py:228-238``: "isolate the <|user|> and <|assistant|> elements ... maybe format with color")."""
+    import re as _re
+
+    parts = _re.split(f"({_re.escape(user_tag)}|{_re.escape(assistant_tag)})", text)
+    out, who = [], None
+    for part in parts:
+        if part == user_tag:
+            who = "user"
+        elif part == assistant_tag:
+            who = "assistant"
+        elif part.strip():
+            label = {"user": "User", "assistant": "Assistant", None: ""}[who]
+            if color and label:
+                label = ("\033[36m" if who == "user" else "\033[33m") + label + "\033[0m"
+            out.append(f"{label}: {part.strip()}" if label else part.strip())
+    return "\n\n".join(out)

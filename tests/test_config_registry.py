@@ -55,3 +55,55 @@ def test_registry_matches_reference(tmp_path, monkeypatch):
         mine = Config(**name_to_config[rc["name"]])
         theirs = Config(**rc)
         assert mine.asdict() == theirs.asdict(), rc["name"]
+
+
+@pytest.mark.skipif(not os.path.isfile(REF_CFG), reason="reference not mounted")
+def test_family_lists_match_reference(tmp_path, monkeypatch):
+    """The per-family module-level lists of the reference (`from sub.config import llama_3` ...) exist here as
+    views of the table-driven registry, with the same members."""
+    import mdi_llm_b200.config as C
+
+    monkeypatch.chdir(tmp_path)
+    spec = importlib.util.spec_from_file_location("_refcfg2", REF_CFG)
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    families = ["stablecode", "pythia", "dolly", "redpajama_incite", "falcon", "falcon180b", "open_LLaMA", "vicuna", "long_chat",
+                "nous_research", "llama_2", "llama_3", "gemma", "codegemma", "danube2", "freewilly_2", "code_llama", "platypus",
+                "together_llama2_32k", "phi", "mistral", "tiny_llama", "llama_2_function_calling"]
+
+    all_names = {c["name"] for c in configs}
+
+    def members(obj):  # the reference keeps lists of dicts, single dicts and "{}" name templates
+        items = [obj] if isinstance(obj, dict) else [c for c in obj if isinstance(c, dict)]
+        out = set()
+        for c in items:
+            n = c["name"]
+            if "{}" in n:
+                head, tail = n.split("{}")
+                out |= {x for x in all_names if x.startswith(head) and x.endswith(tail)}
+            else:
+                out.add(n)
+        return out
+
+    for fam in families:
+        theirs, mine = members(getattr(ref, fam)), {c["name"] for c in getattr(C, fam)}
+        assert theirs and theirs <= mine, (fam, sorted(theirs - mine))
+    assert C.PLOTS is False
+
+
+def test_compat_names_exist():
+    from mdi_llm_b200.models.gpt import KVCache, multinomial_num_samples_1
+    from mdi_llm_b200.models.stage import NodePrototype, StageModule
+    from mdi_llm_b200.parallel.transport.socket_transport import InputNodeConnection, NodeConnection, OutputNodeConnection
+    from mdi_llm_b200.utils.misc import format_output
+    import torch
+
+    assert NodePrototype is StageModule and issubclass(InputNodeConnection, NodeConnection) and issubclass(OutputNodeConnection, NodeConnection)
+    kv = KVCache((1, 2, 8, 4), (1, 2, 8, 4), dtype=torch.float32)
+    k, v = kv(torch.tensor([3]), torch.ones(1, 2, 1, 4), torch.full((1, 2, 1, 4), 2.0))
+    assert k[0, 0, 3].tolist() == [1.0] * 4 and v[0, 1, 3].tolist() == [2.0] * 4 and float(k.sum()) == 8.0
+    kv.reset_parameters()
+    assert float(kv.k.abs().sum()) == 0.0
+    assert multinomial_num_samples_1(torch.tensor([[0.0, 1.0, 0.0]])).tolist() == [[1]]
+    txt = format_output("<|user|>hi there<|assistant|>hello!<|user|>bye")
+    assert txt == "User: hi there\n\nAssistant: hello!\n\nUser: bye"
