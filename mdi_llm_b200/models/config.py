@@ -19,7 +19,7 @@ from typing import Any, Dict, Optional, Union
 
 import yaml
 
-__all__ = ["Config", "find_multiple"]
+__all__ = ["Config", "GPTConfig", "find_multiple"]
 
 
 def find_multiple(n: int, k: int) -> int:
@@ -190,3 +190,16 @@ class Config:
         with open(p, "w", encoding="utf-8") as fp:
             yaml.safe_dump(self.asdict(), fp)
         return p
+
+
+def GPTConfig(block_size: int = 1024, vocab_size: int = 50304, n_layer: int = 12, n_head: int = 12, n_embd: int = 768,
+              dropout: float = 0.0, bias: bool = True, activation_function: str = "GELU", **extra: Any) -> Config:
+    """The second-generation (GPT-2 / nanoGPT) configuration object as a factory for :class:`Config`
+    (reference ``old/GPT2/sub/model.py:38-62``): learned positions, LayerNorm, GELU MLP, tied head.
+    ``dropout`` is accepted and ignored (inference / the trainer here run without dropout)."""
+    if activation_function.upper() != "GELU":
+        raise ValueError("only the GELU MLP of GPT-2 is supported")
+    return Config(name=extra.pop("name", f"gpt2-custom-{n_layer}l"), block_size=block_size, vocab_size=vocab_size,
+                  padded_vocab_size=vocab_size, n_layer=n_layer, n_head=n_head, n_embd=n_embd, rotary_percentage=0.0,
+                  parallel_residual=False, bias=bias, norm_class_name="LayerNorm", mlp_class_name="GptNeoxMLP",
+                  gelu_approximate="tanh", pos_embedding="learned", tie_embeddings=True, **extra)

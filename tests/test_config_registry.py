@@ -107,3 +107,17 @@ def test_compat_names_exist():
     assert multinomial_num_samples_1(torch.tensor([[0.0, 1.0, 0.0]])).tolist() == [[1]]
     txt = format_output("<|user|>hi there<|assistant|>hello!<|user|>bye")
     assert txt == "User: hi there\n\nAssistant: hello!\n\nUser: bye"
+
+
+def test_legacy_gptconfig_factory():
+    import torch
+    from mdi_llm_b200.models.config import GPTConfig
+    from mdi_llm_b200.models.gpt import GPT
+
+    cfg = GPTConfig(block_size=32, vocab_size=64, n_layer=2, n_head=2, n_embd=16, dropout=0.1)
+    assert cfg.pos_embedding == "learned" and cfg.tie_embeddings and cfg.norm_class_name == "LayerNorm"
+    m = GPT(cfg).eval()
+    assert m.lm_head.weight is m.transformer.wte.weight
+    assert m(torch.tensor([[1, 2, 3]])).shape == (1, 3, 64)
+    with pytest.raises(ValueError):
+        GPTConfig(activation_function="ReLU")
