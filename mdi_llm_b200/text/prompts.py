@@ -238,3 +238,9 @@ def get_user_prompt(prompt: str, n_samples: int = 1, prompt_style: Optional[Prom
     if kwargs.get("verb"):
         print(out)
     return out
+
+
+def get_prompt(prompt: str, n_samples: int = 1, **kwargs: Any) -> List[str]:
+    """Second-generation name of :func:`get_user_prompt` without a prompt style
+    (reference ``old/GPT2/sub/utils.py:478-531``)."""
+    return get_user_prompt(prompt, n_samples, None, **kwargs)
