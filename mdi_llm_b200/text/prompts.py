@@ -241,6 +241,6 @@ def get_user_prompt(prompt: str, n_samples: int = 1, prompt_style: Optional[Prom
 
 
 def get_prompt(prompt: str, n_samples: int = 1, **kwargs: Any) -> List[str]:
-    """Second-generation name of :func:`get_user_prompt` without a prompt style
+    """Second-generation prompt expansion: no prompt style, the text is used verbatim
     (reference ``old/GPT2/sub/utils.py:478-531``)."""
-    return get_user_prompt(prompt, n_samples, None, **kwargs)
+    return get_user_prompt(prompt, n_samples, Default(), **kwargs)

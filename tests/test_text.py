@@ -105,3 +105,12 @@ def test_misc_helpers():
     assert detect_stop_tokens(toks[:, :7], ([5, 9],)) and not detect_stop_tokens(toks, ([5, 9],))
     assert get_lr(0) == 0 and abs(get_lr(2000) - 3e-4) < 1e-12 and get_lr(10 ** 7) == 6e-5
     assert loading_bar(5, 10, 10) == "[=====    ]"
+
+
+def test_legacy_get_prompt_is_verbatim(tmp_path):
+    from mdi_llm_b200.text.prompts import get_prompt
+
+    assert get_prompt("hi", 2) == ["hi", "hi"]
+    f = tmp_path / "p.txt"
+    f.write_text("first\nparagraph\n\nsecond\n")
+    assert get_prompt(f"FILE:{f}", 3) == ["first\nparagraph\n", "second\n", "\n"]
