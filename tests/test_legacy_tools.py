@@ -83,3 +83,12 @@ def test_toy_models_train_a_little():
             opt.zero_grad(); loss.backward(); opt.step()
         assert loss.item() < first
         assert m.generate(data[:1, :3], 5, temperature=0.0).shape == (1, 8)
+
+
+def test_shared_parse_args_builds_both_flag_sets():
+    from mdi_llm_b200.cli.common import parse_args
+
+    tr = parse_args(True, ["--batch-size", "4", "--init", "resume", "--always-update"])
+    assert tr.batch_size == 4 and tr.init == "resume" and tr.always_update and not tr.verb
+    gen = parse_args(False, ["--n-samples", "3", "-p", "--n-tokens", "10", "--prompt", "hi"])
+    assert gen.plots and gen.n_samples == 3 and gen.n_tokens == 10 and gen.prompt == "hi"
