@@ -76,7 +76,9 @@ def _write_checkpoint(ckpt: Path, model_name: str, device: str) -> None:
         else:
             sd[name] = rnd(*t.shape)
     V = cfg.padded_vocab_size
-    torch.save(sd, ckpt / "lit_model.pth")
+    tmp = ckpt / "lit_model.pth.tmp"  # atomic: a run killed half-way must not leave a truncated checkpoint behind
+    torch.save(sd, tmp)
+    os.replace(tmp, ckpt / "lit_model.pth")
     with open(ckpt / "model_config.yaml", "w") as f:
         yaml.safe_dump(cfg.asdict(), f)
     _write_tokenizer(ckpt, V)
@@ -128,7 +130,13 @@ def run_reference(args: Any) -> Dict[str, Any]:
         ckpt = Path(os.environ.get("MDI_REF_CKPT_DIR", "/tmp/mdi_ref_ckpt")) / "custom" / (cfg.name + "-random")
         if rank == 0 and not (ckpt / "lit_model.pth").is_file():
             _write_checkpoint(ckpt, model_name, dev)
-        if rank == 0 and world > 1 and not (ckpt / "chunks" / f"{world}nodes" / "model_starter.pth").is_file():
+        chunk_dir = ckpt / "chunks" / f"{world}nodes"
+        wanted = [chunk_dir / "model_starter.pth"] + [chunk_dir / f"model_secondary{i}.pth" for i in range(world - 1)]
+        done_mark = chunk_dir / ".complete"
+        if rank == 0 and world > 1 and not (done_mark.is_file() and all(f.is_file() for f in wanted)):
+            import shutil
+
+            shutil.rmtree(chunk_dir, ignore_errors=True)  # leftovers of an interrupted split
             # the reference's documented workflow: prepare_model.py splits the checkpoint first
             # (src/prepare_model.py:57-58).  (Its split-on-the-fly path calls torch.load(device=...),
             # model_dist.py:456, which current torch rejects.)
@@ -137,6 +145,7 @@ def run_reference(args: Any) -> Dict[str, Any]:
             _, full_sd = load_from_pt(ckpt)
             split_and_store(full_sd, world, ckpt)
             del full_sd
+            done_mark.write_text("ok")
         if world > 1:
             dist.barrier()
         # ports derived from the rendezvous port so that concurrent / stale runs never collide

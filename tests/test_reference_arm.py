@@ -37,3 +37,24 @@ def test_reference_arm_unavailable_is_clean(tmp_path):
     assert r.returncode == 0
     out = json.loads(r.stdout.strip().splitlines()[-1])
     assert out["impl"] == "reference" and "unavailable" in out
+
+
+@pytest.mark.skipif(not (ROOT / "baseline/_ref/sub/model_dist.py").is_file(), reason="baseline/_ref not installed")
+def test_reference_arm_two_nodes_cpu(tmp_path):
+    """Two reference nodes (starter + secondary) as two torchrun ranks on CPU: the checkpoint is split with the
+    reference's own split_and_store, the nodes talk over its loopback sockets, rank 0 prints the one JSON line."""
+    from conftest import free_ports
+
+    env = dict(os.environ, MDI_REF_DEVICE="cpu", MDI_REF_MODEL="pythia-160m", MDI_REF_CKPT_DIR=str(tmp_path))
+    (port,) = free_ports(1)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), str(ROOT / "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "3", "--warmup", "3",
+           "--prompt-len", "8"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-3000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip().startswith("{")]
+    assert len(lines) == 1, r.stdout[-2000:]
+    out = json.loads(lines[0])
+    assert out["impl"] == "reference" and out["n_gpus"] == 2 and out["value"] > 0, out
+    chunk_dir = next(tmp_path.glob("custom/*/chunks/2nodes"))
+    assert (chunk_dir / ".complete").is_file() and (chunk_dir / "model_secondary0.pth").is_file()
