@@ -107,10 +107,11 @@ def lib() -> ctypes.CDLL:
         raise OpsError(f"cannot load {_build.LIB}: {e}") from e
 
 
-def set_prefill_attn_pipe(on: bool) -> None:
-    """Prefill attention kernel: True = pipelined (double-buffered K/V^T tiles and score matrix), False = the
-    simple sequential kernel.  ``MDI_PREFILL_ATTN_PIPE`` sets it at load."""
-    lib().mdi_set_prefill_attn_pipe(int(bool(on)))
+def set_prefill_attn_pipe(mode: int) -> None:
+    """Prefill attention kernel: 1 / True = pipelined (double-buffered K/V^T tiles and score matrix; default),
+    0 / False = the simple sequential kernel, 2 = pipelined with two softmax warpgroups (experimental, not yet
+    validated on hardware).  ``MDI_PREFILL_ATTN_PIPE`` sets it at load."""
+    lib().mdi_set_prefill_attn_pipe(int(mode))
 
 
 def set_l2_prefetch_mb(mb: int) -> None:

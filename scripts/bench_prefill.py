@@ -42,14 +42,19 @@ for T in (128, 512, 2048, 4096):
     ms = timeit(lambda: ops.attn_prefill(qkv, cos, sin, pool, 0, n_head=H, n_groups=G, head_size=hs, rope_n_elem=hs))
     ops.set_prefill_attn_pipe(True)
     ms_pipe = timeit(lambda: ops.attn_prefill(qkv, cos, sin, pool, 0, n_head=H, n_groups=G, head_size=hs, rope_n_elem=hs))
-    ops.set_prefill_attn_pipe(bool(int(os.environ.get("MDI_PREFILL_ATTN_PIPE", "1"))))
+    row_extra = {}
+    if os.environ.get("MDI_TEST_EXPERIMENTAL"):  # two softmax warpgroups (mode 2)
+        ops.set_prefill_attn_pipe(2)
+        ms2 = timeit(lambda: ops.attn_prefill(qkv, cos, sin, pool, 0, n_head=H, n_groups=G, head_size=hs, rope_n_elem=hs))
+        row_extra = {"tcgen05_pipe2_ms": round(ms2, 4)}
+    ops.set_prefill_attn_pipe(int(os.environ.get("MDI_PREFILL_ATTN_PIPE", "1")))
     q = torch.randn(1, H, T, hs, device="cuda").bfloat16()
     k = torch.randn(1, H, T, hs, device="cuda").bfloat16()
     ms_ref = timeit(lambda: torch.nn.functional.scaled_dot_product_attention(q, k, k, is_causal=True))
     flops = 4.0 * H * hs * T * T / 2  # causal
     out["attention"].append({"T": T, "tcgen05_ms": round(ms, 4), "tcgen05_tflops": round(flops / ms / 1e9, 1),
                              "tcgen05_pipelined_ms": round(ms_pipe, 4), "tcgen05_pipelined_tflops": round(flops / ms_pipe / 1e9, 1),
-                             "sdpa_ms (attention only, no rope/split/cache)": round(ms_ref, 4)})
+                             "sdpa_ms (attention only, no rope/split/cache)": round(ms_ref, 4), **row_extra})
     print(out["attention"][-1], flush=True)
 
 cfg = Config.from_name("Llama-3-8B", n_layer=4, block_size=4096)
