@@ -29,6 +29,7 @@ __all__ = [
     "N_LAYERS_NODES", "plan_layers", "balanced_plan", "layer_ranges", "split_parameters",
     "split_and_store", "merge_chunks", "count_transformer_blocks", "chunk_dir", "chunk_file",
     "HalfStage", "plan_half_units", "half_stages", "split_parameters_half", "decode_unit_costs",
+    "stage_shape_from_state_dict", "stage_specs",
 ]
 
 # n_nodes -> n_layer -> (starter layers, layers per secondary).  Data of config.py:56-98.
@@ -213,6 +214,38 @@ def split_parameters_half(model_params: Dict[str, Any], units_per_stage: Sequenc
     return {"starter": chunks[0], "secondary": chunks[1:]}
 
 
+def stage_shape_from_state_dict(sd: Dict[str, Any]) -> Dict[str, Any]:
+    """``{"n_blocks", "first_mlp_only", "last_attn_only"}`` of a chunk, read off its keys: a block without
+    ``attn.*`` tensors holds only its MLP half (and vice versa) — so chunk files fully describe half-layer plans."""
+    blocks: Dict[int, set] = {}
+    for k in sd:
+        if k.startswith("transformer.h."):
+            _, _, li, tail = k.split(".", 3)
+            blocks.setdefault(int(li), set()).add(tail.split(".", 1)[0])
+    n = len(blocks)
+    if n == 0:
+        return {"n_blocks": 0, "first_mlp_only": False, "last_attn_only": False}
+    first, last = blocks[min(blocks)], blocks[max(blocks)]
+    return {"n_blocks": n, "first_mlp_only": "attn" not in first, "last_attn_only": "mlp" not in last}
+
+
+def stage_specs(n_nodes: int, config: Config, policy: str = "auto") -> List[Dict[str, Any]]:
+    """Per-stage shape for a partition policy: ``"half"`` = half-layer units (boundaries may fall between a
+    layer's attention and MLP), else whole layers via :func:`plan_layers`.  Every entry carries ``n_blocks``,
+    ``first_mlp_only``, ``last_attn_only``, ``layer_offset`` (global index of local block 0) and ``units``."""
+    if policy == "half" and n_nodes > 1 and not config.parallel_residual:
+        units = plan_half_units(n_nodes, config)
+        return [{"n_blocks": h.n_blocks, "first_mlp_only": h.first_mlp_only, "last_attn_only": h.last_attn_only,
+                 "layer_offset": h.lo_layer, "units": u} for h, u in zip(half_stages(units), units)]
+    pol = "balanced" if policy == "half" else policy
+    plan = plan_layers(n_nodes, config.n_layer, config, policy=pol) if n_nodes > 1 else [config.n_layer]
+    out, off = [], 0
+    for n in plan:
+        out.append({"n_blocks": n, "first_mlp_only": False, "last_attn_only": False, "layer_offset": off, "units": 2 * n})
+        off += n
+    return out
+
+
 def layer_ranges(plan: Sequence[int]) -> List[Tuple[int, int]]:
     out, start = [], 0
     for n in plan:
@@ -309,8 +342,13 @@ def split_and_store(
 ) -> Path:
     """Split a state dict and write the chunk files; returns the chunk directory."""
     verb = bool(kwargs.get("verb", False))
-    chunks, info = split_parameters(model_params, n_nodes, plan=plan, config=config,
-                                    head_on=kwargs.get("head_on", "starter"))
+    units = kwargs.get("units")
+    if units is not None:  # half-layer plan: a cut layer's attention / MLP tensors land in neighbouring chunks
+        chunks = split_parameters_half(model_params, units)
+        info = {"plan": [u / 2 for u in units]}
+    else:
+        chunks, info = split_parameters(model_params, n_nodes, plan=plan, config=config,
+                                        head_on=kwargs.get("head_on", "starter"))
     if len(model_params):
         warnings.warn(f"{len(model_params)} elements have not been used")
     del model_params

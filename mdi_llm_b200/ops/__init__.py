@@ -18,11 +18,12 @@ import torch
 from . import build as _build
 
 __all__ = ["lib", "available", "require", "OpsError", "ptr", "stream_ptr", "check", "ACT", "CTX_INTS",
-           "linear_decode", "qkv_decode", "attn_decode", "gemm", "sample_fast", "sample_scratch", "embed", "rmsnorm_rows", "sample", "advance_step",
+           "linear_decode", "qkv_decode", "attn_decode", "gemm", "sample_fast", "sample_scratch", "stamp", "POISON", "embed", "rmsnorm_rows", "sample", "advance_step",
            "CudaGraph"]
 
 CTX_SLOT, CTX_POS, CTX_WAIT, CTX_SIGNAL, CTX_TOKEN, CTX_STEP = 0, 1, 2, 3, 4, 5
 CTX_INTS = 8
+POISON = 0x7FFFFFFF  # flag value of an aborted ring (csrc/common.cuh: MDI_POISON)
 ACT = {"none": 0, "silu_gate": 1, "gelu_tanh_gate": 2, "gelu_erf_gate": 3, "gelu_tanh": 4, "gelu_erf": 5}
 
 _lib: Optional[ctypes.CDLL] = None
@@ -47,11 +48,12 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.mdi_attn_decode.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, i64, vp]
     lib.mdi_embed.argtypes = [vp, vp, vp, i64, vp, vp, i64, i32, f32, i32, vp]
     lib.mdi_rmsnorm_rows.argtypes = [vp, vp, vp, i32, i32, f32, i32, vp]
-    lib.mdi_sample.argtypes = [vp, i64, vp, i64, vp, vp, i32, i32, f32, i32, c_ulonglong, i32, vp]
-    lib.mdi_sample_fast.argtypes = [vp, vp, vp, i64, vp, vp, i32, i32, f32, i32, c_ulonglong, i32, vp]
+    lib.mdi_sample.argtypes = [vp, i64, vp, i64, vp, vp, i32, i32, f32, i32, c_ulonglong, i32, f32, vp]
+    lib.mdi_sample_fast.argtypes = [vp, vp, vp, i64, vp, vp, i32, i32, f32, i32, c_ulonglong, i32, f32, vp, i64, vp, vp]
+    lib.mdi_stamp.argtypes = [vp, vp]
     lib.mdi_sample_scratch_bytes.restype = c_size_t
     lib.mdi_gemm_bf16.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp]
-    lib.mdi_gemm_bf16_ex.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp,
+    lib.mdi_gemm_bf16_ex.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp,
                                      i32, i32, i32, i32, vp]
     lib.mdi_attn_prefill.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp]
     lib.mdi_set_prefill_attn_pipe.argtypes = [i32]
@@ -60,7 +62,7 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.mdi_wait_flag.argtypes = [vp, vp, vp, i64, vp]
     lib.mdi_set_flag.argtypes = [vp, vp, vp]
     lib.mdi_copy_bytes.argtypes = [vp, vp, c_size_t, vp]
-    lib.mdi_copy_signal.argtypes = [vp, vp, c_size_t, vp, vp, vp, vp]
+    lib.mdi_copy_signal.argtypes = [vp, vp, c_size_t, vp, vp, vp, vp, vp]
     lib.mdi_device_info.argtypes = [POINTER(i32), POINTER(i32), POINTER(i32), POINTER(c_size_t)]
     lib.mdi_p2p_alloc.argtypes = [c_size_t, POINTER(vp), c_char_p]
     lib.mdi_p2p_open.argtypes = [c_char_p, POINTER(vp)]
@@ -92,8 +94,14 @@ def lib() -> ctypes.CDLL:
         if alt:
             handle = ctypes.CDLL(alt)
         else:
-            if not _build.LIB.exists() or (not _build.is_fresh() and _build.nvcc_path()):
-                _build.build()
+            if not _build.is_fresh():
+                if _build.nvcc_path():
+                    _build.build()
+                elif not _build.LIB.exists():
+                    raise OpsError("kernel library not built and nvcc not available")
+                else:  # argtypes below describe the CURRENT sources: an older binary would be called with a wrong ABI
+                    raise OpsError(f"{_build.LIB} was built from different sources (digest {_build.embedded_digest()}) "
+                                   "and nvcc is not available to rebuild it")
             handle = ctypes.CDLL(str(_build.LIB))
         _declare(handle)
         _lib = handle
@@ -256,19 +264,21 @@ def rmsnorm_rows(x: torch.Tensor, w: torch.Tensor, eps: float, unit_offset: bool
 
 def sample(logits: torch.Tensor, tokens: torch.Tensor, ctx: torch.Tensor, *, vocab: int, top_k: Optional[int],
            temperature: float, greedy: bool, seed: int, tok_slot_stride: int, logits_slot_stride: int = 0,
-           last_token: Optional[torch.Tensor] = None, use_pdl: bool = False) -> None:
+           last_token: Optional[torch.Tensor] = None, use_pdl: bool = False, top_p: float = 1.0) -> None:
+    """Stand-alone sampler (one CTA): exact top-k list for k <= 1024 without nucleus crop, else the
+    whole-vocabulary sampler (any k, top-p by probability-mass radix selection)."""
     if logits.dtype != torch.float32 or tokens.dtype != torch.int32:
         raise OpsError("sample: logits fp32 and tokens int32 expected")
     check(lib().mdi_sample(ptr(logits), logits_slot_stride, ptr(tokens), tok_slot_stride, ptr(last_token), ptr(ctx),
                            vocab, int(top_k or 0), float(temperature), int(greedy), seed & (2 ** 64 - 1), int(use_pdl),
-                           stream_ptr()), "sample")
+                           float(top_p), stream_ptr()), "sample")
 
 
 def gemm(a: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
          out: Optional[torch.Tensor] = None, block_n: int = 128, w2: Optional[torch.Tensor] = None,
          bias2: Optional[torch.Tensor] = None, act: str = "silu_gate", out_ptr: Optional[int] = None,
          signal_flag: Optional[int] = None, done_ctr: Optional[torch.Tensor] = None, ctx: Optional[torch.Tensor] = None,
-         _knobs: Tuple[int, int, int, int] = (0, 0, 0, 0)) -> Optional[torch.Tensor]:
+         status: Optional[torch.Tensor] = None, _knobs: Tuple[int, int, int, int] = (0, 0, 0, 0)) -> Optional[torch.Tensor]:
     """``a [M, K] @ w [N, K]^T (+bias) (+residual)`` on the tcgen05 tensor cores (TMA-fed, TMEM
     accumulator) — the prefill GEMM.  bf16 in/out, fp32 accumulate.
 
@@ -290,7 +300,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] = Non
         c_ptr, out = out_ptr, None
     check(lib().mdi_gemm_bf16_ex(ptr(a), ptr(w), ptr(w2), c_ptr, ptr(bias), ptr(bias2), ptr(residual), M, N, K,
                                  ACT[act] if w2 is not None else 0, block_n, signal_flag, ptr(done_ctr), ptr(ctx),
-                                 *_knobs, stream_ptr()), "gemm_bf16 (tcgen05)")
+                                 ptr(status), *_knobs, stream_ptr()), "gemm_bf16 (tcgen05)")
     return out
 
 
@@ -330,13 +340,22 @@ def sample_scratch(device: Any) -> torch.Tensor:
 
 def sample_fast(logits: torch.Tensor, scratch: torch.Tensor, tokens: torch.Tensor, ctx: torch.Tensor, *, vocab: int,
                 top_k: Optional[int], temperature: float, greedy: bool, seed: int, tok_slot_stride: int,
-                last_token: Optional[torch.Tensor] = None, use_pdl: bool = False) -> None:
-    """Sampling from statistics the lm_head epilogue left in ``scratch`` (``linear_decode(stats=scratch)``)."""
+                last_token: Optional[torch.Tensor] = None, use_pdl: bool = False, top_p: float = 1.0,
+                tok_ts: Optional[torch.Tensor] = None, status: Optional[torch.Tensor] = None) -> None:
+    """Sampling from statistics the lm_head epilogue left in ``scratch`` (``linear_decode(stats=scratch)``).
+    ``top_p < 1``, ``top_k`` beyond 1024 / None, or an overflowing candidate list take the exact whole-vocabulary
+    sampler inside the same launch.  ``tok_ts`` (int64 ``[n_slots, stride]``) receives the device time of every token."""
     if logits.dtype != torch.float32 or tokens.dtype != torch.int32:
         raise OpsError("sample_fast: logits fp32 and tokens int32 expected")
     check(lib().mdi_sample_fast(ptr(logits), ptr(scratch), ptr(tokens), tok_slot_stride, ptr(last_token), ptr(ctx),
                                 vocab, int(top_k or 0), float(temperature), int(greedy), seed & (2 ** 64 - 1),
-                                int(use_pdl), stream_ptr()), "sample_fast")
+                                int(use_pdl), float(top_p), ptr(tok_ts), tok_ts.shape[1] if tok_ts is not None else 0,
+                                ptr(status), stream_ptr()), "sample_fast")
+
+
+def stamp(dst: torch.Tensor) -> None:
+    """``dst[0] = %globaltimer`` on the current stream (int64 tensor): time base of the per-token device timeline."""
+    check(lib().mdi_stamp(ptr(dst), stream_ptr()), "stamp")
 
 
 def advance_step(ctx: torch.Tensor, state: torch.Tensor, pos: torch.Tensor, n_slots: int, is_starter: bool,

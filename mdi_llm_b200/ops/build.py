@@ -41,8 +41,25 @@ def _digest() -> str:
     return h.hexdigest()
 
 
+_MARK = b"MDI_BUILD_DIGEST:"
+
+
+def embedded_digest(path: Path = LIB) -> Optional[str]:
+    """Digest of the sources a built library was compiled from, read out of the binary itself (the string is
+    compiled into ``runtime.cu``), so a stale ``.so`` can never pass for a fresh one whatever the state of the
+    work tree (a separate stamp file could — and did — get out of sync with a git-ignored binary)."""
+    try:
+        blob = path.read_bytes()
+    except OSError:
+        return None
+    i = blob.find(_MARK)
+    if i < 0:
+        return None
+    return blob[i + len(_MARK): i + len(_MARK) + 64].decode("ascii", "replace")
+
+
 def is_fresh() -> bool:
-    return LIB.exists() and STAMP.exists() and STAMP.read_text().strip() == _digest()
+    return LIB.exists() and embedded_digest() == _digest()
 
 
 def build(force: bool = False, verbose: bool = False, ptxas_info: bool = False) -> Path:
@@ -54,8 +71,9 @@ def build(force: bool = False, verbose: bool = False, ptxas_info: bool = False) 
         raise RuntimeError("nvcc not found: cannot build the sm_100a kernels")
     objdir = HERE / "build"
     objdir.mkdir(exist_ok=True)
+    digest = _digest()
     common = [nvcc, "-O3", "-std=c++17", "-lineinfo", *ARCH_FLAGS, "-Xcompiler", "-fPIC",
-              "--use_fast_math", "-I", str(CSRC)]
+              "--use_fast_math", "-I", str(CSRC), f'-DMDI_BUILD_DIGEST_STR="{digest}"']
     if ptxas_info:
         common += ["-Xptxas", "-v"]
     procs = []
@@ -81,7 +99,10 @@ def build(force: bool = False, verbose: bool = False, ptxas_info: bool = False) 
     if verbose:
         print(" ".join(link))
     subprocess.run(link, check=True)
-    STAMP.write_text(_digest())
+    if embedded_digest() != digest:
+        raise RuntimeError("built library does not carry the source digest (runtime.cu: mdi_build_digest)")
+    if STAMP.exists():
+        STAMP.unlink()  # superseded by the embedded digest
     return LIB
 
 

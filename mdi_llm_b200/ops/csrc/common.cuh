@@ -76,25 +76,52 @@ __device__ __forceinline__ bool wait_flag_ge(const int* flag, int want, long lon
   return true;
 }
 
+// ---- abort propagation ---------------------------------------------------------------------------------
+// Flags carry round numbers (small positive ints).  MDI_POISON is larger than any of them, so a poisoned
+// flag satisfies every wait at once.  A stage that (a) trips its watchdog or (b) reads a poisoned flag marks
+// itself aborted (status[1] = 1); an aborted stage never waits again and publishes MDI_POISON instead of its
+// round number, so the abort travels round the ring at hop speed and every rank's queued steps drain in
+// microseconds instead of each one spinning out its own watchdog budget.  The host can start an abort by
+// writing MDI_POISON into a node's own flags (DevicePipeline.poison / PUT /stop).
+// status words: [0] error bits (1 = hop watchdog expired here, 2 = intra-stage dependency watchdog,
+//               4 = sampler candidate overflow), [1] aborted, [2..3] cycles CTA 0 spent waiting (64-bit).
+#define MDI_POISON 0x7fffffff
+
 struct HopWait {   // consumer side; flag == nullptr disables
   const int* flag;       // base of this GPU's flag array (one int per sample slot)
-  int* status;           // error word (set to 1 on watchdog expiry), may be null
+  int* status;           // status words (see above), may be null
   long long max_cycles;  // 0 = wait forever
 };
 struct HopSignal {  // producer side; flag == nullptr disables
   int* flag;               // base of the NEXT stage's flag array (peer-mapped or local)
   unsigned int* done_ctr;  // local counter of finished CTAs (self-resetting)
+  const int* status;       // this stage's status words (abort -> publish poison), may be null
 };
 
+// one thread: wait until flag >= want, honouring / recording aborts
+__device__ __forceinline__ void hop_wait_one(const int* flag, int want, int* status, long long max_cycles) {
+  if (status && ld_volatile(status + 1) != 0) return;  // already aborted: drain
+  const long long t0 = clock64();
+  int v;
+  while ((v = ld_acquire_sys(flag)) < want) {
+    __nanosleep(64);
+    if (max_cycles > 0 && clock64() - t0 > max_cycles) {
+      if (status) { atomicOr(status, 1); atomicExch(status + 1, 1); }
+      return;
+    }
+  }
+  if (v == MDI_POISON && status) atomicExch(status + 1, 1);
+}
+
 // All threads call; thread 0 spins, everybody leaves after the flag for ctx's slot >= ctx's wait value.
-// status[0] = watchdog error; status[2..3] (as one 64-bit word) accumulates the cycles CTA 0 spent
-// waiting — the *exposed* hop/idle time the benchmark reports per token.
+// status[2..3] (as one 64-bit word) accumulates the cycles CTA 0 spent waiting — the *exposed* hop/idle
+// time the benchmark reports per token.
 __device__ __forceinline__ void hop_wait(const HopWait& w, const int* ctx) {
   if (w.flag == nullptr) return;
   if (threadIdx.x == 0) {
     const int slot = ctx[MDI_CTX_SLOT], want = ctx[MDI_CTX_WAIT];
     const long long t0 = clock64();
-    if (!wait_flag_ge(w.flag + slot, want, w.max_cycles) && w.status) atomicExch(w.status, 1);
+    hop_wait_one(w.flag + slot, want, w.status, w.max_cycles);
     if (w.status && blockIdx.x == 0 && blockIdx.y == 0)
       atomicAdd(reinterpret_cast<unsigned long long*>(w.status + 2), (unsigned long long)(clock64() - t0));
   }
@@ -114,7 +141,8 @@ __device__ __forceinline__ void hop_signal(const HopSignal& s, const int* ctx) {
     if (prev == total - 1) {
       *s.done_ctr = 0;  // ready for the next launch (stream-ordered)
       __threadfence_system();
-      st_release_sys(s.flag + ctx[MDI_CTX_SLOT], ctx[MDI_CTX_SIGNAL]);
+      const bool aborted = s.status != nullptr && ld_volatile(s.status + 1) != 0;
+      st_release_sys(s.flag + ctx[MDI_CTX_SLOT], aborted ? MDI_POISON : ctx[MDI_CTX_SIGNAL]);
     }
   }
 }

@@ -824,7 +824,7 @@ int mdi_linear_decode(const void* W, const void* W2, const void* bias, const voi
   a.x_slot_stride = x_slot_stride; a.res_slot_stride = res_slot_stride; a.y_slot_stride = y_slot_stride;
   a.N = N; a.K = K; a.eps = eps; a.unit_offset = unit_offset; a.act = act; a.out_fp32 = out_fp32;
   a.wait = HopWait{wait_flag, status, wait_max_cycles};
-  a.signal = HopSignal{signal_flag, done_ctr};
+  a.signal = HopSignal{signal_flag, done_ctr, status};
   a.n_items = W2 ? N : (N + 1) / 2;
   a.hist = hist; a.amax = amax; a.trace = trace; a.wscale = wscale; a.wscale2 = wscale2;
   a.dep_wait = DepWait{dep_wait_flag, status, wait_max_cycles}; a.dep_signal = DepSignal{dep_signal_flag, dep_ctr};
@@ -848,7 +848,7 @@ int mdi_qkv_decode(const void* W, const void* bias, const void* x, const void* n
   a.n_head = n_head; a.n_groups = n_groups; a.head_size = head_size; a.rope_n_elem = rope_n_elem;
   a.max_seq = max_seq; a.eps = eps; a.unit_offset = unit_offset;
   a.wait = HopWait{wait_flag, status, wait_max_cycles};
-  a.signal = HopSignal{nullptr, nullptr};
+  a.signal = HopSignal{nullptr, nullptr, nullptr};
   a.trace = trace; a.wscale = wscale;
   a.dep_wait = DepWait{dep_wait_flag, status, wait_max_cycles}; a.dep_signal = DepSignal{dep_signal_flag, dep_ctr};
   a.ctx_early = (use_pdl >> 1) & 1; use_pdl &= 1;

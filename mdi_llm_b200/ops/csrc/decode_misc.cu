@@ -70,6 +70,187 @@ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
   return x ^ (x >> 31);
 }
 
+
+// ---- general sampler (any top-k, nucleus top-p) -------------------------------------------------------------
+// One CTA of SMP_THREADS threads over the whole vocabulary.  Semantics of the eager `sample()`
+// (models/gpt.py, reference model.py:42-90): crop to the k largest logits, divide by the temperature, drop the
+// low-probability tail whose ascending cumulative probability is <= 1 - top_p (i.e. keep a token iff the
+// probability mass strictly above it is < top_p), renormalise, one multinomial draw.  Both crops are radix
+// selections over the orderable 32-bit logit key: by COUNT for top-k, by probability MASS for top-p; ties of the
+// threshold key are kept as a group.  Histogram updates are warp-aggregated (most logits share their top bits).
+__device__ __forceinline__ void hist_add_u(unsigned int* hist, bool on, unsigned int digit) {
+  const unsigned int peers = __match_any_sync(0xffffffffu, on ? digit : 0xffffffffu);
+  if (on && (threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) atomicAdd(hist + digit, (unsigned)__popc(peers));
+}
+__device__ __forceinline__ void hist_add_f(float* hist, bool on, unsigned int digit, float w) {
+  const unsigned int peers = __match_any_sync(0xffffffffu, on ? digit : 0xffffffffu);
+  float tot = 0.f;
+  for (unsigned int m = peers; m; m &= m - 1) tot += __shfl_sync(peers, w, __ffs(m) - 1);
+  if (on && (threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) atomicAdd(hist + digit, tot);
+}
+
+// scratch: 256 u32 + 256 f32 + 40 f32 in shared memory
+__device__ int sample_full(const float* __restrict__ lg, int V, int k, float top_p, float inv_t, float u01,
+                           unsigned int* hist, float* fhist, float* red) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  __shared__ unsigned int sf_prefix, sf_kleft;
+  __shared__ float sf_above, sf_val;
+  __shared__ int sf_pick;
+  // ---- max logit ------------------------------------------------------------------------------------------
+  float mx = -INFINITY;
+  for (int i = tid; i < V; i += SMP_THREADS) mx = fmaxf(mx, __ldcg(lg + i));
+  mx = warp_max(mx);
+  if (lane == 0) red[warp] = mx;
+  __syncthreads();
+  if (warp == 0) { const float t = warp_max(red[lane]); if (lane == 0) sf_val = t; }
+  __syncthreads();
+  mx = sf_val;
+  __syncthreads();
+  // ---- top-k: key of the k-th largest (by count) ------------------------------------------------------------
+  uint32_t thr = 0u;
+  if (k > 0 && k < V) {
+    if (tid == 0) { sf_prefix = 0; sf_kleft = (unsigned)k; }
+    __syncthreads();
+    for (int pass = 0; pass < 4; ++pass) {
+      const int shift = 24 - 8 * pass;
+      if (tid < 256) hist[tid] = 0;
+      __syncthreads();
+      const unsigned int prefix = sf_prefix;
+      const unsigned int mask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
+      for (int i0 = 0; i0 < V; i0 += SMP_THREADS) {
+        const int i = i0 + tid;
+        const uint32_t key = i < V ? float_key(__ldcg(lg + i)) : 0u;
+        hist_add_u(hist, i < V && (key & mask) == prefix, (key >> shift) & 0xffu);
+      }
+      __syncthreads();
+      if (tid == 0) {
+        unsigned int left = sf_kleft, cum = 0;
+        int b = 255;
+        for (; b > 0; --b) {
+          if (cum + hist[b] >= left) break;
+          cum += hist[b];
+        }
+        sf_kleft = left - cum;
+        sf_prefix = prefix | ((unsigned)b << shift);
+      }
+      __syncthreads();
+    }
+    thr = sf_prefix;
+    __syncthreads();
+  }
+  // ---- probability mass of the kept set ------------------------------------------------------------------------
+  auto mass_ge = [&](uint32_t t) -> float {
+    float s = 0.f;
+    for (int i = tid; i < V; i += SMP_THREADS) {
+      const float v = __ldcg(lg + i);
+      if (float_key(v) >= t) s += __expf((v - mx) * inv_t);
+    }
+    s = warp_sum(s);
+    __syncthreads();
+    if (lane == 0) red[warp] = s;
+    __syncthreads();
+    if (warp == 0) { const float t2 = warp_sum(red[lane]); if (lane == 0) sf_val = t2; }
+    __syncthreads();
+    return sf_val;
+  };
+  float total = mass_ge(thr);
+  // ---- top-p: smallest key K with mass(keys > K) < top_p * total ------------------------------------------------
+  if (top_p < 1.f) {
+    const float P = top_p * total;
+    if (tid == 0) { sf_prefix = 0; sf_above = 0.f; }
+    __syncthreads();
+    for (int pass = 0; pass < 4; ++pass) {
+      const int shift = 24 - 8 * pass;
+      if (tid < 256) fhist[tid] = 0.f;
+      __syncthreads();
+      const unsigned int prefix = sf_prefix;
+      const unsigned int mask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
+      for (int i0 = 0; i0 < V; i0 += SMP_THREADS) {
+        const int i = i0 + tid;
+        const float v = i < V ? __ldcg(lg + i) : 0.f;
+        const uint32_t key = float_key(v);
+        const bool on = i < V && key >= thr && (key & mask) == prefix;
+        hist_add_f(fhist, on, (key >> shift) & 0xffu, on ? __expf((v - mx) * inv_t) : 0.f);
+      }
+      __syncthreads();
+      if (tid == 0) {
+        float above = sf_above;  // mass of every key above the current prefix range
+        int b = 255;
+        // descend while the mass strictly above bin b's successor still leaves room: stop at the lowest bin whose
+        // "mass of higher bins" is < P
+        for (; b > 0; --b) {
+          if (above + fhist[b] >= P) break;  // bins below b would have mass-above >= P: dropped
+          above += fhist[b];
+        }
+        sf_above = above;
+        sf_prefix = prefix | ((unsigned)b << shift);
+      }
+      __syncthreads();
+    }
+    uint32_t thr_p = sf_prefix;
+    __syncthreads();
+    if (thr_p > thr) thr = thr_p;
+    total = mass_ge(thr);
+  }
+  // ---- one draw in vocabulary order (a fixed seed gives a fixed token) ---------------------------------------------
+  const int chunk = (V + SMP_THREADS - 1) / SMP_THREADS;
+  const int lo = tid * chunk, hi = min(V, lo + chunk);
+  float mine = 0.f;
+  for (int i = lo; i < hi; ++i) {
+    const float v = __ldcg(lg + i);
+    if (float_key(v) >= thr) mine += __expf((v - mx) * inv_t);
+  }
+  float sc = mine;  // inclusive scan over threads
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const float t = __shfl_up_sync(0xffffffffu, sc, o); if (lane >= o) sc += t; }
+  __syncthreads();
+  if (lane == 31) red[warp] = sc;
+  __syncthreads();
+  if (warp == 0) {
+    float w = red[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const float t = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += t; }
+    red[lane] = w;
+  }
+  __syncthreads();
+  const float incl = sc + (warp > 0 ? red[warp - 1] : 0.f), excl = incl - mine;
+  const float target = u01 * red[31];
+  if (tid == 0) sf_pick = -1;
+  __syncthreads();
+  if (mine > 0.f && target >= excl && target < incl) {
+    float run = excl;
+    int pick = -1;
+    for (int i = lo; i < hi; ++i) {
+      const float v = __ldcg(lg + i);
+      if (float_key(v) >= thr) {
+        pick = i;  // last kept element of the chunk absorbs round-off
+        run += __expf((v - mx) * inv_t);
+        if (target < run) break;
+      }
+    }
+    sf_pick = pick;
+  }
+  __syncthreads();
+  if (sf_pick < 0) {  // round-off at the upper end (or an all -inf row): fall back to the arg-max
+    float best = -INFINITY; int bi = 0x7fffffff;
+    for (int i = tid; i < V; i += SMP_THREADS) { const float v = __ldcg(lg + i); if (v > best || (v == best && i < bi)) { best = v; bi = i; } }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, best, o); const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    __syncthreads();
+    if (lane == 0) { red[warp] = best; hist[warp] = (unsigned)bi; }
+    __syncthreads();
+    if (tid == 0) {
+      for (int w = 0; w < SMP_THREADS / 32; ++w) if (red[w] > best || (red[w] == best && (int)hist[w] < bi)) { best = red[w]; bi = (int)hist[w]; }
+      sf_pick = bi;
+    }
+    __syncthreads();
+  }
+  return sf_pick;
+}
+
 struct SampleArgs {
   const float* logits;  // [V] (+ slot * logits_slot_stride)
   long long logits_slot_stride;
@@ -82,6 +263,7 @@ struct SampleArgs {
   float temperature;    // <= 0 with greedy != 0: arg-max
   int greedy;
   unsigned long long seed;
+  float top_p;          // >= 1: no nucleus crop
 };
 
 __global__ void __launch_bounds__(SMP_THREADS) sample_kernel(const SampleArgs a) {
@@ -135,7 +317,17 @@ __global__ void __launch_bounds__(SMP_THREADS) sample_kernel(const SampleArgs a)
   }
 
   int k = (a.top_k > 0 && a.top_k < V) ? a.top_k : V;
-  if (k > SMP_KMAX) k = SMP_KMAX;  // documented cap of the device sampler
+  if (k > SMP_KMAX || a.top_p < 1.f) {  // beyond the candidate-list path: whole-vocabulary sampler
+    __shared__ float fh[256];
+    const uint64_t r0 = splitmix64(a.seed ^ splitmix64(((uint64_t)(uint32_t)slot << 32) | (uint32_t)pos));
+    const int tok = sample_full(lg, V, k < V ? k : 0, a.top_p, a.temperature > 0.f ? 1.f / a.temperature : 1.f,
+                                (float)((r0 >> 40) * (1.0 / 16777216.0)), hist, fh, red_f);
+    if (tid == 0) {
+      a.tokens[(size_t)slot * a.tok_slot_stride + pos] = tok;
+      if (a.last_token) a.last_token[slot] = tok;
+    }
+    return;
+  }
   // ---- radix select: key of the k-th largest logit ---------------------------------------------
   if (tid == 0) { sh_prefix = 0; sh_kleft = (unsigned)k; sh_ngreater = 0; }
   __syncthreads();
@@ -257,6 +449,10 @@ struct SampleFastArgs {
   int* tokens; long long tok_slot_stride; int* last_token;
   const int* ctx;
   int V, top_k; float temperature; int greedy; unsigned long long seed;
+  float top_p;                  // >= 1: no nucleus crop
+  unsigned long long* tok_ts;   // optional [n_slots, ts_slot_stride]: %globaltimer when the token was produced
+  long long ts_slot_stride;
+  int* status;                  // status words of the stage (bit 4 of [0]: candidate overflow, handled exactly)
 };
 
 __global__ void __launch_bounds__(256) sample_filter_kernel(const SampleFastArgs a) {
@@ -318,12 +514,34 @@ __global__ void __launch_bounds__(SMP_THREADS) sample_final_kernel(const SampleF
       const int tok = (int)(0xffffffffu - (uint32_t)(best & 0xffffffffull));
       a.tokens[(size_t)slot * a.tok_slot_stride + pos] = tok;
       if (a.last_token) a.last_token[slot] = tok;
+      if (a.tok_ts) a.tok_ts[(size_t)slot * a.ts_slot_stride + pos] = globaltimer_ns();
       *a.amax = 0ull;
     }
     for (int i = tid; i < SF_BINS; i += SMP_THREADS) a.hist[i] = 0;
     return;
   }
-  const int n_cand = (int)min(__ldcg(a.cand_count), (unsigned)SF_CAND_MAX);
+  const unsigned int n_cand_raw = __ldcg(a.cand_count);
+  {
+    const int kk = (a.top_k > 0 && a.top_k < a.V) ? a.top_k : a.V;
+    if (n_cand_raw > (unsigned)SF_CAND_MAX || kk > SMP_KMAX || a.top_p < 1.f) {
+      // nucleus sampling, k beyond the candidate list, or a logit distribution so flat that the threshold bin
+      // overflowed the list: exact whole-vocabulary sampler (slower, never wrong)
+      if (tid == 0 && n_cand_raw > (unsigned)SF_CAND_MAX && a.status) atomicOr(a.status, 4);
+      const uint64_t r0 = splitmix64(a.seed ^ splitmix64(((uint64_t)(uint32_t)slot << 32) | (uint32_t)pos));
+      const int tok = sample_full(a.logits, a.V, kk < a.V ? kk : 0, a.top_p, a.temperature > 0.f ? 1.f / a.temperature : 1.f,
+                                  (float)((r0 >> 40) * (1.0 / 16777216.0)), hist, reinterpret_cast<float*>(top_val), red_f);
+      if (tid == 0) {
+        a.tokens[(size_t)slot * a.tok_slot_stride + pos] = tok;
+        if (a.last_token) a.last_token[slot] = tok;
+        if (a.tok_ts) a.tok_ts[(size_t)slot * a.ts_slot_stride + pos] = globaltimer_ns();
+        *a.cand_count = 0;
+        *a.amax = 0ull;
+      }
+      for (int i = tid; i < SF_BINS; i += SMP_THREADS) a.hist[i] = 0;
+      return;
+    }
+  }
+  const int n_cand = (int)min(n_cand_raw, (unsigned)SF_CAND_MAX);
   for (int i = tid; i < n_cand; i += SMP_THREADS) { cv[i] = __ldcg(a.cand_val + i); ci[i] = __ldcg(a.cand_idx + i); }
   int k = (a.top_k > 0 && a.top_k < a.V) ? a.top_k : a.V;
   k = min(min(k, SMP_KMAX), n_cand);
@@ -414,6 +632,7 @@ __global__ void __launch_bounds__(SMP_THREADS) sample_final_kernel(const SampleF
   if (tid == 0) {
     a.tokens[(size_t)slot * a.tok_slot_stride + pos] = sh_pick;
     if (a.last_token) a.last_token[slot] = sh_pick;
+    if (a.tok_ts) a.tok_ts[(size_t)slot * a.ts_slot_stride + pos] = globaltimer_ns();
     *a.cand_count = 0;
     *a.amax = 0ull;
   }
@@ -445,15 +664,17 @@ __global__ void advance_step_kernel(int* __restrict__ ctx, int* __restrict__ sta
 }
 
 __global__ void wait_flag_kernel(const int* flag, const int* ctx, int* status, long long max_cycles) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) {
-    if (!wait_flag_ge(flag + ctx[MDI_CTX_SLOT], ctx[MDI_CTX_WAIT], max_cycles) && status) atomicExch(status, 1);
-  }
+  if (threadIdx.x == 0 && blockIdx.x == 0) hop_wait_one(flag + ctx[MDI_CTX_SLOT], ctx[MDI_CTX_WAIT], status, max_cycles);
 }
 __global__ void set_flag_kernel(int* flag, const int* ctx) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     __threadfence_system();
     st_release_sys(flag + ctx[MDI_CTX_SLOT], ctx[MDI_CTX_SIGNAL]);
   }
+}
+// %globaltimer -> *dst (time base of the per-token device timeline)
+__global__ void stamp_kernel(unsigned long long* dst) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) *dst = globaltimer_ns();
 }
 // copy n 16-byte vectors (prefill hop payload: T x C hidden states) to a (peer) destination
 __global__ void copy_vec_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, size_t nvec) {
@@ -505,8 +726,8 @@ int mdi_rmsnorm_rows(const void* x, const void* w, void* y, int rows, int C, flo
 
 int mdi_sample(const float* logits, long long logits_slot_stride, int* tokens, long long tok_slot_stride,
                int* last_token, const int* ctx, int V, int top_k, float temperature, int greedy,
-               unsigned long long seed, int use_pdl, cudaStream_t stream) {
-  SampleArgs a{logits, logits_slot_stride, tokens, tok_slot_stride, last_token, ctx, V, top_k, temperature, greedy, seed};
+               unsigned long long seed, int use_pdl, float top_p, cudaStream_t stream) {
+  SampleArgs a{logits, logits_slot_stride, tokens, tok_slot_stride, last_token, ctx, V, top_k, temperature, greedy, seed, top_p};
   void* args[] = {&a};
   return launch_small((const void*)sample_kernel, dim3(1), dim3(SMP_THREADS), args, use_pdl, stream);
 }
@@ -516,7 +737,8 @@ size_t mdi_sample_scratch_bytes() { return 4096 * 4 + 8 + 8 + 8192 * 4 + 8192 * 
 
 int mdi_sample_fast(const float* logits, void* scratch, int* tokens, long long tok_slot_stride, int* last_token,
                     const int* ctx, int V, int top_k, float temperature, int greedy, unsigned long long seed,
-                    int use_pdl, cudaStream_t stream) {
+                    int use_pdl, float top_p, unsigned long long* tok_ts, long long ts_slot_stride, int* status,
+                    cudaStream_t stream) {
   char* base = (char*)scratch;
   SampleFastArgs a;
   a.logits = logits;
@@ -527,6 +749,7 @@ int mdi_sample_fast(const float* logits, void* scratch, int* tokens, long long t
   a.cand_idx = (int*)(base + 4096 * 4 + 16 + 8192 * 4);
   a.tokens = tokens; a.tok_slot_stride = tok_slot_stride; a.last_token = last_token; a.ctx = ctx;
   a.V = V; a.top_k = top_k; a.temperature = temperature; a.greedy = greedy; a.seed = seed;
+  a.top_p = top_p; a.tok_ts = tok_ts; a.ts_slot_stride = ts_slot_stride; a.status = status;
   void* args[] = {&a};
   int rc = 0;
   if (!greedy) {
@@ -566,14 +789,18 @@ int mdi_set_flag(int* flag, const int* ctx, cudaStream_t stream) {
   set_flag_kernel<<<1, 32, 0, stream>>>(flag, ctx);
   return (int)cudaGetLastError();
 }
+int mdi_stamp(unsigned long long* dst, cudaStream_t stream) {
+  stamp_kernel<<<1, 32, 0, stream>>>(dst);
+  return (int)cudaGetLastError();
+}
 int mdi_copy_signal(const void* src, void* dst, size_t bytes, int* flag, unsigned int* done_ctr, const int* ctx,
-                    cudaStream_t stream) {
+                    const int* status, cudaStream_t stream) {
   if (bytes % 16) return -2;
   size_t nvec = bytes / 16;
   int blocks = (int)((nvec + 255) / 256);
   if (blocks > 296) blocks = 296;
   if (blocks < 1) blocks = 1;
-  copy_signal_kernel<<<blocks, 256, 0, stream>>>((const uint4*)src, (uint4*)dst, nvec, HopSignal{flag, done_ctr}, ctx);
+  copy_signal_kernel<<<blocks, 256, 0, stream>>>((const uint4*)src, (uint4*)dst, nvec, HopSignal{flag, done_ctr, status}, ctx);
   return (int)cudaGetLastError();
 }
 int mdi_copy_bytes(const void* src, void* dst, size_t bytes, cudaStream_t stream) {

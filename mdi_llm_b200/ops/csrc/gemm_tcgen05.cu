@@ -255,15 +255,15 @@ using namespace mdi;
 // knobs: sbo/lbo/hi_bits/k_step <= 0 select the canonical encoding.
 extern "C" int mdi_gemm_bf16_ex(const void* A, const void* W, const void* W2, void* C, const void* bias,
                                 const void* bias2, const void* residual, int M, int N, int K, int act, int block_n,
-                                int* signal_flag, unsigned int* done_ctr, const int* ctx, int sbo, int lbo,
-                                int hi_bits, int k_step, cudaStream_t stream) {
+                                int* signal_flag, unsigned int* done_ctr, const int* ctx, const int* status, int sbo,
+                                int lbo, int hi_bits, int k_step, cudaStream_t stream) {
   if (K % 8 != 0 || M <= 0 || N <= 0) return -2;
   if (W2 && residual) return -2;
   if (signal_flag && (!done_ctr || !ctx)) return -2;
   GemmParams p;
   p.C = (bf16*)C; p.bias = (const bf16*)bias; p.bias2 = (const bf16*)bias2; p.residual = (const bf16*)residual;
   p.M = M; p.N = N; p.K = K; p.act = act;
-  p.signal = HopSignal{signal_flag, done_ctr}; p.ctx = ctx;
+  p.signal = HopSignal{signal_flag, done_ctr, status}; p.ctx = ctx;
   p.desc_sbo = sbo > 0 ? (unsigned)sbo : 64u;
   p.desc_lbo = lbo > 0 ? (unsigned)lbo : 1u;
   p.desc_hi_bits = hi_bits > 0 ? (unsigned)hi_bits : (1u | (2u << 15));  // version = 1 (bit 46), SWIZZLE_128B = 2 (bits 61-63)
@@ -296,5 +296,5 @@ extern "C" int mdi_gemm_bf16(const void* A, const void* W, void* C, const void* 
                              int N, int K, int block_n, int sbo, int lbo, int hi_bits, int k_step,
                              cudaStream_t stream) {
   return mdi_gemm_bf16_ex(A, W, nullptr, C, bias, nullptr, residual, M, N, K, 0, block_n, nullptr, nullptr, nullptr,
-                          sbo, lbo, hi_bits, k_step, stream);
+                          nullptr, sbo, lbo, hi_bits, k_step, stream);
 }

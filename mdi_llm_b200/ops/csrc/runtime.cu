@@ -16,6 +16,12 @@
 
 extern "C" {
 
+// sources digest this binary was built from (ops/build.py compares it with the work tree before loading)
+#ifndef MDI_BUILD_DIGEST_STR
+#define MDI_BUILD_DIGEST_STR "unknown"
+#endif
+const char* mdi_build_digest() { return "MDI_BUILD_DIGEST:" MDI_BUILD_DIGEST_STR; }
+
 const char* mdi_error_string(int code) { return cudaGetErrorString((cudaError_t)code); }
 
 int mdi_device_info(int* sm_count, int* cc_major, int* cc_minor, size_t* total_mem) {

@@ -7,12 +7,19 @@ Parity: the reference mounts every ``GPTServer`` on a CherryPy ``MethodDispatche
 
 CherryPy is not available on the target image, so the same verbs/paths/bodies are served by
 the standard library (``http.server.ThreadingHTTPServer``), with no body-size limit (model
-chunks are GBs, gptserver.py:345).  Bodies stay pickled dicts for protocol compatibility — the
-control plane is meant for a trusted cluster network, exactly like the reference.
+chunks are GBs, gptserver.py:345).  Bodies stay pickled dicts for protocol compatibility, but they are
+*decoded* with :func:`~mdi_llm_b200.utils.safe_pickle.safe_loads` (containers + tensors only), a
+shared secret (``MDI_CLUSTER_TOKEN`` / ``token=``) is checked on every request when configured, and a
+node refuses to listen on a non-loopback address without one unless ``insecure=True`` /
+``MDI_ALLOW_INSECURE=1`` (the reference's trust model: anybody who reaches the port owns the node).
+
+Requests may return a body: handlers that return a ``dict`` answer with its pickle — this is how a
+secondary hands the CUDA-IPC handles of its hop buffers back to the starter at ``POST /init``.
 """
 from __future__ import annotations
 
 import json
+import os
 import pickle
 import threading
 import time
@@ -21,7 +28,17 @@ import urllib.request
 from http.server import BaseHTTPRequestHandler, ThreadingHTTPServer
 from typing import Any, Callable, Dict, Optional, Tuple
 
-__all__ = ["ControlServer", "HTTPError", "request_to_node", "http_get_json"]
+__all__ = ["ControlServer", "HTTPError", "request_to_node", "http_get_json", "call_node", "is_loopback", "TOKEN_HEADER"]
+
+TOKEN_HEADER = "X-MDI-Token"
+
+
+def is_loopback(addr: str) -> bool:
+    return addr in ("localhost", "::1") or addr.startswith("127.")
+
+
+def cluster_token(explicit: Optional[str] = None) -> Optional[str]:
+    return explicit if explicit else (os.environ.get("MDI_CLUSTER_TOKEN") or None)
 
 
 class HTTPError(Exception):
@@ -40,8 +57,15 @@ class ControlServer:
     raises :class:`HTTPError`.
     """
 
-    def __init__(self, app: Any, host: str, port: int) -> None:
+    def __init__(self, app: Any, host: str, port: int, token: Optional[str] = None, insecure: Optional[bool] = None) -> None:
         self.app = app
+        self.token = cluster_token(token)
+        if insecure is None:
+            insecure = os.environ.get("MDI_ALLOW_INSECURE", "") not in ("", "0")
+        if not is_loopback(str(host)) and self.token is None and not insecure:
+            raise PermissionError(
+                f"refusing to serve the control plane on {host}:{port} without a shared secret: set MDI_CLUSTER_TOKEN "
+                "on every node (or pass insecure=True / MDI_ALLOW_INSECURE=1 to accept unauthenticated peers)")
         outer = self
 
         class _Req(BaseHTTPRequestHandler):
@@ -56,6 +80,8 @@ class ControlServer:
                 path = tuple(p for p in self.path.split("?")[0].split("/") if p)
                 status, payload, ctype = 200, b"", "text/plain"
                 try:
+                    if outer.token is not None and self.headers.get(TOKEN_HEADER) != outer.token:
+                        raise HTTPError(401, "bad or missing cluster token")
                     fn = getattr(outer.app, verb, None)
                     if fn is None:
                         raise HTTPError(501, f"{verb} not implemented!")
@@ -64,6 +90,8 @@ class ControlServer:
                         payload, ctype = out.encode("utf-8"), "application/json"
                     elif isinstance(out, bytes):
                         payload, ctype = out, "application/octet-stream"
+                    elif isinstance(out, dict):
+                        payload, ctype = pickle.dumps(out), "application/x-pickle"
                 except HTTPError as e:
                     status, payload = e.status, e.message.encode("utf-8")
                 except Exception as e:  # noqa: BLE001
@@ -112,40 +140,65 @@ class ControlServer:
             raise
 
 
-def _http(method: str, addr: str, data: Optional[bytes], timeout: float) -> int:
+def _http(method: str, addr: str, data: Optional[bytes], timeout: float, token: Optional[str] = None) -> Tuple[int, bytes]:
     req = urllib.request.Request(addr, data=data, method=method.upper())
     if data is not None:
         req.add_header("Content-Type", "application/octet-stream")
+    tok = cluster_token(token)
+    if tok is not None:
+        req.add_header(TOKEN_HEADER, tok)
     try:
         with urllib.request.urlopen(req, timeout=timeout) as resp:
-            resp.read()
-            return resp.status
+            return resp.status, resp.read()
     except urllib.error.HTTPError as e:
-        return e.code
+        return e.code, e.read()
 
 
-def request_to_node(req_type: str, addr: str, content: Any, max_n_requests: int = 100,
-                    retry_wait: float = 2.0, timeout: float = 100.0, verb: bool = False) -> int:
-    """POST/PUT ``pickle.dumps(content)`` to ``addr`` until it answers 200; 1 on success else 0."""
+def call_node(req_type: str, addr: str, content: Any, max_n_requests: int = 100, retry_wait: float = 2.0,
+              timeout: float = 100.0, verb: bool = False, token: Optional[str] = None) -> Tuple[int, Any]:
+    """POST/PUT ``pickle.dumps(content)``; returns ``(status, decoded body | text)``.
+
+    Retries only while the node cannot be *reached* (not up yet — the reference's start-up race,
+    model_dist.py:548-569).  Once a node answers, its status is final: a 4xx/5xx is surfaced with its
+    body instead of re-posting a multi-GB chunk a hundred times."""
     method = req_type.lower()
     if method not in ("post", "put"):
         raise ValueError(f"Unsupported request type '{req_type}'")
     payload = pickle.dumps(content)
+    status, body = 0, b""
     for attempt in range(max(1, max_n_requests)):
         try:
-            status = _http(method, addr, payload, timeout)
-            if status == 413:
-                raise ConnectionError(f"Max payload for {req_type} was exceeded!")
-            if status == 200:
-                return 1
-        except (urllib.error.URLError, ConnectionError, TimeoutError, OSError):
-            status = None
+            status, body = _http(method, addr, payload, timeout, token)
+            break
+        except (urllib.error.URLError, ConnectionError, TimeoutError, OSError) as e:
+            status, body = 0, repr(e).encode()
         if verb:
             print(f"Unable to reach node ({addr}) - retrying in {retry_wait}s ({attempt + 1}/{max_n_requests})")
-        time.sleep(retry_wait)
-    return 0
+        if attempt + 1 < max(1, max_n_requests):
+            time.sleep(retry_wait)
+    if status == 413:
+        raise ConnectionError(f"Max payload for {req_type} was exceeded!")
+    if status == 200 and body[:1] == b"\x80":
+        from ..utils.safe_pickle import safe_loads
+
+        return status, safe_loads(body)
+    return status, body.decode("utf-8", "replace") if isinstance(body, bytes) else body
+
+
+def request_to_node(req_type: str, addr: str, content: Any, max_n_requests: int = 100,
+                    retry_wait: float = 2.0, timeout: float = 100.0, verb: bool = False) -> int:
+    """POST/PUT ``pickle.dumps(content)`` to ``addr``; 1 if the node answered 200 else 0."""
+    status, body = call_node(req_type, addr, content, max_n_requests=max_n_requests, retry_wait=retry_wait,
+                             timeout=timeout, verb=verb)
+    if status != 200 and verb:
+        print(f"Node {addr} answered {status}: {body}")
+    return 1 if status == 200 else 0
 
 
 def http_get_json(addr: str, timeout: float = 10.0) -> Dict[str, Any]:
-    with urllib.request.urlopen(addr, timeout=timeout) as resp:
+    req = urllib.request.Request(addr)
+    tok = cluster_token()
+    if tok is not None:
+        req.add_header(TOKEN_HEADER, tok)
+    with urllib.request.urlopen(req, timeout=timeout) as resp:
         return json.loads(resp.read().decode("utf-8"))

@@ -10,6 +10,14 @@ and optionally the chunk itself), ``stop_nodes`` (:486-497), ``_request_to_node`
 Differences: ``n_local_layers`` is per secondary (non-uniform plans for topologies the reference
 table lacks, e.g. 8 stages); ``start`` does not crash when plotting is off (the reference
 indexes an empty ``time_gen``, model_dist.py:383, and then never stops its secondaries).
+
+B200 data plane: where the reference's nodes open sockets at init (gptserver.py:540-583), ``configure_nodes``
+here wires the *device ring* when the topology allows it (``transport="auto"|"p2p"|"nccl"``, see
+:mod:`.server`): the starter allocates its hop buffers, every ``POST /init`` answers with the CUDA-IPC
+handles of that secondary's buffers, and one ``POST /ring {"op": "connect"}`` per node hands it the handles
+of its successor.  ``partition="half"`` plans half-layer units, ``weights="fp8"`` serves block-scaled fp8,
+``random_init=<seed>`` replaces checkpoint chunks by synthetic weights (benchmarks).  ``open_session`` exposes
+the prepared generation so that a caller can run it in timed segments (``bench.py``).
 """
 from __future__ import annotations
 
@@ -21,9 +29,10 @@ from typing import Any, Dict, List, Optional, Sequence, Tuple, Union
 import torch
 
 from ..models.config import Config
-from ..models.partition import chunk_dir, count_transformer_blocks, plan_layers, split_and_store
+from ..models.partition import (chunk_dir, count_transformer_blocks, plan_half_units, plan_layers, split_and_store,
+                                stage_specs)
 from ..utils.checkpoint import lazy_load, load_from_pt
-from .control import request_to_node
+from .control import call_node, request_to_node
 from .server import GPTServer
 
 FileType = Union[str, Path]
@@ -58,6 +67,8 @@ class GPTDistributed:
         self.partition_policy = kwargs.pop("partition", "auto")
         self.push_chunks = bool(kwargs.pop("push_chunks", False))
         self.head_on: str = kwargs.get("head_on", "starter")
+        self.random_init: Optional[int] = kwargs.get("random_init")
+        self.specs: Optional[List[Dict[str, Any]]] = None
         self.full_model_name = self.ckpt_dir.name if self.ckpt_dir else None
         self.node_type = node_type
         if isinstance(config_file, dict):
@@ -80,15 +91,25 @@ class GPTDistributed:
             else:
                 node_chunks_dir = chunk_dir(self.ckpt_dir, self.n_nodes)
                 self.model_was_split = node_chunks_dir.is_dir() and (node_chunks_dir / "model_starter.pth").is_file()
-            if not self.model_was_split and self.n_nodes > 1:
+            if self.random_init is not None:  # synthetic weights: only model_config.yaml is read
+                self.model_config, _ = load_from_pt(self.ckpt_dir, config_only=True)
+                self.specs = stage_specs(self.n_nodes, self.model_config, self.partition_policy)
+                kwargs["stage_spec"] = self.specs[0]
+                self.model_was_split = True
+            elif not self.model_was_split and self.n_nodes > 1:
                 if self.verb:
                     print("Chunks not found! Splitting the model")
                 self.model_config, full_model = load_from_pt(self.ckpt_dir)
                 assert full_model is not None
-                self.plan = plan_layers(self.n_nodes, self.model_config.n_layer, self.model_config,
-                                        policy=self.partition_policy)
-                node_chunks_dir = split_and_store(full_model, self.n_nodes, self.ckpt_dir, plan=self.plan,
-                                                  config=self.model_config, verb=self.verb, head_on=self.head_on)
+                if self.partition_policy == "half" and not self.model_config.parallel_residual and self.head_on == "starter":
+                    units = plan_half_units(self.n_nodes, self.model_config)
+                    self.plan = None
+                    node_chunks_dir = split_and_store(full_model, self.n_nodes, self.ckpt_dir, units=units, verb=self.verb)
+                else:
+                    self.plan = plan_layers(self.n_nodes, self.model_config.n_layer, self.model_config,
+                                            policy="balanced" if self.partition_policy == "half" else self.partition_policy)
+                    node_chunks_dir = split_and_store(full_model, self.n_nodes, self.ckpt_dir, plan=self.plan,
+                                                      config=self.model_config, verb=self.verb, head_on=self.head_on)
                 self.model_was_split = not self.push_chunks
             else:
                 self.model_config, _ = load_from_pt(self.ckpt_dir, config_only=True)
@@ -143,9 +164,9 @@ class GPTDistributed:
                 print("Node was stopped!")
             return None
         assert n_samples and tokens_per_sample and self.model_config
-        if not self.configure_nodes(n_samples=n_samples):
-            raise RuntimeError("Unable to initialize network nodes!")
         try:
+            if not self.configure_nodes(n_samples=n_samples):
+                raise RuntimeError("Unable to initialize network nodes!")
             out_text, time_gen = self.gpt_serv.launch_starter(n_samples, tokens_per_sample, prompt)
             self.out_text = out_text
             if not quiet:
@@ -181,8 +202,10 @@ class GPTDistributed:
                 break
         if len(counts) == self.n_secondary:
             return counts
+        if self.specs is not None:
+            return [sp["n_blocks"] for sp in self.specs[1:]]
         plan = self.plan or plan_layers(self.n_nodes, self.model_config.n_layer, self.model_config,
-                                        policy=self.partition_policy)
+                                        policy="balanced" if self.partition_policy == "half" else self.partition_policy)
         return list(plan[1:])
 
     def configure_nodes(self, n_samples: int) -> int:
@@ -192,13 +215,21 @@ class GPTDistributed:
             raise ValueError("The model configuration was not loaded!")
         nodes = self.node_config["nodes"]
         secondaries = nodes.get("secondary", [])
+        serv = self.gpt_serv
+        transport = serv.resolve_transport()
+        self.transport = transport
+        handles: List[Dict[str, Any]] = []
+        if transport != "socket":  # device ring: the starter's hop buffers first (the last node stores into them)
+            handles.append(serv.ring_setup(n_samples, 0, self.n_nodes, transport))
         if not secondaries:
             if self.verb:
                 print("No secondary nodes found! Running standalone")
+            if transport != "socket":
+                serv.ring.connect(None)
             return 1
         counts = self._secondary_layer_counts()
         ring = [nodes["starter"]] + list(secondaries)  # ring order == order in the JSON
-        s = self.gpt_serv.sampling
+        s = serv.sampling
         for i, sec in enumerate(secondaries):
             msg = dict(self.init_msg)
             msg.update(
@@ -206,15 +237,48 @@ class GPTDistributed:
                 n_local_layers=counts[i], n_samples=n_samples, prev_node=ring[i],
                 next_node=ring[(i + 2) % len(ring)], max_seq_length=self.model_seq_length,
                 sampling=dict(temperature=s.temperature, top_k=s.top_k, top_p=s.top_p, seed=s.seed),
-                use_kv_cache=self.gpt_serv.use_kv_cache, head_on=self.head_on,
+                use_kv_cache=serv.use_kv_cache, head_on=self.head_on, transport=transport, weights=serv.weights,
+                max_prompt_len=serv.max_prompt_len, watchdog_s=serv.watchdog_s,
             )
-            if not self.model_was_split:
+            if self.random_init is not None:
+                assert self.specs is not None
+                msg.update(random_init=self.random_init, stage_spec=self.specs[i + 1])
+            elif not self.model_was_split:
                 msg["params"] = torch.load(self.node_chunks_dir / f"model_secondary{i}.pth",
                                            map_location="cpu", weights_only=True)
             addr = f"http://{sec['addr']}:{sec['communication']['port']}/init"
-            if not self._request_to_node("post", addr, msg):
+            status, body = call_node("post", addr, msg, verb=self.verb, timeout=3600.0)
+            if status != 200:
+                print(f"Node secondary:{i} refused initialisation ({status}): {body}")
                 return 0
+            if transport != "socket":
+                if not isinstance(body, dict) or "handles" not in body:
+                    print(f"Node secondary:{i} did not return hop-buffer handles: {body!r}")
+                    return 0
+                handles.append(body["handles"])
+        if transport != "socket":  # every node maps the buffers of its successor (ring order)
+            for j, sec in enumerate(secondaries):
+                addr = f"http://{sec['addr']}:{sec['communication']['port']}/ring"
+                status, body = call_node("post", addr, {"op": "connect", "next": handles[(j + 2) % len(handles)]},
+                                         max_n_requests=3, retry_wait=0.5, timeout=600.0)
+                if status != 200:
+                    print(f"Node secondary:{j} could not map its successor's buffers ({status}): {body}")
+                    return 0
+            serv.ring.connect(handles[1])
         return 1
+
+    def open_session(self, n_samples: int, tokens_per_sample: int,
+                     prompt: Optional[Union[str, Sequence[torch.Tensor]]] = None, mode: Optional[str] = None) -> Any:
+        """Configure the nodes and return the prepared generation (:class:`~.ring.RingSession`): ``run(rounds)``
+        enqueues prefill + that many decode rounds on every node and returns per-node device times, ``tokens()``
+        the result.  Only for the device ring (``transport`` p2p / nccl); call :meth:`stop_nodes` when done."""
+        if self.node_type != "starter":
+            raise ValueError("This method can only be called on starter nodes!")
+        if not self.configure_nodes(n_samples=n_samples):
+            raise RuntimeError("Unable to initialize network nodes!")
+        if self.gpt_serv.ring is None:
+            raise RuntimeError(f"open_session needs the device ring; this topology resolved to transport {self.transport!r}")
+        return self.gpt_serv.open_ring_session(n_samples, prompt, tokens_per_sample, mode=mode)
 
     def stop_nodes(self) -> int:
         out = 1

@@ -145,7 +145,9 @@ class FusedStage:
             self._ring_i = 0
             self.state = torch.zeros(4, **i32)
             self.pos_arr = torch.zeros(n_slots, **i32)
-            self.status = torch.zeros(4, **i32)  # [0] watchdog flag, [2:4] 64-bit exposed-wait cycle counter
+            # [0] error bits (1 hop watchdog, 2 dependency watchdog, 4 sampler overflow), [1] aborted (poison seen /
+            # own watchdog), [2:4] 64-bit exposed-wait cycle counter — see csrc/common.cuh
+            self.status = torch.zeros(4, **i32)
             self.done_ctr = torch.zeros(1, **i32)
             # intra-stage flag dependencies (see common.cuh: dep_wait / dep_signal): one flag per kernel of a step
             self.dep_flags = torch.zeros(1024, **i32)
@@ -165,6 +167,9 @@ class FusedStage:
                 self.tokens = torch.zeros(n_slots, self.S + 1, **i32)
                 self.last_token = torch.zeros(n_slots, **i32)
                 self.sample_scratch = ops.sample_scratch(dev)
+                # device timeline: %globaltimer of every sampled token + the generation's time base
+                self.tok_ts = torch.zeros(n_slots, self.S + 1, dtype=torch.int64, device=dev)
+                self.t0_ts = torch.zeros(1, dtype=torch.int64, device=dev)
         self.hop_self = HopTarget(self.hidden_in.data_ptr(), self.flags.data_ptr())
         self._graphs: Dict[Any, ops.CudaGraph] = {}
         self._trace: Optional[torch.Tensor] = None  # device tracer records [n, 6] int64 (see common.cuh)
@@ -305,7 +310,8 @@ class FusedStage:
         ops.sample_fast(self.logits, self.sample_scratch, self.tokens, self.ctx, vocab=self.cfg.padded_vocab_size,
                         top_k=s.top_k, temperature=s.temperature, greedy=greedy,
                         seed=s.seed if s.seed is not None else 0x5EED, tok_slot_stride=self.tokens.shape[1],
-                        last_token=self.last_token, use_pdl=self.use_pdl)
+                        last_token=self.last_token, use_pdl=self.use_pdl, top_p=1.0 if greedy else s.top_p,
+                        tok_ts=self.tok_ts, status=self.status)
 
     def enqueue_embed(self, from_tokens: bool) -> None:
         m, cfg = self.model, self.cfg
@@ -422,7 +428,7 @@ class FusedStage:
         def out_gemm(a_in: torch.Tensor, lin: Any, last: bool) -> Optional[torch.Tensor]:
             if hop is not None and last:
                 ops.gemm(a_in, self._dense(lin), bias=lin.bias, residual=x, out_ptr=hop[0], signal_flag=hop[1],
-                         done_ctr=self.done_ctr, ctx=self.ctx, block_n=bn)
+                         done_ctr=self.done_ctr, ctx=self.ctx, status=self.status, block_n=bn)
                 return None
             return ops.gemm(a_in, self._dense(lin), bias=lin.bias, residual=x, block_n=bn)
 

@@ -38,6 +38,16 @@ from .scheduler import SamplingParams
 __all__ = ["DevicePipeline", "connect_ring_local"]
 
 
+def _nvtx(name: str):
+    """NVTX range around a phase of the pipeline (visible in nsys / ncu timelines)."""
+    try:
+        return torch.cuda.nvtx.range(name)
+    except Exception:  # noqa: BLE001  (torch built without nvtx)
+        import contextlib
+
+        return contextlib.nullcontext()
+
+
 class DevicePipeline:
     def __init__(self, model: StageModule, rank: int, world: int, n_samples: int, max_seq_length: int,
                  sampling: Optional[SamplingParams] = None, max_prompt_len: int = 0, use_pdl: bool = True,
@@ -85,11 +95,18 @@ class DevicePipeline:
                 "prefill": self.prefill_raw.handle if self.prefill_raw else None,
                 "hidden_ptr": st.hidden_in.data_ptr(), "flag_ptr": st.flags.data_ptr(),
                 "prefill_ptr": self.prefill_in.data_ptr() if self.prefill_in is not None else 0,
-                "device": self.device.index}
+                "device": self.device.index, "pid": os.getpid()}
 
     def connect_ipc(self, nxt: Dict[str, Any]) -> None:
-        """Open the next stage's exported buffers (other process)."""
+        """Open the next stage's exported buffers (other process; a stage living in THIS process — several nodes
+        of a test in one interpreter — is addressed directly, an IPC handle cannot be opened by its exporter)."""
         lib = ops.lib()
+        if nxt.get("pid") == os.getpid():
+            if nxt["device"] != self.device.index:
+                ops.check(lib.mdi_enable_peer(self.device.index, nxt["device"]), "enable peer access")
+            self.next_hop = HopTarget(nxt["hidden_ptr"], nxt["flag_ptr"])
+            self.next_prefill_ptr = nxt["prefill_ptr"]
+            return
         with torch.cuda.device(self.device):
             p = ctypes.c_void_p()
             ops.check(lib.mdi_p2p_open(nxt["hidden"], ctypes.byref(p)), "open next hidden_in")
@@ -149,9 +166,10 @@ class DevicePipeline:
             st.pos_arr.copy_(torch.tensor(self.prompt_lens, dtype=torch.int32))
             if self.is_starter:
                 st.tokens.zero_()
+                st.tok_ts.zero_()
                 for i, p in enumerate(prompts):
-                    st.tokens[i, : p.numel()].copy_(p.to(torch.int32))
-            self.prompts = [p.to(self.device) for p in prompts] if self.is_starter else None
+                    st.tokens[i, : p.numel()].copy_(p.to(torch.int32), non_blocking=True)
+            self.prompts = [p.to(self.device, non_blocking=True) for p in prompts] if self.is_starter else None
             torch.cuda.current_stream().synchronize()
 
     def _hop_copy(self, src: torch.Tensor, dst_ptr: int) -> None:
@@ -160,7 +178,7 @@ class DevicePipeline:
         st = self.stage
         ops.check(ops.lib().mdi_copy_signal(src.data_ptr(), dst_ptr, src.numel() * src.element_size(),
                                             self.next_hop.flag_ptr, st.done_ctr.data_ptr(), st.ctx.data_ptr(),
-                                            ops.stream_ptr()), "prefill hop")
+                                            st.status.data_ptr(), ops.stream_ptr()), "prefill hop")
 
     @torch.inference_mode()
     def prefill(self) -> None:
@@ -169,9 +187,12 @@ class DevicePipeline:
         the next stage's prefill buffer over NVLink and publishes the flag from its last CTA — no copy
         kernel, no NCCL.  The last stage returns only the final row to the starter (8 KB copy+signal)."""
         st, lib = self.stage, ops.lib()
+        if self.is_starter:
+            with torch.cuda.device(self.device):
+                ops.stamp(st.t0_ts)  # time base of the device timeline (the reference's clock also starts before prefill)
         if self.hop == "nccl":
             return self._prefill_nccl()
-        with torch.cuda.device(self.device):
+        with torch.cuda.device(self.device), _nvtx(f"mdi.prefill[{self.rank}]"):
             for slot in range(self.n):
                 T = self.prompt_lens[slot]
                 pos = torch.arange(T, device=self.device)
@@ -281,7 +302,7 @@ class DevicePipeline:
         if self.hop == "nccl":
             return self._decode_rounds_nccl(n_rounds)
         launched = 0
-        with torch.cuda.device(self.device):
+        with torch.cuda.device(self.device), _nvtx(f"mdi.decode[{self.rank}] x{n_rounds}"):
             for _ in range(n_rounds):
                 r = self.round
                 if r > self.max_new:
@@ -335,13 +356,36 @@ class DevicePipeline:
         st = self.stage
         assert self.is_starter
         torch.cuda.synchronize(self.device)
-        if int(st.status[0].item()) != 0:
-            raise RuntimeError("hop watchdog expired: a pipeline stage stopped responding")
+        err, aborted = (int(x) for x in st.status[:2].tolist())
+        if err & 3 or aborted:
+            raise RuntimeError("pipeline aborted: " + ("hop watchdog expired on this stage (a neighbour stopped responding)"
+                                                       if err & 1 else "abort flag received from the ring"))
         done = min(self.round - 1, self.max_new)
         out = {}
         for i, T in enumerate(self.prompt_lens):
             out[i] = st.tokens[i, : T + done].to("cpu", torch.int64).view(1, -1)
         return out
+
+    def token_times(self) -> List[float]:
+        """starter: seconds (device clock, since the start of prefill) at which the 1st, 2nd, ... generated token
+        of the run was sampled — the reference's ``tok_time`` (gptserver.py:952-956) without a host in the loop."""
+        st = self.stage
+        assert self.is_starter
+        torch.cuda.synchronize(self.device)
+        done = min(self.round - 1, self.max_new)
+        t0 = int(st.t0_ts.item())
+        ts: List[int] = []
+        for i, T in enumerate(self.prompt_lens):
+            ts += st.tok_ts[i, T: T + done].tolist()
+        return [(t - t0) * 1e-9 for t in sorted(x for x in ts if x > 0)]
+
+    def poison(self) -> None:
+        """Abort from the host: overwrite this stage's incoming flags with the poison value on a side stream.
+        Queued steps stop waiting, mark the stage aborted and publish poison downstream (common.cuh)."""
+        side = torch.cuda.Stream(device=self.device)
+        with torch.cuda.stream(side):
+            self.stage.flags.fill_(ops.POISON)
+        side.synchronize()
 
     def generate(self, prompts: Sequence[torch.Tensor], max_new_tokens: int, sync: Optional[Callable[[], None]] = None,
                  mode: str = "device") -> Optional[Dict[int, torch.Tensor]]:

@@ -9,14 +9,21 @@ prompt-style loading (:716-749), REST verbs ``GET /``, ``POST /init``, ``PUT /st
 
 State is per instance (the reference keeps it in class attributes, one node per process,
 gptserver.py:72-137), so several nodes can share a process — which is what the CPU tests do.
+
+Data plane (``transport=``): ``"socket"`` is the reference's TCP+pickle ring driven by the host loops of
+:mod:`.scheduler`; ``"p2p"`` (what ``"auto"`` picks when every node is a CUDA device of this box and the
+architecture is covered by the fused kernels) is the device ring of :mod:`.ring` / :mod:`.pipeline`:
+hop buffers exported as CUDA-IPC handles in the ``POST /init`` response, neighbours mapped at
+``POST /ring {"op": "connect"}``, generation enqueued as CUDA-graph replays with the hop fused into the
+kernels; ``"nccl"`` keeps those kernels but moves the hop to NCCL send/recv (the comparison midpoint).
 """
 from __future__ import annotations
 
 import gc
 import json
 import logging
-import pickle
 import threading
+import time
 import warnings
 from pathlib import Path
 from typing import Any, Dict, List, Optional, Sequence, Tuple, Union
@@ -25,14 +32,15 @@ import torch
 
 from .. import config as C
 from ..models.config import Config
-from ..models.partition import count_transformer_blocks, plan_layers
+from ..models.partition import count_transformer_blocks, plan_layers, stage_shape_from_state_dict
 from ..models.stage import StageModule, build_stage
 from ..text.prompts import PromptStyle, get_user_prompt, has_prompt_style, load_prompt_style
 from ..text.tokenizer import Tokenizer
 from ..utils.checkpoint import lazy_load, materialize_stage
 from ..utils.context_managers import catch_loop_errors
 from ..utils.misc import find_eot, waiting_animation
-from .control import ControlServer, HTTPError
+from ..utils.safe_pickle import safe_loads
+from .control import ControlServer, HTTPError, is_loopback
 from .scheduler import (EagerStageRunner, GenerationResult, SamplingParams, StageRunner, secondary_loop,
                         starter_loop)
 from .transport import LoopbackTransport, SocketTransport, Transport
@@ -72,7 +80,21 @@ class GPTServer:
         self.max_seq_length: Optional[int] = kwargs.get("model_seq_length")
         self.compile = bool(kwargs.get("compile", False))
         self.engine_kind: str = kwargs.get("engine", "auto")  # "auto" | "eager" | "cuda"
-        self.transport_kind: str = kwargs.get("transport", "socket")
+        self.transport_kind: str = kwargs.get("transport", "auto")  # auto | socket | p2p | nccl
+        if self.transport_kind not in ("auto", "socket", "p2p", "nccl"):
+            raise ValueError(f"transport must be auto, socket, p2p or nccl, got {self.transport_kind!r}")
+        self.weights: str = kwargs.get("weights", "bf16")          # bf16 | fp8 (block-scaled, device ring only)
+        self.decode_mode: str = kwargs.get("decode_mode", "device")  # device ring: device-driven | host-fed steps
+        self.random_init: Optional[int] = kwargs.get("random_init")  # seed: synthetic weights instead of a chunk
+        self.stage_spec: Optional[Dict[str, Any]] = kwargs.get("stage_spec")
+        self.max_prompt_len: int = int(kwargs.get("max_prompt_len") or 0)
+        self.on_token = kwargs.get("on_token")  # streaming callback(sample, position, token) in host-fed mode
+        self.token = kwargs.get("token")
+        self.insecure = kwargs.get("insecure")
+        self.ring: Optional[Any] = None  # RingBackend when the device ring is the data plane
+        self.ring_transport: Optional[str] = None
+        self.peer_handles: List[Dict[str, Any]] = []
+        self.last_ring_stats: Optional[Dict[str, Any]] = None
         self.sampling: SamplingParams = kwargs.get("sampling") or SamplingParams(
             temperature=kwargs.get("temperature", C.TEMPERATURE), top_k=kwargs.get("top_k", C.TOP_K),
             top_p=kwargs.get("top_p", 1.0), seed=kwargs.get("seed"))
@@ -100,6 +122,7 @@ class GPTServer:
         self.prev_node: Optional[Dict[str, Any]] = None
         self.next_node: Optional[Dict[str, Any]] = None
         self.loop_error: Optional[BaseException] = None
+        self._initializing = threading.Lock()
 
         self.node_type = node_type
         self.node_config = node_config
@@ -123,7 +146,7 @@ class GPTServer:
             self.prev_node = None if self.n_nodes == 1 else secondaries[-1]
             self.model_config = model_config
             self.n_layers_local = self._infer_local_layers(self.model_path, "starter")
-            self._init_model(self.n_layers_local, model_path=self.model_path)
+            self._init_model(self.n_layers_local, model_path=None if self.random_init is not None else self.model_path)
             self._load_tokenizer(self.tokenizer_dir)
         else:
             self.model_config = model_config
@@ -151,7 +174,7 @@ class GPTServer:
 
     # ---- web server ---------------------------------------------------------------------------
     def start_webserv(self) -> None:
-        self.webserv = ControlServer(self, self.own_addr, self.own_comm_port)
+        self.webserv = ControlServer(self, self.own_addr, self.own_comm_port, token=self.token, insecure=self.insecure)
         self.webserv.start()
 
     def stop_webserv(self) -> None:
@@ -180,6 +203,8 @@ class GPTServer:
         """Layer count of this node: read it off the chunk file when there is one (works for
         any partition plan), else fall back to the planner / reference table."""
         assert self.model_config is not None
+        if self.random_init is not None and self.stage_spec:
+            return int(self.stage_spec["n_blocks"])
         if chunk is not None and Path(chunk).is_file():
             n = count_transformer_blocks(lazy_load(chunk))
             if n:
@@ -193,7 +218,7 @@ class GPTServer:
                     model_parameters: Optional[Dict[str, Any]] = None) -> None:
         assert self.model_config is not None, "No model configuration was found!"
         assert self.model is None, "The model was already initialized!"
-        if not (model_path or model_parameters):
+        if not (model_path or model_parameters) and self.random_init is None:
             raise ValueError("At least one between model_path and model_parameters must be nonempty")
         role, extra = self.node_type, {}
         if self.head_on == "finisher" and (self.n_nodes or 1) > 1:
@@ -201,25 +226,38 @@ class GPTServer:
                 extra["with_head"] = False
             elif int(role.split(":")[1]) == self.n_nodes - 2:
                 role = "finisher"
+        sd = None
+        if model_path or model_parameters is not None:
+            sd = lazy_load(model_path) if model_path else model_parameters
+            shape = stage_shape_from_state_dict(sd)  # half-layer chunks describe themselves
+        else:
+            shape = dict(self.stage_spec or {})
+        for k in ("first_mlp_only", "last_attn_only"):
+            if shape.get(k):
+                extra[k] = True
         model = build_stage(self.model_config, role, n_transf_layers, meta=True, verb=self.verb, **extra)
-        sd = lazy_load(model_path) if model_path else model_parameters
-        assert sd is not None
-        wanted = {k for k, _ in model.named_parameters()}
-        if model_path and "starter" in self.node_type and self.n_nodes == 1:
-            # standalone: the chunk is the full lit_model.pth — keys already match the starter
-            sd = {k: v for k, v in sd.items() if k in wanted or k == "lm_head.weight"}
-        materialize_stage(model, dict(sd), self.torch_model_device, self.ptdtype)
+        if sd is None:  # synthetic weights (benchmarks on a box without checkpoints): same model for any partition
+            from ..utils.checkpoint import random_init_stage_
+
+            random_init_stage_(model, self.torch_model_device, self.ptdtype, seed=int(self.random_init),
+                               layer_offset=int((self.stage_spec or {}).get("layer_offset", 0)))
+        else:
+            wanted = {k for k, _ in model.named_parameters()}
+            if model_path and "starter" in self.node_type and self.n_nodes == 1:
+                # standalone: the chunk is the full lit_model.pth — keys already match the starter
+                sd = {k: v for k, v in sd.items() if k in wanted or k == "lm_head.weight"}
+            materialize_stage(model, dict(sd), self.torch_model_device, self.ptdtype)
         if self.max_seq_length:
             model.max_seq_length = self.max_seq_length
             model.cos, model.sin = model.cos.to(self.torch_model_device), model.sin.to(self.torch_model_device)
         else:
             self.max_seq_length = model.max_seq_length
         self.model = model.eval()
-        self.runner = self._make_runner(model)
+        self.runner = None  # built on first use: sized from n_samples, and not at all when the device ring runs
         del sd
         gc.collect()
 
-    def _make_runner(self, model: StageModule) -> StageRunner:
+    def _make_runner(self, model: StageModule, n_samples: Optional[int] = None) -> StageRunner:
         kind = self.engine_kind
         legacy = not self.use_kv_cache or (self.head_on == "finisher" and (self.n_nodes or 1) > 1)
         if kind in ("auto", "cuda") and self.torch_model_device.type == "cuda" and not legacy:
@@ -227,13 +265,57 @@ class GPTServer:
                 from .engine import FusedStageRunner, engine_supports
 
                 if engine_supports(model.config, self.ptdtype):
-                    return FusedStageRunner(model, max_seq_length=model.max_seq_length)
+                    return FusedStageRunner(model, max_seq_length=model.max_seq_length, n_slots=max(1, int(n_samples or 8)),
+                                            sampling=self.sampling)
                 if kind == "cuda":
                     raise RuntimeError(f"CUDA engine does not support config {model.config.name}")
             except ImportError:
                 if kind == "cuda":
                     raise
-        return EagerStageRunner(model)
+        return EagerStageRunner(model, n_slots_hint=max(1, int(n_samples or 1)))
+
+    # ---- device ring (transport p2p / nccl) --------------------------------------------------------------
+    def resolve_transport(self) -> str:
+        """The data plane this run will use.  ``auto`` → ``p2p`` iff this node can run the fused ring and
+        every node of the topology lives on this box (CUDA IPC cannot cross hosts) on a CUDA device."""
+        legacy = not self.use_kv_cache or self.head_on == "finisher"
+        kind = self.transport_kind
+        if kind == "socket" or self.engine_kind == "eager" or legacy or self.chaos is not None:
+            if kind in ("p2p", "nccl"):
+                raise ValueError(f"transport {kind!r} needs the fused engine with KV caches (no chaos policy, no legacy protocol)")
+            return "socket"
+        from .ring import ring_capable
+
+        assert self.model_config is not None
+        capable = ring_capable(self.model_device, self.ptdtype, self.model_config)
+        if kind in ("p2p", "nccl"):
+            if not capable:
+                raise ValueError(f"transport {kind!r}: {self.model_config.name} / {self.dtype} on {self.model_device} is not "
+                                 "covered by the fused engine — use --transport socket")
+            return kind
+        nodes = self.node_config.get("nodes", {}) if "nodes" in self.node_config else {}
+        every = [nodes.get("starter", self.own_config)] + list(nodes.get("secondary", []))
+        one_box = all(is_loopback(str(n["addr"])) for n in every) or len({str(n["addr"]) for n in every}) == 1
+        all_cuda = all(str(n.get("device", self.model_device)).startswith("cuda") for n in every)
+        return "p2p" if capable and one_box and all_cuda else "socket"
+
+    def ring_setup(self, n_samples: int, rank: int, world: int, transport: str = "p2p") -> Dict[str, Any]:
+        """Build this node's :class:`RingBackend` (hop buffers allocated exportable) and return the CUDA-IPC
+        handles a predecessor needs to store into them."""
+        from .ring import RingBackend
+
+        assert self.model is not None
+        if self.ring is not None and (self.ring.n_samples != n_samples or self.ring.world != world):
+            self.ring.close()
+            self.ring = None
+        if self.ring is None:
+            cycles = int(self.watchdog_s * 1.9e9) if self.watchdog_s else 20_000_000_000
+            self.ring = RingBackend(self.model, rank, world, n_samples, self.model.max_seq_length, sampling=self.sampling,
+                                    max_prompt_len=self.max_prompt_len or self.model.max_seq_length,
+                                    hop="nccl" if transport == "nccl" else "p2p", weight_dtype=self.weights,
+                                    wait_max_cycles=cycles)
+        self.ring_transport = transport
+        return self.ring.handles()
 
     def _load_tokenizer(self, tokenizer_dir: FileType) -> None:
         d = Path(tokenizer_dir)
@@ -262,6 +344,9 @@ class GPTServer:
             raise ValueError(f"Cannot run `launch_starter` for node type {self.role}")
         metrics: Dict[str, Any] = {}
         self.n_samples = n_samples
+        if self.ring is None and (self.n_nodes or 1) == 1 and self.resolve_transport() != "socket":
+            self.ring_setup(n_samples, 0, 1, "p2p")  # standalone on a GPU: the ring closes on this node
+            self.ring.connect(None)
         self.inference_thread = threading.Thread(
             target=self.start_inference, args=(n_samples,),
             kwargs={"max_new_tokens": max_tokens, "prompt": prompt, "metrics": metrics})
@@ -277,15 +362,31 @@ class GPTServer:
             return LoopbackTransport(chaos=self.chaos)
         if self.prev_node is None or self.next_node is None:
             raise RuntimeError("Missing neighboring node info!")
-        if self.transport_kind != "socket":
-            raise ValueError(f"GPTServer supports the socket transport between processes, got {self.transport_kind!r}")
         return SocketTransport(self.own_config, self.prev_node, self.next_node,
                                is_starter=self.role == "starter", chaos=self.chaos, verb=self.verb)
 
     def start_inference(self, n_samples: int, *, max_new_tokens: Optional[int] = None,
                         prompt: Optional[Union[str, Sequence[torch.Tensor]]] = None,
                         metrics: Optional[Dict[str, Any]] = None) -> None:
-        assert self.model_config is not None and self.model is not None and self.runner is not None
+        assert self.model_config is not None and self.model is not None
+        if self.ring is not None and self.role == "starter":
+            try:
+                self.running.set()
+                assert max_new_tokens is not None
+                out_text, gen_time = self._starter_ring(n_samples, prompt, int(max_new_tokens))
+                if metrics is not None:
+                    metrics["gen_text"], metrics["gen_time"] = out_text, gen_time
+            except BaseException as e:  # noqa: BLE001
+                self.loop_error = e
+                logger_wp.error(f"device ring failed: {e!r}")
+                if metrics is not None:
+                    metrics.setdefault("gen_text", [])
+                    metrics.setdefault("gen_time", [])
+            finally:
+                self.running.clear()
+            return
+        if self.runner is None:
+            self.runner = self._make_runner(self.model, n_samples)
         try:
             if self.transport is not None:
                 self.transport.shutdown()
@@ -351,6 +452,51 @@ class GPTServer:
         assert self.tok is not None
         return [self.tok.decode(s) for s in truncated], self.tok_time
 
+    def open_ring_session(self, n_samples: int, prompt: Any, max_new_tokens: int, mode: Optional[str] = None) -> Any:
+        """Prepared generation over the device ring (prompts encoded, every node reset); drive it with
+        ``session.run(rounds)``.  ``launch_starter`` is ``open_ring_session`` + ``run()`` + decode."""
+        from .ring import RingSession
+
+        assert self.ring is not None and self.model is not None
+        idx = self.encode_prompts(prompt, n_samples)
+        S = self.model.max_seq_length
+        if any(max_new_tokens + p.numel() > S for p in idx):
+            raise ValueError(f"Cannot generate {max_new_tokens} tokens - would exceed block size!")
+        secondaries = self.node_config.get("nodes", {}).get("secondary", []) if self.n_nodes and self.n_nodes > 1 else []
+        return RingSession(self.ring, secondaries, idx, max_new_tokens, mode=mode or self.decode_mode)
+
+    def _starter_ring(self, n_samples: int, prompt: Any, max_new: int) -> Tuple[List[str], List[Tuple[int, float]]]:
+        """Generation through the device ring.  Device-driven: everything is enqueued at once and the per-token
+        timeline comes from device timestamps; host-fed: every sampled token is read back as it appears."""
+        sess = self.open_ring_session(n_samples, prompt, max_new)
+        tok_time: List[Tuple[int, float]] = [(0, 0.0)]
+        try:
+            if sess.mode == "host":
+                t0 = [0.0]
+
+                def on_token(slot: int, pos: int, tok: int) -> None:
+                    if not t0[0]:
+                        t0[0] = sess.t0_host
+                    tok_time.append((len(tok_time), time.time() - t0[0]))
+                    if self.on_token is not None:
+                        self.on_token(slot, pos, tok)
+
+                stats = sess.run(on_token=on_token)
+            else:
+                stats = sess.run()
+                tok_time += [(i + 1, t) for i, t in enumerate(self.ring.token_times())]
+            self.last_ring_stats = stats
+            samples = sess.tokens()
+        finally:
+            sess.close()
+        lens = {i: n for i, n in enumerate(sess.prompt_lens)}
+        self.last_result = GenerationResult(samples=samples, prompt_lengths=lens, tok_time=tok_time,
+                                            n_tokens=max_new * n_samples, elapsed=tok_time[-1][1])
+        self.tok_time = tok_time
+        truncated = [find_eot(samples[i], self.stop_tokens, lens[i]) for i in sorted(samples)]
+        assert self.tok is not None
+        return [self.tok.decode(s) for s in truncated], tok_time
+
     def _secondary_loop(self) -> None:
         assert self.runner is not None and self.transport is not None
         with catch_loop_errors(running_event=self.running):
@@ -360,6 +506,11 @@ class GPTServer:
     def stop_generation(self) -> int:
         try:
             self.running.clear()
+            if self.ring is not None:
+                if "starter" not in self.role:
+                    self.ring.abort()  # a node told to stop while steps are queued: poison, so the ring drains
+                self.ring.close()
+                self.ring = None
             if "starter" not in self.role and self.inference_thread is not None \
                     and self.inference_thread is not threading.current_thread():
                 self.inference_thread.join(timeout=10)
@@ -388,16 +539,32 @@ class GPTServer:
                                "error": repr(self.loop_error) if self.loop_error else None})
         raise HTTPError(404, "Not found")
 
-    def POST(self, path: Tuple[str, ...], body: bytes) -> None:  # noqa: N802
+    def POST(self, path: Tuple[str, ...], body: bytes) -> Optional[Dict[str, Any]]:  # noqa: N802
         if "secondary" not in (self.node_type or "secondary"):
             raise HTTPError(403, "Unable to initialize node!")
+        if path and path[0] == "ring":
+            if self.ring is None:
+                raise HTTPError(409, "this node was not initialised for the device ring")
+            try:
+                return self.ring.handle(safe_loads(body))
+            except Exception as e:  # noqa: BLE001
+                self.loop_error = e
+                raise HTTPError(500, f"ring op failed: {e!r}") from e
+        if self._initializing.acquire(blocking=False) is False:
+            raise HTTPError(409, "node initialisation already in progress")
+        try:
+            return self._post_init(path, body)
+        finally:
+            self._initializing.release()
+
+    def _post_init(self, path: Tuple[str, ...], body: bytes) -> Optional[Dict[str, Any]]:
         if self.model is not None:
             raise HTTPError(403, f"Failed to configure node - the model was already initialized: {self.node_type}")
         if not path or path[0] != "init":
             raise HTTPError(404, "Not found")
         if self.running.is_set():
             raise HTTPError(409, "node is already running")
-        init_msg = pickle.loads(body)
+        init_msg = safe_loads(body)
         self.prev_node, self.next_node = init_msg["prev_node"], init_msg["next_node"]
         self.model_config = Config.from_dict(init_msg["model_config"])
         self.n_nodes = init_msg["n_nodes"]
@@ -408,19 +575,41 @@ class GPTServer:
             self.sampling = SamplingParams(**init_msg["sampling"])
         self.use_kv_cache = bool(init_msg.get("use_kv_cache", True))
         self.head_on = init_msg.get("head_on", "starter")
+        transport = init_msg.get("transport", "socket")
+        self.weights = init_msg.get("weights", self.weights)
+        self.max_prompt_len = int(init_msg.get("max_prompt_len") or self.max_prompt_len or 0)
+        if init_msg.get("watchdog_s"):
+            self.watchdog_s = float(init_msg["watchdog_s"])
+        if init_msg.get("random_init") is not None:
+            self.random_init, self.stage_spec = int(init_msg["random_init"]), init_msg.get("stage_spec")
+        elif init_msg.get("stage_spec") and self.stage_spec is None:
+            self.stage_spec = init_msg["stage_spec"]
+        if transport in ("p2p", "nccl"):
+            from .ring import ring_capable
+
+            if not ring_capable(self.model_device, self.ptdtype, self.model_config):
+                raise HTTPError(400, f"node {self.role} ({self.model_device}, {self.dtype}) cannot join a {transport} device "
+                                     "ring: restart the run with --transport socket")
         params = init_msg.pop("params", None)
         if params is not None:
             self._init_model(self.n_layers_local, model_parameters=params)
             del params
             gc.collect()
+        elif self.random_init is not None:
+            self._init_model(self.n_layers_local)
         else:
             if self.model_path is None:
                 raise HTTPError(400, "The received message did not contain the model parameters - please "
                                      "specify a model chunk path when initializing GPTServer object")
             self._init_model(self.n_layers_local, model_path=self.model_path)
         logger_wp.info("Received initialization information!")
+        if transport in ("p2p", "nccl"):
+            rank = 1 + int(self.role.split(":")[1])
+            handles = self.ring_setup(int(self.n_samples), rank, int(self.n_nodes), transport)
+            return {"transport": transport, "handles": handles}
         self.inference_thread = threading.Thread(target=self.start_inference, daemon=True, args=(self.n_samples,))
         self.inference_thread.start()
+        return {"transport": "socket"}
 
     def PUT(self, path: Tuple[str, ...], body: bytes) -> None:  # noqa: N802
         if self.node_type == "starter":

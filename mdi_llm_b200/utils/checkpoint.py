@@ -261,15 +261,31 @@ def write_random_checkpoint(
     return out
 
 
+def _key_seed(seed: int, key: str) -> int:
+    import zlib
+
+    return (int(seed) * 1000003 + zlib.crc32(key.encode())) & (2 ** 62 - 1)
+
+
 def random_init_stage_(model: nn.Module, device: Union[str, torch.device], dtype: torch.dtype = torch.bfloat16,
-                       seed: int = 1234, std: float = 0.02) -> nn.Module:
+                       seed: int = 1234, std: float = 0.02, layer_offset: int = 0) -> nn.Module:
     """Materialise a meta-built stage directly on ``device`` with random weights (no checkpoint
-    I/O — benchmarks on the network-less GPU box).  Norm weights ~ 1 ± 0.1, the rest N(0, std)."""
-    g = torch.Generator(device=device).manual_seed(seed)
+    I/O — benchmarks on the network-less GPU box).  Norm weights ~ 1 ± 0.1, the rest N(0, std).
+
+    Every tensor is drawn from its own generator seeded by ``(seed, global parameter name)`` — the local
+    block index shifted by ``layer_offset`` — so the SAME model comes out whatever the partition: the N
+    stages of a pipeline and a single-stage copy built with the same seed hold identical weights (what the
+    token-exactness checks of ``bench.py`` and the tests rely on)."""
+    g = torch.Generator(device=device)
     for key, (mod, attr) in get_keys_to_submodule(model).items():
         old = getattr(mod, attr)
         if old.device.type != "meta":
             continue
+        gkey = key
+        if key.startswith("transformer.h."):
+            _, _, li, tail = key.split(".", 3)
+            gkey = f"transformer.h.{int(li) + layer_offset}.{tail}"
+        g.manual_seed(_key_seed(seed, gkey))
         if "norm" in key or "ln_f" in key:
             t = (1.0 + 0.1 * torch.randn(old.shape, generator=g, device=device, dtype=torch.float32))
             if key.endswith(".bias"):
