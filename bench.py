@@ -12,8 +12,13 @@ Contract (driver): ``python bench.py --gpus N --steps K --warmup W`` (N > 1: lau
   *decode*), bracketed by barrier + ``torch.cuda.synchronize()``; device time from CUDA events,
   MAX over ranks.  Inputs larger than L2: each round streams the stage's weights
   (16 GB / N ≫ 126 MB L2) so no L2 flush is needed between iterations.
-* ``e2e``: the same rounds through the public host-fed API (``DevicePipeline`` mode="host"):
-  every step copies its descriptor H2D from pinned memory and reads the sampled token back D2H.
+* The run goes THROUGH THE NODE API: rank 0 builds ``GPTDistributed("starter")``, rank i ``GPTDistributed("secondary:i-1")``
+  (the objects behind the ``starter`` / ``secondary`` CLIs); HTTP control plane, CUDA-IPC handles exchanged at ``POST /init``,
+  fused NVLink hops.  ``open_session().run(rounds)`` is how exactly K rounds get timed (CUDA events on every node, max).
+* ``e2e``: the same API with ``decode_mode="host"``: every step copies its descriptor H2D from pinned memory and reads the
+  sampled token back D2H; wall clock on the starter.
+* after the timed regions: ``tokens_match`` (greedy N-node tokens == one-stage pipeline tokens, and near-arg-max of the eager
+  PyTorch model), ``long_run`` (>= 256 timed rounds), and at N=8 BASELINE config #5 (fp8, 2048-token context).
 * ``--impl reference`` runs the unmodified reference (baseline/_ref) — see baseline/run_reference.py.
 
 Synthetic prompts, random-init weights of the Llama-3-8B architecture (no network on the box).
@@ -147,7 +152,8 @@ def parse_args() -> argparse.Namespace:
     ap.add_argument("--warmup", type=int, default=8)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--model", default="Llama-3-8B")
-    ap.add_argument("--prompt-len", type=int, default=64)
+    ap.add_argument("--prompt-len", type=int, default=448,
+                    help="prompt tokens per sample; the timed rounds then run at a realistic context (~0.5k positions) in both arms")
     ap.add_argument("--seq-len", type=int, default=0, help="KV/context budget (0 = prompt + all rounds)")
     ap.add_argument("--e2e-steps", type=int, default=0, help="rounds of the host-fed e2e measurement (0 = min(steps, 64))")
     ap.add_argument("--n-samples", type=int, default=0, help="concurrent samples (0 = number of GPUs)")
@@ -163,10 +169,16 @@ def parse_args() -> argparse.Namespace:
     ap.add_argument("--temperature", type=float, default=0.8)
     ap.add_argument("--top-k", type=int, default=200)
     ap.add_argument("--tiny", action="store_true", help="tiny model (CI smoke of the harness; NOT a valid bench number)")
+    ap.add_argument("--direct", action="store_true", help="drive DevicePipeline directly under torch.distributed (round-1 harness, A/B only)")
+    ap.add_argument("--no-check", action="store_true", help="skip the greedy token check that follows the timed regions")
+    ap.add_argument("--long-steps", type=int, default=256, help="rounds of the additional long run reported as long_run (0 = off)")
+    ap.add_argument("--no-extras", dest="extras", action="store_false",
+                    help="N=8: skip the extra fp8 / 2048-context job (BASELINE config #5) that follows the headline job")
     return ap.parse_args()
 
 
-def run_ours(args: argparse.Namespace) -> Dict[str, Any]:
+def run_direct(args: argparse.Namespace) -> Dict[str, Any]:
+    """Round-1 harness kept for A/B: ``DevicePipeline`` driven directly under torch.distributed (no node API)."""
     import torch
     import torch.distributed as dist
 
@@ -298,7 +310,7 @@ def run_ours(args: argparse.Namespace) -> Dict[str, Any]:
         "warmup": args.warmup, "ms_per_step": round(ms_total / args.steps, 5), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": _vs_published(cfg.name, world, value),
         "dtype": "bf16" if args.weights == "bf16" else "fp8-e4m3 block-scaled weights (128), bf16 activations, fp32 accumulate",
-        "data": "synthetic prompts, random-init weights", "impl": "ours",
+        "data": "synthetic prompts, random-init weights", "impl": "ours-direct",
         "config": {"model": cfg.name, "n_layer": cfg.n_layer, "global_batch": n_samples, "seq_len": seq_len,
                    "prompt_len": args.prompt_len, "parallelism": f"pp{world} recurrent pipeline, plan {plan}",
                    "tokens_per_step": n_samples, "l2_policy": "inputs (stage weights) larger than L2, no flush",
@@ -323,6 +335,235 @@ def run_ours(args: argparse.Namespace) -> Dict[str, Any]:
     return out if rank == 0 else {}
 
 
+def _bench_topology(world: int, job: int) -> Dict[str, Any]:
+    """Loopback node JSON (reference schema); ports derived from the rendezvous port so that every rank computes
+    the same file without talking and concurrent / stale runs never collide."""
+    base = 30000 + (int(os.environ.get("MASTER_PORT", "29500")) % 1000) * 30 + job * 1000
+
+    def node(i: int) -> Dict[str, Any]:
+        return {"addr": "127.0.0.1", "communication": {"port": base + i, "starter_addr": "127.0.0.1"},
+                "inference": {"port_in": base + 10 + 2 * i, "port_out": base + 11 + 2 * i}, "device": f"cuda:{i}"}
+
+    return {"nodes": {"starter": node(0), "secondary": [node(i) for i in range(1, world)]}}
+
+
+def run_job(args: argparse.Namespace, job: int = 0, light: bool = False) -> Dict[str, Any]:
+    """One benchmark job THROUGH THE NODE API: rank 0 is a ``GPTDistributed("starter")``, rank i a
+    ``GPTDistributed("secondary:i-1")`` — the objects behind the ``starter`` / ``secondary`` CLIs — on
+    ``cuda:LOCAL_RANK``; HTTP control plane, CUDA-IPC handle exchange at ``/init``, fused NVLink hops.
+    torch.distributed is not used by the p2p data plane at all (``--hop nccl`` initialises NCCL for its hops)."""
+    import tempfile
+
+    import torch
+
+    from mdi_llm_b200.models.config import Config
+    from mdi_llm_b200.parallel.distributed import GPTDistributed
+    from mdi_llm_b200.parallel.scheduler import SamplingParams
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit(f"--gpus {args.gpus} needs torch.distributed.run --nproc-per-node {args.gpus}")
+        args.gpus = world
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if args.hop == "nccl" and world > 1:
+        import torch.distributed as dist
+
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if not dist.is_initialized():
+            dist.init_process_group("nccl", device_id=device)
+    if args.variant >= 0:
+        from mdi_llm_b200 import ops as _ops
+
+        _ops.set_linear_variant(args.variant)
+    if args.tiny:
+        cfg = Config.from_name("tiny-llama-1.1b", n_layer=8, n_embd=512, n_head=8, n_query_groups=2,
+                               intermediate_size=1024, vocab_size=2000, padded_vocab_size=2048, block_size=2048)
+    else:
+        cfg = Config.from_name(args.model)
+    n_samples = args.n_samples or world
+    e2e_rounds = args.e2e_steps or min(args.steps, 64)
+    check_rounds = 16
+    rounds_total = args.warmup + args.steps + 1
+    need = rounds_total if light else max(rounds_total, e2e_rounds + 4, check_rounds + 1)
+    # same context budget formula as the reference arm (baseline/run_reference.py)
+    seq_len = args.seq_len or min(cfg.block_size, ((args.prompt_len + need + 64) // 64) * 64)
+    ckpt = os.path.join(tempfile.gettempdir(), f"mdi_bench_{os.environ.get('MASTER_PORT', '0')}_{job}_r{rank}", "custom", cfg.name)
+    os.makedirs(ckpt, exist_ok=True)
+    cfg.save(ckpt)  # model_config.yaml: all the API needs next to synthetic weights
+    topo = _bench_topology(world, job)
+    sampling = SamplingParams(temperature=args.temperature, top_k=args.top_k, seed=2024)
+    common = dict(ckpt_dir=ckpt, device=f"cuda:{local_rank}", dtype="bfloat16", transport=args.hop if world > 1 else "p2p",
+                  weights=args.weights, engine="cuda")
+    if rank > 0:  # ---- worker nodes: exactly what `secondary.py` does -------------------------------------------
+        node = GPTDistributed(f"secondary:{rank - 1}", topo, **common)
+        node.start()  # serves POST /init, POST /ring ... until the starter's PUT /stop
+        return {}
+
+    import warnings
+
+    warnings.filterwarnings("ignore", message="No tokenizer files")
+    gd = GPTDistributed("starter", topo, model_seq_length=seq_len, partition=args.partition, random_init=1234, sampling=sampling,
+                        max_prompt_len=args.prompt_len, **common)
+    g = torch.Generator().manual_seed(7)
+    prompts = [torch.randint(0, cfg.vocab_size, (args.prompt_len,), generator=g, dtype=torch.int32) for _ in range(n_samples)]
+    out: Dict[str, Any] = {}
+    try:
+        # ---------------- device-driven, device-timed (CUDA events on every node, max over nodes) ----------------
+        sess = gd.open_session(n_samples, rounds_total, prompts, mode="device")
+        plan = [sp["units"] / 2 for sp in gd.specs] if gd.specs else [cfg.n_layer]
+        warm = sess.run(args.warmup)  # prefill of every prompt through every stage + W warm-up rounds
+        sampler = ClockSampler(world)
+        sampler.start()
+        timed = sess.run(args.steps)
+        clocks = sampler.stop()
+        sess.close()
+        ms_total = timed["decode_ms"]
+        tokens = args.steps * n_samples
+        value = tokens / (ms_total / 1e3)
+        launches = sum(r["graph_launches"] * r["kernels_per_graph"] for r in timed["per_node"])
+        sm_khz = 1_965_000
+        waits = [r["wait_cycles"] / (sm_khz / 1e3) / max(1, tokens) for r in sorted(timed["per_node"], key=lambda r: r["rank"])]
+
+        # ---------------- end to end: host-fed steps through the same API objects ----------------------------------
+        serv = gd.gpt_serv
+        if light or (args.hop == "nccl" and world > 1):
+            e2e = {"value": None, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+        else:
+            pinned = [p.pin_memory() for p in prompts]  # inputs start in pinned host memory
+            s2 = serv.open_ring_session(n_samples, pinned, e2e_rounds + 2, mode="host")
+            s2.run(1)  # prefill + one untimed round (graph capture of the host-fed variant)
+            t0 = time.perf_counter()
+            r2 = s2.run(e2e_rounds)
+            e2e_s = time.perf_counter() - t0  # wall clock on the starter around the API call; nodes' GPUs are done when it returns
+            s2.close()
+            steps_e2e = e2e_rounds * n_samples
+            st_local = r2["per_node"][0]
+            e2e = {"value": round(steps_e2e / e2e_s, 3), "unit": "tokens/s", "h2d_bytes_per_step": st_local["h2d"] // steps_e2e,
+                   "d2h_bytes_per_step": st_local["d2h"] // steps_e2e, "rounds": e2e_rounds,
+                   "how": "GPTDistributed/GPTServer API, decode_mode=host: pinned step descriptor H2D + sampled token D2H every "
+                          "step on the starter; wall clock around the call (includes the HTTP fan-out to the nodes)"}
+
+        # ---------------- correctness, outside the timed regions ---------------------------------------------------
+        check = _token_check(serv, cfg, prompts, n_samples, min(check_rounds, seq_len - args.prompt_len - 1), seq_len, world, args) \
+            if not (args.no_check or (light and args.weights == "bf16")) else {}
+
+        out = {
+            "metric": METRIC.replace("Llama-3-8B", cfg.name) if cfg.name != "Llama-3-8B" else METRIC, "value": round(value, 3),
+            "unit": "tokens/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": round(ms_total / args.steps, 5), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": _vs_published(cfg.name, world, value),
+            "dtype": "bf16" if args.weights == "bf16" else "fp8-e4m3 block-scaled weights (128), bf16 activations, fp32 accumulate",
+            "data": "synthetic prompts, random-init weights", "impl": "ours",
+            "config": {"model": cfg.name, "n_layer": cfg.n_layer, "global_batch": n_samples, "seq_len": seq_len,
+                       "prompt_len": args.prompt_len, "parallelism": f"pp{world} recurrent pipeline, plan {plan}",
+                       "tokens_per_step": n_samples, "l2_policy": "inputs (stage weights) larger than L2, no flush",
+                       "sampling": {"temperature": args.temperature, "top_k": args.top_k},
+                       "api": "GPTDistributed(starter) + GPTDistributed(secondary:i) per GPU, HTTP control plane, "
+                              "CUDA-IPC handles exchanged at POST /init",
+                       "hop": ("NCCL send/recv (baseline midpoint)" if args.hop == "nccl" else "fused P2P store + flag (NVLink)") if world > 1 else "local (standalone ring)",
+                       "timing": "CUDA events around each node's K decode rounds, max over nodes"},
+            "clocks": clocks, "e2e": e2e,
+            "prefill_ms_all_samples": round(warm["prefill_ms"], 3), "gpu_launches": int(launches),
+            "hop_watchdog_status": max(max(r["status"]) for r in timed["per_node"]),
+            "stage_wait_us_per_step": [round(x, 2) for x in waits],
+            "stage_busy_us_per_step": [round(ms_total * 1e3 / tokens - x, 2) for x in waits],
+            "per_node_decode_ms": [round(r["decode_ms"], 3) for r in sorted(timed["per_node"], key=lambda r: r["rank"])],
+        }
+        out.update(check)
+        if args.tiny:
+            out["config"]["WARNING"] = "tiny smoke model — not the BASELINE config"
+    finally:
+        gd.stop_nodes()
+        gd.gpt_serv.shutdown()
+    return out
+
+
+def _token_check(serv: Any, cfg: Any, prompts: List[Any], n_samples: int, rounds: int, seq_len: int, world: int,
+                 args: argparse.Namespace) -> Dict[str, Any]:
+    """Greedy decoding through the N-node API must give the SAME tokens as a one-stage pipeline holding the same
+    model (weights are seeded per parameter name, so any partition is the same model), and every token must be the
+    (near-)arg-max of the eager PyTorch model's teacher-forced logits."""
+    import torch
+
+    from mdi_llm_b200.models.stage import build_stage
+    from mdi_llm_b200.parallel.pipeline import DevicePipeline
+    from mdi_llm_b200.parallel.scheduler import SamplingParams
+    from mdi_llm_b200.utils.checkpoint import random_init_stage_
+
+    dev = serv.torch_model_device
+    s = serv.open_ring_session(n_samples, prompts, rounds, mode="device", sampling=SamplingParams.greedy())
+    s.run()
+    got = s.tokens()
+    s.close()
+    res: Dict[str, Any] = {"token_check_rounds": rounds}
+    full = build_stage(cfg, "starter", cfg.n_layer, meta=True)
+    random_init_stage_(full, dev, torch.bfloat16, seed=1234)
+    if world > 1 or args.weights != "bf16":
+        single = DevicePipeline(full, 0, 1, n_samples=n_samples, max_seq_length=seq_len, sampling=SamplingParams.greedy(),
+                                weight_dtype=args.weights)
+        ref = single.generate(prompts, rounds)
+        res["tokens_match"] = all(torch.equal(got[i], ref[i]) for i in range(n_samples))
+        res["tokens_match_what"] = f"{world}-node API run vs one-stage pipeline, greedy, {rounds} tokens x {n_samples} samples"
+        del single
+    if args.weights == "bf16":  # eager oracle: same weights through stock PyTorch ops
+        full.max_seq_length = seq_len
+        full.set_kv_cache(1, device=dev, dtype=torch.bfloat16)
+        worst = 0.0
+        with torch.inference_mode():
+            for i in range(min(n_samples, 2)):
+                toks = got[i].to(dev)
+                T = toks.shape[1]
+                h = full(toks[:, :-1].long(), torch.arange(T - 1, device=dev), slot=0)
+                logits = full.head(h).float()[0]
+                P = prompts[i].numel()
+                rows = logits[P - 1:]
+                chosen = rows.gather(1, toks[0, P:].long().view(-1, 1)).squeeze(1)
+                worst = max(worst, float((rows.max(dim=1).values - chosen).max()))
+        res["tokens_vs_eager_max_logit_gap"] = round(worst, 4)
+        res["tokens_near_argmax_of_eager"] = worst <= 0.25
+        if world == 1:
+            res["tokens_match"] = res["tokens_near_argmax_of_eager"]
+            res["tokens_match_what"] = "1-node API run vs eager PyTorch model: every token within 0.25 logit of the oracle's arg-max"
+    del full
+    torch.cuda.empty_cache()
+    return res
+
+
+def run_ours(args: argparse.Namespace) -> Dict[str, Any]:
+    """Headline job, then (same ranks, fresh nodes) the BASELINE-length jobs that the 20-step headline cannot show."""
+    import copy
+    import gc
+
+    out = run_job(args, 0)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    extras = []
+    if args.extras and not args.tiny and args.long_steps > 0:  # >= 256 timed rounds at the same dtype / prompt length
+        a = copy.copy(args)
+        a.steps, a.warmup, a.seq_len = args.long_steps, 8, 0
+        extras.append(("long_run", a))
+    if args.extras and world == 8 and not args.tiny and args.weights == "bf16" and args.model == "Llama-3-8B":
+        a = copy.copy(args)  # BASELINE config #5: fp8 block-scaled weights, 1024-token prompts, 2048-token context
+        a.weights, a.prompt_len, a.seq_len, a.steps, a.warmup = "fp8", 1024, 2048, 256, 8
+        extras.append(("baseline_config_5_fp8_2048ctx", a))
+    for job, (key, a) in enumerate(extras, start=1):
+        import torch
+
+        gc.collect()
+        torch.cuda.empty_cache()
+        try:
+            r = run_job(a, job, light=True)
+        except Exception as e:  # noqa: BLE001  (never lose the headline line to an extra)
+            r = {"error": repr(e)[:300]}
+        if out:
+            out[key] = {k: r[k] for k in ("value", "unit", "dtype", "steps", "warmup", "ms_per_step", "prefill_ms_all_samples",
+                                          "tokens_match", "tokens_match_what", "config", "error") if k in r}
+    return out
+
+
 def main() -> None:
     args = parse_args()
     if args.impl == "reference":
@@ -339,6 +580,8 @@ def main() -> None:
             sys.stdout.flush()
             os.dup2(saved, 1)
             os.close(saved)
+    elif args.direct:
+        out = run_direct(args)
     else:
         out = run_ours(args)
     if out:

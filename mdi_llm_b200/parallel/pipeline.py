@@ -136,9 +136,23 @@ class DevicePipeline:
         dist.barrier(group=group)
 
     def close(self) -> None:
+        """Unmap the neighbour's buffers and release this stage's exportable allocations."""
+        torch.cuda.synchronize(self.device)
         for p in self._opened:
             ops.lib().mdi_p2p_close(p)
         self._opened.clear()
+        self.stage._graphs.clear()
+        for raw in (self.prefill_raw, self.stage.raw):
+            if raw is not None:
+                raw.free()
+        self.prefill_raw = self.stage.raw = None
+
+    def set_sampling(self, sampling: SamplingParams) -> None:
+        """Change the sampling parameters (starter): they are kernel arguments of the captured step graphs, so the
+        graphs are dropped and re-captured on the next launch."""
+        if sampling != self.stage.sampling:
+            self.stage.sampling = sampling
+            self.stage._graphs.clear()
 
     # ---- generation phases ------------------------------------------------------------------------
     def prepare(self, prompts: Sequence[torch.Tensor], max_new_tokens: int) -> None:

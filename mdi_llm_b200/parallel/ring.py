@@ -184,7 +184,7 @@ class RingSession:
         self._join(futs)
 
     def _post(self, url: str, msg: Dict[str, Any]) -> Dict[str, Any]:
-        status, body = call_node("post", url, msg, max_n_requests=3, retry_wait=0.5, timeout=self.timeout)
+        status, body = call_node("post", url, msg, max_n_requests=1, timeout=self.timeout)  # ring ops are not idempotent: never re-post
         if status != 200 or not isinstance(body, dict):
             raise RingError(f"node {url} answered {status}: {body}")
         return body
@@ -213,7 +213,7 @@ class RingSession:
         per_node = [local] + self._join(futs)
         self.prefilled = True
         self.rounds_done += rounds
-        bad = [r["rank"] for r in per_node if any(r["status"])]
+        bad = [r["rank"] for r in per_node if (r["status"][0] & 3) or r["status"][1]]  # bit 4 (sampler overflow) is handled exactly
         if bad:
             raise RingError(f"pipeline aborted: hop watchdog / abort flag set on node(s) {bad} "
                             f"(status words {[r['status'] for r in per_node]})")

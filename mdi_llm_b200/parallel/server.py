@@ -452,12 +452,14 @@ class GPTServer:
         assert self.tok is not None
         return [self.tok.decode(s) for s in truncated], self.tok_time
 
-    def open_ring_session(self, n_samples: int, prompt: Any, max_new_tokens: int, mode: Optional[str] = None) -> Any:
+    def open_ring_session(self, n_samples: int, prompt: Any, max_new_tokens: int, mode: Optional[str] = None,
+                          sampling: Optional[SamplingParams] = None) -> Any:
         """Prepared generation over the device ring (prompts encoded, every node reset); drive it with
         ``session.run(rounds)``.  ``launch_starter`` is ``open_ring_session`` + ``run()`` + decode."""
         from .ring import RingSession
 
         assert self.ring is not None and self.model is not None
+        self.ring.pipe.set_sampling(sampling or self.sampling)  # sampling lives on the starter only
         idx = self.encode_prompts(prompt, n_samples)
         S = self.model.max_seq_length
         if any(max_new_tokens + p.numel() > S for p in idx):

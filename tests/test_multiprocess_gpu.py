@@ -59,3 +59,53 @@ def test_train_ddp_nccl_two_gpus(tmp_path):
     losses = [float(l.split("val loss ")[1]) for l in p.stdout.splitlines() if "val loss" in l]
     assert losses[-1] < losses[0], losses
     assert (ck / "lit_model.pth").is_file()
+
+
+def _api_tokens(tmp_path, ck, n_nodes, tag, *starter_flags):
+    """One run through the public CLIs: `launch` spawns `secondary` x (N-1) and `starter`; returns the JSON the
+    starter wrote with --tokens-out."""
+    out = tmp_path / f"tokens_{tag}.json"
+    env = dict(os.environ, MDI_LOGS_DIR=str(tmp_path / "logs"), MDI_IMG_DIR=str(tmp_path / "img"))
+    cmd = [sys.executable, "-m", "mdi_llm_b200.cli.launch", "--ckpt", str(ck), "--n-nodes", str(n_nodes), "--",
+           "--n-samples", str(n_nodes + 1), "--n-tokens", "12", "--prompt", "Hello there", "--greedy", "--sequence-length", "128",
+           "--tokens-out", str(out), *starter_flags]
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
+    assert p.returncode == 0 and out.is_file(), p.stdout[-3000:] + "\n" + p.stderr[-3000:]
+    return json.loads(out.read_text())
+
+
+@pytest.fixture
+def fused_ckpt(tmp_path):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_engine_gpu import _cfg
+    from mdi_llm_b200.utils.checkpoint import write_random_checkpoint
+
+    return write_random_checkpoint(tmp_path / "custom" / "TinyFused", _cfg(n_layer=8), dtype=torch.bfloat16, seed=3)
+
+
+@pytest.mark.parametrize("world,flags", [(2, ()), (2, ("--partition", "half", "--decode-mode", "host")), (4, ("--partition", "half",)),
+                                         (8, ())])
+def test_starter_secondary_clis_device_ring_matches_single_gpu(tmp_path, fused_ckpt, world, flags):
+    """The product path THROUGH THE PUBLIC API: `starter` + `secondary` CLI processes (one per GPU), HTTP control
+    plane, CUDA-IPC handles exchanged at POST /init, fused NVLink hops — token-identical to one GPU, greedy."""
+    if torch.cuda.device_count() < world:
+        pytest.skip("not enough GPUs")
+    one = _api_tokens(tmp_path, fused_ckpt, 1, "n1")
+    many = _api_tokens(tmp_path, fused_ckpt, world, f"n{world}", *flags)
+    assert one["transport"] == "p2p" and many["transport"] == "p2p" and many["n_nodes"] == world
+    n = min(len(one["tokens"]), len(many["tokens"]))
+    assert n >= 2
+    for i in range(n):
+        assert one["tokens"][str(i)] == many["tokens"][str(i)], (i, one["tokens"][str(i)], many["tokens"][str(i)])
+    assert len(many["tok_time"]) == 1 + 12 * (world + 1)  # one timeline point per generated token (device clock or host clock)
+    assert all(b[1] >= a[1] for a, b in zip(many["tok_time"], many["tok_time"][1:]))
+
+
+def test_ring_abort_when_a_node_dies(tmp_path, fused_ckpt):
+    """Freeze one secondary mid-generation: the starter's watchdog trips, the poison flag drains the ring and the
+    API raises instead of hanging."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "_mp_abort_worker.py"), str(fused_ckpt)], capture_output=True,
+                       text=True, timeout=300, cwd=ROOT)
+    assert "ABORT_RESULT ok" in p.stdout, p.stdout[-2000:] + p.stderr[-3000:]

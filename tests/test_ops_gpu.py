@@ -2,6 +2,8 @@
 import math
 import os
 
+import time
+
 import pytest
 import torch
 
@@ -252,7 +254,7 @@ def test_hop_flag_wait_and_signal_same_device(variant):
     inbox = torch.zeros(4, N, device="cuda", dtype=torch.bfloat16)
     flags = torch.zeros(4, dtype=torch.int32, device="cuda")
     done = torch.zeros(1, dtype=torch.int32, device="cuda")
-    status = torch.zeros(1, dtype=torch.int32, device="cuda")
+    status = torch.zeros(4, dtype=torch.int32, device="cuda")
     ctx = _ctx(ops, slot=3, wait=7, signal=7)
     ops.linear_decode(W, x, None, ctx, y_ptr=inbox.data_ptr(), y_slot_stride=N, signal_flag=flags.data_ptr(),
                       done_ctr=done.data_ptr())
@@ -260,14 +262,117 @@ def test_hop_flag_wait_and_signal_same_device(variant):
     ops.linear_decode(W, inbox, y, ctx, x_slot_stride=N, wait_flag=flags.data_ptr(), status=status.data_ptr(),
                       wait_max_cycles=10 ** 9)
     torch.cuda.synchronize()
-    assert flags.tolist() == [0, 0, 0, 7] and done.item() == 0 and status.item() == 0
+    assert flags.tolist() == [0, 0, 0, 7] and done.item() == 0 and status[:2].tolist() == [0, 0]
     assert torch.equal(y, x)
     # watchdog: waiting for a value that never comes sets the status word instead of hanging
     ctx2 = _ctx(ops, slot=0, wait=1)
     ops.linear_decode(W, inbox, y, ctx2, x_slot_stride=N, wait_flag=flags.data_ptr(), status=status.data_ptr(),
                       wait_max_cycles=2_000_000)
     torch.cuda.synchronize()
-    assert status.item() == 1
+    assert status[:2].tolist() == [1, 1]  # watchdog bit + aborted
+
+
+def test_poison_flag_aborts_and_propagates():
+    """Abort protocol (common.cuh): a poisoned incoming flag satisfies the wait at once and marks the stage
+    aborted; an aborted stage never waits again and publishes the poison instead of its round number."""
+    ops = _ops()
+    N = K = 256
+    W = torch.eye(N, device="cuda").bfloat16()
+    inbox = torch.randn(4, N, device="cuda").bfloat16()
+    flags = torch.zeros(4, dtype=torch.int32, device="cuda")
+    nxt_flags = torch.zeros(4, dtype=torch.int32, device="cuda")
+    nxt_in = torch.zeros(4, N, device="cuda", dtype=torch.bfloat16)
+    done = torch.zeros(1, dtype=torch.int32, device="cuda")
+    status = torch.zeros(4, dtype=torch.int32, device="cuda")
+    flags[2] = ops.POISON
+    ctx = _ctx(ops, slot=2, wait=5, signal=5)
+    t0 = time.time()
+    ops.linear_decode(W, inbox, None, ctx, x_slot_stride=N, wait_flag=flags.data_ptr(), status=status.data_ptr(),
+                      wait_max_cycles=10 ** 11, y_ptr=nxt_in.data_ptr(), y_slot_stride=N, signal_flag=nxt_flags.data_ptr(),
+                      done_ctr=done.data_ptr())
+    # now aborted: a wait that could never be satisfied (slot 0, flag 0 < 9) returns immediately, no watchdog bit
+    ops.linear_decode(W, inbox, None, _ctx(ops, slot=0, wait=9, signal=9), x_slot_stride=N, wait_flag=flags.data_ptr(),
+                      status=status.data_ptr(), wait_max_cycles=10 ** 11, y_ptr=nxt_in.data_ptr(), y_slot_stride=N,
+                      signal_flag=nxt_flags.data_ptr(), done_ctr=done.data_ptr())
+    torch.cuda.synchronize()
+    assert time.time() - t0 < 5.0
+    assert status[:2].tolist() == [0, 1]
+    assert nxt_flags.tolist() == [ops.POISON, 0, ops.POISON, 0]
+
+
+def _ref_support_probs(logits, top_k, top_p, temperature):
+    from mdi_llm_b200.models.gpt import sample_top_p
+
+    row = logits.float().clone()
+    if top_k is not None and top_k < row.numel():
+        vals, idx = torch.topk(row, top_k)
+        row = torch.full_like(row, float("-inf")).scatter_(-1, idx, vals)
+    row = row / temperature
+    if top_p < 1.0:
+        row = sample_top_p(row, top_p)
+    return torch.softmax(row, -1)
+
+
+@pytest.mark.parametrize("top_k,top_p", [(None, 0.6), (3000, 1.0), (50, 0.9), (None, 1.0)])
+def test_device_sampler_top_p_and_large_k(top_k, top_p):
+    """Whole-vocabulary sampler (nucleus by probability-mass radix selection, any k): the support and the
+    frequencies of many draws follow the eager `sample()` distribution (reference model.py:42-90)."""
+    ops = _ops()
+    torch.manual_seed(11)
+    V = 6000
+    logits = (torch.randn(V, device="cuda") * 2.0).float()
+    logits[[5, 77, 4000, 5999]] += torch.tensor([9.0, 8.5, 8.0, 7.0], device="cuda")
+    temp = 0.9
+    probs = _ref_support_probs(logits, top_k, top_p, temp).cpu()
+    n = 600
+    tokens = torch.zeros(1, n + 1, dtype=torch.int32, device="cuda")
+    scratch = ops.sample_scratch("cuda")
+    status = torch.zeros(4, dtype=torch.int32, device="cuda")
+    half = n // 2
+    for pos in range(half):  # stand-alone kernel
+        ops.sample(logits, tokens, _ctx(ops, slot=0, pos=pos), vocab=V, top_k=top_k, temperature=temp, greedy=False, seed=5,
+                   tok_slot_stride=n + 1, top_p=top_p)
+    W = torch.eye(8, device="cuda").bfloat16()  # statistics as the lm_head epilogue would leave them are not needed for this path
+    for pos in range(half, n):  # fast-sampler entry point routes to the same whole-vocabulary code
+        ops.sample_fast(logits, scratch, tokens, _ctx(ops, slot=0, pos=pos), vocab=V, top_k=top_k, temperature=temp, greedy=False,
+                        seed=5, tok_slot_stride=n + 1, top_p=top_p, status=status)
+    torch.cuda.synchronize()
+    draws = tokens[0, :n].cpu().long()
+    support = set(torch.nonzero(probs > 0).view(-1).tolist())
+    assert set(draws.tolist()) <= support, "sampled a token outside the top-k / top-p support"
+    freq = torch.bincount(draws, minlength=V).float() / n
+    top = torch.topk(probs, 4).indices
+    assert (freq[top] - probs[top]).abs().max().item() < 0.07, (freq[top], probs[top])
+    # the two entry points draw from the same stream: same (seed, slot, pos) -> same token
+    ops.sample(logits, tokens, _ctx(ops, slot=0, pos=half), vocab=V, top_k=top_k, temperature=temp, greedy=False, seed=5,
+               tok_slot_stride=n + 1, top_p=top_p)
+    torch.cuda.synchronize()
+    assert tokens[0, half].item() == int(draws[half])
+
+
+def test_fast_sampler_candidate_overflow_is_exact_not_silent():
+    """A flat logit row puts the whole vocabulary into the threshold bin: the candidate list overflows, status bit 4
+    is raised and the draw still comes from the exact distribution (all ties kept -> uniform over the row)."""
+    ops = _ops()
+    ops.set_linear_variant(0)
+    V, K = 20000, 256
+    W = torch.zeros(V, K, device="cuda").bfloat16()
+    nw = torch.ones(K, device="cuda", dtype=torch.bfloat16)
+    scratch = ops.sample_scratch("cuda")
+    logits = torch.zeros(V, device="cuda", dtype=torch.float32)
+    status = torch.zeros(4, dtype=torch.int32, device="cuda")
+    tok = torch.zeros(1, 64, dtype=torch.int32, device="cuda")
+    x = torch.randn(K, device="cuda").bfloat16()
+    for step in range(40):
+        ctx = _ctx(ops, slot=0, pos=step)
+        ops.linear_decode(W, x, logits, ctx, norm_w=nw, stats=scratch)
+        ops.sample_fast(logits, scratch, tok, ctx, vocab=V, top_k=200, temperature=0.8, greedy=False, seed=3, tok_slot_stride=64,
+                        status=status)
+    torch.cuda.synchronize()
+    assert status[0].item() & 4
+    got = tok[0, :40].tolist()
+    assert all(0 <= t < V for t in got) and len(set(got)) > 30  # spread over the row, not stuck on one id
+    assert scratch[: 4096 + 4].abs().sum() == 0
 
 
 def test_cuda_graph_capture_and_replay():

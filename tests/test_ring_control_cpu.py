@@ -1,0 +1,196 @@
+"""CPU tests of the pieces around the device ring that do not need a GPU: the restricted unpickler, the
+control plane's token / loopback policy and response bodies, the ring protocol (with a recording stand-in for
+the CUDA backend), stage-shape inference of half-layer chunks, partition-independent random weights, and the
+one-box launcher."""
+import json
+import os
+import pickle
+import subprocess
+import sys
+import threading
+
+import pytest
+import torch
+
+from conftest import free_ports
+from mdi_llm_b200.models.config import Config
+from mdi_llm_b200.parallel.control import ControlServer, HTTPError, call_node, request_to_node
+from mdi_llm_b200.utils.safe_pickle import UnsafePayload, safe_loads
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+class _Evil:
+    def __reduce__(self):
+        return (os.system, ("echo pwned > /tmp/mdi_pwned",))
+
+
+def test_safe_loads_accepts_messages_and_rejects_code():
+    msg = {"sample_index": 3, "data": torch.randn(1, 2, 8).to(torch.bfloat16), "stop": False,
+           "params": {"w": torch.nn.Parameter(torch.ones(3))}, "cfg": {"a": [1, 2.5, None, "x", (1, 2)]}}
+    back = safe_loads(pickle.dumps(msg))
+    assert torch.equal(back["data"], msg["data"]) and back["cfg"] == msg["cfg"] and back["sample_index"] == 3
+    assert torch.equal(back["params"]["w"], msg["params"]["w"])
+    with pytest.raises(UnsafePayload):
+        safe_loads(pickle.dumps({"x": _Evil()}))
+    assert not os.path.exists("/tmp/mdi_pwned")
+
+
+class _App:
+    def __init__(self):
+        self.n = 0
+
+    def POST(self, path, body):
+        self.n += 1
+        if path == ("init",):
+            return {"handles": {"hidden": b"\x01" * 64, "flag_off": 256}, "echo": safe_loads(body)["role"]}
+        if path == ("boom",):
+            raise HTTPError(500, "failed on purpose")
+        raise HTTPError(404, "Not found")
+
+
+def test_control_plane_token_bodies_and_no_blind_retries(monkeypatch):
+    (port,) = free_ports(1)
+    app = _App()
+    srv = ControlServer(app, "127.0.0.1", port, token="s3cret")
+    srv.start()
+    try:
+        url = f"http://127.0.0.1:{port}"
+        status, body = call_node("post", url + "/init", {"role": "secondary:0"}, max_n_requests=1, token="s3cret")
+        assert status == 200 and body["echo"] == "secondary:0" and body["handles"]["hidden"] == b"\x01" * 64
+        status, body = call_node("post", url + "/init", {"role": "x"}, max_n_requests=1)  # no token
+        assert status == 401 and app.n == 1
+        status, body = call_node("post", url + "/boom", {}, max_n_requests=50, retry_wait=5.0, token="s3cret")
+        assert status == 500 and "on purpose" in body and app.n == 2  # a node that answered is not asked again
+        monkeypatch.setenv("MDI_CLUSTER_TOKEN", "s3cret")
+        assert request_to_node("post", url + "/init", {"role": "y"}, max_n_requests=1) == 1
+    finally:
+        srv.stop()
+    monkeypatch.delenv("MDI_CLUSTER_TOKEN")
+    with pytest.raises(PermissionError):
+        ControlServer(app, "10.1.2.3", port)  # non-loopback bind without a shared secret is refused up front
+
+
+def test_stage_shape_and_partition_independent_random_weights(tiny_llama_cfg):
+    from mdi_llm_b200.models.partition import (split_parameters_half, stage_shape_from_state_dict, stage_specs)
+    from mdi_llm_b200.models.stage import build_stage
+    from mdi_llm_b200.utils.checkpoint import random_init_stage_, random_state_dict
+
+    cfg = tiny_llama_cfg
+    sd = random_state_dict(cfg, dtype=torch.float32)
+    chunks = split_parameters_half(dict(sd), [3, 4, 3])
+    shapes = [stage_shape_from_state_dict(c) for c in [chunks["starter"]] + chunks["secondary"]]
+    assert shapes == [{"n_blocks": 2, "first_mlp_only": False, "last_attn_only": True},
+                      {"n_blocks": 3, "first_mlp_only": True, "last_attn_only": True},
+                      {"n_blocks": 2, "first_mlp_only": True, "last_attn_only": False}]
+    # the same seed gives the same model whatever the partition
+    full = build_stage(cfg, "starter", cfg.n_layer, meta=True)
+    random_init_stage_(full, "cpu", torch.float32, seed=11)
+    ref = full.state_dict()
+    for policy in ("auto", "half"):
+        specs = stage_specs(3, cfg, policy)
+        assert sum(s["units"] for s in specs) == 2 * cfg.n_layer
+        for i, sp in enumerate(specs):
+            st = build_stage(cfg, "starter" if i == 0 else f"secondary:{i - 1}", sp["n_blocks"], meta=True,
+                             first_mlp_only=sp["first_mlp_only"], last_attn_only=sp["last_attn_only"])
+            random_init_stage_(st, "cpu", torch.float32, seed=11, layer_offset=sp["layer_offset"])
+            for k, v in st.state_dict().items():
+                if k.startswith("transformer.h."):
+                    _, _, li, tail = k.split(".", 3)
+                    k = f"transformer.h.{int(li) + sp['layer_offset']}.{tail}"
+                assert torch.equal(v, ref[k]), (policy, i, k)
+
+
+class _FakeBackend:
+    """Stands in for RingBackend on a machine without CUDA: records the protocol."""
+
+    def __init__(self, rank, log):
+        self.rank, self.log, self.n_samples, self.world = rank, log, 2, 3
+        self.prepared = False
+
+    def handle(self, msg):
+        from mdi_llm_b200.parallel.ring import RingBackend
+
+        return RingBackend.handle(self, msg)
+
+    def connect(self, nxt):
+        self.log.append((self.rank, "connect", nxt["rank"]))
+
+    def prepare(self, lens, max_new, prompts=None):
+        self.prepared = True
+        self.log.append((self.rank, "prepare", tuple(lens), max_new, prompts is not None))
+
+    def run(self, prefill, rounds, start_at=None, mode="device", on_token=None):
+        assert self.prepared
+        self.log.append((self.rank, "run", prefill, rounds, mode if self.rank == 0 else "device"))
+        return {"rank": self.rank, "prefill_ms": 1.0 * prefill, "decode_ms": 0.5 * rounds + self.rank, "graph_launches": rounds * 2,
+                "kernels_per_graph": 7, "wait_cycles": 0, "status": [0, 0], "h2d": 0, "d2h": 0, "round": rounds}
+
+    def abort(self):
+        self.log.append((self.rank, "abort"))
+
+    def tokens(self):
+        return {0: torch.zeros(1, 4, dtype=torch.int64)}
+
+
+class _Node:
+    def __init__(self, backend):
+        self.ring = backend
+
+    def POST(self, path, body):
+        assert path == ("ring",)
+        return self.ring.handle(safe_loads(body))
+
+
+def test_ring_session_protocol_over_http():
+    """prepare everywhere before anything runs; prefill only in the first segment; per-node device times come
+    back; a node reporting an abort turns into RingError on the starter."""
+    from mdi_llm_b200.parallel.ring import RingError, RingSession
+
+    log = []
+    ports = free_ports(2)
+    nodes = [{"addr": "127.0.0.1", "communication": {"port": p}} for p in ports]
+    backends = [_FakeBackend(i + 1, log) for i in range(2)]
+    servers = [ControlServer(_Node(b), "127.0.0.1", p) for b, p in zip(backends, ports)]
+    for s in servers:
+        s.start()
+    try:
+        local = _FakeBackend(0, log)
+        prompts = [torch.tensor([1, 2, 3]), torch.tensor([4, 5])]
+        sess = RingSession(local, nodes, prompts, 6, mode="host")
+        assert sorted(e for e in log if e[1] == "prepare") == [(0, "prepare", (3, 2), 6, True), (1, "prepare", (3, 2), 6, False),
+                                                               (2, "prepare", (3, 2), 6, False)]
+        r1 = sess.run(2)
+        r2 = sess.run()
+        assert r1["tokens"] == 4 and r1["decode_ms"] == 3.0 and r1["prefill_ms"] == 1.0 and len(r1["per_node"]) == 3
+        assert r2["rounds"] == 4 and r2["prefill_ms"] == 0.0
+        runs = [e for e in log if e[1] == "run"]
+        assert sorted(runs[:3]) == [(0, "run", True, 2, "host"), (1, "run", True, 2, "device"), (2, "run", True, 2, "device")]
+        assert all(e[2] is False and e[3] == 4 for e in runs[3:])
+        backends[1].run = lambda *a, **k: {"rank": 2, "prefill_ms": 0.0, "decode_ms": 0.0, "graph_launches": 0, "kernels_per_graph": 0,
+                                           "wait_cycles": 0, "status": [1, 1], "h2d": 0, "d2h": 0, "round": 0}
+        sess.max_new = 99
+        with pytest.raises(RingError, match="node"):
+            sess.run(1)
+        sess.abort()
+        assert {e[0] for e in log if e[1] == "abort"} == {0, 1, 2}
+        sess.close()
+    finally:
+        for s in servers:
+            s.stop()
+
+
+def test_one_box_launcher_cpu(tmp_path, tiny_llama_cfg):
+    """`python -m mdi_llm_b200.cli.launch`: 3 node processes on loopback (CPU, socket transport), two runs,
+    run statistics appended, no stragglers (parity: old/nanoGPT/test_mdi_local.sh)."""
+    from mdi_llm_b200.utils.checkpoint import write_random_checkpoint
+
+    ck = write_random_checkpoint(tmp_path / "custom" / "NanoLlama", tiny_llama_cfg, dtype=torch.float32)
+    stats = tmp_path / "runs.csv"
+    env = dict(os.environ, MDI_LOGS_DIR=str(tmp_path / "logs"), MDI_IMG_DIR=str(tmp_path / "img"))
+    cmd = [sys.executable, "-m", "mdi_llm_b200.cli.launch", "--ckpt", str(ck), "--n-nodes", "3", "--device", "cpu", "--dtype", "float32",
+           "--runs", "2", "--", "--n-samples", "3", "--n-tokens", "4", "--prompt", "Hi", "--greedy", "--time-run", str(stats)]
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT, env=env)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-3000:]
+    assert p.stdout.count("Sample 3:") == 2 and "=== run 2/2" in p.stdout
+    assert len(stats.read_text().strip().splitlines()) == 3  # header + one row per run
