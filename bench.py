@@ -424,7 +424,7 @@ def run_job(args: argparse.Namespace, job: int = 0, light: bool = False) -> Dict
         ms_total = timed["decode_ms"]
         tokens = args.steps * n_samples
         value = tokens / (ms_total / 1e3)
-        launches = sum(r["graph_launches"] * r["kernels_per_graph"] for r in timed["per_node"])
+        launches = sum(r["kernel_launches"] for r in timed["per_node"])
         sm_khz = 1_965_000
         waits = [r["wait_cycles"] / (sm_khz / 1e3) / max(1, tokens) for r in sorted(timed["per_node"], key=lambda r: r["rank"])]
 

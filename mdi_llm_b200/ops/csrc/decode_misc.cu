@@ -647,6 +647,10 @@ __global__ void __launch_bounds__(SMP_THREADS) sample_final_kernel(const SampleF
 // (round 0 is the prefill, handled outside the graph; decode rounds start at first_round.)
 __global__ void advance_step_kernel(int* __restrict__ ctx, int* __restrict__ state, int* __restrict__ pos_arr,
                                     int n_slots, int is_starter) {
+  // Release the next kernel at once: it becomes resident and prefetches its weights while the previous step's last
+  // kernel is still draining.  Safe: its griddepcontrol.wait returns only after THIS grid has completed, and this
+  // grid writes ctx only after the previous step has completed (the wait below) — the chain stays transitive.
+  pdl_launch_dependents();
   pdl_wait_prior();
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     const int t = state[0];
@@ -660,7 +664,6 @@ __global__ void advance_step_kernel(int* __restrict__ ctx, int* __restrict__ sta
     pos_arr[slot] += 1;
     state[0] = t + 1;
   }
-  pdl_launch_dependents();
 }
 
 __global__ void wait_flag_kernel(const int* flag, const int* ctx, int* status, long long max_cycles) {

@@ -86,7 +86,12 @@ class DevicePipeline:
         self.prompt_lens: List[int] = []
         self.round = 1
         self.max_new = 0
-        self.n_graph_launches = 0
+        self.n_graph_launches = 0   # decode steps enqueued (one CUDA-graph replay covers `steps_per_graph` of them)
+        self.n_kernel_launches = 0  # kernels inside those replays
+        # device mode: consecutive steps captured in ONE graph keep their programmatic (PDL) edges, so the first
+        # kernel of step t+1 is resident and prefetching its weights while the last kernel of step t drains
+        # (a graph boundary is a full stop).  Default: one round per graph, at least 8 steps.
+        self.steps_per_graph = int(os.environ.get("MDI_STEPS_PER_GRAPH", "0")) or max(n_samples, 8)
 
     # ---- ring wiring ------------------------------------------------------------------------------
     def export_handles(self) -> Dict[str, Any]:
@@ -275,7 +280,9 @@ class DevicePipeline:
                     if final and not self.is_starter:
                         continue
                     dist.recv(st.hidden_in[slot], src=prev, group=g_in)  # stream-ordered, host does not block
-                    self._g_nccl(final).launch()
+                    g = self._g_nccl(final)
+                    g.launch()
+                    self.n_kernel_launches += g.n_nodes
                     launched += 1
                     if not final:
                         dist.send(st.out_local[slot], dst=nxt, group=g_out)
@@ -284,19 +291,21 @@ class DevicePipeline:
         return launched
 
     # graph builders ---------------------------------------------------------------------------------
-    def _g_full(self, dev_ctx: bool) -> ops.CudaGraph:
+    def _g_full(self, dev_ctx: bool, k: int = 1) -> ops.CudaGraph:
+        """``k`` consecutive full steps (device mode; host-fed steps are one per graph)."""
         st = self.stage
 
         def build() -> None:
-            if dev_ctx:
-                ops.advance_step(st.ctx, st.state, st.pos_arr, self.n, self.is_starter, use_pdl=False)
-            if self.is_starter:
-                st.enqueue_head(wait=True)
-                st.enqueue_sample()
-                st.enqueue_embed(from_tokens=True)
-            st.enqueue_blocks(self.next_hop, wait_input=True, dep_flags=self.dep_flags)
+            for j in range(k):
+                if dev_ctx:
+                    ops.advance_step(st.ctx, st.state, st.pos_arr, self.n, self.is_starter, use_pdl=self.stage.use_pdl and j > 0)
+                if self.is_starter:
+                    st.enqueue_head(wait=True)
+                    st.enqueue_sample()
+                    st.enqueue_embed(from_tokens=True)
+                st.enqueue_blocks(self.next_hop, wait_input=True, dep_flags=self.dep_flags)
 
-        return st.graph(("full", dev_ctx, self.next_hop.hidden_ptr, self.dep_flags), build, warm=False)
+        return st.graph(("full", dev_ctx, self.next_hop.hidden_ptr, self.dep_flags, k), build, warm=False)
 
     def _g_head(self, dev_ctx: bool) -> ops.CudaGraph:
         st = self.stage
@@ -311,23 +320,30 @@ class DevicePipeline:
 
     def decode_rounds(self, n_rounds: int) -> int:
         """Enqueue ``n_rounds`` decode rounds (every sample advances one token per round) in
-        device-driven mode.  Returns the number of graph launches issued."""
+        device-driven mode.  Returns the number of steps issued."""
         st = self.stage
         if self.hop == "nccl":
             return self._decode_rounds_nccl(n_rounds)
         launched = 0
         with torch.cuda.device(self.device), _nvtx(f"mdi.decode[{self.rank}] x{n_rounds}"):
-            for _ in range(n_rounds):
-                r = self.round
-                if r > self.max_new:
-                    break
-                final = r == self.max_new
-                if final:
-                    if self.is_starter:
-                        self._g_head(True).launch(self.n)
-                        launched += self.n
-                else:
-                    self._g_full(True).launch(self.n)
+            full_rounds = max(0, min(n_rounds, self.max_new - self.round))  # rounds before the final (head-only) one
+            steps = full_rounds * self.n
+            k = max(1, min(self.steps_per_graph, steps)) if steps else 1
+            if steps:
+                g = self._g_full(True, k)
+                g.launch(steps // k)
+                self.n_kernel_launches += g.n_nodes * (steps // k)
+                if steps % k:
+                    g1 = self._g_full(True, 1)
+                    g1.launch(steps % k)
+                    self.n_kernel_launches += g1.n_nodes * (steps % k)
+                launched += steps
+                self.round += full_rounds
+            if n_rounds > full_rounds and self.round == self.max_new:
+                if self.is_starter:
+                    g = self._g_head(True)
+                    g.launch(self.n)
+                    self.n_kernel_launches += g.n_nodes * self.n
                     launched += self.n
                 self.round += 1
         st._step_seq += launched  # advance_step numbered these steps on the device
@@ -352,7 +368,9 @@ class DevicePipeline:
                     h2d += ops.CTX_INTS * 4
                     if final and not self.is_starter:
                         continue
-                    (self._g_head(False) if final else self._g_full(False)).launch()
+                    g = self._g_head(False) if final else self._g_full(False)
+                    g.launch()
+                    self.n_kernel_launches += g.n_nodes
                     launched += 1
                     if not self.is_starter and launched % 2048 == 0:
                         torch.cuda.current_stream().synchronize()  # keep the pinned ctx ring ahead of the GPU

@@ -107,7 +107,7 @@ class RingBackend:
         p = self.pipe
         with self.lock, torch.cuda.device(self.device):
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
-            launches0, wait0 = p.n_graph_launches, p.stage.wait_cycles()
+            launches0, kern0, wait0 = p.n_graph_launches, p.n_kernel_launches, p.stage.wait_cycles()
             h2d = d2h = 0
             _spin_until(start_at)
             ev[0].record()
@@ -122,9 +122,8 @@ class RingBackend:
             ev[2].record()
             torch.cuda.synchronize(self.device)
             status = p.stage.status[:2].tolist()
-            nodes = next(iter(p.stage._graphs.values())).n_nodes if p.stage._graphs else 0
             return {"rank": self.rank, "prefill_ms": ev[0].elapsed_time(ev[1]), "decode_ms": ev[1].elapsed_time(ev[2]),
-                    "graph_launches": p.n_graph_launches - launches0, "kernels_per_graph": nodes,
+                    "steps": p.n_graph_launches - launches0, "kernel_launches": p.n_kernel_launches - kern0,
                     "wait_cycles": p.stage.wait_cycles() - wait0, "status": status, "h2d": h2d, "d2h": d2h,
                     "round": p.round}
 

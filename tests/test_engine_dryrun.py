@@ -191,7 +191,9 @@ def test_device_pipeline_orchestration_single_stage(mode):
     # rounds 1..4 run the full step for both samples, the final round only the head (ln_f + lm_head + sample)
     full = [g for g in _FakeGraph.instances if "qkv_decode" in g.kernels]
     head = [g for g in _FakeGraph.instances if "qkv_decode" not in g.kernels and "sample_fast" in g.kernels]
-    assert sum(g.launched for g in full) == 4 * 2 and sum(g.launched for g in head) == 2
+    steps = lambda g: g.kernels.count("embed")  # a device-mode graph holds a whole round (n_samples steps) -> PDL edges across steps
+    assert sum(g.launched * steps(g) for g in full) == 4 * 2 and sum(g.launched for g in head) == 2
+    assert all((steps(g) > 1) == (mode == "device") for g in full)  # device mode: several steps per graph; host-fed: one
     assert pipe.n_graph_launches == 10
     dev_ctx = mode == "device"
     assert all(("advance_step" in g.kernels) == dev_ctx for g in full + head)
@@ -235,5 +237,6 @@ def test_device_pipeline_orchestration_two_stages():
         assert all(c[1].get("out_ptr") is None for c in calls if c[0] == "gemm")
         p1.decode_rounds(4)  # rounds 1..3 forward; the final round has nothing to do on a secondary
         g = [x for x in _FakeGraph.instances if "qkv_decode" in x.kernels]
-        assert sum(x.launched for x in g) == 6 and not any("sample_fast" in x.kernels for x in _FakeGraph.instances)
+        assert sum(x.launched * x.kernels.count("advance_step") for x in g) == 6 \
+            and not any("sample_fast" in x.kernels for x in _FakeGraph.instances)
         assert g[0].kernels[0] == "advance_step" and g[0].kernels[1] == "qkv_decode"

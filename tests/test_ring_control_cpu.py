@@ -123,8 +123,8 @@ class _FakeBackend:
     def run(self, prefill, rounds, start_at=None, mode="device", on_token=None):
         assert self.prepared
         self.log.append((self.rank, "run", prefill, rounds, mode if self.rank == 0 else "device"))
-        return {"rank": self.rank, "prefill_ms": 1.0 * prefill, "decode_ms": 0.5 * rounds + self.rank, "graph_launches": rounds * 2,
-                "kernels_per_graph": 7, "wait_cycles": 0, "status": [0, 0], "h2d": 0, "d2h": 0, "round": rounds}
+        return {"rank": self.rank, "prefill_ms": 1.0 * prefill, "decode_ms": 0.5 * rounds + self.rank, "steps": rounds * 2,
+                "kernel_launches": rounds * 14, "wait_cycles": 0, "status": [0, 0], "h2d": 0, "d2h": 0, "round": rounds}
 
     def abort(self):
         self.log.append((self.rank, "abort"))
@@ -167,7 +167,7 @@ def test_ring_session_protocol_over_http():
         runs = [e for e in log if e[1] == "run"]
         assert sorted(runs[:3]) == [(0, "run", True, 2, "host"), (1, "run", True, 2, "device"), (2, "run", True, 2, "device")]
         assert all(e[2] is False and e[3] == 4 for e in runs[3:])
-        backends[1].run = lambda *a, **k: {"rank": 2, "prefill_ms": 0.0, "decode_ms": 0.0, "graph_launches": 0, "kernels_per_graph": 0,
+        backends[1].run = lambda *a, **k: {"rank": 2, "prefill_ms": 0.0, "decode_ms": 0.0, "steps": 0, "kernel_launches": 0,
                                            "wait_cycles": 0, "status": [1, 1], "h2d": 0, "d2h": 0, "round": 0}
         sess.max_new = 99
         with pytest.raises(RingError, match="node"):
