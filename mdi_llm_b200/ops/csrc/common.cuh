@@ -147,6 +147,38 @@ __device__ __forceinline__ void hop_signal(const HopSignal& s, const int* ctx) {
   }
 }
 
+// Decode hop, cheap form: every CTA has written its part of the output row to LOCAL memory; tickets are taken
+// at gpu scope (fence + atomic, the classic "last block" pattern) and only the last CTA touches the peer: it
+// copies the finished row over NVLink with 16-byte stores, fences once at system scope and releases the flag.
+// (hop_signal above makes EVERY CTA fence at system scope after its few remote bytes: measured +8-10 us on the
+// tail of the stage's last kernel, because a MEMBAR.SYS waits behind the SM's in-flight weight stream.)
+__device__ __forceinline__ void hop_signal_copy(const HopSignal& s, const int* ctx, const __nv_bfloat16* local_row,
+                                                __nv_bfloat16* remote_row, int n_elems) {
+  if (s.flag == nullptr) return;
+  __shared__ int hop_is_last;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned int total = gridDim.x * gridDim.y * gridDim.z;
+    const unsigned int prev = atomicAdd(s.done_ctr, 1u);
+    hop_is_last = (prev == total - 1);
+    if (hop_is_last) *s.done_ctr = 0;
+  }
+  __syncthreads();
+  if (!hop_is_last) return;
+  __threadfence();
+  const uint4* src = reinterpret_cast<const uint4*>(local_row);
+  uint4* dst = reinterpret_cast<uint4*>(remote_row);
+  for (int v = threadIdx.x; v < n_elems / 8; v += blockDim.x) dst[v] = __ldcg(src + v);
+  for (int i = (n_elems / 8) * 8 + threadIdx.x; i < n_elems; i += blockDim.x) remote_row[i] = local_row[i];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    const bool aborted = s.status != nullptr && ld_volatile(s.status + 1) != 0;
+    st_release_sys(s.flag + ctx[MDI_CTX_SLOT], aborted ? MDI_POISON : ctx[MDI_CTX_SIGNAL]);
+  }
+}
+
 // ---- intra-stage dependencies by flag instead of grid completion -----------------------------------------
 // A PDL-launched consumer is already resident while its producer runs; `griddepcontrol.wait` releases it
 // only after the producer grid has completed AND flushed (~1.4 us after the last CTA's exit, measured).

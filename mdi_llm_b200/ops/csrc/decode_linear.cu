@@ -216,7 +216,29 @@ struct StreamArgs {
   DepSignal dep_signal;  // ... and the flag this kernel publishes for the next one
   int l2_pf_chunks;  // bulk kernels: chunk pairs per warp prefetched into L2 beyond the smem ring (0 = off)
   int ctx_early;     // ctx was written >= 2 launches ago: slot/pos may be read before the PDL wait
+  // hop by row copy: y is a LOCAL row buffer; the last CTA copies it to hop_row (+ slot * hop_slot_stride) in
+  // the next stage's memory and releases the flag (hop_signal_copy); null = epilogues store to y directly
+  bf16* hop_row;
+  long long hop_slot_stride;
+  // look-ahead for the NEXT kernel: while this kernel waits for its input (o_proj behind the latency-bound
+  // attention: HBM idle) its warps ask the TMA engine to pull `pf_bytes` of each of these regions into L2
+  const unsigned char* pf_a;
+  const unsigned char* pf_b;
+  unsigned long long pf_bytes;
 };
+
+// bulk L2 prefetch of [base, base + bytes) spread over all warps of the grid (lane 0 of each warp issues)
+__device__ __forceinline__ void prefetch_region(const unsigned char* base, unsigned long long bytes, int gw, int n_gw) {
+  if (base == nullptr || bytes == 0) return;
+  const unsigned long long per = ((bytes / (unsigned long long)n_gw) + 127ull) & ~127ull;
+  const unsigned long long lo = (unsigned long long)gw * per;
+  if (lo >= bytes) return;
+  const unsigned long long hi = lo + per < bytes ? lo + per : bytes;
+  for (unsigned long long o = lo; o < hi; o += 4096ull) {
+    const unsigned long long n = hi - o < 4096ull ? hi - o : 4096ull;
+    bulk_prefetch_l2(base + o, (uint32_t)(n & ~15ull));
+  }
+}
 
 __device__ __forceinline__ uint32_t float_key(float f) {  // monotone: larger float -> larger key
   const uint32_t u = __float_as_uint(f);
@@ -375,7 +397,9 @@ __global__ void __launch_bounds__(LIN_THREADS, 3) stream_ldg_kernel(const Stream
     if (lane == 0) item_epilogue<MODE>(a, it, da, db, slot, pos, res, hist_s, best);
   }
   stats_flush(a, hist_s, best);
-  hop_signal(a.signal, a.ctx);
+  if (a.hop_row) hop_signal_copy(a.signal, a.ctx, reinterpret_cast<const bf16*>(a.y) + (size_t)slot * a.y_slot_stride,
+                                 a.hop_row + (size_t)slot * a.hop_slot_stride, a.N);
+  else hop_signal(a.signal, a.ctx);
   dep_signal(a.dep_signal, a.ctx);
   trace_mark(a.trace, 3, true);
   trace_mark(a.trace, 4, false);
@@ -436,6 +460,8 @@ __global__ void __launch_bounds__(LIN_THREADS, STAGES == 2 ? 3 : (STAGES == 3 ? 
       bulk_prefetch_l2(wa + k0, bytes);
       bulk_prefetch_l2(wb + k0, bytes);
     }
+    prefetch_region(a.pf_a, a.pf_bytes, gw, n_gw);
+    prefetch_region(a.pf_b, a.pf_bytes, gw, n_gw);
   }
   unsigned int* hist_s = stats_begin(a, reinterpret_cast<unsigned char*>(bars - warp * STAGES + LIN_WARPS * STAGES));
   unsigned long long best = 0ull;
@@ -482,7 +508,9 @@ __global__ void __launch_bounds__(LIN_THREADS, STAGES == 2 ? 3 : (STAGES == 3 ? 
     if (lane == 0 && f + STAGES < total) issue(f + STAGES);  // ... so it can be refilled right away
   }
   stats_flush(a, hist_s, best);
-  hop_signal(a.signal, a.ctx);
+  if (a.hop_row) hop_signal_copy(a.signal, a.ctx, reinterpret_cast<const bf16*>(a.y) + (size_t)slot * a.y_slot_stride,
+                                 a.hop_row + (size_t)slot * a.hop_slot_stride, a.N);
+  else hop_signal(a.signal, a.ctx);
   dep_signal(a.dep_signal, a.ctx);
   trace_mark(a.trace, 3, true);
   trace_mark(a.trace, 4, false);
@@ -610,7 +638,9 @@ __global__ void __launch_bounds__(LIN_THREADS, 3) stream_ldg_fp8_kernel(const St
     if (lane == 0) item_epilogue<MODE>(a, it, da, db, slot, pos, res, hist_s, best);
   }
   stats_flush(a, hist_s, best);
-  hop_signal(a.signal, a.ctx);
+  if (a.hop_row) hop_signal_copy(a.signal, a.ctx, reinterpret_cast<const bf16*>(a.y) + (size_t)slot * a.y_slot_stride,
+                                 a.hop_row + (size_t)slot * a.hop_slot_stride, a.N);
+  else hop_signal(a.signal, a.ctx);
   dep_signal(a.dep_signal, a.ctx);
   trace_mark(a.trace, 3, true);
   trace_mark(a.trace, 4, false);
@@ -716,7 +746,9 @@ __global__ void __launch_bounds__(LIN_THREADS, 3) stream_bulk_fp8_kernel(const S
     if (lane == 0 && f + STAGES < total) issue(f + STAGES);
   }
   stats_flush(a, hist_s, best);
-  hop_signal(a.signal, a.ctx);
+  if (a.hop_row) hop_signal_copy(a.signal, a.ctx, reinterpret_cast<const bf16*>(a.y) + (size_t)slot * a.y_slot_stride,
+                                 a.hop_row + (size_t)slot * a.hop_slot_stride, a.N);
+  else hop_signal(a.signal, a.ctx);
   dep_signal(a.dep_signal, a.ctx);
   trace_mark(a.trace, 3, true);
   trace_mark(a.trace, 4, false);
@@ -788,7 +820,7 @@ static int launch_stream(const StreamArgs& a, int variant, int ctas_per_sm, int 
   const int per_sm = variant == 1 ? 1 : max(1, min(ctas_per_sm, (int)((227 * 1024) / (smem + 1024))));
   const int grid = grid_override > 0 ? min(grid_override, max_useful) : max(1, min(sms * per_sm, max_useful));
   StreamArgs b = a;
-  if (g_l2_prefetch_mb > 0) {  // bytes of L2 look-ahead per launch, spread evenly over the warps
+  if (g_l2_prefetch_mb > 0 && b.l2_pf_chunks == 0) {  // bytes of L2 look-ahead per launch, spread evenly over the warps
     const size_t per_step = (size_t)grid * LIN_WARPS * 2 * TS_CHUNK * 2;
     b.l2_pf_chunks = (int)min((size_t)16, ((size_t)g_l2_prefetch_mb << 20) / per_step);
   }
@@ -816,8 +848,10 @@ int mdi_linear_decode(const void* W, const void* W2, const void* bias, const voi
                       int* signal_flag, unsigned int* done_ctr, int ctas_per_sm, int use_pdl, int variant,
                       unsigned int* hist, unsigned long long* amax, unsigned long long* trace, const float* wscale,
                       const float* wscale2, const int* dep_wait_flag, int* dep_signal_flag, unsigned int* dep_ctr,
-                      cudaStream_t stream) {
+                      void* hop_row, long long hop_slot_stride, const void* pf_a, const void* pf_b,
+                      unsigned long long pf_bytes, int l2_pf_chunks, cudaStream_t stream) {
   if (K % 8 != 0) return -2;
+  if (hop_row && (out_fp32 || !signal_flag || !y)) return -2;
   StreamArgs a{};
   a.W = (const bf16*)W; a.W2 = (const bf16*)W2; a.bias = (const bf16*)bias; a.bias2 = (const bf16*)bias2;
   a.x = (const bf16*)x; a.norm_w = (const bf16*)norm_w; a.residual = (const bf16*)residual; a.y = y; a.ctx = ctx;
@@ -829,6 +863,9 @@ int mdi_linear_decode(const void* W, const void* W2, const void* bias, const voi
   a.hist = hist; a.amax = amax; a.trace = trace; a.wscale = wscale; a.wscale2 = wscale2;
   a.dep_wait = DepWait{dep_wait_flag, status, wait_max_cycles}; a.dep_signal = DepSignal{dep_signal_flag, dep_ctr};
   a.ctx_early = (use_pdl >> 1) & 1; use_pdl &= 1;  // launch flags: bit 0 = PDL, bit 1 = ctx readable before the wait
+  a.hop_row = (bf16*)hop_row; a.hop_slot_stride = hop_slot_stride;
+  a.pf_a = (const unsigned char*)pf_a; a.pf_b = (const unsigned char*)pf_b; a.pf_bytes = pf_bytes;
+  a.l2_pf_chunks = l2_pf_chunks > 0 ? l2_pf_chunks : 0;
   if (variant < 0) variant = g_default_variant;
   if (W2) return launch_stream<MODE_GATED>(a, variant, ctas_per_sm, use_pdl, stream);
   return launch_stream<MODE_PLAIN>(a, variant, ctas_per_sm, use_pdl, stream);

@@ -178,6 +178,12 @@ class FusedStage:
         self.weight_dtype = weight_dtype
         # prefill attention: "tcgen05" (hand-written flash attention, prompts start at position 0) or "sdpa"
         self.prefill_attn = os.environ.get("MDI_PREFILL_ATTN", "tcgen05")
+        # decode hop: last-CTA row copy (one system-scope fence per step) or per-CTA remote stores + fences
+        self.hop_copy = os.environ.get("MDI_HOP_COPY", "1") != "0"
+        # MB of the MLP's gate / up weights that the attention output projection pulls into L2 while it waits for
+        # the (latency-bound) attention kernel, and chunk pairs per warp of its own rows beyond the ring
+        self.pf_next_mb = float(os.environ.get("MDI_PF_NEXT_MB", "0"))
+        self.pf_self_chunks = int(os.environ.get("MDI_PF_SELF_CHUNKS", "0"))
         self._q: Dict[int, Tuple[torch.Tensor, torch.Tensor]] = {}  # id(linear) -> (fp8 weight, block scales)
         if weight_dtype == "fp8":
             self._quantize(free_bf16)
@@ -246,7 +252,7 @@ class FusedStage:
         return self._trace[i].data_ptr()
 
     def trace_step(self, builder: Any, max_records: int = 512, detail: Sequence[str] = (),
-                   detail_ctas: int = 1024) -> List[Dict[str, Any]]:
+                   detail_ctas: int = 1024, graph: bool = True) -> List[Dict[str, Any]]:
         """Run ``builder()`` (a sequence of ``enqueue_*`` calls) once with the kernel tracer on and
         return one row per launch: times in µs relative to the first kernel's entry —
         ``entry`` (first CTA starts), ``ready`` (first CTA past the PDL/hop wait), ``staged`` (last CTA
@@ -266,7 +272,13 @@ class FusedStage:
                 self._trace[:, 6] = table.data_ptr() + torch.arange(max_records, device=self.device) * (detail_ctas * 64)
                 self._trace[:, 7] = detail_ctas
             try:
-                builder()
+                if graph:  # replayed as ONE graph: launch gaps are the device's, not the Python caller's
+                    g = ops.CudaGraph()
+                    with g:
+                        builder()
+                    g.launch()
+                else:
+                    builder()
                 torch.cuda.synchronize(self.device)
                 rec = self._trace[: len(self._trace_names)].cpu()
                 names = list(self._trace_names)
@@ -374,7 +386,16 @@ class FusedStage:
                                 n_split=self.n_split, use_pdl=self.use_pdl, trace=self._tr(f"L{li}.attn"),
                                 status=self.status.data_ptr(), wait_max_cycles=self.wait_max_cycles, **dep())
                 lw, src, name = self._w(blk.attn.proj), self.y_attn, f"L{li}.o_proj"
+                pf = {}
+                if self.pf_self_chunks:
+                    pf["l2_pf_chunks"] = self.pf_self_chunks
+                if self.pf_next_mb > 0 and getattr(blk, "has_mlp", True) and hasattr(blk.mlp, "fc_1"):
+                    w1 = self._w(blk.mlp.fc_1)["W"]
+                    w2 = self._w(blk.mlp.fc_2)["W"]
+                    nbytes = min(int(self.pf_next_mb * 2 ** 20) // 2, w1.numel() * w1.element_size()) & ~4095
+                    pf["prefetch"] = (w1.data_ptr(), w2.data_ptr(), nbytes)
             else:
+                pf = {}
                 gw = {**self._w(blk.mlp.fc_1), **self._w(blk.mlp.fc_2, second=True)}
                 ops.linear_decode(gw.pop("W"), x_in, self.h_mlp, self.ctx, **gw, norm_w=blk.norm_2.weight,
                                   eps=cfg.norm_eps, unit_offset=cfg.unit_offset_norm, act=self._gate_act(),
@@ -386,10 +407,15 @@ class FusedStage:
             w_out = lw.pop("W")
             res = dict(residual=x_in, res_slot_stride=x_in_stride, ctx_early=True,  # never the first launch after advance_step
                        ctas_per_sm=self._ctas("o_proj" if kind == "attn" else "down"), status=self.status.data_ptr(),
-                       wait_max_cycles=self.wait_max_cycles, **dep())
+                       wait_max_cycles=self.wait_max_cycles, **pf, **dep())
             if not last:
                 ops.linear_decode(w_out, src, x_out, self.ctx, **lw, **res, trace=self._tr(name), **common)
                 x_in, x_in_stride = x_out, 0
+            elif hop is not None and self.hop_copy:
+                # the row is finished locally (out_local), the last CTA copies it to the next stage and signals
+                ops.linear_decode(w_out, src, self.out_local, self.ctx, **lw, **res, y_slot_stride=C,
+                                  hop_ptr=hop.hidden_ptr, hop_slot_stride=C, signal_flag=hop.flag_ptr,
+                                  done_ctr=self.done_ctr.data_ptr(), trace=self._tr(name + "+hop"), **common)
             elif hop is not None:
                 ops.linear_decode(w_out, src, None, self.ctx, **lw, **res, y_ptr=hop.hidden_ptr, y_slot_stride=C,
                                   signal_flag=hop.flag_ptr, done_ctr=self.done_ctr.data_ptr(),

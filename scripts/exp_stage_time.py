@@ -18,7 +18,22 @@ from mdi_llm_b200.parallel.scheduler import SamplingParams  # noqa: E402
 from mdi_llm_b200.utils.checkpoint import random_init_stage_  # noqa: E402
 
 
-def measure(model, role, layers, k, n_samples, ctx, steps=300, warm=50, weights="bf16", **stage_kw):
+def measure(model, role, layers, k, n_samples, ctx, steps=300, warm=50, weights="bf16", env=None, **stage_kw):
+    saved = {}
+    for key, val in (env or {}).items():
+        saved[key] = os.environ.get(key)
+        os.environ[key] = val
+    try:
+        return _measure(model, role, layers, k, n_samples, ctx, steps, warm, weights, **stage_kw)
+    finally:
+        for key, val in saved.items():
+            if val is None:
+                os.environ.pop(key, None)
+            else:
+                os.environ[key] = val
+
+
+def _measure(model, role, layers, k, n_samples, ctx, steps=300, warm=50, weights="bf16", **stage_kw):
     cfg = Config.from_name(model, n_layer=max(layers, 1), block_size=2048)
     st = build_stage(cfg, role, layers, meta=True, **stage_kw)
     random_init_stage_(st, "cuda", torch.bfloat16, seed=1)
@@ -102,13 +117,14 @@ if __name__ == "__main__":
     for case in a.cases.split(","):
         f = case.split(":")
         role, layers, k = f[0], int(f[1]), int(f[2])
-        extra = {}
+        env = {}
         if len(f) > 3 and f[3]:
             for flag in f[3].split("+"):
-                extra[flag] = True
+                key, _, val = flag.partition("=")
+                env[key] = val
         role_name = "starter" if role == "starter" else "secondary:0"
-        us, status = measure(a.model, role_name, layers, k, 1 if (role == "starter" and layers >= 16) else a.n_samples, a.ctx, **extra)
-        rows.append({"role": role, "layers": layers, "steps_per_graph": k, "extra": sorted(extra), "us_per_step": us, "status": status})
+        us, status = measure(a.model, role_name, layers, k, 1 if (role == "starter" and layers >= 16) else a.n_samples, a.ctx, env=env)
+        rows.append({"role": role, "layers": layers, "steps_per_graph": k, "env": env, "us_per_step": us, "status": status})
         print(rows[-1], flush=True)
     if a.out:
         json.dump(rows, open(a.out, "w"), indent=1)

@@ -93,7 +93,8 @@ def test_decode_launch_sequence_binds(role, kw, expect_first, expect_last):
     sigs = [c[1].get("signal_flag") for c in seq]
     assert all(w is None for w in waits[1:]) and all(s is None for s in sigs[:-1]) and sigs[-1] == 0x2000
     assert (waits[0] is None) == fs.is_starter
-    assert seq[-1][1]["y_ptr"] == 0x1000 and seq[-1][1]["done_ctr"] is not None
+    # hop by row copy: the row is finished in out_local, the last CTA copies it to the next stage's hidden_in
+    assert seq[-1][1]["hop_ptr"] == 0x1000 and seq[-1][1]["y"] is fs.out_local and seq[-1][1]["done_ctr"] is not None
     # residual stream ping-pong: a kernel never writes the buffer it reads its residual from
     for n, args in seq:
         if n == "linear_decode" and args.get("residual") is not None and args.get("y") is not None:
