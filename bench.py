@@ -157,8 +157,8 @@ def parse_args() -> argparse.Namespace:
     ap.add_argument("--seq-len", type=int, default=0, help="KV/context budget (0 = prompt + all rounds)")
     ap.add_argument("--e2e-steps", type=int, default=0, help="rounds of the host-fed e2e measurement (0 = min(steps, 64))")
     ap.add_argument("--n-samples", type=int, default=0, help="concurrent samples (0 = number of GPUs)")
-    ap.add_argument("--partition", default="half", choices=["auto", "table", "balanced", "half"],
-                    help="table: the reference's N_LAYERS_NODES; balanced: whole layers, head-aware; half: attention|MLP half-layer units")
+    ap.add_argument("--partition", default="third", choices=["auto", "table", "balanced", "half", "third"],
+                    help="table: the reference's N_LAYERS_NODES; balanced: whole layers, head-aware; half: attention|MLP units; third: attention|gate-up|down units")
     ap.add_argument("--no-pdl", action="store_true")
     ap.add_argument("--ctas-per-sm", type=int, default=4)
     ap.add_argument("--weights", default="bf16", choices=["bf16", "fp8"],
@@ -414,7 +414,7 @@ def run_job(args: argparse.Namespace, job: int = 0, light: bool = False) -> Dict
     try:
         # ---------------- device-driven, device-timed (CUDA events on every node, max over nodes) ----------------
         sess = gd.open_session(n_samples, rounds_total, prompts, mode="device")
-        plan = [sp["units"] / 2 for sp in gd.specs] if gd.specs else [cfg.n_layer]
+        plan = [sp["layers"] for sp in gd.specs] if gd.specs else [cfg.n_layer]
         warm = sess.run(args.warmup)  # prefill of every prompt through every stage + W warm-up rounds
         sampler = ClockSampler(world)
         sampler.start()

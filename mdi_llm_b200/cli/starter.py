@@ -47,8 +47,8 @@ def build_parser() -> argparse.ArgumentParser:
                    help="GPT-2 generation protocol: no KV caches, the whole context travels the ring every step")
     p.add_argument("--head-on", default="starter", choices=["starter", "finisher"],
                    help="'finisher': first-generation chain, the last node owns ln_f + lm_head and returns logits")
-    p.add_argument("--partition", default="auto", choices=["auto", "table", "balanced", "half"],
-                   help="layer partition policy (half: boundaries may fall between a layer's attention and MLP)")
+    p.add_argument("--partition", default="auto", choices=["auto", "table", "balanced", "half", "third"],
+                   help="layer partition policy (half / third: boundaries may fall between a layer's attention, gate/up and down passes)")
     p.add_argument("--top-p", type=float, default=None, help="nucleus sampling threshold")
     p.add_argument("--transport", "--hop", dest="transport", default="auto", choices=["auto", "socket", "p2p", "nccl"],
                    help="inter-node data plane: p2p = fused NVLink stores + flags (device ring, one box), nccl = same "

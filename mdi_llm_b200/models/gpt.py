@@ -355,30 +355,68 @@ def build_mlp(config: Config) -> nn.Module:
         raise ValueError(f"unknown mlp class {config.mlp_class_name!r}") from None
 
 
+SUB_UNITS = ("attn", "gu", "down")  # the three residual sub-units of a sequential-residual block with a gated MLP
+_PART_ALIASES = {"both": ("attn", "gu", "down"), "attn": ("attn",), "mlp": ("gu", "down"), "attn_gu": ("attn", "gu"),
+                 "gu": ("gu",), "down": ("down",)}
+
+
+def part_units(parts: str) -> Tuple[str, ...]:
+    try:
+        return _PART_ALIASES[parts]
+    except KeyError:
+        raise ValueError(f"parts must be one of {sorted(_PART_ALIASES)}, got {parts!r}") from None
+
+
+class _PartialGatedMLP(nn.Module):
+    """The gate/up half (``fc_1``, ``fc_2``) or the down half (``proj``) of a gated MLP — a pipeline boundary
+    between them carries ``[x | act(fc_1 n) * fc_2 n]`` (width C + I)."""
+
+    def __init__(self, config: Config, units: Tuple[str, ...]) -> None:
+        super().__init__()
+        if "gu" in units:
+            self.fc_1 = nn.Linear(config.n_embd, config.intermediate_size, bias=config.bias)
+            self.fc_2 = nn.Linear(config.n_embd, config.intermediate_size, bias=config.bias)
+        if "down" in units:
+            self.proj = nn.Linear(config.intermediate_size, config.n_embd, bias=config.bias)
+        self.silu = config.mlp_class_name == "LLaMAMLP"
+        self.approx = config.gelu_approximate
+
+    def gate(self, a: torch.Tensor) -> torch.Tensor:
+        return F.silu(a) if self.silu else F.gelu(a, approximate=self.approx)
+
+
 class Block(nn.Module):
     """Transformer block, sequential or parallel residual (model.py:576-629)."""
 
     def __init__(self, config: Config, parts: str = "both") -> None:
-        """``parts``: "both" (a whole block), or one sub-layer of a sequential-residual block —
-        "attn" (``norm_1`` + attention + residual) / "mlp" (``norm_2`` + MLP + residual).  Half blocks
-        let a pipeline boundary fall *inside* a layer (finer stage balancing than the reference's
-        whole-layer chunks); the owner of the attention half owns the layer's KV cache."""
+        """``parts``: "both" (a whole block) or a contiguous run of the sub-units of a sequential-residual block:
+        "attn" (``norm_1`` + attention + residual), "gu" (``norm_2`` + the gate/up projections of a gated MLP),
+        "down" (the MLP's output projection + residual); "mlp" = gu+down, "attn_gu" = attn+gu.  Partial blocks
+        let a pipeline boundary fall *inside* a layer (finer stage balancing than the reference's whole-layer
+        chunks); the owner of the attention sub-unit owns the layer's KV cache.  A boundary after "gu" carries
+        ``[x | h]`` (width ``n_embd + intermediate_size``): the residual stream and the gated activations."""
         super().__init__()
         if not config.parallel_residual and config.shared_attention_norm:
             raise NotImplementedError("sequential residual with a shared attention norm")
-        if parts not in ("both", "attn", "mlp"):
-            raise ValueError(f"parts must be 'both', 'attn' or 'mlp', got {parts!r}")
+        units = part_units(parts)
         if parts != "both" and config.parallel_residual:
             raise ValueError("a parallel-residual block cannot be split between stages")
         self.config = config
         self.parts = parts
-        self.has_attn, self.has_mlp = parts in ("both", "attn"), parts in ("both", "mlp")
+        self.units = units
+        self.has_attn, self.has_gu, self.has_down = "attn" in units, "gu" in units, "down" in units
+        self.has_mlp = self.has_gu and self.has_down
         if self.has_attn:
             self.norm_1 = build_norm(config)
             self.attn = CausalSelfAttention(config)
-        if self.has_mlp:
+        if self.has_gu:
             self.norm_2 = None if config.shared_attention_norm else build_norm(config)
+        if self.has_mlp:
             self.mlp = build_mlp(config)
+        elif self.has_gu or self.has_down:
+            if config.mlp_class_name not in ("LLaMAMLP", "GemmaMLP"):
+                raise ValueError("only gated MLPs can be cut between their up and down projections")
+            self.mlp = _PartialGatedMLP(config, units)
 
     def forward(
         self,
@@ -388,17 +426,28 @@ class Block(nn.Module):
         input_pos: Optional[torch.Tensor] = None,
         kv: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
     ) -> torch.Tensor:
-        if self.parts == "mlp":
+        if self.parts == "both":
+            h = self.norm_1(x)
+            a = self.attn(h, cos, sin, input_pos, kv)
+            if self.config.parallel_residual:
+                h2 = h if self.norm_2 is None else self.norm_2(x)
+                return self.mlp(h2) + a + x
+            x = x + a
             return x + self.mlp(self.norm_2(x))
-        h = self.norm_1(x)
-        a = self.attn(h, cos, sin, input_pos, kv)
-        if self.parts == "attn":
-            return x + a
-        if self.config.parallel_residual:
-            h2 = h if self.norm_2 is None else self.norm_2(x)
-            return self.mlp(h2) + a + x
-        x = x + a
-        return x + self.mlp(self.norm_2(x))
+        C = self.config.n_embd
+        g = None
+        if self.units[0] == "down":  # the message is [x | h]
+            x, g = x[..., :C], x[..., C:]
+        if self.has_attn:
+            x = x + self.attn(self.norm_1(x), cos, sin, input_pos, kv)
+        if self.has_mlp:
+            return x + self.mlp(self.norm_2(x))
+        if self.has_gu:
+            n2 = self.norm_2(x)
+            return torch.cat((x, self.mlp.gate(self.mlp.fc_1(n2)) * self.mlp.fc_2(n2)), dim=-1)
+        if self.has_down:
+            return x + self.mlp.proj(g)
+        return x
 
 
 # =============================================================================================

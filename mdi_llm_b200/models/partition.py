@@ -29,7 +29,8 @@ __all__ = [
     "N_LAYERS_NODES", "plan_layers", "balanced_plan", "layer_ranges", "split_parameters",
     "split_and_store", "merge_chunks", "count_transformer_blocks", "chunk_dir", "chunk_file",
     "HalfStage", "plan_half_units", "half_stages", "split_parameters_half", "decode_unit_costs",
-    "stage_shape_from_state_dict", "stage_specs",
+    "stage_shape_from_state_dict", "stage_specs", "plan_third_units", "third_stages", "split_parameters_units",
+    "decode_third_costs",
 ]
 
 # n_nodes -> n_layer -> (starter layers, layers per secondary).  Data of config.py:56-98.
@@ -214,34 +215,151 @@ def split_parameters_half(model_params: Dict[str, Any], units_per_stage: Sequenc
     return {"starter": chunks[0], "secondary": chunks[1:]}
 
 
+# ---- third-layer partitions -------------------------------------------------------------------------------
+# A gated MLP is itself two weight passes: gate/up (2 x [I, C]) and down ([C, I]).  Cutting between them makes the
+# planner's unit a third of a layer: unit u = 3*layer + (0: attention | 1: gate/up | 2: down).  The boundary after
+# a gate/up unit carries [x | h] (n_embd + intermediate_size values per token instead of n_embd) — still nothing
+# next to the weight stream it balances: measured decode costs 30 / 34 / 19 us per unit (Llama-3-8B, B200) against
+# a 200 us output head put the 8-stage bottleneck at 377 us with thirds vs 396 us with halves.
+_THIRD_OF = {"norm_1": 0, "attn": 0, "norm_2": 1, "mlp.fc_1": 1, "mlp.fc_2": 1, "mlp.proj": 2}
+_FIRST_PARTS = {0: "both", 1: "mlp", 2: "down"}   # by (first unit % 3)
+_LAST_PARTS = {0: "both", 1: "attn", 2: "attn_gu"}  # by (one-past-last unit % 3)
+
+
+def _third_of(tail: str) -> int:
+    for prefix, k in _THIRD_OF.items():
+        if tail.startswith(prefix + "."):
+            return k
+    return 1  # anything else of the MLP half travels with gate/up
+
+
+def third_stages(units_per_stage: Sequence[int]) -> List[Dict[str, Any]]:
+    """Stage shapes of a third-unit plan: ``n_blocks``, ``first_parts`` / ``last_parts`` (see ``Block``),
+    ``layer_offset``, ``lo_unit`` / ``hi_unit``."""
+    out, u = [], 0
+    for n in units_per_stage:
+        if n < 1:
+            raise ValueError("every stage needs at least one unit")
+        lo, hi = u, u + n
+        lo_layer, hi_layer = lo // 3, (hi + 2) // 3
+        out.append({"n_blocks": hi_layer - lo_layer, "first_parts": _FIRST_PARTS[lo % 3], "last_parts": _LAST_PARTS[hi % 3],
+                    "layer_offset": lo_layer, "lo_unit": lo, "hi_unit": hi, "units": n, "unit": "third"})
+        u = hi
+    return out
+
+
+def decode_third_costs(config: Config, bytes_per_param: float = 2.0, eff_tbps: float = 6.45, small_us: float = 2.6,
+                       attn_kernel_us: float = 10.5, head_extra_us: float = 38.0) -> Tuple[float, float, float, float, float]:
+    """``(attention, gate/up, down, head, per-step)`` decode costs in microseconds, fitted to the per-kernel device
+    trace of a Llama-3-8B stage on a B200 at ~0.5k context (profiles/README.md): weight bytes at the achieved HBM
+    rate plus a latency term per small kernel, the latency-bound attention kernel, and the fixed cost of a step."""
+    C, bw = config.n_embd, eff_tbps * 1e6
+    qkv = config.qkv_size * C * bytes_per_param / bw + small_us
+    o = config.attn_out_dim * C * bytes_per_param / bw + small_us + 1.3
+    gu = 2 * C * config.intermediate_size * bytes_per_param / bw - 1.5  # its first chunks are prefetched under the o_proj
+    down = C * config.intermediate_size * bytes_per_param / bw + 1.0
+    head = config.padded_vocab_size * C * bytes_per_param / bw + head_extra_us
+    return qkv + attn_kernel_us + o, gu, down, head, 9.0
+
+
+def _plan_units(costs: Sequence[float], n_nodes: int, head: float, fixed: float) -> List[int]:
+    """Exact DP over contiguous partitions of ``costs`` minimising the slowest stage (stage 0 adds ``head``)."""
+    U = len(costs)
+    if n_nodes < 1 or U < n_nodes:
+        raise ValueError(f"cannot split {U} units over {n_nodes} nodes")
+    pre = [0.0]
+    for c in costs:
+        pre.append(pre[-1] + c)
+    INF = float("inf")
+    best = [[INF] * (U + 1) for _ in range(n_nodes + 1)]
+    arg = [[0] * (U + 1) for _ in range(n_nodes + 1)]
+    for u in range(1, U + 1):
+        best[1][u] = pre[u] + head + fixed
+    for k in range(2, n_nodes + 1):
+        for u in range(k, U + 1):
+            for a in range(k - 1, u):
+                c = max(best[k - 1][a], pre[u] - pre[a] + fixed)
+                if c < best[k][u] - 1e-9:
+                    best[k][u], arg[k][u] = c, a
+    cuts, u = [], U
+    for k in range(n_nodes, 1, -1):
+        a = arg[k][u]
+        cuts.append(u - a)
+        u = a
+    cuts.append(u)
+    return cuts[::-1]
+
+
+def plan_third_units(n_nodes: int, config: Config, costs: Optional[Tuple[float, float, float, float, float]] = None) -> List[int]:
+    """Third-units per stage (sum = 3 * n_layer) minimising the slowest stage of the decode ring."""
+    if config.parallel_residual or config.mlp_class_name not in ("LLaMAMLP", "GemmaMLP"):
+        raise ValueError("third-layer partitions need sequential-residual blocks with a gated MLP")
+    ca, cg, cd, ch, fx = costs if costs is not None else decode_third_costs(config)
+    return _plan_units([ca, cg, cd] * config.n_layer, n_nodes, ch, fx)
+
+
+def split_parameters_units(model_params: Dict[str, Any], specs: Sequence[Dict[str, Any]]) -> Dict[str, Any]:
+    """Chunks for a third-unit plan (``specs`` from :func:`third_stages`): every tensor of a layer goes to the stage
+    that owns its sub-unit, re-indexed from that stage's first (possibly partial) block."""
+    n_layer = count_transformer_blocks(model_params)
+    if specs[-1]["hi_unit"] != 3 * n_layer:
+        raise ValueError(f"plan does not cover {3 * n_layer} third-layer units")
+    chunks: List[Dict[str, Any]] = [{} for _ in specs]
+    for k in [k for k in model_params if k.startswith("transformer.h.")]:
+        _, _, li, tail = k.split(".", 3)
+        unit = 3 * int(li) + _third_of(tail)
+        si = next(i for i, sp in enumerate(specs) if sp["lo_unit"] <= unit < sp["hi_unit"])
+        chunks[si][f"transformer.h.{int(li) - specs[si]['layer_offset']}.{tail}"] = model_params.pop(k)
+    for k in ("transformer.wte.weight", "transformer.wte.bias", "transformer.wpe.weight", "transformer.ln_f.weight",
+              "transformer.ln_f.bias", "lm_head.weight", "lm_head.bias"):
+        if k in model_params:
+            chunks[0][k] = model_params.pop(k)
+    return {"starter": chunks[0], "secondary": chunks[1:]}
+
+
 def stage_shape_from_state_dict(sd: Dict[str, Any]) -> Dict[str, Any]:
-    """``{"n_blocks", "first_mlp_only", "last_attn_only"}`` of a chunk, read off its keys: a block without
-    ``attn.*`` tensors holds only its MLP half (and vice versa) — so chunk files fully describe half-layer plans."""
+    """``{"n_blocks", "first_parts", "last_parts"}`` (+ the half-plan booleans) of a chunk, read off its keys: which
+    sub-units of its first / last block are present — so chunk files fully describe sub-layer plans."""
     blocks: Dict[int, set] = {}
     for k in sd:
         if k.startswith("transformer.h."):
             _, _, li, tail = k.split(".", 3)
-            blocks.setdefault(int(li), set()).add(tail.split(".", 1)[0])
+            blocks.setdefault(int(li), set()).add(_third_of(tail))
     n = len(blocks)
     if n == 0:
-        return {"n_blocks": 0, "first_mlp_only": False, "last_attn_only": False}
+        return {"n_blocks": 0, "first_parts": "both", "last_parts": "both", "first_mlp_only": False, "last_attn_only": False}
     first, last = blocks[min(blocks)], blocks[max(blocks)]
-    return {"n_blocks": n, "first_mlp_only": "attn" not in first, "last_attn_only": "mlp" not in last}
+    gated = not any(".mlp.fc." in k or ".mlp.experts." in k for k in sd)  # fc + proj (GPT-NeoX) / MoE MLPs are never cut inside
+    if not gated:  # two-matrix MLPs (fc + proj) are never cut inside: "mlp present" = units 1 and 2
+        first = first | ({1, 2} if first & {1, 2} else set())
+        last = last | ({1, 2} if last & {1, 2} else set())
+    fp = "both" if 0 in first else ("mlp" if 1 in first else "down")
+    lp = "both" if 2 in last else ("attn_gu" if 1 in last else "attn")
+    return {"n_blocks": n, "first_parts": fp, "last_parts": lp, "first_mlp_only": fp == "mlp", "last_attn_only": lp == "attn"}
 
 
 def stage_specs(n_nodes: int, config: Config, policy: str = "auto") -> List[Dict[str, Any]]:
-    """Per-stage shape for a partition policy: ``"half"`` = half-layer units (boundaries may fall between a
-    layer's attention and MLP), else whole layers via :func:`plan_layers`.  Every entry carries ``n_blocks``,
-    ``first_mlp_only``, ``last_attn_only``, ``layer_offset`` (global index of local block 0) and ``units``."""
-    if policy == "half" and n_nodes > 1 and not config.parallel_residual:
+    """Per-stage shape for a partition policy: ``"third"`` / ``"half"`` = sub-layer units (boundaries may fall
+    between a layer's attention, gate/up and down passes), else whole layers via :func:`plan_layers`.  Every entry
+    carries ``n_blocks``, ``first_parts``, ``last_parts``, ``layer_offset`` and ``layers`` (layer-equivalents)."""
+    sub_ok = n_nodes > 1 and not config.parallel_residual
+    if policy == "third" and sub_ok and config.mlp_class_name in ("LLaMAMLP", "GemmaMLP"):
+        specs = third_stages(plan_third_units(n_nodes, config))
+        for sp in specs:
+            sp["layers"] = round(sp["units"] / 3, 2)
+        return specs
+    if policy in ("half", "third") and sub_ok:
         units = plan_half_units(n_nodes, config)
-        return [{"n_blocks": h.n_blocks, "first_mlp_only": h.first_mlp_only, "last_attn_only": h.last_attn_only,
-                 "layer_offset": h.lo_layer, "units": u} for h, u in zip(half_stages(units), units)]
-    pol = "balanced" if policy == "half" else policy
+        return [{"n_blocks": h.n_blocks, "first_parts": "mlp" if h.first_mlp_only else "both",
+                 "last_parts": "attn" if h.last_attn_only else "both", "first_mlp_only": h.first_mlp_only,
+                 "last_attn_only": h.last_attn_only, "layer_offset": h.lo_layer, "units": u, "unit": "half", "layers": u / 2}
+                for h, u in zip(half_stages(units), units)]
+    pol = "balanced" if policy in ("half", "third") else policy
     plan = plan_layers(n_nodes, config.n_layer, config, policy=pol) if n_nodes > 1 else [config.n_layer]
     out, off = [], 0
     for n in plan:
-        out.append({"n_blocks": n, "first_mlp_only": False, "last_attn_only": False, "layer_offset": off, "units": 2 * n})
+        out.append({"n_blocks": n, "first_parts": "both", "last_parts": "both", "first_mlp_only": False, "last_attn_only": False,
+                    "layer_offset": off, "units": n, "unit": "layer", "layers": float(n)})
         off += n
     return out
 
@@ -343,7 +461,11 @@ def split_and_store(
     """Split a state dict and write the chunk files; returns the chunk directory."""
     verb = bool(kwargs.get("verb", False))
     units = kwargs.get("units")
-    if units is not None:  # half-layer plan: a cut layer's attention / MLP tensors land in neighbouring chunks
+    specs = kwargs.get("specs")
+    if specs is not None and specs[0].get("unit") == "third":  # a cut layer's sub-units land in neighbouring chunks
+        chunks = split_parameters_units(model_params, specs)
+        info = {"plan": [sp["layers"] for sp in specs]}
+    elif units is not None:  # half-layer plan
         chunks = split_parameters_half(model_params, units)
         info = {"plan": [u / 2 for u in units]}
     else:

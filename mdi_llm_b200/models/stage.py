@@ -33,10 +33,13 @@ class StageModule(nn.Module, RopeMixin):
         super().__init__()
         self.config = config
         self.n_local_layers = int(n_transf_layers)
-        # half-layer boundaries (models/partition.py:plan_half_units): the first local block may hold
-        # only its MLP half, the last one only its attention half
-        self.first_mlp_only = bool(kwargs.get("first_mlp_only", False))
-        self.last_attn_only = bool(kwargs.get("last_attn_only", False))
+        # sub-layer boundaries (models/partition.py: plan_half_units / plan_third_units): the first local block
+        # may start at its MLP ("mlp") or at the MLP's down projection ("down"), the last one may end after its
+        # attention ("attn") or after the gate/up projections ("attn_gu"); "both" = whole block
+        self.first_parts = str(kwargs.get("first_parts") or ("mlp" if kwargs.get("first_mlp_only") else "both"))
+        self.last_parts = str(kwargs.get("last_parts") or ("attn" if kwargs.get("last_attn_only") else "both"))
+        self.first_mlp_only = self.first_parts == "mlp"
+        self.last_attn_only = self.last_parts == "attn"
         self.verb = bool(kwargs.get("verb", False))
         self.params_init = False
         self.kv_pool: Optional[KVPool] = None
@@ -79,18 +82,38 @@ class StageModule(nn.Module, RopeMixin):
         return 1
 
     def _make_blocks(self) -> nn.ModuleList:
+        from .gpt import SUB_UNITS, part_units
+
         n = self.n_local_layers
-        if n == 1 and self.first_mlp_only and self.last_attn_only:
-            raise ValueError("a stage cannot hold only 'mlp' and only 'attn' of the same single block")
+        names = {("attn", "gu", "down"): "both", ("attn",): "attn", ("gu", "down"): "mlp", ("attn", "gu"): "attn_gu",
+                 ("gu",): "gu", ("down",): "down"}
 
         def parts(i: int) -> str:
-            if i == 0 and self.first_mlp_only:
-                return "mlp"
-            if i == n - 1 and self.last_attn_only:
-                return "attn"
-            return "both"
+            units = set(SUB_UNITS)
+            if i == 0:
+                units &= set(part_units(self.first_parts))
+            if i == n - 1:
+                units &= set(part_units(self.last_parts))
+            key = tuple(u for u in SUB_UNITS if u in units)
+            if key not in names:
+                raise ValueError(f"block {i}: first_parts={self.first_parts!r} and last_parts={self.last_parts!r} leave no "
+                                 "contiguous sub-units")
+            return names[key]
 
         return nn.ModuleList(Block(self.config, parts(i)) for i in range(n))
+
+    @property
+    def in_width(self) -> int:
+        """Width of the incoming hidden message: ``[x | h]`` when the stage starts at a down projection."""
+        c = self.config
+        blocks = self.transformer.h
+        return c.n_embd + c.intermediate_size if len(blocks) and blocks[0].units[0] == "down" else c.n_embd
+
+    @property
+    def out_width(self) -> int:
+        c = self.config
+        blocks = self.transformer.h
+        return c.n_embd + c.intermediate_size if len(blocks) and blocks[-1].units[-1] == "gu" else c.n_embd
 
     def _blocks(self, x: torch.Tensor, input_pos: Optional[torch.Tensor], slot: int) -> torch.Tensor:
         T = x.size(1)

@@ -40,7 +40,7 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.mdi_error_string.argtypes = [i32]
     lib.mdi_linear_decode.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, i32, i32, f32, i32, i32, i32,
                                       vp, vp, i64, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp,
-                                      vp, i64, vp, vp, c_ulonglong, i32, vp]
+                                      vp, i64, vp, vp, c_ulonglong, i32, vp, i64, i32, vp]
     lib.mdi_qkv_decode.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, i32, i32, i32, f32, i32,
                                    vp, vp, i64, i32, i32, i32, vp, vp, vp, vp, vp, vp]
     lib.mdi_set_linear_variant.argtypes = [i32]
@@ -193,13 +193,16 @@ def linear_decode(
     wscale: Optional[torch.Tensor] = None, wscale2: Optional[torch.Tensor] = None,
     ctx_early: bool = False, dep_wait: Optional[int] = None,
     dep_signal: Optional[int] = None, dep_ctr: Optional[int] = None, hop_ptr: Optional[int] = None,
-    hop_slot_stride: int = 0, prefetch: Optional[Tuple[int, int, int]] = None, l2_pf_chunks: int = 0) -> None:
+    hop_slot_stride: int = 0, prefetch: Optional[Tuple[int, int, int]] = None, l2_pf_chunks: int = 0,
+    hop_pre: Optional[Tuple[int, int, int]] = None) -> None:
     """``y = epilogue(W @ norm?(x))`` for one token.  ``*_ptr`` overrides let the output /
     residual / input live in peer-mapped (other GPU) memory that has no torch tensor.
     With ``wscale`` (fp32 ``[N, K/128]``) ``W`` (and ``W2``/``wscale2``) are fp8-e4m3 block-scaled.
 
     ``hop_ptr`` (with ``signal_flag``): the fused hop by row copy — ``y`` is a local ``[n_slots, N]`` buffer and the
-    last CTA copies the finished row to ``hop_ptr + slot * hop_slot_stride`` (peer memory) before releasing the flag.
+    last CTA copies the finished row to ``hop_ptr + slot * hop_slot_stride`` (peer memory) before releasing the flag;
+    ``hop_pre = (ptr, slot_stride, n)`` puts ``n`` more elements (the residual row ``x`` of a ``[x | h]`` message) in
+    front of it.
     ``prefetch = (ptr_a, ptr_b, bytes)``: while waiting for its input the kernel pulls that many bytes of each region
     (the NEXT kernel's weights) into L2; ``l2_pf_chunks``: the same for its own rows beyond the shared-memory ring."""
     if wscale is None:
@@ -218,6 +221,7 @@ def linear_decode(
         wait_flag, status, wait_max_cycles, signal_flag, done_ctr, ctas_per_sm, int(use_pdl) | (2 if ctx_early else 0), variant, hist, amax,
         trace, ptr(wscale), ptr(wscale2), dep_wait, dep_signal, dep_ctr, hop_ptr, hop_slot_stride,
         prefetch[0] if prefetch else None, prefetch[1] if prefetch else None, prefetch[2] if prefetch else 0, l2_pf_chunks,
+        hop_pre[0] if hop_pre else None, hop_pre[1] if hop_pre else 0, hop_pre[2] if hop_pre else 0,
         stream_ptr()), "linear_decode")
 
 

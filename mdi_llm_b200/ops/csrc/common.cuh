@@ -152,8 +152,11 @@ __device__ __forceinline__ void hop_signal(const HopSignal& s, const int* ctx) {
 // copies the finished row over NVLink with 16-byte stores, fences once at system scope and releases the flag.
 // (hop_signal above makes EVERY CTA fence at system scope after its few remote bytes: measured +8-10 us on the
 // tail of the stage's last kernel, because a MEMBAR.SYS waits behind the SM's in-flight weight stream.)
+// `pre` (n_pre elements, may be null): a second local row that goes in FRONT of the main one — the residual
+// stream x of an [x | h] message (stage boundary between a gated MLP's gate/up and down projections).
 __device__ __forceinline__ void hop_signal_copy(const HopSignal& s, const int* ctx, const __nv_bfloat16* local_row,
-                                                __nv_bfloat16* remote_row, int n_elems) {
+                                                __nv_bfloat16* remote_row, int n_elems,
+                                                const __nv_bfloat16* pre = nullptr, int n_pre = 0) {
   if (s.flag == nullptr) return;
   __shared__ int hop_is_last;
   __syncthreads();
@@ -167,6 +170,12 @@ __device__ __forceinline__ void hop_signal_copy(const HopSignal& s, const int* c
   __syncthreads();
   if (!hop_is_last) return;
   __threadfence();
+  if (pre != nullptr && n_pre > 0) {
+    const uint4* psrc = reinterpret_cast<const uint4*>(pre);
+    uint4* pdst = reinterpret_cast<uint4*>(remote_row);
+    for (int v = threadIdx.x; v < n_pre / 8; v += blockDim.x) pdst[v] = __ldcg(psrc + v);
+    remote_row += n_pre;
+  }
   const uint4* src = reinterpret_cast<const uint4*>(local_row);
   uint4* dst = reinterpret_cast<uint4*>(remote_row);
   for (int v = threadIdx.x; v < n_elems / 8; v += blockDim.x) dst[v] = __ldcg(src + v);

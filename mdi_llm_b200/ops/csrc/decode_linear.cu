@@ -220,6 +220,9 @@ struct StreamArgs {
   // the next stage's memory and releases the flag (hop_signal_copy); null = epilogues store to y directly
   bf16* hop_row;
   long long hop_slot_stride;
+  const bf16* hop_pre;            // [x | h] messages: the residual row copied in front (hop_pre + slot * stride)
+  long long hop_pre_slot_stride;
+  int hop_pre_elems;
   // look-ahead for the NEXT kernel: while this kernel waits for its input (o_proj behind the latency-bound
   // attention: HBM idle) its warps ask the TMA engine to pull `pf_bytes` of each of these regions into L2
   const unsigned char* pf_a;
@@ -398,7 +401,8 @@ __global__ void __launch_bounds__(LIN_THREADS, 3) stream_ldg_kernel(const Stream
   }
   stats_flush(a, hist_s, best);
   if (a.hop_row) hop_signal_copy(a.signal, a.ctx, reinterpret_cast<const bf16*>(a.y) + (size_t)slot * a.y_slot_stride,
-                                 a.hop_row + (size_t)slot * a.hop_slot_stride, a.N);
+                                 a.hop_row + (size_t)slot * a.hop_slot_stride, a.N,
+                                 a.hop_pre ? a.hop_pre + (size_t)slot * a.hop_pre_slot_stride : nullptr, a.hop_pre_elems);
   else hop_signal(a.signal, a.ctx);
   dep_signal(a.dep_signal, a.ctx);
   trace_mark(a.trace, 3, true);
@@ -509,7 +513,8 @@ __global__ void __launch_bounds__(LIN_THREADS, STAGES == 2 ? 3 : (STAGES == 3 ? 
   }
   stats_flush(a, hist_s, best);
   if (a.hop_row) hop_signal_copy(a.signal, a.ctx, reinterpret_cast<const bf16*>(a.y) + (size_t)slot * a.y_slot_stride,
-                                 a.hop_row + (size_t)slot * a.hop_slot_stride, a.N);
+                                 a.hop_row + (size_t)slot * a.hop_slot_stride, a.N,
+                                 a.hop_pre ? a.hop_pre + (size_t)slot * a.hop_pre_slot_stride : nullptr, a.hop_pre_elems);
   else hop_signal(a.signal, a.ctx);
   dep_signal(a.dep_signal, a.ctx);
   trace_mark(a.trace, 3, true);
@@ -639,7 +644,8 @@ __global__ void __launch_bounds__(LIN_THREADS, 3) stream_ldg_fp8_kernel(const St
   }
   stats_flush(a, hist_s, best);
   if (a.hop_row) hop_signal_copy(a.signal, a.ctx, reinterpret_cast<const bf16*>(a.y) + (size_t)slot * a.y_slot_stride,
-                                 a.hop_row + (size_t)slot * a.hop_slot_stride, a.N);
+                                 a.hop_row + (size_t)slot * a.hop_slot_stride, a.N,
+                                 a.hop_pre ? a.hop_pre + (size_t)slot * a.hop_pre_slot_stride : nullptr, a.hop_pre_elems);
   else hop_signal(a.signal, a.ctx);
   dep_signal(a.dep_signal, a.ctx);
   trace_mark(a.trace, 3, true);
@@ -747,7 +753,8 @@ __global__ void __launch_bounds__(LIN_THREADS, 3) stream_bulk_fp8_kernel(const S
   }
   stats_flush(a, hist_s, best);
   if (a.hop_row) hop_signal_copy(a.signal, a.ctx, reinterpret_cast<const bf16*>(a.y) + (size_t)slot * a.y_slot_stride,
-                                 a.hop_row + (size_t)slot * a.hop_slot_stride, a.N);
+                                 a.hop_row + (size_t)slot * a.hop_slot_stride, a.N,
+                                 a.hop_pre ? a.hop_pre + (size_t)slot * a.hop_pre_slot_stride : nullptr, a.hop_pre_elems);
   else hop_signal(a.signal, a.ctx);
   dep_signal(a.dep_signal, a.ctx);
   trace_mark(a.trace, 3, true);
@@ -849,7 +856,8 @@ int mdi_linear_decode(const void* W, const void* W2, const void* bias, const voi
                       unsigned int* hist, unsigned long long* amax, unsigned long long* trace, const float* wscale,
                       const float* wscale2, const int* dep_wait_flag, int* dep_signal_flag, unsigned int* dep_ctr,
                       void* hop_row, long long hop_slot_stride, const void* pf_a, const void* pf_b,
-                      unsigned long long pf_bytes, int l2_pf_chunks, cudaStream_t stream) {
+                      unsigned long long pf_bytes, int l2_pf_chunks, const void* hop_pre, long long hop_pre_slot_stride,
+                      int hop_pre_elems, cudaStream_t stream) {
   if (K % 8 != 0) return -2;
   if (hop_row && (out_fp32 || !signal_flag || !y)) return -2;
   StreamArgs a{};
@@ -864,6 +872,8 @@ int mdi_linear_decode(const void* W, const void* W2, const void* bias, const voi
   a.dep_wait = DepWait{dep_wait_flag, status, wait_max_cycles}; a.dep_signal = DepSignal{dep_signal_flag, dep_ctr};
   a.ctx_early = (use_pdl >> 1) & 1; use_pdl &= 1;  // launch flags: bit 0 = PDL, bit 1 = ctx readable before the wait
   a.hop_row = (bf16*)hop_row; a.hop_slot_stride = hop_slot_stride;
+  a.hop_pre = (const bf16*)hop_pre; a.hop_pre_slot_stride = hop_pre_slot_stride; a.hop_pre_elems = hop_pre ? hop_pre_elems : 0;
+  if (a.hop_pre_elems % 8 != 0) return -2;
   a.pf_a = (const unsigned char*)pf_a; a.pf_b = (const unsigned char*)pf_b; a.pf_bytes = pf_bytes;
   a.l2_pf_chunks = l2_pf_chunks > 0 ? l2_pf_chunks : 0;
   if (variant < 0) variant = g_default_variant;

@@ -101,13 +101,19 @@ class GPTDistributed:
                     print("Chunks not found! Splitting the model")
                 self.model_config, full_model = load_from_pt(self.ckpt_dir)
                 assert full_model is not None
-                if self.partition_policy == "half" and not self.model_config.parallel_residual and self.head_on == "starter":
-                    units = plan_half_units(self.n_nodes, self.model_config)
+                sub = self.partition_policy in ("half", "third") and not self.model_config.parallel_residual \
+                    and self.head_on == "starter"
+                specs = stage_specs(self.n_nodes, self.model_config, self.partition_policy) if sub else None
+                if specs is not None and specs[0].get("unit") == "third":
                     self.plan = None
-                    node_chunks_dir = split_and_store(full_model, self.n_nodes, self.ckpt_dir, units=units, verb=self.verb)
+                    node_chunks_dir = split_and_store(full_model, self.n_nodes, self.ckpt_dir, specs=specs, verb=self.verb)
+                elif specs is not None and specs[0].get("unit") == "half":
+                    self.plan = None
+                    node_chunks_dir = split_and_store(full_model, self.n_nodes, self.ckpt_dir, units=[sp["units"] for sp in specs],
+                                                      verb=self.verb)
                 else:
                     self.plan = plan_layers(self.n_nodes, self.model_config.n_layer, self.model_config,
-                                            policy="balanced" if self.partition_policy == "half" else self.partition_policy)
+                                            policy="balanced" if self.partition_policy in ("half", "third") else self.partition_policy)
                     node_chunks_dir = split_and_store(full_model, self.n_nodes, self.ckpt_dir, plan=self.plan,
                                                       config=self.model_config, verb=self.verb, head_on=self.head_on)
                 self.model_was_split = not self.push_chunks
@@ -205,7 +211,7 @@ class GPTDistributed:
         if self.specs is not None:
             return [sp["n_blocks"] for sp in self.specs[1:]]
         plan = self.plan or plan_layers(self.n_nodes, self.model_config.n_layer, self.model_config,
-                                        policy="balanced" if self.partition_policy == "half" else self.partition_policy)
+                                        policy="balanced" if self.partition_policy in ("half", "third") else self.partition_policy)
         return list(plan[1:])
 
     def configure_nodes(self, n_samples: int) -> int:

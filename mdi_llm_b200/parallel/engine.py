@@ -129,17 +129,20 @@ class FusedStage:
             self.kv = model.kv_pool.data  # [L, n_slots, 2, G, S, hs]
             i32 = dict(dtype=torch.int32, device=dev)
             bf = dict(dtype=torch.bfloat16, device=dev)
-            # hop-visible region: hidden_in [n_slots, C] bf16 | flags [n_slots] i32 (64B aligned)
-            hid_bytes = n_slots * C * 2
+            # message widths: C, or C + I when the stage starts at a down projection / ends after a gate/up unit
+            # (third-layer plans, models/partition.py); hop-visible region: hidden_in [n_slots, W_in] bf16 | flags
+            self.W_in = int(getattr(model, "in_width", C))
+            self.W_out = int(getattr(model, "out_width", C))
+            hid_bytes = n_slots * self.W_in * 2
             self._flag_off = (hid_bytes + 255) // 256 * 256
             self.raw = RawBuffer(self._flag_off + max(256, n_slots * 4), dev) if exportable else None
             if self.raw is not None:
-                self.hidden_in = self.raw.view(0, (n_slots, C), torch.bfloat16)
+                self.hidden_in = self.raw.view(0, (n_slots, self.W_in), torch.bfloat16)
                 self.flags = self.raw.view(self._flag_off, (n_slots,), torch.int32)
             else:
-                self.hidden_in = torch.zeros(n_slots, C, **bf)
+                self.hidden_in = torch.zeros(n_slots, self.W_in, **bf)
                 self.flags = torch.zeros(n_slots, **i32)
-            self.out_local = torch.zeros(n_slots, C, **bf)  # host-driven mode: stage output lands here
+            self.out_local = torch.zeros(n_slots, self.W_out, **bf)  # the stage's output row (copied to the next stage by the hop)
             self.ctx = torch.zeros(ops.CTX_INTS, **i32)
             self.ctx_ring = torch.zeros(4096, ops.CTX_INTS, dtype=torch.int32).pin_memory()
             self._ring_i = 0
@@ -171,6 +174,7 @@ class FusedStage:
                 self.tok_ts = torch.zeros(n_slots, self.S + 1, dtype=torch.int64, device=dev)
                 self.t0_ts = torch.zeros(1, dtype=torch.int64, device=dev)
         self.hop_self = HopTarget(self.hidden_in.data_ptr(), self.flags.data_ptr())
+        self._last_x: Optional[Tuple[torch.Tensor, int]] = None
         self._graphs: Dict[Any, ops.CudaGraph] = {}
         self._trace: Optional[torch.Tensor] = None  # device tracer records [n, 6] int64 (see common.cuh)
         self._trace_names: List[str] = []
@@ -204,8 +208,10 @@ class FusedStage:
         for blk in self.model.transformer.h:
             if getattr(blk, "has_attn", True):
                 lins += [blk.attn.attn, blk.attn.proj]
-            if getattr(blk, "has_mlp", True):
-                lins += [blk.mlp.fc_1, blk.mlp.fc_2, blk.mlp.proj]
+            if getattr(blk, "has_gu", True):
+                lins += [blk.mlp.fc_1, blk.mlp.fc_2]
+            if getattr(blk, "has_down", True):
+                lins.append(blk.mlp.proj)
         if self.is_starter and not self.cfg.tie_embeddings:
             lins.append(self.model.lm_head)
         with torch.cuda.device(self.device):
@@ -332,28 +338,39 @@ class FusedStage:
                   use_pdl=self.use_pdl)
 
     def _units(self) -> List[Tuple[int, str]]:
-        """The stage's work as residual sub-layers ``(local block, "attn" | "mlp")`` — whole blocks
-        contribute both; a half-layer pipeline boundary contributes one (models/partition.py)."""
+        """The stage's work as residual sub-layers ``(local block, "attn" | "mlp" | "gu" | "down")`` — whole
+        blocks contribute attn + mlp; a sub-layer pipeline boundary leaves a partial block (models/partition.py)."""
         out: List[Tuple[int, str]] = []
         for li, blk in enumerate(self.model.transformer.h):
             if getattr(blk, "has_attn", True):
                 out.append((li, "attn"))
-            if getattr(blk, "has_mlp", True):
+            gu, down = getattr(blk, "has_gu", True), getattr(blk, "has_down", True)
+            if gu and down:
                 out.append((li, "mlp"))
+            elif gu:
+                out.append((li, "gu"))    # stage ends after the gate/up projections: the hop carries [x | h]
+            elif down:
+                out.append((li, "down"))  # stage starts at the down projection of a layer cut after gate/up
         return out
 
     def enqueue_blocks(self, hop: Optional[HopTarget], wait_input: bool, dep_flags: bool = False) -> None:
         """All local sub-layers for one token.  Input residual: ``xa`` on the starter (embedding),
-        ``hidden_in[slot]`` on a secondary.  The first kernel (QKV projection, or gate/up projection when
-        the stage starts inside a layer) acquires the incoming hop; the last one (down projection, or
-        attention output projection when the stage ends inside a layer) writes the ``hop`` target and
-        releases its flag, or writes ``out_local[slot]``."""
+        ``hidden_in[slot]`` on a secondary.  The first kernel (QKV projection; gate/up or down projection when
+        the stage starts inside a layer) acquires the incoming hop; the last one (down projection; attention
+        output projection or gate/up when the stage ends inside a layer) finishes the outgoing row in
+        ``out_local[slot]`` and — with a ``hop`` target — its last CTA copies the row into the next stage's
+        ``hidden_in[slot]`` over NVLink and releases the flag.  A stage that ends after gate/up sends
+        ``[x | h]``; the stage that starts at the matching down projection reads both halves from its
+        ``hidden_in`` row."""
         cfg, C = self.cfg, self.cfg.n_embd
-        x_in, x_in_stride = (self.xa, 0) if self.is_starter else (self.hidden_in, C)
+        I = cfg.intermediate_size
+        W_in, W_out = self.W_in, self.W_out
+        x_in, x_in_stride = (self.xa, 0) if self.is_starter else (self.hidden_in, W_in)
         common = dict(use_pdl=self.use_pdl)
         units = self._units()
-        n_kernels = sum(3 if k == "attn" else 2 for _, k in units)
+        n_kernels = sum({"attn": 3, "mlp": 2, "gu": 1, "down": 1}[k] for _, k in units)
         kidx = [0]
+        st_kw = dict(status=self.status.data_ptr(), wait_max_cycles=self.wait_max_cycles)
 
         def dep() -> Dict[str, Any]:
             """Flag dependency wiring of the next launch: wait on the previous kernel's flag, publish ours
@@ -366,12 +383,30 @@ class FusedStage:
             return dict(dep_wait=base + 4 * (j - 1) if j > 0 else None,
                         dep_signal=base + 4 * j if j < n_kernels - 1 else None, dep_ctr=self.dep_ctr.data_ptr())
 
+        def out_kw(name: str, n_pre: int = 0, pre: Optional[Tuple[torch.Tensor, int]] = None) -> Dict[str, Any]:
+            """Destination of the stage's LAST kernel: the local row (offset ``n_pre`` elements when ``[x | h]`` is
+            sent) and, with a hop target, the copy + signal done by its last CTA."""
+            kw: Dict[str, Any] = dict(y_ptr=self.out_local.data_ptr() + 2 * n_pre, y_slot_stride=W_out, trace=self._tr(name))
+            if hop is None:
+                return kw
+            if not self.hop_copy:
+                if n_pre:
+                    raise RuntimeError("stages that end after a gate/up unit need the row-copy hop (MDI_HOP_COPY=1)")
+                return dict(y_ptr=hop.hidden_ptr, y_slot_stride=W_out, signal_flag=hop.flag_ptr,
+                            done_ctr=self.done_ctr.data_ptr(), trace=self._tr(name + "+hop"))
+            kw.update(hop_ptr=hop.hidden_ptr, hop_slot_stride=W_out, signal_flag=hop.flag_ptr, done_ctr=self.done_ctr.data_ptr(),
+                      trace=self._tr(name + "+hop"))
+            if pre is not None:
+                kw.update(hop_pre=(pre[0].data_ptr(), pre[1], n_pre))
+            return kw
+
+        self._last_x = None
         for ui, (li, kind) in enumerate(units):
             first, last = ui == 0, ui == len(units) - 1
             blk = self.model.transformer.h[li]
-            wait = dict(wait_flag=self.flags.data_ptr() if (first and wait_input and not self.is_starter) else None,
-                        status=self.status.data_ptr(), wait_max_cycles=self.wait_max_cycles)
+            wait = dict(wait_flag=self.flags.data_ptr() if (first and wait_input and not self.is_starter) else None, **st_kw)
             x_out = self.xb if x_in is not self.xb else self.xa
+            pf: Dict[str, Any] = {}
             if kind == "attn":
                 kv_layer = self.kv[li]
                 qw = self._w(blk.attn.attn)
@@ -383,46 +418,42 @@ class FusedStage:
                     trace=self._tr(f"L{li}.qkv"), ctas_per_sm=self._ctas("qkv"), ctx_early=not first, **wait, **dep(), **common)
                 ops.attn_decode(self.q, kv_layer, self.y_attn, self.part, self.tickets, self.ctx, n_head=cfg.n_head,
                                 n_groups=cfg.n_query_groups, head_size=cfg.head_size, max_seq=self.S,
-                                n_split=self.n_split, use_pdl=self.use_pdl, trace=self._tr(f"L{li}.attn"),
-                                status=self.status.data_ptr(), wait_max_cycles=self.wait_max_cycles, **dep())
-                lw, src, name = self._w(blk.attn.proj), self.y_attn, f"L{li}.o_proj"
-                pf = {}
+                                n_split=self.n_split, use_pdl=self.use_pdl, trace=self._tr(f"L{li}.attn"), **st_kw, **dep())
+                lw, src, name, ctas = self._w(blk.attn.proj), dict(x=self.y_attn), f"L{li}.o_proj", self._ctas("o_proj")
                 if self.pf_self_chunks:
                     pf["l2_pf_chunks"] = self.pf_self_chunks
-                if self.pf_next_mb > 0 and getattr(blk, "has_mlp", True) and hasattr(blk.mlp, "fc_1"):
-                    w1 = self._w(blk.mlp.fc_1)["W"]
-                    w2 = self._w(blk.mlp.fc_2)["W"]
+                if self.pf_next_mb > 0 and getattr(blk, "has_gu", False):
+                    w1, w2 = self._w(blk.mlp.fc_1)["W"], self._w(blk.mlp.fc_2)["W"]
                     nbytes = min(int(self.pf_next_mb * 2 ** 20) // 2, w1.numel() * w1.element_size()) & ~4095
                     pf["prefetch"] = (w1.data_ptr(), w2.data_ptr(), nbytes)
-            else:
-                pf = {}
+            if kind in ("mlp", "gu"):
                 gw = {**self._w(blk.mlp.fc_1), **self._w(blk.mlp.fc_2, second=True)}
-                ops.linear_decode(gw.pop("W"), x_in, self.h_mlp, self.ctx, **gw, norm_w=blk.norm_2.weight,
-                                  eps=cfg.norm_eps, unit_offset=cfg.unit_offset_norm, act=self._gate_act(),
-                                  x_slot_stride=x_in_stride, trace=self._tr(f"L{li}.gate_up"),
-                                  ctas_per_sm=self._ctas("gate_up"), ctx_early=not first,
-                                  **(wait if first else dict(status=self.status.data_ptr(), wait_max_cycles=self.wait_max_cycles)),
-                                  **dep(), **common)
-                lw, src, name = self._w(blk.mlp.proj), self.h_mlp, f"L{li}.down"
-            w_out = lw.pop("W")
-            res = dict(residual=x_in, res_slot_stride=x_in_stride, ctx_early=True,  # never the first launch after advance_step
-                       ctas_per_sm=self._ctas("o_proj" if kind == "attn" else "down"), status=self.status.data_ptr(),
-                       wait_max_cycles=self.wait_max_cycles, **pf, **dep())
-            if not last:
-                ops.linear_decode(w_out, src, x_out, self.ctx, **lw, **res, trace=self._tr(name), **common)
-                x_in, x_in_stride = x_out, 0
-            elif hop is not None and self.hop_copy:
-                # the row is finished locally (out_local), the last CTA copies it to the next stage and signals
-                ops.linear_decode(w_out, src, self.out_local, self.ctx, **lw, **res, y_slot_stride=C,
-                                  hop_ptr=hop.hidden_ptr, hop_slot_stride=C, signal_flag=hop.flag_ptr,
-                                  done_ctr=self.done_ctr.data_ptr(), trace=self._tr(name + "+hop"), **common)
-            elif hop is not None:
-                ops.linear_decode(w_out, src, None, self.ctx, **lw, **res, y_ptr=hop.hidden_ptr, y_slot_stride=C,
-                                  signal_flag=hop.flag_ptr, done_ctr=self.done_ctr.data_ptr(),
-                                  trace=self._tr(name + "+hop"), **common)
+                gu_kw = dict(norm_w=blk.norm_2.weight, eps=cfg.norm_eps, unit_offset=cfg.unit_offset_norm, act=self._gate_act(),
+                             x_slot_stride=x_in_stride, ctas_per_sm=self._ctas("gate_up"), ctx_early=not first,
+                             **(wait if first else st_kw), **dep(), **common)
+                if kind == "gu":  # the stage ends here: out row = [x | h], x copied by the hop's last CTA
+                    assert last, "a gate/up-only unit is the last unit of its stage"
+                    self._last_x = (x_in, x_in_stride)
+                    ops.linear_decode(gw.pop("W"), x_in, None, self.ctx, **gw, **gu_kw,
+                                      **out_kw(f"L{li}.gate_up", n_pre=C, pre=(x_in, x_in_stride)))
+                    return
+                ops.linear_decode(gw.pop("W"), x_in, self.h_mlp, self.ctx, **gw, trace=self._tr(f"L{li}.gate_up"), **gu_kw)
+                lw, src, name, ctas = self._w(blk.mlp.proj), dict(x=self.h_mlp), f"L{li}.down", self._ctas("down")
+            if kind == "down":  # the stage starts here: h and the residual are the two halves of the incoming row
+                assert first and not self.is_starter, "a down-only unit is the first unit of a secondary stage"
+                lw, name, ctas = self._w(blk.mlp.proj), f"L{li}.down", self._ctas("down")
+                src = dict(x=None, x_ptr=self.hidden_in.data_ptr() + 2 * C, x_slot_stride=W_in)
+                res = dict(residual=None, residual_ptr=self.hidden_in.data_ptr(), res_slot_stride=W_in, ctx_early=False,
+                           ctas_per_sm=ctas, **wait, **dep())
             else:
-                ops.linear_decode(w_out, src, self.out_local, self.ctx, **lw, **res, y_slot_stride=C,
-                                  trace=self._tr(name), **common)
+                res = dict(residual=x_in, res_slot_stride=x_in_stride, ctx_early=True,  # never the first launch after advance_step
+                           ctas_per_sm=ctas, **st_kw, **pf, **dep())
+            w_out = lw.pop("W")
+            if not last:
+                ops.linear_decode(w_out, src.pop("x"), x_out, self.ctx, **src, **lw, **res, trace=self._tr(name), **common)
+                x_in, x_in_stride = x_out, 0
+            else:
+                ops.linear_decode(w_out, src.pop("x"), None, self.ctx, **src, **lw, **res, **out_kw(name), **common)
 
     # ---- prefill (T > 1): linears on the tcgen05 GEMM ------------------------------------------------
     @torch.inference_mode()
@@ -437,9 +468,14 @@ class FusedStage:
         (residual added) straight into the next stage's buffer at ``dst_ptr`` (peer memory) and releases
         ``flag[ctx.slot] = ctx.signal`` from inside the GEMM — the fused prefill hop; returns None."""
         m, cfg = self.model, self.cfg
+        C = cfg.n_embd
         T = data.size(1)
+        g_in = None
         if self.is_starter:
             x = m.embed(data.long(), input_pos)[0].to(torch.bfloat16).contiguous()
+        elif self.W_in > C:  # [x | h]: the stage starts at the down projection of a layer cut after gate/up
+            d = data[0].to(torch.bfloat16)
+            x, g_in = d[:, :C].contiguous(), d[:, C:].contiguous()
         else:
             x = data[0].to(torch.bfloat16).contiguous()
         cos, sin = m.rope_for(T, input_pos)
@@ -469,10 +505,20 @@ class FusedStage:
                 else:  # eager helper (SDPA): the oracle path
                     y = blk.attn.attend_qkv(qkv.unsqueeze(0), cos, sin, input_pos, m.kv_pool.layer(li, slot))[0].contiguous()
                 x = out_gemm(y, blk.attn.proj, last)
+            elif kind == "down":
+                x = out_gemm(g_in, blk.mlp.proj, last)
             else:
                 h = ops.rmsnorm_rows(x, blk.norm_2.weight, eps, uo)
                 g = ops.gemm(h, self._dense(blk.mlp.fc_1), bias=blk.mlp.fc_1.bias, w2=self._dense(blk.mlp.fc_2),
                              bias2=blk.mlp.fc_2.bias, act=self._gate_act())
+                if kind == "gu":  # the stage ends here: [x | h] travels (copy + in-kernel flag release)
+                    out = torch.cat((x, g), dim=1)
+                    if hop is None:
+                        return out.unsqueeze(0)
+                    ops.check(ops.lib().mdi_copy_signal(out.data_ptr(), hop[0], out.numel() * 2, hop[1], self.done_ctr.data_ptr(),
+                                                        self.ctx.data_ptr(), self.status.data_ptr(), ops.stream_ptr()),
+                              "prefill hop ([x | h])")
+                    return None
                 x = out_gemm(g, blk.mlp.proj, last)
             if x is None:
                 return None
@@ -576,6 +622,9 @@ class FusedStageRunner(StageRunner):
                 st.hidden_in[slot].copy_(data.reshape(-1).to(self.dtype))
                 st.set_ctx(slot, pos)
                 self._run("fwd", lambda: st.enqueue_blocks(None, False))
+            if st._last_x is not None:  # stage ends after gate/up: the outgoing row is [x | h], x added here (no hop kernel)
+                buf, stride = st._last_x
+                st.out_local[slot, : st.cfg.n_embd].copy_((buf[slot] if stride else buf)[: st.cfg.n_embd])
             return st.out_local[slot].view(1, 1, -1).clone()
 
     @torch.inference_mode()

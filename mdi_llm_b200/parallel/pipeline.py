@@ -69,17 +69,20 @@ class DevicePipeline:
         self.model = model.eval()
         self.device = self.stage.device
         self.C = model.config.n_embd
+        self.W_in, self.W_out = self.stage.W_in, self.stage.W_out  # message widths (C, or C + I around a cut MLP)
+        if self.hop == "nccl" and (self.W_in != self.C or self.W_out != self.C):
+            raise ValueError("the NCCL-hop baseline carries plain hidden states: use a whole- or half-layer partition")
         self.max_prompt_len = int(max_prompt_len or max_seq_length)
         # prefill hop payload (T x C per sample) lands here on secondaries
         self.prefill_raw: Optional[RawBuffer] = None
         self.prefill_in: Optional[torch.Tensor] = None
         if world > 1 and not self.is_starter:
-            nbytes = n_samples * self.max_prompt_len * self.C * 2
+            nbytes = n_samples * self.max_prompt_len * self.W_in * 2
             if exportable:
                 self.prefill_raw = RawBuffer(nbytes, self.device)
-                self.prefill_in = self.prefill_raw.view(0, (n_samples, self.max_prompt_len, self.C), torch.bfloat16)
+                self.prefill_in = self.prefill_raw.view(0, (n_samples, self.max_prompt_len, self.W_in), torch.bfloat16)
             else:
-                self.prefill_in = torch.zeros(n_samples, self.max_prompt_len, self.C, dtype=torch.bfloat16, device=self.device)
+                self.prefill_in = torch.zeros(n_samples, self.max_prompt_len, self.W_in, dtype=torch.bfloat16, device=self.device)
         self.next_hop: HopTarget = self.stage.hop_self  # world == 1: the ring closes on myself
         self.next_prefill_ptr: int = 0
         self._opened: List[int] = []
@@ -216,7 +219,7 @@ class DevicePipeline:
                 T = self.prompt_lens[slot]
                 pos = torch.arange(T, device=self.device)
                 st.set_ctx(slot, T - 1, wait=1, signal=1)
-                hop = None if self.is_last else (self.next_prefill_ptr + slot * self.max_prompt_len * self.C * 2,
+                hop = None if self.is_last else (self.next_prefill_ptr + slot * self.max_prompt_len * self.W_out * 2,
                                                  self.next_hop.flag_ptr)
                 if self.is_starter:
                     hidden = st.prefill(self.prompts[slot].view(1, -1), pos, slot, hop=hop)

@@ -232,9 +232,10 @@ class GPTServer:
             shape = stage_shape_from_state_dict(sd)  # half-layer chunks describe themselves
         else:
             shape = dict(self.stage_spec or {})
-        for k in ("first_mlp_only", "last_attn_only"):
-            if shape.get(k):
-                extra[k] = True
+        for k, legacy, val in (("first_parts", "first_mlp_only", "mlp"), ("last_parts", "last_attn_only", "attn")):
+            parts = shape.get(k) or (val if shape.get(legacy) else "both")
+            if parts != "both":
+                extra[k] = parts
         model = build_stage(self.model_config, role, n_transf_layers, meta=True, verb=self.verb, **extra)
         if sd is None:  # synthetic weights (benchmarks on a box without checkpoints): same model for any partition
             from ..utils.checkpoint import random_init_stage_

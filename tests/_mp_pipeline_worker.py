@@ -10,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-from test_engine_gpu import _cfg, _half_stages, _stages  # noqa: E402
+from test_engine_gpu import _cfg, _half_stages, _stages, _third_stages  # noqa: E402
 from mdi_llm_b200.parallel.pipeline import DevicePipeline  # noqa: E402
 from mdi_llm_b200.parallel.scheduler import SamplingParams  # noqa: E402
 
@@ -27,6 +27,10 @@ def main():
     if len(sys.argv) > 3 and sys.argv[3] == "half":  # boundaries inside layers (attention | MLP units)
         units = [3] + [2] * (world - 2) + [2 * cfg.n_layer - 3 - 2 * (world - 2)]
         stages = _half_stages(cfg, units, [f"cuda:{local}"] * world)
+    elif len(sys.argv) > 3 and sys.argv[3] == "third":  # boundaries between attention | gate/up | down units
+        n_units = 3 * cfg.n_layer
+        units = [4] + [5] * (world - 2) + [n_units - 4 - 5 * (world - 2)]  # cuts after a gate/up unit AND after attention units
+        stages = _third_stages(cfg, units, [f"cuda:{local}"] * world)
     else:
         _, stages = _stages(cfg, world, device=[f"cuda:{local}"] * world)  # every rank materialises only its own use
     stage = stages[rank]

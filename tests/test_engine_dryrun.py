@@ -94,7 +94,7 @@ def test_decode_launch_sequence_binds(role, kw, expect_first, expect_last):
     assert all(w is None for w in waits[1:]) and all(s is None for s in sigs[:-1]) and sigs[-1] == 0x2000
     assert (waits[0] is None) == fs.is_starter
     # hop by row copy: the row is finished in out_local, the last CTA copies it to the next stage's hidden_in
-    assert seq[-1][1]["hop_ptr"] == 0x1000 and seq[-1][1]["y"] is fs.out_local and seq[-1][1]["done_ctr"] is not None
+    assert seq[-1][1]["hop_ptr"] == 0x1000 and seq[-1][1]["y_ptr"] == fs.out_local.data_ptr() and seq[-1][1]["done_ctr"] is not None
     # residual stream ping-pong: a kernel never writes the buffer it reads its residual from
     for n, args in seq:
         if n == "linear_decode" and args.get("residual") is not None and args.get("y") is not None:
@@ -107,7 +107,7 @@ def test_local_output_and_prefill_sequences_bind():
         st.set_kv_cache(2, dtype=torch.bfloat16)
         fs = FusedStage(st, n_slots=2, max_seq_length=32)
         fs.enqueue_blocks(None, wait_input=False)
-        assert calls[-1][1]["y"] is fs.out_local and calls[-1][1].get("signal_flag") is None
+        assert calls[-1][1]["y_ptr"] == fs.out_local.data_ptr() and calls[-1][1].get("signal_flag") is None
         calls.clear()
         x = torch.zeros(1, 5, 256, dtype=torch.bfloat16)
         assert fs.prefill_attn == "tcgen05"
@@ -137,6 +137,37 @@ def test_flag_dependency_wiring_is_a_linear_chain():
     assert fs._step_seq == 2 and int(fs.ctx_ring[1][ops.CTX_STEP]) == 1
     fs.reset_deps()
     assert fs._step_seq == 0
+
+
+def test_third_unit_stages_bind_and_route_the_wide_message():
+    """Stage boundary between a gated MLP's gate/up and down projections: the upstream stage ends with the gate/up
+    kernel (row [x | h]: h written behind x in out_local, x copied by the hop's last CTA), the downstream stage
+    starts with the down projection reading h and the residual from the two halves of its hidden_in row."""
+    C, I = 256, 128
+    with dry_ops() as calls:
+        up = FusedStage(_stage("secondary:0", 2, last_parts="attn_gu"), n_slots=2, max_seq_length=32)
+        assert (up.W_in, up.W_out) == (C, C + I) and up._units() == [(0, "attn"), (0, "mlp"), (1, "attn"), (1, "gu")]
+        up.enqueue_blocks(HopTarget(0x1000, 0x2000), wait_input=True)
+        last = calls[-1][1]
+        assert calls[-1][0] == "linear_decode" and last["W2"] is not None  # the gate/up kernel is the last one
+        assert last["y_ptr"] == up.out_local.data_ptr() + 2 * C and last["y_slot_stride"] == C + I
+        assert last["hop_ptr"] == 0x1000 and last["hop_slot_stride"] == C + I and last["signal_flag"] == 0x2000
+        assert last["hop_pre"][2] == C  # x goes in front
+        calls.clear()
+        dn = FusedStage(_stage("secondary:1", 2, first_parts="down"), n_slots=2, max_seq_length=32)
+        assert (dn.W_in, dn.W_out) == (C + I, C) and dn._units() == [(0, "down"), (1, "attn"), (1, "mlp")]
+        dn.enqueue_blocks(HopTarget(0x3000, 0x4000), wait_input=True)
+        first = calls[0][1]
+        assert calls[0][0] == "linear_decode" and first["wait_flag"] == dn.flags.data_ptr()
+        assert first["x_ptr"] == dn.hidden_in.data_ptr() + 2 * C and first["x_slot_stride"] == C + I
+        assert first["residual_ptr"] == dn.hidden_in.data_ptr() and first["res_slot_stride"] == C + I
+        assert all(c[1].get("wait_flag") is None for c in calls[1:])
+        # prefill: [x | h] in, plain x out through the fused-hop GEMM
+        calls.clear()
+        dn.model.set_kv_cache(2, dtype=torch.bfloat16)
+        assert dn.prefill(torch.zeros(1, 5, C + I, dtype=torch.bfloat16), torch.arange(5), 0, hop=(0x5000, 0x6000)) is None
+        gemms = [c[1] for c in calls if c[0] == "gemm"]
+        assert gemms[0]["residual"] is not None and gemms[0].get("w2") is None and gemms[-1]["out_ptr"] == 0x5000
 
 
 # ---- DevicePipeline orchestration (fake graphs, no GPU) ---------------------------------------------------

@@ -248,6 +248,97 @@ def test_fused_stage_half_blocks_single_gpu():
     assert (got.float() - ref.float()).abs().max().item() <= 0.03 * ref.float().abs().max().item() + 0.03
 
 
+def _third_stages(cfg, units, devs, seed=7):
+    from mdi_llm_b200.models.partition import split_parameters_units, third_stages
+    from mdi_llm_b200.models.stage import build_stage
+    from mdi_llm_b200.utils.checkpoint import materialize_stage, random_state_dict
+
+    sd = random_state_dict(cfg, dtype=torch.bfloat16, seed=seed, std=0.05)
+    specs = third_stages(units)
+    chunks = split_parameters_units(dict(sd), specs)
+    out = []
+    for i, sp in enumerate(specs):
+        st = build_stage(cfg, "starter" if i == 0 else f"secondary:{i - 1}", sp["n_blocks"], meta=True,
+                         first_parts=sp["first_parts"], last_parts=sp["last_parts"])
+        materialize_stage(st, chunks["starter"] if i == 0 else chunks["secondary"][i - 1], devs[i], torch.bfloat16)
+        out.append(st)
+    return out
+
+
+def test_fused_stage_third_units_single_gpu():
+    """Stages cut between a gated MLP's gate/up and down projections, against the eager modules: the upstream
+    stage emits [x | h] (prefill and decode), the downstream stage consumes it."""
+    import copy
+
+    from mdi_llm_b200.parallel.engine import FusedStage
+
+    cfg = _cfg(n_layer=4)
+    C, I = cfg.n_embd, cfg.intermediate_size
+    # 12 units: [L0, L1.attn, L1.gu] | [L1.down, L2, L3.attn, L3.gu] | [L3.down]  -> middle stage: wide in AND wide out
+    stages = _third_stages(cfg, [5, 6, 1], ["cuda", "cuda", "cuda"])
+    mid = stages[1]
+    assert [b.parts for b in mid.transformer.h] == ["down", "both", "attn_gu"] and (mid.in_width, mid.out_width) == (C + I, C + I)
+    fs = FusedStage(mid, n_slots=2, max_seq_length=32)
+    fs.warmup()
+    eager = copy.deepcopy(mid)
+    eager.kv_pool = None
+    eager.set_kv_cache(2)
+    x = (torch.randn(1, 5, C + I, device="cuda") * 0.5).bfloat16()
+    pos = torch.arange(5, device="cuda")
+    fs.set_ctx(1, 4)
+    out_f = fs.prefill(x, pos, 1)
+    with torch.inference_mode():
+        out_e = eager(x, pos, slot=1)
+    assert out_f.shape == out_e.shape == (1, 5, C + I)
+    scale = out_e.float().abs().max().item()
+    assert (out_f.float() - out_e.float()).abs().max().item() <= 0.03 * scale + 0.03
+    # one decode token: fused kernels, local output row + the row copy of the hop (target = a local sink)
+    xt = (torch.randn(C + I, device="cuda") * 0.5).bfloat16()
+    fs.hidden_in[1].copy_(xt)
+    sink = torch.zeros(2, C + I, device="cuda", dtype=torch.bfloat16)
+    sink_flags = torch.zeros(2, dtype=torch.int32, device="cuda")
+    from mdi_llm_b200.parallel.engine import HopTarget
+
+    fs.set_ctx(1, 5, wait=0, signal=3)
+    fs.enqueue_blocks(HopTarget(sink.data_ptr(), sink_flags.data_ptr()), wait_input=False)
+    torch.cuda.synchronize()
+    with torch.inference_mode():
+        ref = eager(xt.view(1, 1, -1), torch.tensor([5], device="cuda"), slot=1)[0, 0]
+    got = sink[1]
+    assert sink_flags.tolist() == [0, 3] and sink[0].abs().sum() == 0
+    assert (got.float() - ref.float()).abs().max().item() <= 0.03 * ref.float().abs().max().item() + 0.03
+    assert torch.equal(got[:C], ref[:C]) or (got[:C].float() - ref[:C].float()).abs().max().item() <= 0.03 * scale + 0.03
+
+
+def test_fused_runner_chain_third_units_matches_single_stage_tokens():
+    """Three third-unit stages chained on ONE GPU through the host-driven runner interface (what the socket data
+    plane drives) generate the same greedy tokens as the single-stage device pipeline."""
+    from mdi_llm_b200.parallel.engine import FusedStageRunner
+    from mdi_llm_b200.parallel.pipeline import DevicePipeline
+    from mdi_llm_b200.parallel.scheduler import SamplingParams
+
+    cfg = _cfg(n_layer=4)
+    stages = _third_stages(cfg, [5, 3, 4], ["cuda"] * 3)  # [.., L1.gu] | [L1.down, L2.attn, L2.gu] | [L2.down, L3]
+    runners = [FusedStageRunner(st, max_seq_length=64, n_slots=1, sampling=SamplingParams.greedy()) for st in stages]
+    for r in runners:
+        r.begin_sample(0)
+    prompt = torch.tensor([[1, 10, 20, 30, 7]], device="cuda")
+    toks = prompt.clone()
+    pos = torch.arange(5, device="cuda")
+    data = prompt
+    for step in range(8):
+        h = runners[0].forward(0, data, pos)
+        for r in runners[1:]:
+            h = r.forward(0, h, pos)
+        logits = runners[0].head(h)
+        nxt = logits[0, -1].argmax().view(1, 1)
+        toks = torch.cat((toks, nxt), dim=1)
+        data, pos = nxt, pos[-1:] + 1
+    _, (st1,) = _stages(cfg, 1)
+    ref = DevicePipeline(st1, 0, 1, n_samples=1, max_seq_length=64, sampling=SamplingParams.greedy()).generate([prompt[0].cpu()], 8)
+    assert toks[0].tolist() == ref[0][0].tolist()
+
+
 def test_fp8_weights_pipeline_follows_the_dequantised_model():
     """BASELINE config #5 path: fp8 block-scaled weights end to end (prefill dequantised + tcgen05,
     decode on the fp8 streaming kernels) tracks the eager model run on the dequantised weights."""

@@ -40,6 +40,13 @@ def test_ipc_ring_half_layer_boundaries(world):
     _run(world, "device", 29660 + world, "8", "half")
 
 
+@pytest.mark.parametrize("world", [2, 4])
+def test_ipc_ring_third_layer_boundaries(world):
+    """Stage boundaries between attention | gate/up | down units: a boundary after gate/up carries [x | h]
+    (decode: row copy by the last CTA of the gate/up kernel; prefill: copy + in-kernel flag release)."""
+    _run(world, "device", 29680 + world, "8", "third")
+
+
 def test_train_ddp_nccl_two_gpus(tmp_path):
     """The trainer's DistributedDataParallel path over NCCL under torchrun (SURVEY #23) on two B200s:
     bf16 autocast, fused AdamW, gradient accumulation with no_sync, checkpoint written by rank 0."""
@@ -83,8 +90,8 @@ def fused_ckpt(tmp_path):
     return write_random_checkpoint(tmp_path / "custom" / "TinyFused", _cfg(n_layer=8), dtype=torch.bfloat16, seed=3)
 
 
-@pytest.mark.parametrize("world,flags", [(2, ()), (2, ("--partition", "half", "--decode-mode", "host")), (4, ("--partition", "half",)),
-                                         (8, ())])
+@pytest.mark.parametrize("world,flags", [(2, ()), (2, ("--partition", "third", "--decode-mode", "host")), (4, ("--partition", "half",)),
+                                         (8, ("--partition", "third"))])
 def test_starter_secondary_clis_device_ring_matches_single_gpu(tmp_path, fused_ckpt, world, flags):
     """The product path THROUGH THE PUBLIC API: `starter` + `secondary` CLI processes (one per GPU), HTTP control
     plane, CUDA-IPC handles exchanged at POST /init, fused NVLink hops — token-identical to one GPU, greedy."""

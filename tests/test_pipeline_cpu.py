@@ -225,3 +225,24 @@ def test_cacheless_mode_through_gptdistributed(tmp_path, topology, tiny_gpt2_cfg
     sec.gpt_serv.shutdown()
     assert sec.gpt_serv.use_kv_cache is False
     assert [st.gpt_serv.last_result.samples[i].tolist() for i in range(2)] == _reference_tokens(ck, prompts, 5)
+
+
+@pytest.mark.parametrize("policy,n_nodes", [("half", 3), ("third", 3), ("third", 4)])
+def test_sub_layer_partitions_token_exact(tmp_path, topology, tiny_llama_cfg, policy, n_nodes):
+    """Stage boundaries INSIDE layers (attention | gate/up | down units; the boundary after a gate/up unit carries
+    ``[x | h]``): chunks split on the fly by ``GPTDistributed(partition=...)``, every node infers its shape from
+    its chunk file, and the ring reproduces single-device greedy decode token for token."""
+    ck = write_random_checkpoint(tmp_path / "custom" / f"tiny-{policy}", tiny_llama_cfg, dtype=torch.float32)
+    prompts = [torch.tensor([256, 10 + i, 20, 30 + i][: 3 + i % 2]) for i in range(n_nodes + 1)]
+    st, _ = _run_cluster(ck, topology(n_nodes), n_nodes, prompts, 6, pre_split=False, partition=policy)
+    from mdi_llm_b200.models.partition import stage_shape_from_state_dict
+    from mdi_llm_b200.utils.checkpoint import lazy_load
+
+    shapes = [stage_shape_from_state_dict(lazy_load(ck / "chunks" / f"{n_nodes}nodes" / f))
+              for f in ["model_starter.pth"] + [f"model_secondary{i}.pth" for i in range(n_nodes - 1)]]
+    assert any(s["first_parts"] != "both" or s["last_parts"] != "both" for s in shapes)  # a layer really was cut
+    if policy == "third":
+        assert any(s["last_parts"] == "attn_gu" or s["first_parts"] == "down" for s in shapes) or n_nodes < 4
+    ref = _reference_tokens(ck, prompts, 6)
+    for i in range(len(prompts)):
+        assert st.gpt_serv.last_result.samples[i].tolist() == ref[i], f"sample {i}"

@@ -80,19 +80,26 @@ def test_stage_shape_and_partition_independent_random_weights(tiny_llama_cfg):
     sd = random_state_dict(cfg, dtype=torch.float32)
     chunks = split_parameters_half(dict(sd), [3, 4, 3])
     shapes = [stage_shape_from_state_dict(c) for c in [chunks["starter"]] + chunks["secondary"]]
-    assert shapes == [{"n_blocks": 2, "first_mlp_only": False, "last_attn_only": True},
-                      {"n_blocks": 3, "first_mlp_only": True, "last_attn_only": True},
-                      {"n_blocks": 2, "first_mlp_only": True, "last_attn_only": False}]
+    assert [(s["n_blocks"], s["first_parts"], s["last_parts"]) for s in shapes] == [(2, "both", "attn"), (3, "mlp", "attn"), (2, "mlp", "both")]
+    # third-layer units: cuts between attention | gate/up | down; chunk files describe their own shape
+    from mdi_llm_b200.models.partition import split_parameters_units, third_stages
+
+    tspecs = third_stages([5, 5, 5])  # 15 units = 5 layers: [L0, L1.attn, L1.gu] [L1.down, L2, L3.attn] [L3.gu, L3.down, L4]
+    tchunks = split_parameters_units(dict(sd), tspecs)
+    tshapes = [stage_shape_from_state_dict(c) for c in [tchunks["starter"]] + tchunks["secondary"]]
+    assert [(s["n_blocks"], s["first_parts"], s["last_parts"]) for s in tshapes] == [(2, "both", "attn_gu"), (3, "down", "attn"), (2, "mlp", "both")]
+    assert [(s["n_blocks"], s["first_parts"], s["last_parts"]) for s in tspecs] == [(2, "both", "attn_gu"), (3, "down", "attn"), (2, "mlp", "both")]
+    assert "transformer.h.0.mlp.proj.weight" in tchunks["secondary"][0] and "transformer.h.1.mlp.fc_1.weight" in tchunks["starter"]
     # the same seed gives the same model whatever the partition
     full = build_stage(cfg, "starter", cfg.n_layer, meta=True)
     random_init_stage_(full, "cpu", torch.float32, seed=11)
     ref = full.state_dict()
-    for policy in ("auto", "half"):
+    for policy in ("auto", "half", "third"):
         specs = stage_specs(3, cfg, policy)
-        assert sum(s["units"] for s in specs) == 2 * cfg.n_layer
+        assert abs(sum(s["layers"] for s in specs) - cfg.n_layer) < 0.02
         for i, sp in enumerate(specs):
             st = build_stage(cfg, "starter" if i == 0 else f"secondary:{i - 1}", sp["n_blocks"], meta=True,
-                             first_mlp_only=sp["first_mlp_only"], last_attn_only=sp["last_attn_only"])
+                             first_parts=sp["first_parts"], last_parts=sp["last_parts"])
             random_init_stage_(st, "cpu", torch.float32, seed=11, layer_offset=sp["layer_offset"])
             for k, v in st.state_dict().items():
                 if k.startswith("transformer.h."):
