@@ -274,7 +274,8 @@ __device__ __forceinline__ void item_rows(const StreamArgs& a, int it, const bf1
 // lane 0 of the owning warp: bias / activation / residual / RoPE / KV append, then the store
 template <int MODE>
 __device__ __forceinline__ void item_epilogue(const StreamArgs& a, int it, float da, float db, int slot, int pos,
-                                              const bf16* res, unsigned int* hist_s, unsigned long long& best) {
+                                              const bf16* res, unsigned int* hist_s, unsigned long long& best,
+                                              const float* pre_res = nullptr) {
   if (MODE == MODE_GATED) {
     if (a.bias) da += __bfloat162float(a.bias[it]);
     if (a.bias2) db += __bfloat162float(a.bias2[it]);
@@ -297,7 +298,7 @@ __device__ __forceinline__ void item_epilogue(const StreamArgs& a, int it, float
       if (a.bias) v += __bfloat162float(a.bias[row]);
       if (a.act == ACT_GELU_TANH) v = gelu_tanh(round_bf16(v));
       else if (a.act == ACT_GELU_ERF) v = gelu_erf(round_bf16(v));
-      if (res) v = round_bf16(v) + __bfloat162float(res[row]);
+      if (res) v = round_bf16(v) + (pre_res ? pre_res[j] : __bfloat162float(res[row]));
       // fp32 output = logits: bf16 values like nn.Linear would produce, kept in fp32 for the sampler
       if (a.out_fp32) {
         v = round_bf16(v);
@@ -483,8 +484,14 @@ __global__ void __launch_bounds__(LIN_THREADS, STAGES == 2 ? 3 : (STAGES == 3 ? 
   const bf16* res = a.residual ? a.residual + (size_t)slot * a.res_slot_stride : nullptr;
   float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
   int c = 0, ii = 0;
+  float pre_res[2] = {0.f, 0.f};  // the item's two residual values, requested when the item starts (off the tail)
   for (int f = 0; f < total; ++f) {
     const int st = f % STAGES;
+    if (MODE == MODE_PLAIN && c == 0 && res != nullptr && lane == 0) {
+      const int row = 2 * (gw + ii * n_gw);
+      pre_res[0] = __bfloat162float(res[row]);
+      pre_res[1] = row + 1 < a.N ? __bfloat162float(res[row + 1]) : 0.f;
+    }
     mbar_wait(&bars[st], (uint32_t)((f / STAGES) & 1));
     const int k0 = c * TS_CHUNK;
     const int nv = min(TS_CHUNK, a.K - k0) / 8;
@@ -503,7 +510,8 @@ __global__ void __launch_bounds__(LIN_THREADS, STAGES == 2 ? 3 : (STAGES == 3 ? 
     }
     if (++c == n_chunks) {
       const float da = warp_sum(a0 + a1), db = warp_sum(b0 + b1);
-      if (lane == 0) item_epilogue<MODE>(a, gw + ii * n_gw, da, db, slot, pos, res, hist_s, best);
+      if (lane == 0) item_epilogue<MODE>(a, gw + ii * n_gw, da, db, slot, pos, res, hist_s, best,
+                                         (MODE == MODE_PLAIN && res != nullptr) ? pre_res : nullptr);
       a0 = a1 = b0 = b1 = 0.f;
       c = 0;
       ++ii;

@@ -242,6 +242,13 @@ class FusedStage:
         v = os.environ.get(f"MDI_CTAS_{kernel.upper()}")
         return int(v) if v else self.ctas_per_sm
 
+    def _variant(self, kernel: str) -> Dict[str, int]:
+        """Weight-streaming path of one decode linear: ``MDI_VARIANT_<KERNEL>`` (0 LDG, 1 ring x4 / 1 CTA per SM,
+        2 ring x2, 3 ring x3) overrides the library default — small matrices want a deeper ring (the whole row pair
+        in flight before the input arrives), the big MLP matrices want more resident warps."""
+        v = os.environ.get(f"MDI_VARIANT_{kernel.upper()}")
+        return {"variant": int(v)} if v else {}
+
     def _gate_act(self) -> str:
         if self.cfg.mlp_class_name == "LLaMAMLP":
             return "silu_gate"
@@ -415,11 +422,13 @@ class FusedStage:
                     n_head=cfg.n_head, n_groups=cfg.n_query_groups, head_size=cfg.head_size,
                     rope_n_elem=cfg.rope_n_elem, max_seq=self.S, norm_w=blk.norm_1.weight, **qw,
                     eps=cfg.norm_eps, unit_offset=cfg.unit_offset_norm, x_slot_stride=x_in_stride,
-                    trace=self._tr(f"L{li}.qkv"), ctas_per_sm=self._ctas("qkv"), ctx_early=not first, **wait, **dep(), **common)
+                    trace=self._tr(f"L{li}.qkv"), ctas_per_sm=self._ctas("qkv"), ctx_early=not first, **self._variant("qkv"),
+                    **wait, **dep(), **common)
                 ops.attn_decode(self.q, kv_layer, self.y_attn, self.part, self.tickets, self.ctx, n_head=cfg.n_head,
                                 n_groups=cfg.n_query_groups, head_size=cfg.head_size, max_seq=self.S,
                                 n_split=self.n_split, use_pdl=self.use_pdl, trace=self._tr(f"L{li}.attn"), **st_kw, **dep())
                 lw, src, name, ctas = self._w(blk.attn.proj), dict(x=self.y_attn), f"L{li}.o_proj", self._ctas("o_proj")
+                pf.update(self._variant("o_proj"))
                 if self.pf_self_chunks:
                     pf["l2_pf_chunks"] = self.pf_self_chunks
                 if self.pf_next_mb > 0 and getattr(blk, "has_gu", False):
@@ -439,6 +448,7 @@ class FusedStage:
                     return
                 ops.linear_decode(gw.pop("W"), x_in, self.h_mlp, self.ctx, **gw, trace=self._tr(f"L{li}.gate_up"), **gu_kw)
                 lw, src, name, ctas = self._w(blk.mlp.proj), dict(x=self.h_mlp), f"L{li}.down", self._ctas("down")
+                pf.update(self._variant("down"))
             if kind == "down":  # the stage starts here: h and the residual are the two halves of the incoming row
                 assert first and not self.is_starter, "a down-only unit is the first unit of a secondary stage"
                 lw, name, ctas = self._w(blk.mlp.proj), f"L{li}.down", self._ctas("down")
