@@ -155,7 +155,7 @@ def parse_args() -> argparse.Namespace:
     ap.add_argument("--prompt-len", type=int, default=448,
                     help="prompt tokens per sample; the timed rounds then run at a realistic context (~0.5k positions) in both arms")
     ap.add_argument("--seq-len", type=int, default=0, help="KV/context budget (0 = prompt + all rounds)")
-    ap.add_argument("--e2e-steps", type=int, default=0, help="rounds of the host-fed e2e measurement (0 = min(steps, 64))")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="rounds of the host-fed e2e measurement (0 = max(steps, 64))")
     ap.add_argument("--n-samples", type=int, default=0, help="concurrent samples (0 = number of GPUs)")
     ap.add_argument("--partition", default="third", choices=["auto", "table", "balanced", "half", "third"],
                     help="table: the reference's N_LAYERS_NODES; balanced: whole layers, head-aware; half: attention|MLP units; third: attention|gate-up|down units")
@@ -218,7 +218,7 @@ def run_direct(args: argparse.Namespace) -> Dict[str, Any]:
     else:
         cfg = Config.from_name(args.model)
     n_samples = args.n_samples or world
-    e2e_rounds = args.e2e_steps or min(args.steps, 64)
+    e2e_rounds = args.e2e_steps or max(args.steps, 64)
     rounds_total = args.warmup + args.steps + 1
     seq_len = args.seq_len or min(cfg.block_size, ((args.prompt_len + max(rounds_total, e2e_rounds + 4) + 64) // 64) * 64)
     role = "starter" if rank == 0 else f"secondary:{rank - 1}"
@@ -385,7 +385,7 @@ def run_job(args: argparse.Namespace, job: int = 0, light: bool = False) -> Dict
     else:
         cfg = Config.from_name(args.model)
     n_samples = args.n_samples or world
-    e2e_rounds = args.e2e_steps or min(args.steps, 64)
+    e2e_rounds = args.e2e_steps or max(args.steps, 64)
     check_rounds = 16
     rounds_total = args.warmup + args.steps + 1
     need = rounds_total if light else max(rounds_total, e2e_rounds + 4, check_rounds + 1)

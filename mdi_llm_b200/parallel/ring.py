@@ -204,11 +204,15 @@ class RingSession:
         left = self.max_new - self.rounds_done
         rounds = left if rounds is None else min(int(rounds), left)
         prefill = not self.prefilled
-        start_at = time.time() + (0.004 if self.urls else 0.0)
-        futs = self._fan({"op": "run", "prefill": prefill, "rounds": rounds, "start_at": start_at})
+        # device-driven segments start together on every node (their CUDA-event times are then comparable); a
+        # host-fed segment is paced by the starter's own token read-backs, so nobody waits for a common start
+        start_at = time.time() + (0.004 if self.urls and self.mode == "device" else 0.0)
+        futs = self._fan({"op": "run", "prefill": prefill, "rounds": rounds,
+                          "start_at": start_at if self.mode == "device" else None})
         if prefill:
             self.t0_host = start_at
-        local = self.backend.run(prefill, rounds, start_at if self.urls else None, mode=self.mode, on_token=on_token)
+        local = self.backend.run(prefill, rounds, start_at if self.urls and self.mode == "device" else None, mode=self.mode,
+                                 on_token=on_token)
         per_node = [local] + self._join(futs)
         self.prefilled = True
         self.rounds_done += rounds
