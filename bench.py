@@ -388,9 +388,10 @@ def run_job(args: argparse.Namespace, job: int = 0, light: bool = False) -> Dict
     e2e_rounds = args.e2e_steps or max(args.steps, 64)
     check_rounds = 16
     rounds_total = args.warmup + args.steps + 1
-    need = rounds_total if light else max(rounds_total, e2e_rounds + 4, check_rounds + 1)
-    # same context budget formula as the reference arm (baseline/run_reference.py)
-    seq_len = args.seq_len or min(cfg.block_size, ((args.prompt_len + need + 64) // 64) * 64)
+    # same context budget formula as the reference arm (baseline/run_reference.py): room for the timed rounds only;
+    # the e2e and check sessions that follow fit themselves into it
+    seq_len = args.seq_len or min(cfg.block_size, ((args.prompt_len + rounds_total + 64) // 64) * 64)
+    e2e_rounds = max(1, min(e2e_rounds, seq_len - args.prompt_len - 4))
     ckpt = os.path.join(tempfile.gettempdir(), f"mdi_bench_{os.environ.get('MASTER_PORT', '0')}_{job}_r{rank}", "custom", cfg.name)
     os.makedirs(ckpt, exist_ok=True)
     cfg.save(ckpt)  # model_config.yaml: all the API needs next to synthetic weights
