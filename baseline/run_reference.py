@@ -28,8 +28,8 @@ SHIMS = HERE / "shims"
 METRIC = "generated tokens/sec (whole box, device-timed, max over ranks) Llama-3-8B recurrent-pipeline decode"
 
 
-def _unavailable(why: str) -> Dict[str, Any]:
-    return {"impl": "reference", "unavailable": why}
+def _unavailable(why: str, variant: str = "reference") -> Dict[str, Any]:
+    return {"impl": variant, "unavailable": why}
 
 
 def _write_tokenizer(ckpt: Path, vocab_size: int) -> None:
@@ -92,7 +92,12 @@ def _topology(n: int, base: int) -> Dict[str, Any]:
     return {"nodes": {"starter": node(0), "secondary": [node(i) for i in range(1, n)]}}
 
 
-def run_reference(args: Any) -> Dict[str, Any]:
+def run_reference(args: Any, variant: str = "reference") -> Dict[str, Any]:
+    """``variant``: ``"reference"`` = byte-stock reference (sockets + pickle, its own partition table);
+    ``"reference-table"`` = the same plus, for node counts its table lacks, an injected ``N_LAYERS_NODES`` entry
+    (data only, reference-style uniform split) so that e.g. 8 GPUs get a comparator; ``"reference-nccl"`` = the
+    reference NCCL-p2p build: ``sub.connections`` replaced by ``baseline/nccl_connections.py`` (torch.distributed
+    send/recv), everything else stock (table entry injected when missing)."""
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -112,15 +117,41 @@ def run_reference(args: Any) -> Dict[str, Any]:
             torch.cuda.set_device(local_rank)
         dev = "cpu" if cpu_mode else f"cuda:{local_rank}"
         dtype = "float32" if cpu_mode else "bfloat16"
+        nccl = variant == "reference-nccl" and world > 1
         if world > 1:
             os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-            dist.init_process_group("gloo")  # only used here for barriers around the reference run
+            if nccl:  # the data plane of this variant; also used for the barriers around the run
+                if cpu_mode:
+                    dist.init_process_group("gloo")  # protocol test of the shim on a machine without GPUs
+                else:
+                    dist.init_process_group("nccl", device_id=torch.device(dev))
+                import importlib.util
+
+                spec = importlib.util.spec_from_file_location("sub.connections", HERE / "nccl_connections.py")
+                mod = importlib.util.module_from_spec(spec)
+                import sub  # noqa: F401  (the reference package: parent of the module being replaced)
+
+                spec.loader.exec_module(mod)
+                sys.modules["sub.connections"] = mod
+                mod._edge_groups()  # collective: every rank creates the edge groups in the same order, now
+            else:
+                dist.init_process_group("gloo")  # only used here for barriers around the reference run
         from sub.config import N_LAYERS_NODES  # noqa: E402
         from sub.model import Config  # noqa: E402
         from sub.model_dist import GPTDistributed  # noqa: E402
 
         model_name = os.environ.get("MDI_REF_MODEL") or ("tiny-llama-1.1b" if getattr(args, "tiny", False) else args.model)
         cfg = Config.from_name(model_name)
+        injected = None
+        if variant != "reference" and world > 1 and (world not in N_LAYERS_NODES or cfg.n_layer not in N_LAYERS_NODES[world]):
+            # data only: a partition entry in the reference's own format, uniform like its existing rows
+            sec = -(-cfg.n_layer // world)  # ceil
+            start = cfg.n_layer - sec * (world - 1)
+            while start < 1:
+                sec -= 1
+                start = cfg.n_layer - sec * (world - 1)
+            injected = {"N_LAYERS_START": start, "N_LAYERS_SECONDARY": sec}
+            N_LAYERS_NODES.setdefault(world, {})[cfg.n_layer] = injected
         if world not in N_LAYERS_NODES or cfg.n_layer not in N_LAYERS_NODES[world]:
             return _unavailable(f"the reference has no layer partition for {world} nodes x {cfg.n_layer} layers "
                                 f"(KeyError in N_LAYERS_NODES, src/sub/config.py:56-98)") if rank == 0 else {}
@@ -128,6 +159,8 @@ def run_reference(args: Any) -> Dict[str, Any]:
         n_tokens = args.warmup + args.steps + 1
         seq_len = args.seq_len or ((args.prompt_len + n_tokens + 64) // 64) * 64
         ckpt = Path(os.environ.get("MDI_REF_CKPT_DIR", "/tmp/mdi_ref_ckpt")) / "custom" / (cfg.name + "-random")
+        transport_desc = ("torch.distributed send/recv over NCCL replacing sub.connections (baseline/nccl_connections.py); "
+                          "everything else stock") if nccl else "loopback TCP + pickle (reference stock path)"
         if rank == 0 and not (ckpt / "lit_model.pth").is_file():
             _write_checkpoint(ckpt, model_name, dev)
         chunk_dir = ckpt / "chunks" / f"{world}nodes"
@@ -181,10 +214,11 @@ def run_reference(args: Any) -> Dict[str, Any]:
             "metric": METRIC.replace("Llama-3-8B", cfg.name) if cfg.name != "Llama-3-8B" else METRIC, "value": round(value, 3), "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(dt * 1e3 / args.steps, 5), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if dtype == "bfloat16" else dtype,
-            "data": "synthetic prompts, random-init weights", "impl": "reference",
+            "data": "synthetic prompts, random-init weights", "impl": variant,
             "config": {"model": cfg.name, "global_batch": n_samples, "seq_len": seq_len, "prompt_len": args.prompt_len,
-                       "parallelism": f"pp{world} recurrent pipeline (reference table split)", "tokens_per_step": n_samples,
-                       "transport": "loopback TCP + pickle (reference stock path)", "compute": "eager PyTorch / cuBLAS",
+                       "parallelism": f"pp{world} recurrent pipeline (reference table split)" + (f", INJECTED table entry {injected}" if injected else ""),
+                       "tokens_per_step": n_samples,
+                       "transport": transport_desc, "compute": "eager PyTorch / cuBLAS",
                        "timing": "the reference's own per-token wall-clock timeline on the starter (tok_time)",
                        "shims": ["cherrypy", "accelerate", "matplotlib"], "setup_s": round(setup_s, 1)},
             "e2e": {"value": round(value, 3), "unit": "tokens/s", "note": "reference timing is end-to-end by construction"},

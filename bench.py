@@ -150,7 +150,9 @@ def parse_args() -> argparse.Namespace:
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=128)
     ap.add_argument("--warmup", type=int, default=8)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-table", "reference-nccl"],
+                    help="reference = byte-stock reference; reference-table = + injected partition-table entry for node counts it lacks; "
+                         "reference-nccl = its data plane swapped for torch.distributed send/recv (baseline/nccl_connections.py)")
     ap.add_argument("--model", default="Llama-3-8B")
     ap.add_argument("--prompt-len", type=int, default=448,
                     help="prompt tokens per sample; the timed rounds then run at a realistic context (~0.5k positions) in both arms")
@@ -567,7 +569,7 @@ def run_ours(args: argparse.Namespace) -> Dict[str, Any]:
 
 def main() -> None:
     args = parse_args()
-    if args.impl == "reference":
+    if args.impl.startswith("reference"):
         from baseline.run_reference import run_reference
 
         # the reference prints its generated samples and progress spinners on stdout: keep stdout for
@@ -576,7 +578,7 @@ def main() -> None:
         saved = os.dup(1)
         os.dup2(2, 1)
         try:
-            out = run_reference(args)
+            out = run_reference(args, args.impl)
         finally:
             sys.stdout.flush()
             os.dup2(saved, 1)
@@ -587,6 +589,10 @@ def main() -> None:
         out = run_ours(args)
     if out:
         print(json.dumps(out), flush=True)
+    if args.impl == "reference-nccl":  # RX threads may sit in a posted NCCL recv: leave without tearing the communicators down
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

@@ -58,3 +58,29 @@ def test_reference_arm_two_nodes_cpu(tmp_path):
     assert out["impl"] == "reference" and out["n_gpus"] == 2 and out["value"] > 0, out
     chunk_dir = next(tmp_path.glob("custom/*/chunks/2nodes"))
     assert (chunk_dir / ".complete").is_file() and (chunk_dir / "model_secondary0.pth").is_file()
+
+
+@pytest.mark.skipif(not (ROOT / "baseline/_ref/sub/model_dist.py").is_file(), reason="baseline/_ref not installed")
+@pytest.mark.parametrize("impl,world", [("reference-nccl", 2), ("reference-table", 4)])
+def test_reference_variants_cpu(tmp_path, impl, world):
+    """The two comparator variants of the reference arm on CPU (gloo stands in for NCCL): ``reference-nccl`` swaps
+    ``sub.connections`` for torch.distributed send/recv and leaves the rest of the reference stock;
+    ``reference-table`` injects a partition-table entry for a node count the reference's table lacks
+    (4 nodes x 12 layers here, as 8 nodes x 32 layers on the GPU box)."""
+    from conftest import free_ports
+
+    env = dict(os.environ, MDI_REF_DEVICE="cpu", MDI_REF_MODEL="pythia-160m", MDI_REF_CKPT_DIR=str(tmp_path))
+    (port,) = free_ports(1)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), str(ROOT / "bench.py"), "--impl", impl, "--gpus", str(world), "--steps", "3", "--warmup", "3",
+           "--prompt-len", "8"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-3000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip().startswith("{")]
+    assert len(lines) == 1, r.stdout[-2000:]
+    out = json.loads(lines[0])
+    assert out["impl"] == impl and out["n_gpus"] == world and out.get("value", 0) > 0, out
+    if impl == "reference-table":
+        assert "INJECTED" in out["config"]["parallelism"]
+    else:
+        assert "torch.distributed" in out["config"]["transport"]
