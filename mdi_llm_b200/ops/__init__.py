@@ -40,9 +40,9 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.mdi_error_string.argtypes = [i32]
     lib.mdi_linear_decode.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, i32, i32, f32, i32, i32, i32,
                                       vp, vp, i64, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp,
-                                      vp, i64, vp, vp, c_ulonglong, i32, vp, i64, i32, vp]
+                                      vp, i64, vp, vp, c_ulonglong, i32, vp, i64, i32, vp, i32, vp]
     lib.mdi_qkv_decode.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, i32, i32, i32, f32, i32,
-                                   vp, vp, i64, i32, i32, i32, vp, vp, vp, vp, vp, vp]
+                                   vp, vp, i64, i32, i32, i32, vp, vp, vp, vp, vp, vp, i32, vp]
     lib.mdi_set_linear_variant.argtypes = [i32]
     lib.mdi_set_l2_prefetch_mb.argtypes = [i32]
     lib.mdi_get_linear_variant.restype = i32
@@ -194,7 +194,7 @@ def linear_decode(
     ctx_early: bool = False, dep_wait: Optional[int] = None,
     dep_signal: Optional[int] = None, dep_ctr: Optional[int] = None, hop_ptr: Optional[int] = None,
     hop_slot_stride: int = 0, prefetch: Optional[Tuple[int, int, int]] = None, l2_pf_chunks: int = 0,
-    hop_pre: Optional[Tuple[int, int, int]] = None) -> None:
+    hop_pre: Optional[Tuple[int, int, int]] = None, norm_b: Optional[torch.Tensor] = None, layer_norm: bool = False) -> None:
     """``y = epilogue(W @ norm?(x))`` for one token.  ``*_ptr`` overrides let the output /
     residual / input live in peer-mapped (other GPU) memory that has no torch tensor.
     With ``wscale`` (fp32 ``[N, K/128]``) ``W`` (and ``W2``/``wscale2``) are fp8-e4m3 block-scaled.
@@ -222,7 +222,7 @@ def linear_decode(
         trace, ptr(wscale), ptr(wscale2), dep_wait, dep_signal, dep_ctr, hop_ptr, hop_slot_stride,
         prefetch[0] if prefetch else None, prefetch[1] if prefetch else None, prefetch[2] if prefetch else 0, l2_pf_chunks,
         hop_pre[0] if hop_pre else None, hop_pre[1] if hop_pre else 0, hop_pre[2] if hop_pre else 0,
-        stream_ptr()), "linear_decode")
+        ptr(norm_b), int(layer_norm), stream_ptr()), "linear_decode")
 
 
 def qkv_decode(
@@ -232,7 +232,8 @@ def qkv_decode(
     unit_offset: bool = False, x_slot_stride: int = 0, wait_flag: Optional[int] = None, status: Optional[int] = None,
     wait_max_cycles: int = 0, ctas_per_sm: int = 4, use_pdl: bool = False, x_ptr: Optional[int] = None,
     variant: int = -1, trace: Optional[int] = None, wscale: Optional[torch.Tensor] = None, ctx_early: bool = False, dep_wait: Optional[int] = None,
-    dep_signal: Optional[int] = None, dep_ctr: Optional[int] = None) -> None:
+    dep_signal: Optional[int] = None, dep_ctr: Optional[int] = None, norm_b: Optional[torch.Tensor] = None,
+    layer_norm: bool = False) -> None:
     if wscale is None:
         _bf16(W, "W")
     else:
@@ -242,7 +243,8 @@ def qkv_decode(
     check(lib().mdi_qkv_decode(
         ptr(W), ptr(bias), x_ptr if x_ptr is not None else ptr(x), ptr(norm_w), ptr(cos), ptr(sin), ptr(q_out),
         ptr(kv_layer), ptr(ctx), x_slot_stride, W.shape[1], n_head, n_groups, head_size, rope_n_elem, max_seq, eps,
-        int(unit_offset), wait_flag, status, wait_max_cycles, ctas_per_sm, int(use_pdl) | (2 if ctx_early else 0), variant, trace, ptr(wscale), dep_wait, dep_signal, dep_ctr, stream_ptr()),
+        int(unit_offset), wait_flag, status, wait_max_cycles, ctas_per_sm, int(use_pdl) | (2 if ctx_early else 0), variant, trace, ptr(wscale), dep_wait, dep_signal, dep_ctr,
+        ptr(norm_b), int(layer_norm), stream_ptr()),
         "qkv_decode")
 
 

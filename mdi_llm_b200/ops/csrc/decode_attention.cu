@@ -272,6 +272,7 @@ extern "C" int mdi_attn_decode(const void* q, const void* kv, void* y, float* pa
   if (head_size == HS_ && qpk == QPK_) return launch_attn<HS_, QPK_>(a, use_pdl, stream);
   MDI_ATT_CASE(128, 1) MDI_ATT_CASE(128, 2) MDI_ATT_CASE(128, 4) MDI_ATT_CASE(128, 8)
   MDI_ATT_CASE(64, 1) MDI_ATT_CASE(64, 2) MDI_ATT_CASE(64, 4) MDI_ATT_CASE(64, 8)
+  MDI_ATT_CASE(256, 1) MDI_ATT_CASE(256, 2)  // Gemma-7b / Pythia-1b class heads (static shared memory <= 48 KB)
 #undef MDI_ATT_CASE
   return -3;  // unsupported (head_size, q_per_kv): caller falls back to the eager path
 }

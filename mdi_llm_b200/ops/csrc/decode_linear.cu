@@ -91,8 +91,66 @@ __device__ __forceinline__ uint32_t norm_pair(uint32_t xp, uint32_t wp, float rs
   return *reinterpret_cast<const uint32_t*>(&o);
 }
 
+// LayerNorm variant (GPT-2 / Pythia / Falcon / Phi families): y = bf16((x - mean) * rstd * w + b), statistics in
+// fp32 — what torch's layer_norm computes on a bf16 row (one rounding at the end).
+__device__ __forceinline__ uint32_t ln_pair(uint32_t xp, uint32_t wp, uint32_t bp, float mean, float rstd, bool has_b) {
+  const float y0 = (bf16lo(xp) - mean) * rstd * bf16lo(wp) + (has_b ? bf16lo(bp) : 0.f);
+  const float y1 = (bf16hi(xp) - mean) * rstd * bf16hi(wp) + (has_b ? bf16hi(bp) : 0.f);
+  const __nv_bfloat162 o = __floats2bfloat162_rn(y0, y1);
+  return *reinterpret_cast<const uint32_t*>(&o);
+}
+
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  v = warp_sum(v);
+  __syncthreads();  // red may still be read from a previous reduction
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int w = 0; w < LIN_THREADS / 32; ++w) tot += red[w];
+  return tot;
+}
+
+__device__ __forceinline__ void stage_input_layernorm(const bf16* __restrict__ x, const bf16* __restrict__ norm_w,
+                                                      const bf16* __restrict__ norm_b, float eps, int K, bf16* xs, float* red) {
+  const int tid = threadIdx.x;
+  const int nvec = K / 8;
+  const uint4* src = reinterpret_cast<const uint4*>(x);
+  const uint4* wsrc = reinterpret_cast<const uint4*>(norm_w);
+  const uint4* bsrc = reinterpret_cast<const uint4*>(norm_b);
+  uint4* dst = reinterpret_cast<uint4*>(xs);
+  float s = 0.f;
+  for (int v = tid; v < nvec; v += LIN_THREADS) {  // pass 1: row to shared memory + sum
+    const uint4 r = __ldcg(src + v);
+    dst[v] = r;
+    const uint32_t p[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) s += bf16lo(p[q]) + bf16hi(p[q]);
+  }
+  const float mean = block_sum(s, red) / (float)K;
+  float ss = 0.f;
+  for (int v = tid; v < nvec; v += LIN_THREADS) {  // pass 2: centred second moment (own vectors: no sync needed)
+    const uint4 r = dst[v];
+    const uint32_t p[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { const float a = bf16lo(p[q]) - mean, b = bf16hi(p[q]) - mean; ss = fmaf(a, a, ss); ss = fmaf(b, b, ss); }
+  }
+  const float rstd = rsqrtf(block_sum(ss, red) / (float)K + eps);
+  for (int v = tid; v < nvec; v += LIN_THREADS) {
+    const uint4 r = dst[v], wv = __ldg(wsrc + v);
+    const uint4 bv = norm_b ? __ldg(bsrc + v) : make_uint4(0, 0, 0, 0);
+    uint4 o;
+    o.x = ln_pair(r.x, wv.x, bv.x, mean, rstd, norm_b != nullptr); o.y = ln_pair(r.y, wv.y, bv.y, mean, rstd, norm_b != nullptr);
+    o.z = ln_pair(r.z, wv.z, bv.z, mean, rstd, norm_b != nullptr); o.w = ln_pair(r.w, wv.w, bv.w, mean, rstd, norm_b != nullptr);
+    dst[v] = o;
+  }
+  __syncthreads();
+}
+
 __device__ __forceinline__ void stage_input(const bf16* __restrict__ x, const bf16* __restrict__ norm_w,
-                                            float eps, int unit_offset, int K, bf16* xs, float* red) {
+                                            float eps, int unit_offset, int K, bf16* xs, float* red,
+                                            const bf16* __restrict__ norm_b = nullptr, int layer_norm = 0) {
+  if (layer_norm && norm_w != nullptr) { stage_input_layernorm(x, norm_w, norm_b, eps, K, xs, red); return; }
   const int tid = threadIdx.x;
   const int nvec = K / 8;
   const uint4* src = reinterpret_cast<const uint4*>(x);
@@ -185,7 +243,9 @@ struct StreamArgs {
   const bf16* bias;      // [N] or null
   const bf16* bias2;     // [N] or null
   const bf16* x;         // input activation row: x + slot * x_slot_stride
-  const bf16* norm_w;    // fused RMSNorm weight [K] or null
+  const bf16* norm_w;    // fused RMSNorm / LayerNorm weight [K] or null
+  const bf16* norm_b;    // LayerNorm bias [K] or null
+  int layer_norm;        // 1: LayerNorm statistics (mean / variance), 0: RMS
   const bf16* residual;  // residual + slot * res_slot_stride, [N], or null
   void* y;               // output (bf16, or fp32 when out_fp32): y + slot * y_slot_stride
   const int* ctx;
@@ -386,7 +446,7 @@ __global__ void __launch_bounds__(LIN_THREADS, 3) stream_ldg_kernel(const Stream
   hop_wait(a.wait, a.ctx);
   trace_mark(a.trace, 1, true);
   const int slot = a.ctx ? a.ctx[MDI_CTX_SLOT] : 0, pos = a.ctx ? a.ctx[MDI_CTX_POS] : 0;
-  stage_input(a.x + (size_t)slot * a.x_slot_stride, a.norm_w, a.eps, a.unit_offset, a.K, xs, red);
+  stage_input(a.x + (size_t)slot * a.x_slot_stride, a.norm_w, a.eps, a.unit_offset, a.K, xs, red, a.norm_b, a.layer_norm);
   trace_mark(a.trace, 2, false);
   pdl_launch_dependents();
 
@@ -477,7 +537,7 @@ __global__ void __launch_bounds__(LIN_THREADS, STAGES == 2 ? 3 : (STAGES == 3 ? 
   hop_wait(a.wait, a.ctx);
   trace_mark(a.trace, 1, true);
   if (!a.ctx_early && a.ctx) { slot = a.ctx[MDI_CTX_SLOT]; pos = a.ctx[MDI_CTX_POS]; }
-  stage_input(a.x + (size_t)slot * a.x_slot_stride, a.norm_w, a.eps, a.unit_offset, a.K, xs, red);
+  stage_input(a.x + (size_t)slot * a.x_slot_stride, a.norm_w, a.eps, a.unit_offset, a.K, xs, red, a.norm_b, a.layer_norm);
   trace_mark(a.trace, 2, false);
   pdl_launch_dependents();
 
@@ -631,7 +691,7 @@ __global__ void __launch_bounds__(LIN_THREADS, 3) stream_ldg_fp8_kernel(const St
   hop_wait(a.wait, a.ctx);
   trace_mark(a.trace, 1, true);
   const int slot = a.ctx ? a.ctx[MDI_CTX_SLOT] : 0, pos = a.ctx ? a.ctx[MDI_CTX_POS] : 0;
-  stage_input(a.x + (size_t)slot * a.x_slot_stride, a.norm_w, a.eps, a.unit_offset, a.K, xs, red);
+  stage_input(a.x + (size_t)slot * a.x_slot_stride, a.norm_w, a.eps, a.unit_offset, a.K, xs, red, a.norm_b, a.layer_norm);
   // activations to fp16 in place (same 2 bytes) for the HFMA2 inner product
   __half* xh16 = reinterpret_cast<__half*>(smem_raw);
   for (int i = threadIdx.x; i < a.K; i += LIN_THREADS) xh16[i] = __float2half_rn(__bfloat162float(xs[i]));
@@ -709,7 +769,7 @@ __global__ void __launch_bounds__(LIN_THREADS, 3) stream_bulk_fp8_kernel(const S
   hop_wait(a.wait, a.ctx);
   trace_mark(a.trace, 1, true);
   if (!a.ctx_early && a.ctx) { slot = a.ctx[MDI_CTX_SLOT]; pos = a.ctx[MDI_CTX_POS]; }
-  stage_input(a.x + (size_t)slot * a.x_slot_stride, a.norm_w, a.eps, a.unit_offset, a.K, xs, red);
+  stage_input(a.x + (size_t)slot * a.x_slot_stride, a.norm_w, a.eps, a.unit_offset, a.K, xs, red, a.norm_b, a.layer_norm);
   __half* xh16 = reinterpret_cast<__half*>(xs);  // activations to fp16 in place for the HFMA2 inner product
   for (int i = threadIdx.x; i < a.K; i += LIN_THREADS) xh16[i] = __float2half_rn(__bfloat162float(xs[i]));
   __syncthreads();
@@ -865,12 +925,13 @@ int mdi_linear_decode(const void* W, const void* W2, const void* bias, const voi
                       const float* wscale2, const int* dep_wait_flag, int* dep_signal_flag, unsigned int* dep_ctr,
                       void* hop_row, long long hop_slot_stride, const void* pf_a, const void* pf_b,
                       unsigned long long pf_bytes, int l2_pf_chunks, const void* hop_pre, long long hop_pre_slot_stride,
-                      int hop_pre_elems, cudaStream_t stream) {
+                      int hop_pre_elems, const void* norm_b, int layer_norm, cudaStream_t stream) {
   if (K % 8 != 0) return -2;
   if (hop_row && (out_fp32 || !signal_flag || !y)) return -2;
   StreamArgs a{};
   a.W = (const bf16*)W; a.W2 = (const bf16*)W2; a.bias = (const bf16*)bias; a.bias2 = (const bf16*)bias2;
   a.x = (const bf16*)x; a.norm_w = (const bf16*)norm_w; a.residual = (const bf16*)residual; a.y = y; a.ctx = ctx;
+  a.norm_b = (const bf16*)norm_b; a.layer_norm = layer_norm;
   a.x_slot_stride = x_slot_stride; a.res_slot_stride = res_slot_stride; a.y_slot_stride = y_slot_stride;
   a.N = N; a.K = K; a.eps = eps; a.unit_offset = unit_offset; a.act = act; a.out_fp32 = out_fp32;
   a.wait = HopWait{wait_flag, status, wait_max_cycles};
@@ -894,10 +955,11 @@ int mdi_qkv_decode(const void* W, const void* bias, const void* x, const void* n
                    int n_head, int n_groups, int head_size, int rope_n_elem, int max_seq, float eps,
                    int unit_offset, const int* wait_flag, int* status, long long wait_max_cycles, int ctas_per_sm,
                    int use_pdl, int variant, unsigned long long* trace, const float* wscale, const int* dep_wait_flag,
-                   int* dep_signal_flag, unsigned int* dep_ctr, cudaStream_t stream) {
+                   int* dep_signal_flag, unsigned int* dep_ctr, const void* norm_b, int layer_norm, cudaStream_t stream) {
   if (K % 8 != 0 || head_size % 2 != 0 || rope_n_elem % 2 != 0 || rope_n_elem > head_size) return -2;
   StreamArgs a{};
   a.W = (const bf16*)W; a.bias = (const bf16*)bias; a.x = (const bf16*)x; a.norm_w = (const bf16*)norm_w;
+  a.norm_b = (const bf16*)norm_b; a.layer_norm = layer_norm;
   a.cos = cos; a.sin = sin; a.q_out = (bf16*)q_out; a.kv = (bf16*)kv; a.ctx = ctx; a.x_slot_stride = x_slot_stride;
   a.K = K; a.N = (n_head + 2 * n_groups) * head_size;
   a.n_head = n_head; a.n_groups = n_groups; a.head_size = head_size; a.rope_n_elem = rope_n_elem;

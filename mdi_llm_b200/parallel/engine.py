@@ -31,22 +31,35 @@ from ..models.config import Config
 from ..models.stage import StageModule, StarterNode
 from .scheduler import SamplingParams, StageRunner
 
-__all__ = ["engine_supports", "FusedStage", "FusedStageRunner", "HopTarget"]
+__all__ = ["engine_supports", "fused_prefill_supports", "FusedStage", "FusedStageRunner", "HopTarget"]
 
 
 def engine_supports(config: Config, dtype: torch.dtype) -> bool:
-    """Architectures the fused decode kernels cover (the rest runs on the eager runner)."""
+    """Architectures the fused decode kernels cover (the rest runs on the eager runner): RMSNorm or LayerNorm,
+    sequential or parallel residual (with or without a shared attention norm), gated (SwiGLU / GeGLU) or plain
+    GELU MLPs, rotary (full or partial) or learned positions, head sizes 64 / 128 / 256 — i.e. the Llama, Mistral,
+    TinyLlama, Gemma, Pythia / GPT-NeoX, StableLM, GPT-2 families.  Not covered: mixture-of-experts MLPs, odd head
+    sizes (Phi: 80) and very wide GQA groups (Falcon-7B: 71 query heads per KV head)."""
     return (
         dtype == torch.bfloat16
-        and config.norm_class_name == "RMSNorm"
-        and not config.parallel_residual
-        and config.mlp_class_name in ("LLaMAMLP", "GemmaMLP")
-        and config.pos_embedding == "rope"
-        and config.head_size in (64, 128)
+        and config.norm_class_name in ("RMSNorm", "LayerNorm")
+        and config.mlp_class_name in ("LLaMAMLP", "GemmaMLP", "GptNeoxMLP")
+        and config.pos_embedding in ("rope", "learned")
+        and config.head_size in (64, 128, 256)
         and config.q_per_kv in (1, 2, 4, 8)
+        and not (config.head_size == 256 and config.q_per_kv > 2)
         and config.n_embd % 8 == 0 and config.intermediate_size % 8 == 0
-        and config.rope_n_elem % 2 == 0 and config.rope_n_elem > 0
+        and config.rope_n_elem % 2 == 0 and (config.rope_n_elem > 0 or config.pos_embedding == "learned")
+        and (config.parallel_residual or not config.shared_attention_norm)
     )
+
+
+def fused_prefill_supports(config: Config) -> bool:
+    """Prompt processing on the tcgen05 GEMM + attention kernels (the Llama-shaped subset); other covered
+    architectures prefill through their eager modules and decode through the fused kernels."""
+    return (config.norm_class_name == "RMSNorm" and not config.parallel_residual
+            and config.mlp_class_name in ("LLaMAMLP", "GemmaMLP") and config.pos_embedding == "rope" and config.rope_n_elem > 0
+            and config.head_size in (64, 128))
 
 
 @dataclass
@@ -158,6 +171,7 @@ class FusedStage:
             self._step_seq = 0  # host mirror of ctx[STEP] (device mode: advance_step counts the same steps)
             self.xa = torch.zeros(C, **bf)
             self.xb = torch.zeros(C, **bf)
+            self.xc = torch.zeros(C, **bf)  # third residual buffer: parallel-residual blocks keep x, x + attn and the output apart
             self.q = torch.zeros(cfg.n_head * cfg.head_size, **bf)
             self.y_attn = torch.zeros(cfg.n_head * cfg.head_size, **bf)
             self.h_mlp = torch.zeros(cfg.intermediate_size, **bf)
@@ -182,6 +196,7 @@ class FusedStage:
         self.weight_dtype = weight_dtype
         # prefill attention: "tcgen05" (hand-written flash attention, prompts start at position 0) or "sdpa"
         self.prefill_attn = os.environ.get("MDI_PREFILL_ATTN", "tcgen05")
+        self.fused_prefill = fused_prefill_supports(cfg)
         # decode hop: last-CTA row copy (one system-scope fence per step) or per-CTA remote stores + fences
         self.hop_copy = os.environ.get("MDI_HOP_COPY", "1") != "0"
         # MB of the MLP's gate / up weights that the attention output projection pulls into L2 while it waits for
@@ -208,6 +223,9 @@ class FusedStage:
         for blk in self.model.transformer.h:
             if getattr(blk, "has_attn", True):
                 lins += [blk.attn.attn, blk.attn.proj]
+            if hasattr(blk.mlp, "fc"):  # plain two-matrix MLP
+                lins += [blk.mlp.fc, blk.mlp.proj]
+                continue
             if getattr(blk, "has_gu", True):
                 lins += [blk.mlp.fc_1, blk.mlp.fc_2]
             if getattr(blk, "has_down", True):
@@ -248,6 +266,15 @@ class FusedStage:
         in flight before the input arrives), the big MLP matrices want more resident warps."""
         v = os.environ.get(f"MDI_VARIANT_{kernel.upper()}")
         return {"variant": int(v)} if v else {}
+
+    def _norm(self, norm: Any) -> Dict[str, Any]:
+        """Fused-prologue arguments for a norm module (RMSNorm, Gemma's unit-offset RMSNorm or LayerNorm)."""
+        if isinstance(norm, torch.nn.LayerNorm):
+            return dict(norm_w=norm.weight, norm_b=norm.bias, layer_norm=True, eps=norm.eps)
+        return dict(norm_w=norm.weight, eps=self.cfg.norm_eps, unit_offset=self.cfg.unit_offset_norm)
+
+    def _plain_act(self) -> str:
+        return "gelu_tanh" if self.cfg.gelu_approximate == "tanh" else "gelu_erf"
 
     def _gate_act(self) -> str:
         if self.cfg.mlp_class_name == "LLaMAMLP":
@@ -322,8 +349,7 @@ class FusedStage:
         m, cfg = self.model, self.cfg
         lw = self._w(m.lm_head)
         ops.linear_decode(
-            lw.pop("W"), self.hidden_in, self.logits, self.ctx, **lw,
-            norm_w=m.transformer.ln_f.weight, eps=cfg.norm_eps, unit_offset=cfg.unit_offset_norm,
+            lw.pop("W"), self.hidden_in, self.logits, self.ctx, **lw, **self._norm(m.transformer.ln_f),
             x_slot_stride=cfg.n_embd, wait_flag=self.flags.data_ptr() if wait else None,
             status=self.status.data_ptr(), wait_max_cycles=self.wait_max_cycles, ctas_per_sm=self._ctas("lm_head"),
             use_pdl=self.use_pdl, stats=self.sample_scratch if stats else None, trace=self._tr("lm_head"))
@@ -342,13 +368,16 @@ class FusedStage:
         m, cfg = self.model, self.cfg
         ops.embed(m.transformer.wte.weight, self.xa, self.ctx, tokens=self.tokens if from_tokens else None,
                   tok_slot_stride=self.tokens.shape[1], scale=float(cfg.n_embd ** 0.5) if cfg.scale_embeddings else 1.0,
-                  use_pdl=self.use_pdl)
+                  wpe=m.transformer.wpe.weight if "wpe" in m.transformer else None, use_pdl=self.use_pdl)
 
     def _units(self) -> List[Tuple[int, str]]:
         """The stage's work as residual sub-layers ``(local block, "attn" | "mlp" | "gu" | "down")`` — whole
         blocks contribute attn + mlp; a sub-layer pipeline boundary leaves a partial block (models/partition.py)."""
         out: List[Tuple[int, str]] = []
         for li, blk in enumerate(self.model.transformer.h):
+            if self.cfg.parallel_residual:
+                out.append((li, "par"))  # attention and MLP both read the block input: one indivisible unit
+                continue
             if getattr(blk, "has_attn", True):
                 out.append((li, "attn"))
             gu, down = getattr(blk, "has_gu", True), getattr(blk, "has_down", True)
@@ -375,7 +404,7 @@ class FusedStage:
         x_in, x_in_stride = (self.xa, 0) if self.is_starter else (self.hidden_in, W_in)
         common = dict(use_pdl=self.use_pdl)
         units = self._units()
-        n_kernels = sum({"attn": 3, "mlp": 2, "gu": 1, "down": 1}[k] for _, k in units)
+        n_kernels = sum({"attn": 3, "mlp": 2, "gu": 1, "down": 1, "par": 5}[k] for _, k in units)
         kidx = [0]
         st_kw = dict(status=self.status.data_ptr(), wait_max_cycles=self.wait_max_cycles)
 
@@ -408,45 +437,82 @@ class FusedStage:
             return kw
 
         self._last_x = None
+        plain_mlp = cfg.mlp_class_name == "GptNeoxMLP"
+
+        def attn_part(li: int, blk: Any, x_src: torch.Tensor, x_stride: int, first: bool, wait: Dict[str, Any]) -> None:
+            """QKV projection (+norm, RoPE, KV append) and split-KV attention of block ``li`` -> ``self.y_attn``."""
+            kv_layer = self.kv[li]
+            qw = self._w(blk.attn.attn)
+            ops.qkv_decode(
+                qw.pop("W"), x_src, self.model.cos, self.model.sin, self.q, kv_layer, self.ctx,
+                n_head=cfg.n_head, n_groups=cfg.n_query_groups, head_size=cfg.head_size,
+                rope_n_elem=cfg.rope_n_elem, max_seq=self.S, **self._norm(blk.norm_1), **qw, x_slot_stride=x_stride,
+                trace=self._tr(f"L{li}.qkv"), ctas_per_sm=self._ctas("qkv"), ctx_early=not first, **self._variant("qkv"),
+                **wait, **dep(), **common)
+            ops.attn_decode(self.q, kv_layer, self.y_attn, self.part, self.tickets, self.ctx, n_head=cfg.n_head,
+                            n_groups=cfg.n_query_groups, head_size=cfg.head_size, max_seq=self.S,
+                            n_split=self.n_split, use_pdl=self.use_pdl, trace=self._tr(f"L{li}.attn"), **st_kw, **dep())
+
+        def mlp_up(li: int, blk: Any, x_src: torch.Tensor, x_stride: int, norm: Any, first: bool, wait: Dict[str, Any],
+                   extra: Optional[Dict[str, Any]] = None) -> None:
+            """First MLP pass -> ``self.h_mlp`` (or the destination in ``extra``): gate/up with act(g) * u, or fc + GELU."""
+            kw = dict(**self._norm(norm), x_slot_stride=x_stride, ctas_per_sm=self._ctas("gate_up"), ctx_early=not first,
+                      **(wait if first else st_kw), **dep(), **common)
+            dst = extra if extra is not None else dict(trace=self._tr(f"L{li}.{'fc' if plain_mlp else 'gate_up'}"))
+            y = None if extra is not None else self.h_mlp
+            if plain_mlp:
+                fw = self._w(blk.mlp.fc)
+                ops.linear_decode(fw.pop("W"), x_src, y, self.ctx, **fw, act=self._plain_act(), **kw, **dst)
+            else:
+                gw = {**self._w(blk.mlp.fc_1), **self._w(blk.mlp.fc_2, second=True)}
+                ops.linear_decode(gw.pop("W"), x_src, y, self.ctx, **gw, act=self._gate_act(), **kw, **dst)
+
+        def free_buf(*busy: Any) -> torch.Tensor:
+            return next(b_ for b_ in (self.xa, self.xb, self.xc) if all(b_ is not o for o in busy))
+
         for ui, (li, kind) in enumerate(units):
             first, last = ui == 0, ui == len(units) - 1
             blk = self.model.transformer.h[li]
             wait = dict(wait_flag=self.flags.data_ptr() if (first and wait_input and not self.is_starter) else None, **st_kw)
-            x_out = self.xb if x_in is not self.xb else self.xa
+            x_out = free_buf(x_in)
             pf: Dict[str, Any] = {}
+            if kind == "par":
+                # parallel residual (model.py:596-629): out = x + attn(norm_1 x) + mlp(norm_2 x | norm_1 x)
+                attn_part(li, blk, x_in, x_in_stride, first, wait)
+                ow = self._w(blk.attn.proj)
+                x_mid = x_out
+                ops.linear_decode(ow.pop("W"), self.y_attn, x_mid, self.ctx, **ow, residual=x_in, res_slot_stride=x_in_stride,
+                                  ctx_early=True, ctas_per_sm=self._ctas("o_proj"), trace=self._tr(f"L{li}.o_proj"), **st_kw,
+                                  **dep(), **common)
+                mlp_up(li, blk, x_in, x_in_stride, blk.norm_1 if blk.norm_2 is None else blk.norm_2, False, wait)
+                x_out = free_buf(x_in, x_mid)
+                lw, src, name, ctas = self._w(blk.mlp.proj), dict(x=self.h_mlp), f"L{li}.down", self._ctas("down")
+                res = dict(residual=x_mid, res_slot_stride=0, ctx_early=True, ctas_per_sm=ctas, **st_kw, **dep())
+                w_out = lw.pop("W")
+                if not last:
+                    ops.linear_decode(w_out, src.pop("x"), x_out, self.ctx, **lw, **res, trace=self._tr(name), **common)
+                    x_in, x_in_stride = x_out, 0
+                else:
+                    ops.linear_decode(w_out, src.pop("x"), None, self.ctx, **lw, **res, **out_kw(name), **common)
+                continue
             if kind == "attn":
-                kv_layer = self.kv[li]
-                qw = self._w(blk.attn.attn)
-                ops.qkv_decode(
-                    qw.pop("W"), x_in, self.model.cos, self.model.sin, self.q, kv_layer, self.ctx,
-                    n_head=cfg.n_head, n_groups=cfg.n_query_groups, head_size=cfg.head_size,
-                    rope_n_elem=cfg.rope_n_elem, max_seq=self.S, norm_w=blk.norm_1.weight, **qw,
-                    eps=cfg.norm_eps, unit_offset=cfg.unit_offset_norm, x_slot_stride=x_in_stride,
-                    trace=self._tr(f"L{li}.qkv"), ctas_per_sm=self._ctas("qkv"), ctx_early=not first, **self._variant("qkv"),
-                    **wait, **dep(), **common)
-                ops.attn_decode(self.q, kv_layer, self.y_attn, self.part, self.tickets, self.ctx, n_head=cfg.n_head,
-                                n_groups=cfg.n_query_groups, head_size=cfg.head_size, max_seq=self.S,
-                                n_split=self.n_split, use_pdl=self.use_pdl, trace=self._tr(f"L{li}.attn"), **st_kw, **dep())
+                attn_part(li, blk, x_in, x_in_stride, first, wait)
                 lw, src, name, ctas = self._w(blk.attn.proj), dict(x=self.y_attn), f"L{li}.o_proj", self._ctas("o_proj")
                 pf.update(self._variant("o_proj"))
                 if self.pf_self_chunks:
                     pf["l2_pf_chunks"] = self.pf_self_chunks
-                if self.pf_next_mb > 0 and getattr(blk, "has_gu", False):
+                if self.pf_next_mb > 0 and getattr(blk, "has_gu", False) and not plain_mlp:
                     w1, w2 = self._w(blk.mlp.fc_1)["W"], self._w(blk.mlp.fc_2)["W"]
                     nbytes = min(int(self.pf_next_mb * 2 ** 20) // 2, w1.numel() * w1.element_size()) & ~4095
                     pf["prefetch"] = (w1.data_ptr(), w2.data_ptr(), nbytes)
-            if kind in ("mlp", "gu"):
-                gw = {**self._w(blk.mlp.fc_1), **self._w(blk.mlp.fc_2, second=True)}
-                gu_kw = dict(norm_w=blk.norm_2.weight, eps=cfg.norm_eps, unit_offset=cfg.unit_offset_norm, act=self._gate_act(),
-                             x_slot_stride=x_in_stride, ctas_per_sm=self._ctas("gate_up"), ctx_early=not first,
-                             **(wait if first else st_kw), **dep(), **common)
-                if kind == "gu":  # the stage ends here: out row = [x | h], x copied by the hop's last CTA
-                    assert last, "a gate/up-only unit is the last unit of its stage"
-                    self._last_x = (x_in, x_in_stride)
-                    ops.linear_decode(gw.pop("W"), x_in, None, self.ctx, **gw, **gu_kw,
-                                      **out_kw(f"L{li}.gate_up", n_pre=C, pre=(x_in, x_in_stride)))
-                    return
-                ops.linear_decode(gw.pop("W"), x_in, self.h_mlp, self.ctx, **gw, trace=self._tr(f"L{li}.gate_up"), **gu_kw)
+            if kind == "gu":  # the stage ends after the gate/up pass: out row = [x | h], x copied by the hop's last CTA
+                assert last, "a gate/up-only unit is the last unit of its stage"
+                self._last_x = (x_in, x_in_stride)
+                mlp_up(li, blk, x_in, x_in_stride, blk.norm_2, first, wait,
+                       extra=out_kw(f"L{li}.gate_up", n_pre=C, pre=(x_in, x_in_stride)))
+                return
+            if kind == "mlp":
+                mlp_up(li, blk, x_in, x_in_stride, blk.norm_2, first, wait)
                 lw, src, name, ctas = self._w(blk.mlp.proj), dict(x=self.h_mlp), f"L{li}.down", self._ctas("down")
                 pf.update(self._variant("down"))
             if kind == "down":  # the stage starts here: h and the residual are the two halves of the incoming row
@@ -481,6 +547,16 @@ class FusedStage:
         C = cfg.n_embd
         T = data.size(1)
         g_in = None
+        if not self.fused_prefill:
+            # architectures outside the tcgen05 prefill subset (LayerNorm / parallel residual / plain MLP / learned
+            # positions): the prompt goes through the eager modules on the SAME KV pool, decode stays fused
+            out = m(data.long() if self.is_starter else data.to(torch.bfloat16), input_pos, slot=slot).to(torch.bfloat16).contiguous()
+            if hop is None:
+                return out
+            ops.check(ops.lib().mdi_copy_signal(out.data_ptr(), hop[0], out.numel() * 2, hop[1], self.done_ctr.data_ptr(),
+                                                self.ctx.data_ptr(), self.status.data_ptr(), ops.stream_ptr()), "prefill hop (eager)")
+            self._keep = out  # the copy kernel reads it asynchronously
+            return None
         if self.is_starter:
             x = m.embed(data.long(), input_pos)[0].to(torch.bfloat16).contiguous()
         elif self.W_in > C:  # [x | h]: the stage starts at the down projection of a layer cut after gate/up

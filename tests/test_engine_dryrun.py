@@ -139,6 +139,48 @@ def test_flag_dependency_wiring_is_a_linear_chain():
     assert fs._step_seq == 0
 
 
+@pytest.mark.parametrize("kw,n_per_block", [
+    (dict(norm_class_name="LayerNorm", parallel_residual=True, shared_attention_norm=False, mlp_class_name="GptNeoxMLP", bias=True,
+          rotary_percentage=0.25), 5),
+    (dict(norm_class_name="LayerNorm", parallel_residual=True, shared_attention_norm=True, mlp_class_name="GptNeoxMLP"), 5),
+    (dict(norm_class_name="LayerNorm", parallel_residual=False, mlp_class_name="GptNeoxMLP", gelu_approximate="tanh", bias=True,
+          rotary_percentage=0.0, pos_embedding="learned", tie_embeddings=True), 5),
+])
+def test_decode_sequences_bind_for_neox_falcon_gpt2_shapes(kw, n_per_block):
+    """LayerNorm prologues, parallel-residual blocks (x, x + attn and the block output in three distinct buffers),
+    plain GELU MLPs and learned positions go through the same fused kernels."""
+    cfg = Config.from_name("tiny-llama-1.1b", n_layer=3, n_embd=256, n_head=4, n_query_groups=4, intermediate_size=128, vocab_size=120,
+                           padded_vocab_size=128, block_size=64, **kw)
+    assert eng.engine_supports(cfg, torch.bfloat16) and not eng.fused_prefill_supports(cfg)
+    with dry_ops() as calls:
+        st = build_stage(cfg, "starter", 3).to(torch.bfloat16)
+        st.max_seq_length = 32
+        fs = FusedStage(st, n_slots=2, max_seq_length=32)
+        fs.enqueue_head(wait=True)
+        fs.enqueue_sample()
+        fs.enqueue_embed(from_tokens=True)
+        assert (calls[-1][1]["wpe"] is not None) == (cfg.pos_embedding == "learned")
+        n0 = len(calls)
+        fs.enqueue_blocks(HopTarget(0x1000, 0x2000), wait_input=True)
+        seq = calls[n0:]
+    assert len(seq) == 3 * n_per_block
+    lin = [c[1] for c in seq if c[0] in ("linear_decode", "qkv_decode")]
+    assert all(c.get("layer_norm") for c in lin if c.get("norm_w") is not None)
+    assert all((c.get("norm_b") is not None) for c in lin if c.get("norm_w") is not None)
+    for n, args in seq:  # a kernel never writes the buffer it reads its input or residual from
+        if n == "linear_decode" and args.get("y") is not None:
+            assert args["y"] is not args.get("residual") and args["y"] is not args["x"]
+    if cfg.parallel_residual:
+        o_proj, fc, down = seq[2][1], seq[3][1], seq[4][1]
+        assert fc["x"] is o_proj["residual"]          # the MLP reads the block INPUT, not x + attn
+        assert down["residual"] is o_proj["y"]        # ... and its output is added to x + attn
+        assert (fc["norm_w"] is qkv_norm(seq)) == cfg.shared_attention_norm
+
+
+def qkv_norm(seq):
+    return seq[0][1]["norm_w"]
+
+
 def test_third_unit_stages_bind_and_route_the_wide_message():
     """Stage boundary between a gated MLP's gate/up and down projections: the upstream stage ends with the gate/up
     kernel (row [x | h]: h written behind x in out_local, x copied by the hop's last CTA), the downstream stage

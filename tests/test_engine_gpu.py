@@ -55,13 +55,26 @@ def _near_argmax_check(cfg, full_sd, tokens, prompt_len, tol=0.15):
     return (gap == 0).float().mean().item()
 
 
-@pytest.mark.parametrize("variant", ["gqa_hs64", "mha_hs128", "qpk8_bias", "gemma_like"])
+@pytest.mark.parametrize("variant", ["gqa_hs64", "mha_hs128", "qpk8_bias", "gemma_like", "pythia_like", "falcon_like", "gpt2_like",
+                                     "stablelm_like", "hs256"])
 def test_fused_runner_matches_eager_hidden_and_logits(variant):
     from mdi_llm_b200.parallel.engine import FusedStageRunner
     from mdi_llm_b200.parallel.scheduler import EagerStageRunner
 
     kw = {"gqa_hs64": dict(), "mha_hs128": dict(n_head=4, n_query_groups=4), "qpk8_bias": dict(n_head=8, n_query_groups=1, bias=True),
-          "gemma_like": dict(mlp_class_name="GemmaMLP", gelu_approximate="tanh", rotary_percentage=0.5)}[variant]
+          "gemma_like": dict(mlp_class_name="GemmaMLP", gelu_approximate="tanh", rotary_percentage=0.5),
+          # GPT-NeoX / Pythia: LayerNorm, parallel residual with two norms, plain GELU MLP, biases, partial rotary
+          "pythia_like": dict(norm_class_name="LayerNorm", parallel_residual=True, shared_attention_norm=False, mlp_class_name="GptNeoxMLP",
+                              bias=True, rotary_percentage=0.25, n_query_groups=8),
+          # Falcon-style block: parallel residual with ONE shared norm, MQA-ish groups
+          "falcon_like": dict(norm_class_name="LayerNorm", parallel_residual=True, shared_attention_norm=True, mlp_class_name="GptNeoxMLP",
+                              bias=False, n_query_groups=1),
+          # GPT-2: LayerNorm, sequential residual, plain tanh-GELU MLP, learned positions, tied head, biases, no rotary
+          "gpt2_like": dict(norm_class_name="LayerNorm", parallel_residual=False, mlp_class_name="GptNeoxMLP", gelu_approximate="tanh",
+                            bias=True, rotary_percentage=0.0, pos_embedding="learned", tie_embeddings=True, n_query_groups=8),
+          # StableLM-style: LayerNorm + gated MLP + partial rotary, sequential residual
+          "stablelm_like": dict(norm_class_name="LayerNorm", rotary_percentage=0.25),
+          "hs256": dict(n_head=2, n_query_groups=1, head_size=256)}[variant]
     cfg = _cfg(**kw)
     _, (st_a,) = _stages(cfg, 1)
     _, (st_b,) = _stages(cfg, 1)
