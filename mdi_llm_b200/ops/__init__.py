@@ -18,7 +18,7 @@ import torch
 from . import build as _build
 
 __all__ = ["lib", "available", "require", "OpsError", "ptr", "stream_ptr", "check", "ACT", "CTX_INTS",
-           "linear_decode", "qkv_decode", "attn_decode", "gemm", "sample_fast", "sample_scratch", "stamp", "POISON", "embed", "rmsnorm_rows", "sample", "advance_step",
+           "linear_decode", "qkv_decode", "attn_decode", "gemm", "gemm_fp8", "quantize_rows_fp8", "sample_fast", "sample_scratch", "stamp", "POISON", "embed", "rmsnorm_rows", "sample", "advance_step",
            "CudaGraph"]
 
 CTX_SLOT, CTX_POS, CTX_WAIT, CTX_SIGNAL, CTX_TOKEN, CTX_STEP = 0, 1, 2, 3, 4, 5
@@ -56,6 +56,8 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.mdi_gemm_bf16.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp]
     lib.mdi_gemm_bf16_ex.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp,
                                      i32, i32, i32, i32, vp]
+    lib.mdi_gemm_fp8.argtypes = [vp, vp, i64, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp]
+    lib.mdi_quantize_rows_fp8.argtypes = [vp, vp, vp, i32, i32, i64, vp]
     lib.mdi_attn_prefill.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp]
     lib.mdi_set_prefill_attn_pipe.argtypes = [i32]
     lib.mdi_get_prefill_attn_pipe.restype = i32
@@ -316,6 +318,55 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] = Non
     check(lib().mdi_gemm_bf16_ex(ptr(a), ptr(w), ptr(w2), c_ptr, ptr(bias), ptr(bias2), ptr(residual), M, N, K,
                                  ACT[act] if w2 is not None else 0, block_n, signal_flag, ptr(done_ctr), ptr(ctx),
                                  ptr(status), *_knobs, stream_ptr()), "gemm_bf16 (tcgen05)")
+    return out
+
+
+def quantize_rows_fp8(x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Per-token block quantisation of activations for the fp8 GEMM: ``x [M, K]`` bf16 -> (``q [M, K]`` e4m3 as
+    uint8, ``scale_t [K/128, M_pad]`` fp32, transposed so that the GEMM's promotion warps read it coalesced)."""
+    _bf16(x, "x")
+    M, K = x.shape
+    if K % 128:
+        raise OpsError("quantize_rows_fp8: K must be a multiple of 128")
+    m_pad = (M + 127) // 128 * 128
+    q = torch.empty(M, K, dtype=torch.uint8, device=x.device)
+    scale_t = torch.zeros(K // 128, m_pad, dtype=torch.float32, device=x.device)
+    check(lib().mdi_quantize_rows_fp8(ptr(x), ptr(q), ptr(scale_t), M, K, m_pad, stream_ptr()), "quantize_rows_fp8")
+    return q, scale_t
+
+
+def gemm_fp8(a8: torch.Tensor, a_scale_t: torch.Tensor, w8: torch.Tensor, w_scale_t: torch.Tensor, *,
+             bias: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+             w2_8: Optional[torch.Tensor] = None, w2_scale_t: Optional[torch.Tensor] = None, bias2: Optional[torch.Tensor] = None,
+             act: str = "silu_gate", out_ptr: Optional[int] = None, signal_flag: Optional[int] = None,
+             done_ctr: Optional[torch.Tensor] = None, ctx: Optional[torch.Tensor] = None,
+             status: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
+    """Block-scaled fp8 GEMM on ``tcgen05.mma kind::f8f6f4`` (csrc/gemm_fp8_tcgen05.cu): e4m3 operands, one fp32
+    scale per 128 K elements per row on both sides (``*_scale_t`` are the TRANSPOSED scale tables ``[K/128, rows]``),
+    every K block accumulated in a fresh TMEM partial and folded into fp32 registers with its scales.  bf16 output
+    with the same bias / residual / gated-activation / fused-hop epilogues as :func:`gemm`."""
+    for t, n in ((a8, "a8"), (w8, "w8"), (w2_8, "w2_8")):
+        if t is not None and (t.element_size() != 1 or not t.is_cuda or not t.is_contiguous()):
+            raise OpsError(f"gemm_fp8: {n} must be a contiguous CUDA 1-byte (e4m3) tensor")
+    _bf16(bias, "bias"); _bf16(residual, "residual"); _bf16(bias2, "bias2")
+    M, K = a8.shape
+    N = w8.shape[0]
+    if w8.shape[1] != K or K % 128 or (w2_8 is not None and tuple(w2_8.shape) != tuple(w8.shape)):
+        raise OpsError(f"gemm_fp8: operand shapes differ or K not a multiple of 128 ({tuple(a8.shape)} x {tuple(w8.shape)})")
+    nkb = K // 128
+    if tuple(w_scale_t.shape) != (nkb, N) or a_scale_t.shape[0] != nkb or a_scale_t.shape[1] < M or a_scale_t.dtype != torch.float32:
+        raise OpsError("gemm_fp8: scale tables must be fp32 [K/128, rows] (transposed)")
+    if w2_8 is not None and (w2_scale_t is None or tuple(w2_scale_t.shape) != (nkb, N)):
+        raise OpsError("gemm_fp8: gated mode needs w2_scale_t [K/128, N]")
+    if out_ptr is None:
+        if out is None:
+            out = torch.empty(M, N, device=a8.device, dtype=torch.bfloat16)
+        c_ptr = ptr(out)
+    else:
+        c_ptr, out = out_ptr, None
+    check(lib().mdi_gemm_fp8(ptr(a8), ptr(a_scale_t), a_scale_t.shape[1], ptr(w8), ptr(w_scale_t), ptr(w2_8), ptr(w2_scale_t),
+                             c_ptr, ptr(bias), ptr(bias2), ptr(residual), M, N, K, ACT[act] if w2_8 is not None else 0,
+                             signal_flag, ptr(done_ctr), ptr(ctx), ptr(status), stream_ptr()), "gemm_fp8 (tcgen05 f8f6f4)")
     return out
 
 

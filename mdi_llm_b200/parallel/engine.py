@@ -204,6 +204,7 @@ class FusedStage:
         self.pf_next_mb = float(os.environ.get("MDI_PF_NEXT_MB", "0"))
         self.pf_self_chunks = int(os.environ.get("MDI_PF_SELF_CHUNKS", "0"))
         self._q: Dict[int, Tuple[torch.Tensor, torch.Tensor]] = {}  # id(linear) -> (fp8 weight, block scales)
+        self._qt: Dict[int, torch.Tensor] = {}  # id(linear) -> transposed block scales [K/128, N] for the prefill GEMM
         if weight_dtype == "fp8":
             self._quantize(free_bf16)
         elif weight_dtype != "bf16":
@@ -235,6 +236,7 @@ class FusedStage:
         with torch.cuda.device(self.device):
             for lin in lins:
                 self._q[id(lin)] = quantize_fp8_block(lin.weight.data)
+                self._qt[id(lin)] = self._q[id(lin)][1].t().contiguous()
                 if free_bf16:
                     lin.weight.data = torch.empty(0, dtype=torch.bfloat16, device=self.device)
 
@@ -245,14 +247,21 @@ class FusedStage:
             return dict(W2=lin.weight, bias2=lin.bias) if q is None else dict(W2=q[0], wscale2=q[1], bias2=lin.bias)
         return dict(W=lin.weight, bias=lin.bias) if q is None else dict(W=q[0], wscale=q[1], bias=lin.bias)
 
-    def _dense(self, lin: Any) -> torch.Tensor:
-        """bf16 weight matrix for the prefill GEMM (dequantised scratch in fp8 mode)."""
+    def _gemm(self, a: torch.Tensor, lin: Any, lin2: Any = None, **kw: Any) -> Optional[torch.Tensor]:
+        """One prefill projection on the tensor cores: bf16 weights -> ``ops.gemm`` (kind::f16); fp8 block-scaled
+        weights -> activations quantised per token and ``ops.gemm_fp8`` (kind::f8f6f4, scales folded in per
+        128-element K block) — the fp8 checkpoint is never expanded to bf16.  ``lin2``: gated MLP in one pass."""
         q = self._q.get(id(lin))
         if q is None:
-            return lin.weight
-        from ..utils.quantize import dequantize_fp8_block
-
-        return dequantize_fp8_block(q[0], q[1], torch.bfloat16)
+            if lin2 is not None:
+                kw.update(w2=lin2.weight, bias2=lin2.bias)
+            return ops.gemm(a, lin.weight, bias=lin.bias, **kw)
+        kw.pop("block_n", None)
+        a8, a_s = ops.quantize_rows_fp8(a)
+        if lin2 is not None:
+            q2 = self._q[id(lin2)]
+            kw.update(w2_8=q2[0], w2_scale_t=self._qt[id(lin2)], bias2=lin2.bias)
+        return ops.gemm_fp8(a8, a_s, q[0], self._qt[id(lin)], bias=lin.bias, **kw)
 
     def _ctas(self, kernel: str) -> int:
         """CTAs per SM for one of the decode linears; ``MDI_CTAS_<KERNEL>`` (e.g. ``MDI_CTAS_GATE_UP=-256``:
@@ -575,16 +584,16 @@ class FusedStage:
 
         def out_gemm(a_in: torch.Tensor, lin: Any, last: bool) -> Optional[torch.Tensor]:
             if hop is not None and last:
-                ops.gemm(a_in, self._dense(lin), bias=lin.bias, residual=x, out_ptr=hop[0], signal_flag=hop[1],
-                         done_ctr=self.done_ctr, ctx=self.ctx, status=self.status, block_n=bn)
+                self._gemm(a_in, lin, residual=x, out_ptr=hop[0], signal_flag=hop[1], done_ctr=self.done_ctr, ctx=self.ctx,
+                           status=self.status, block_n=bn)
                 return None
-            return ops.gemm(a_in, self._dense(lin), bias=lin.bias, residual=x, block_n=bn)
+            return self._gemm(a_in, lin, residual=x, block_n=bn)
 
         for ui, (li, kind) in enumerate(units):
             blk, last = m.transformer.h[li], ui == len(units) - 1
             if kind == "attn":
                 h = ops.rmsnorm_rows(x, blk.norm_1.weight, eps, uo)
-                qkv = ops.gemm(h, self._dense(blk.attn.attn), bias=blk.attn.attn.bias, block_n=bn)
+                qkv = self._gemm(h, blk.attn.attn, block_n=bn)
                 if use_fa:  # RoPE + KV append + causal flash attention with S / P.V in TMEM
                     y = ops.attn_prefill(qkv, m.cos, m.sin, self.kv[li], slot, n_head=cfg.n_head,
                                          n_groups=cfg.n_query_groups, head_size=cfg.head_size, rope_n_elem=cfg.rope_n_elem)
@@ -595,8 +604,7 @@ class FusedStage:
                 x = out_gemm(g_in, blk.mlp.proj, last)
             else:
                 h = ops.rmsnorm_rows(x, blk.norm_2.weight, eps, uo)
-                g = ops.gemm(h, self._dense(blk.mlp.fc_1), bias=blk.mlp.fc_1.bias, w2=self._dense(blk.mlp.fc_2),
-                             bias2=blk.mlp.fc_2.bias, act=self._gate_act())
+                g = self._gemm(h, blk.mlp.fc_1, blk.mlp.fc_2, act=self._gate_act())
                 if kind == "gu":  # the stage ends here: [x | h] travels (copy + in-kernel flag release)
                     out = torch.cat((x, g), dim=1)
                     if hop is None:

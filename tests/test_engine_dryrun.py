@@ -16,7 +16,7 @@ from mdi_llm_b200.parallel import engine as eng
 from mdi_llm_b200.parallel.engine import FusedStage, HopTarget
 
 KERNELS = ["linear_decode", "qkv_decode", "attn_decode", "embed", "sample_fast", "advance_step", "rmsnorm_rows", "gemm",
-           "attn_prefill"]
+           "attn_prefill", "gemm_fp8", "quantize_rows_fp8"]
 
 
 def _cfg(n_layer=3):
@@ -41,6 +41,10 @@ def dry_ops():
                 return torch.zeros(a[0].shape[0], a[1].shape[0], dtype=torch.bfloat16)
             if _n == "rmsnorm_rows":
                 return torch.zeros_like(a[0])
+            if _n == "quantize_rows_fp8":
+                return torch.zeros(a[0].shape, dtype=torch.uint8), torch.zeros(a[0].shape[1] // 128, 128)
+            if _n == "gemm_fp8":
+                return None if kw.get("out_ptr") is not None else torch.zeros(a[0].shape[0], a[2].shape[0], dtype=torch.bfloat16)
             if _n == "attn_prefill":
                 return torch.zeros(a[0].shape[0], kw["n_head"] * kw["head_size"], dtype=torch.bfloat16)
             return None

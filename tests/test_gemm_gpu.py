@@ -95,3 +95,82 @@ def test_gemm_fused_hop_signal_local():
     assert flags.tolist() == [0, 0, 7, 0] and int(ctr) == 0
     ref = (a.float() @ w.float().T).bfloat16().float() + res.float()
     torch.testing.assert_close(dst.float(), ref, rtol=2e-2, atol=6e-2)
+
+
+def _deq_rows(q8, scale_t, M):
+    """e4m3 bytes + transposed block scales -> fp32."""
+    K = q8.shape[1]
+    return (q8.view(torch.float8_e4m3fn).float().view(M, K // 128, 128) * scale_t[:, :M].t().unsqueeze(-1)).view(M, K)
+
+
+def test_quantize_rows_fp8_matches_torch():
+    from mdi_llm_b200 import ops
+
+    ops.require()
+    torch.manual_seed(0)
+    x = (torch.randn(70, 512, device="cuda") * 3).bfloat16()
+    x[3] = 0  # an all-zero row keeps scale 1 and zeros
+    q, st = ops.quantize_rows_fp8(x)
+    assert q.shape == (70, 512) and st.shape == (4, 128)
+    xf = x.float().view(70, 4, 128)
+    scale = xf.abs().amax(-1) / 448.0
+    scale = torch.where(scale > 0, scale, torch.ones_like(scale))
+    torch.testing.assert_close(st[:, :70].t(), scale, rtol=1e-6, atol=0)
+    ref = (xf / scale.unsqueeze(-1)).clamp(-448, 448).to(torch.float8_e4m3fn).view(70, 512)
+    assert (q.view(torch.float8_e4m3fn).float() - ref.float()).abs().max().item() <= 32.0 * 0.07  # <= 1 ulp at the top binade
+    assert (q.view(torch.float8_e4m3fn).float() == ref.float()).float().mean().item() > 0.99
+
+
+@pytest.mark.parametrize("M,N,K,bias,res", [(128, 128, 128, False, False), (200, 384, 512, True, True), (64, 4096, 4096, False, True),
+                                             (300, 1000, 1792, True, False), (1024, 6144, 4096, False, False)])
+def test_gemm_fp8_blockscaled_matches_dequantised_reference(M, N, K, bias, res):
+    """tcgen05.mma kind::f8f6f4 with per-128-K block scales on both operands against the same product computed in
+    fp32 from the dequantised operands (identical rounding of the inputs, only the accumulation order differs)."""
+    from mdi_llm_b200 import ops
+    from mdi_llm_b200.utils.quantize import dequantize_fp8_block, quantize_fp8_block
+
+    ops.require()
+    torch.manual_seed(1)
+    a = (torch.randn(M, K, device="cuda") * 0.7).bfloat16()
+    w = (torch.randn(N, K, device="cuda") * 0.05).bfloat16()
+    w[:, 128:256] *= 8.0 if K > 128 else 1.0  # block scales that really differ along K
+    b = (torch.randn(N, device="cuda") * 0.3).bfloat16() if bias else None
+    r = (torch.randn(M, N, device="cuda") * 0.5).bfloat16() if res else None
+    q, s = quantize_fp8_block(w)
+    a8, a_st = ops.quantize_rows_fp8(a)
+    out = ops.gemm_fp8(a8, a_st, q.view(torch.uint8), s.t().contiguous(), bias=b, residual=r)
+    ref = _deq_rows(a8, a_st, M) @ dequantize_fp8_block(q, s, torch.float32).t()
+    if b is not None:
+        ref = ref + b.float()
+    ref = ref.bfloat16().float()
+    if r is not None:
+        ref = ref + r.float()
+    err = (out.float() - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    assert err <= 0.01 * scale + 0.02, f"max err {err} (scale {scale})"
+    # and it is a faithful fp8 GEMM of the ORIGINAL operands (quantisation error only)
+    full = a.float() @ w.float().t() + (b.float() if b is not None else 0) + (r.float() if r is not None else 0)
+    assert (out.float() - full).norm().item() <= 0.06 * full.norm().item()
+
+
+@pytest.mark.parametrize("M,I,K", [(128, 64, 128), (130, 448, 512), (512, 3584, 4096)])
+def test_gemm_fp8_gated_mlp_one_pass(M, I, K):
+    """SwiGLU in one fp8 GEMM: fc_1 and fc_2 rows share a B tile, act(g) * u in the epilogue."""
+    from mdi_llm_b200 import ops
+    from mdi_llm_b200.utils.quantize import dequantize_fp8_block, quantize_fp8_block
+
+    ops.require()
+    torch.manual_seed(2)
+    a = (torch.randn(M, K, device="cuda") * 0.6).bfloat16()
+    w1 = (torch.randn(I, K, device="cuda") * 0.05).bfloat16()
+    w2 = (torch.randn(I, K, device="cuda") * 0.05).bfloat16()
+    (q1, s1), (q2, s2) = quantize_fp8_block(w1), quantize_fp8_block(w2)
+    a8, a_st = ops.quantize_rows_fp8(a)
+    out = ops.gemm_fp8(a8, a_st, q1.view(torch.uint8), s1.t().contiguous(), w2_8=q2.view(torch.uint8), w2_scale_t=s2.t().contiguous(),
+                       act="silu_gate")
+    ad = _deq_rows(a8, a_st, M)
+    g = (ad @ dequantize_fp8_block(q1, s1, torch.float32).t()).bfloat16().float()
+    u = (ad @ dequantize_fp8_block(q2, s2, torch.float32).t()).bfloat16().float()
+    ref = torch.nn.functional.silu(g).bfloat16().float() * u
+    err = (out.float() - ref).abs().max().item()
+    assert out.shape == (M, I) and err <= 0.02 * ref.abs().max().item() + 0.02, err
