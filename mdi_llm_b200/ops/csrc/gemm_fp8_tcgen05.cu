@@ -7,10 +7,10 @@
 // same way per token.  Scales change every 128 K elements, so the tensor core cannot accumulate the whole K
 // range in one go: every K block (= one 128-byte shared-memory slab = 4 MMAs of K = 32) is accumulated into a
 // FRESH partial accumulator in TMEM, and "promotion" warps fold it into fp32 register accumulators with the
-// block's scales while the tensor core already works on the next block in the other TMEM buffer:
+// block's scales while the tensor core already works on the next blocks in the other TMEM buffers (4 x 128 columns):
 //
 //   warp 0      TMA producer: A8 / W8 tiles (128 rows x 128 B, SWIZZLE_128B) -> 5-stage shared-memory ring
-//   warp 1      MMA issuer: per K block 4 x tcgen05.mma.kind::f8f6f4 (M=128, N=128, K=32) into partial buffer kb & 1,
+//   warp 1      MMA issuer: per K block 4 x tcgen05.mma.kind::f8f6f4 (M=128, N=128, K=32) into one of 4 partial buffers,
 //               tcgen05.commit -> "stage free" and "partial full"
 //   warp 2      TMEM allocator
 //   warps 4-11  promotion + epilogue: tcgen05.ld (warpgroup 0: columns 0-63, warpgroup 1: columns 64-127),
@@ -30,6 +30,29 @@ constexpr int F8_BM = 128, F8_BN = 128, F8_BK = 128;  // BK in elements == bytes
 constexpr int F8_STAGES = 5;
 constexpr int F8_THREADS = 384;
 constexpr int F8_TILE_BYTES = F8_BM * F8_BK;  // 16 KB (A) and 16 KB (B) per stage
+// Block scales travel with the tiles: per K block 128 weight-column scales + 128 activation-row scales (2 x 512 B bulk
+// copies onto the stage's "full" barrier) into a small ring of their own.  A scale slot outlives its tile stage — the
+// promotion warps still read it after the MMAs have released the stage — so the ring is 3 slots deeper: stage reuse
+// means MMA(it - STAGES) retired, hence promotion(it - STAGES - PBUF) has started, hence promotion(it - STAGES - PBUF - 1) is done.
+constexpr int F8_PBUF = 4;  // partial accumulators in TMEM (4 x 128 columns = all 512): depth of the MMA <-> promotion pipeline
+constexpr int F8_SCALE_SLOTS = F8_STAGES + F8_PBUF + 1;
+
+// packed fp32 pair arithmetic (sm_100: FFMA2 / FMUL2 — two lanes per issue slot)
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+  return (unsigned long long)__float_as_uint(lo) | ((unsigned long long)__float_as_uint(hi) << 32);
+}
+__device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigned long long b) {
+  unsigned long long d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ float lo32(unsigned long long v) { return __uint_as_float((uint32_t)v); }
+__device__ __forceinline__ float hi32(unsigned long long v) { return __uint_as_float((uint32_t)(v >> 32)); }
 
 struct Fp8GemmParams {
   CUtensorMap tma_a;   // A8  [M, K] uint8, box 128 x 128
@@ -69,12 +92,14 @@ __global__ void __launch_bounds__(F8_THREADS, 1) gemm_fp8_blockscaled_kernel(con
   unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(f8_smem) + 1023) & ~uintptr_t(1023));
   unsigned char* smem_a = base;
   unsigned char* smem_b = base + F8_STAGES * F8_TILE_BYTES;
-  float* xchg = reinterpret_cast<float*>(smem_b + F8_STAGES * F8_TILE_BYTES);  // gated: u hand-over [128 rows][64]
+  float* sc_w = reinterpret_cast<float*>(smem_b + F8_STAGES * F8_TILE_BYTES);  // [F8_SCALE_SLOTS][128] weight-column scales
+  float* sc_a = sc_w + F8_SCALE_SLOTS * 128;                                    // [F8_SCALE_SLOTS][128] activation-row scales
+  float* xchg = sc_a + F8_SCALE_SLOTS * 128;  // gated: u hand-over [128 rows][64]
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(xchg) + (GATED ? F8_BM * 64 * 4 : 0));
   uint64_t* empty_bar = full_bar + F8_STAGES;
-  uint64_t* pfull_bar = empty_bar + F8_STAGES;  // [2] partial accumulator complete
-  uint64_t* pempty_bar = pfull_bar + 2;         // [2] partial accumulator drained (8 promotion warps)
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(pempty_bar + 2);
+  uint64_t* pfull_bar = empty_bar + F8_STAGES;   // [PBUF] partial accumulator complete
+  uint64_t* pempty_bar = pfull_bar + F8_PBUF;    // [PBUF] partial accumulator drained (8 promotion warps)
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(pempty_bar + F8_PBUF);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_cols = GATED ? 64 : F8_BN;  // output columns per tile
@@ -90,11 +115,11 @@ __global__ void __launch_bounds__(F8_THREADS, 1) gemm_fp8_blockscaled_kernel(con
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < F8_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&pfull_bar[b], 1); mbar_init(&pempty_bar[b], 8); }
+    for (int b = 0; b < F8_PBUF; ++b) { mbar_init(&pfull_bar[b], 1); mbar_init(&pempty_bar[b], 8); }
     mbar_fence_init();
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "n"(2 * F8_BN) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "n"(F8_PBUF * F8_BN) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tcgen05_fence_before();
@@ -109,9 +134,14 @@ __global__ void __launch_bounds__(F8_THREADS, 1) gemm_fp8_blockscaled_kernel(con
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int m0 = (tile % tiles_m) * F8_BM, n0 = (tile / tiles_m) * n_cols;
         for (int kb = 0; kb < nkb; ++kb, ++it) {
-          const int s = it % F8_STAGES;
+          const int s = it % F8_STAGES, sl = it % F8_SCALE_SLOTS;
           mbar_wait(&empty_bar[s], ((it / F8_STAGES) & 1) ^ 1);
-          mbar_expect_tx(&full_bar[s], 2 * F8_TILE_BYTES);
+          const int wn = min(n_cols, p.N - n0);  // valid output columns of this tile (N % 4 == 0: 16-byte copies)
+          const uint32_t wbytes = (uint32_t)((GATED ? 2 : 1) * wn * 4);
+          mbar_expect_tx(&full_bar[s], 2 * F8_TILE_BYTES + 512u + wbytes);
+          bulk_g2s(sc_a + sl * 128, p.a_scale_t + (size_t)kb * p.ld_as + m0, 512u, &full_bar[s]);
+          bulk_g2s(sc_w + sl * 128, p.w_scale_t + (size_t)kb * p.N + n0, (uint32_t)(wn * 4), &full_bar[s]);
+          if (GATED) bulk_g2s(sc_w + sl * 128 + 64, p.w2_scale_t + (size_t)kb * p.N + n0, (uint32_t)(wn * 4), &full_bar[s]);
           tma_load_2d(smem_a + s * F8_TILE_BYTES, &p.tma_a, &full_bar[s], kb * F8_BK, m0);
           if (GATED) {  // rows 0-63 of the B tile: fc_1[n0 : n0+64], rows 64-127: fc_2[n0 : n0+64]
             tma_load_2d(smem_b + s * F8_TILE_BYTES, &p.tma_b, &full_bar[s], kb * F8_BK, n0);
@@ -128,8 +158,8 @@ __global__ void __launch_bounds__(F8_THREADS, 1) gemm_fp8_blockscaled_kernel(con
     int it = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       for (int kb = 0; kb < nkb; ++kb, ++it) {
-        const int s = it % F8_STAGES, pb = it & 1;
-        mbar_wait(&pempty_bar[pb], ((it >> 1) & 1) ^ 1);  // promotion warps are done with this buffer
+        const int s = it % F8_STAGES, pb = it % F8_PBUF;
+        mbar_wait(&pempty_bar[pb], ((it / F8_PBUF) & 1) ^ 1);  // promotion warps are done with this buffer
         mbar_wait(&full_bar[s], (it / F8_STAGES) & 1);
         tcgen05_fence_after();
         if (lane == 0) {
@@ -152,17 +182,12 @@ __global__ void __launch_bounds__(F8_THREADS, 1) gemm_fp8_blockscaled_kernel(con
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const int m0 = (tile % tiles_m) * F8_BM, n0 = (tile / tiles_m) * n_cols;
       const int row = m0 + lg * 32 + lane;
-      // scale column of my 64 accumulator columns: plain -> w[n0 + 64*half + j]; gated -> half 0: fc_1, half 1: fc_2, both [n0 + j]
-      const float* ws_base = (GATED && half) ? p.w2_scale_t : p.w_scale_t;
-      const int wcol0 = GATED ? n0 : n0 + 64 * half;
-      float acc[64];
+      unsigned long long acc2[32];  // 64 fp32 accumulators as 32 packed pairs
 #pragma unroll
-      for (int j = 0; j < 64; ++j) acc[j] = 0.f;
+      for (int j = 0; j < 32; ++j) acc2[j] = 0ull;
       for (int kb = 0; kb < nkb; ++kb, ++it) {
-        const int pb = it & 1;
-        const float a_s = (row < p.M) ? __ldg(p.a_scale_t + (size_t)kb * p.ld_as + row) : 0.f;
-        const float* ws = ws_base + (size_t)kb * p.N + wcol0;
-        mbar_wait(&pfull_bar[pb], (it >> 1) & 1);
+        const int pb = it % F8_PBUF, sl = it % F8_SCALE_SLOTS;
+        mbar_wait(&pfull_bar[pb], (it / F8_PBUF) & 1);  // MMAs of this K block retired => its stage (tiles AND scales) had landed
         tcgen05_fence_after();
         const uint32_t taddr = tmem_base + (uint32_t)(pb * F8_BN + 64 * half) + ((uint32_t)(lg * 32) << 16);
         uint32_t t0[32], t1[32];
@@ -171,14 +196,21 @@ __global__ void __launch_bounds__(F8_THREADS, 1) gemm_fp8_blockscaled_kernel(con
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&pempty_bar[pb]);  // the tensor core may overwrite this buffer
+        const float a_s = sc_a[sl * 128 + lg * 32 + lane];
+        const unsigned long long a2 = pack2(a_s, a_s);
+        const float4* ws4 = reinterpret_cast<const float4*>(sc_w + sl * 128 + 64 * half);  // broadcast reads
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float s0 = (wcol0 + j < p.N) ? __ldg(ws + j) * a_s : 0.f;
-          const float s1 = (wcol0 + 32 + j < p.N) ? __ldg(ws + 32 + j) * a_s : 0.f;
-          acc[j] = fmaf(__uint_as_float(t0[j]), s0, acc[j]);
-          acc[32 + j] = fmaf(__uint_as_float(t1[j]), s1, acc[32 + j]);
+        for (int j = 0; j < 8; ++j) {
+          const float4 w0 = ws4[j], w1 = ws4[8 + j];
+          acc2[2 * j] = fma2(pack2(__uint_as_float(t0[4 * j]), __uint_as_float(t0[4 * j + 1])), mul2(pack2(w0.x, w0.y), a2), acc2[2 * j]);
+          acc2[2 * j + 1] = fma2(pack2(__uint_as_float(t0[4 * j + 2]), __uint_as_float(t0[4 * j + 3])), mul2(pack2(w0.z, w0.w), a2), acc2[2 * j + 1]);
+          acc2[16 + 2 * j] = fma2(pack2(__uint_as_float(t1[4 * j]), __uint_as_float(t1[4 * j + 1])), mul2(pack2(w1.x, w1.y), a2), acc2[16 + 2 * j]);
+          acc2[16 + 2 * j + 1] = fma2(pack2(__uint_as_float(t1[4 * j + 2]), __uint_as_float(t1[4 * j + 3])), mul2(pack2(w1.z, w1.w), a2), acc2[16 + 2 * j + 1]);
         }
       }
+      float acc[64];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) { acc[2 * j] = lo32(acc2[j]); acc[2 * j + 1] = hi32(acc2[j]); }
       // ---- epilogue ----
       if (GATED) {
         // warpgroup 1 holds u (fc_2), warpgroup 0 holds g (fc_1) for the same 64 output columns
@@ -253,7 +285,7 @@ __global__ void __launch_bounds__(F8_THREADS, 1) gemm_fp8_blockscaled_kernel(con
   __syncthreads();
   if (warp == 2) {
     tcgen05_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * F8_BN) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(F8_PBUF * F8_BN) : "memory");
   }
   hop_signal(p.signal, p.ctx);
 }
@@ -324,7 +356,9 @@ extern "C" int mdi_gemm_fp8(const void* A8, const float* a_scale_t, long long ld
   if (rc) return rc;
   rc = make_map_u8(&p.tma_b2, gated ? W2_8 : W8, N, K, gated ? 64 : F8_BN);
   if (rc) return rc;
-  const size_t smem = 1024 + (size_t)F8_STAGES * 2 * F8_TILE_BYTES + (gated ? (size_t)F8_BM * 64 * 4 : 0) + 256;
+  if (N % 4 != 0) return -2;  // scale rows are fetched with 16-byte bulk copies
+  const size_t smem = 1024 + (size_t)F8_STAGES * 2 * F8_TILE_BYTES + (size_t)F8_SCALE_SLOTS * 2 * 512 +
+                      (gated ? (size_t)F8_BM * 64 * 4 : 0) + 256;
   const int n_cols = gated ? 64 : F8_BN;
   const int n_tiles = ((M + F8_BM - 1) / F8_BM) * ((N + n_cols - 1) / n_cols);
   dim3 grid(min(n_tiles, device_sm_count()));
