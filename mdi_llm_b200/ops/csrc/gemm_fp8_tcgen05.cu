@@ -51,6 +51,16 @@ __device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigne
   asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
   return d;
 }
+// explicit shared-space loads: the pointers below derive from the re-aligned dynamic-smem base, which the compiler
+// only knows as a generic address (it emitted 64-bit generic LD.E for them)
+__device__ __forceinline__ void lds_v2x2(uint32_t saddr, unsigned long long& lo, unsigned long long& hi) {
+  asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(lo), "=l"(hi) : "r"(saddr));
+}
+__device__ __forceinline__ float lds_f32(uint32_t saddr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr));
+  return v;
+}
 __device__ __forceinline__ float lo32(unsigned long long v) { return __uint_as_float((uint32_t)v); }
 __device__ __forceinline__ float hi32(unsigned long long v) { return __uint_as_float((uint32_t)(v >> 32)); }
 
@@ -196,16 +206,18 @@ __global__ void __launch_bounds__(F8_THREADS, 1) gemm_fp8_blockscaled_kernel(con
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&pempty_bar[pb]);  // the tensor core may overwrite this buffer
-        const float a_s = sc_a[sl * 128 + lg * 32 + lane];
+        const float a_s = lds_f32(smem_u32(sc_a + sl * 128 + lg * 32 + lane));
         const unsigned long long a2 = pack2(a_s, a_s);
-        const float4* ws4 = reinterpret_cast<const float4*>(sc_w + sl * 128 + 64 * half);  // broadcast reads
+        const uint32_t ws_addr = smem_u32(sc_w + sl * 128 + 64 * half);  // 64 column scales: broadcast 16-byte reads
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float4 w0 = ws4[j], w1 = ws4[8 + j];
-          acc2[2 * j] = fma2(pack2(__uint_as_float(t0[4 * j]), __uint_as_float(t0[4 * j + 1])), mul2(pack2(w0.x, w0.y), a2), acc2[2 * j]);
-          acc2[2 * j + 1] = fma2(pack2(__uint_as_float(t0[4 * j + 2]), __uint_as_float(t0[4 * j + 3])), mul2(pack2(w0.z, w0.w), a2), acc2[2 * j + 1]);
-          acc2[16 + 2 * j] = fma2(pack2(__uint_as_float(t1[4 * j]), __uint_as_float(t1[4 * j + 1])), mul2(pack2(w1.x, w1.y), a2), acc2[16 + 2 * j]);
-          acc2[16 + 2 * j + 1] = fma2(pack2(__uint_as_float(t1[4 * j + 2]), __uint_as_float(t1[4 * j + 3])), mul2(pack2(w1.z, w1.w), a2), acc2[16 + 2 * j + 1]);
+          unsigned long long w0a, w0b, w1a, w1b;
+          lds_v2x2(ws_addr + 16 * j, w0a, w0b);
+          lds_v2x2(ws_addr + 128 + 16 * j, w1a, w1b);
+          acc2[2 * j] = fma2(pack2(__uint_as_float(t0[4 * j]), __uint_as_float(t0[4 * j + 1])), mul2(w0a, a2), acc2[2 * j]);
+          acc2[2 * j + 1] = fma2(pack2(__uint_as_float(t0[4 * j + 2]), __uint_as_float(t0[4 * j + 3])), mul2(w0b, a2), acc2[2 * j + 1]);
+          acc2[16 + 2 * j] = fma2(pack2(__uint_as_float(t1[4 * j]), __uint_as_float(t1[4 * j + 1])), mul2(w1a, a2), acc2[16 + 2 * j]);
+          acc2[16 + 2 * j + 1] = fma2(pack2(__uint_as_float(t1[4 * j + 2]), __uint_as_float(t1[4 * j + 3])), mul2(w1b, a2), acc2[16 + 2 * j + 1]);
         }
       }
       float acc[64];

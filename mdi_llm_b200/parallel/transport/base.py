@@ -6,9 +6,12 @@ one pipeline stage to the next one in the ring.  Implementations:
 
 * :mod:`.socket_transport` — TCP + pickle, wire-compatible with the reference;
 * :mod:`.inproc`           — loop-back queue (standalone, 1 node: ``gptserver.py:276-278``);
-* :mod:`.nccl_p2p`         — ``torch.distributed`` isend/irecv on a side stream (baseline);
-* :mod:`.p2p_store`        — peer-mapped buffers + flags written by the fused hop kernels
-  (the product path; the host never touches activations there).
+* :mod:`.nccl_p2p`         — ``torch.distributed`` isend/irecv on a side stream (baseline).
+
+The product data plane is not a ``Transport`` at all: on one NVSwitch box the activations never pass through the
+host, so there is nothing to ``send``/``recv`` — the hop is fused into the kernels and wired by
+:mod:`mdi_llm_b200.parallel.ring` (CUDA-IPC handles exchanged over the control plane, peer stores + flags issued by
+the last kernel of a stage, see ``parallel/pipeline.py`` and ``ops/csrc/common.cuh``).
 
 A :class:`ChaosPolicy` can be attached to any host-side transport to delay or drop messages —
 the fault-injection hook the reference lacks.
