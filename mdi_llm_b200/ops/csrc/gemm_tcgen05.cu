@@ -245,6 +245,203 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
   hop_signal(p.signal, p.ctx);  // the __syncthreads above ordered every epilogue store before the ticket
 }
 
+// ---- CTA-pair variant: tcgen05.mma.cta_group::2 -----------------------------------------------------------------
+// Two CTAs of a cluster (same TPC) work on ONE 256 x BLOCK_N output tile: rank r owns rows [128 r, 128 r + 128) and loads
+// its own A rows plus HALF of the B tile (BLOCK_N / 2 weight rows); the leader CTA issues M = 256 MMAs that read both
+// CTAs' shared memory, every CTA's TMEM receives the accumulators of its own 128 rows.  Per CTA and K block that is
+// 16 KB (A) + 16 KB (B half) for a 128 x 256 share of the output instead of 16 + 32 KB: a third less shared-memory
+// fill and L2 traffic per FLOP, and the tensor core is fed M = 256.
+//   * "full" barriers live in the leader; both CTAs' TMA loads complete on them (cp.async.bulk.tensor ... cta_group::2)
+//   * "empty" / "accumulator full" barriers exist in both CTAs; the leader's tcgen05.commit multicasts to the pair
+//   * "accumulator drained" lives in the leader; rank 1's epilogue warps arrive remotely (mapa + shared::cluster)
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* map, uint64_t* leader_bar, int x, int y) {
+  // executed by both CTAs; clearing the peer bit makes the transaction bytes land on CTA 0's barrier
+  const uint32_t bar = smem_u32(leader_bar) & 0xFEFFFFFFu;
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(bar), "r"(x), "r"(y)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_mma_f16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                     uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_commit_pair(uint64_t* bar) {  // arrives on the same barrier in BOTH CTAs
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cta(uint64_t* bar, uint32_t cta) {  // arrive on `bar` of CTA `cta` of the cluster
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(smem_u32(bar)), "r"(cta) : "memory");
+}
+
+template <int BLOCK_N>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ GemmParams p) {
+  extern __shared__ __align__(1024) unsigned char gemm_smem[];
+  constexpr int A_BYTES = GEMM_BLOCK_M * GEMM_BLOCK_K * 2;      // this CTA's 128 rows of A
+  constexpr int B_BYTES = (BLOCK_N / 2) * GEMM_BLOCK_K * 2;     // this CTA's half of the B tile
+  constexpr int TMEM_COLS = 2 * BLOCK_N;                        // two accumulator buffers
+  static_assert(TMEM_COLS <= 512 && BLOCK_N % 32 == 0, "accumulators exceed TMEM");
+  unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(gemm_smem) + 1023) & ~uintptr_t(1023));
+  unsigned char* smem_a = base;
+  unsigned char* smem_b = base + GEMM_STAGES * A_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_b + GEMM_STAGES * B_BYTES);  // used in the leader
+  uint64_t* empty_bar = full_bar + GEMM_STAGES;                                       // both CTAs (multicast commit)
+  uint64_t* tmem_full_bar = empty_bar + GEMM_STAGES;                                  // [2] both CTAs
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;                                       // [2] leader: 8 epilogue warps of the pair
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int tiles_m = (p.M + 2 * GEMM_BLOCK_M - 1) / (2 * GEMM_BLOCK_M);
+  const int tiles_n = (p.N + BLOCK_N - 1) / BLOCK_N;
+  const int n_tiles = tiles_m * tiles_n;
+  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  const int num_k_blocks = (p.K + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tma_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tma_b) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < GEMM_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full_bar[b], 1); mbar_init(&tmem_empty_bar[b], 8); }
+    mbar_fence_init();
+  }
+  if (warp == 2) {  // same warp in both CTAs: the allocation is collective over the pair
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "n"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  cluster_sync_all();  // barriers of BOTH CTAs are initialised before any remote arrive / multicast commit
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ===== TMA producer (both CTAs): own A rows + own half of B, completing on the leader's barrier =====
+    if (lane == 0) {
+      int it = 0;
+      for (int tile = pair; tile < n_tiles; tile += n_pairs) {
+        const int m0 = (tile % tiles_m) * 2 * GEMM_BLOCK_M + (int)rank * GEMM_BLOCK_M;
+        const int n0 = (tile / tiles_m) * BLOCK_N + (int)rank * (BLOCK_N / 2);
+        for (int kb = 0; kb < num_k_blocks; ++kb, ++it) {
+          const int s = it % GEMM_STAGES;
+          mbar_wait(&empty_bar[s], ((it / GEMM_STAGES) & 1) ^ 1);
+          if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * (A_BYTES + B_BYTES));  // bytes of the whole pair
+          tma_load_2d_pair(smem_a + s * A_BYTES, &p.tma_a, &full_bar[s], kb * GEMM_BLOCK_K, m0);
+          tma_load_2d_pair(smem_b + s * B_BYTES, &p.tma_b, &full_bar[s], kb * GEMM_BLOCK_K, n0);
+        }
+      }
+    }
+  } else if (warp == 1 && rank == 0) {
+    // ===== MMA issuer (leader only): M = 256 over the pair =====
+    const uint32_t idesc = umma_idesc_bf16(2 * GEMM_BLOCK_M, BLOCK_N);
+    int it = 0, lt = 0;
+    for (int tile = pair; tile < n_tiles; tile += n_pairs, ++lt) {
+      const int acc = lt & 1;
+      const uint32_t tmem_acc = tmem_base + (uint32_t)(acc * BLOCK_N);
+      mbar_wait(&tmem_empty_bar[acc], ((lt >> 1) & 1) ^ 1);  // both CTAs' epilogues have drained this buffer
+      tcgen05_fence_after();
+      for (int kb = 0; kb < num_k_blocks; ++kb, ++it) {
+        const int s = it % GEMM_STAGES;
+        mbar_wait(&full_bar[s], (it / GEMM_STAGES) & 1);
+        tcgen05_fence_after();
+        if (lane == 0) {
+          const uint32_t a_addr = smem_u32(smem_a + s * A_BYTES), b_addr = smem_u32(smem_b + s * B_BYTES);
+#pragma unroll
+          for (int k = 0; k < GEMM_BLOCK_K / UMMA_K; ++k)
+            tcgen05_mma_f16_pair(tmem_acc, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc, (kb | k) ? 1u : 0u);
+          tcgen05_commit_pair(&empty_bar[s]);
+          if (kb == num_k_blocks - 1) tcgen05_commit_pair(&tmem_full_bar[acc]);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue (both CTAs): own 128 rows =====
+    const int ew = warp - 4;
+    const bool vec_ok = (p.N % 8 == 0);
+    int lt = 0;
+    for (int tile = pair; tile < n_tiles; tile += n_pairs, ++lt) {
+      const int m0 = (tile % tiles_m) * 2 * GEMM_BLOCK_M + (int)rank * GEMM_BLOCK_M, n0 = (tile / tiles_m) * BLOCK_N;
+      const int acc = lt & 1;
+      const uint32_t tmem_acc = tmem_base + (uint32_t)(acc * BLOCK_N) + ((uint32_t)(ew * 32) << 16);
+      mbar_wait(&tmem_full_bar[acc], (lt >> 1) & 1);
+      tcgen05_fence_after();
+      const int row = m0 + ew * 32 + lane;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+        uint32_t acc_r[32];
+        tmem_ld_32x32(tmem_acc + (uint32_t)c0, acc_r);
+        const int col0 = n0 + c0;
+        if (row < p.M && col0 < p.N) {
+          bf16* crow = p.C + (size_t)row * p.N + col0;
+          const bf16* rrow = p.residual ? p.residual + (size_t)row * p.N + col0 : nullptr;
+          if (vec_ok && col0 + 32 <= p.N) {
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+              float f[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                f[j] = __uint_as_float(acc_r[v * 8 + j]);
+                if (p.bias) f[j] += __bfloat162float(p.bias[col0 + v * 8 + j]);
+              }
+              if (rrow) {
+                const uint4 r4 = *reinterpret_cast<const uint4*>(rrow + v * 8);
+                const uint32_t rw[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  f[2 * j] = round_bf16(f[2 * j]) + bf16lo(rw[j]);
+                  f[2 * j + 1] = round_bf16(f[2 * j + 1]) + bf16hi(rw[j]);
+                }
+              }
+              uint4 o;
+              o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]);
+              o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
+              *reinterpret_cast<uint4*>(crow + v * 8) = o;
+            }
+          } else {
+#pragma unroll 1
+            for (int j = 0; j < 32 && col0 + j < p.N; ++j) {
+              float v0 = __uint_as_float(acc_r[j]);
+              if (p.bias) v0 += __bfloat162float(p.bias[col0 + j]);
+              if (rrow) v0 = round_bf16(v0) + __bfloat162float(rrow[j]);
+              crow[j] = __float2bfloat16_rn(v0);
+            }
+          }
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cta(&tmem_empty_bar[acc], 0);  // the leader's MMA warp waits for all 8 warps of the pair
+    }
+  }
+  tcgen05_fence_before();
+  cluster_sync_all();  // nobody leaves while the peer may still touch its barriers / shared memory
+  if (warp == 2) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+  }
+  hop_signal(p.signal, p.ctx);
+}
+
 // ---- host side ------------------------------------------------------------------------------------
 }  // namespace mdi
 
@@ -269,6 +466,21 @@ extern "C" int mdi_gemm_bf16_ex(const void* A, const void* W, const void* W2, vo
   p.desc_hi_bits = hi_bits > 0 ? (unsigned)hi_bits : (1u | (2u << 15));  // version = 1 (bit 46), SWIZZLE_128B = 2 (bits 61-63)
   p.k_step_bytes = k_step > 0 ? (unsigned)k_step : 32u;
   const bool gated = W2 != nullptr;
+  if (block_n == 512) {  // CTA-pair kernel (cta_group::2): 256 x 256 tiles shared by two CTAs of a cluster
+    if (gated) return -3;
+    int rc2 = make_map(&p.tma_a, A, M, K, GEMM_BLOCK_M);
+    if (rc2) return rc2;
+    rc2 = make_map(&p.tma_b, W, N, K, 128);  // each CTA loads half (128 rows) of the 256-row B tile
+    if (rc2) return rc2;
+    p.tma_b2 = p.tma_b;
+    const size_t smem2 = 1024 + (size_t)GEMM_STAGES * (GEMM_BLOCK_M + 128) * GEMM_BLOCK_K * 2 + 128;
+    const int n_tiles2 = ((M + 255) / 256) * ((N + 255) / 256);
+    const int pairs = min(n_tiles2, device_sm_count() / 2);
+    cudaError_t e2 = cudaFuncSetAttribute(gemm_bf16_tcgen05_pair_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+    if (e2 != cudaSuccess) return (int)e2;
+    gemm_bf16_tcgen05_pair_kernel<256><<<dim3(2 * pairs), GEMM_THREADS, smem2, stream>>>(p);
+    return (int)cudaGetLastError();
+  }
   if (block_n != 64 && block_n != 128 && block_n != 256) block_n = 128;
   if (gated && block_n == 256) block_n = 128;  // 2 buffers x 2 accumulators x BLOCK_N <= 512 TMEM columns
   int rc = make_map(&p.tma_a, A, M, K, GEMM_BLOCK_M);

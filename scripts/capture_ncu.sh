@@ -10,6 +10,7 @@ for what in ${@:-decode gemm attn}; do
     gemm)   k="regex:gemm_bf16_tcgen05_kernel" ;;
     attn)   k="regex:attn_decode_kernel" ;;
     attnp)  k="regex:attn_prefill_tcgen05_kernel" ;;
+    gemm_fp8) k="regex:gemm_fp8_blockscaled_kernel" ;;
   esac
   timeout 600 ncu --set full --clock-control none --import-source on -k "$k" --launch-skip 2 --launch-count 1 -f \
     -o gpurun_out/prof_$what python scripts/profile_targets.py $what > gpurun_out/ncu_$what.log 2>&1

@@ -3,7 +3,8 @@
    decode: the Llama-3-8B gate/up weight-streaming kernel (+RMSNorm, SiLU*mul epilogue), 235 MB of weights
    gemm  : the tcgen05 prefill GEMM 2048 x 14336 x 4096
    attn  : decode attention at 2048 context, Llama-3-8B heads
-   attnp : tcgen05 prefill attention, 2048-token prompt, Llama-3-8B heads"""
+   attnp : tcgen05 prefill attention, 2048-token prompt, Llama-3-8B heads
+   gemm_fp8: the block-scaled fp8 GEMM (tcgen05 kind::f8f6f4) 2048 x 6144 x 4096"""
 import os
 import sys
 
@@ -40,6 +41,16 @@ elif what == "attn":
     ctx[1] = 2047
     for _ in range(4):
         ops.attn_decode(q, kv, y, part, tickets, ctx, n_head=H, n_groups=G, head_size=hs, max_seq=S, n_split=37)
+elif what == "gemm_fp8":
+    from mdi_llm_b200.utils.quantize import quantize_fp8_block
+
+    M, N, K = 2048, 6144, 4096
+    a = torch.randn(M, K, device="cuda").bfloat16()
+    q, s = quantize_fp8_block((torch.randn(N, K, device="cuda") * 0.02).bfloat16())
+    a8, a_st = ops.quantize_rows_fp8(a)
+    st = s.t().contiguous()
+    for _ in range(4):
+        ops.gemm_fp8(a8, a_st, q.view(torch.uint8), st)
 torch.cuda.synchronize()
 print("done", what)
 

@@ -3,7 +3,7 @@
 # hottest SASS lines).  Runs where the report is (no GPU needed).
 set -uo pipefail
 cd "$(dirname "$0")/.."
-for what in ${@:-decode_linear gemm attn attnp}; do
+for what in ${@:-decode_linear gemm attn attnp gemm_fp8}; do
   src=$what; [ "$what" = decode_linear ] && src=decode
   rep=gpurun_out/prof_$src.ncu-rep
   [ -f "$rep" ] || { echo "missing $rep"; continue; }

@@ -174,3 +174,25 @@ def test_gemm_fp8_gated_mlp_one_pass(M, I, K):
     ref = torch.nn.functional.silu(g).bfloat16().float() * u
     err = (out.float() - ref).abs().max().item()
     assert out.shape == (M, I) and err <= 0.02 * ref.abs().max().item() + 0.02, err
+
+
+@pytest.mark.parametrize("M,N,K,bias,res", [(256, 256, 64, False, False), (256, 256, 512, False, False), (512, 768, 1024, True, True),
+                                             (2048, 6144, 4096, False, False), (1000, 4096, 14336, False, True), (300, 1000, 520, True, False)])
+def test_gemm_cta_pair_kernel_matches_reference(M, N, K, bias, res):
+    """cta_group::2: two CTAs of a cluster share one 256 x 256 tile (each loads its A rows and half of B, the
+    leader issues M = 256 MMAs, commits are multicast to the pair)."""
+    import os
+
+    if os.environ.get("MDI_TEST_PAIR", "1") == "0":
+        pytest.skip("CTA-pair GEMM disabled")
+    ops = _ops()
+    torch.manual_seed(M + N + K)
+    a = torch.randn(M, K, device="cuda").bfloat16()
+    w = (torch.randn(N, K, device="cuda") * 0.05).bfloat16()
+    b = torch.randn(N, device="cuda").bfloat16() if bias else None
+    r = torch.randn(M, N, device="cuda").bfloat16() if res else None
+    out = ops.gemm(a, w, bias=b, residual=r, block_n=512)
+    ref = a.float() @ w.float().T + (b.float() if bias else 0)
+    ref = ref.bfloat16().float() + (r.float() if res else 0)
+    err = (out.float() - ref).abs().max().item()
+    assert err <= 0.02 * ref.abs().max().item() + 0.06, f"max err {err}"
