@@ -291,7 +291,9 @@ __device__ __forceinline__ void mbar_arrive_cta(uint64_t* bar, uint32_t cta) {  
       ::"r"(smem_u32(bar)), "r"(cta) : "memory");
 }
 
-template <int BLOCK_N>
+// GATED: the 256-column MMA tile is [fc_1 rows n0 .. n0+128 | fc_2 rows n0 .. n0+128] — rank 0 loads the fc_1 half of
+// the B tile, rank 1 the fc_2 half — and the epilogue writes act(g) * u for 128 output columns.
+template <int BLOCK_N, bool GATED>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ GemmParams p) {
   extern __shared__ __align__(1024) unsigned char gemm_smem[];
@@ -310,8 +312,9 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ GemmParams p) {
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
+  constexpr int OUT_N = GATED ? BLOCK_N / 2 : BLOCK_N;  // output columns per tile
   const int tiles_m = (p.M + 2 * GEMM_BLOCK_M - 1) / (2 * GEMM_BLOCK_M);
-  const int tiles_n = (p.N + BLOCK_N - 1) / BLOCK_N;
+  const int tiles_n = (p.N + OUT_N - 1) / OUT_N;
   const int n_tiles = tiles_m * tiles_n;
   const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
   const int num_k_blocks = (p.K + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K;
@@ -319,6 +322,7 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ GemmParams p) {
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tma_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tma_b) : "memory");
+    if (GATED) asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tma_b2) : "memory");
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < GEMM_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
@@ -340,13 +344,14 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ GemmParams p) {
       int it = 0;
       for (int tile = pair; tile < n_tiles; tile += n_pairs) {
         const int m0 = (tile % tiles_m) * 2 * GEMM_BLOCK_M + (int)rank * GEMM_BLOCK_M;
-        const int n0 = (tile / tiles_m) * BLOCK_N + (int)rank * (BLOCK_N / 2);
+        const int n0 = GATED ? (tile / tiles_m) * OUT_N : (tile / tiles_m) * BLOCK_N + (int)rank * (BLOCK_N / 2);
+        const CUtensorMap* map_b = (GATED && rank == 1) ? &p.tma_b2 : &p.tma_b;
         for (int kb = 0; kb < num_k_blocks; ++kb, ++it) {
           const int s = it % GEMM_STAGES;
           mbar_wait(&empty_bar[s], ((it / GEMM_STAGES) & 1) ^ 1);
           if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * (A_BYTES + B_BYTES));  // bytes of the whole pair
           tma_load_2d_pair(smem_a + s * A_BYTES, &p.tma_a, &full_bar[s], kb * GEMM_BLOCK_K, m0);
-          tma_load_2d_pair(smem_b + s * B_BYTES, &p.tma_b, &full_bar[s], kb * GEMM_BLOCK_K, n0);
+          tma_load_2d_pair(smem_b + s * B_BYTES, map_b, &full_bar[s], kb * GEMM_BLOCK_K, n0);
         }
       }
     }
@@ -380,17 +385,31 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ GemmParams p) {
     const bool vec_ok = (p.N % 8 == 0);
     int lt = 0;
     for (int tile = pair; tile < n_tiles; tile += n_pairs, ++lt) {
-      const int m0 = (tile % tiles_m) * 2 * GEMM_BLOCK_M + (int)rank * GEMM_BLOCK_M, n0 = (tile / tiles_m) * BLOCK_N;
+      const int m0 = (tile % tiles_m) * 2 * GEMM_BLOCK_M + (int)rank * GEMM_BLOCK_M, n0 = (tile / tiles_m) * OUT_N;
       const int acc = lt & 1;
       const uint32_t tmem_acc = tmem_base + (uint32_t)(acc * BLOCK_N) + ((uint32_t)(ew * 32) << 16);
       mbar_wait(&tmem_full_bar[acc], (lt >> 1) & 1);
       tcgen05_fence_after();
       const int row = m0 + ew * 32 + lane;
 #pragma unroll 1
-      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+      for (int c0 = 0; c0 < OUT_N; c0 += 32) {
         uint32_t acc_r[32];
         tmem_ld_32x32(tmem_acc + (uint32_t)c0, acc_r);
         const int col0 = n0 + c0;
+        if (GATED) {
+          uint32_t acc2[32];
+          tmem_ld_32x32(tmem_acc + (uint32_t)(OUT_N + c0), acc2);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float g = __uint_as_float(acc_r[j]), u = __uint_as_float(acc2[j]);
+            if (col0 + j < p.N) {
+              if (p.bias) g += __bfloat162float(p.bias[col0 + j]);
+              if (p.bias2) u += __bfloat162float(p.bias2[col0 + j]);
+            }
+            g = round_bf16(g); u = round_bf16(u);
+            acc_r[j] = __float_as_uint(round_bf16(apply_act(g, p.act)) * u);
+          }
+        }
         if (row < p.M && col0 < p.N) {
           bf16* crow = p.C + (size_t)row * p.N + col0;
           const bf16* rrow = p.residual ? p.residual + (size_t)row * p.N + col0 : nullptr;
@@ -401,7 +420,7 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ GemmParams p) {
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
                 f[j] = __uint_as_float(acc_r[v * 8 + j]);
-                if (p.bias) f[j] += __bfloat162float(p.bias[col0 + v * 8 + j]);
+                if (!GATED && p.bias) f[j] += __bfloat162float(p.bias[col0 + v * 8 + j]);
               }
               if (rrow) {
                 const uint4 r4 = *reinterpret_cast<const uint4*>(rrow + v * 8);
@@ -421,7 +440,7 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ GemmParams p) {
 #pragma unroll 1
             for (int j = 0; j < 32 && col0 + j < p.N; ++j) {
               float v0 = __uint_as_float(acc_r[j]);
-              if (p.bias) v0 += __bfloat162float(p.bias[col0 + j]);
+              if (!GATED && p.bias) v0 += __bfloat162float(p.bias[col0 + j]);
               if (rrow) v0 = round_bf16(v0) + __bfloat162float(rrow[j]);
               crow[j] = __float2bfloat16_rn(v0);
             }
@@ -466,19 +485,26 @@ extern "C" int mdi_gemm_bf16_ex(const void* A, const void* W, const void* W2, vo
   p.desc_hi_bits = hi_bits > 0 ? (unsigned)hi_bits : (1u | (2u << 15));  // version = 1 (bit 46), SWIZZLE_128B = 2 (bits 61-63)
   p.k_step_bytes = k_step > 0 ? (unsigned)k_step : 32u;
   const bool gated = W2 != nullptr;
-  if (block_n == 512) {  // CTA-pair kernel (cta_group::2): 256 x 256 tiles shared by two CTAs of a cluster
-    if (gated) return -3;
+  if (block_n == 512) {  // CTA-pair kernel (cta_group::2): 256 x 256 MMA tiles shared by two CTAs of a cluster
     int rc2 = make_map(&p.tma_a, A, M, K, GEMM_BLOCK_M);
     if (rc2) return rc2;
     rc2 = make_map(&p.tma_b, W, N, K, 128);  // each CTA loads half (128 rows) of the 256-row B tile
     if (rc2) return rc2;
-    p.tma_b2 = p.tma_b;
+    rc2 = make_map(&p.tma_b2, gated ? W2 : W, N, K, 128);
+    if (rc2) return rc2;
     const size_t smem2 = 1024 + (size_t)GEMM_STAGES * (GEMM_BLOCK_M + 128) * GEMM_BLOCK_K * 2 + 128;
-    const int n_tiles2 = ((M + 255) / 256) * ((N + 255) / 256);
+    const int n_tiles2 = ((M + 255) / 256) * ((N + (gated ? 127 : 255)) / (gated ? 128 : 256));
     const int pairs = min(n_tiles2, device_sm_count() / 2);
-    cudaError_t e2 = cudaFuncSetAttribute(gemm_bf16_tcgen05_pair_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
-    if (e2 != cudaSuccess) return (int)e2;
-    gemm_bf16_tcgen05_pair_kernel<256><<<dim3(2 * pairs), GEMM_THREADS, smem2, stream>>>(p);
+    cudaError_t e2;
+    if (gated) {
+      e2 = cudaFuncSetAttribute(gemm_bf16_tcgen05_pair_kernel<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+      if (e2 != cudaSuccess) return (int)e2;
+      gemm_bf16_tcgen05_pair_kernel<256, true><<<dim3(2 * pairs), GEMM_THREADS, smem2, stream>>>(p);
+    } else {
+      e2 = cudaFuncSetAttribute(gemm_bf16_tcgen05_pair_kernel<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+      if (e2 != cudaSuccess) return (int)e2;
+      gemm_bf16_tcgen05_pair_kernel<256, false><<<dim3(2 * pairs), GEMM_THREADS, smem2, stream>>>(p);
+    }
     return (int)cudaGetLastError();
   }
   if (block_n != 64 && block_n != 128 && block_n != 256) block_n = 128;

@@ -28,9 +28,13 @@ def timeit(fn, iters=20):
 
 
 rows = []
-for (M, N, K, bn, gated) in [(2048, 14336, 4096, 256, False), (2048, 14336, 4096, 128, False), (2048, 4096, 4096, 128, False),
-                             (2048, 6144, 4096, 128, False), (2048, 4096, 14336, 128, False), (2048, 14336, 4096, 128, True),
-                             (64, 14336, 4096, 128, True), (64, 4096, 14336, 64, False), (512, 14336, 4096, 256, False)]:
+# block_n 512 = the CTA-pair kernel (cta_group::2, 256 x 256 MMA tiles over a 2-CTA cluster)
+for (M, N, K, bn, gated) in [(2048, 14336, 4096, 512, False), (2048, 14336, 4096, 256, False), (2048, 4096, 4096, 512, False),
+                             (2048, 4096, 4096, 128, False), (2048, 6144, 4096, 512, False), (2048, 6144, 4096, 128, False),
+                             (2048, 4096, 14336, 512, False), (2048, 4096, 14336, 256, False), (2048, 14336, 4096, 512, True),
+                             (2048, 14336, 4096, 128, True), (8192, 14336, 4096, 512, True), (8192, 4096, 14336, 512, False),
+                             (512, 14336, 4096, 512, False), (512, 14336, 4096, 256, False), (64, 14336, 4096, 128, True),
+                             (64, 4096, 14336, 64, False)]:
     ring = max(2, int(200e6 // (N * K * 2)) + 1)
     a = torch.randn(M, K, device=dev).bfloat16()
     ws = [(torch.randn(N, K, device=dev) * 0.02).bfloat16() for _ in range(ring)]

@@ -196,3 +196,19 @@ def test_gemm_cta_pair_kernel_matches_reference(M, N, K, bias, res):
     ref = ref.bfloat16().float() + (r.float() if res else 0)
     err = (out.float() - ref).abs().max().item()
     assert err <= 0.02 * ref.abs().max().item() + 0.06, f"max err {err}"
+
+
+@pytest.mark.parametrize("M,I,K", [(256, 128, 64), (300, 1000, 520), (2048, 14336, 4096)])
+def test_gemm_cta_pair_gated_matches_reference(M, I, K):
+    """Gated MLP on the CTA-pair kernel: rank 0 loads the fc_1 half of the B tile, rank 1 the fc_2 half."""
+    ops = _ops()
+    torch.manual_seed(M + I + K)
+    a = (torch.randn(M, K, device="cuda") * 0.5).bfloat16()
+    w1 = (torch.randn(I, K, device="cuda") * 0.05).bfloat16()
+    w2 = (torch.randn(I, K, device="cuda") * 0.05).bfloat16()
+    out = ops.gemm(a, w1, w2=w2, act="silu_gate", block_n=512)
+    g = (a.float() @ w1.float().T).bfloat16().float()
+    u = (a.float() @ w2.float().T).bfloat16().float()
+    ref = torch.nn.functional.silu(g).bfloat16().float() * u
+    err = (out.float() - ref).abs().max().item()
+    assert out.shape == (M, I) and err <= 0.02 * ref.abs().max().item() + 0.05, err
