@@ -293,6 +293,7 @@ __device__ __forceinline__ void mbar_arrive_cta(uint64_t* bar, uint32_t cta) {  
 
 // GATED: the 256-column MMA tile is [fc_1 rows n0 .. n0+128 | fc_2 rows n0 .. n0+128] — rank 0 loads the fc_1 half of
 // the B tile, rank 1 the fc_2 half — and the epilogue writes act(g) * u for 128 output columns.
+constexpr int PAIR_STAGES = 6;  // 6 x (16 KB A + 16 KB B half) = 192 KB of the 227 KB
 template <int BLOCK_N, bool GATED>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ GemmParams p) {
@@ -303,10 +304,10 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ GemmParams p) {
   static_assert(TMEM_COLS <= 512 && BLOCK_N % 32 == 0, "accumulators exceed TMEM");
   unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(gemm_smem) + 1023) & ~uintptr_t(1023));
   unsigned char* smem_a = base;
-  unsigned char* smem_b = base + GEMM_STAGES * A_BYTES;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_b + GEMM_STAGES * B_BYTES);  // used in the leader
-  uint64_t* empty_bar = full_bar + GEMM_STAGES;                                       // both CTAs (multicast commit)
-  uint64_t* tmem_full_bar = empty_bar + GEMM_STAGES;                                  // [2] both CTAs
+  unsigned char* smem_b = base + PAIR_STAGES * A_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_b + PAIR_STAGES * B_BYTES);  // used in the leader
+  uint64_t* empty_bar = full_bar + PAIR_STAGES;                                       // both CTAs (multicast commit)
+  uint64_t* tmem_full_bar = empty_bar + PAIR_STAGES;                                  // [2] both CTAs
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;                                       // [2] leader: 8 epilogue warps of the pair
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
@@ -325,7 +326,7 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ GemmParams p) {
     if (GATED) asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tma_b2) : "memory");
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < GEMM_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < PAIR_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full_bar[b], 1); mbar_init(&tmem_empty_bar[b], 8); }
     mbar_fence_init();
   }
@@ -347,8 +348,8 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ GemmParams p) {
         const int n0 = GATED ? (tile / tiles_m) * OUT_N : (tile / tiles_m) * BLOCK_N + (int)rank * (BLOCK_N / 2);
         const CUtensorMap* map_b = (GATED && rank == 1) ? &p.tma_b2 : &p.tma_b;
         for (int kb = 0; kb < num_k_blocks; ++kb, ++it) {
-          const int s = it % GEMM_STAGES;
-          mbar_wait(&empty_bar[s], ((it / GEMM_STAGES) & 1) ^ 1);
+          const int s = it % PAIR_STAGES;
+          mbar_wait(&empty_bar[s], ((it / PAIR_STAGES) & 1) ^ 1);
           if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * (A_BYTES + B_BYTES));  // bytes of the whole pair
           tma_load_2d_pair(smem_a + s * A_BYTES, &p.tma_a, &full_bar[s], kb * GEMM_BLOCK_K, m0);
           tma_load_2d_pair(smem_b + s * B_BYTES, map_b, &full_bar[s], kb * GEMM_BLOCK_K, n0);
@@ -365,8 +366,8 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ GemmParams p) {
       mbar_wait(&tmem_empty_bar[acc], ((lt >> 1) & 1) ^ 1);  // both CTAs' epilogues have drained this buffer
       tcgen05_fence_after();
       for (int kb = 0; kb < num_k_blocks; ++kb, ++it) {
-        const int s = it % GEMM_STAGES;
-        mbar_wait(&full_bar[s], (it / GEMM_STAGES) & 1);
+        const int s = it % PAIR_STAGES;
+        mbar_wait(&full_bar[s], (it / PAIR_STAGES) & 1);
         tcgen05_fence_after();
         if (lane == 0) {
           const uint32_t a_addr = smem_u32(smem_a + s * A_BYTES), b_addr = smem_u32(smem_b + s * B_BYTES);
@@ -492,7 +493,7 @@ extern "C" int mdi_gemm_bf16_ex(const void* A, const void* W, const void* W2, vo
     if (rc2) return rc2;
     rc2 = make_map(&p.tma_b2, gated ? W2 : W, N, K, 128);
     if (rc2) return rc2;
-    const size_t smem2 = 1024 + (size_t)GEMM_STAGES * (GEMM_BLOCK_M + 128) * GEMM_BLOCK_K * 2 + 128;
+    const size_t smem2 = 1024 + (size_t)PAIR_STAGES * (GEMM_BLOCK_M + 128) * GEMM_BLOCK_K * 2 + 256;
     const int n_tiles2 = ((M + 255) / 256) * ((N + (gated ? 127 : 255)) / (gated ? 128 : 256));
     const int pairs = min(n_tiles2, device_sm_count() / 2);
     cudaError_t e2;

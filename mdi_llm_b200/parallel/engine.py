@@ -576,7 +576,11 @@ class FusedStage:
         cos, sin = m.rope_for(T, input_pos)
         eps, uo = cfg.norm_eps, cfg.unit_offset_norm
         units = self._units()
-        bn = 256 if T > 128 else 128  # 128x256 tiles reach 1.18 PFLOP/s; short prompts want more (smaller) tiles
+        # tile choice: prompts of >= 192 rows take the CTA-pair kernel (cta_group::2: two CTAs share a 256 x 256 MMA tile,
+        # 86-97 % of cuBLAS on the Llama-3 shapes and ahead of it on the fused gated MLP); shorter ones want more,
+        # smaller tiles
+        pair = T >= 192 and os.environ.get("MDI_GEMM_PAIR", "1") != "0"
+        bn = 512 if pair else (256 if T > 128 else 128)
         # the tcgen05 attention kernel covers a prompt that starts at position 0 (every prefill of the pipeline);
         # anything else (a continuation at an offset) takes the eager helper
         use_fa = (self.prefill_attn == "tcgen05" and cfg.rope_n_elem % 16 == 0
@@ -604,7 +608,7 @@ class FusedStage:
                 x = out_gemm(g_in, blk.mlp.proj, last)
             else:
                 h = ops.rmsnorm_rows(x, blk.norm_2.weight, eps, uo)
-                g = self._gemm(h, blk.mlp.fc_1, blk.mlp.fc_2, act=self._gate_act())
+                g = self._gemm(h, blk.mlp.fc_1, blk.mlp.fc_2, act=self._gate_act(), **({"block_n": 512} if pair else {}))
                 if kind == "gu":  # the stage ends here: [x | h] travels (copy + in-kernel flag release)
                     out = torch.cat((x, g), dim=1)
                     if hop is None:
