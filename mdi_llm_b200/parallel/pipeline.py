@@ -192,6 +192,11 @@ class DevicePipeline:
                 for i, p in enumerate(prompts):
                     st.tokens[i, : p.numel()].copy_(p.to(torch.int32), non_blocking=True)
             self.prompts = [p.to(self.device, non_blocking=True) for p in prompts] if self.is_starter else None
+            if self.hop != "nccl":  # capture (once) every graph the device-driven rounds will replay
+                self._g_full(True, self.steps_per_graph)
+                self._g_full(True, 1)
+                if self.is_starter:
+                    self._g_head(True)
             torch.cuda.current_stream().synchronize()
 
     def _hop_copy(self, src: torch.Tensor, dst_ptr: int) -> None:
@@ -331,7 +336,9 @@ class DevicePipeline:
         with torch.cuda.device(self.device), _nvtx(f"mdi.decode[{self.rank}] x{n_rounds}"):
             full_rounds = max(0, min(n_rounds, self.max_new - self.round))  # rounds before the final (head-only) one
             steps = full_rounds * self.n
-            k = max(1, min(self.steps_per_graph, steps)) if steps else 1
+            # only two graph shapes ever exist (k steps, 1 step), both captured in prepare(): a segment never pays
+            # for a capture inside somebody's timed region
+            k = self.steps_per_graph if steps >= self.steps_per_graph else 1
             if steps:
                 g = self._g_full(True, k)
                 g.launch(steps // k)
