@@ -119,9 +119,9 @@ def lib() -> ctypes.CDLL:
 
 
 def set_prefill_attn_pipe(mode: int) -> None:
-    """Prefill attention kernel: 1 / True = pipelined (double-buffered K/V^T tiles and score matrix; default),
-    0 / False = the simple sequential kernel, 2 = pipelined with two softmax warpgroups (experimental, not yet
-    validated on hardware).  ``MDI_PREFILL_ATTN_PIPE`` sets it at load."""
+    """Prefill attention kernel: 2 = pipelined with two softmax warpgroups (default: validated on B200, 9-12 % faster
+    than mode 1 at 2-4k tokens), 1 / True = pipelined with one softmax warpgroup (double-buffered K/V^T tiles and score
+    matrix), 0 / False = the simple sequential kernel.  ``MDI_PREFILL_ATTN_PIPE`` sets it at load."""
     lib().mdi_set_prefill_attn_pipe(int(mode))
 
 

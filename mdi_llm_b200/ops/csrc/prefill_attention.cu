@@ -715,7 +715,7 @@ __global__ void __launch_bounds__(PA2_THREADS, 1) attn_prefill_tcgen05_pipe2_ker
   }
 }
 
-static int g_prefill_attn_pipe = 1;  // see mdi_set_prefill_attn_pipe
+static int g_prefill_attn_pipe = 2;  // two softmax warpgroups (validated on B200); see mdi_set_prefill_attn_pipe
 
 template <int HS>
 static int launch_prefill_attn_pipe(const PrefillAttnParams& p, cudaStream_t stream) {

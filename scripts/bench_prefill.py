@@ -43,7 +43,7 @@ for T in (128, 512, 2048, 4096):
     ops.set_prefill_attn_pipe(True)
     ms_pipe = timeit(lambda: ops.attn_prefill(qkv, cos, sin, pool, 0, n_head=H, n_groups=G, head_size=hs, rope_n_elem=hs))
     row_extra = {}
-    if os.environ.get("MDI_TEST_EXPERIMENTAL"):  # two softmax warpgroups (mode 2)
+    if True:  # two softmax warpgroups (mode 2, the default)
         ops.set_prefill_attn_pipe(2)
         ms2 = timeit(lambda: ops.attn_prefill(qkv, cos, sin, pool, 0, n_head=H, n_groups=G, head_size=hs, rope_n_elem=hs))
         row_extra = {"tcgen05_pipe2_ms": round(ms2, 4)}

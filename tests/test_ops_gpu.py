@@ -448,7 +448,7 @@ def test_qkv_decode_fp8_block_scaled():
 
 @pytest.mark.parametrize("H,G,hs,ne", [(32, 8, 128, 128), (8, 2, 64, 64), (4, 4, 128, 64), (8, 1, 64, 32)])
 @pytest.mark.parametrize("T", [5, 64, 128, 129, 300, 512])
-@pytest.mark.parametrize("pipe", [0, 1] + ([2] if os.environ.get("MDI_TEST_EXPERIMENTAL") else []))
+@pytest.mark.parametrize("pipe", [0, 1, 2])
 def test_attn_prefill_tcgen05_matches_eager(H, G, hs, ne, T, pipe):
     """RoPE + KV append + causal flash attention (tcgen05, S / P.V in TMEM) vs the eager attend_qkv."""
     from mdi_llm_b200.models.config import Config
