@@ -548,7 +548,8 @@ def run_ours(args: argparse.Namespace) -> Dict[str, Any]:
         a = copy.copy(args)
         a.steps, a.warmup, a.seq_len = args.long_steps, 8, 0
         extras.append(("long_run", a))
-    if args.extras and world == 8 and not args.tiny and args.weights == "bf16" and args.model == "Llama-3-8B":
+    force5 = os.environ.get("MDI_BENCH_FORCE_CFG5", "") not in ("", "0")  # exercise the extra job below at any N (harness test)
+    if args.extras and (world == 8 or force5) and not args.tiny and args.weights == "bf16" and args.model == "Llama-3-8B":
         a = copy.copy(args)  # BASELINE config #5: fp8 block-scaled weights, 1024-token prompts, 2048-token context
         a.weights, a.prompt_len, a.seq_len, a.steps, a.warmup = "fp8", 1024, 2048, 256, 8
         extras.append(("baseline_config_5_fp8_2048ctx", a))
