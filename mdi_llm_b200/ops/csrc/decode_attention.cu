@@ -13,7 +13,10 @@
 //     is a latency chain (ctx -> q -> K -> softmax -> V -> merge), not a bandwidth problem; small
 //     tiles over many warps keep the serial instruction count per warp low;
 //   * the last CTA of a group to finish merges the spans (atomic ticket) and writes bf16
-//     y[H*hs] directly: no separate combine launch.
+//     y[H*hs] directly: no separate combine launch;
+//   * K / V of OLD positions do not depend on this step's QKV projection: every warp requests its first tile
+//     BEFORE the programmatic-dependency wait (the kernel is resident while the QKV kernel still streams its
+//     weights), so after the wait only q — and the tile that holds the newest position — remain to be fetched.
 #include "common.cuh"
 
 namespace mdi {
@@ -54,28 +57,60 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const AttnArgs
   const int g = blockIdx.x, split = blockIdx.y;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   trace_mark(a.trace, 0, true);
-  if (a.dep_wait.flag) dep_wait(a.dep_wait, a.ctx); else pdl_wait_prior();
-  trace_mark(a.trace, 1, true);
+  // ctx was written at the start of the step (advance_step / the host's descriptor copy), at least two launches ago:
+  // readable before the dependency wait
   const int slot = a.ctx[MDI_CTX_SLOT], L = a.ctx[MDI_CTX_POS] + 1;
-  pdl_launch_dependents();
-
   // spans of whole tiles, at least ATT_WARPS tiles (128 positions) each
   const int tiles = (L + ATT_TILE - 1) / ATT_TILE;
   int tiles_per_split = (tiles + a.n_split - 1) / a.n_split;
   if (tiles_per_split < ATT_WARPS) tiles_per_split = ATT_WARPS;
   const int n_active = (tiles + tiles_per_split - 1) / tiles_per_split;
-  if (split >= n_active) { dep_signal(a.dep_signal, a.ctx); return; }  // idle span: only its ticket
-  trace_mark(a.trace, 2, false);
+  const bool active = split < n_active;
   const int t_lo = split * tiles_per_split, t_hi = min(tiles, t_lo + tiles_per_split);
+  const bf16* kbase = a.kv + (((size_t)slot * 2 + 0) * a.n_groups + g) * (size_t)a.max_seq * HS;
+  const bf16* vbase = a.kv + (((size_t)slot * 2 + 1) * a.n_groups + g) * (size_t)a.max_seq * HS;
+
+  // K / V registers of one tile.  PRE: the whole tile's K (all passes) and V are requested together, so the warp's
+  // first tile can be requested before the wait when it only holds positions older than this step's
+  constexpr bool PRE = V_EARLY && (KPASS == ATT_NPASS);
+  uint4 kk[KPASS][KV4];
+  uint32_t vv[VB][DPL / 2];
+  auto load_k = [&](int p0, int pg) {
+#pragma unroll
+    for (int pp = 0; pp < KPASS; ++pp) {
+      const int pos = min(p0 + (pg * KPASS + pp) * 8 + (lane >> 2), L - 1);  // clamp: masked below
+      const uint4* kr = reinterpret_cast<const uint4*>(kbase + (size_t)pos * HS + (lane & 3) * QDIM);
+#pragma unroll
+      for (int v = 0; v < KV4; ++v) kk[pp][v] = __ldg(kr + v);
+    }
+  };
+  auto load_v = [&](int p0, int half) {
+#pragma unroll
+    for (int r = 0; r < VB; ++r) {
+      const int pos = min(p0 + half * VB + r, L - 1);  // masked rows have p == 0
+      const uint32_t* vr = reinterpret_cast<const uint32_t*>(vbase + (size_t)pos * HS + lane * DPL);
+#pragma unroll
+      for (int w = 0; w < DPL / 2; ++w) vv[r][w] = __ldg(vr + w);
+    }
+  };
+  const int t_first = t_lo + warp;
+  bool pre = false;
+  if (PRE && active && t_first < t_hi && (t_first + 1) * ATT_TILE <= L - 1) {  // no row of this tile is written by this step
+    load_k(t_first * ATT_TILE, 0);
+    load_v(t_first * ATT_TILE, 0);
+    pre = true;
+  }
+  if (a.dep_wait.flag) dep_wait(a.dep_wait, a.ctx); else pdl_wait_prior();
+  trace_mark(a.trace, 1, true);
+  pdl_launch_dependents();
+  if (!active) { dep_signal(a.dep_signal, a.ctx); return; }  // idle span: only its ticket
+  trace_mark(a.trace, 2, false);
 
   for (int i = threadIdx.x; i < QPK * HS; i += ATT_THREADS) {
     const int h = i / HS, d = i % HS;
     q_s[h][d] = __bfloat162float(a.q[(size_t)(g * QPK + h) * HS + d]) * a.scale_log2;
   }
   __syncthreads();
-
-  const bf16* kbase = a.kv + (((size_t)slot * 2 + 0) * a.n_groups + g) * (size_t)a.max_seq * HS;
-  const bf16* vbase = a.kv + (((size_t)slot * 2 + 1) * a.n_groups + g) * (size_t)a.max_seq * HS;
 
   float m[QPK], l[QPK], acc[QPK][DPL];
 #pragma unroll
@@ -85,30 +120,16 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const AttnArgs
     for (int d = 0; d < DPL; ++d) acc[h][d] = 0.f;
   }
 
-  for (int t = t_lo + warp; t < t_hi; t += ATT_WARPS) {
+  for (int t = t_first; t < t_hi; t += ATT_WARPS) {
     const int p0 = t * ATT_TILE;
+    const bool have = PRE && pre && t == t_first;  // requested before the wait
     // ---- issue the K loads of KPASS passes (8 positions each) and the V rows up-front, then consume --
-    uint32_t vv[VB][DPL / 2];
-    auto load_v = [&](int half) {
-#pragma unroll
-      for (int r = 0; r < VB; ++r) {
-        const int pos = min(p0 + half * VB + r, L - 1);  // masked rows have p == 0
-        const uint32_t* vr = reinterpret_cast<const uint32_t*>(vbase + (size_t)pos * HS + lane * DPL);
-#pragma unroll
-        for (int w = 0; w < DPL / 2; ++w) vv[r][w] = __ldg(vr + w);
-      }
-    };
 #pragma unroll
     for (int pg = 0; pg < ATT_NPASS / KPASS; ++pg) {
-      uint4 kk[KPASS][KV4];
-#pragma unroll
-      for (int pp = 0; pp < KPASS; ++pp) {
-        const int pos = min(p0 + (pg * KPASS + pp) * 8 + (lane >> 2), L - 1);  // clamp: masked below
-        const uint4* kr = reinterpret_cast<const uint4*>(kbase + (size_t)pos * HS + (lane & 3) * QDIM);
-#pragma unroll
-        for (int v = 0; v < KV4; ++v) kk[pp][v] = __ldg(kr + v);
+      if (!have) {
+        load_k(p0, pg);
+        if (V_EARLY && pg == 0) load_v(p0, 0);
       }
-      if (V_EARLY && pg == 0) load_v(0);
 #pragma unroll
       for (int pp = 0; pp < KPASS; ++pp) {
         const int pj = (pg * KPASS + pp) * 8 + (lane >> 2), pos = p0 + pj, qd = (lane & 3) * QDIM;
@@ -157,7 +178,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const AttnArgs
     // ---- PV: lane owns DPL consecutive output dims ---------------------------------------------------
 #pragma unroll
     for (int half = 0; half < ATT_TILE / VB; ++half) {
-      if (!V_EARLY) load_v(half);
+      if (!V_EARLY) load_v(p0, half);
 #pragma unroll
       for (int r = 0; r < VB; ++r) {
 #pragma unroll
