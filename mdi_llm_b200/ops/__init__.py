@@ -44,6 +44,7 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.mdi_qkv_decode.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, i32, i32, i32, f32, i32,
                                    vp, vp, i64, i32, i32, i32, vp, vp, vp, vp, vp, vp, i32, vp]
     lib.mdi_set_linear_variant.argtypes = [i32]
+    lib.mdi_set_attn_cluster.argtypes = [i32]
     lib.mdi_set_l2_prefetch_mb.argtypes = [i32]
     lib.mdi_get_linear_variant.restype = i32
     lib.mdi_attn_decode.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, i64, vp]
@@ -110,6 +111,8 @@ def lib() -> ctypes.CDLL:
         _lib = handle
         if os.environ.get("MDI_PREFILL_ATTN_PIPE"):
             handle.mdi_set_prefill_attn_pipe(int(os.environ["MDI_PREFILL_ATTN_PIPE"]))
+        if os.environ.get("MDI_ATTN_CLUSTER"):
+            handle.mdi_set_attn_cluster(int(os.environ["MDI_ATTN_CLUSTER"]))
         if os.environ.get("MDI_L2_PF_MB"):
             handle.mdi_set_l2_prefetch_mb(int(os.environ["MDI_L2_PF_MB"]))
         return handle

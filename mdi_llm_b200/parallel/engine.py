@@ -176,7 +176,11 @@ class FusedStage:
             self.y_attn = torch.zeros(cfg.n_head * cfg.head_size, **bf)
             self.h_mlp = torch.zeros(cfg.intermediate_size, **bf)
             sms = torch.cuda.get_device_properties(dev).multi_processor_count
+            # split-KV spans per KV group: ~2 CTAs per SM over all groups, a multiple of 8 so that the spans of a group
+            # launch as clusters of 8 (short contexts merge through distributed shared memory, decode_attention.cu)
             self.n_split = max(1, min(64, (2 * sms) // max(1, cfg.n_query_groups)))
+            if self.n_split >= 8:
+                self.n_split = (self.n_split + 7) // 8 * 8
             self.part = torch.zeros(cfg.n_head * self.n_split * (cfg.head_size + 2), dtype=torch.float32, device=dev)
             self.tickets = torch.zeros(cfg.n_query_groups, **i32)
             if self.is_starter:

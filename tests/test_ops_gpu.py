@@ -141,7 +141,7 @@ def test_qkv_decode_rope_and_kv_append(H, G, hs, ne, C, variant):
 
 
 @pytest.mark.parametrize("H,G,hs", [(32, 8, 128), (32, 4, 64), (8, 8, 64), (8, 1, 128), (4, 2, 128)])
-@pytest.mark.parametrize("L", [1, 15, 16, 17, 31, 32, 33, 129, 500, 2048])
+@pytest.mark.parametrize("L", [1, 15, 16, 17, 31, 32, 33, 129, 500, 1024, 1025, 2048])
 def test_attn_decode_matches_sdpa(H, G, hs, L):
     ops = _ops()
     torch.manual_seed(L)
@@ -150,7 +150,9 @@ def test_attn_decode_matches_sdpa(H, G, hs, L):
     kv = torch.randn(n_slots, 2, G, S, hs, device="cuda").bfloat16()
     y = torch.zeros(H * hs, device="cuda", dtype=torch.bfloat16)
     tickets = torch.zeros(G, device="cuda", dtype=torch.int32)
-    for n_split in (1, 5, 37):
+    # 8 / 40: multiples of the cluster size -> spans launch as clusters of 8 and contexts of 129..1024 positions merge
+    # through distributed shared memory; longer ones (and the other split counts) take the ticket merge
+    for n_split in (1, 5, 37, 8, 40):
         part = torch.zeros(H * n_split * (hs + 2), device="cuda", dtype=torch.float32)
         y.zero_()
         ops.attn_decode(q, kv, y, part, tickets, _ctx(ops, slot=slot, pos=L - 1), n_head=H, n_groups=G, head_size=hs,
