@@ -584,10 +584,17 @@ def main() -> None:
             sys.stdout.flush()
             os.dup2(saved, 1)
             os.close(saved)
-    elif args.direct:
-        out = run_direct(args)
     else:
-        out = run_ours(args)
+        # stdout carries exactly ONE line (the JSON): anything the framework prints while it runs goes to stderr
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            out = run_direct(args) if args.direct else run_ours(args)
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     if out:
         print(json.dumps(out), flush=True)
     if args.impl == "reference-nccl":  # RX threads may sit in a posted NCCL recv: leave without tearing the communicators down

@@ -228,13 +228,16 @@ class FusedStage:
         for blk in self.model.transformer.h:
             if getattr(blk, "has_attn", True):
                 lins += [blk.attn.attn, blk.attn.proj]
-            if hasattr(blk.mlp, "fc"):  # plain two-matrix MLP
-                lins += [blk.mlp.fc, blk.mlp.proj]
+            mlp = getattr(blk, "mlp", None)  # absent in a block cut down to its attention
+            if mlp is None:
+                continue
+            if hasattr(mlp, "fc"):  # plain two-matrix MLP
+                lins += [mlp.fc, mlp.proj]
                 continue
             if getattr(blk, "has_gu", True):
-                lins += [blk.mlp.fc_1, blk.mlp.fc_2]
+                lins += [mlp.fc_1, mlp.fc_2]
             if getattr(blk, "has_down", True):
-                lins.append(blk.mlp.proj)
+                lins.append(mlp.proj)
         if self.is_starter and not self.cfg.tie_embeddings:
             lins.append(self.model.lm_head)
         with torch.cuda.device(self.device):
