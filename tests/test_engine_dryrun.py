@@ -216,6 +216,23 @@ def test_third_unit_stages_bind_and_route_the_wide_message():
         assert gemms[0]["residual"] is not None and gemms[0].get("w2") is None and gemms[-1]["out_ptr"] == 0x5000
 
 
+@pytest.mark.parametrize("kw", [dict(last_parts="attn"), dict(first_parts="down"), dict(first_parts="mlp", last_parts="attn_gu")])
+def test_fp8_quantisation_covers_partial_blocks(kw):
+    """Sub-layer stages in fp8: a block cut down to its attention has no MLP to quantise, a gate/up-only or a
+    down-only block quantises exactly the projections it owns (the 8-GPU fp8 job of bench.py hit this)."""
+    import mdi_llm_b200.utils.quantize as Q
+
+    with dry_ops() as calls:
+        st = _stage("secondary:0", 2, **kw)
+        fake = lambda w: (torch.zeros(w.shape, dtype=torch.uint8), torch.ones(w.shape[0], max(1, w.shape[1] // 128)))  # noqa: E731
+        with mock.patch.object(Q, "quantize_fp8_block", fake):
+            fs = FusedStage(st, n_slots=1, max_seq_length=32, weight_dtype="fp8")
+        n_lin = sum(1 for n, _ in st.named_parameters() if n.endswith(".weight") and (".attn." in n or ".mlp." in n))
+        assert len(fs._q) == n_lin == len(fs._qt)
+        fs.enqueue_blocks(HopTarget(0x1000, 0x2000), wait_input=True)
+        assert all(c[1].get("wscale") is not None for c in calls if c[0] in ("linear_decode", "qkv_decode"))
+
+
 # ---- DevicePipeline orchestration (fake graphs, no GPU) ---------------------------------------------------
 class _FakeGraph:
     instances = []
