@@ -147,9 +147,23 @@ __device__ __forceinline__ void stage_input_layernorm(const bf16* __restrict__ x
   __syncthreads();
 }
 
+// `w_pre`: the norm weights of this thread's vectors, requested BEFORE the dependency wait (they are static; after
+// ~200 MB of streamed matrices they are no longer in L2, so loading them next to x put a DRAM round trip on the
+// post-wait critical path of every normalising kernel).
+__device__ __forceinline__ void preload_norm_w(const bf16* __restrict__ norm_w, int K, uint4 (&w_pre)[4]) {
+  const uint4* wsrc = reinterpret_cast<const uint4*>(norm_w);
+  const int nvec = K / 8;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int v = threadIdx.x + j * 256;
+    w_pre[j] = v < nvec ? __ldg(wsrc + v) : make_uint4(0, 0, 0, 0);
+  }
+}
+
 __device__ __forceinline__ void stage_input(const bf16* __restrict__ x, const bf16* __restrict__ norm_w,
                                             float eps, int unit_offset, int K, bf16* xs, float* red,
-                                            const bf16* __restrict__ norm_b = nullptr, int layer_norm = 0) {
+                                            const bf16* __restrict__ norm_b = nullptr, int layer_norm = 0,
+                                            const uint4* w_pre = nullptr) {
   if (layer_norm && norm_w != nullptr) { stage_input_layernorm(x, norm_w, norm_b, eps, K, xs, red); return; }
   const int tid = threadIdx.x;
   const int nvec = K / 8;
@@ -178,7 +192,7 @@ __device__ __forceinline__ void stage_input(const bf16* __restrict__ x, const bf
 #pragma unroll
     for (int j = 0; j < STAGE_VPT; ++j) {
       const int v = tid + j * LIN_THREADS;
-      if (v < nvec) { xr[j] = __ldcg(src + v); wr[j] = __ldg(wsrc + v); }
+      if (v < nvec) { xr[j] = __ldcg(src + v); wr[j] = w_pre ? w_pre[j] : __ldg(wsrc + v); }
       else { xr[j] = make_uint4(0, 0, 0, 0); wr[j] = xr[j]; }
     }
     float ss = 0.f;
@@ -533,11 +547,15 @@ __global__ void __launch_bounds__(LIN_THREADS, STAGES == 2 ? 3 : (STAGES == 3 ? 
 
   int slot = 0, pos = 0;
   if (a.ctx_early && a.ctx) { slot = a.ctx[MDI_CTX_SLOT]; pos = a.ctx[MDI_CTX_POS]; }  // off the post-wait chain
+  uint4 w_pre[4];
+  const bool have_w = a.norm_w != nullptr && !a.layer_norm && a.K <= STAGE_VPT * LIN_THREADS * 8;
+  if (have_w) preload_norm_w(a.norm_w, a.K, w_pre);
   if (a.dep_wait.flag) dep_wait(a.dep_wait, a.ctx); else pdl_wait_prior();
   hop_wait(a.wait, a.ctx);
   trace_mark(a.trace, 1, true);
   if (!a.ctx_early && a.ctx) { slot = a.ctx[MDI_CTX_SLOT]; pos = a.ctx[MDI_CTX_POS]; }
-  stage_input(a.x + (size_t)slot * a.x_slot_stride, a.norm_w, a.eps, a.unit_offset, a.K, xs, red, a.norm_b, a.layer_norm);
+  stage_input(a.x + (size_t)slot * a.x_slot_stride, a.norm_w, a.eps, a.unit_offset, a.K, xs, red, a.norm_b, a.layer_norm,
+              have_w ? w_pre : nullptr);
   trace_mark(a.trace, 2, false);
   pdl_launch_dependents();
 
