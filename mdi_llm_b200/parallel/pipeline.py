@@ -361,11 +361,25 @@ class DevicePipeline:
         return launched
 
     def decode_rounds_host(self, n_rounds: int, on_token: Optional[Callable[[int, int, int], None]] = None) -> Tuple[int, int, int]:
-        """Host-fed variant (end-to-end mode): per step the descriptor goes H2D from pinned memory
-        and, on the starter, the sampled token comes back D2H before the next step is issued.
+        """Host-fed variant (end-to-end / streaming mode): per step the descriptor goes H2D from pinned memory and,
+        on the starter, the sampled token comes back D2H into pinned memory and is handed to ``on_token``.  The read-back
+        of step t is awaited AFTER step t+1 has been issued (its descriptor does not depend on the token — the device
+        reads tokens from its own ring), so the GPU is not idle during the host's turnaround.
         Returns (launches, h2d_bytes, d2h_bytes)."""
         st = self.stage
         launched = h2d = d2h = 0
+        use_events = self.is_starter and st.last_token.is_cuda
+        if use_events and not hasattr(self, "_tok_pinned"):
+            self._tok_pinned = torch.zeros(4, dtype=torch.int32).pin_memory()
+            self._tok_events = [torch.cuda.Event() for _ in range(4)]
+        pending: Optional[Tuple[int, int, int]] = None  # (ring index, slot, pos) of the step whose token is still in flight
+
+        def deliver(p: Tuple[int, int, int]) -> None:
+            i, slot_, pos_ = p
+            self._tok_events[i].synchronize()
+            if on_token is not None:
+                on_token(slot_, pos_, int(self._tok_pinned[i]))
+
         with torch.cuda.device(self.device):
             for _ in range(n_rounds):
                 r = self.round
@@ -385,11 +399,21 @@ class DevicePipeline:
                     if not self.is_starter and launched % 2048 == 0:
                         torch.cuda.current_stream().synchronize()  # keep the pinned ctx ring ahead of the GPU
                     if self.is_starter:
-                        tok = int(st.last_token[slot].item())  # D2H + sync: the token the user sees
                         d2h += 4
-                        if on_token is not None:
-                            on_token(slot, pos, tok)
+                        if use_events:
+                            i = launched % 4
+                            self._tok_pinned[i: i + 1].copy_(st.last_token[slot: slot + 1], non_blocking=True)
+                            self._tok_events[i].record()
+                            if pending is not None:
+                                deliver(pending)
+                            pending = (i, slot, pos)
+                        else:  # CPU dry run of the orchestration
+                            tok = int(st.last_token[slot].item())
+                            if on_token is not None:
+                                on_token(slot, pos, tok)
                 self.round += 1
+            if pending is not None:
+                deliver(pending)
         self.n_graph_launches += launched
         return launched, h2d, d2h
 
