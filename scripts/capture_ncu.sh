@@ -7,7 +7,7 @@ mkdir -p gpurun_out
 for what in ${@:-decode gemm attn}; do
   case $what in
     decode) k="regex:stream_bulk_kernel" ;;
-    gemm)   k="regex:gemm_bf16_tcgen05_kernel" ;;
+    gemm)   k="regex:gemm_bf16_tcgen05_pair_kernel" ;;
     attn)   k="regex:attn_decode_kernel" ;;
     attnp)  k="regex:attn_prefill_tcgen05_kernel" ;;
     gemm_fp8) k="regex:gemm_fp8_blockscaled_kernel" ;;

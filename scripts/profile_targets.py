@@ -1,8 +1,8 @@
 #!/usr/bin/env python3
 """Small deterministic workloads for `ncu --set full` captures (see profiles/README.md):
    decode: the Llama-3-8B gate/up weight-streaming kernel (+RMSNorm, SiLU*mul epilogue), 235 MB of weights
-   gemm  : the tcgen05 prefill GEMM 2048 x 14336 x 4096
-   attn  : decode attention at 2048 context, Llama-3-8B heads
+   gemm  : the tcgen05 CTA-pair prefill GEMM 2048 x 14336 x 4096
+   attn  : decode attention at 470 live positions (cluster merge), Llama-3-8B heads
    attnp : tcgen05 prefill attention, 2048-token prompt, Llama-3-8B heads
    gemm_fp8: the block-scaled fp8 GEMM (tcgen05 kind::f8f6f4) 2048 x 6144 x 4096"""
 import os
@@ -30,17 +30,17 @@ elif what == "gemm":
     a = torch.randn(M, K, device="cuda").bfloat16()
     w = torch.randn(N, K, device="cuda").bfloat16()
     for _ in range(4):
-        ops.gemm(a, w, block_n=256)
+        ops.gemm(a, w, block_n=512)  # the CTA-pair kernel (cta_group::2)
 elif what == "attn":
     H, G, hs, S = 32, 8, 128, 4096
     q = torch.randn(H * hs, device="cuda").bfloat16()
     kv = torch.randn(1, 2, G, S, hs, device="cuda").bfloat16()
     y = torch.zeros(H * hs, device="cuda", dtype=torch.bfloat16)
-    part = torch.zeros(H * 37 * (hs + 2), device="cuda")
+    part = torch.zeros(H * 40 * (hs + 2), device="cuda")
     tickets = torch.zeros(G, dtype=torch.int32, device="cuda")
-    ctx[1] = 2047
+    ctx[1] = int(sys.argv[2]) - 1 if len(sys.argv) > 2 else 469  # live context: 470 positions -> 4 spans, cluster (DSMEM) merge
     for _ in range(4):
-        ops.attn_decode(q, kv, y, part, tickets, ctx, n_head=H, n_groups=G, head_size=hs, max_seq=S, n_split=37)
+        ops.attn_decode(q, kv, y, part, tickets, ctx, n_head=H, n_groups=G, head_size=hs, max_seq=S, n_split=40)
 elif what == "gemm_fp8":
     from mdi_llm_b200.utils.quantize import quantize_fp8_block
 
