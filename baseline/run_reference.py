@@ -215,12 +215,16 @@ def run_reference(args: Any, variant: str = "reference") -> Dict[str, Any]:
             "warmup": args.warmup, "ms_per_step": round(dt * 1e3 / args.steps, 5), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if dtype == "bfloat16" else dtype,
             "data": "synthetic prompts, random-init weights", "impl": variant,
+            # `config`: identical keys / values to the ours arm (bench.py); how this arm runs it is under `details`
             "config": {"model": cfg.name, "global_batch": n_samples, "seq_len": seq_len, "prompt_len": args.prompt_len,
-                       "parallelism": f"pp{world} recurrent pipeline (reference table split)" + (f", INJECTED table entry {injected}" if injected else ""),
-                       "tokens_per_step": n_samples,
-                       "transport": transport_desc, "compute": "eager PyTorch / cuBLAS",
-                       "timing": "the reference's own per-token wall-clock timeline on the starter (tok_time)",
-                       "shims": ["cherrypy", "accelerate", "matplotlib"], "setup_s": round(setup_s, 1)},
+                       "parallelism": f"pp{world}", "tokens_per_step": n_samples,
+                       "sampling": {"temperature": 0.8, "top_k": 200},
+                       "l2_policy": "inputs (stage weights) larger than L2, no flush"},
+            "details": {"partition": "reference table split" + (f", INJECTED table entry {injected}" if injected else ""),
+                        "transport": transport_desc, "compute": "eager PyTorch / cuBLAS",
+                        "sampling_source": "the reference's defaults (TOP_K = 200, TEMPERATURE = 0.8, config.py:47-52)",
+                        "timing": "the reference's own per-token wall-clock timeline on the starter (tok_time)",
+                        "shims": ["cherrypy", "accelerate", "matplotlib"], "setup_s": round(setup_s, 1)},
             "e2e": {"value": round(value, 3), "unit": "tokens/s", "note": "reference timing is end-to-end by construction"},
             "gpu_launches": 0,
         }

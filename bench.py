@@ -461,14 +461,17 @@ def run_job(args: argparse.Namespace, job: int = 0, light: bool = False) -> Dict
             "vs_baseline": _vs_published(cfg.name, world, value),
             "dtype": "bf16" if args.weights == "bf16" else "fp8-e4m3 block-scaled weights (128), bf16 activations, fp32 accumulate",
             "data": "synthetic prompts, random-init weights", "impl": "ours",
-            "config": {"model": cfg.name, "n_layer": cfg.n_layer, "global_batch": n_samples, "seq_len": seq_len,
-                       "prompt_len": args.prompt_len, "parallelism": f"pp{world} recurrent pipeline, plan {plan}",
-                       "tokens_per_step": n_samples, "l2_policy": "inputs (stage weights) larger than L2, no flush",
+            # `config`: the benchmark configuration proper — the SAME keys and values in both arms (see baseline/run_reference.py);
+            # everything that describes how this arm runs it is under `details`
+            "config": {"model": cfg.name, "global_batch": n_samples, "seq_len": seq_len, "prompt_len": args.prompt_len,
+                       "parallelism": f"pp{world}", "tokens_per_step": n_samples,
                        "sampling": {"temperature": args.temperature, "top_k": args.top_k},
-                       "api": "GPTDistributed(starter) + GPTDistributed(secondary:i) per GPU, HTTP control plane, "
-                              "CUDA-IPC handles exchanged at POST /init",
-                       "hop": ("NCCL send/recv (baseline midpoint)" if args.hop == "nccl" else "fused P2P store + flag (NVLink)") if world > 1 else "local (standalone ring)",
-                       "timing": "CUDA events around each node's K decode rounds, max over nodes"},
+                       "l2_policy": "inputs (stage weights) larger than L2, no flush"},
+            "details": {"n_layer": cfg.n_layer, "plan_layers_per_stage": plan, "partition": args.partition,
+                        "api": "GPTDistributed(starter) + GPTDistributed(secondary:i) per GPU, HTTP control plane, "
+                               "CUDA-IPC handles exchanged at POST /init",
+                        "hop": ("NCCL send/recv (baseline midpoint)" if args.hop == "nccl" else "fused P2P store + flag (NVLink)") if world > 1 else "local (standalone ring)",
+                        "timing": "CUDA events around each node's K decode rounds, max over nodes"},
             "clocks": clocks, "e2e": e2e,
             "prefill_ms_all_samples": round(warm["prefill_ms"], 3), "gpu_launches": int(launches),
             "hop_watchdog_status": max(max(r["status"]) for r in timed["per_node"]),
@@ -564,7 +567,7 @@ def run_ours(args: argparse.Namespace) -> Dict[str, Any]:
             r = {"error": repr(e)[:300]}
         if out:
             out[key] = {k: r[k] for k in ("value", "unit", "dtype", "steps", "warmup", "ms_per_step", "prefill_ms_all_samples",
-                                          "tokens_match", "tokens_match_what", "config", "error") if k in r}
+                                          "tokens_match", "tokens_match_what", "config", "details", "error") if k in r}
     return out
 
 

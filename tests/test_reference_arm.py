@@ -81,6 +81,8 @@ def test_reference_variants_cpu(tmp_path, impl, world):
     out = json.loads(lines[0])
     assert out["impl"] == impl and out["n_gpus"] == world and out.get("value", 0) > 0, out
     if impl == "reference-table":
-        assert "INJECTED" in out["config"]["parallelism"]
+        assert "INJECTED" in out["details"]["partition"]
     else:
-        assert "torch.distributed" in out["config"]["transport"]
+        assert "torch.distributed" in out["details"]["transport"]
+    assert set(out["config"]) == {"model", "global_batch", "seq_len", "prompt_len", "parallelism", "tokens_per_step", "sampling",
+                                  "l2_policy"}  # the keys the ours arm prints too
