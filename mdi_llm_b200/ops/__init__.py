@@ -43,6 +43,9 @@ def _declare(lib: ctypes.CDLL) -> None:
                                       vp, i64, vp, vp, c_ulonglong, i32, vp, i64, i32, vp, i32, vp]
     lib.mdi_qkv_decode.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, i32, i32, i32, f32, i32,
                                    vp, vp, i64, i32, i32, i32, vp, vp, vp, vp, vp, vp, i32, vp]
+    lib.mdi_moe_router.argtypes = [vp, vp, vp, vp, i32, vp, i64, i32, i32, i32, f32, i32, vp, vp, vp, vp, i64, i32, vp, vp]
+    lib.mdi_moe_linear_decode.argtypes = [vp, vp, vp, vp, i32, vp, vp, vp, vp, i32, vp, vp, vp, i64, i64, i64, i32, i32, f32,
+                                          i32, i32, vp, vp, vp, vp, i64, i32, i32, vp, vp]
     lib.mdi_set_linear_variant.argtypes = [i32]
     lib.mdi_set_attn_cluster.argtypes = [i32]
     lib.mdi_set_l2_prefetch_mb.argtypes = [i32]
@@ -228,6 +231,48 @@ def linear_decode(
         prefetch[0] if prefetch else None, prefetch[1] if prefetch else None, prefetch[2] if prefetch else 0, l2_pf_chunks,
         hop_pre[0] if hop_pre else None, hop_pre[1] if hop_pre else 0, hop_pre[2] if hop_pre else 0,
         ptr(norm_b), int(layer_norm), stream_ptr()), "linear_decode")
+
+
+def moe_router(Wg: torch.Tensor, x: torch.Tensor, sel: torch.Tensor, wts: torch.Tensor, ctx: torch.Tensor, *, top: int,
+               norm_w: Optional[torch.Tensor] = None, norm_b: Optional[torch.Tensor] = None, layer_norm: bool = False,
+               eps: float = 1e-5, unit_offset: bool = False, x_slot_stride: int = 0, wait_flag: Optional[int] = None,
+               status: Optional[int] = None, wait_max_cycles: int = 0, use_pdl: bool = False, trace: Optional[int] = None,
+               x_ptr: Optional[int] = None) -> None:
+    """Router of a mixture-of-experts MLP for one token: ``logits = Wg @ norm(x)`` (bf16), the ``top`` best experts
+    and the softmax over their logits -> ``sel`` (int32 ``[top]``) / ``wts`` (fp32 ``[top]``, bf16 values) on the
+    device — nothing comes back to the host, the expert passes read both through :func:`moe_linear_decode`."""
+    _bf16(Wg, "Wg")
+    E, K = Wg.shape
+    if sel.dtype != torch.int32 or wts.dtype != torch.float32 or sel.numel() < top or wts.numel() < top:
+        raise OpsError("moe_router: sel must be int32 [top], wts fp32 [top]")
+    check(lib().mdi_moe_router(ptr(Wg), x_ptr if x_ptr is not None else ptr(x), ptr(norm_w), ptr(norm_b), int(layer_norm),
+                               ptr(ctx), x_slot_stride, K, E, top, eps, int(unit_offset), ptr(sel), ptr(wts), wait_flag, status,
+                               wait_max_cycles, int(use_pdl), trace, stream_ptr()), "moe_router")
+
+
+def moe_linear_decode(w_ptrs: torch.Tensor, x: torch.Tensor, y: Optional[torch.Tensor], ctx: torch.Tensor, sel: torch.Tensor,
+                      wts: torch.Tensor, k: int, *, N: int, K: int, w2_ptrs: Optional[torch.Tensor] = None,
+                      prev: Optional[torch.Tensor] = None, norm_w: Optional[torch.Tensor] = None,
+                      norm_b: Optional[torch.Tensor] = None, layer_norm: bool = False, residual: Optional[torch.Tensor] = None,
+                      residual_ptr: Optional[int] = None, eps: float = 1e-5, unit_offset: bool = False, act: str = "none",
+                      x_slot_stride: int = 0, res_slot_stride: int = 0, y_slot_stride: int = 0, y_ptr: Optional[int] = None,
+                      status: Optional[int] = None, signal_flag: Optional[int] = None, done_ctr: Optional[int] = None,
+                      hop_ptr: Optional[int] = None, hop_slot_stride: int = 0, ctas_per_sm: int = 3, use_pdl: bool = False,
+                      trace: Optional[int] = None, x_ptr: Optional[int] = None) -> None:
+    """One expert pass of a routed token.  ``w_ptrs`` / ``w2_ptrs``: int64 ``[E]`` device tables of the experts' weight
+    pointers (``[N, K]`` bf16 each); the kernel reads ``sel[k]`` AFTER its dependency wait and streams only that
+    expert.  With ``w2_ptrs``: ``y = act(W1 norm(x)) * (W2 norm(x))``; without: the down pass
+    ``y = bf16(wts[k] * bf16(W x)) (+ prev) (+ residual)``, optionally finishing the stage's hop like
+    :func:`linear_decode`."""
+    for t, n in ((w_ptrs, "w_ptrs"), (w2_ptrs, "w2_ptrs")):
+        if t is not None and (t.dtype != torch.int64 or not t.is_cuda):
+            raise OpsError(f"moe_linear_decode: {n} must be an int64 device tensor of pointers")
+    check(lib().mdi_moe_linear_decode(
+        ptr(w_ptrs), ptr(w2_ptrs), ptr(sel), ptr(wts), k, ptr(prev), x_ptr if x_ptr is not None else ptr(x), ptr(norm_w),
+        ptr(norm_b), int(layer_norm), residual_ptr if residual_ptr is not None else ptr(residual),
+        y_ptr if y_ptr is not None else ptr(y), ptr(ctx), x_slot_stride, res_slot_stride, y_slot_stride, N, K, eps,
+        int(unit_offset), ACT[act], status, signal_flag, done_ctr, hop_ptr, hop_slot_stride, ctas_per_sm, int(use_pdl), trace,
+        stream_ptr()), "moe_linear_decode")
 
 
 def qkv_decode(

@@ -847,6 +847,151 @@ __global__ void __launch_bounds__(LIN_THREADS, 3) stream_bulk_fp8_kernel(const S
   trace_mark(a.trace, 4, false);
 }
 
+// ---- mixture of experts (LLaMAMoE, model.py:823-853) ------------------------------------------------------
+// The reference routes with torch.topk + torch.where (a host sync per layer) and loops over ALL experts.  Here the
+// router is one small kernel that leaves the token's expert ids and routing weights in device memory, and each of
+// the token's `top` experts is one gate/up + one down launch whose weight base pointers are looked up through a
+// device pointer table AFTER the dependency wait — so a decode step streams only the chosen experts' matrices
+// (Mixtral: 2 of 8) and stays graph-capturable.  Rounding points follow the eager module: logits, routing weights,
+// each expert's output and the running sum are bf16.
+struct RouterArgs {
+  const bf16* Wg;        // [E, K] router matrix
+  const bf16* x;         // residual stream row: x + slot * x_slot_stride
+  const bf16* norm_w;    // the block's norm_2
+  const bf16* norm_b;
+  int layer_norm;
+  const int* ctx;
+  long long x_slot_stride;
+  int K, E, top;
+  float eps;
+  int unit_offset;
+  int* sel;              // out [top]: chosen expert ids, best first
+  float* wts;            // out [top]: softmax over the chosen logits (bf16 values)
+  HopWait wait;
+  unsigned long long* trace;
+};
+
+constexpr int MOE_MAX_EXPERTS = 256;
+constexpr int MOE_MAX_TOP = 8;
+
+__global__ void __launch_bounds__(LIN_THREADS) moe_router_kernel(const RouterArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  bf16* xs = reinterpret_cast<bf16*>(smem_raw);
+  __shared__ float red[LIN_WARPS];
+  __shared__ float logit_s[MOE_MAX_EXPERTS];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  trace_mark(a.trace, 0, true);
+  pdl_wait_prior();
+  hop_wait(a.wait, a.ctx);
+  trace_mark(a.trace, 1, true);
+  const int slot = a.ctx ? a.ctx[MDI_CTX_SLOT] : 0;
+  stage_input(a.x + (size_t)slot * a.x_slot_stride, a.norm_w, a.eps, a.unit_offset, a.K, xs, red, a.norm_b, a.layer_norm);
+  trace_mark(a.trace, 2, false);
+  pdl_launch_dependents();  // the expert kernels still wait for this grid to COMPLETE before they read sel / wts
+  const uint4* xv = reinterpret_cast<const uint4*>(xs);
+  const int nvec = a.K / 8;
+  for (int e = warp; e < a.E; e += LIN_WARPS) {
+    const uint4* w = reinterpret_cast<const uint4*>(a.Wg + (size_t)e * a.K);
+    float s = 0.f;
+    for (int v = lane; v < nvec; v += 32) s += dot8(__ldg(w + v), xv[v]);
+    s = warp_sum(s);
+    if (lane == 0) logit_s[e] = round_bf16(s);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int chosen[MOE_MAX_TOP];
+    float val[MOE_MAX_TOP];
+    for (int k = 0; k < a.top; ++k) {  // E is small: selection by repeated arg-max, lowest index wins ties
+      int best = -1;
+      float bv = 0.f;
+      for (int e = 0; e < a.E; ++e) {
+        bool taken = false;
+        for (int j = 0; j < k; ++j) taken |= chosen[j] == e;
+        if (!taken && (best < 0 || logit_s[e] > bv)) { best = e; bv = logit_s[e]; }
+      }
+      chosen[k] = best;
+      val[k] = bv;
+    }
+    float den = 0.f;
+    for (int k = 0; k < a.top; ++k) { val[k] = expf(val[k] - val[0]); den += val[k]; }
+    for (int k = 0; k < a.top; ++k) {
+      a.sel[k] = chosen[k];
+      a.wts[k] = round_bf16(val[k] / den);
+    }
+  }
+  trace_mark(a.trace, 3, true);
+  trace_mark(a.trace, 4, false);
+}
+
+struct MoeArgs {
+  const bf16* const* w;   // [E] device pointers: fc_1 (gated pass) or proj (down pass) of every expert
+  const bf16* const* w2;  // [E] fc_2 of every expert (gated pass) or null
+  const int* sel;         // the router's output
+  const float* wts;
+  int k;                  // which of the token's experts this launch computes
+  const bf16* prev;       // down pass: running bf16 sum of the previous experts' weighted outputs [N], or null
+};
+
+// Register-streamed like stream_ldg_kernel, but nothing of the weights may be touched before the wait: which
+// matrices to read is the router's output.  GATED: h = act(fc_1 x) * fc_2 x of expert sel[k].  PLAIN (down):
+// y = bf16(wts[k] * bf16(proj h)) (+ prev) (+ residual on the token's last expert).
+template <int MODE>
+__global__ void __launch_bounds__(LIN_THREADS, 3) moe_stream_kernel(const StreamArgs a, const MoeArgs m) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  bf16* xs = reinterpret_cast<bf16*>(smem_raw);
+  __shared__ float red[LIN_WARPS];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int gw = blockIdx.x * LIN_WARPS + warp, n_gw = gridDim.x * LIN_WARPS;
+  trace_mark(a.trace, 0, true);
+  unsigned long long best = 0ull;
+  pdl_wait_prior();
+  trace_mark(a.trace, 1, true);
+  const int slot = a.ctx ? a.ctx[MDI_CTX_SLOT] : 0, pos = a.ctx ? a.ctx[MDI_CTX_POS] : 0;
+  const int e = m.sel[m.k];
+  const float route = m.wts[m.k];
+  const bf16* W = m.w[e];
+  const bf16* W2 = MODE == MODE_GATED ? m.w2[e] : nullptr;
+  stage_input(a.x + (size_t)slot * a.x_slot_stride, a.norm_w, a.eps, a.unit_offset, a.K, xs, red, a.norm_b, a.layer_norm);
+  trace_mark(a.trace, 2, false);
+  pdl_launch_dependents();
+
+  const bf16* res = a.residual ? a.residual + (size_t)slot * a.res_slot_stride : nullptr;
+  const uint4* xv = reinterpret_cast<const uint4*>(xs);
+  const int nvec = a.K / 8;
+  for (int it = gw; it < a.n_items; it += n_gw) {
+    const bf16 *wa, *wb;
+    if (MODE == MODE_GATED) {
+      wa = W + (size_t)it * a.K;
+      wb = W2 + (size_t)it * a.K;
+    } else {
+      wa = W + (size_t)(2 * it) * a.K;
+      wb = W + (size_t)min(2 * it + 1, a.N - 1) * a.K;
+    }
+    float da, db;
+    warp_dot2(wa, wb, xv, nvec, lane, da, db);
+    if (lane != 0) continue;
+    if (MODE == MODE_GATED) {
+      item_epilogue<MODE_GATED>(a, it, da, db, slot, pos, res, nullptr, best);
+    } else {
+      const float o[2] = {da, db};
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int row = 2 * it + j;
+        if (row >= a.N) continue;
+        float v = round_bf16(round_bf16(o[j]) * route);
+        if (m.prev) v = round_bf16(v + __bfloat162float(m.prev[row]));
+        if (res) v += __bfloat162float(res[row]);
+        reinterpret_cast<bf16*>(a.y)[(size_t)slot * a.y_slot_stride + row] = __float2bfloat16_rn(v);
+      }
+    }
+  }
+  if (a.hop_row) hop_signal_copy(a.signal, a.ctx, reinterpret_cast<const bf16*>(a.y) + (size_t)slot * a.y_slot_stride,
+                                 a.hop_row + (size_t)slot * a.hop_slot_stride, a.N, nullptr, 0);
+  else hop_signal(a.signal, a.ctx);
+  trace_mark(a.trace, 3, true);
+  trace_mark(a.trace, 4, false);
+}
+
 static int g_num_sms = 0;
 static int num_sms() {
   if (!g_num_sms) {
@@ -990,6 +1135,81 @@ int mdi_qkv_decode(const void* W, const void* bias, const void* x, const void* n
   a.n_items = (n_head + 2 * n_groups) * (head_size / 2);
   if (variant < 0) variant = g_default_variant;
   return launch_stream<MODE_QKV>(a, variant, ctas_per_sm, use_pdl, stream);
+}
+
+// Router of a mixture-of-experts MLP: norm_2 + [E, K] GEMV + top-k + softmax -> sel[top], wts[top] (device memory).
+int mdi_moe_router(const void* Wg, const void* x, const void* norm_w, const void* norm_b, int layer_norm, const int* ctx,
+                   long long x_slot_stride, int K, int E, int top, float eps, int unit_offset, int* sel, float* wts,
+                   const int* wait_flag, int* status, long long wait_max_cycles, int use_pdl, unsigned long long* trace,
+                   cudaStream_t stream) {
+  if (K % 8 != 0 || E < 1 || E > MOE_MAX_EXPERTS || top < 1 || top > MOE_MAX_TOP || top > E) return -2;
+  RouterArgs a{};
+  a.Wg = (const bf16*)Wg; a.x = (const bf16*)x; a.norm_w = (const bf16*)norm_w; a.norm_b = (const bf16*)norm_b;
+  a.layer_norm = layer_norm; a.ctx = ctx; a.x_slot_stride = x_slot_stride; a.K = K; a.E = E; a.top = top; a.eps = eps;
+  a.unit_offset = unit_offset; a.sel = sel; a.wts = wts; a.wait = HopWait{wait_flag, status, wait_max_cycles}; a.trace = trace;
+  const size_t smem = (size_t)((K + 63) / 64) * 64 * sizeof(bf16);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(moe_router_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(1);
+  cfg.blockDim = dim3(LIN_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = use_pdl ? 1 : 0;
+  return (int)cudaLaunchKernelEx(&cfg, moe_router_kernel, a);
+}
+
+// One expert pass of a routed token: gate/up (w2_ptrs != null) or down (+ routing weight, running sum, residual, hop).
+int mdi_moe_linear_decode(const void* w_ptrs, const void* w2_ptrs, const int* sel, const float* wts, int k, const void* prev,
+                          const void* x, const void* norm_w, const void* norm_b, int layer_norm, const void* residual, void* y,
+                          const int* ctx, long long x_slot_stride, long long res_slot_stride, long long y_slot_stride, int N,
+                          int K, float eps, int unit_offset, int act, int* status, int* signal_flag, unsigned int* done_ctr,
+                          void* hop_row, long long hop_slot_stride, int ctas_per_sm, int use_pdl, unsigned long long* trace,
+                          cudaStream_t stream) {
+  if (K % 8 != 0 || !w_ptrs || !sel || !wts || k < 0 || k >= MOE_MAX_TOP) return -2;
+  if (hop_row && (!signal_flag || !y)) return -2;
+  StreamArgs a{};
+  a.x = (const bf16*)x; a.norm_w = (const bf16*)norm_w; a.norm_b = (const bf16*)norm_b; a.layer_norm = layer_norm;
+  a.residual = (const bf16*)residual; a.y = y; a.ctx = ctx;
+  a.x_slot_stride = x_slot_stride; a.res_slot_stride = res_slot_stride; a.y_slot_stride = y_slot_stride;
+  a.N = N; a.K = K; a.eps = eps; a.unit_offset = unit_offset; a.act = act;
+  a.signal = HopSignal{signal_flag, done_ctr, status};
+  a.n_items = w2_ptrs ? N : (N + 1) / 2;
+  a.trace = trace; a.hop_row = (bf16*)hop_row; a.hop_slot_stride = hop_slot_stride;
+  MoeArgs m{};
+  m.w = (const bf16* const*)w_ptrs; m.w2 = (const bf16* const*)w2_ptrs; m.sel = sel; m.wts = wts; m.k = k;
+  m.prev = (const bf16*)prev;
+  if (ctas_per_sm <= 0) ctas_per_sm = 3;
+  const int grid = max(1, min(num_sms() * min(ctas_per_sm, 3), (a.n_items + LIN_WARPS - 1) / LIN_WARPS));
+  const size_t smem = (size_t)((K + 63) / 64) * 64 * sizeof(bf16);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(LIN_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = use_pdl ? 1 : 0;
+  if (w2_ptrs) {
+    if (smem > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(moe_stream_kernel<MODE_GATED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return (int)e;
+    }
+    return (int)cudaLaunchKernelEx(&cfg, moe_stream_kernel<MODE_GATED>, a, m);
+  }
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(moe_stream_kernel<MODE_PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+  }
+  return (int)cudaLaunchKernelEx(&cfg, moe_stream_kernel<MODE_PLAIN>, a, m);
 }
 
 }  // extern "C"

@@ -37,13 +37,16 @@ __all__ = ["engine_supports", "fused_prefill_supports", "FusedStage", "FusedStag
 def engine_supports(config: Config, dtype: torch.dtype) -> bool:
     """Architectures the fused decode kernels cover (the rest runs on the eager runner): RMSNorm or LayerNorm,
     sequential or parallel residual (with or without a shared attention norm), gated (SwiGLU / GeGLU) or plain
-    GELU MLPs, rotary (full or partial) or learned positions, head sizes 64 / 128 / 256 — i.e. the Llama, Mistral,
-    TinyLlama, Gemma, Pythia / GPT-NeoX, StableLM, GPT-2 families.  Not covered: mixture-of-experts MLPs, odd head
-    sizes (Phi: 80) and very wide GQA groups (Falcon-7B: 71 query heads per KV head)."""
+    GELU MLPs or a routed mixture of SwiGLU experts, rotary (full or partial) or learned positions, head sizes
+    64 / 128 / 256 — i.e. the Llama, Mistral, Mixtral, TinyLlama, Gemma, Pythia / GPT-NeoX, StableLM, GPT-2 families.
+    Not covered: odd head sizes (Phi: 80) and very wide GQA groups (Falcon-7B: 71 query heads per KV head)."""
+    moe = config.mlp_class_name == "LLaMAMoE"
     return (
         dtype == torch.bfloat16
         and config.norm_class_name in ("RMSNorm", "LayerNorm")
-        and config.mlp_class_name in ("LLaMAMLP", "GemmaMLP", "GptNeoxMLP")
+        and config.mlp_class_name in ("LLaMAMLP", "GemmaMLP", "GptNeoxMLP", "LLaMAMoE")
+        and (not moe or (not config.parallel_residual and not config.bias and 1 <= config.n_expert_per_token <= 8
+                         and config.n_expert_per_token <= config.n_expert <= 256))
         and config.pos_embedding in ("rope", "learned")
         and config.head_size in (64, 128, 256)
         and config.q_per_kv in (1, 2, 4, 8)
@@ -175,6 +178,19 @@ class FusedStage:
             self.q = torch.zeros(cfg.n_head * cfg.head_size, **bf)
             self.y_attn = torch.zeros(cfg.n_head * cfg.head_size, **bf)
             self.h_mlp = torch.zeros(cfg.intermediate_size, **bf)
+            self.moe = cfg.mlp_class_name == "LLaMAMoE"
+            if self.moe:
+                # the router's per-token output (expert ids, routing weights), the running sum of the experts' outputs
+                # (ping-pong) and, per block, device tables of the experts' weight pointers (csrc/decode_linear.cu)
+                self.moe_sel = torch.zeros(8, **i32)
+                self.moe_wts = torch.zeros(8, dtype=torch.float32, device=dev)
+                self.moe_acc = [torch.zeros(C, **bf), torch.zeros(C, **bf)]
+                self.moe_ptrs: Dict[int, Tuple[torch.Tensor, torch.Tensor, torch.Tensor]] = {}
+                for li, blk in enumerate(model.transformer.h):
+                    if getattr(blk, "has_mlp", True) and hasattr(blk, "mlp"):
+                        self.moe_ptrs[li] = tuple(  # type: ignore[assignment]
+                            torch.tensor([getattr(e, n).weight.data_ptr() for e in blk.mlp.experts], dtype=torch.int64, device=dev)
+                            for n in ("fc_1", "fc_2", "proj"))
             sms = torch.cuda.get_device_properties(dev).multi_processor_count
             # split-KV spans per KV group: ~2 CTAs per SM over all groups, a multiple of 8 so that the spans of a group
             # launch as clusters of 8 (short contexts merge through distributed shared memory, decode_attention.cu)
@@ -224,6 +240,8 @@ class FusedStage:
         """fp8-e4m3 block-scaled copies of every projection (BASELINE config #5); embeddings/norms stay bf16."""
         from ..utils.quantize import quantize_fp8_block
 
+        if self.moe:
+            raise ValueError("fp8 weights are not available for mixture-of-experts models on the fused engine")
         lins = []
         for blk in self.model.transformer.h:
             if getattr(blk, "has_attn", True):
@@ -420,7 +438,10 @@ class FusedStage:
         x_in, x_in_stride = (self.xa, 0) if self.is_starter else (self.hidden_in, W_in)
         common = dict(use_pdl=self.use_pdl)
         units = self._units()
-        n_kernels = sum({"attn": 3, "mlp": 2, "gu": 1, "down": 1, "par": 5}[k] for _, k in units)
+        n_moe = 1 + 2 * cfg.n_expert_per_token if self.moe else 2  # router + (gate/up, down) per chosen expert
+        n_kernels = sum({"attn": 3, "mlp": n_moe, "gu": 1, "down": 1, "par": 5}[k] for _, k in units)
+        if self.moe and dep_flags:
+            raise RuntimeError("flag dependencies are not wired through the mixture-of-experts kernels (use PDL)")
         kidx = [0]
         st_kw = dict(status=self.status.data_ptr(), wait_max_cycles=self.wait_max_cycles)
 
@@ -483,6 +504,35 @@ class FusedStage:
                 gw = {**self._w(blk.mlp.fc_1), **self._w(blk.mlp.fc_2, second=True)}
                 ops.linear_decode(gw.pop("W"), x_src, y, self.ctx, **gw, act=self._gate_act(), **kw, **dst)
 
+        def moe_mlp(li: int, blk: Any, x_src: torch.Tensor, x_stride: int, wait: Dict[str, Any], dst: Optional[torch.Tensor],
+                    last: bool) -> None:
+            """Routed MLP (model.py:823-853) without a host round trip: the router kernel leaves the token's expert ids
+            and routing weights on the device; each chosen expert is a gate/up + a down launch that looks its weight
+            pointers up after the dependency wait.  The last down pass adds the residual and, on the stage's last
+            block, finishes the outgoing row (local row + hop copy)."""
+            top = cfg.n_expert_per_token
+            p1, p2, p3 = self.moe_ptrs[li]
+            norm = self._norm(blk.norm_2)
+            ops.moe_router(blk.mlp.gate.weight, x_src, self.moe_sel, self.moe_wts, self.ctx, top=top, **norm,
+                           x_slot_stride=x_stride, trace=self._tr(f"L{li}.router"), **wait, **common)
+            kidx[0] += 1
+            for k in range(top):
+                ops.moe_linear_decode(p1, x_src, self.h_mlp, self.ctx, self.moe_sel, self.moe_wts, k, N=I, K=C, w2_ptrs=p2,
+                                      **norm, act=self._gate_act(), x_slot_stride=x_stride, ctas_per_sm=min(3, self._ctas("gate_up")),
+                                      status=self.status.data_ptr(), trace=self._tr(f"L{li}.e{k}.gate_up"), **common)
+                kw: Dict[str, Any] = dict(N=C, K=I, prev=self.moe_acc[(k + 1) % 2] if k > 0 else None,
+                                          ctas_per_sm=min(3, self._ctas("down")), status=self.status.data_ptr(), **common)
+                if k < top - 1:
+                    ops.moe_linear_decode(p3, self.h_mlp, self.moe_acc[k % 2], self.ctx, self.moe_sel, self.moe_wts, k,
+                                          trace=self._tr(f"L{li}.e{k}.down"), **kw)
+                elif not last:
+                    ops.moe_linear_decode(p3, self.h_mlp, dst, self.ctx, self.moe_sel, self.moe_wts, k, residual=x_src,
+                                          res_slot_stride=x_stride, trace=self._tr(f"L{li}.e{k}.down"), **kw)
+                else:
+                    ops.moe_linear_decode(p3, self.h_mlp, None, self.ctx, self.moe_sel, self.moe_wts, k, residual=x_src,
+                                          res_slot_stride=x_stride, **out_kw(f"L{li}.e{k}.down"), **kw)
+                kidx[0] += 2
+
         def free_buf(*busy: Any) -> torch.Tensor:
             return next(b_ for b_ in (self.xa, self.xb, self.xc) if all(b_ is not o for o in busy))
 
@@ -527,6 +577,10 @@ class FusedStage:
                 mlp_up(li, blk, x_in, x_in_stride, blk.norm_2, first, wait,
                        extra=out_kw(f"L{li}.gate_up", n_pre=C, pre=(x_in, x_in_stride)))
                 return
+            if kind == "mlp" and self.moe:
+                moe_mlp(li, blk, x_in, x_in_stride, wait, None if last else x_out, last)
+                x_in, x_in_stride = x_out, 0
+                continue
             if kind == "mlp":
                 mlp_up(li, blk, x_in, x_in_stride, blk.norm_2, first, wait)
                 lw, src, name, ctas = self._w(blk.mlp.proj), dict(x=self.h_mlp), f"L{li}.down", self._ctas("down")

@@ -16,7 +16,7 @@ from mdi_llm_b200.parallel import engine as eng
 from mdi_llm_b200.parallel.engine import FusedStage, HopTarget
 
 KERNELS = ["linear_decode", "qkv_decode", "attn_decode", "embed", "sample_fast", "advance_step", "rmsnorm_rows", "gemm",
-           "attn_prefill", "gemm_fp8", "quantize_rows_fp8"]
+           "attn_prefill", "gemm_fp8", "quantize_rows_fp8", "moe_router", "moe_linear_decode"]
 
 
 def _cfg(n_layer=3):
@@ -103,6 +103,44 @@ def test_decode_launch_sequence_binds(role, kw, expect_first, expect_last):
     for n, args in seq:
         if n == "linear_decode" and args.get("residual") is not None and args.get("y") is not None:
             assert args["y"] is not args["residual"]
+
+
+@pytest.mark.parametrize("role,kw", [("starter", {}), ("secondary:0", {"first_mlp_only": True, "last_attn_only": True}),
+                                     ("secondary:0", {})])
+def test_moe_decode_launch_sequence_binds(role, kw):
+    """Mixture of experts: router, then (gate/up, down) per chosen expert; only the router may carry the incoming
+    hop wait, the token's last down pass adds the residual and carries the outgoing hop."""
+    cfg = Config.from_name("tiny-llama-1.1b", n_layer=3, n_embd=256, n_head=4, n_query_groups=2, intermediate_size=128, vocab_size=120,
+                           padded_vocab_size=128, block_size=64, mlp_class_name="LLaMAMoE", n_expert=4, n_expert_per_token=2)
+    assert eng.engine_supports(cfg, torch.bfloat16) and not eng.fused_prefill_supports(cfg)
+    with dry_ops() as calls:
+        st = build_stage(cfg, role, 3, **kw).to(torch.bfloat16)
+        st.max_seq_length = 32
+        fs = FusedStage(st, n_slots=2, max_seq_length=32)
+        fs.enqueue_blocks(HopTarget(0x1000, 0x2000), wait_input=True)
+    names = [c[0] for c in calls]
+    units = fs._units()
+    assert len(names) == sum(3 if k == "attn" else 5 for _, k in units)
+    first_mlp = units[0][1] == "mlp"
+    assert names[0] == ("moe_router" if first_mlp else "qkv_decode")
+    assert (calls[0][1].get("wait_flag") is None) == fs.is_starter
+    assert all(c[1].get("wait_flag") is None for c in calls[1:])
+    sigs = [c[1].get("signal_flag") for c in calls]
+    assert all(s_ is None for s_ in sigs[:-1]) and sigs[-1] == 0x2000
+    moe = [c[1] for c in calls if c[0] == "moe_linear_decode"]
+    per_layer = [moe[i:i + 4] for i in range(0, len(moe), 4)]
+    for gu0, dn0, gu1, dn1 in per_layer:
+        assert gu0["w2_ptrs"] is not None and gu1["w2_ptrs"] is not None and dn0.get("w2_ptrs") is None
+        assert (gu0["k"], dn0["k"], gu1["k"], dn1["k"]) == (0, 0, 1, 1)
+        assert dn0.get("residual") is None and dn0.get("prev") is None and dn0["y"] is fs.moe_acc[0]
+        assert dn1["prev"] is fs.moe_acc[0] and dn1["residual"] is not None  # running sum + residual on the last expert
+        assert dn1.get("y") is not dn1["residual"]
+        assert gu0["w_ptrs"].dtype == torch.int64 and gu0["w_ptrs"].numel() == 4
+    if units[-1][1] == "mlp":
+        assert moe[-1]["hop_ptr"] == 0x1000 and moe[-1]["y_ptr"] == fs.out_local.data_ptr()
+    with dry_ops():
+        with pytest.raises(ValueError, match="fp8"):
+            FusedStage(build_stage(cfg, "starter", 3).to(torch.bfloat16), n_slots=1, max_seq_length=32, weight_dtype="fp8")
 
 
 def test_local_output_and_prefill_sequences_bind():

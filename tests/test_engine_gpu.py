@@ -56,7 +56,7 @@ def _near_argmax_check(cfg, full_sd, tokens, prompt_len, tol=0.15):
 
 
 @pytest.mark.parametrize("variant", ["gqa_hs64", "mha_hs128", "qpk8_bias", "gemma_like", "pythia_like", "falcon_like", "gpt2_like",
-                                     "stablelm_like", "hs256"])
+                                     "stablelm_like", "hs256", "mixtral_like"])
 def test_fused_runner_matches_eager_hidden_and_logits(variant):
     from mdi_llm_b200.parallel.engine import FusedStageRunner
     from mdi_llm_b200.parallel.scheduler import EagerStageRunner
@@ -74,7 +74,9 @@ def test_fused_runner_matches_eager_hidden_and_logits(variant):
                             bias=True, rotary_percentage=0.0, pos_embedding="learned", tie_embeddings=True, n_query_groups=8),
           # StableLM-style: LayerNorm + gated MLP + partial rotary, sequential residual
           "stablelm_like": dict(norm_class_name="LayerNorm", rotary_percentage=0.25),
-          "hs256": dict(n_head=2, n_query_groups=1, head_size=256)}[variant]
+          "hs256": dict(n_head=2, n_query_groups=1, head_size=256),
+          # Mixtral: top-2 of 8 SwiGLU experts per token, routed on the device (router kernel + expert pointer tables)
+          "mixtral_like": dict(mlp_class_name="LLaMAMoE", n_expert=8, n_expert_per_token=2)}[variant]
     cfg = _cfg(**kw)
     _, (st_a,) = _stages(cfg, 1)
     _, (st_b,) = _stages(cfg, 1)
@@ -226,11 +228,13 @@ def test_device_pipeline_half_layer_boundaries():
         assert torch.equal(results[0][i], ref[i]), f"sample {i}: {results[0][i].tolist()} vs {ref[i].tolist()}"
 
 
-def test_fused_stage_half_blocks_single_gpu():
-    """A stage that starts with an MLP half and ends with an attention half, against the eager modules."""
+@pytest.mark.parametrize("moe", [False, True])
+def test_fused_stage_half_blocks_single_gpu(moe):
+    """A stage that starts with an MLP half and ends with an attention half, against the eager modules (``moe``: the
+    MLPs are routed mixtures of experts — the stage then starts with the router kernel)."""
     from mdi_llm_b200.parallel.engine import FusedStage
 
-    cfg = _cfg(n_layer=4)
+    cfg = _cfg(n_layer=4, **(dict(mlp_class_name="LLaMAMoE", n_expert=4, n_expert_per_token=2) if moe else {}))
     stages = _half_stages(cfg, [3, 4, 1], ["cuda", "cuda", "cuda"])
     mid = stages[1]  # MLP of layer 1, layer 2, attention of layer 3
     assert [b.parts for b in mid.transformer.h] == ["mlp", "both", "attn"]

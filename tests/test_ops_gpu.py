@@ -483,3 +483,77 @@ def test_attn_prefill_tcgen05_matches_eager(H, G, hs, ne, T, pipe):
     torch.testing.assert_close(pool[slot, :, :, :T].float(), pool_ref[slot, :, :, :T].float(), rtol=2e-2, atol=2e-2)
     other = [s for s in range(n_slots) if s != slot]
     assert torch.equal(pool[other], pool_ref[other]) and torch.equal(pool[slot, :, :, T:], pool_ref[slot, :, :, T:])
+
+
+@pytest.mark.parametrize("E,top,K", [(8, 2, 4096), (4, 1, 256), (64, 8, 1024)])
+def test_moe_router_picks_the_top_experts(E, top, K):
+    """Router kernel vs torch: bf16 logits of the normalised row, top-k, softmax over the chosen logits (model.py:835-838)."""
+    ops = _ops()
+    torch.manual_seed(E * 7 + K)
+    Wg = (torch.randn(E, K, device="cuda") * 0.05).bfloat16()
+    x = torch.randn(3, K, device="cuda").bfloat16()  # slotted input: slot 2 is the live one
+    nw = (1 + 0.1 * torch.randn(K, device="cuda")).bfloat16()
+    sel = torch.full((8,), -1, dtype=torch.int32, device="cuda")
+    wts = torch.zeros(8, dtype=torch.float32, device="cuda")
+    ops.moe_router(Wg, x, sel, wts, _ctx(ops, slot=2), top=top, norm_w=nw, eps=1e-5, x_slot_stride=K)
+    torch.cuda.synchronize()
+    logits = (_rmsnorm_ref(x[2], nw, 1e-5).float() @ Wg.float().T).bfloat16()
+    w_ref, c_ref = torch.topk(logits, top)
+    w_ref = w_ref.softmax(dim=-1, dtype=torch.float).bfloat16().float()
+    # a different summation order may flip two experts whose bf16 logits are (nearly) tied: compare through the logits
+    got = sel[:top].long()
+    assert len(set(got.tolist())) == top and int(got.min()) >= 0 and int(got.max()) < E
+    torch.testing.assert_close(logits[got].float(), logits[c_ref].float(), rtol=0, atol=2 ** -6 * float(logits.abs().max()))
+    if torch.equal(got, c_ref):
+        torch.testing.assert_close(wts[:top], w_ref, rtol=2e-2, atol=4e-3)
+    assert abs(float(wts[:top].sum()) - 1.0) < 2e-2 and int(sel[top:].max() if top < 8 else -1) == -1
+
+
+@pytest.mark.parametrize("N,I", [(4096, 14336), (256, 128), (1000, 384)])
+def test_moe_expert_passes_follow_the_router_output(N, I):
+    """Two routed experts through the pointer tables: h = silu(W1[e] xn) * W2[e] xn, y = x + sum_k w_k * (W3[e_k] h_k), with
+    the eager module's rounding points; the pass of the last expert adds the residual and hops by row copy."""
+    ops = _ops()
+    torch.manual_seed(N + I)
+    E, C = 4, N
+    W1 = [(torch.randn(I, C, device="cuda") * 0.03).bfloat16() for _ in range(E)]
+    W2 = [(torch.randn(I, C, device="cuda") * 0.03).bfloat16() for _ in range(E)]
+    W3 = [(torch.randn(C, I, device="cuda") * 0.03).bfloat16() for _ in range(E)]
+    tab = lambda ws: torch.tensor([w.data_ptr() for w in ws], dtype=torch.int64, device="cuda")  # noqa: E731
+    p1, p2, p3 = tab(W1), tab(W2), tab(W3)
+    x = torch.randn(2, C, device="cuda").bfloat16()
+    nw = (1 + 0.1 * torch.randn(C, device="cuda")).bfloat16()
+    sel = torch.tensor([3, 1, 0, 0, 0, 0, 0, 0], dtype=torch.int32, device="cuda")
+    wts = torch.tensor([0.625, 0.375, 0, 0, 0, 0, 0, 0], dtype=torch.float32, device="cuda")
+    ctx = _ctx(ops, slot=1, signal=7)
+    h = torch.empty(I, device="cuda", dtype=torch.bfloat16)
+    acc = torch.zeros(C, device="cuda", dtype=torch.bfloat16)
+    out_local = torch.zeros(2, C, device="cuda", dtype=torch.bfloat16)
+    peer = torch.zeros(2, C, device="cuda", dtype=torch.bfloat16)
+    flag = torch.zeros(2, dtype=torch.int32, device="cuda")
+    done = torch.zeros(1, dtype=torch.int32, device="cuda")
+    status = torch.zeros(4, dtype=torch.int32, device="cuda")
+    xn = _rmsnorm_ref(x[1], nw, 1e-5)
+    ref_sum = None
+    for k, (e, w) in enumerate([(3, 0.625), (1, 0.375)]):
+        ops.moe_linear_decode(p1, x, h, ctx, sel, wts, k, N=I, K=C, w2_ptrs=p2, norm_w=nw, eps=1e-5, act="silu_gate", x_slot_stride=C)
+        g = (xn.float() @ W1[e].float().T).bfloat16()
+        u = (xn.float() @ W2[e].float().T).bfloat16()
+        h_ref = torch.nn.functional.silu(g.float()).bfloat16() * u
+        torch.testing.assert_close(h.float(), h_ref.float(), rtol=3e-2, atol=3e-2)
+        y_e = ((h.float() @ W3[e].float().T).bfloat16().float() * w).bfloat16()
+        if k == 0:
+            ops.moe_linear_decode(p3, h, acc, ctx, sel, wts, k, N=C, K=I)
+            torch.cuda.synchronize()
+            torch.testing.assert_close(acc.float(), y_e.float(), rtol=2e-2, atol=2e-2)
+            ref_sum = y_e
+        else:
+            ops.moe_linear_decode(p3, h, None, ctx, sel, wts, k, N=C, K=I, prev=acc, residual=x, res_slot_stride=C,
+                                  y_ptr=out_local.data_ptr(), y_slot_stride=C, hop_ptr=peer.data_ptr(), hop_slot_stride=C,
+                                  signal_flag=flag.data_ptr(), done_ctr=done.data_ptr(), status=status.data_ptr())
+            ref_sum = (ref_sum.float() + y_e.float()).bfloat16()
+    torch.cuda.synchronize()
+    ref = x[1].float() + ref_sum.float()
+    torch.testing.assert_close(out_local[1].float(), ref, rtol=2e-2, atol=3e-2)
+    assert torch.equal(peer[1], out_local[1]) and int(flag[1]) == 7 and int(flag[0]) == 0 and int(peer[0].abs().max()) == 0
+    assert int(status[0]) == 0
