@@ -104,11 +104,12 @@ def test_fused_runner_matches_eager_hidden_and_logits(variant):
     assert fused.n_launches > 0
 
 
-def test_device_pipeline_single_gpu_device_and_host_modes_agree():
+@pytest.mark.parametrize("moe", [False, True])
+def test_device_pipeline_single_gpu_device_and_host_modes_agree(moe):
     from mdi_llm_b200.parallel.pipeline import DevicePipeline
     from mdi_llm_b200.parallel.scheduler import SamplingParams
 
-    cfg = _cfg()
+    cfg = _cfg(**(dict(mlp_class_name="LLaMAMoE", n_expert=8, n_expert_per_token=2) if moe else {}))
     full, (st,) = _stages(cfg, 1)
     pipe = DevicePipeline(st, 0, 1, n_samples=3, max_seq_length=128, sampling=SamplingParams.greedy())
     prompts = [torch.tensor([1, 50, 60, 70]), torch.tensor([1, 9]), torch.tensor([1, 1500, 3, 4, 5, 6, 7])]
