@@ -913,7 +913,8 @@ __global__ void __launch_bounds__(LIN_THREADS) moe_router_kernel(const RouterArg
       val[k] = bv;
     }
     float den = 0.f;
-    for (int k = 0; k < a.top; ++k) { val[k] = expf(val[k] - val[0]); den += val[k]; }
+    const float vmax = val[0];  // best first
+    for (int k = 0; k < a.top; ++k) { val[k] = expf(val[k] - vmax); den += val[k]; }
     for (int k = 0; k < a.top; ++k) {
       a.sel[k] = chosen[k];
       a.wts[k] = round_bf16(val[k] / den);

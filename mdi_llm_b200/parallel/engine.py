@@ -311,7 +311,7 @@ class FusedStage:
         return "gelu_tanh" if self.cfg.gelu_approximate == "tanh" else "gelu_erf"
 
     def _gate_act(self) -> str:
-        if self.cfg.mlp_class_name == "LLaMAMLP":
+        if self.cfg.mlp_class_name in ("LLaMAMLP", "LLaMAMoE"):  # SwiGLU (the experts of a mixture are LLaMAMLPs)
             return "silu_gate"
         return "gelu_tanh_gate" if self.cfg.gelu_approximate == "tanh" else "gelu_erf_gate"
 

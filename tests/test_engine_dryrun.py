@@ -135,7 +135,7 @@ def test_moe_decode_launch_sequence_binds(role, kw):
         assert dn0.get("residual") is None and dn0.get("prev") is None and dn0["y"] is fs.moe_acc[0]
         assert dn1["prev"] is fs.moe_acc[0] and dn1["residual"] is not None  # running sum + residual on the last expert
         assert dn1.get("y") is not dn1["residual"]
-        assert gu0["w_ptrs"].dtype == torch.int64 and gu0["w_ptrs"].numel() == 4
+        assert gu0["w_ptrs"].dtype == torch.int64 and gu0["w_ptrs"].numel() == 4 and gu0["act"] == "silu_gate"
     if units[-1][1] == "mlp":
         assert moe[-1]["hop_ptr"] == 0x1000 and moe[-1]["y_ptr"] == fs.out_local.data_ptr()
     with dry_ops():
