@@ -150,10 +150,14 @@ def decode_unit_costs(config: Config, bytes_per_param: float = 2.0, eff_tbps: fl
     C = config.n_embd
     bw = eff_tbps * 1e6  # bytes per microsecond
     attn_b = (config.qkv_size + config.attn_out_dim) * C * bytes_per_param
-    mlp_mats = 3 if config.mlp_class_name in ("LLaMAMLP", "GemmaMLP") else 2
+    mlp_mats = 3 if config.mlp_class_name in ("LLaMAMLP", "GemmaMLP", "LLaMAMoE") else 2
     mlp_b = mlp_mats * C * config.intermediate_size * bytes_per_param
+    mlp_kernels = 2
+    if config.mlp_class_name == "LLaMAMoE":  # a token streams only its chosen experts: router + (gate/up, down) per expert
+        mlp_b = config.n_expert_per_token * mlp_b + config.n_expert * C * bytes_per_param
+        mlp_kernels = 1 + 2 * config.n_expert_per_token
     head_b = config.padded_vocab_size * C * bytes_per_param
-    return (attn_b / bw + 2 * kernel_us + attn_kernel_us, mlp_b / bw + 2 * kernel_us,
+    return (attn_b / bw + 2 * kernel_us + attn_kernel_us, mlp_b / bw + mlp_kernels * kernel_us,
             head_b / bw + kernel_us + sampler_us)
 
 
