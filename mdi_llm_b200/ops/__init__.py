@@ -45,7 +45,8 @@ def _declare(lib: ctypes.CDLL) -> None:
                                    vp, vp, i64, i32, i32, i32, vp, vp, vp, vp, vp, vp, i32, vp]
     lib.mdi_moe_router.argtypes = [vp, vp, vp, vp, i32, vp, i64, i32, i32, i32, f32, i32, vp, vp, vp, vp, i64, i32, vp, vp]
     lib.mdi_moe_linear_decode.argtypes = [vp, vp, vp, vp, i32, vp, vp, vp, vp, i32, vp, vp, vp, i64, i64, i64, i32, i32, f32,
-                                          i32, i32, vp, vp, vp, vp, i64, i32, i32, vp, vp]
+                                          i32, i32, vp, vp, vp, vp, i64, i32, i32, vp, i32, vp]
+    lib.mdi_set_moe_variant.argtypes = [i32]
     lib.mdi_set_linear_variant.argtypes = [i32]
     lib.mdi_set_attn_cluster.argtypes = [i32]
     lib.mdi_set_l2_prefetch_mb.argtypes = [i32]
@@ -258,12 +259,13 @@ def moe_linear_decode(w_ptrs: torch.Tensor, x: torch.Tensor, y: Optional[torch.T
                       x_slot_stride: int = 0, res_slot_stride: int = 0, y_slot_stride: int = 0, y_ptr: Optional[int] = None,
                       status: Optional[int] = None, signal_flag: Optional[int] = None, done_ctr: Optional[int] = None,
                       hop_ptr: Optional[int] = None, hop_slot_stride: int = 0, ctas_per_sm: int = 3, use_pdl: bool = False,
-                      trace: Optional[int] = None, x_ptr: Optional[int] = None) -> None:
+                      trace: Optional[int] = None, x_ptr: Optional[int] = None, sel_early: bool = False) -> None:
     """One expert pass of a routed token.  ``w_ptrs`` / ``w2_ptrs``: int64 ``[E]`` device tables of the experts' weight
     pointers (``[N, K]`` bf16 each); the kernel reads ``sel[k]`` AFTER its dependency wait and streams only that
     expert.  With ``w2_ptrs``: ``y = act(W1 norm(x)) * (W2 norm(x))``; without: the down pass
     ``y = bf16(wts[k] * bf16(W x)) (+ prev) (+ residual)``, optionally finishing the stage's hop like
-    :func:`linear_decode`."""
+    :func:`linear_decode`.  ``sel_early``: the router ran at least two launches before this one, so the expert is
+    known before the programmatic-dependency wait and the kernel starts streaming its weights at once."""
     for t, n in ((w_ptrs, "w_ptrs"), (w2_ptrs, "w2_ptrs")):
         if t is not None and (t.dtype != torch.int64 or not t.is_cuda):
             raise OpsError(f"moe_linear_decode: {n} must be an int64 device tensor of pointers")
@@ -272,7 +274,12 @@ def moe_linear_decode(w_ptrs: torch.Tensor, x: torch.Tensor, y: Optional[torch.T
         ptr(norm_b), int(layer_norm), residual_ptr if residual_ptr is not None else ptr(residual),
         y_ptr if y_ptr is not None else ptr(y), ptr(ctx), x_slot_stride, res_slot_stride, y_slot_stride, N, K, eps,
         int(unit_offset), ACT[act], status, signal_flag, done_ctr, hop_ptr, hop_slot_stride, ctas_per_sm, int(use_pdl), trace,
-        stream_ptr()), "moe_linear_decode")
+        int(sel_early), stream_ptr()), "moe_linear_decode")
+
+
+def set_moe_variant(v: int) -> None:
+    """Weight path of the expert passes: 0 = register-streamed (LDG), otherwise the per-warp bulk-copy ring (default)."""
+    lib().mdi_set_moe_variant(v)
 
 
 def qkv_decode(

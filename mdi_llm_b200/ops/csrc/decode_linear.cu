@@ -931,7 +931,16 @@ struct MoeArgs {
   const float* wts;
   int k;                  // which of the token's experts this launch computes
   const bf16* prev;       // down pass: running bf16 sum of the previous experts' weighted outputs [N], or null
+  int sel_early;          // the router finished >= 2 launches ago: sel / wts may be read BEFORE the dependency wait
 };
+
+__device__ __forceinline__ void moe_down_store(const StreamArgs& a, int row, int slot, float acc, float route, bool has_prev,
+                                               float prev, bool has_res, float res) {
+  float v = round_bf16(round_bf16(acc) * route);
+  if (has_prev) v = round_bf16(v + prev);
+  if (has_res) v += res;
+  reinterpret_cast<bf16*>(a.y)[(size_t)slot * a.y_slot_stride + row] = __float2bfloat16_rn(v);
+}
 
 // Register-streamed like stream_ldg_kernel, but nothing of the weights may be touched before the wait: which
 // matrices to read is the router's output.  GATED: h = act(fc_1 x) * fc_2 x of expert sel[k].  PLAIN (down):
@@ -979,10 +988,8 @@ __global__ void __launch_bounds__(LIN_THREADS, 3) moe_stream_kernel(const Stream
       for (int j = 0; j < 2; ++j) {
         const int row = 2 * it + j;
         if (row >= a.N) continue;
-        float v = round_bf16(round_bf16(o[j]) * route);
-        if (m.prev) v = round_bf16(v + __bfloat162float(m.prev[row]));
-        if (res) v += __bfloat162float(res[row]);
-        reinterpret_cast<bf16*>(a.y)[(size_t)slot * a.y_slot_stride + row] = __float2bfloat16_rn(v);
+        moe_down_store(a, row, slot, o[j], route, m.prev != nullptr, m.prev ? __bfloat162float(m.prev[row]) : 0.f,
+                       res != nullptr, res ? __bfloat162float(res[row]) : 0.f);
       }
     }
   }
@@ -992,6 +999,134 @@ __global__ void __launch_bounds__(LIN_THREADS, 3) moe_stream_kernel(const Stream
   trace_mark(a.trace, 3, true);
   trace_mark(a.trace, 4, false);
 }
+
+// The same passes through the per-warp bulk-copy ring of stream_bulk_kernel.  Every launch but the first one after
+// the router (`sel_early`) knows its expert before the dependency wait and fills its ring while the previous kernel
+// drains, exactly like the dense kernels; the first one resolves its pointers right after the wait.
+template <int MODE, int STAGES>
+__global__ void __launch_bounds__(LIN_THREADS, STAGES == 2 ? 3 : 2) moe_bulk_kernel(const StreamArgs a, const MoeArgs m) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int gw = blockIdx.x * LIN_WARPS + warp, n_gw = gridDim.x * LIN_WARPS;
+  trace_mark(a.trace, 0, true);
+  bf16* ring = reinterpret_cast<bf16*>(smem_raw) + (size_t)warp * STAGES * 2 * TS_CHUNK;
+  bf16* xs = reinterpret_cast<bf16*>(smem_raw) + (size_t)LIN_WARPS * STAGES * 2 * TS_CHUNK;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(xs + ((a.K + 63) / 64) * 64) + warp * STAGES;
+  __shared__ float red[LIN_WARPS];
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) mbar_init(&bars[s], 1);
+    mbar_fence_init();
+  }
+  __syncwarp();
+
+  const int n_chunks = (a.K + TS_CHUNK - 1) / TS_CHUNK;
+  const int n_my = gw < a.n_items ? (a.n_items - gw + n_gw - 1) / n_gw : 0;
+  const int total = n_my * n_chunks;
+  const bf16 *W = nullptr, *W2 = nullptr;
+  float route = 0.f;
+  auto resolve = [&]() {
+    const int e = m.sel[m.k];
+    route = m.wts[m.k];
+    W = m.w[e];
+    if (MODE == MODE_GATED) W2 = m.w2[e];
+  };
+  auto issue = [&](int f) {
+    const int ii = f / n_chunks, c = f - ii * n_chunks;
+    const int it = gw + ii * n_gw;
+    const bf16 *wa, *wb;
+    if (MODE == MODE_GATED) {
+      wa = W + (size_t)it * a.K;
+      wb = W2 + (size_t)it * a.K;
+    } else {
+      wa = W + (size_t)(2 * it) * a.K;
+      wb = W + (size_t)min(2 * it + 1, a.N - 1) * a.K;
+    }
+    const int k0 = c * TS_CHUNK;
+    const uint32_t bytes = (uint32_t)min(TS_CHUNK, a.K - k0) * 2u;
+    const int st = f % STAGES;
+    bf16* dst = ring + (size_t)st * 2 * TS_CHUNK;
+    mbar_expect_tx(&bars[st], 2 * bytes);
+    bulk_g2s(dst, wa + k0, bytes, &bars[st]);
+    bulk_g2s(dst + TS_CHUNK, wb + k0, bytes, &bars[st]);
+  };
+  if (m.sel_early) {
+    resolve();
+    if (lane == 0)
+      for (int f = 0; f < min(STAGES, total); ++f) issue(f);
+  }
+  uint4 w_pre[4];
+  const bool have_w = a.norm_w != nullptr && !a.layer_norm && a.K <= STAGE_VPT * LIN_THREADS * 8;
+  if (have_w) preload_norm_w(a.norm_w, a.K, w_pre);
+  pdl_wait_prior();
+  trace_mark(a.trace, 1, true);
+  if (!m.sel_early) {
+    resolve();
+    if (lane == 0)
+      for (int f = 0; f < min(STAGES, total); ++f) issue(f);
+  }
+  const int slot = a.ctx ? a.ctx[MDI_CTX_SLOT] : 0, pos = a.ctx ? a.ctx[MDI_CTX_POS] : 0;
+  stage_input(a.x + (size_t)slot * a.x_slot_stride, a.norm_w, a.eps, a.unit_offset, a.K, xs, red, a.norm_b, a.layer_norm,
+              have_w ? w_pre : nullptr);
+  trace_mark(a.trace, 2, false);
+  pdl_launch_dependents();
+
+  const bf16* res = a.residual ? a.residual + (size_t)slot * a.res_slot_stride : nullptr;
+  float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+  int c = 0, ii = 0;
+  float pre_res[2] = {0.f, 0.f}, pre_prev[2] = {0.f, 0.f};  // requested when the item starts (off the tail)
+  unsigned long long best = 0ull;
+  for (int f = 0; f < total; ++f) {
+    const int st = f % STAGES;
+    if (MODE == MODE_PLAIN && c == 0 && lane == 0) {
+      const int row = 2 * (gw + ii * n_gw);
+      const bool two = row + 1 < a.N;
+      if (res != nullptr) { pre_res[0] = __bfloat162float(res[row]); pre_res[1] = two ? __bfloat162float(res[row + 1]) : 0.f; }
+      if (m.prev != nullptr) { pre_prev[0] = __bfloat162float(m.prev[row]); pre_prev[1] = two ? __bfloat162float(m.prev[row + 1]) : 0.f; }
+    }
+    mbar_wait(&bars[st], (uint32_t)((f / STAGES) & 1));
+    const int k0 = c * TS_CHUNK;
+    const int nv = min(TS_CHUNK, a.K - k0) / 8;
+    const uint4* wa = reinterpret_cast<const uint4*>(ring + (size_t)st * 2 * TS_CHUNK);
+    const uint4* wb = wa + TS_CHUNK / 8;
+    const uint4* xv = reinterpret_cast<const uint4*>(xs + k0);
+    if (nv == TS_CHUNK / 8) {
+#pragma unroll
+      for (int u = 0; u < TS_CHUNK / 8 / 32; ++u) {
+        const uint4 x = xv[lane + 32 * u];
+        if (u & 1) { a1 += dot8(wa[lane + 32 * u], x); b1 += dot8(wb[lane + 32 * u], x); }
+        else { a0 += dot8(wa[lane + 32 * u], x); b0 += dot8(wb[lane + 32 * u], x); }
+      }
+    } else {
+      for (int v = lane; v < nv; v += 32) { const uint4 x = xv[v]; a0 += dot8(wa[v], x); b0 += dot8(wb[v], x); }
+    }
+    if (++c == n_chunks) {
+      const float da = warp_sum(a0 + a1), db = warp_sum(b0 + b1);
+      if (lane == 0) {
+        const int it = gw + ii * n_gw;
+        if (MODE == MODE_GATED) {
+          item_epilogue<MODE_GATED>(a, it, da, db, slot, pos, res, nullptr, best);
+        } else {
+          moe_down_store(a, 2 * it, slot, da, route, m.prev != nullptr, pre_prev[0], res != nullptr, pre_res[0]);
+          if (2 * it + 1 < a.N)
+            moe_down_store(a, 2 * it + 1, slot, db, route, m.prev != nullptr, pre_prev[1], res != nullptr, pre_res[1]);
+        }
+      }
+      a0 = a1 = b0 = b1 = 0.f;
+      c = 0;
+      ++ii;
+    }
+    __syncwarp();
+    if (lane == 0 && f + STAGES < total) issue(f + STAGES);
+  }
+  if (a.hop_row) hop_signal_copy(a.signal, a.ctx, reinterpret_cast<const bf16*>(a.y) + (size_t)slot * a.y_slot_stride,
+                                 a.hop_row + (size_t)slot * a.hop_slot_stride, a.N, nullptr, 0);
+  else hop_signal(a.signal, a.ctx);
+  trace_mark(a.trace, 3, true);
+  trace_mark(a.trace, 4, false);
+}
+
+static int g_moe_variant = 2;  // 0 = register-streamed, 2 = bulk-copy ring x2 (see mdi_set_moe_variant)
 
 static int g_num_sms = 0;
 static int num_sms() {
@@ -1077,6 +1212,7 @@ using namespace mdi;
 extern "C" {
 
 void mdi_set_linear_variant(int v) { g_default_variant = v; }
+void mdi_set_moe_variant(int v) { g_moe_variant = v; }  // expert passes: 0 = register-streamed, else the bulk-copy ring
 void mdi_set_l2_prefetch_mb(int mb) { g_l2_prefetch_mb = mb; }
 int mdi_get_linear_variant() { return g_default_variant; }
 
@@ -1172,7 +1308,7 @@ int mdi_moe_linear_decode(const void* w_ptrs, const void* w2_ptrs, const int* se
                           const int* ctx, long long x_slot_stride, long long res_slot_stride, long long y_slot_stride, int N,
                           int K, float eps, int unit_offset, int act, int* status, int* signal_flag, unsigned int* done_ctr,
                           void* hop_row, long long hop_slot_stride, int ctas_per_sm, int use_pdl, unsigned long long* trace,
-                          cudaStream_t stream) {
+                          int sel_early, cudaStream_t stream) {
   if (K % 8 != 0 || !w_ptrs || !sel || !wts || k < 0 || k >= MOE_MAX_TOP) return -2;
   if (hop_row && (!signal_flag || !y)) return -2;
   StreamArgs a{};
@@ -1185,10 +1321,17 @@ int mdi_moe_linear_decode(const void* w_ptrs, const void* w2_ptrs, const int* se
   a.trace = trace; a.hop_row = (bf16*)hop_row; a.hop_slot_stride = hop_slot_stride;
   MoeArgs m{};
   m.w = (const bf16* const*)w_ptrs; m.w2 = (const bf16* const*)w2_ptrs; m.sel = sel; m.wts = wts; m.k = k;
-  m.prev = (const bf16*)prev;
+  m.prev = (const bf16*)prev; m.sel_early = sel_early;
   if (ctas_per_sm <= 0) ctas_per_sm = 3;
-  const int grid = max(1, min(num_sms() * min(ctas_per_sm, 3), (a.n_items + LIN_WARPS - 1) / LIN_WARPS));
-  const size_t smem = (size_t)((K + 63) / 64) * 64 * sizeof(bf16);
+  const int max_useful = (a.n_items + LIN_WARPS - 1) / LIN_WARPS;
+  int grid = max(1, min(num_sms() * min(ctas_per_sm, 3), max_useful));
+  size_t smem = (size_t)((K + 63) / 64) * 64 * sizeof(bf16);
+  const size_t smem_ring = (size_t)LIN_WARPS * 2 * 2 * TS_CHUNK * 2 + smem + (size_t)LIN_WARPS * 2 * 8;
+  const bool ring = g_moe_variant != 0 && smem_ring <= 227 * 1024;
+  if (ring) {
+    smem = smem_ring;
+    grid = max(1, min(num_sms() * max(1, min(min(ctas_per_sm, 3), (int)((227 * 1024) / (smem + 1024)))), max_useful));
+  }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(LIN_THREADS);
@@ -1199,6 +1342,12 @@ int mdi_moe_linear_decode(const void* w_ptrs, const void* w2_ptrs, const int* se
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = use_pdl ? 1 : 0;
+  if (ring) {
+    auto kern = w2_ptrs ? moe_bulk_kernel<MODE_GATED, 2> : moe_bulk_kernel<MODE_PLAIN, 2>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    return (int)cudaLaunchKernelEx(&cfg, kern, a, m);
+  }
   if (w2_ptrs) {
     if (smem > 48 * 1024) {
       cudaError_t e = cudaFuncSetAttribute(moe_stream_kernel<MODE_GATED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -519,8 +519,9 @@ class FusedStage:
             for k in range(top):
                 ops.moe_linear_decode(p1, x_src, self.h_mlp, self.ctx, self.moe_sel, self.moe_wts, k, N=I, K=C, w2_ptrs=p2,
                                       **norm, act=self._gate_act(), x_slot_stride=x_stride, ctas_per_sm=min(3, self._ctas("gate_up")),
-                                      status=self.status.data_ptr(), trace=self._tr(f"L{li}.e{k}.gate_up"), **common)
-                kw: Dict[str, Any] = dict(N=C, K=I, prev=self.moe_acc[(k + 1) % 2] if k > 0 else None,
+                                      status=self.status.data_ptr(), trace=self._tr(f"L{li}.e{k}.gate_up"), sel_early=k > 0, **common)
+                # every pass but the first runs >= 2 launches after the router: its expert is known before the PDL wait
+                kw: Dict[str, Any] = dict(N=C, K=I, prev=self.moe_acc[(k + 1) % 2] if k > 0 else None, sel_early=True,
                                           ctas_per_sm=min(3, self._ctas("down")), status=self.status.data_ptr(), **common)
                 if k < top - 1:
                     ops.moe_linear_decode(p3, self.h_mlp, self.moe_acc[k % 2], self.ctx, self.moe_sel, self.moe_wts, k,

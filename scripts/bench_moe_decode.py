@@ -4,7 +4,7 @@
 (torch.topk / torch.where routing, the reference's formulation) on the same GPU, and against the bytes a step has
 to stream (attention + the two chosen experts of every layer) at the measured HBM copy bandwidth.
 CUDA events, warm; consecutive tokens pick different experts, so the expert matrices (2.8 GB per layer) do not
-stay in L2.  Writes gpurun_out/moe_decode_bench.json."""
+stay in L2.  Writes gpurun_out/moe_decode_bench_v<variant>.json."""
 import argparse
 import json
 import os
@@ -28,8 +28,10 @@ def main() -> None:
     ap.add_argument("--ctx", type=int, default=64)
     ap.add_argument("--steps", type=int, default=160)
     ap.add_argument("--n-samples", type=int, default=8)
+    ap.add_argument("--moe-variant", type=int, default=2, help="expert passes: 0 register-streamed, 2 bulk-copy ring")
     a = ap.parse_args()
     ops.require()
+    ops.set_moe_variant(a.moe_variant)
     cfg = Config.from_name(a.model, n_layer=a.layers, block_size=1024)
     st = build_stage(cfg, "secondary:0", a.layers, meta=True)
     random_init_stage_(st, "cuda", torch.bfloat16, seed=1)
@@ -76,14 +78,14 @@ def main() -> None:
     except OSError:
         pass
     bw = float(peaks.get("hbm_gbs", 6577.0)) if isinstance(peaks, dict) else 6577.0
-    out = {"model": a.model, "layers": a.layers, "ctx": a.ctx, "n_samples": n, "fused_us_per_step": round(fused_us, 2),
+    out = {"model": a.model, "moe_variant": a.moe_variant, "layers": a.layers, "ctx": a.ctx, "n_samples": n, "fused_us_per_step": round(fused_us, 2),
            "eager_us_per_step": round(eager_us, 2), "speedup_vs_eager": round(eager_us / fused_us, 2),
            "weight_bytes_per_step": step_bytes, "hbm_floor_us": round(step_bytes / (bw * 1e3), 2),
            "fraction_of_hbm_floor": round(step_bytes / (bw * 1e3) / fused_us, 3), "hbm_gbps_assumed": bw,
            "kernel_launches": launches, "status": status}
     print(json.dumps(out), flush=True)
     os.makedirs("gpurun_out", exist_ok=True)
-    json.dump(out, open("gpurun_out/moe_decode_bench.json", "w"), indent=1)
+    json.dump(out, open(f"gpurun_out/moe_decode_bench_v{a.moe_variant}.json", "w"), indent=1)
 
 
 if __name__ == "__main__":

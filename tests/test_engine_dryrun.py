@@ -132,6 +132,8 @@ def test_moe_decode_launch_sequence_binds(role, kw):
     for gu0, dn0, gu1, dn1 in per_layer:
         assert gu0["w2_ptrs"] is not None and gu1["w2_ptrs"] is not None and dn0.get("w2_ptrs") is None
         assert (gu0["k"], dn0["k"], gu1["k"], dn1["k"]) == (0, 0, 1, 1)
+        # only the pass right behind the router has to wait for it before it knows its expert
+        assert [bool(c.get("sel_early")) for c in (gu0, dn0, gu1, dn1)] == [False, True, True, True]
         assert dn0.get("residual") is None and dn0.get("prev") is None and dn0["y"] is fs.moe_acc[0]
         assert dn1["prev"] is fs.moe_acc[0] and dn1["residual"] is not None  # running sum + residual on the last expert
         assert dn1.get("y") is not dn1["residual"]

@@ -509,11 +509,13 @@ def test_moe_router_picks_the_top_experts(E, top, K):
     assert abs(float(wts[:top].sum()) - 1.0) < 2e-2 and int(sel[top:].max() if top < 8 else -1) == -1
 
 
+@pytest.mark.parametrize("variant", [0, 2])
 @pytest.mark.parametrize("N,I", [(4096, 14336), (256, 128), (1000, 384)])
-def test_moe_expert_passes_follow_the_router_output(N, I):
+def test_moe_expert_passes_follow_the_router_output(N, I, variant):
     """Two routed experts through the pointer tables: h = silu(W1[e] xn) * W2[e] xn, y = x + sum_k w_k * (W3[e_k] h_k), with
     the eager module's rounding points; the pass of the last expert adds the residual and hops by row copy."""
     ops = _ops()
+    ops.set_moe_variant(variant)  # 0: register-streamed, 2: bulk-copy ring
     torch.manual_seed(N + I)
     E, C = 4, N
     W1 = [(torch.randn(I, C, device="cuda") * 0.03).bfloat16() for _ in range(E)]
@@ -536,24 +538,26 @@ def test_moe_expert_passes_follow_the_router_output(N, I):
     xn = _rmsnorm_ref(x[1], nw, 1e-5)
     ref_sum = None
     for k, (e, w) in enumerate([(3, 0.625), (1, 0.375)]):
-        ops.moe_linear_decode(p1, x, h, ctx, sel, wts, k, N=I, K=C, w2_ptrs=p2, norm_w=nw, eps=1e-5, act="silu_gate", x_slot_stride=C)
+        ops.moe_linear_decode(p1, x, h, ctx, sel, wts, k, N=I, K=C, w2_ptrs=p2, norm_w=nw, eps=1e-5, act="silu_gate", x_slot_stride=C,
+                              sel_early=k > 0)
         g = (xn.float() @ W1[e].float().T).bfloat16()
         u = (xn.float() @ W2[e].float().T).bfloat16()
         h_ref = torch.nn.functional.silu(g.float()).bfloat16() * u
         torch.testing.assert_close(h.float(), h_ref.float(), rtol=3e-2, atol=3e-2)
         y_e = ((h.float() @ W3[e].float().T).bfloat16().float() * w).bfloat16()
         if k == 0:
-            ops.moe_linear_decode(p3, h, acc, ctx, sel, wts, k, N=C, K=I)
+            ops.moe_linear_decode(p3, h, acc, ctx, sel, wts, k, N=C, K=I, sel_early=True)
             torch.cuda.synchronize()
             torch.testing.assert_close(acc.float(), y_e.float(), rtol=2e-2, atol=2e-2)
             ref_sum = y_e
         else:
             ops.moe_linear_decode(p3, h, None, ctx, sel, wts, k, N=C, K=I, prev=acc, residual=x, res_slot_stride=C,
                                   y_ptr=out_local.data_ptr(), y_slot_stride=C, hop_ptr=peer.data_ptr(), hop_slot_stride=C,
-                                  signal_flag=flag.data_ptr(), done_ctr=done.data_ptr(), status=status.data_ptr())
+                                  signal_flag=flag.data_ptr(), done_ctr=done.data_ptr(), status=status.data_ptr(), sel_early=True)
             ref_sum = (ref_sum.float() + y_e.float()).bfloat16()
     torch.cuda.synchronize()
     ref = x[1].float() + ref_sum.float()
     torch.testing.assert_close(out_local[1].float(), ref, rtol=2e-2, atol=3e-2)
     assert torch.equal(peer[1], out_local[1]) and int(flag[1]) == 7 and int(flag[0]) == 0 and int(peer[0].abs().max()) == 0
     assert int(status[0]) == 0
+    ops.set_moe_variant(2)
