@@ -278,7 +278,7 @@ def moe_linear_decode(w_ptrs: torch.Tensor, x: torch.Tensor, y: Optional[torch.T
 
 
 def set_moe_variant(v: int) -> None:
-    """Weight path of the expert passes: 0 = register-streamed (LDG), otherwise the per-warp bulk-copy ring (default)."""
+    """Weight path of the expert passes: 0 = register-streamed (LDG, default), otherwise the per-warp bulk-copy ring."""
     lib().mdi_set_moe_variant(v)
 
 

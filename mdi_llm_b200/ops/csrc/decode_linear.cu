@@ -1126,7 +1126,9 @@ __global__ void __launch_bounds__(LIN_THREADS, STAGES == 2 ? 3 : 2) moe_bulk_ker
   trace_mark(a.trace, 4, false);
 }
 
-static int g_moe_variant = 2;  // 0 = register-streamed, 2 = bulk-copy ring x2 (see mdi_set_moe_variant)
+// 0 = register-streamed (default), 2 = bulk-copy ring x2 (mdi_set_moe_variant).  Measured on Mixtral-8x7B shapes the two are
+// within run-to-run noise (302.9 vs 309.4 us per 2-layer step, profiles/r2/moe_decode_bench_v*.json), so the simpler one stays.
+static int g_moe_variant = 0;
 
 static int g_num_sms = 0;
 static int num_sms() {

@@ -28,7 +28,7 @@ def main() -> None:
     ap.add_argument("--ctx", type=int, default=64)
     ap.add_argument("--steps", type=int, default=160)
     ap.add_argument("--n-samples", type=int, default=8)
-    ap.add_argument("--moe-variant", type=int, default=2, help="expert passes: 0 register-streamed, 2 bulk-copy ring")
+    ap.add_argument("--moe-variant", type=int, default=0, help="expert passes: 0 register-streamed, 2 bulk-copy ring")
     a = ap.parse_args()
     ops.require()
     ops.set_moe_variant(a.moe_variant)

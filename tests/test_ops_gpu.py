@@ -560,4 +560,4 @@ def test_moe_expert_passes_follow_the_router_output(N, I, variant):
     torch.testing.assert_close(out_local[1].float(), ref, rtol=2e-2, atol=3e-2)
     assert torch.equal(peer[1], out_local[1]) and int(flag[1]) == 7 and int(flag[0]) == 0 and int(peer[0].abs().max()) == 0
     assert int(status[0]) == 0
-    ops.set_moe_variant(2)
+    ops.set_moe_variant(0)
