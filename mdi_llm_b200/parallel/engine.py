@@ -60,8 +60,9 @@ def engine_supports(config: Config, dtype: torch.dtype) -> bool:
 def fused_prefill_supports(config: Config) -> bool:
     """Prompt processing on the tcgen05 GEMM + attention kernels (the Llama-shaped subset); other covered
     architectures prefill through their eager modules and decode through the fused kernels."""
+    mlps = ("LLaMAMLP", "GemmaMLP") if os.environ.get("MDI_MOE_PREFILL", "gemm") == "eager" else ("LLaMAMLP", "GemmaMLP", "LLaMAMoE")
     return (config.norm_class_name == "RMSNorm" and not config.parallel_residual
-            and config.mlp_class_name in ("LLaMAMLP", "GemmaMLP") and config.pos_embedding == "rope" and config.rope_n_elem > 0
+            and config.mlp_class_name in mlps and config.pos_embedding == "rope" and config.rope_n_elem > 0
             and config.head_size in (64, 128))
 
 
@@ -668,6 +669,14 @@ class FusedStage:
                 x = out_gemm(y, blk.attn.proj, last)
             elif kind == "down":
                 x = out_gemm(g_in, blk.mlp.proj, last)
+            elif self.moe:
+                x = self._moe_prefill(blk, x, eps, uo)
+                if last and hop is not None:
+                    ops.check(ops.lib().mdi_copy_signal(x.data_ptr(), hop[0], x.numel() * 2, hop[1], self.done_ctr.data_ptr(),
+                                                        self.ctx.data_ptr(), self.status.data_ptr(), ops.stream_ptr()),
+                              "prefill hop (mixture of experts)")
+                    self._keep = x  # the copy kernel reads it asynchronously
+                    return None
             else:
                 h = ops.rmsnorm_rows(x, blk.norm_2.weight, eps, uo)
                 g = self._gemm(h, blk.mlp.fc_1, blk.mlp.fc_2, act=self._gate_act(), **({"block_n": 512} if pair else {}))
@@ -683,6 +692,37 @@ class FusedStage:
             if x is None:
                 return None
         return x.unsqueeze(0)
+
+    def _moe_prefill(self, blk: Any, x: torch.Tensor, eps: float, uo: bool) -> torch.Tensor:
+        """Routed MLP of a whole prompt (model.py:823-853) on the tcgen05 GEMMs: route every token (top-k of the bf16
+        router logits, softmax over the chosen ones), sort the (token, expert) pairs by expert, and run each expert's
+        gated gate/up GEMM and down GEMM over ITS rows only.  One host read per layer (the per-expert row counts shape
+        the GEMM launches; prompt processing is not graph-captured) against the reference's ``torch.where`` per expert."""
+        mlp, top = blk.mlp, self.cfg.n_expert_per_token
+        T = x.shape[0]
+        h = ops.rmsnorm_rows(x, blk.norm_2.weight, eps, uo)
+        weight, chosen = torch.topk(torch.nn.functional.linear(h, mlp.gate.weight), top, dim=-1)  # [T, top]; E x C: negligible
+        weight = weight.softmax(dim=-1, dtype=torch.float).to(torch.bfloat16)
+        flat = chosen.reshape(-1)
+        order = torch.argsort(flat, stable=True)
+        counts = torch.bincount(flat, minlength=self.cfg.n_expert).tolist()
+        tok = order // top
+        rows = h.index_select(0, tok)  # [T * top, C], grouped by expert
+        w_sorted = weight.reshape(-1).index_select(0, order)
+        contrib = torch.empty(T * top, self.cfg.n_embd, dtype=torch.bfloat16, device=x.device)
+        off = 0
+        for e, n in enumerate(counts):
+            if n == 0:
+                continue
+            ex = mlp.experts[e]
+            bn = 512 if n >= 192 and os.environ.get("MDI_GEMM_PAIR", "1") != "0" else (256 if n > 128 else 128)
+            g = self._gemm(rows[off:off + n], ex.fc_1, ex.fc_2, act="silu_gate", block_n=bn)
+            self._gemm(g, ex.proj, out=contrib[off:off + n], block_n=bn)
+            off += n
+        contrib.mul_(w_sorted.unsqueeze(1))
+        out = torch.zeros_like(x)
+        out.index_add_(0, tok, contrib)  # bf16 accumulation like the eager module
+        return x + out
 
     # ---- graphs ------------------------------------------------------------------------------------
     def graph(self, key: Any, builder: Any, warm: bool = True) -> ops.CudaGraph:

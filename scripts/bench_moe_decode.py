@@ -28,6 +28,7 @@ def main() -> None:
     ap.add_argument("--ctx", type=int, default=64)
     ap.add_argument("--steps", type=int, default=160)
     ap.add_argument("--n-samples", type=int, default=8)
+    ap.add_argument("--prefill", type=int, default=1024, help="prompt length of the prefill comparison")
     ap.add_argument("--moe-variant", type=int, default=0, help="expert passes: 0 register-streamed, 2 bulk-copy ring")
     a = ap.parse_args()
     ops.require()
@@ -70,6 +71,25 @@ def main() -> None:
         torch.cuda.synchronize()
     eager_us = e0.elapsed_time(e1) * 1e3 / (4 * n)
 
+    # the prompt: routed MLPs on the tcgen05 GEMMs (per-expert rows) + tcgen05 attention, against the eager modules
+    T = a.prefill
+    xp = (torch.randn(1, T, cfg.n_embd, device="cuda") * 0.5).bfloat16()
+    ppos = torch.arange(T, device="cuda")
+    pf = {}
+    with torch.inference_mode():
+        for name, fn in (("fused", lambda: fs.prefill(xp, ppos, 0)), ("eager", lambda: st(xp, ppos, slot=0))):
+            fs.set_ctx(0, T - 1)
+            for _ in range(2):
+                fn()
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(5):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            pf[name] = e0.elapsed_time(e1) / 5
+        err = (fs.prefill(xp, ppos, 0).float() - st(xp, ppos, slot=0).float()).abs().max().item()
+
     C, I = cfg.n_embd, cfg.intermediate_size
     step_bytes = a.layers * 2 * (cfg.qkv_size * C + cfg.attn_out_dim * C + cfg.n_expert * C + cfg.n_expert_per_token * 3 * C * I)
     peaks = {}
@@ -82,7 +102,11 @@ def main() -> None:
            "eager_us_per_step": round(eager_us, 2), "speedup_vs_eager": round(eager_us / fused_us, 2),
            "weight_bytes_per_step": step_bytes, "hbm_floor_us": round(step_bytes / (bw * 1e3), 2),
            "fraction_of_hbm_floor": round(step_bytes / (bw * 1e3) / fused_us, 3), "hbm_gbps_assumed": bw,
-           "kernel_launches": launches, "status": status}
+           "kernel_launches": launches, "status": status,
+           "prefill": {"tokens": T, "fused_ms": round(pf["fused"], 3), "eager_ms": round(pf["eager"], 3),
+                       "speedup_vs_eager": round(pf["eager"] / pf["fused"], 2), "max_abs_diff": round(err, 4),
+                       "flops": a.layers * 2 * T * (cfg.qkv_size * C + cfg.attn_out_dim * C + cfg.n_expert_per_token * 3 * C * I)}}
+    out["prefill"]["tflops_fused"] = round(out["prefill"]["flops"] / (pf["fused"] * 1e-3) / 1e12, 1)
     print(json.dumps(out), flush=True)
     os.makedirs("gpurun_out", exist_ok=True)
     json.dump(out, open(f"gpurun_out/moe_decode_bench_v{a.moe_variant}.json", "w"), indent=1)

@@ -112,7 +112,7 @@ def test_moe_decode_launch_sequence_binds(role, kw):
     hop wait, the token's last down pass adds the residual and carries the outgoing hop."""
     cfg = Config.from_name("tiny-llama-1.1b", n_layer=3, n_embd=256, n_head=4, n_query_groups=2, intermediate_size=128, vocab_size=120,
                            padded_vocab_size=128, block_size=64, mlp_class_name="LLaMAMoE", n_expert=4, n_expert_per_token=2)
-    assert eng.engine_supports(cfg, torch.bfloat16) and not eng.fused_prefill_supports(cfg)
+    assert eng.engine_supports(cfg, torch.bfloat16) and eng.fused_prefill_supports(cfg)
     with dry_ops() as calls:
         st = build_stage(cfg, role, 3, **kw).to(torch.bfloat16)
         st.max_seq_length = 32
@@ -143,6 +143,20 @@ def test_moe_decode_launch_sequence_binds(role, kw):
     with dry_ops():
         with pytest.raises(ValueError, match="fp8"):
             FusedStage(build_stage(cfg, "starter", 3).to(torch.bfloat16), n_slots=1, max_seq_length=32, weight_dtype="fp8")
+    # the prompt: every routed MLP = per-expert gated GEMM + down GEMM over that expert's rows only
+    if role != "starter":
+        with dry_ops() as calls:
+            st = build_stage(cfg, role, 3, **kw).to(torch.bfloat16)
+            st.set_kv_cache(2, dtype=torch.bfloat16)
+            fs = FusedStage(st, n_slots=2, max_seq_length=32)
+            with mock.patch.object(ops, "check", lambda *a, **k: None), mock.patch.object(ops, "lib", lambda: mock.MagicMock()), \
+                    mock.patch.object(ops, "stream_ptr", lambda: 0):
+                out = fs.prefill(torch.zeros(1, 5, 256, dtype=torch.bfloat16), torch.arange(5), 0, hop=(0x3000, 0x4000))
+            assert out is None
+            gated = [c[1] for c in calls if c[0] == "gemm" and c[1].get("w2") is not None]
+            n_moe = sum(1 for _, k in fs._units() if k == "mlp")
+            # all-zero router logits: topk picks experts 0 and 1 for every token -> two experts x 5 rows per routed MLP
+            assert len(gated) == 2 * n_moe and all(g["a"].shape == (5, 256) and g["act"] == "silu_gate" for g in gated)
 
 
 def test_local_output_and_prefill_sequences_bind():
