@@ -618,6 +618,8 @@ class FusedStage:
         m, cfg = self.model, self.cfg
         C = cfg.n_embd
         T = data.size(1)
+        if T > self.S:
+            raise ValueError(f"prompt of {T} tokens does not fit the stage's KV slots ({self.S} positions)")
         g_in = None
         if not self.fused_prefill:
             # architectures outside the tcgen05 prefill subset (LayerNorm / parallel residual / plain MLP / learned

@@ -38,7 +38,7 @@ def main() -> None:
     random_init_stage_(st, "cuda", torch.bfloat16, seed=1)
     n = a.n_samples
     warm = 5 * n
-    pipe = DevicePipeline(st, 1, 2, n_samples=n, max_seq_length=a.ctx + a.steps + warm + 80, sampling=SamplingParams(seed=1),
+    pipe = DevicePipeline(st, 1, 2, n_samples=n, max_seq_length=max(a.ctx + a.steps + warm + 80, a.prefill + 16), sampling=SamplingParams(seed=1),
                           exportable=False)
     pipe.prepare([torch.zeros(a.ctx, dtype=torch.int32) for _ in range(n)], (a.steps + warm) // n + 3)
     fs = pipe.stage
