@@ -703,7 +703,7 @@ class FusedStage:
         mlp, top = blk.mlp, self.cfg.n_expert_per_token
         T = x.shape[0]
         h = ops.rmsnorm_rows(x, blk.norm_2.weight, eps, uo)
-        weight, chosen = torch.topk(torch.nn.functional.linear(h, mlp.gate.weight), top, dim=-1)  # [T, top]; E x C: negligible
+        weight, chosen = torch.topk(mlp.gate(h), top, dim=-1)  # [T, top]; the router is E x C: negligible
         weight = weight.softmax(dim=-1, dtype=torch.float).to(torch.bfloat16)
         flat = chosen.reshape(-1)
         order = torch.argsort(flat, stable=True)

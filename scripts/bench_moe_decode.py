@@ -33,7 +33,7 @@ def main() -> None:
     a = ap.parse_args()
     ops.require()
     ops.set_moe_variant(a.moe_variant)
-    cfg = Config.from_name(a.model, n_layer=a.layers, block_size=1024)
+    cfg = Config.from_name(a.model, n_layer=a.layers, block_size=4096)
     st = build_stage(cfg, "secondary:0", a.layers, meta=True)
     random_init_stage_(st, "cuda", torch.bfloat16, seed=1)
     n = a.n_samples
@@ -88,7 +88,25 @@ def main() -> None:
             e1.record()
             torch.cuda.synchronize()
             pf[name] = e0.elapsed_time(e1) / 5
-        err = (fs.prefill(xp, ppos, 0).float() - st(xp, ppos, slot=0).float()).abs().max().item()
+        # accuracy: a routed model is discontinuous where two experts' router logits nearly tie, so rows whose routing
+        # differs between the two runs (bf16 noise of the attention / norm in front of the router) are counted apart
+        routed = []
+        hooks = [blk.mlp.gate.register_forward_hook(lambda _m, _i, o: routed.append(torch.topk(o, cfg.n_expert_per_token, dim=-1).indices.sort(-1).values))
+                 for blk in st.transformer.h]
+        out_e = st(xp, ppos, slot=0).float()[0]
+        out_f = fs.prefill(xp, ppos, 0).float()[0]
+        for hk in hooks:
+            hk.remove()
+        L = len(st.transformer.h)
+        same = torch.ones(T, dtype=torch.bool, device="cuda")
+        for li in range(L):
+            same &= (routed[li].reshape(T, -1) == routed[L + li].reshape(T, -1)).all(-1)
+        row_err = (out_e - out_f).abs().max(-1).values
+        scale = out_e.abs().max().item()
+        acc = {"out_scale": round(scale, 3), "rows_same_routing": int(same.sum()), "rows_routing_flipped": int((~same).sum()),
+               "max_err_same_routing": round(row_err[same].max().item(), 4) if bool(same.any()) else None,
+               "mean_err_same_routing": round((out_e - out_f).abs()[same].mean().item(), 5) if bool(same.any()) else None,
+               "max_err_flipped": round(row_err[~same].max().item(), 4) if bool((~same).any()) else None}
 
     C, I = cfg.n_embd, cfg.intermediate_size
     step_bytes = a.layers * 2 * (cfg.qkv_size * C + cfg.attn_out_dim * C + cfg.n_expert * C + cfg.n_expert_per_token * 3 * C * I)
@@ -104,7 +122,7 @@ def main() -> None:
            "fraction_of_hbm_floor": round(step_bytes / (bw * 1e3) / fused_us, 3), "hbm_gbps_assumed": bw,
            "kernel_launches": launches, "status": status,
            "prefill": {"tokens": T, "fused_ms": round(pf["fused"], 3), "eager_ms": round(pf["eager"], 3),
-                       "speedup_vs_eager": round(pf["eager"] / pf["fused"], 2), "max_abs_diff": round(err, 4),
+                       "speedup_vs_eager": round(pf["eager"] / pf["fused"], 2), "accuracy_vs_eager": acc,
                        "flops": a.layers * 2 * T * (cfg.qkv_size * C + cfg.attn_out_dim * C + cfg.n_expert_per_token * 3 * C * I)}}
     out["prefill"]["tflops_fused"] = round(out["prefill"]["flops"] / (pf["fused"] * 1e-3) / 1e12, 1)
     print(json.dumps(out), flush=True)
