@@ -29,7 +29,7 @@ from typing import Any, Dict, List, Optional, Sequence, Tuple, Union
 import torch
 
 from ..models.config import Config
-from ..models.partition import (chunk_dir, count_transformer_blocks, plan_half_units, plan_layers, split_and_store,
+from ..models.partition import (chunk_dir, count_transformer_blocks, plan_layers, split_and_store,
                                 stage_specs)
 from ..utils.checkpoint import lazy_load, load_from_pt
 from .control import call_node, request_to_node

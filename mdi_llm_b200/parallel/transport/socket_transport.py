@@ -22,7 +22,7 @@ from typing import Any, Dict, Optional
 import torch
 
 from ...config import HEADERLENGTH
-from .base import ChaosPolicy, Message, MessageQueue, Transport, TransportError
+from .base import ChaosPolicy, Message, MessageQueue, Transport
 
 __all__ = ["InputNodeConnection", "OutputNodeConnection", "SocketTransport", "encode_frame", "read_exact"]
 
