@@ -74,6 +74,8 @@ def build_parser() -> argparse.ArgumentParser:
     p.add_argument("--once", type=str, default=None, help="answer this single prompt and exit (non-interactive)")
     p.add_argument("--engine", default="auto", choices=["auto", "eager", "cuda"], help="fused sm_100a engine or eager PyTorch")
     p.add_argument("--top-p", type=float, default=1.0)
+    p.add_argument("-c", "--compile", action="store_true",
+                   help="accepted for compatibility (chat.py:215): the fused engine needs no compilation step")
     return p
 
 
