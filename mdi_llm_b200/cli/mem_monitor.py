@@ -50,9 +50,14 @@ def main(argv=None) -> int:
     p = argparse.ArgumentParser(description=__doc__)
     p.add_argument("command", nargs=argparse.REMAINDER, help="command to run and monitor (after --)")
     p.add_argument("-i", "--interval", type=float, default=1.0)
-    p.add_argument("-o", "--out", type=Path, default=Path("logs/mem_usage.csv"))
-    p.add_argument("-p", "--plot", action="store_true")
+    p.add_argument("-o", "--out", "--output", dest="out", type=Path, default=Path("logs/mem_usage.csv"),
+                   help="CSV with the samples (the reference's -o/--output)")
+    p.add_argument("-p", "--plot", action="store_true", help="also write <out>.png")
+    p.add_argument("--img", type=Path, default=None, help="plot to this image file (the reference's --img; implies --plot)")
+    p.add_argument("-v", "--version", action="version", version="%(prog)s 0.2")
     a = p.parse_args(argv)
+    if a.img is not None:
+        a.plot = True
     cmd = [c for c in a.command if c != "--"]
     if not cmd:
         p.error("no command given")
@@ -87,7 +92,9 @@ def main(argv=None) -> int:
             for g in range(n_gpu):
                 plt.plot([r[0] for r in rows], [r[2 + g] for r in rows], label=f"GPU{g} (MiB)")
             plt.xlabel("time (s)"); plt.legend(); plt.grid()
-            plt.savefig(a.out.with_suffix(".png"))
+            img = a.img if a.img is not None else a.out.with_suffix(".png")
+            img.parent.mkdir(parents=True, exist_ok=True)
+            plt.savefig(img)
     return proc.returncode or 0
 
 

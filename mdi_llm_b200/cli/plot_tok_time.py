@@ -26,12 +26,19 @@ def read_points(path: Path) -> List[Tuple[float, int]]:
 
 def main(argv=None) -> int:
     p = argparse.ArgumentParser(description=__doc__)
-    p.add_argument("--model", required=True)
+    p.add_argument("MODEL_DIR", nargs="?", type=Path, default=None,
+                   help="checkpoint directory of the model (the reference's positional form: its name selects the CSVs)")
+    p.add_argument("--model", default=None, help="model name, instead of MODEL_DIR")
+    p.add_argument("-nt", "--no-title", action="store_true", help="if set, don't print the figure title")
     p.add_argument("--n-samples", type=int, default=3)
     p.add_argument("--max-nodes", type=int, default=8)
     p.add_argument("--logs-dir", type=Path, default=LOGS_DIR)
     p.add_argument("-o", "--out", type=Path, default=None)
     a = p.parse_args(argv)
+    if a.model is None:
+        if a.MODEL_DIR is None:
+            p.error("give the model as MODEL_DIR or --model")
+        a.model = a.MODEL_DIR.name
     curves: Dict[int, List[Tuple[float, int]]] = {}
     for k in range(1, a.max_nodes + 1):
         f = a.logs_dir / tokens_time_csv_name(k, a.model, a.n_samples)
@@ -56,7 +63,9 @@ def main(argv=None) -> int:
         plt.figure(figsize=(12, 6))
         for k, pts in sorted(curves.items()):
             plt.plot([t for t, _ in pts], [n for _, n in pts], label=f"{k} node{'s' if k > 1 else ''}")
-        plt.xlabel("Time (s)"); plt.ylabel("Tokens"); plt.title(f"{a.model}: generated tokens vs time"); plt.grid(); plt.legend()
+        plt.xlabel("Time (s)"); plt.ylabel("Tokens"); plt.grid(); plt.legend()
+        if not a.no_title:
+            plt.title(f"{a.model}: generated tokens vs time")
         out = a.out or (a.logs_dir / f"tokens_time_{a.model}_{a.n_samples}samples.png")
         plt.savefig(out)
         print(f"plot saved to {out}")

@@ -32,12 +32,18 @@ def write_sharded(token_lists, total_len: int, path: Path, n_shards: int = 1024)
 
 def main(argv=None) -> int:
     p = argparse.ArgumentParser(description=__doc__)
-    p.add_argument("--tokenizer", type=Path, required=True)
-    p.add_argument("--out-dir", type=Path, default=Path("data/openwebtext"))
-    p.add_argument("--num-proc", type=int, default=max(1, (os.cpu_count() or 2) // 2))
+    p.add_argument("TOKENIZER_PATH", nargs="?", type=Path, default=None,
+                   help="directory containing the tokenizer (the reference's positional form, prepare_owt.py:76)")
+    p.add_argument("--tokenizer", type=Path, default=None, help="the same, as an option")
+    p.add_argument("--out-dir", "--data-path", dest="out_dir", type=Path, default=Path("data/openwebtext"))
+    p.add_argument("--num-proc", "--nproc", dest="num_proc", type=int, default=max(1, (os.cpu_count() or 2) // 2))
+    p.add_argument("--device", default=None, help="accepted for compatibility (tokenisation runs on the CPU)")
     p.add_argument("--text-dir", type=Path, default=None, help="tokenise local .txt files instead of downloading")
     p.add_argument("--val-fraction", type=float, default=0.0005)
     a = p.parse_args(argv)
+    a.tokenizer = a.tokenizer or a.TOKENIZER_PATH
+    if a.tokenizer is None:
+        p.error("give the tokenizer directory (positional TOKENIZER_PATH or --tokenizer)")
     from ..text.tokenizer import Tokenizer
 
     tok = Tokenizer(a.tokenizer)

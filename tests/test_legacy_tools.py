@@ -92,3 +92,34 @@ def test_shared_parse_args_builds_both_flag_sets():
     assert tr.batch_size == 4 and tr.init == "resume" and tr.always_update and not tr.verb
     gen = parse_args(False, ["--n-samples", "3", "-p", "--n-tokens", "10", "--prompt", "hi"])
     assert gen.plots and gen.n_samples == 3 and gen.n_tokens == 10 and gen.prompt == "hi"
+
+
+def test_tools_accept_the_reference_spellings(tmp_path, capsys):
+    """mem_monitor (-o/--output, --img, one quoted command), plot_tok_time (positional MODEL_DIR, -nt) and prepare_owt
+    (positional TOKENIZER_PATH, --data-path, --nproc) take the argument forms of the reference's scripts."""
+    import sys
+
+    from mdi_llm_b200.cli import mem_monitor, plot_tok_time, prepare_owt
+    from mdi_llm_b200.cli.common import tokens_time_csv_name
+    from mdi_llm_b200.text.tokenizer import write_bytes_tokenizer
+
+    out, img = tmp_path / "mem" / "usage.csv", tmp_path / "mem" / "usage_plot.png"
+    rc = mem_monitor.main(["-i", "0.05", "--output", str(out), "--img", str(img), f"{sys.executable} -c \"import time; time.sleep(0.3)\""])
+    assert rc == 0
+    rows = out.read_text().strip().splitlines()
+    assert rows[0].startswith("time_s,rss_mib") and len(rows) >= 2
+
+    logs = tmp_path / "logs"
+    logs.mkdir()
+    for k in (1, 2):
+        (logs / tokens_time_csv_name(k, "NanoLlama", 3)).write_text("".join(f"{0.1 * i / k},{i}\n" for i in range(1, 6)))
+    assert plot_tok_time.main([str(tmp_path / "ckpt" / "NanoLlama"), "-nt", "--n-samples", "3", "--logs-dir", str(logs)]) == 0
+    assert "speed-up" in capsys.readouterr().out
+
+    tok_dir, text_dir, data = tmp_path / "tok", tmp_path / "text", tmp_path / "owt"
+    tok_dir.mkdir(); text_dir.mkdir()
+    write_bytes_tokenizer(tok_dir)
+    for i in range(3):
+        (text_dir / f"d{i}.txt").write_text(f"document number {i} " * 20)
+    assert prepare_owt.main([str(tok_dir), "--data-path", str(data), "--nproc", "1", "--text-dir", str(text_dir)]) == 0
+    assert (data / "train.bin").is_file() and (data / "val.bin").is_file()
