@@ -14,13 +14,29 @@ from pathlib import Path
 
 def main(argv=None) -> int:
     p = argparse.ArgumentParser(description=__doc__)
-    p.add_argument("ckpt", type=Path)
+    p.add_argument("ckpt", type=Path, nargs="?", default=None)
+    p.add_argument("--model", type=str, default=None,
+                   help="the reference's form (inspect_lit.py:112): a local checkpoint folder, or a Hugging Face repo id that is "
+                        "downloaded and converted into --ckpt-folder first")
+    p.add_argument("--ckpt-folder", type=Path, default=Path("checkpoints"))
+    p.add_argument("--device", type=str, default="cpu", help="accepted for compatibility (tensors are memory-mapped)")
+    p.add_argument("-s", "--save", action="store_true", help="write the parameter names to tmp/<model>_params_keys_lit.txt")
     p.add_argument("--keys", action="store_true", help="print every parameter key and shape")
     p.add_argument("--tokenizer", type=str, default=None, help="encode/decode this text with the checkpoint's tokenizer")
     a = p.parse_args(argv)
     from ..models.partition import count_transformer_blocks
     from ..utils.checkpoint import lazy_load, load_from_pt
 
+    if a.ckpt is None:
+        if a.model is None:
+            p.error("give the checkpoint directory (positional) or --model")
+        a.ckpt = Path(a.model)
+        if not a.ckpt.is_dir():  # a hub id: fetch + convert like the reference's load_from_hf
+            from ..utils.checkpoint import load_from_hf
+
+            print(f"Loading pretrained model {a.model} from Huggingface")
+            load_from_hf(a.model, checkpoint_dir=a.ckpt_folder)
+            a.ckpt = a.ckpt_folder / a.model
     cfg, _ = load_from_pt(a.ckpt, config_only=True)
     print("Model config:")
     for k, v in cfg.asdict().items():
@@ -35,6 +51,11 @@ def main(argv=None) -> int:
     if a.keys:
         for k, v in sd.items():
             print(f"  {k}: {tuple(v.shape)}")
+    if a.save:
+        keys_file = Path("tmp") / f"{a.ckpt.name}_params_keys_lit.txt"
+        keys_file.parent.mkdir(parents=True, exist_ok=True)
+        keys_file.write_text("".join(f"{k}\n" for k in sd))
+        print(f"Writing keys of Lit model to {keys_file}")
     chunks = a.ckpt / "chunks"
     if chunks.is_dir():
         for d in sorted(chunks.iterdir()):

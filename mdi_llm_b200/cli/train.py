@@ -40,7 +40,7 @@ def build_parser() -> argparse.ArgumentParser:
     p.add_argument("--dataset", type=Path, default=Path("./data/shakespeare"), help="directory with train.bin and val.bin")
     p.add_argument("--init", type=str, default="scratch", choices=["scratch", "resume", "hf"])
     p.add_argument("--model-name", type=str, default=None, help="registry name used when --ckpt has no model_config.yaml")
-    p.add_argument("--force-old", action="store_true", help="on resume keep the old training settings")
+    p.add_argument("-F", "--force-old", action="store_true", help="on resume keep the old training settings")
     p.add_argument("--batch-size", type=int, default=10)
     p.add_argument("--block-size", type=int, default=None, help="training context (default: model block size)")
     p.add_argument("--max-iters", type=int, default=100)

@@ -3,6 +3,7 @@ plots, tokenizer demo, offline splitter, toy models, split_map.json."""
 import json
 from pathlib import Path
 
+import pytest
 import torch
 
 from mdi_llm_b200.cli import inspect_checkpoint, plot_mem, split_model, test_tokenizer as tok_cli
@@ -123,3 +124,17 @@ def test_tools_accept_the_reference_spellings(tmp_path, capsys):
         (text_dir / f"d{i}.txt").write_text(f"document number {i} " * 20)
     assert prepare_owt.main([str(tok_dir), "--data-path", str(data), "--nproc", "1", "--text-dir", str(text_dir)]) == 0
     assert (data / "train.bin").is_file() and (data / "val.bin").is_file()
+
+
+def test_inspect_lit_reference_form(tmp_path, tiny_llama_cfg, capsys, monkeypatch):
+    """`inspect_lit --model <dir> -s` (scripts/inspect_lit.py:106-131): config dump, block-count check, key file."""
+    from mdi_llm_b200.cli import inspect_lit
+
+    ck = write_random_checkpoint(tmp_path / "tiny", tiny_llama_cfg, dtype=torch.float32)
+    monkeypatch.chdir(tmp_path)
+    assert inspect_lit.main(["--model", str(ck), "-s", "--device", "cpu"]) == 0
+    out = capsys.readouterr().out
+    assert f"{tiny_llama_cfg.n_layer} transformer blocks" in out
+    assert "transformer.wte.weight" in (tmp_path / "tmp" / "tiny_params_keys_lit.txt").read_text()
+    with pytest.raises(SystemExit):
+        inspect_lit.main([])
