@@ -138,3 +138,9 @@ def test_inspect_lit_reference_form(tmp_path, tiny_llama_cfg, capsys, monkeypatc
     assert "transformer.wte.weight" in (tmp_path / "tmp" / "tiny_params_keys_lit.txt").read_text()
     with pytest.raises(SystemExit):
         inspect_lit.main([])
+    # scripts/test_tok.py: the special tokens of a checkpoint's tokenizer
+    from mdi_llm_b200.text.tokenizer import write_bytes_tokenizer
+
+    write_bytes_tokenizer(ck)
+    assert tok_cli.main([str(ck)]) == 0
+    assert "Beginning of sentence: 256" in capsys.readouterr().out
