@@ -23,6 +23,9 @@ def build_parser() -> argparse.ArgumentParser:
     p.add_argument("--nodes-config", type=str, nargs=2, metavar=("CONFIG-PATH", "SECONDARY-INDEX"),
                    default=[str(SETTINGS_DIR / "configuration.json"), "0"],
                    help="JSON node topology and the zero-based index of this secondary")
+    p.add_argument("--secondary-config", type=Path, default=None,
+                   help="JSON holding only THIS node's entry (addr / communication / inference), alternative to --nodes-config "
+                        "(old/GPT2/secondary.py:46-52); the chunk then has to be given with --chunk or arrives with POST /init")
     p.add_argument("--device", type=str, default=None)
     p.add_argument("--dtype", type=str, default=None)
     p.add_argument("--seed", type=int, default=10137)
@@ -39,6 +42,8 @@ def main(argv=None) -> int:
     from ..parallel.distributed import GPTDistributed
 
     cfg_path, idx = Path(args.nodes_config[0]), int(args.nodes_config[1])
+    if args.secondary_config is not None:
+        cfg_path, idx = args.secondary_config, 0
     node = GPTDistributed(node_type=f"secondary:{idx}", config_file=cfg_path, ckpt_dir=args.ckpt, chunk_path=args.chunk,
                           device=args.device, dtype=args.dtype, verb=args.verb, compile=args.compile, engine=args.engine)
     node.start()

@@ -63,6 +63,31 @@ def test_starter_and_secondary_clis_over_loopback(tmp_path, tiny_ckpt, topology,
     assert plot_tok_time.main(["--model", "NanoLlama", "--n-samples", "2", "--logs-dir", str(tmp_path / "logs")]) == 0
 
 
+def test_secondary_started_from_its_own_node_file(tmp_path, tiny_ckpt, topology, monkeypatch):
+    """`secondary --secondary-config node.json --chunk …` (old/GPT2/secondary.py:46-52): the worker knows only its own
+    entry; everything else arrives with POST /init."""
+    topo = topology(2)
+    cfg_file, own = tmp_path / "nodes.json", tmp_path / "secondary0.json"
+    cfg_file.write_text(json.dumps(topo))
+    own.write_text(json.dumps(topo["nodes"]["secondary"][0]))
+    prepare_model.main([str(tiny_ckpt), "--n-nodes", "2"])
+    import mdi_llm_b200.cli.common as common
+    import mdi_llm_b200.cli.starter as starter_mod
+
+    for mod in (common, starter_mod):
+        monkeypatch.setattr(mod, "LOGS_DIR", tmp_path / "logs")
+    monkeypatch.setattr(starter_mod, "IMG_DIR", tmp_path / "img")
+    chunk = tiny_ckpt / "chunks" / "2nodes" / "model_secondary0.pth"
+    t = threading.Thread(target=secondary.main, args=(["--secondary-config", str(own), "--chunk", str(chunk), "--dtype", "float32"],),
+                         daemon=True)
+    t.start()
+    rc = starter.main(["--ckpt", str(tiny_ckpt), "--nodes-config", str(cfg_file), "--n-samples", "2", "--n-tokens", "3",
+                       "--prompt", "Hi", "--dtype", "float32", "--greedy"])
+    assert rc == 0
+    t.join(timeout=15)
+    assert not t.is_alive()
+
+
 def test_sample_and_chat_cli(tmp_path, tiny_ckpt, capsys, monkeypatch):
     import mdi_llm_b200.cli.sample as sample_mod
 
