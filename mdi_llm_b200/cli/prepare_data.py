@@ -15,8 +15,10 @@ import numpy as np
 
 def main(argv=None) -> int:
     p = argparse.ArgumentParser(description=__doc__)
-    p.add_argument("DATA", type=Path, help="text file (.txt/.md/.tex)")
-    p.add_argument("--tokenizer", type=str, required=True, help="tokenizer directory, or 'char' / 'bpe[:vocab_size]' / 'bytes'")
+    p.add_argument("DATA", type=Path, help="text file (.txt/.md/.tex), or a directory holding one .txt file (old/GPT2/prepare_data.py:24)")
+    p.add_argument("-t", "--tokenizer", type=str, default="character",
+                   help="tokenizer directory, or 'char' / 'character' / 'bpe[:vocab_size]' / 'bytes'")
+    p.add_argument("--vocab-size", type=int, default=500, help="vocabulary size of a custom BPE tokenizer ('-t bpe')")
     p.add_argument("--frac-train", type=float, default=0.9)
     p.add_argument("--out-dir", type=Path, default=None)
     a = p.parse_args(argv)
@@ -24,16 +26,23 @@ def main(argv=None) -> int:
     from ..text.tokenizer import Tokenizer, write_bytes_tokenizer
     from ..utils.data_loader import load_dataset, split_dataset
 
+    if a.DATA.is_dir():  # the older generations pass the data-set folder: its only .txt file is the corpus
+        txt = sorted(a.DATA.glob("*.txt"))
+        if not txt:
+            raise FileNotFoundError(f"no .txt file in {a.DATA}")
+        a.DATA = txt[0]
     out = a.out_dir or a.DATA.parent
     out.mkdir(parents=True, exist_ok=True)
     spec = a.tokenizer
-    if spec == "char":
+    if spec.lower() == "gpt2" and not Path(spec).is_dir():
+        raise SystemExit("'-t gpt2' needs the GPT-2 tokenizer files: pass the directory that holds them (tokenizer.json / vocab)")
+    if spec.lower() in ("char", "character"):
         t = CharacterTokenizer()
         t.tokenize(a.DATA.read_text(encoding="utf-8"))
         t.save(out)
         tok = Tokenizer(out, force_backend="char")
     elif spec.startswith("bpe"):
-        vocab = int(spec.split(":")[1]) if ":" in spec else 500
+        vocab = int(spec.split(":")[1]) if ":" in spec else a.vocab_size
         t = BPETokenizer()
         t.tokenize(a.DATA.read_text(encoding="utf-8"), vocab)
         t.store_tokenizer_info(out, overwrite=True)

@@ -144,3 +144,21 @@ def test_inspect_lit_reference_form(tmp_path, tiny_llama_cfg, capsys, monkeypatc
     write_bytes_tokenizer(ck)
     assert tok_cli.main([str(ck)]) == 0
     assert "Beginning of sentence: 256" in capsys.readouterr().out
+
+
+def test_prepare_data_legacy_forms(tmp_path):
+    """`prepare_data.py DATA_DIR -t character` / `-t bpe --vocab-size N` of the older generations (old/GPT2/prepare_data.py:22-47)."""
+    import numpy as np
+
+    from mdi_llm_b200.cli import prepare_data
+
+    d = tmp_path / "shakespeare"
+    d.mkdir()
+    (d / "input.txt").write_text("To be, or not to be, that is the question. " * 40)
+    assert prepare_data.main([str(d), "-t", "character"]) == 0
+    n_char = np.fromfile(d / "train.bin", dtype=np.uint16).size + np.fromfile(d / "val.bin", dtype=np.uint16).size
+    assert n_char == len("To be, or not to be, that is the question. " * 40)
+    out = tmp_path / "bpe"
+    assert prepare_data.main([str(d), "-t", "bpe", "--vocab-size", "270", "--out-dir", str(out)]) == 0
+    n_bpe = np.fromfile(out / "train.bin", dtype=np.uint16).size + np.fromfile(out / "val.bin", dtype=np.uint16).size
+    assert 0 < n_bpe < n_char  # merges shorten the sequence
