@@ -30,7 +30,7 @@ def main(argv=None) -> int:
                    help="checkpoint directory of the model (the reference's positional form: its name selects the CSVs)")
     p.add_argument("--model", default=None, help="model name, instead of MODEL_DIR")
     p.add_argument("-nt", "--no-title", action="store_true", help="if set, don't print the figure title")
-    p.add_argument("--n-samples", type=int, default=3)
+    p.add_argument("-n", "--n-samples", type=int, default=3)
     p.add_argument("--max-nodes", type=int, default=8)
     p.add_argument("--logs-dir", type=Path, default=LOGS_DIR)
     p.add_argument("-o", "--out", type=Path, default=None)
