@@ -569,7 +569,7 @@ class FusedStage:
                 pf.update(self._variant("o_proj"))
                 if self.pf_self_chunks:
                     pf["l2_pf_chunks"] = self.pf_self_chunks
-                if self.pf_next_mb > 0 and getattr(blk, "has_gu", False) and not plain_mlp:
+                if self.pf_next_mb > 0 and getattr(blk, "has_gu", False) and not plain_mlp and not self.moe:
                     w1, w2 = self._w(blk.mlp.fc_1)["W"], self._w(blk.mlp.fc_2)["W"]
                     nbytes = min(int(self.pf_next_mb * 2 ** 20) // 2, w1.numel() * w1.element_size()) & ~4095
                     pf["prefetch"] = (w1.data_ptr(), w2.data_ptr(), nbytes)
