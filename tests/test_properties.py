@@ -187,3 +187,51 @@ def test_frame_header_is_the_reference_format(idx, stop, n):
     assert int(header.decode("ascii")) == len(body)
     back = safe_loads(body)
     assert back["sample_index"] == idx and back["stop"] == stop and torch.equal(back["data"], msg["data"])
+
+
+@FAST
+@given(vals=st.lists(st.integers(-128, 128), min_size=2, max_size=40, unique=True).map(lambda v: [x / 16 for x in v]),
+       k=st.integers(1, 40), top_p=st.floats(0.05, 1.0),
+       temp=st.floats(0.1, 2.0), seed=st.integers(0, 1000))
+def test_sampler_only_draws_from_the_allowed_set(vals, k, top_p, temp, seed):
+    """top-k then nucleus (model.py:42-90): the drawn token is always among the k largest logits AND inside the smallest
+    prefix of them whose probability mass reaches top_p; temperature 0 with top_p 0 is the arg-max."""
+    from mdi_llm_b200.models.gpt import sample
+
+    logits = torch.tensor(vals, dtype=torch.float32).view(1, 1, -1)
+    g = torch.Generator().manual_seed(seed)
+    tok = int(sample(logits, temperature=temp, top_k=k, top_p=top_p, generator=g))
+    order = sorted(range(len(vals)), key=lambda i: -vals[i])
+    kept = order[: min(k, len(vals))]
+    assert tok in kept
+    probs = torch.tensor([vals[i] for i in kept]).div(temp).softmax(-1)
+    mass_before = float(probs[: kept.index(tok)].sum())  # mass of the strictly more likely kept tokens
+    assert mass_before < top_p + 1e-4
+    assert int(sample(logits, temperature=0.0, top_k=k, top_p=0.0)) == order[0]
+
+
+@FAST
+@given(text=st.text(alphabet=st.characters(blacklist_categories=("Cs",)), max_size=60))
+def test_byte_tokenizer_roundtrips_any_text(tmp_path_factory, text):
+    from mdi_llm_b200.text.tokenizer import Tokenizer, write_bytes_tokenizer
+
+    d = tmp_path_factory.mktemp("tok")
+    write_bytes_tokenizer(d)
+    tok = Tokenizer(d, force_backend="bytes")
+    ids = tok.encode(text, bos=False)
+    assert tok.decode(ids) == text and int(ids.max() if ids.numel() else 0) < tok.vocab_size
+
+
+@settings(max_examples=25, deadline=None)
+@given(corpus=st.text(alphabet="abcdefgh ,.\n", min_size=20, max_size=200), probe=st.text(alphabet="abcdefgh ,.\n", max_size=40),
+       merges=st.integers(0, 30))
+def test_trained_bpe_and_char_tokenizers_roundtrip(corpus, probe, merges):
+    from mdi_llm_b200.text.simple_tokenizers import BPETokenizer, CharacterTokenizer
+
+    bpe = BPETokenizer()
+    bpe.tokenize(corpus, out_vocab_size=256 + merges)
+    assert bpe.decode(bpe.encode(probe)) == probe
+    assert len(bpe.encode(corpus)) <= len(corpus.encode("utf-8"))
+    ch = CharacterTokenizer()
+    ch.tokenize(corpus + probe)
+    assert ch.decode(ch.encode(probe)) == probe
