@@ -15,7 +15,8 @@ from mdi_llm_b200.parallel.transport.socket_transport import encode_frame
 from mdi_llm_b200.utils.checkpoint import random_state_dict
 from mdi_llm_b200.utils.safe_pickle import UnsafePayload, safe_loads
 
-FAST = settings(max_examples=60, deadline=None, suppress_health_check=[HealthCheck.too_slow])
+FAST = settings(max_examples=60, deadline=None, derandomize=True, database=None,
+                suppress_health_check=[HealthCheck.too_slow, HealthCheck.function_scoped_fixture])  # same examples on every run
 
 
 def _brute_force(costs, n, head, fixed):
@@ -222,7 +223,7 @@ def test_byte_tokenizer_roundtrips_any_text(tmp_path_factory, text):
     assert tok.decode(ids) == text and int(ids.max() if ids.numel() else 0) < tok.vocab_size
 
 
-@settings(max_examples=25, deadline=None)
+@settings(max_examples=25, deadline=None, derandomize=True, database=None)
 @given(corpus=st.text(alphabet="abcdefgh ,.\n", min_size=20, max_size=200), probe=st.text(alphabet="abcdefgh ,.\n", max_size=40),
        merges=st.integers(0, 30))
 def test_trained_bpe_and_char_tokenizers_roundtrip(corpus, probe, merges):
