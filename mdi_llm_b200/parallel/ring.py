@@ -182,8 +182,9 @@ class RingSession:
         self.backend.prepare(self.prompt_lens, self.max_new, prompts=pinned)  # H2D of the prompts from pinned memory
         self._join(futs)
 
-    def _post(self, url: str, msg: Dict[str, Any]) -> Dict[str, Any]:
-        status, body = call_node("post", url, msg, max_n_requests=1, timeout=self.timeout)  # ring ops are not idempotent: never re-post
+    def _post(self, url: str, msg: Dict[str, Any], timeout: Optional[float] = None) -> Dict[str, Any]:
+        status, body = call_node("post", url, msg, max_n_requests=1,  # ring ops are not idempotent: never re-post
+                                 timeout=self.timeout if timeout is None else timeout)
         if status != 200 or not isinstance(body, dict):
             raise RingError(f"node {url} answered {status}: {body}")
         return body
@@ -224,12 +225,17 @@ class RingSession:
                 "decode_ms": max(r["decode_ms"] for r in per_node), "prefill_ms": max(r["prefill_ms"] for r in per_node)}
 
     def abort(self) -> None:
+        """Poison every node's incoming flags.  Meant to be called from another thread while :meth:`run` is blocked, so
+        the posts go out on their OWN threads: the session's pool is busy with the very `run` requests to be aborted."""
         self.backend.abort()
-        for f in self._fan({"op": "abort"}):
-            try:
-                f.result()
-            except Exception:  # noqa: BLE001  (a dead node cannot be told)
-                pass
+        if not self.urls:
+            return
+        with ThreadPoolExecutor(max_workers=len(self.urls)) as urgent:
+            for f in [urgent.submit(self._post, u, {"op": "abort"}, 5.0) for u in self.urls]:  # a frozen node must not hold up the others
+                try:
+                    f.result()
+                except Exception:  # noqa: BLE001  (a dead node cannot be told)
+                    pass
 
     def tokens(self) -> Dict[int, torch.Tensor]:
         return self.backend.tokens()

@@ -8,6 +8,7 @@ import pickle
 import subprocess
 import sys
 import threading
+import time
 
 import pytest
 import torch
@@ -201,3 +202,42 @@ def test_one_box_launcher_cpu(tmp_path, tiny_llama_cfg):
     assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-3000:]
     assert p.stdout.count("Sample 3:") == 2 and "=== run 2/2" in p.stdout
     assert len(stats.read_text().strip().splitlines()) == 3  # header + one row per run
+
+
+def test_abort_is_served_while_a_run_is_in_flight():
+    """The abort path depends on the control server answering `POST /ring abort` while the same node's `run` request
+    is still blocked on its GPU: a node whose run only returns once it has been aborted must not dead-lock the session."""
+    import threading
+
+    from mdi_llm_b200.parallel.ring import RingError, RingSession
+
+    log = []
+    (port,) = free_ports(1)
+    released = threading.Event()
+
+    class Blocking(_FakeBackend):
+        def run(self, prefill, rounds, start_at=None, mode="device", on_token=None):
+            ok = released.wait(timeout=20)  # "spinning on a flag that never comes"
+            out = super().run(prefill, rounds, start_at, mode, on_token)
+            out["status"] = [0, 1] if ok else [1, 1]
+            return out
+
+        def abort(self):
+            super().abort()
+            released.set()
+
+    remote = Blocking(1, log)
+    server = ControlServer(_Node(remote), "127.0.0.1", port)
+    server.start()
+    try:
+        local = _FakeBackend(0, log)
+        sess = RingSession(local, [{"addr": "127.0.0.1", "communication": {"port": port}}], [torch.tensor([1, 2])], 4)
+        threading.Timer(0.3, sess.abort).start()
+        t0 = time.time()
+        with pytest.raises(RingError, match="aborted"):
+            sess.run(2)
+        assert time.time() - t0 < 10  # released by the abort, not by the 20 s stand-in for the watchdog
+        assert (1, "abort") in log and (0, "abort") in log
+        sess.close()
+    finally:
+        server.stop()
