@@ -490,6 +490,14 @@ class GPTServer:
                 tok_time += [(i + 1, t) for i, t in enumerate(self.ring.token_times())]
             self.last_ring_stats = stats
             samples = sess.tokens()
+        except BaseException:
+            # Ctrl-C, a node that answered with an error, a tripped watchdog: whatever is still queued on the GPUs of the
+            # ring must not spin out its own watchdog budget — poison every node's flags, then let the error surface
+            try:
+                sess.abort()
+            except Exception:  # noqa: BLE001
+                pass
+            raise
         finally:
             sess.close()
         lens = {i: n for i, n in enumerate(sess.prompt_lens)}
