@@ -241,3 +241,32 @@ def test_abort_is_served_while_a_run_is_in_flight():
         sess.close()
     finally:
         server.stop()
+
+
+def test_failed_ring_generation_poisons_before_raising():
+    """`GPTServer._starter_ring`: whatever makes the generation fail (here: a node reporting an abort), the session is
+    told to abort — so nothing keeps spinning on the other GPUs — and closed, and the error still reaches the caller."""
+    import types
+
+    from mdi_llm_b200.parallel.ring import RingError
+    from mdi_llm_b200.parallel.server import GPTServer
+
+    calls = []
+
+    class Sess:
+        mode, prompt_lens, t0_host = "device", [2], 0.0
+
+        def run(self, on_token=None):
+            calls.append("run")
+            raise RingError("pipeline aborted: node 1")
+
+        def abort(self):
+            calls.append("abort")
+
+        def close(self):
+            calls.append("close")
+
+    fake = types.SimpleNamespace(open_ring_session=lambda n, p, m: Sess(), on_token=None, ring=None)
+    with pytest.raises(RingError, match="node 1"):
+        GPTServer._starter_ring(fake, 1, "x", 4)
+    assert calls == ["run", "abort", "close"]
