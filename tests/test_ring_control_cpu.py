@@ -270,3 +270,34 @@ def test_failed_ring_generation_poisons_before_raising():
     with pytest.raises(RingError, match="node 1"):
         GPTServer._starter_ring(fake, 1, "x", 4)
     assert calls == ["run", "abort", "close"]
+
+
+def test_ring_generation_success_path_collects_tokens_and_timeline():
+    import types
+
+    from mdi_llm_b200.parallel.server import GPTServer
+
+    calls = []
+
+    class Sess:
+        mode, prompt_lens, t0_host = "device", [2, 2], 0.0
+
+        def run(self, on_token=None):
+            calls.append("run")
+            return {"rounds": 3, "tokens": 6, "decode_ms": 1.0, "prefill_ms": 0.5, "per_node": []}
+
+        def tokens(self):
+            return {0: torch.tensor([[5, 6, 7, 8, 9]]), 1: torch.tensor([[5, 6, 1, 2, 3]])}
+
+        def abort(self):
+            calls.append("abort")
+
+        def close(self):
+            calls.append("close")
+
+    fake = types.SimpleNamespace(open_ring_session=lambda n, p, m: Sess(), on_token=None,
+                                 ring=types.SimpleNamespace(token_times=lambda: [0.01 * i for i in range(1, 7)]),
+                                 stop_tokens=(), tok=types.SimpleNamespace(decode=lambda t: " ".join(str(int(x)) for x in t.reshape(-1))))
+    texts, tok_time = GPTServer._starter_ring(fake, 2, "x", 3)
+    assert calls == ["run", "close"] and texts == ["5 6 7 8 9", "5 6 1 2 3"]
+    assert tok_time[0] == (0, 0.0) and tok_time[-1] == (6, pytest.approx(0.06)) and fake.last_result.n_tokens == 6
