@@ -432,3 +432,35 @@ def test_moe_prompt_grouping_matches_the_eager_module():
     torch.testing.assert_close(got.float(), ref.float(), rtol=1e-4, atol=1e-4)
     # every expert that received tokens ran exactly once over exactly its rows
     assert got.shape == x.shape
+
+
+def test_device_pipeline_orchestration_with_routed_mlps():
+    """A mixture-of-experts stage through prepare -> prefill -> decode: the prompt takes the per-expert GEMM path, the
+    step graphs hold router + expert launches, and a 2-stage ring hands the prompt on with the copy + signal kernel."""
+    from mdi_llm_b200.parallel.pipeline import DevicePipeline
+    from mdi_llm_b200.parallel.scheduler import SamplingParams
+
+    cfg = Config.from_name("tiny-llama-1.1b", n_layer=2, n_embd=256, n_head=4, n_query_groups=2, intermediate_size=128, vocab_size=120,
+                           padded_vocab_size=128, block_size=64, mlp_class_name="LLaMAMoE", n_expert=4, n_expert_per_token=2)
+    prompts = [torch.tensor([1, 2, 3]), torch.tensor([4, 5, 6, 7])]
+    with dry_pipeline() as (calls, lib):
+        st = build_stage(cfg, "starter", 2).to(torch.bfloat16)
+        st.max_seq_length = 32
+        pipe = DevicePipeline(st, 0, 1, n_samples=2, max_seq_length=32, sampling=SamplingParams.greedy())
+        out = pipe.generate(prompts, 3, mode="device")
+        assert out[1].shape == (1, 4 + 3)
+        gated = [c[1] for c in calls if c[0] == "gemm" and c[1].get("w2") is not None]
+        assert len(gated) == 2 * 2 * 2  # 2 prompts x 2 layers x 2 experts (all-zero logits route to experts 0 and 1)
+        full = [g for g in _FakeGraph.instances if "moe_router" in g.kernels]
+        assert full and all(g.kernels.count("moe_linear_decode") == 4 * g.kernels.count("moe_router") for g in full)
+        assert sum(g.launched * g.kernels.count("embed") for g in full) == 2 * 2  # rounds 1..2 x 2 samples
+    with dry_pipeline() as (calls, lib):
+        st = build_stage(cfg, "starter", 1).to(torch.bfloat16)
+        st.max_seq_length = 32
+        p0 = DevicePipeline(st, 0, 2, n_samples=2, max_seq_length=32, sampling=SamplingParams.greedy(), exportable=False)
+        p0.next_hop, p0.next_prefill_ptr = HopTarget(0x10000, 0x20000), 0x30000
+        p0.prepare(prompts, 3)
+        p0.prefill()
+        assert lib.mdi_copy_signal.call_count == 2  # the routed MLP's output leaves through the copy + signal kernel
+        args = lib.mdi_copy_signal.call_args_list
+        assert args[0][0][1] == 0x30000 and args[0][0][3] == 0x20000
