@@ -460,6 +460,10 @@ class GPTServer:
         from .ring import RingSession
 
         assert self.ring is not None and self.model is not None
+        if n_samples < 1:  # the same checks as the socket path (gptserver.py:816-821)
+            raise ValueError("Cannot generate less than 1 sample!")
+        if self.n_nodes and n_samples < self.n_nodes:
+            warnings.warn(f"Generating less samples ({n_samples}) than nodes ({self.n_nodes}) will not be efficient!")
         self.ring.pipe.set_sampling(sampling or self.sampling)  # sampling lives on the starter only
         idx = self.encode_prompts(prompt, n_samples)
         S = self.model.max_seq_length

@@ -301,3 +301,22 @@ def test_ring_generation_success_path_collects_tokens_and_timeline():
     texts, tok_time = GPTServer._starter_ring(fake, 2, "x", 3)
     assert calls == ["run", "close"] and texts == ["5 6 7 8 9", "5 6 1 2 3"]
     assert tok_time[0] == (0, 0.0) and tok_time[-1] == (6, pytest.approx(0.06)) and fake.last_result.n_tokens == 6
+
+
+def test_ring_session_validates_the_sample_count():
+    """Same contract as the socket path (gptserver.py:816-821): fewer samples than nodes only warns, zero raises."""
+    import types
+    import warnings
+
+    from mdi_llm_b200.parallel.server import GPTServer
+
+    fake = types.SimpleNamespace(ring=object(), model=object(), n_nodes=3)
+    with pytest.raises(ValueError, match="less than 1 sample"):
+        GPTServer.open_ring_session(fake, 0, "x", 4)
+    fake.ring = types.SimpleNamespace(pipe=types.SimpleNamespace(set_sampling=lambda s: (_ for _ in ()).throw(StopIteration())))
+    fake.sampling = None
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        with pytest.raises(StopIteration):  # the fake stops right after the checks
+            GPTServer.open_ring_session(fake, 2, "x", 4)
+    assert any("will not be efficient" in str(x.message) for x in w)
