@@ -1,0 +1,92 @@
+"""The ctypes prototypes in ``mdi_llm_b200/ops/__init__.py`` against the ``extern "C"`` signatures in ``csrc/*.cu``:
+parameter count and kind of every entry point.  (A mismatch is silent memory corruption at run time: ctypes pushes what
+the prototype says, the kernel launcher reads what its C signature says.)  Runs on CPU — the library only has to load."""
+import ctypes
+import re
+from pathlib import Path
+
+import pytest
+
+CSRC = Path(__file__).resolve().parents[1] / "mdi_llm_b200" / "ops" / "csrc"
+
+
+def _c_signatures():
+    sigs = {}
+    for f in sorted(CSRC.glob("*.cu")):
+        src = re.sub(r"//[^\n]*", "", f.read_text())
+        src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+        # every top-level definition `<type> mdi_xxx(<params>) {` — the exported entry points all carry the prefix
+        for m in re.finditer(r'^(?:extern\s+"C"\s+)?(?:[A-Za-z_][\w \t\*]*?)\b(mdi_\w+)\s*\(([^{;]*?)\)\s*\{', src, flags=re.M | re.S):
+            name, params = m.group(1), m.group(2).strip()
+            sigs[name] = [] if params in ("", "void") else [" ".join(p.split()) for p in params.split(",")]
+    return sigs
+
+
+def _kind(c_param: str) -> str:
+    if "*" in c_param or re.search(r"\bcuda\w+_t\b", c_param):  # CUDA handle types (stream, graph exec, ...) are pointers
+        return "ptr"
+    t = c_param.rsplit(" ", 1)[0] if " " in c_param else c_param
+    t = t.replace("const ", "").strip()
+    return {"int": "i32", "unsigned int": "u32", "unsigned": "u32", "long long": "i64", "unsigned long long": "u64", "size_t": "u64",
+            "float": "f32", "double": "f64"}.get(t, f"?{t}")
+
+
+_CT = {ctypes.c_void_p: "ptr", ctypes.c_char_p: "ptr", ctypes.c_int: "i32", ctypes.c_uint: "u32", ctypes.c_longlong: "i64",
+       ctypes.c_int64: "i64", ctypes.c_ulonglong: "u64", ctypes.c_uint64: "u64", ctypes.c_size_t: "u64", ctypes.c_float: "f32",
+       ctypes.c_double: "f64"}
+
+
+def test_every_prototype_matches_its_c_signature():
+    from mdi_llm_b200 import ops
+
+    try:
+        lib = ops.lib()
+    except Exception as e:  # noqa: BLE001
+        pytest.skip(f"kernel library not loadable here: {e}")
+    sigs = _c_signatures()
+    assert len(sigs) > 40, sorted(sigs)
+    checked, problems = 0, []
+    for name, params in sorted(sigs.items()):
+        fn = getattr(lib, name)
+        proto = fn.argtypes
+        if proto is None:
+            if params:  # an entry point called without a declared prototype relies on ctypes' int default: only fine without arguments
+                problems.append(f"{name}: {len(params)} parameters but no argtypes declared")
+            continue
+        want = [_kind(p) for p in params]
+        got = []
+        for t in proto:
+            k = _CT.get(t)
+            if k is None and isinstance(t, type) and issubclass(t, ctypes._Pointer):
+                k = "ptr"
+            got.append(k or f"?{t}")
+        if len(want) != len(got):
+            problems.append(f"{name}: C has {len(want)} parameters, prototype has {len(got)}")
+        else:
+            bad = [(i, params[i], w, g) for i, (w, g) in enumerate(zip(want, got)) if w != g]
+            if bad:
+                problems.append(f"{name}: " + "; ".join(f"#{i} `{p}` is {w}, prototype says {g}" for i, p, w, g in bad))
+        checked += 1
+    assert not problems, "\n".join(problems)
+    assert checked > 35
+
+
+def test_the_check_notices_a_drifted_prototype():
+    from mdi_llm_b200 import ops
+
+    try:
+        lib = ops.lib()
+    except Exception as e:  # noqa: BLE001
+        pytest.skip(f"kernel library not loadable here: {e}")
+    saved = lib.mdi_qkv_decode.argtypes
+    try:
+        lib.mdi_qkv_decode.argtypes = list(saved)[:-1]  # "someone added a parameter on the C side only"
+        with pytest.raises(AssertionError, match="mdi_qkv_decode"):
+            test_every_prototype_matches_its_c_signature()
+        wrong = list(saved)
+        wrong[9] = ctypes.c_int  # x_slot_stride is a long long
+        lib.mdi_qkv_decode.argtypes = wrong
+        with pytest.raises(AssertionError, match="x_slot_stride"):
+            test_every_prototype_matches_its_c_signature()
+    finally:
+        lib.mdi_qkv_decode.argtypes = saved
