@@ -90,3 +90,20 @@ def test_the_check_notices_a_drifted_prototype():
             test_every_prototype_matches_its_c_signature()
     finally:
         lib.mdi_qkv_decode.argtypes = saved
+
+
+def test_constants_mirrored_in_python_match_the_headers():
+    """Step-descriptor layout, poison value and activation codes exist on both sides of the ctypes boundary."""
+    from mdi_llm_b200 import ops
+
+    h = (CSRC / "common.cuh").read_text()
+    defs = {m.group(1): int(m.group(2), 0) for m in re.finditer(r"^#define\s+(MDI_\w+)\s+(0x[0-9a-fA-F]+|\d+)\b", h, flags=re.M)}
+    for py, c in (("CTX_SLOT", "MDI_CTX_SLOT"), ("CTX_POS", "MDI_CTX_POS"), ("CTX_WAIT", "MDI_CTX_WAIT"), ("CTX_SIGNAL", "MDI_CTX_SIGNAL"),
+                  ("CTX_TOKEN", "MDI_CTX_TOKEN"), ("CTX_STEP", "MDI_CTX_STEP"), ("CTX_INTS", "MDI_CTX_INTS"), ("POISON", "MDI_POISON")):
+        assert getattr(ops, py) == defs[c], (py, c)
+    enum = re.search(r"enum Act \{([^}]*)\}", h).group(1)
+    codes = {k.strip()[4:].lower(): int(v) for k, v in (item.split("=") for item in enum.split(","))}
+    assert codes == ops.ACT
+    from mdi_llm_b200.parallel.protocol_model import POISON
+
+    assert POISON == ops.POISON
