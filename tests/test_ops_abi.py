@@ -107,3 +107,51 @@ def test_constants_mirrored_in_python_match_the_headers():
     from mdi_llm_b200.parallel.protocol_model import POISON
 
     assert POISON == ops.POISON
+
+
+# (entry point, C parameter) -> a token that must appear in the Python argument expression instead of the C name
+_ALIASES = {("mdi_set_prefill_attn_pipe", "on"): "mode", ("mdi_linear_decode", "pf_a"): "prefetch", ("mdi_linear_decode", "pf_b"): "prefetch",
+            ("mdi_linear_decode", "pf_bytes"): "prefetch", ("mdi_qkv_decode", "k"): "shape", ("mdi_embed", "c"): "shape",
+            ("mdi_rmsnorm_rows", "rows"): "numel", ("mdi_sample", "v"): "vocab", ("mdi_sample_fast", "v"): "vocab",
+            ("mdi_quantize_rows_fp8", "ld_s"): "m_pad", ("mdi_gemm_fp8", "ld_as"): "a_scale_t", ("mdi_gemm_fp8", "c"): "c_ptr",
+            ("mdi_attn_prefill", "q_scratch"): "q_s", ("mdi_attn_prefill", "max_seq"): "s", ("mdi_graph_end", "n_nodes"): "n"}
+
+
+def test_wrappers_pass_their_arguments_in_the_c_order():
+    """Prototypes only fix count and kind; two `long long` strides swapped at a call site would still corrupt silently.
+    Every positional argument of every `lib().mdi_*()` call in ops/__init__.py must mention its C parameter's name (or a
+    listed alias): an argument in the wrong position names the wrong parameter."""
+    import ast
+
+    sigs = _c_signatures()
+    src = (CSRC.parent / "__init__.py").read_text()
+
+    def tokens(node):
+        out = set()
+        for n in ast.walk(node):
+            if isinstance(n, ast.Name):
+                out.add(n.id.lower())
+            elif isinstance(n, ast.Attribute):
+                out.add(n.attr.lower())
+        return out
+
+    checked, problems = 0, []
+    for n in ast.walk(ast.parse(src)):
+        if not (isinstance(n, ast.Call) and isinstance(n.func, ast.Attribute) and n.func.attr in sigs):
+            continue
+        name, params = n.func.attr, sigs[n.func.attr]
+        if any(isinstance(a, ast.Starred) for a in n.args) or len(params) < 2:
+            continue  # a tuple of tuning knobs forwarded as a block / nothing to get out of order
+        if len(n.args) != len(params):
+            problems.append(f"{name}: call passes {len(n.args)} arguments, C takes {len(params)}")
+            continue
+        for a, p in zip(n.args, params):
+            pname = p.split()[-1].strip("*").lower()
+            flat = " ".join(sorted(tokens(a)))
+            want = _ALIASES.get((name, pname))
+            ok = (want in flat) if want else (pname in flat or any(len(x) > 1 and x in flat for x in pname.split("_")))
+            checked += 1
+            if not ok:
+                problems.append(f"{name}: parameter `{pname}` receives `{ast.unparse(a)[:60]}`")
+    assert not problems, "\n".join(problems)
+    assert checked > 250
