@@ -140,12 +140,18 @@ def test_wrappers_pass_their_arguments_in_the_c_order():
         if not (isinstance(n, ast.Call) and isinstance(n.func, ast.Attribute) and n.func.attr in sigs):
             continue
         name, params = n.func.attr, sigs[n.func.attr]
-        if any(isinstance(a, ast.Starred) for a in n.args) or len(params) < 2:
-            continue  # a tuple of tuning knobs forwarded as a block / nothing to get out of order
-        if len(n.args) != len(params):
+        if len(params) < 2:
+            continue  # nothing to get out of order
+        pairs = list(zip(n.args, params))
+        star = [i for i, a in enumerate(n.args) if isinstance(a, ast.Starred)]
+        if star:  # one tuple of tuning knobs forwarded as a block: what precedes it aligns from the front, the rest from the back
+            assert len(star) == 1
+            i, tail = star[0], len(n.args) - star[0] - 1
+            pairs = list(zip(n.args[:i], params[:i])) + list(zip(n.args[i + 1:], params[len(params) - tail:]))
+        elif len(n.args) != len(params):
             problems.append(f"{name}: call passes {len(n.args)} arguments, C takes {len(params)}")
             continue
-        for a, p in zip(n.args, params):
+        for a, p in pairs:
             pname = p.split()[-1].strip("*").lower()
             flat = " ".join(sorted(tokens(a)))
             want = _ALIASES.get((name, pname))
