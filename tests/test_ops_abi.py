@@ -161,3 +161,42 @@ def test_wrappers_pass_their_arguments_in_the_c_order():
                 problems.append(f"{name}: parameter `{pname}` receives `{ast.unparse(a)[:60]}`")
     assert not problems, "\n".join(problems)
     assert checked > 250
+
+
+def test_built_library_contains_the_blackwell_instructions():
+    """The shipped binary really is the sm_100a build: tcgen05 MMAs (UTCHMMA bf16, UTCQMMA fp8), TMEM loads (LDTM), TMA tensor
+    loads (UTMALDG) and bulk copies (UBLKCP), mbarrier ops (SYNCS), cluster barriers — and no legacy tensor-core path (HMMA)
+    in the GEMM / attention kernels."""
+    import shutil
+    import subprocess
+
+    from mdi_llm_b200.ops import build
+
+    tool = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not Path(tool).exists() or not build.LIB.exists():
+        pytest.skip("cuobjdump or the built library is not available here")
+    out = subprocess.run([tool, "-sass", str(build.LIB)], capture_output=True, text=True, timeout=300).stdout
+    assert "sm_100a" in out
+    per_fn, fn = {}, None
+    for line in out.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            fn = m.group(1)
+            per_fn[fn] = set()
+        elif fn:
+            m = re.search(r"^\s+/\*[0-9a-f]+\*/\s+(?:@!?U?P\d+\s+)?([A-Z][A-Z0-9_.]+)", line)
+            if m:
+                per_fn[fn].add(m.group(1).split(".")[0])
+
+    def ops_of(substr):
+        hit = [v for k, v in per_fn.items() if substr in k]
+        assert hit, substr
+        return set().union(*hit)
+
+    gemm, fp8, attn = ops_of("gemm_bf16_tcgen05"), ops_of("gemm_fp8_blockscaled"), ops_of("attn_prefill_tcgen05")
+    assert {"UTCHMMA", "LDTM", "UTMALDG", "UTCBAR", "SYNCS"} <= gemm
+    assert {"UTCQMMA", "LDTM", "UTMALDG", "SYNCS"} <= fp8
+    assert {"UTCHMMA", "LDTM", "UTMALDG"} <= attn
+    assert not ({"HMMA", "IMMA", "QMMA"} & (gemm | fp8 | attn))  # no mma.sync-class fallback
+    assert {"UBLKCP", "SYNCS"} <= ops_of("stream_bulk_kernel")   # decode weight streaming through the TMA engine
+    assert "UCGABAR_ARV" in ops_of("attn_decode_kernel") or "UCGABAR_WAIT" in ops_of("attn_decode_kernel")  # cluster barrier (DSMEM merge)
