@@ -200,3 +200,33 @@ def test_built_library_contains_the_blackwell_instructions():
     assert not ({"HMMA", "IMMA", "QMMA"} & (gemm | fp8 | attn))  # no mma.sync-class fallback
     assert {"UBLKCP", "SYNCS"} <= ops_of("stream_bulk_kernel")   # decode weight streaming through the TMA engine
     assert "UCGABAR_ARV" in ops_of("attn_decode_kernel") or "UCGABAR_WAIT" in ops_of("attn_decode_kernel")  # cluster barrier (DSMEM merge)
+
+
+def test_hot_kernels_fit_their_occupancy_budgets():
+    """Register / stack budgets the launch configurations rely on: the decode streamers run 3 CTAs of 256 threads per SM
+    (<= 85 registers, no stack), the flagship attention instantiation and the MoE passes do not spill."""
+    import shutil
+    import subprocess
+
+    from mdi_llm_b200.ops import build
+
+    tool = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not Path(tool).exists() or not build.LIB.exists():
+        pytest.skip("cuobjdump or the built library is not available here")
+    out = subprocess.run([tool, "-res-usage", str(build.LIB)], capture_output=True, text=True, timeout=300).stdout
+    usage = {m.group(1): {k: int(v) for k, v in re.findall(r"(REG|STACK|LOCAL):(\d+)", m.group(2))}
+             for m in re.finditer(r"Function (\S+):\s*\n\s*(REG:[^\n]*)", out)}
+    assert len(usage) > 60
+
+    def sel(substr):
+        hit = {k: v for k, v in usage.items() if substr in k}
+        assert hit, substr
+        return hit
+
+    for k, u in {**sel("stream_bulk_kernelILi0ELi2"), **sel("stream_bulk_kernelILi1ELi2"), **sel("stream_bulk_kernelILi2ELi2"),
+                 **sel("moe_stream_kernel"), **sel("moe_bulk_kernel")}.items():
+        assert u["REG"] * 256 * 3 <= 65536 and u["STACK"] == 0 and u["LOCAL"] == 0, (k, u)
+    for k, u in sel("attn_decode_kernelILi128ELi4").items():  # Llama-3 / Mistral: 4 query heads per KV head
+        assert u["STACK"] == 0 and u["LOCAL"] == 0, (k, u)
+    for k, u in {**sel("gemm_bf16_tcgen05"), **sel("gemm_fp8_blockscaled")}.items():
+        assert u["LOCAL"] == 0 and u["REG"] * 384 <= 65536, (k, u)  # one CTA per SM of up to 384 threads (fp8: 8 promotion warps)
