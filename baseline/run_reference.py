@@ -87,7 +87,7 @@ def _write_checkpoint(ckpt: Path, model_name: str, device: str) -> None:
 def _topology(n: int, base: int) -> Dict[str, Any]:
     def node(i: int) -> Dict[str, Any]:
         return {"addr": "127.0.0.1", "communication": {"port": base + i, "starter_addr": "127.0.0.1"},
-                "inference": {"port_in": base + 100 + 2 * i, "port_out": base + 101 + 2 * i}, "device": f"cuda:{i}"}
+                "inference": {"port_in": base + 8 + 2 * i, "port_out": base + 9 + 2 * i}, "device": f"cuda:{i}"}
 
     return {"nodes": {"starter": node(0), "secondary": [node(i) for i in range(1, n)]}}
 
@@ -181,8 +181,12 @@ def run_reference(args: Any, variant: str = "reference") -> Dict[str, Any]:
             done_mark.write_text("ok")
         if world > 1:
             dist.barrier()
-        # ports derived from the rendezvous port so that concurrent / stale runs never collide
-        topo = _topology(world, 20000 + (int(os.environ.get("MASTER_PORT", "29500")) % 2000) * 10)
+        # ports derived from the rendezvous port AND the node count, so that concurrent / stale runs never collide: the
+        # reference binds its data sockets without SO_REUSEADDR (connections.py:122,292), and a scaling sweep runs
+        # N = 1, 2, 4, 8 within TIME_WAIT of each other
+        # (a block of 24 ports per (rendezvous port, node count): 8 control + 16 data)
+        topo = _topology(world, 20000 + (int(os.environ.get("MASTER_PORT", "29500")) % 400) * 100
+                         + {1: 0, 2: 24, 4: 48, 8: 72}.get(world, 0))
         topo_file = ckpt.parent / f"nodes_{world}.json"
         if rank == 0:
             topo_file.write_text(json.dumps(topo))
