@@ -153,3 +153,12 @@ def test_partition_table_cli(capsys):
     assert table["2"]["32"] == {"N_LAYERS_START": 14, "N_LAYERS_SECONDARY": 18}
     assert partition_table.main(["--model", "Llama-3-8B"]) == 0
     assert "8 nodes: table=None balanced=[2, 5, 5, 4, 4, 4, 4, 4]" in capsys.readouterr().out
+    # what-if view: the fitted cost model's stage times and ring throughput per policy; measured on B200 through the API
+    # (profiles/README.md): 353 / 693 / 1339 / 2558-2649 tok/s at 1 / 2 / 4 / 8 nodes with third-layer units
+    assert partition_table.main(["--model", "Llama-3-8B", "--predict"]) == 0
+    rows = {(int(l.split()[0]), l.split()[2]): float(l.split("->")[1].split()[0]) for l in capsys.readouterr().out.splitlines() if "->" in l}
+    for n, measured in ((1, 353.0), (2, 693.0), (4, 1339.0), (8, 2603.0)):
+        pred = rows[(n, "third" if n > 1 else "table")]
+        assert abs(pred - measured) / measured < 0.04, (n, pred, measured)
+    assert rows[(8, "third")] > rows[(8, "half")] > rows[(8, "balanced")]  # finer units flatten the 8-stage ring
+    assert partition_table.main(["--model", "Mixtral-8x7B-v0.1", "--predict", "--max-nodes", "2"]) == 0  # non-gated / MoE cost path
