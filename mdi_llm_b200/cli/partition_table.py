@@ -34,9 +34,11 @@ def stage_times_us(cfg, specs):
 
 
 def predict(cfg, max_nodes: int) -> int:
+    from ..models.memory import B200_HBM_BYTES, plan_memory
     from ..models.partition import stage_specs
 
-    print(f"{cfg.name}: predicted decode step per stage and ring throughput (n_samples = n_nodes, ~0.5k context, bf16)")
+    print(f"{cfg.name}: predicted decode step per stage and ring throughput (n_samples = n_nodes, ~0.5k context, bf16);\n"
+          f"GB = the fullest stage's weights + KV slots for n_nodes samples x {min(cfg.block_size, 4096)} positions + hop buffers")
     one_gpu = 1e6 / stage_times_us(cfg, stage_specs(1, cfg, "balanced"))[0]
     for n in range(1, max_nodes + 1):
         for policy in ("table", "balanced", "half", "third"):
@@ -47,8 +49,10 @@ def predict(cfg, max_nodes: int) -> int:
             ts = stage_times_us(cfg, specs)
             layers = "/".join(f"{sp['layers']:g}" for sp in specs)
             rate = 1e6 / max(ts)  # a full ring emits one token per step of its slowest stage
+            gb = max(m["total"] for m in plan_memory(cfg, specs, n, min(cfg.block_size, 4096))) / 1e9
+            fits = "" if gb * 1e9 <= 0.94 * B200_HBM_BYTES else "  [does NOT fit 180 GB]"
             print(f"{n} nodes  {policy:<8} layers {layers:<40} stage us {'/'.join(f'{t:.0f}' for t in ts)}  "
-                  f"-> {rate:7.0f} tok/s ({rate / n / one_gpu:.2f} of n x 1 GPU)")
+                  f"-> {rate:7.0f} tok/s ({rate / n / one_gpu:.2f} of n x 1 GPU)  {gb:6.1f} GB{fits}")
             if n == 1:
                 break
     return 0

@@ -226,6 +226,7 @@ class GPTDistributed:
         self.transport = transport
         handles: List[Dict[str, Any]] = []
         if transport != "socket":  # device ring: the starter's hop buffers first (the last node stores into them)
+            self.warn_if_plan_does_not_fit(n_samples)
             handles.append(serv.ring_setup(n_samples, 0, self.n_nodes, transport))
         if not secondaries:
             if self.verb:
@@ -272,6 +273,27 @@ class GPTDistributed:
                     return 0
             serv.ring.connect(handles[1])
         return 1
+
+    def warn_if_plan_does_not_fit(self, n_samples: int, capacity: Optional[int] = None) -> List[str]:
+        """HBM budget of every stage of the plan (``models/memory.py``: weights + KV slots + hop buffers) against the
+        device's memory, BEFORE any node allocates: a stage that cannot fit is announced with its numbers instead of an
+        out-of-memory error half-way through a 100 GB chunk.  Advisory (a warning per stage), never fatal."""
+        try:
+            from ..models.memory import check_plan
+            from ..models.partition import stage_specs
+
+            assert self.model_config is not None
+            if capacity is None:
+                capacity = int(torch.cuda.get_device_properties(self.torch_device).total_memory)
+            specs = self.specs or stage_specs(self.n_nodes, self.model_config, self.partition_policy)
+            serv = self.gpt_serv
+            msgs = check_plan(self.model_config, specs, n_samples, int(self.model_seq_length or self.model_config.block_size),
+                              getattr(serv, "max_prompt_len", None) or None, getattr(serv, "weights", "bf16"), capacity=capacity)
+        except Exception:  # noqa: BLE001  (an estimate must never stop a run)
+            return []
+        for m in msgs:
+            warnings.warn(m)
+        return msgs
 
     def open_session(self, n_samples: int, tokens_per_sample: int,
                      prompt: Optional[Union[str, Sequence[torch.Tensor]]] = None, mode: Optional[str] = None) -> Any:
