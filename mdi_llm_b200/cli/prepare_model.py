@@ -28,6 +28,10 @@ def build_parser() -> argparse.ArgumentParser:
     p.add_argument("--head-on", default="starter", choices=["starter", "finisher"],
                    help="which node owns ln_f + lm_head ('finisher' = first-generation chain layout)")
     p.add_argument("--seed", type=int, default=1234)
+    p.add_argument("--fit-engine", action="store_true",
+                   help="re-parametrise a model whose head size / GQA width is outside the fused sm_100a engine (Phi-2: head size "
+                        "80, Falcon-7B: 71 query heads per KV head) into an exactly equivalent one inside it "
+                        "(utils/fit_engine.py); written to <checkpoint>-fused/, which is then split")
     return p
 
 
@@ -63,6 +67,26 @@ def main(argv=None) -> int:
                                        checkpoint_dir=args.ckpt_folder, model_name=args.model_name)
     cfg, sd = load_from_pt(model_path, args.device)
     print(f"Model {cfg.name}: {cfg.n_layer} layers, checkpoint at {model_path}")
+    if args.fit_engine:
+        import shutil
+
+        from ..utils.fit_engine import fit_engine
+
+        new_cfg, sd, notes = fit_engine(cfg, sd)
+        if notes:
+            fused = model_path.parent / (model_path.name + "-fused")
+            fused.mkdir(parents=True, exist_ok=True)
+            for f in model_path.iterdir():  # tokenizer, prompt style, generation config travel unchanged
+                if f.is_file() and f.name not in ("lit_model.pth", "model_config.yaml"):
+                    shutil.copy2(f, fused / f.name)
+            new_cfg.save(fused)
+            torch.save(sd, fused / "lit_model.pth")
+            for n in notes:
+                print(f"fit-engine: {n}")
+            print(f"fit-engine: equivalent checkpoint written to {fused}")
+            cfg, model_path = new_cfg, fused
+        else:
+            print("fit-engine: the architecture is already inside the fused engine, nothing to do")
     if args.n_nodes and args.n_nodes > 1:
         plan = plan_layers(args.n_nodes, cfg.n_layer, cfg, policy=args.partition)
         out = split_and_store(sd, args.n_nodes, model_path, plan=plan, config=cfg, verb=True, head_on=args.head_on)
