@@ -8,8 +8,9 @@ The decode kernels are instantiated for head sizes 64 / 128 / 256 and 1 / 2 / 4 
   ``proj``; the softmax scale ``1/sqrt(head_size)`` changes with the padded size, so the q rows (and bias) are scaled by
   ``sqrt(new / old)`` — RoPE is linear, the rotated dimensions stay the first ``rope_n_elem`` of the head, and
   ``rotary_percentage`` is re-expressed against the new size.
-* **wide GQA / MQA groups** (Falcon-7B: 71 query heads on one KV head).  ``expand_kv_groups`` gives every query head
-  its own copy of its group's k / v rows (``n_query_groups = n_head``): the same function with a larger KV cache.
+* **wide GQA / MQA groups** (Falcon-7B: 71 query heads on one KV head, Falcon-40B: 16, Gemma-2B: 8 at head size 256).
+  ``expand_kv_groups`` splits a group into narrower ones (the widest supported divisor: 16 -> 8, 71 -> 1), each with
+  its own copy of the group's k / v rows: the same function with a larger KV cache.
 
 Both are *exact* (same logits up to floating-point summation order): ``tests/test_fit_engine.py`` checks the
 transformed eager model against the original, prefill and cached decoding.  Costs: Phi-2's attention matrices and KV
@@ -66,21 +67,28 @@ def pad_head_size(config: Config, sd: Optional[Dict[str, torch.Tensor]], new_hea
     return new_cfg, out
 
 
-def expand_kv_groups(config: Config, sd: Optional[Dict[str, torch.Tensor]]) -> Tuple[Config, Optional[Dict[str, torch.Tensor]]]:
-    """One KV head per query head (``q_per_kv = 1``): group ``g``'s k / v rows are repeated for each of its query heads."""
+def expand_kv_groups(config: Config, sd: Optional[Dict[str, torch.Tensor]], q_per_kv: int = 1) -> Tuple[Config, Optional[Dict[str, torch.Tensor]]]:
+    """Split every KV group into groups of ``q_per_kv`` query heads (a divisor of the current width), each with its own
+    copy of the group's k / v rows.  ``q_per_kv = 1``: one KV head per query head."""
     hs, G, qpk, H, C = config.head_size, config.n_query_groups, config.q_per_kv, config.n_head, config.n_embd
-    new_cfg = dataclasses.replace(config, n_query_groups=H)
-    if sd is None or qpk == 1:
+    if qpk % q_per_kv:
+        raise ValueError(f"{q_per_kv} does not divide the {qpk} query heads of a KV group")
+    r = qpk // q_per_kv  # new groups per old group
+    new_cfg = dataclasses.replace(config, n_query_groups=G * r)
+    if sd is None or r == 1:
         return new_cfg, sd
     out = dict(sd)
+
+    def regroup(t: torch.Tensor, tail: Tuple[int, ...]) -> torch.Tensor:
+        t = t.view(G, qpk + 2, hs, *tail)
+        q = t[:, :qpk].reshape(G, r, q_per_kv, hs, *tail)
+        kv = t[:, qpk:].unsqueeze(1).expand(G, r, 2, hs, *tail)
+        return torch.cat((q, kv), dim=2).reshape(G * r * (q_per_kv + 2) * hs, *tail).contiguous()
+
     for b in _blocks(sd):
-        w = sd[f"{b}.attn.attn.weight"].view(G, qpk + 2, hs, C)
-        q, k, v = w[:, :qpk], w[:, qpk: qpk + 1].expand(G, qpk, hs, C), w[:, qpk + 1:].expand(G, qpk, hs, C)
-        out[f"{b}.attn.attn.weight"] = torch.stack((q, k, v), dim=2).reshape(3 * H * hs, C).contiguous()  # [G, qpk, 3, hs, C]
+        out[f"{b}.attn.attn.weight"] = regroup(sd[f"{b}.attn.attn.weight"], (C,))
         if f"{b}.attn.attn.bias" in sd:
-            bias = sd[f"{b}.attn.attn.bias"].view(G, qpk + 2, hs)
-            bq, bk, bv = bias[:, :qpk], bias[:, qpk: qpk + 1].expand(G, qpk, hs), bias[:, qpk + 1:].expand(G, qpk, hs)
-            out[f"{b}.attn.attn.bias"] = torch.stack((bq, bk, bv), dim=2).reshape(-1).contiguous()
+            out[f"{b}.attn.attn.bias"] = regroup(sd[f"{b}.attn.attn.bias"], ())
     return new_cfg, out
 
 
@@ -91,18 +99,23 @@ def fit_engine(config: Config, sd: Optional[Dict[str, torch.Tensor]] = None) -> 
 
     notes: List[str] = []
     cfg = config
-    if cfg.q_per_kv not in SUPPORTED_Q_PER_KV or (cfg.head_size > 128 and cfg.q_per_kv > 2):
-        notes.append(f"{cfg.q_per_kv} query heads per KV head -> one KV head per query head ({cfg.n_query_groups} -> {cfg.n_head} groups)")
-        cfg, sd = expand_kv_groups(cfg, sd)
-    if cfg.head_size not in SUPPORTED_HEAD_SIZES:
-        new = next((h for h in SUPPORTED_HEAD_SIZES if h >= cfg.head_size), None)
-        if new is None:
-            raise ValueError(f"head size {cfg.head_size} is larger than any kernel instantiation")
-        if new > 128 and cfg.q_per_kv > 2:
-            notes.append(f"head size {new} needs at most 2 query heads per KV head -> one KV head per query head")
-            cfg, sd = expand_kv_groups(cfg, sd)
-        notes.append(f"head size {cfg.head_size} -> {new} (zero-padded, q rows scaled by sqrt({new}/{cfg.head_size}))")
-        cfg, sd = pad_head_size(cfg, sd, new)
+
+    def narrow(limit: int) -> None:
+        nonlocal cfg, sd
+        target = next(q for q in (8, 4, 2, 1) if q <= limit and cfg.q_per_kv % q == 0)
+        notes.append(f"{cfg.q_per_kv} query heads per KV head -> {target} ({cfg.n_query_groups} -> "
+                     f"{cfg.n_query_groups * cfg.q_per_kv // target} KV groups, k / v rows repeated)")
+        cfg, sd = expand_kv_groups(cfg, sd, target)
+
+    new_hs = cfg.head_size if cfg.head_size in SUPPORTED_HEAD_SIZES else next((h for h in SUPPORTED_HEAD_SIZES if h >= cfg.head_size), None)
+    if new_hs is None:
+        raise ValueError(f"head size {cfg.head_size} is larger than any kernel instantiation")
+    limit = 2 if new_hs > 128 else 8  # the head-size-256 attention kernel serves at most 2 query heads per KV head
+    if cfg.q_per_kv not in SUPPORTED_Q_PER_KV or cfg.q_per_kv > limit:
+        narrow(limit)
+    if new_hs != cfg.head_size:
+        notes.append(f"head size {cfg.head_size} -> {new_hs} (zero-padded, q rows scaled by sqrt({new_hs}/{cfg.head_size}))")
+        cfg, sd = pad_head_size(cfg, sd, new_hs)
     if not engine_supports(cfg, torch.bfloat16):
         raise ValueError(f"{config.name}: outside the fused engine for a reason no re-parametrisation removes "
                          f"(norm {cfg.norm_class_name}, mlp {cfg.mlp_class_name}, positions {cfg.pos_embedding})")

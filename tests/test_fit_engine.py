@@ -43,11 +43,18 @@ def _run(m, idx, steps=4):
     return full, torch.stack(outs), toks
 
 
-@pytest.mark.parametrize("base,how", [(PHI, "pad"), (FALCON, "expand"), (LLAMA_ODD, "pad"), (LLAMA_ODD, "both")])
+WIDE = dict(n_layer=2, n_embd=96, n_head=12, n_query_groups=2, head_size=8, bias=True, vocab_size=100, padded_vocab_size=128, block_size=32,
+            intermediate_size=96)  # 6 query heads per KV head -> groups of 2 (Falcon-40B: 16 -> 8)
+
+
+@pytest.mark.parametrize("base,how", [(PHI, "pad"), (FALCON, "expand"), (LLAMA_ODD, "pad"), (LLAMA_ODD, "both"), (WIDE, "narrow2")])
 def test_reparametrised_model_is_the_same_function(base, how):
     cfg = Config.from_name("tiny-llama-1.1b", **base)
     sd = random_state_dict(cfg, dtype=torch.float32, seed=3, std=0.2)
     cfg2, sd2 = cfg, dict(sd)
+    if how == "narrow2":
+        cfg2, sd2 = expand_kv_groups(cfg2, sd2, 2)
+        assert cfg2.q_per_kv == 2 and cfg2.n_query_groups == 6
     if how in ("expand", "both"):
         cfg2, sd2 = expand_kv_groups(cfg2, sd2)
         assert cfg2.q_per_kv == 1 and cfg2.n_query_groups == cfg.n_head
@@ -63,6 +70,25 @@ def test_reparametrised_model_is_the_same_function(base, how):
     # only the attention tensors changed
     changed = {k for k in sd if sd2[k].shape != sd[k].shape}
     assert changed and all(".attn." in k for k in changed)
+
+
+def test_every_registry_model_is_inside_the_engine_natively_or_after_fitting():
+    """The whole registry (the reference's 112 configurations + ours): 92 run on the fused engine as they are, the
+    rest after an exact re-parametrisation — none is left to the eager fallback for its attention geometry."""
+    from mdi_llm_b200.models import registry
+
+    native, fitted = 0, {}
+    for name in [c["name"] for c in registry.configs]:
+        cfg = Config.from_name(name)
+        if engine_supports(cfg, torch.bfloat16):
+            native += 1
+            continue
+        new, _, notes = fit_engine(cfg)
+        assert engine_supports(new, torch.bfloat16) and notes and new.n_head == cfg.n_head and new.rope_n_elem == cfg.rope_n_elem
+        fitted[name] = (new.n_query_groups, new.q_per_kv, new.head_size)
+    assert native >= 90 and len(fitted) >= 20
+    assert fitted["falcon-40b"] == (16, 8, 64) and fitted["Gemma-2b"] == (4, 2, 256) and fitted["falcon-180B"] == (232, 1, 64)
+    assert fitted["open_llama_3b"][2] == 128 and fitted["pythia-14m"][2] == 64
 
 
 def test_registry_models_land_inside_the_engine():
