@@ -270,10 +270,25 @@ class GPTServer:
                                             sampling=self.sampling)
                 if kind == "cuda":
                     raise RuntimeError(f"CUDA engine does not support config {model.config.name}")
+                self._hint_fit_engine(model.config)
             except ImportError:
                 if kind == "cuda":
                     raise
         return EagerStageRunner(model, n_slots_hint=max(1, int(n_samples or 1)))
+
+    @staticmethod
+    def _hint_fit_engine(config: Config) -> None:
+        """The model runs on the eager fallback although an exact re-parametrisation would put it on the fused kernels."""
+        try:
+            from ..utils.fit_engine import fit_engine
+
+            _, _, notes = fit_engine(config)
+        except Exception:  # noqa: BLE001  (outside the engine for another reason: nothing to suggest)
+            return
+        if notes:
+            warnings.warn(f"{config.name} runs on the eager PyTorch fallback ({'; '.join(notes)} would be needed): "
+                          "`python -m mdi_llm_b200.cli.prepare_model <checkpoint> --fit-engine` writes an exactly equivalent "
+                          "checkpoint that the fused sm_100a engine covers")
 
     # ---- device ring (transport p2p / nccl) --------------------------------------------------------------
     def resolve_transport(self) -> str:

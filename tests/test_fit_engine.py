@@ -154,3 +154,15 @@ def test_fitted_registry_shapes_bind_on_the_fused_engine(name):
     assert attn["head_size"] == full.head_size and attn["n_groups"] == full.n_query_groups and attn["n_split"] >= 1
     head = [c[1] for c in calls[:n0] if c[0] == "linear_decode"][0]
     assert (head.get("bias") is not None) == cfg.lm_head_bias
+
+
+def test_server_suggests_fitting_when_it_falls_back_to_eager():
+    import warnings
+
+    from mdi_llm_b200.parallel.server import GPTServer
+
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        GPTServer._hint_fit_engine(Config.from_name("phi-2"))
+        GPTServer._hint_fit_engine(Config.from_name("Llama-3-8B"))  # inside the engine: nothing to say
+    assert len(w) == 1 and "--fit-engine" in str(w[0].message) and "head size 80 -> 128" in str(w[0].message)
