@@ -1,0 +1,67 @@
+"""Numerical parity with the reference's OWN model code: the same state dict in ``sub.model.GPT`` (the unmodified
+reference tree, run in a subprocess) and in ``mdi_llm_b200.models.gpt.GPT`` gives the same logits — teacher-forced and
+through the KV cache — for every block style of the registry (Llama, Gemma, GPT-NeoX / Pythia, Falcon, Phi, Mixtral)."""
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+import pytest
+import torch
+
+from mdi_llm_b200.models.config import Config
+from mdi_llm_b200.models.gpt import GPT
+from mdi_llm_b200.utils.checkpoint import random_state_dict
+
+ROOT = Path(__file__).resolve().parents[1]
+REF = next((p for p in (ROOT / "baseline" / "_ref", Path("/root/reference/src")) if (p / "sub" / "model.py").is_file()), None)
+pytestmark = pytest.mark.skipif(REF is None, reason="reference tree not available")
+
+BASE = dict(n_layer=2, n_embd=64, n_head=4, n_query_groups=2, intermediate_size=96, vocab_size=100, padded_vocab_size=128, block_size=32)
+VARIANTS = {
+    "llama_gqa": dict(),
+    "gemma": dict(mlp_class_name="GemmaMLP", gelu_approximate="tanh", scale_embeddings=True, norm_class_name="RMSNorm", rotary_percentage=1.0),
+    "pythia": dict(norm_class_name="LayerNorm", parallel_residual=True, shared_attention_norm=False, mlp_class_name="GptNeoxMLP", bias=True,
+                   rotary_percentage=0.25, n_query_groups=4),
+    "falcon": dict(norm_class_name="LayerNorm", parallel_residual=True, shared_attention_norm=True, mlp_class_name="GptNeoxMLP", bias=False,
+                   n_query_groups=1),
+    "phi": dict(norm_class_name="LayerNorm", parallel_residual=True, shared_attention_norm=True, mlp_class_name="GptNeoxMLP", bias=True,
+                lm_head_bias=True, gelu_approximate="tanh", rotary_percentage=0.5, n_query_groups=4),
+    "mixtral": dict(mlp_class_name="LLaMAMoE", n_expert=4, n_expert_per_token=2),
+}
+
+
+@pytest.mark.parametrize("variant", sorted(VARIANTS))
+def test_same_logits_as_the_reference_model(tmp_path, variant):
+    kw = {**BASE, **VARIANTS[variant]}
+    cfg = Config.from_name("tiny-llama-1.1b", **kw)
+    sd = random_state_dict(cfg, dtype=torch.float32, seed=11, std=0.2)
+    # the reference's Config takes the same litGPT field names
+    ref_kw = {k: v for k, v in cfg.asdict().items() if k not in ("pos_embedding", "tie_embeddings")}
+    torch.save(ref_kw, tmp_path / "cfg.pt")
+    torch.save(sd, tmp_path / "sd.pt")
+    out = tmp_path / "ref.pt"
+    env = dict(os.environ, PYTHONPATH="")
+    r = subprocess.run([sys.executable, str(ROOT / "tests" / "helpers" / "ref_logits.py"), str(REF), str(ROOT / "baseline" / "shims"),
+                        str(tmp_path / "cfg.pt"), str(tmp_path / "sd.pt"), str(out)], capture_output=True, text=True, timeout=300,
+                       cwd=tmp_path, env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    ref = torch.load(out)
+    m = GPT(cfg)
+    m.load_state_dict(sd)
+    m.eval()
+    idx = torch.tensor([[5, 17, 3, 88, 42, 7]])
+    with torch.no_grad():
+        full = m(idx)
+        m.max_seq_length = 32
+        m.set_kv_cache(batch_size=1)
+        logits = m(idx, torch.arange(idx.size(1)))
+        outs, toks = [logits[:, -1]], []
+        for i in range(4):
+            t = logits[:, -1].argmax(-1, keepdim=True)
+            toks.append(int(t))
+            logits = m(t, torch.tensor([idx.size(1) + i]))
+            outs.append(logits[:, -1])
+    torch.testing.assert_close(full, ref["full"], rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(torch.stack(outs), ref["dec"], rtol=1e-4, atol=1e-5)
+    assert toks == ref["toks"]
