@@ -65,3 +65,26 @@ def test_same_logits_as_the_reference_model(tmp_path, variant):
     torch.testing.assert_close(full, ref["full"], rtol=1e-4, atol=1e-5)
     torch.testing.assert_close(torch.stack(outs), ref["dec"], rtol=1e-4, atol=1e-5)
     assert toks == ref["toks"]
+
+
+def test_prompt_styles_and_their_dispatch_match_the_reference(tmp_path):
+    """Every prompt style renders the same text as the reference's class of that name, and the regex dispatch picks the
+    same style for every model name of the registry (prompts.py:36-366)."""
+    import json
+
+    from mdi_llm_b200.text.prompts import PromptStyle, model_name_to_prompt_style
+
+    out = tmp_path / "prompts.json"
+    r = subprocess.run([sys.executable, str(ROOT / "tests" / "helpers" / "ref_prompts.py"), str(REF), str(ROOT / "baseline" / "shims"), str(out)],
+                       capture_output=True, text=True, timeout=300, cwd=tmp_path, env=dict(os.environ, PYTHONPATH=""))
+    assert r.returncode == 0, r.stderr[-2000:]
+    ref = json.loads(out.read_text())
+    prompts = ["Hello, how are you?", "Write a haiku about GPUs.\nMake it rhyme."]
+    assert len(ref["applied"]) >= 20
+    for name, theirs in ref["applied"].items():
+        style = PromptStyle.from_name(name)
+        if isinstance(theirs, str):  # the reference itself fails on this style with a bare prompt
+            continue
+        assert [style.apply(p) for p in prompts] == theirs, name
+    for model_name, cls in ref["picked"].items():
+        assert type(model_name_to_prompt_style(model_name)).__name__ == cls, model_name
