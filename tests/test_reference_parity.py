@@ -130,3 +130,30 @@ def test_weight_converters_agree_with_the_reference_both_ways(tmp_path, family):
         assert family == "phi" and "defaultdict" in ref["hf_to_lit_error"]
     else:
         assert ref["lit"].keys() == lit.keys() and all(torch.equal(ref["lit"][k], lit[k]) for k in lit)
+
+
+@pytest.mark.parametrize("n_layer,n_nodes", [(5, 2), (7, 3), (12, 3), (22, 4), (32, 5)])
+def test_table_split_produces_the_reference_chunks(tmp_path, n_layer, n_nodes):
+    """`--partition table`: the chunk dictionaries (which tensors, renumbered how) equal the reference's
+    ``split_parameters`` for topologies its table covers — chunk files are interchangeable (utils.py:241-340)."""
+    from mdi_llm_b200.models.partition import plan_layers, split_parameters
+
+    cfg = Config.from_name("tiny-llama-1.1b", n_layer=n_layer, n_embd=16, n_head=2, n_query_groups=1, intermediate_size=24, vocab_size=50,
+                           padded_vocab_size=64, block_size=16)
+    sd = random_state_dict(cfg, dtype=torch.float32, seed=9, std=0.1)
+    torch.save(sd, tmp_path / "sd.pt")
+    out = tmp_path / "split.pt"
+    r = subprocess.run([sys.executable, str(ROOT / "tests" / "helpers" / "ref_split.py"), str(REF), str(ROOT / "baseline" / "shims"),
+                        str(tmp_path / "sd.pt"), str(n_nodes), str(out)], capture_output=True, text=True, timeout=300, cwd=tmp_path,
+                       env=dict(os.environ, PYTHONPATH=""))
+    assert r.returncode == 0, r.stderr[-2000:]
+    ref = torch.load(out)
+    plan = plan_layers(n_nodes, n_layer, cfg, policy="table")
+    chunks, info = split_parameters({k: v.clone() for k, v in sd.items()}, n_nodes, plan=plan)
+    assert info["N_LAYERS_START"] == ref["info"]["N_LAYERS_START"] and info["N_LAYERS_SECONDARY"] == ref["info"]["N_LAYERS_SECONDARY"]
+    theirs = [ref["chunks"]["starter"]] + list(ref["chunks"]["secondary"])
+    ours = [chunks["starter"]] + list(chunks["secondary"])
+    assert len(ours) == len(theirs) == n_nodes
+    for i, (a, b) in enumerate(zip(ours, theirs)):
+        assert a.keys() == b.keys(), (i, sorted(set(a) ^ set(b))[:6])
+        assert all(torch.equal(a[k], b[k]) for k in a), i
