@@ -157,3 +157,39 @@ def test_table_split_produces_the_reference_chunks(tmp_path, n_layer, n_nodes):
     for i, (a, b) in enumerate(zip(ours, theirs)):
         assert a.keys() == b.keys(), (i, sorted(set(a) ^ set(b))[:6])
         assert all(torch.equal(a[k], b[k]) for k in a), i
+
+
+@pytest.mark.parametrize("variant,n_nodes", [("llama_gqa", 3), ("pythia", 2), ("mixtral", 2)])
+def test_our_chunks_run_in_the_reference_stage_classes(tmp_path, variant, n_nodes):
+    """Chunks written by our splitter, loaded by the reference's ``StarterNode`` / ``SecondaryNode``: every hop's hidden
+    state and the final logits equal those of our stage modules on the same chunks (submodels.py:132-300)."""
+    from mdi_llm_b200.models.partition import plan_layers, split_parameters
+    from mdi_llm_b200.models.stage import build_stage
+
+    kw = {**BASE, **VARIANTS[variant], "n_layer": 5}
+    cfg = Config.from_name("tiny-llama-1.1b", **kw)
+    sd = random_state_dict(cfg, dtype=torch.float32, seed=13, std=0.2)
+    plan = plan_layers(n_nodes, cfg.n_layer, cfg, policy="table")
+    chunks, _ = split_parameters({k: v.clone() for k, v in sd.items()}, n_nodes, plan=plan)
+    parts = [chunks["starter"]] + list(chunks["secondary"])
+    torch.save({k: v for k, v in cfg.asdict().items() if k not in ("pos_embedding", "tie_embeddings")}, tmp_path / "cfg.pt")
+    torch.save(parts, tmp_path / "chunks.pt")
+    out = tmp_path / "stages.pt"
+    r = subprocess.run([sys.executable, str(ROOT / "tests" / "helpers" / "ref_stages.py"), str(REF), str(ROOT / "baseline" / "shims"),
+                        str(tmp_path / "cfg.pt"), str(tmp_path / "chunks.pt"), str(out)], capture_output=True, text=True, timeout=300,
+                       cwd=tmp_path, env=dict(os.environ, PYTHONPATH=""))
+    assert r.returncode == 0, r.stderr[-2000:]
+    ref = torch.load(out)
+    stages = []
+    for i, (n, ch) in enumerate(zip(plan, parts)):
+        st = build_stage(cfg, "starter" if i == 0 else f"secondary:{i - 1}", n)
+        st.load_state_dict(ch)
+        stages.append(st.eval())
+    idx = torch.tensor([[5, 17, 3, 44, 42, 7]])
+    with torch.no_grad():
+        x = stages[0](idx)
+        torch.testing.assert_close(x, ref["hidden"][0], rtol=1e-4, atol=1e-5)
+        for st, theirs in zip(stages[1:], ref["hidden"][1:]):
+            x = st(x)
+            torch.testing.assert_close(x, theirs, rtol=1e-4, atol=1e-5)
+        torch.testing.assert_close(stages[0].head(x), ref["logits"], rtol=1e-4, atol=1e-5)
