@@ -193,3 +193,61 @@ def test_our_chunks_run_in_the_reference_stage_classes(tmp_path, variant, n_node
             x = st(x)
             torch.testing.assert_close(x, theirs, rtol=1e-4, atol=1e-5)
         torch.testing.assert_close(stages[0].head(x), ref["logits"], rtol=1e-4, atol=1e-5)
+
+
+def _sp_checkpoint(d):
+    import sentencepiece as spm
+
+    d.mkdir()
+    corpus = ROOT / "mdi_llm_b200" / "data" / "sonnets.txt"
+    spm.SentencePieceTrainer.train(input=str(corpus), model_prefix=str(d / "tokenizer"), vocab_size=300, model_type="bpe",
+                                   bos_id=1, eos_id=2, unk_id=0, pad_id=-1, minloglevel=2)
+    (d / "tokenizer_config.json").write_text('{"add_bos_token": true, "tokenizer_class": "LlamaTokenizer"}')
+    return d
+
+
+def _hf_checkpoint(d):
+    import json
+
+    from tokenizers import Tokenizer as HFTok
+    from tokenizers import models, pre_tokenizers, trainers
+
+    d.mkdir()
+    tk = HFTok(models.BPE(unk_token="<unk>"))
+    tk.pre_tokenizer = pre_tokenizers.ByteLevel(add_prefix_space=False)
+    from tokenizers import decoders
+
+    tk.decoder = decoders.ByteLevel()
+    tr = trainers.BpeTrainer(vocab_size=320, special_tokens=["<unk>", "<s>", "</s>"], initial_alphabet=pre_tokenizers.ByteLevel.alphabet())
+    tk.train([str(ROOT / "mdi_llm_b200" / "data" / "sonnets.txt")], tr)
+    tk.save(str(d / "tokenizer.json"))
+    (d / "tokenizer_config.json").write_text(json.dumps({"bos_token": "<s>", "eos_token": "</s>", "add_bos_token": False}))
+    return d
+
+
+@pytest.mark.parametrize("kind", ["sentencepiece", "huggingface"])
+def test_tokenizer_wrapper_matches_the_reference(tmp_path, kind):
+    """Backend choice, special-token ids, BOS policy, ``max_length`` truncation and decoding of our ``Tokenizer`` against the
+    reference's on the same checkpoint directory (tokenizer.py:12-160)."""
+    import json
+
+    from mdi_llm_b200.text.tokenizer import Tokenizer
+
+    ck = (_sp_checkpoint if kind == "sentencepiece" else _hf_checkpoint)(tmp_path / "ck")
+    out = tmp_path / "tok.json"
+    r = subprocess.run([sys.executable, str(ROOT / "tests" / "helpers" / "ref_tokenizer.py"), str(REF), str(ROOT / "baseline" / "shims"), str(ck),
+                        str(out)], capture_output=True, text=True, timeout=300, cwd=tmp_path, env=dict(os.environ, PYTHONPATH=""))
+    assert r.returncode == 0, r.stderr[-2000:]
+    ref = json.loads(out.read_text())
+    tok = Tokenizer(ck)
+    assert ref["backend"] == kind == tok.backend
+    assert (tok.bos_id, tok.eos_id, tok.use_bos, tok.vocab_size) == (ref["bos_id"], ref["eos_id"], ref["use_bos"], ref["vocab_size"])
+    assert len(ref["cases"]) == 12
+    for c in ref["cases"]:
+        if "error" in c:
+            with pytest.raises(Exception):  # noqa: B017,PT011
+                tok.encode(c["text"], bos=c["bos"], eos=c["eos"], max_length=c["max_length"])
+            continue
+        ids = tok.encode(c["text"], bos=c["bos"], eos=c["eos"], max_length=c["max_length"]).tolist()
+        assert ids == c["ids"], c
+        assert tok.decode(tok.encode(c["text"], bos=False)) == c["decoded"], c
