@@ -251,3 +251,78 @@ def test_tokenizer_wrapper_matches_the_reference(tmp_path, kind):
         ids = tok.encode(c["text"], bos=c["bos"], eos=c["eos"], max_length=c["max_length"]).tolist()
         assert ids == c["ids"], c
         assert tok.decode(tok.encode(c["text"], bos=False)) == c["decoded"], c
+
+
+def _samples(stdout: str):
+    body = stdout.split("Produced output:", 1)[1]
+    return [s.strip() for s in body.split("-------------------------------------------------") if s.strip().startswith("Sample")]
+
+
+def test_our_secondary_serves_the_reference_starter(tmp_path):
+    """Drop-in at node granularity: the UNMODIFIED reference starter (its REST client, its pickle + TCP data plane, its
+    sampler) drives OUR secondary node, and the generated text equals that of an all-reference ring with the same seed."""
+    import json
+    import threading
+    import time
+
+    import yaml
+    from conftest import free_ports
+
+    from mdi_llm_b200.cli import prepare_model, secondary
+    from mdi_llm_b200.utils.checkpoint import write_random_checkpoint
+
+    sys.path.insert(0, str(ROOT / "baseline"))
+    try:
+        from run_reference import _write_tokenizer
+    finally:
+        sys.path.pop(0)
+    cfg = Config.from_name("tiny-llama-1.1b", n_layer=5, n_embd=64, n_head=4, n_query_groups=2, intermediate_size=96, vocab_size=300,
+                           padded_vocab_size=320, block_size=64)
+    ck = write_random_checkpoint(tmp_path / "custom" / "tiny-llama-1.1b", cfg, dtype=torch.float32, seed=21)
+    ref_fields = {k: v for k, v in cfg.asdict().items() if k not in ("pos_embedding", "tie_embeddings")}
+    (ck / "model_config.yaml").write_text(yaml.safe_dump(ref_fields))  # only the fields the reference's Config knows
+    for f in ck.glob("tokenizer*"):
+        f.unlink()
+    _write_tokenizer(ck, cfg.padded_vocab_size)
+    assert prepare_model.main([str(ck), "--n-nodes", "2", "--partition", "table"]) == 0
+
+    def topology():
+        p = free_ports(6)
+        node = lambda i: {"addr": "127.0.0.1", "communication": {"port": p[3 * i], "starter_addr": "127.0.0.1"},  # noqa: E731
+                          "inference": {"port_in": p[3 * i + 1], "port_out": p[3 * i + 2]}, "device": "cpu"}
+        return {"nodes": {"starter": node(0), "secondary": [node(1)]}}
+
+    helper = [sys.executable, str(ROOT / "tests" / "helpers" / "ref_node.py"), str(REF), str(ROOT / "baseline" / "shims")]
+    env = dict(os.environ, PYTHONPATH="")
+    prompt = "t7 t20 t33 t46 t59"
+
+    def run_starter(topo_file):
+        # truncated context (48 of 64): the path on which the reference rebuilds its RoPE tables after loading — with the full
+        # block size they stay meta-device leftovers and its own all-reference ring produces NaN logits
+        r = subprocess.run(helper + ["starter", str(topo_file), str(ck), "2", "6", prompt, "48"], capture_output=True, text=True, timeout=300,
+                           cwd=REF, env=env)
+        assert r.returncode == 0, r.stderr[-3000:]
+        return _samples(r.stdout)
+
+    # A: all-reference ring
+    topo_a = tmp_path / "nodes_a.json"
+    topo_a.write_text(json.dumps(topology()))
+    sec = subprocess.Popen(helper + ["secondary:0", str(topo_a), str(ck)], cwd=REF, env=env, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE)
+    try:
+        time.sleep(1.0)
+        ref_text = run_starter(topo_a)
+        assert sec.wait(timeout=60) == 0
+    finally:
+        if sec.poll() is None:
+            sec.kill()
+    # B: reference starter, OUR secondary
+    topo_b = tmp_path / "nodes_b.json"
+    topo_b.write_text(json.dumps(topology()))
+    t = threading.Thread(target=secondary.main, args=(["--nodes-config", str(topo_b), "0", "--ckpt", str(ck), "--device", "cpu",
+                                                       "--dtype", "float32"],), daemon=True)
+    t.start()
+    time.sleep(1.0)
+    mixed_text = run_starter(topo_b)
+    t.join(timeout=60)
+    assert not t.is_alive()  # the reference's PUT /stop released our node
+    assert len(ref_text) == 2 and mixed_text == ref_text
