@@ -326,3 +326,72 @@ def test_our_secondary_serves_the_reference_starter(tmp_path):
     t.join(timeout=60)
     assert not t.is_alive()  # the reference's PUT /stop released our node
     assert len(ref_text) == 2 and mixed_text == ref_text
+
+
+def test_our_starter_drives_the_reference_secondary(tmp_path, capsys):
+    """The other direction: OUR starter (REST client, init message, socket data plane, sampler) with the UNMODIFIED
+    reference secondary as its worker generates the same tokens as an all-ours ring (greedy)."""
+    import json
+    import threading
+    import time
+
+    import yaml
+    from conftest import free_ports
+
+    import mdi_llm_b200.cli.common as common
+    import mdi_llm_b200.cli.starter as starter_mod
+    from mdi_llm_b200.cli import prepare_model, secondary, starter
+    from mdi_llm_b200.utils.checkpoint import write_random_checkpoint
+
+    sys.path.insert(0, str(ROOT / "baseline"))
+    try:
+        from run_reference import _write_tokenizer
+    finally:
+        sys.path.pop(0)
+    cfg = Config.from_name("tiny-llama-1.1b", n_layer=5, n_embd=64, n_head=4, n_query_groups=2, intermediate_size=96, vocab_size=300,
+                           padded_vocab_size=320, block_size=64)
+    ck = write_random_checkpoint(tmp_path / "custom" / "tiny-llama-1.1b", cfg, dtype=torch.float32, seed=22)
+    (ck / "model_config.yaml").write_text(yaml.safe_dump({k: v for k, v in cfg.asdict().items() if k not in ("pos_embedding", "tie_embeddings")}))
+    for f in ck.glob("tokenizer*"):
+        f.unlink()
+    _write_tokenizer(ck, cfg.padded_vocab_size)
+    assert prepare_model.main([str(ck), "--n-nodes", "2", "--partition", "table"]) == 0
+    for mod in (common, starter_mod):
+        mod.LOGS_DIR = tmp_path / "logs"
+    starter_mod.IMG_DIR = tmp_path / "img"
+
+    def topology():
+        p = free_ports(6)
+        node = lambda i: {"addr": "127.0.0.1", "communication": {"port": p[3 * i], "starter_addr": "127.0.0.1"},  # noqa: E731
+                          "inference": {"port_in": p[3 * i + 1], "port_out": p[3 * i + 2]}, "device": "cpu"}
+        return {"nodes": {"starter": node(0), "secondary": [node(1)]}}
+
+    def run_ours(topo_file):
+        capsys.readouterr()
+        rc = starter.main(["--ckpt", str(ck), "--nodes-config", str(topo_file), "--n-samples", "2", "--n-tokens", "6", "--prompt",
+                           "t7 t20 t33 t46 t59", "--device", "cpu", "--dtype", "float32", "--greedy", "--sequence-length", "48"])
+        assert rc == 0
+        return _samples(capsys.readouterr().out)
+
+    # A: all ours
+    topo_a = tmp_path / "nodes_a.json"
+    topo_a.write_text(json.dumps(topology()))
+    t = threading.Thread(target=secondary.main, args=(["--nodes-config", str(topo_a), "0", "--ckpt", str(ck), "--device", "cpu", "--dtype",
+                                                       "float32"],), daemon=True)
+    t.start()
+    ours = run_ours(topo_a)
+    t.join(timeout=60)
+    # B: our starter, the reference's secondary
+    topo_b = tmp_path / "nodes_b.json"
+    topo_b.write_text(json.dumps(topology()))
+    helper = [sys.executable, str(ROOT / "tests" / "helpers" / "ref_node.py"), str(REF), str(ROOT / "baseline" / "shims")]
+    sec = subprocess.Popen(helper + ["secondary:0", str(topo_b), str(ck)], cwd=REF, env=dict(os.environ, PYTHONPATH=""),
+                           stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True)
+    try:
+        time.sleep(1.0)
+        mixed = run_ours(topo_b)
+        assert sec.wait(timeout=60) == 0, sec.stderr.read()[-2000:]
+    finally:
+        if sec.poll() is None:
+            sec.kill()
+    assert len(ours) == 2 and mixed == ours
