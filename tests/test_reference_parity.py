@@ -395,3 +395,38 @@ def test_our_starter_drives_the_reference_secondary(tmp_path, capsys):
         if sec.poll() is None:
             sec.kill()
     assert len(ours) == 2 and mixed == ours
+
+
+def test_stop_sequences_and_prompt_lists_behave_like_the_reference(tmp_path):
+    """`find_eot` / `detect_stop_tokens` on 300 generated cases and `get_user_prompt` for a literal prompt and a ``FILE:``
+    argument with fewer / more paragraphs than samples (utils.py:185-225, prompts.py:392-447)."""
+    import json
+
+    from mdi_llm_b200.text.prompts import NoPrompt, PromptStyle, get_user_prompt
+    from mdi_llm_b200.utils.misc import detect_stop_tokens, find_eot
+
+    pf = tmp_path / "prompts.txt"
+    pf.write_text("First paragraph,\nstill the first.\n\nSecond paragraph.\n\n\nThird one here.\n")
+    out = tmp_path / "misc.json"
+    r = subprocess.run([sys.executable, str(ROOT / "tests" / "helpers" / "ref_misc.py"), str(REF), str(ROOT / "baseline" / "shims"), str(pf),
+                        str(out)], capture_output=True, text=True, timeout=300, cwd=tmp_path, env=dict(os.environ, PYTHONPATH=""))
+    assert r.returncode == 0, r.stderr[-2000:]
+    ref = json.loads(out.read_text())
+    for c in ref["cases"]:
+        t = torch.tensor([c["tokens"]])
+        stops = tuple(c["stops"])
+        assert detect_stop_tokens(t, stops) == c["detect"], c
+        if isinstance(c["find_eot"], str):
+            with pytest.raises(Exception):  # noqa: B017,PT011
+                find_eot(t, stops, c["prompt_length"])
+        else:
+            assert find_eot(t, stops, c["prompt_length"]).view(-1).tolist() == c["find_eot"], c
+    for key, theirs in ref["prompts"].items():
+        arg_key, style_name = key.split("/")
+        arg, n = {"literal": ("Once upon a time", 3), "file_fewer": (f"FILE:{pf}", 2), "file_more": (f"FILE:{pf}", 5)}[arg_key]
+        style = NoPrompt() if style_name == "none" else PromptStyle.from_name("alpaca")
+        if isinstance(theirs, str):
+            with pytest.raises(Exception):  # noqa: B017,PT011
+                get_user_prompt(arg, n, style)
+        else:
+            assert get_user_prompt(arg, n, style) == theirs, key
