@@ -258,17 +258,10 @@ def _samples(stdout: str):
     return [s.strip() for s in body.split("-------------------------------------------------") if s.strip().startswith("Sample")]
 
 
-def test_our_secondary_serves_the_reference_starter(tmp_path):
-    """Drop-in at node granularity: the UNMODIFIED reference starter (its REST client, its pickle + TCP data plane, its
-    sampler) drives OUR secondary node, and the generated text equals that of an all-reference ring with the same seed."""
-    import json
-    import threading
-    import time
-
+def _interop_checkpoint(tmp_path, n_nodes, seed):
     import yaml
-    from conftest import free_ports
 
-    from mdi_llm_b200.cli import prepare_model, secondary
+    from mdi_llm_b200.cli import prepare_model
     from mdi_llm_b200.utils.checkpoint import write_random_checkpoint
 
     sys.path.insert(0, str(ROOT / "baseline"))
@@ -278,54 +271,76 @@ def test_our_secondary_serves_the_reference_starter(tmp_path):
         sys.path.pop(0)
     cfg = Config.from_name("tiny-llama-1.1b", n_layer=5, n_embd=64, n_head=4, n_query_groups=2, intermediate_size=96, vocab_size=300,
                            padded_vocab_size=320, block_size=64)
-    ck = write_random_checkpoint(tmp_path / "custom" / "tiny-llama-1.1b", cfg, dtype=torch.float32, seed=21)
+    ck = write_random_checkpoint(tmp_path / "custom" / "tiny-llama-1.1b", cfg, dtype=torch.float32, seed=seed)
     ref_fields = {k: v for k, v in cfg.asdict().items() if k not in ("pos_embedding", "tie_embeddings")}
     (ck / "model_config.yaml").write_text(yaml.safe_dump(ref_fields))  # only the fields the reference's Config knows
     for f in ck.glob("tokenizer*"):
         f.unlink()
     _write_tokenizer(ck, cfg.padded_vocab_size)
-    assert prepare_model.main([str(ck), "--n-nodes", "2", "--partition", "table"]) == 0
+    assert prepare_model.main([str(ck), "--n-nodes", str(n_nodes), "--partition", "table"]) == 0
+    return ck
 
-    def topology():
-        p = free_ports(6)
-        node = lambda i: {"addr": "127.0.0.1", "communication": {"port": p[3 * i], "starter_addr": "127.0.0.1"},  # noqa: E731
-                          "inference": {"port_in": p[3 * i + 1], "port_out": p[3 * i + 2]}, "device": "cpu"}
-        return {"nodes": {"starter": node(0), "secondary": [node(1)]}}
 
+def _topology(n_nodes):
+    from conftest import free_ports
+
+    p = free_ports(3 * n_nodes)
+    node = lambda i: {"addr": "127.0.0.1", "communication": {"port": p[3 * i], "starter_addr": "127.0.0.1"},  # noqa: E731
+                      "inference": {"port_in": p[3 * i + 1], "port_out": p[3 * i + 2]}, "device": "cpu"}
+    return {"nodes": {"starter": node(0), "secondary": [node(i) for i in range(1, n_nodes)]}}
+
+
+@pytest.mark.parametrize("secondaries", [("ours",), ("ours", "ref"), ("ref", "ours")])
+def test_our_secondary_serves_the_reference_starter(tmp_path, secondaries):
+    """Drop-in at node granularity: the UNMODIFIED reference starter (its REST client, its pickle + TCP data plane, its
+    sampler) drives rings in which one secondary is OURS — alone, feeding a reference secondary, or fed by one — and the
+    generated text equals that of an all-reference ring with the same seed."""
+    import json
+    import threading
+    import time
+
+    from mdi_llm_b200.cli import secondary
+
+    n_nodes = 1 + len(secondaries)
+    ck = _interop_checkpoint(tmp_path, n_nodes, seed=21)
     helper = [sys.executable, str(ROOT / "tests" / "helpers" / "ref_node.py"), str(REF), str(ROOT / "baseline" / "shims")]
     env = dict(os.environ, PYTHONPATH="")
     prompt = "t7 t20 t33 t46 t59"
 
-    def run_starter(topo_file):
-        # truncated context (48 of 64): the path on which the reference rebuilds its RoPE tables after loading — with the full
-        # block size they stay meta-device leftovers and its own all-reference ring produces NaN logits
-        r = subprocess.run(helper + ["starter", str(topo_file), str(ck), "2", "6", prompt, "48"], capture_output=True, text=True, timeout=300,
-                           cwd=REF, env=env)
-        assert r.returncode == 0, r.stderr[-3000:]
+    def run_ring(who, tag):
+        topo_file = tmp_path / f"nodes_{tag}.json"
+        topo_file.write_text(json.dumps(_topology(n_nodes)))
+        procs, threads = [], []
+        for i, kind in enumerate(who):
+            if kind == "ref":
+                procs.append(subprocess.Popen(helper + [f"secondary:{i}", str(topo_file), str(ck)], cwd=REF, env=env,
+                                              stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True))
+            else:
+                t = threading.Thread(target=secondary.main, args=(["--nodes-config", str(topo_file), str(i), "--ckpt", str(ck), "--device",
+                                                                   "cpu", "--dtype", "float32"],), daemon=True)
+                t.start()
+                threads.append(t)
+        try:
+            time.sleep(1.0)
+            # truncated context (48 of 64): the path on which the reference rebuilds its RoPE tables after loading — with the
+            # full block size they stay meta-device leftovers and its own all-reference ring produces NaN logits
+            r = subprocess.run(helper + ["starter", str(topo_file), str(ck), str(n_nodes), "6", prompt, "48"], capture_output=True, text=True,
+                               timeout=300, cwd=REF, env=env)
+            assert r.returncode == 0, r.stderr[-3000:]
+            for pr in procs:
+                assert pr.wait(timeout=60) == 0, pr.stderr.read()[-2000:]
+            for t in threads:
+                t.join(timeout=60)
+                assert not t.is_alive()  # the reference's PUT /stop released our node
+        finally:
+            for pr in procs:
+                if pr.poll() is None:
+                    pr.kill()
         return _samples(r.stdout)
 
-    # A: all-reference ring
-    topo_a = tmp_path / "nodes_a.json"
-    topo_a.write_text(json.dumps(topology()))
-    sec = subprocess.Popen(helper + ["secondary:0", str(topo_a), str(ck)], cwd=REF, env=env, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE)
-    try:
-        time.sleep(1.0)
-        ref_text = run_starter(topo_a)
-        assert sec.wait(timeout=60) == 0
-    finally:
-        if sec.poll() is None:
-            sec.kill()
-    # B: reference starter, OUR secondary
-    topo_b = tmp_path / "nodes_b.json"
-    topo_b.write_text(json.dumps(topology()))
-    t = threading.Thread(target=secondary.main, args=(["--nodes-config", str(topo_b), "0", "--ckpt", str(ck), "--device", "cpu",
-                                                       "--dtype", "float32"],), daemon=True)
-    t.start()
-    time.sleep(1.0)
-    mixed_text = run_starter(topo_b)
-    t.join(timeout=60)
-    assert not t.is_alive()  # the reference's PUT /stop released our node
-    assert len(ref_text) == 2 and mixed_text == ref_text
+    ref_text = run_ring(("ref",) * len(secondaries), "a")
+    mixed_text = run_ring(secondaries, "b")
+    assert len(ref_text) == n_nodes and mixed_text == ref_text
 
 
 def test_our_starter_drives_the_reference_secondary(tmp_path, capsys):
