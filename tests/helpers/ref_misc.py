@@ -36,4 +36,20 @@ for key, (arg, n) in {"literal": ("Once upon a time", 3), "file_fewer": (f"FILE:
             prompts[f"{key}/{style_name}"] = get_user_prompt(arg, n, style)
         except Exception as e:  # noqa: BLE001
             prompts[f"{key}/{style_name}"] = f"ERR {type(e).__name__}"
-json.dump({"cases": cases, "prompts": prompts}, open(out_file, "w"))
+# training helpers: learning-rate schedule and random batch extraction (same RNG consumption -> same batches)
+lrs = [utils.get_lr(it, lr=3e-4, min_lr=3e-5, warmup_it=10, lr_decay_it=90) for it in range(0, 120, 3)]
+dl = importlib.import_module("sub.utils.data_loader")
+
+
+class _Conf:
+    block_size = 8
+
+
+data = torch.arange(1000) % 97
+torch.manual_seed(5)
+batches = []
+for _ in range(3):
+    x, y = dl.get_batch(data, 4, "cpu", _Conf())
+    batches.append([x.tolist(), y.tolist()])
+tr, va = dl.split_dataset(data, 0.9)
+json.dump({"cases": cases, "prompts": prompts, "lrs": lrs, "batches": batches, "split": [len(tr), len(va)]}, open(out_file, "w"))

@@ -436,6 +436,20 @@ def test_stop_sequences_and_prompt_lists_behave_like_the_reference(tmp_path):
                 find_eot(t, stops, c["prompt_length"])
         else:
             assert find_eot(t, stops, c["prompt_length"]).view(-1).tolist() == c["find_eot"], c
+    # trainer helpers: schedule and batch extraction
+    import types
+
+    from mdi_llm_b200.utils.data_loader import get_batch, split_dataset
+    from mdi_llm_b200.utils.misc import get_lr
+
+    assert [get_lr(it, lr=3e-4, min_lr=3e-5, warmup_it=10, lr_decay_it=90) for it in range(0, 120, 3)] == pytest.approx(ref["lrs"], rel=1e-12)
+    data = torch.arange(1000) % 97
+    torch.manual_seed(5)
+    for xr, yr in ref["batches"]:
+        x, y = get_batch(data, 4, "cpu", types.SimpleNamespace(block_size=8))
+        assert x.tolist() == xr and y.tolist() == yr
+    tr, va = split_dataset(data, 0.9)
+    assert [len(tr), len(va)] == ref["split"]
     for key, theirs in ref["prompts"].items():
         arg_key, style_name = key.split("/")
         arg, n = {"literal": ("Once upon a time", 3), "file_fewer": (f"FILE:{pf}", 2), "file_more": (f"FILE:{pf}", 5)}[arg_key]
