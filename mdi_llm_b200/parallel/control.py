@@ -18,6 +18,7 @@ secondary hands the CUDA-IPC handles of its hop buffers back to the starter at `
 """
 from __future__ import annotations
 
+import hmac
 import json
 import os
 import pickle
@@ -75,13 +76,24 @@ class ControlServer:
                 pass
 
             def _dispatch(self, verb: str) -> None:
-                length = int(self.headers.get("Content-Length") or 0)
-                body = self.rfile.read(length) if length else b""
                 path = tuple(p for p in self.path.split("?")[0].split("/") if p)
                 status, payload, ctype = 200, b"", "text/plain"
+                unread = False  # the request body was not consumed: this connection cannot be reused
                 try:
-                    if outer.token is not None and self.headers.get(TOKEN_HEADER) != outer.token:
+                    # authenticate BEFORE reading the body (an init message may be GBs: a stranger must not make the node
+                    # buffer one), in constant time
+                    if outer.token is not None and not hmac.compare_digest((self.headers.get(TOKEN_HEADER) or "").encode("utf-8"),
+                                                                           outer.token.encode("utf-8")):
+                        unread = True
                         raise HTTPError(401, "bad or missing cluster token")
+                    try:
+                        length = int(self.headers.get("Content-Length") or 0)
+                    except ValueError:
+                        length = -1
+                    if length < 0:
+                        unread = True
+                        raise HTTPError(400, "bad Content-Length")
+                    body = self.rfile.read(length) if length else b""
                     fn = getattr(outer.app, verb, None)
                     if fn is None:
                         raise HTTPError(501, f"{verb} not implemented!")
@@ -99,6 +111,9 @@ class ControlServer:
                 self.send_response(status)
                 self.send_header("Content-Type", ctype)
                 self.send_header("Content-Length", str(len(payload)))
+                if unread:
+                    self.send_header("Connection", "close")
+                    self.close_connection = True
                 self.end_headers()
                 if payload:
                     self.wfile.write(payload)

@@ -15,6 +15,7 @@ import torch
 
 from conftest import free_ports
 from mdi_llm_b200.models.config import Config
+from mdi_llm_b200.parallel.control import TOKEN_HEADER as TOKEN_HEADER_NAME
 from mdi_llm_b200.parallel.control import ControlServer, HTTPError, call_node, request_to_node
 from mdi_llm_b200.utils.safe_pickle import UnsafePayload, safe_loads
 
@@ -320,3 +321,60 @@ def test_ring_session_validates_the_sample_count():
         with pytest.raises(StopIteration):  # the fake stops right after the checks
             GPTServer.open_ring_session(fake, 2, "x", 4)
     assert any("will not be efficient" in str(x.message) for x in w)
+
+
+def test_control_server_survives_malformed_and_unauthenticated_requests():
+    """Hardening of the per-node endpoint: the token is checked before a body is read (a stranger cannot make a node buffer
+    gigabytes), garbage on the wire never takes the server down, and a well-formed request is served afterwards."""
+    import http.client
+    import socket
+
+    class App:
+        def __init__(self):
+            self.bodies = []
+
+        def GET(self, path, body):
+            return json.dumps({"ok": True})
+
+        def POST(self, path, body):
+            self.bodies.append(len(body))
+            return {"n": len(body)}
+
+    (port,) = free_ports(1)
+    app = App()
+    server = ControlServer(app, "127.0.0.1", port, token="s3cret")
+    server.start()
+    try:
+        # 1. no token, 1 GB announced, nothing sent: answered at once with 401, the body is never awaited
+        with socket.create_connection(("127.0.0.1", port), timeout=5) as s:
+            s.sendall(b"POST /init HTTP/1.1\r\nHost: x\r\nContent-Length: 1073741824\r\n\r\n")
+            s.settimeout(5)
+            reply = s.recv(4096)
+        assert reply.startswith(b"HTTP/1.1 401") and b"Connection: close" in reply and app.bodies == []
+        # 2. malformed lengths, unknown verbs, binary noise
+        for raw in (b"POST /init HTTP/1.1\r\nHost: x\r\nX-MDI-Token: s3cret\r\nContent-Length: minus-one\r\n\r\n",
+                    b"POST /init HTTP/1.1\r\nHost: x\r\nX-MDI-Token: s3cret\r\nContent-Length: -5\r\n\r\n",
+                    b"BREW /coffee HTTP/1.1\r\nHost: x\r\n\r\n", b"\x00\xff\xfe garbage \r\n\r\n", b"GET\r\n\r\n"):
+            with socket.create_connection(("127.0.0.1", port), timeout=5) as s:
+                s.sendall(raw)
+                s.settimeout(5)
+                try:
+                    reply = s.recv(4096)
+                except (socket.timeout, ConnectionError):
+                    reply = b""
+            assert not reply.startswith(b"HTTP/1.1 200"), raw
+        # 3. wrong token of the right length, then a pickle that is not a plain message
+        conn = http.client.HTTPConnection("127.0.0.1", port, timeout=5)
+        conn.request("POST", "/init", body=b"x" * 10, headers={TOKEN_HEADER_NAME: "s3creT"})
+        assert conn.getresponse().status == 401
+        conn.close()
+        # 4. the server is still healthy
+        status, body = call_node("post", f"http://127.0.0.1:{port}/init", {"hello": 1}, token="s3cret", max_n_requests=1)
+        assert status == 200 and body["n"] > 0 and len(app.bodies) == 1
+        conn = http.client.HTTPConnection("127.0.0.1", port, timeout=5)
+        conn.request("GET", "/", headers={TOKEN_HEADER_NAME: "s3cret"})
+        resp = conn.getresponse()
+        assert resp.status == 200 and json.loads(resp.read()) == {"ok": True}
+        conn.close()
+    finally:
+        server.stop()
