@@ -6,7 +6,9 @@ left-aligned ASCII decimal length, then ``pickle.dumps(message)``.  A node liste
 next node's ``port_in`` (``connections.py:120-153,288-320``); RX and TX run on their own threads
 feeding :class:`MessageQueue` objects.
 
-Differences from the reference, all behavioural fixes: the ``running`` flag is per connection
+Differences from the reference, all behavioural fixes: frames are DECODED with the restricted unpickler
+(``utils/safe_pickle.py`` — the reference's ``pickle.loads`` on a TCP port is remote code execution for whoever can
+reach it); the ``running`` flag is per connection
 (theirs is a class attribute shared by both directions, connections.py:23); ``accept`` has a
 time-out; tensors are moved to CPU before pickling so the receiver never needs the sender's
 device; queue waits do not poll.
@@ -22,6 +24,7 @@ from typing import Any, Dict, Optional
 import torch
 
 from ...config import HEADERLENGTH
+from ...utils.safe_pickle import safe_loads
 from .base import ChaosPolicy, Message, MessageQueue, Transport
 
 __all__ = ["InputNodeConnection", "OutputNodeConnection", "SocketTransport", "encode_frame", "read_exact"]
@@ -109,8 +112,9 @@ class InputNodeConnection(NodeConnection):
                 conn, peer = self.listener.accept()
             except socket.timeout:
                 raise ConnectionError("Timed out waiting for the previous node to connect") from None
-            if expected is None or peer[0] == expected or expected in ("localhost", "0.0.0.0"):
-                self.conn = conn
+            if (expected is None or peer[0] == expected or expected == "0.0.0.0"
+                    or (expected in ("localhost", "::1") and (peer[0].startswith("127.") or peer[0] == "::1"))):
+                self.conn = conn  # ("localhost" means a loopback peer, not "anybody")
             else:
                 conn.close()
                 if time.time() > deadline:
@@ -138,8 +142,8 @@ class InputNodeConnection(NodeConnection):
             if len(payload) < size:
                 break
             try:
-                msg = pickle.loads(payload)
-            except (EOFError, pickle.UnpicklingError):
+                msg = safe_loads(payload)  # containers, scalars, strings and tensors only: a frame cannot run code here
+            except (EOFError, pickle.UnpicklingError, ValueError, TypeError, AttributeError, IndexError, ImportError):
                 continue
             self.n_received += 1
             self.bytes_received += HEADERLENGTH + size

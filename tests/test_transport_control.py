@@ -114,3 +114,44 @@ def test_torch_distributed_transport_ring_gloo(world):
     assert lines, p.stderr[-2000:]
     res = json.loads(lines[-1][len("TR_RESULT "):])
     assert res["ok"] and res["bytes_sent"] > 0 and p.returncode == 0
+
+
+def test_hostile_frame_on_the_data_port_runs_nothing(tmp_path):
+    """A frame whose pickle would execute code (the reference's `pickle.loads` on a TCP port) is dropped by the restricted
+    unpickler; the stream goes on with the next well-formed message.  A peer that is not loopback is refused when the
+    topology says the previous node is `localhost`."""
+    import os
+    import pickle
+    import socket
+
+    (p_in,) = free_ports(1)
+    rx_cfg = {"addr": "127.0.0.1", "inference": {"port_in": p_in, "port_out": 0}}
+    q_in = MessageQueue()
+    holder = {}
+    t = threading.Thread(target=lambda: holder.setdefault("rx", InputNodeConnection(rx_cfg, {"addr": "localhost"}, q_in)))
+    t.start()
+    marker = tmp_path / "pwned"
+
+    class Evil:
+        def __reduce__(self):
+            return os.system, (f"touch {marker}",)
+
+    s = None
+    for _ in range(50):
+        try:
+            s = socket.create_connection(("127.0.0.1", p_in), timeout=5)
+            break
+        except OSError:
+            time.sleep(0.1)
+    assert s is not None
+    t.join(timeout=5)
+    rx = holder["rx"]
+    rx.launch()
+    bad = pickle.dumps({"sample_index": 0, "data": Evil(), "stop": False})
+    s.sendall(f"{len(bad):<16}".encode() + bad)
+    s.sendall(encode_frame(build_msg(torch.ones(1, 1, 4), 3)))
+    got = q_in.get(timeout=3)
+    assert got["sample_index"] == 3 and float(got["data"].sum()) == 4.0
+    assert not marker.exists() and rx.n_received == 1
+    s.close()
+    rx.shutdown()
