@@ -236,3 +236,54 @@ def test_trained_bpe_and_char_tokenizers_roundtrip(corpus, probe, merges):
     ch = CharacterTokenizer()
     ch.tokenize(corpus + probe)
     assert ch.decode(ch.encode(probe)) == probe
+
+
+class _ScriptedPipe:
+    """Stands in for a one-stage DevicePipeline in host-fed mode: hands out a scripted token per decode round."""
+
+    def __init__(self, script):
+        self.script, self.i = list(script), 0
+
+    def prepare(self, prompts, max_new):
+        self.i = 0
+
+    def prefill(self):
+        pass
+
+    def decode_rounds_host(self, n, on_token=None):
+        for _ in range(n):
+            if self.i < len(self.script):
+                on_token(0, self.i, self.script[self.i])
+                self.i += 1
+        return n, 0, 0
+
+
+def _litgpt_chat_oracle(produced, stops):
+    """The buffering rule of the reference's ``generate_chat`` (model.py:556-573), transcribed over a finished token list."""
+    out, yield_i, buf = [], 0, max((len(s) for s in stops), default=1)
+    for t in range(1, len(produced) + 1):
+        if any(len(s) <= t and tuple(produced[t - len(s):t]) == tuple(s) for s in stops):
+            return out, t
+        if t - yield_i >= buf:
+            out += produced[yield_i:t]
+            yield_i = t
+    return out + produced[yield_i:], None
+
+
+@FAST
+@given(script=st.lists(st.integers(0, 4), min_size=0, max_size=24), stops=st.lists(st.lists(st.integers(0, 4), min_size=1, max_size=3), max_size=3),
+       budget=st.integers(1, 30))
+def test_chat_stream_follows_the_reference_buffering_rule(script, stops, budget):
+    """`cli/chat.py::stream_device` (the fused-engine twin of `generate_chat`): yields what the reference's rule yields for
+    the same token stream — a prefix of the generated tokens that stops before the token completing a stop sequence."""
+    from mdi_llm_b200.cli.chat import stream_device
+
+    stops_t = tuple(tuple(s) for s in stops)
+    got = list(stream_device(_ScriptedPipe(script), torch.tensor([1, 2, 3]), budget, stops_t))
+    produced = script[:budget]
+    expect, fired = _litgpt_chat_oracle(produced, stops_t)
+    assert got == expect and got == produced[:len(got)]
+    if fired is None:
+        assert got == produced
+    else:
+        assert len(got) < fired  # the completing token is never printed
