@@ -39,8 +39,9 @@ def decode_stream(tokenizer, token_stream: Iterator, out=sys.stdout) -> int:
 
 
 def stream_device(pipe, ids, max_new_tokens: int, stop_tokens) -> Iterator[int]:
-    """``GPT.generate_chat`` on the fused engine: yields generated token ids, withholding a tail long enough to
-    never print part of a stop sequence (model.py:526-573)."""
+    """``GPT.generate_chat`` on the fused engine: yields generated token ids in chunks of the longest stop sequence's
+    length and returns, without the pending chunk, as soon as a stop sequence completes — the reference's buffering rule
+    (model.py:526-573: the completing token is never printed; earlier tokens of the sequence may be)."""
     pipe.prepare([ids.cpu()], max_new_tokens)
     pipe.prefill()
     produced: List[int] = []

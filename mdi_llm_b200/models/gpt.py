@@ -640,8 +640,9 @@ class GPT(nn.Module, RopeMixin):
         stop_tokens: Tuple[List[int], ...] = (),
         slot: int = 0,
     ) -> Iterator[torch.Tensor]:
-        """Streaming generation that withholds a tail long enough to never emit part of a
-        stop sequence (model.py:526-573).  Yields token tensors, prompt excluded."""
+        """Streaming generation with the reference's buffering rule (model.py:526-573): tokens are released in chunks
+        of the longest stop sequence's length, generation ends — dropping the pending chunk — when a stop sequence
+        completes.  Yields token tensors, prompt excluded."""
         T = prompt.size(0)
         if self.max_seq_length < max_returned_tokens - 1:
             raise NotImplementedError(f"max_seq_length {self.max_seq_length} needs to be >= {max_returned_tokens - 1}")
