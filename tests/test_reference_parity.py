@@ -464,3 +464,36 @@ def test_stop_sequences_and_prompt_lists_behave_like_the_reference(tmp_path):
                 get_user_prompt(arg, n, style)
         else:
             assert get_user_prompt(arg, n, style) == theirs, key
+
+
+OLD_GPT2 = Path("/root/reference/old/GPT2/sub")
+
+
+@pytest.mark.skipif(not (OLD_GPT2 / "model.py").is_file(), reason="the reference's old/ tree is not available")
+def test_first_generation_gpt2_weights_run_identically(tmp_path):
+    """the GPT-2 generation of the reference (learned positions, LayerNorm, tied head, exact GELU).  Its own
+    model's weights — nanoGPT naming, brought to the HF GPT-2 layout (Conv1D = transposed linears) — go through our HF
+    import rules into our model class and give the same logits as its own forward."""
+    from mdi_llm_b200.utils.convert_hf_checkpoint import convert_state_dict
+
+    out = tmp_path / "old.pt"
+    r = subprocess.run([sys.executable, str(ROOT / "tests" / "helpers" / "old_gpt2_logits.py"), str(OLD_GPT2), str(out)], capture_output=True,
+                       text=True, timeout=300, cwd=tmp_path, env=dict(os.environ, PYTHONPATH=""))
+    assert r.returncode == 0, r.stderr[-2000:]
+    ref = torch.load(out)
+    hf = {}
+    for k, v in ref["sd"].items():
+        if k.endswith(".attn.bias") or k.endswith(".attn.masked_bias"):
+            continue  # causal-mask buffers
+        transposed = k.endswith((".attn.c_attn.weight", ".attn.c_proj.weight", ".mlp.c_fc.weight", ".mlp.c_proj.weight"))
+        hf[k] = v.t().contiguous() if transposed else v  # HF stores these as Conv1D: [in, out]
+    cfg = Config.from_name("gpt2", n_layer=2, n_head=4, n_embd=64, block_size=32, vocab_size=128, padded_vocab_size=128,
+                           gelu_approximate="none")
+    lit = convert_state_dict(hf, cfg)
+    m = GPT(cfg)
+    m.load_state_dict(lit, strict=False)
+    m.eval()
+    idx = torch.tensor([[5, 17, 3, 88, 42, 7]])
+    with torch.no_grad():
+        ours = m(idx)
+    torch.testing.assert_close(ours, ref["logits"], rtol=1e-4, atol=1e-5)
