@@ -466,18 +466,19 @@ def test_stop_sequences_and_prompt_lists_behave_like_the_reference(tmp_path):
             assert get_user_prompt(arg, n, style) == theirs, key
 
 
-OLD_GPT2 = Path("/root/reference/old/GPT2/sub")
+OLD = Path("/root/reference/old")
 
 
-@pytest.mark.skipif(not (OLD_GPT2 / "model.py").is_file(), reason="the reference's old/ tree is not available")
-def test_first_generation_gpt2_weights_run_identically(tmp_path):
+@pytest.mark.skipif(not (OLD / "GPT2" / "sub" / "model.py").is_file(), reason="the reference's old/ tree is not available")
+@pytest.mark.parametrize("tree", ["GPT2"])  # (old/nanoGPT is the lecture-style toy: per-head linears, ReLU feed-forward — another layout)
+def test_first_generation_gpt2_weights_run_identically(tmp_path, tree):
     """the GPT-2 generation of the reference (learned positions, LayerNorm, tied head, exact GELU).  Its own
     model's weights — nanoGPT naming, brought to the HF GPT-2 layout (Conv1D = transposed linears) — go through our HF
     import rules into our model class and give the same logits as its own forward."""
     from mdi_llm_b200.utils.convert_hf_checkpoint import convert_state_dict
 
     out = tmp_path / "old.pt"
-    r = subprocess.run([sys.executable, str(ROOT / "tests" / "helpers" / "old_gpt2_logits.py"), str(OLD_GPT2), str(out)], capture_output=True,
+    r = subprocess.run([sys.executable, str(ROOT / "tests" / "helpers" / "old_gpt2_logits.py"), str(OLD / tree / "sub"), str(out)], capture_output=True,
                        text=True, timeout=300, cwd=tmp_path, env=dict(os.environ, PYTHONPATH=""))
     assert r.returncode == 0, r.stderr[-2000:]
     ref = torch.load(out)
