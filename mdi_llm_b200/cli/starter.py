@@ -47,6 +47,10 @@ def build_parser() -> argparse.ArgumentParser:
                    help="GPT-2 generation protocol: no KV caches, the whole context travels the ring every step")
     p.add_argument("--head-on", default="starter", choices=["starter", "finisher"],
                    help="'finisher': first-generation chain, the last node owns ln_f + lm_head and returns logits")
+    p.add_argument("--push-chunks", action="store_true",
+                   help="after splitting the model on the fly, send every secondary its chunk inside POST /init (the reference's "
+                        "behaviour) instead of expecting it to read the chunk file; a secondary that answers that it has no "
+                        "parameters gets its chunk this way in any case")
     p.add_argument("--partition", default="auto", choices=["auto", "table", "balanced", "half", "third"],
                    help="layer partition policy (half / third: boundaries may fall between a layer's attention, gate/up and down passes)")
     p.add_argument("--top-p", type=float, default=None, help="nucleus sampling threshold")
@@ -86,7 +90,7 @@ def main(argv=None) -> int:
     gpt_distr = GPTDistributed(
         node_type="starter", config_file=args.nodes_config, ckpt_dir=args.ckpt, chunk_path=args.chunk,
         device=args.device, dtype=args.dtype, model_seq_length=args.sequence_length, verb=args.verb, plots=args.plots,
-        compile=args.compile, engine=args.engine, sampling=sampling, partition=args.partition,
+        compile=args.compile, engine=args.engine, sampling=sampling, partition=args.partition, push_chunks=args.push_chunks,
         use_kv_cache=not args.no_kv_cache, head_on=args.head_on, transport=args.transport, weights=args.weights,
         decode_mode=args.decode_mode, random_init=args.random_init, max_prompt_len=args.max_prompt_len,
         watchdog_s=args.watchdog)

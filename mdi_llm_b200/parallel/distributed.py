@@ -133,8 +133,9 @@ class GPTDistributed:
                 chunk_path=self.chunk_path, tokenizer_dir=self.ckpt_dir, model_device=self.torch_device,
                 dtype=dtype, model_type=self.full_model_name, model_seq_length=self.model_seq_length, **kwargs)
         elif "secondary" in self.node_type:
-            assert self.ckpt_dir or self.chunk_path, \
-                "Need to specify at least 1 between the chunk path and the checkpoint directory"
+            # (the reference insists on a chunk path or a checkpoint directory here and notes in a FIXME that a secondary
+            #  could be model-agnostic, model_dist.py:281-286: with neither, this node simply waits for a POST /init that
+            #  carries the model config and the chunk itself)
             split_type = self.node_type.split(":")
             self.secondary_index = secondary_index if len(split_type) < 2 else int(split_type[1])
             assert self.secondary_index is not None
@@ -255,6 +256,15 @@ class GPTDistributed:
                                            map_location="cpu", weights_only=True)
             addr = f"http://{sec['addr']}:{sec['communication']['port']}/init"
             status, body = call_node("post", addr, msg, verb=self.verb, timeout=3600.0)
+            chunk_file = self.node_chunks_dir / f"model_secondary{i}.pth"
+            if status == 400 and "params" not in msg and "model parameters" in str(body) and chunk_file.is_file():
+                # a model-agnostic secondary (started without --ckpt / --chunk, or on a host that does not see this file
+                # system): ship its chunk inside the init message, as the reference does after splitting on the fly
+                # (model_dist.py:454-463)
+                if self.verb:
+                    print(f"Node secondary:{i} has no chunk of its own: sending {chunk_file.name} with the init message")
+                msg["params"] = torch.load(chunk_file, map_location="cpu", weights_only=True)
+                status, body = call_node("post", addr, msg, verb=self.verb, timeout=3600.0)
             if status != 200:
                 print(f"Node secondary:{i} refused initialisation ({status}): {body}")
                 return 0

@@ -18,5 +18,6 @@ if role == "starter":
                           model_seq_length=int(sys.argv[9]) if len(sys.argv) > 9 else None)
     node.start(n_samples=n_samples, tokens_per_sample=n_tokens, prompt=prompt)
 else:
-    node = GPTDistributed(role, topo_file, ckpt_dir=ckpt_dir, device="cpu", dtype="float32", verb=False)
+    # "-" = no checkpoint on this node's disk: it is model-agnostic until POST /init brings config and chunk
+    node = GPTDistributed(role, topo_file, ckpt_dir=None if ckpt_dir == "-" else ckpt_dir, device="cpu", dtype="float32", verb=False)
     node.start()  # blocks until the starter's PUT /stop

@@ -348,7 +348,8 @@ def test_our_secondary_serves_the_reference_starter(tmp_path, secondaries):
     assert len(ref_text) == n_nodes and mixed_text == ref_text
 
 
-def test_our_starter_drives_the_reference_secondary(tmp_path, capsys):
+@pytest.mark.parametrize("chunk_travels", [False, True])
+def test_our_starter_drives_the_reference_secondary(tmp_path, capsys, chunk_travels):
     """The other direction: OUR starter (REST client, init message, socket data plane, sampler) with the UNMODIFIED
     reference secondary as its worker generates the same tokens as an all-ours ring (greedy)."""
     import json
@@ -375,7 +376,8 @@ def test_our_starter_drives_the_reference_secondary(tmp_path, capsys):
     for f in ck.glob("tokenizer*"):
         f.unlink()
     _write_tokenizer(ck, cfg.padded_vocab_size)
-    assert prepare_model.main([str(ck), "--n-nodes", "2", "--partition", "table"]) == 0
+    if not chunk_travels:  # else: no chunk files anywhere — our starter splits on the fly and ships the chunk inside POST /init
+        assert prepare_model.main([str(ck), "--n-nodes", "2", "--partition", "table"]) == 0
     for mod in (common, starter_mod):
         mod.LOGS_DIR = tmp_path / "logs"
     starter_mod.IMG_DIR = tmp_path / "img"
@@ -389,15 +391,16 @@ def test_our_starter_drives_the_reference_secondary(tmp_path, capsys):
     def run_ours(topo_file):
         capsys.readouterr()
         rc = starter.main(["--ckpt", str(ck), "--nodes-config", str(topo_file), "--n-samples", "2", "--n-tokens", "6", "--prompt",
-                           "t7 t20 t33 t46 t59", "--device", "cpu", "--dtype", "float32", "--greedy", "--sequence-length", "48"])
+                           "t7 t20 t33 t46 t59", "--device", "cpu", "--dtype", "float32", "--greedy", "--sequence-length", "48",
+                           "--partition", "table"])
         assert rc == 0
         return _samples(capsys.readouterr().out)
 
     # A: all ours
     topo_a = tmp_path / "nodes_a.json"
     topo_a.write_text(json.dumps(topology()))
-    t = threading.Thread(target=secondary.main, args=(["--nodes-config", str(topo_a), "0", "--ckpt", str(ck), "--device", "cpu", "--dtype",
-                                                       "float32"],), daemon=True)
+    t = threading.Thread(target=secondary.main, args=(["--nodes-config", str(topo_a), "0", "--device", "cpu", "--dtype", "float32"]
+                                                      + ([] if chunk_travels else ["--ckpt", str(ck)]),), daemon=True)
     t.start()
     ours = run_ours(topo_a)
     t.join(timeout=60)
@@ -405,6 +408,8 @@ def test_our_starter_drives_the_reference_secondary(tmp_path, capsys):
     topo_b = tmp_path / "nodes_b.json"
     topo_b.write_text(json.dumps(topology()))
     helper = [sys.executable, str(ROOT / "tests" / "helpers" / "ref_node.py"), str(REF), str(ROOT / "baseline" / "shims")]
+    # (the reference's secondary insists on a checkpoint directory even when the chunk arrives with POST /init: it gets the
+    #  directory — which holds no chunk files in the `chunk_travels` case)
     sec = subprocess.Popen(helper + ["secondary:0", str(topo_b), str(ck)], cwd=REF, env=dict(os.environ, PYTHONPATH=""),
                            stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True)
     try:
