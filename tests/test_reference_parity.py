@@ -293,8 +293,8 @@ def _topology(n_nodes):
     return {"nodes": {"starter": node(0), "secondary": [node(i) for i in range(1, n_nodes)]}}
 
 
-@pytest.mark.parametrize("secondaries", [("ours",), ("ours", "ref"), ("ref", "ours")])
-def test_our_secondary_serves_the_reference_starter(tmp_path, secondaries):
+@pytest.mark.parametrize("secondaries,n_samples", [(("ours",), 2), (("ours", "ref"), 3), (("ref", "ours"), 3), (("ours",), 5), (("ours", "ref"), 1)])
+def test_our_secondary_serves_the_reference_starter(tmp_path, secondaries, n_samples):
     """Drop-in at node granularity: the UNMODIFIED reference starter (its REST client, its pickle + TCP data plane, its
     sampler) drives rings in which one secondary is OURS — alone, feeding a reference secondary, or fed by one — and the
     generated text equals that of an all-reference ring with the same seed."""
@@ -327,7 +327,7 @@ def test_our_secondary_serves_the_reference_starter(tmp_path, secondaries):
             time.sleep(1.0)
             # truncated context (48 of 64): the path on which the reference rebuilds its RoPE tables after loading — with the
             # full block size they stay meta-device leftovers and its own all-reference ring produces NaN logits
-            r = subprocess.run(helper + ["starter", str(topo_file), str(ck), str(n_nodes), "6", prompt, "48"], capture_output=True, text=True,
+            r = subprocess.run(helper + ["starter", str(topo_file), str(ck), str(n_samples), "6", prompt, "48"], capture_output=True, text=True,
                                timeout=300, cwd=REF, env=env)
             assert r.returncode == 0, r.stderr[-3000:]
             for pr in procs:
@@ -341,11 +341,12 @@ def test_our_secondary_serves_the_reference_starter(tmp_path, secondaries):
                     pr.kill()
         return _samples(r.stdout)
 
-    if n_nodes not in _ALL_REFERENCE_TEXT:  # same seed, same checkpoint contents: one all-reference run per ring size
-        _ALL_REFERENCE_TEXT[n_nodes] = run_ring(("ref",) * len(secondaries), "a")
-    ref_text = _ALL_REFERENCE_TEXT[n_nodes]
+    key = (n_nodes, n_samples)
+    if key not in _ALL_REFERENCE_TEXT:  # same seed, same checkpoint contents: one all-reference run per ring size / sample count
+        _ALL_REFERENCE_TEXT[key] = run_ring(("ref",) * len(secondaries), "a")
+    ref_text = _ALL_REFERENCE_TEXT[key]
     mixed_text = run_ring(secondaries, "b")
-    assert len(ref_text) == n_nodes and mixed_text == ref_text
+    assert len(ref_text) == n_samples and mixed_text == ref_text  # also with more samples than nodes, and fewer
 
 
 @pytest.mark.parametrize("chunk_travels", [False, True])
