@@ -52,4 +52,15 @@ for _ in range(3):
     x, y = dl.get_batch(data, 4, "cpu", _Conf())
     batches.append([x.tolist(), y.tolist()])
 tr, va = dl.split_dataset(data, 0.9)
-json.dump({"cases": cases, "prompts": prompts, "lrs": lrs, "batches": batches, "split": [len(tr), len(va)]}, open(out_file, "w"))
+# the sampler: same logits + same RNG state -> same token (top-k crop, temperature, top-p, one multinomial draw)
+from sub.model import sample  # noqa: E402
+
+g = torch.Generator().manual_seed(99)
+draws = []
+for i in range(40):
+    logits = torch.randn(1, 3, 50, generator=g) * 3
+    kw = [dict(temperature=0.8, top_k=20), dict(temperature=1.0, top_k=None), dict(temperature=0.0, top_k=5, top_p=0.0),
+          dict(temperature=0.7, top_k=200, top_p=0.9)][i % 4]
+    torch.manual_seed(1000 + i)
+    draws.append(int(sample(logits, **kw)))
+json.dump({"cases": cases, "prompts": prompts, "lrs": lrs, "batches": batches, "split": [len(tr), len(va)], "draws": draws}, open(out_file, "w"))

@@ -461,6 +461,16 @@ def test_stop_sequences_and_prompt_lists_behave_like_the_reference(tmp_path):
         assert x.tolist() == xr and y.tolist() == yr
     tr, va = split_dataset(data, 0.9)
     assert [len(tr), len(va)] == ref["split"]
+    # sampler (model.py:67-90): same logits and RNG state -> same draw
+    from mdi_llm_b200.models.gpt import sample
+
+    g = torch.Generator().manual_seed(99)
+    for i, theirs in enumerate(ref["draws"]):
+        logits = torch.randn(1, 3, 50, generator=g) * 3
+        kw = [dict(temperature=0.8, top_k=20), dict(temperature=1.0, top_k=None), dict(temperature=0.0, top_k=5, top_p=0.0),
+              dict(temperature=0.7, top_k=200, top_p=0.9)][i % 4]
+        torch.manual_seed(1000 + i)
+        assert int(sample(logits, **kw)) == theirs, (i, kw)
     for key, theirs in ref["prompts"].items():
         arg_key, style_name = key.split("/")
         arg, n = {"literal": ("Once upon a time", 3), "file_fewer": (f"FILE:{pf}", 2), "file_more": (f"FILE:{pf}", 5)}[arg_key]
