@@ -293,7 +293,7 @@ def _topology(n_nodes):
     return {"nodes": {"starter": node(0), "secondary": [node(i) for i in range(1, n_nodes)]}}
 
 
-@pytest.mark.parametrize("secondaries,n_samples", [(("ours",), 2), (("ours", "ref"), 3), (("ref", "ours"), 3), (("ours",), 5), (("ours", "ref"), 1)])
+@pytest.mark.parametrize("secondaries,n_samples", [(("ours",), 5), (("ours", "ref"), 3), (("ref", "ours"), 3), (("ours",), 1)])
 def test_our_secondary_serves_the_reference_starter(tmp_path, secondaries, n_samples):
     """Drop-in at node granularity: the UNMODIFIED reference starter (its REST client, its pickle + TCP data plane, its
     sampler) drives rings in which one secondary is OURS — alone, feeding a reference secondary, or fed by one — and the
